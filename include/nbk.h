@@ -1,0 +1,160 @@
+/* include/nbk.h -- the drop-in boundary: a plain C ABI over the B200 kd-tree hot path.
+ *
+ * The reference (pelahi/NBodylib) has no FFI layer: consumers include <KDTree.h> and link the C++
+ * class NBody::KDTree (reference src/KDTree/KDTree.h:81-657).  This header is what a binding for that
+ * class binds instead: every entry point below names the reference interface it replaces.  The
+ * header-only C++ class in nbodylib_b200/shim/ (same class / method names as the reference) is a thin
+ * marshalling layer over these calls; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - all functions return NBK_OK (0) or a negative nbk_status; nbk_last_error() gives the text
+ *     (the reference printf()s and exit()s instead: KDCalcSmoothQuantities.cxx:205-208).
+ *   - "tree index" = position of a particle in tree order (the reference permutes the caller's array
+ *     into that order, KDTree.cxx:328-370); "ID" = position in the caller's input order
+ *     (KDTree.cxx:1291).  nbk_get_order() returns ID-at-tree-index so a caller can permute its array.
+ *   - pointers are HOST memory unless the call is given NBK_DEVICE_PTRS, in which case every in/out
+ *     array of that call is device memory on the tree's GPU (no copies; used for the resident-data
+ *     benchmark and by callers that already hold particles on the GPU).
+ *   - there is no CPU fallback anywhere: without a CUDA device nbk_create fails with NBK_ERR_CUDA.
+ */
+#ifndef NBK_H
+#define NBK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nbk_tree nbk_tree;
+
+typedef enum {
+    NBK_OK = 0,
+    NBK_ERR_ARG = -1,          /* bad argument (tree type, k, NULL pointer ...)                        */
+    NBK_ERR_CUDA = -2,         /* CUDA runtime error / no device                                       */
+    NBK_ERR_UNSUPPORTED = -3,  /* valid reference call with no device implementation (no CPU fallback) */
+    NBK_ERR_NOMEM = -4,
+    NBK_ERR_CAPACITY = -5      /* caller-provided output buffer too small (required size reported)     */
+} nbk_status;
+
+/* reference KDTree.h:90  TPHYS=0,TPROJ=1,TVEL=2,TPHS=3,TMETRIC=4 */
+enum { NBK_TPHYS = 0, NBK_TPROJ = 1, NBK_TVEL = 2, NBK_TPHS = 3, NBK_TMETRIC = 4 };
+/* reference KDTree.h:97  KSPH=0,KGAUSS=1,KEPAN=2,KTH=3 */
+enum { NBK_KSPH = 0, NBK_KGAUSS = 1, NBK_KEPAN = 2, NBK_KTH = 3 };
+/* reference FOFFunc.h:30-55: the FOFcompfunc criteria that exist in-tree */
+enum { NBK_FOF3D = 0, NBK_FOFVEL = 1, NBK_FOF6D = 2 };
+
+/* flags (bitwise or) */
+enum {
+    NBK_DEVICE_PTRS = 1 << 0,   /* in/out arrays of this call are device pointers                              */
+    NBK_TREE_ORDER = 1 << 1,    /* per-particle outputs indexed by tree index instead of by ID                  */
+    NBK_STRICT_PERIODIC = 1 << 2, /* periodic kNN: dimensionally consistent edge/corner image tests instead of
+                                     the reference's (KDSplitNode.cxx:1134-1146)            */
+    NBK_KNN_TREE_FORM = 1 << 3, /* periodic particle kNN: FindNearest(tt) self rule instead of FindNearestPos(tt)
+                                   (KDFindNearest.cxx:247-334, quirk Q3)                                        */
+    NBK_STORE_F64 = 1 << 4,     /* nbk_create: keep coordinates as fp64 in HBM even if fp32 would be exact      */
+    NBK_STORE_F32 = 1 << 5,     /* nbk_create: force fp32 storage (coordinates rounded if not representable)    */
+    NBK_OUT_IDS = 1 << 6        /* neighbour / ball outputs hold particle IDs instead of tree indices           */
+};
+
+/* Strided, layout-agnostic description of the caller's particles (reference Particle.h:264-354; in the
+ * default build sizeof(Particle)=88 with mass@0, position@8, velocity@32, id@60, rho@72).
+ * pos/vel point at the first particle's x / vx: three consecutive reals; *_stride in bytes. */
+typedef struct {
+    const void* pos;  int64_t pos_stride;
+    const void* vel;  int64_t vel_stride;    /* may be NULL: velocities 0 (TVEL/TPHS/veldensity/6D FOF need it)  */
+    const void* mass; int64_t mass_stride;   /* may be NULL: unit masses (reference NOMASS build)                */
+    int32_t real_bytes;                      /* 8 = double (reference default), 4 = float                        */
+    int32_t on_device;                       /* 0: host memory, 1: device memory                                  */
+} nbk_particles;
+
+typedef struct {
+    int64_t n;
+    int32_t bucket, treetype, kerntype, kernres, nd;
+    int32_t num_nodes, num_leaves, depth;    /* KDTree::GetNumNodes/GetNumLeafNodes (KDTree.h:282-283)             */
+    int32_t store_bytes;                     /* 4 or 8: coordinate storage chosen                                  */
+    int32_t periodic;
+    int64_t inexact_coords;                  /* # input coordinates that fp32 storage had to round (0 => exact)   */
+    double  kernnorm;                        /* KDTree::GetKernNorm (KDTree.h:287)                                 */
+    double  period[3];
+    double  build_ms;                        /* device time of the last build (CUDA events)                        */
+    double  h2d_ms;                          /* host->device staging time of the build                             */
+    double  last_kernel_ms;                  /* device time of the dominant kernel of the last query call          */
+    double  last_call_ms;                    /* device time of the whole last query call (all kernels, no copies)   */
+    int64_t last_launches;                   /* kernels launched by the last call                                   */
+    int64_t device_bytes;                    /* HBM held by the tree                                                */
+} nbk_info;
+
+const char* nbk_last_error(void);
+int nbk_device_count(void);
+
+/* Replaces NBody::KDTree::KDTree(Particle*, numparts, bucket_size, TreeType, KernType, KernRes,
+ * SplittingCriterion, Aniso, ScaleSpace, Period, ...) (reference KDTree.h:229-245, KDTree.cxx:1238-1306).
+ * split must be 0 (KDTREE_SPLIT_SPREAD); period NULL => non periodic.  device < 0 => current device. */
+int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int kerntype, int kernres,
+               int split, const double* period, int flags, int device, nbk_tree** out);
+/* Replaces KDTree::~KDTree (KDTree.cxx:1340-1356); order restoration is the shim's job. */
+int nbk_destroy(nbk_tree* t);
+/* KDTree::GetNumNodes/GetNumLeafNodes/GetKernNorm/GetPeriod ... (KDTree.h:282-289) */
+int nbk_get_info(const nbk_tree* t, nbk_info* info);
+/* ids[i] = ID of the particle at tree index i (what the reference leaves in Particle::id after the
+ * in-place reorder, KDTree.cxx:1291 + :328-370) */
+int nbk_get_order(const nbk_tree* t, int32_t* ids, int flags);
+/* Kernel table of KernelConstruction (KDTree.cxx:1144-1183): table[kernres] */
+int nbk_get_kernel_table(const nbk_tree* t, double* table);
+/* host mirror of the node arrays (KDTree::GetRoot / FindLeafNode consumers, KDTree.h:288,384-386):
+ * per node (heap order, root 0, children 2i+1/2i+2) start,end (tree indices; start<0 => absent),
+ * cut dimension (-1 leaf), bounds[2*nd] (lo0,hi0,lo1,...).  Pass NULL arrays to query *num_slots. */
+int nbk_get_nodes(const nbk_tree* t, int64_t* num_slots, int32_t* start, int32_t* end, int32_t* cutdim, float* bounds);
+
+/* Replaces the per-particle loops over KDTree::FindNearestPos(Int_t tt,...) / FindNearest(Int_t tt,...)
+ * (KDFindNearest.cxx:247-334, whole-system forms :444-459) for tree indices [q0,q1).
+ * nn: (q1-q0) x k tree indices (or IDs with NBK_OUT_IDS), d2: (q1-q0) x k, rows ascending.
+ * Non periodic tree: self and coincident particles excluded (KDLeafNode.cxx:15-28).
+ * Periodic tree: reference image schedule; self at slot 0 unless NBK_KNN_TREE_FORM (quirk Q3). */
+int nbk_knn_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, double* d2, int flags);
+/* Replaces KDTree::FindNearestPos(Double_t *x,...) / (Coordinate x,...) (KDFindNearest.cxx:462-554)
+ * for m query points x[m][3]. */
+int nbk_knn_points(nbk_tree* t, int k, int64_t m, const double* x, int32_t* nn, double* d2, int flags);
+
+/* Replaces KDTree::SearchBallPosTagged(Int_t tt / Double_t* x, fdist2, tagged) (KDFindNearest.cxx:618-688)
+ * for a batch: CSR rows; offsets[m+1]; idx capacity cap; *total = entries required.
+ * Rows hold every particle with d2 < fdist2 (strict; minimum image over the reference's reflections
+ * when periodic).  Particle form (qidx = tree indices): the query itself is excluded when non periodic,
+ * included when periodic (quirk Q5).  Rows are sorted ascending. */
+int nbk_ball_particles(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx, int64_t* offsets,
+                       int32_t* idx, int64_t cap, int64_t* total, int flags);
+int nbk_ball_points(nbk_tree* t, double fdist2, int64_t m, const double* x, int64_t* offsets,
+                    int32_t* idx, int64_t cap, int64_t* total, int flags);
+
+/* Replaces KDTree::CalcDensity(Nsmooth) (KDCalcSmoothQuantities.cxx:203-305).  rho[n] by ID
+ * (or tree index with NBK_TREE_ORDER); hsm (optional) = 0.5*sqrt(d2_k), the smoothing scale. */
+int nbk_calc_density(nbk_tree* t, int nsmooth, double* rho, double* hsm, int flags);
+/* Replaces KDTree::CalcVelDensity(Nsmooth, Nsearch) (KDCalcSmoothQuantities.cxx:309-389). */
+int nbk_calc_veldensity(nbk_tree* t, int nsmooth, int nsearch, double* rho, int flags);
+/* "CalcSmoothingScale" (named by the north star; = hi of KDCalcSmoothQuantities.cxx:260). */
+int nbk_smoothing_scale(nbk_tree* t, int nsmooth, double* hsm, int flags);
+
+/* Optional FOF by-products in tree-index space (reference KDFOF.cxx:52-55: pHead,pNext,pTail,pLen).
+ * Any pointer may be NULL.  head/next/tail have n entries; len has ngroups+1 entries (index = group id). */
+typedef struct { int32_t* head; int32_t* next; int32_t* tail; int32_t* len; } nbk_fof_lists;
+
+/* Replaces KDTree::FOF(fdist, numgroup, minnum, order, pHead,pNext,pTail,pLen, ipcheckflag, check, params)
+ * (KDFOF.cxx:29-153).  On a TPHS tree the link distance is 6D (KDLeafNode.cxx:570-572).
+ * precheck (optional, n entries by ID): non-zero entries are excluded from linking exactly like a
+ * FOFcheckfunc returning non-zero (KDFOF.cxx:65,72); group[n] by ID (or tree index). */
+int nbk_fof(nbk_tree* t, double fdist, int minnum, int order, const int32_t* precheck, int32_t* group,
+            int64_t* ngroups, nbk_fof_lists* lists, int flags);
+/* Replaces KDTree::FOFCriterion(cmp, params, numgroups, minnum, order, ...) (KDFOF.cxx:157-265) for the
+ * in-tree criteria; params laid out as the reference expects (FOFFunc.h:8-15: [0] tree type, [1],[2]
+ * pos/vel pruning length^2, [6],[7] criterion parameters). */
+int nbk_fof_criterion(nbk_tree* t, int criterion, const double* params, int minnum, int order,
+                      const int32_t* precheck, int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags);
+
+/* Device-resident views for callers that stay on the GPU (sharded driver, benchmarks). */
+int nbk_device_arrays(const nbk_tree* t, const void** pos4, const void** vel4, const void** mass, const int32_t** order);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBK_H */

@@ -1,0 +1,91 @@
+"""Loader + ctypes prototypes for libnbk.so (the C ABI of include/nbk.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no fallback:
+if the shared object is missing this module raises, and every entry point needs a CUDA device.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnbk.so")
+
+
+class NbkParticles(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("pos_stride", C.c_int64),
+                ("vel", C.c_void_p), ("vel_stride", C.c_int64),
+                ("mass", C.c_void_p), ("mass_stride", C.c_int64),
+                ("real_bytes", C.c_int32), ("on_device", C.c_int32)]
+
+
+class NbkInfo(C.Structure):
+    _fields_ = [("n", C.c_int64),
+                ("bucket", C.c_int32), ("treetype", C.c_int32), ("kerntype", C.c_int32), ("kernres", C.c_int32), ("nd", C.c_int32),
+                ("num_nodes", C.c_int32), ("num_leaves", C.c_int32), ("depth", C.c_int32),
+                ("store_bytes", C.c_int32), ("periodic", C.c_int32),
+                ("inexact_coords", C.c_int64),
+                ("kernnorm", C.c_double), ("period", C.c_double * 3),
+                ("build_ms", C.c_double), ("h2d_ms", C.c_double), ("last_kernel_ms", C.c_double), ("last_call_ms", C.c_double),
+                ("last_launches", C.c_int64), ("device_bytes", C.c_int64)]
+
+
+class NbkFofLists(C.Structure):
+    _fields_ = [("head", C.c_void_p), ("next", C.c_void_p), ("tail", C.c_void_p), ("len", C.c_void_p)]
+
+
+# flags (include/nbk.h)
+DEVICE_PTRS, TREE_ORDER, STRICT_PERIODIC, KNN_TREE_FORM, STORE_F64, STORE_F32, OUT_IDS = (1 << i for i in range(7))
+
+EXPORTS = [
+    "nbk_last_error", "nbk_device_count", "nbk_create", "nbk_destroy", "nbk_get_info", "nbk_get_order",
+    "nbk_get_kernel_table", "nbk_get_nodes", "nbk_knn_particles", "nbk_knn_points", "nbk_ball_particles",
+    "nbk_ball_points", "nbk_calc_density", "nbk_calc_veldensity", "nbk_smoothing_scale", "nbk_fof",
+    "nbk_fof_criterion", "nbk_device_arrays",
+]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "nbodylib_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    L.nbk_last_error.restype = C.c_char_p
+    L.nbk_device_count.restype = i32
+    L.nbk_create.argtypes = [C.POINTER(NbkParticles), i64, i32, i32, i32, i32, i32, vp, i32, i32, C.POINTER(vp)]
+    L.nbk_destroy.argtypes = [vp]
+    L.nbk_get_info.argtypes = [vp, C.POINTER(NbkInfo)]
+    L.nbk_get_order.argtypes = [vp, vp, i32]
+    L.nbk_get_kernel_table.argtypes = [vp, vp]
+    L.nbk_get_nodes.argtypes = [vp, C.POINTER(i64), vp, vp, vp, vp]
+    L.nbk_knn_particles.argtypes = [vp, i32, i64, i64, vp, vp, i32]
+    L.nbk_knn_points.argtypes = [vp, i32, i64, vp, vp, vp, i32]
+    L.nbk_ball_particles.argtypes = [vp, dbl, i64, vp, vp, vp, i64, C.POINTER(i64), i32]
+    L.nbk_ball_points.argtypes = [vp, dbl, i64, vp, vp, vp, i64, C.POINTER(i64), i32]
+    L.nbk_calc_density.argtypes = [vp, i32, vp, vp, i32]
+    L.nbk_calc_veldensity.argtypes = [vp, i32, i32, vp, i32]
+    L.nbk_smoothing_scale.argtypes = [vp, i32, vp, i32]
+    L.nbk_fof.argtypes = [vp, dbl, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]
+    L.nbk_fof_criterion.argtypes = [vp, i32, vp, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]
+    L.nbk_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    for name in EXPORTS:
+        if name not in ("nbk_last_error", "nbk_device_count"):
+            getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+class NbkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("nbk error %d: %s" % (code, msg))
+        self.code = code
+
+
+def check(rc):
+    if rc != 0:
+        raise NbkError(rc, load().nbk_last_error().decode())

@@ -1,0 +1,615 @@
+// api.cu -- the C ABI of include/nbk.h: argument checking, host<->device staging, call sequencing.
+// No computation happens on the host and nothing here falls back to a CPU path: every entry point either
+// launches the CUDA kernels of build.cu / knn.cu / fof.cu / ball.cu or returns an error.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <thread>
+
+#include "tree.h"
+
+using namespace nbk;
+
+static thread_local std::string g_err;
+
+#define NBK_API_BEGIN try {
+#define NBK_API_END                                                          \
+    }                                                                        \
+    catch (const nbk::Error& e) { g_err = e.what(); return e.code; }         \
+    catch (const std::bad_alloc&) { g_err = "host allocation failed"; return NBK_ERR_NOMEM; } \
+    catch (const std::exception& e) { g_err = e.what(); return NBK_ERR_ARG; } \
+    return NBK_OK;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (dev != prev) NBK_CHECK(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---- staging kernels -----------------------------------------------------------------------------
+// raw strided reals (device visible) -> packed doubles [n][3]
+template <class R>
+__global__ void gather3_kernel(const unsigned char* base, int64_t stride, int64_t n, double* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const R* p = reinterpret_cast<const R*>(base + i * stride);
+    out[3 * i] = (double)p[0]; out[3 * i + 1] = (double)p[1]; out[3 * i + 2] = (double)p[2];
+}
+template <class R>
+__global__ void gather1_kernel(const unsigned char* base, int64_t stride, int64_t n, double* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (double)*reinterpret_cast<const R*>(base + i * stride);
+}
+__global__ void count_inexact_kernel(const double* a, int64_t n3, unsigned long long* cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < n3) { double v = a[i]; bad = ((double)(float)v != v); }
+    unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(cnt, (unsigned long long)__popc(m));
+}
+template <class S>
+__global__ void pack4_kernel(const double* a, int64_t n, Vec4<S>* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Vec4<S> v;
+    v.x = (S)a[3 * i]; v.y = (S)a[3 * i + 1]; v.z = (S)a[3 * i + 2]; v.w = (S)0;
+    out[i] = v;
+}
+__global__ void scatter_f64_kernel(int64_t n, const int32_t* order, const double* src, double* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[order[i]] = src[i];
+}
+__global__ void scatter_i32_kernel(int64_t n, const int32_t* order, const int32_t* src, int32_t* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[order[i]] = src[i];
+}
+__global__ void gather_i32_kernel(int64_t n, const int32_t* order, const int32_t* src, int32_t* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[order[i]];
+}
+
+// Bring n strided triplets (host or device memory) into a packed device double[n][3].
+// Host arrays are packed by a few threads into pinned chunks and copied asynchronously (double buffered).
+void stage3(const void* src, int64_t stride, int real_bytes, bool on_device, int64_t n, int comps, double* d_out, cudaStream_t st) {
+    const int tb = 256;
+    if (on_device) {
+        if (comps == 3) {
+            if (real_bytes == 8) gather3_kernel<double><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)src, stride, n, d_out);
+            else gather3_kernel<float><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)src, stride, n, d_out);
+        } else {
+            if (real_bytes == 8) gather1_kernel<double><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)src, stride, n, d_out);
+            else gather1_kernel<float><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)src, stride, n, d_out);
+        }
+        NBK_CHECK(cudaGetLastError());
+        return;
+    }
+    if (real_bytes == 8 && stride == (int64_t)comps * 8) {   // already packed doubles
+        NBK_CHECK(cudaMemcpyAsync(d_out, src, (size_t)n * comps * 8, cudaMemcpyHostToDevice, st));
+        NBK_CHECK(cudaStreamSynchronize(st));
+        return;
+    }
+    const int64_t chunk = 1 << 22;
+    double* pin[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    for (int b = 0; b < 2; b++) {
+        NBK_CHECK(cudaMallocHost((void**)&pin[b], (size_t)std::min(chunk, n) * comps * 8));
+        NBK_CHECK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    int nth = (int)std::max(1u, std::min(hw ? hw : 4u, 16u));
+    int b = 0;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk, b ^= 1) {
+        int64_t cn = std::min(chunk, n - c0);
+        NBK_CHECK(cudaEventSynchronize(done[b]));
+        auto work = [&](int tid) {
+            int64_t lo = cn * tid / nth, hi = cn * (tid + 1) / nth;
+            const unsigned char* bp = (const unsigned char*)src + (c0 + lo) * stride;
+            double* o = pin[b] + lo * comps;
+            for (int64_t i = lo; i < hi; i++, bp += stride, o += comps) {
+                if (real_bytes == 8) { const double* p = (const double*)bp; for (int k = 0; k < comps; k++) o[k] = p[k]; }
+                else { const float* p = (const float*)bp; for (int k = 0; k < comps; k++) o[k] = (double)p[k]; }
+            }
+        };
+        if (cn < 65536 || nth == 1) { for (int tdx = 0; tdx < nth; tdx++) work(tdx); }
+        else {
+            std::vector<std::thread> th;
+            for (int tdx = 0; tdx < nth; tdx++) th.emplace_back(work, tdx);
+            for (auto& x : th) x.join();
+        }
+        NBK_CHECK(cudaMemcpyAsync(d_out + c0 * comps, pin[b], (size_t)cn * comps * 8, cudaMemcpyHostToDevice, st));
+        NBK_CHECK(cudaEventRecord(done[b], st));
+    }
+    NBK_CHECK(cudaStreamSynchronize(st));
+    for (int q = 0; q < 2; q++) { cudaFreeHost(pin[q]); cudaEventDestroy(done[q]); }
+}
+
+// KernelConstruction, reference KDTree.cxx:1144-1183 + SmoothingKernels.h:32-56
+double kern_w(int type, double r, double h) {
+    if (type == NBK_KSPH) {
+        double rh = r / h;
+        if (rh <= 1.0) return (1.0 - 0.75 * (2.0 - rh) * (rh * rh));
+        else if (rh > 1.0 && rh <= 2.0) return 0.25 * (2.0 - rh) * (2.0 - rh) * (2.0 - rh);
+        return 0;
+    }
+    if (type == NBK_KGAUSS) { double rh = r / h * 2.0; return exp(-0.5 * pow(rh, 2.0)); }
+    if (type == NBK_KEPAN) { double rh = r / h * 0.5; return rh <= 1.0 ? (1.0 - rh * rh) : 0.; }
+    double rh = r / h * 0.5;
+    return (rh <= 1.0);
+}
+void build_kernel_table(nbk_tree& t) {
+    const int ND = t.nd;
+    double kn = 1.0 / ND * pow(M_1_PI, ND / 2.) * tgamma(ND / 2. + 1.);
+    int type = t.kerntype;
+    if (type == NBK_KSPH) kn *= ND * (ND + 1.) * (ND + 2.) * (ND + 3.) / (6 * (pow(2., ND + 1) - 1.));
+    else if (type == NBK_KGAUSS) kn *= pow(0.5 * M_1_PI, ND / 2.);
+    else if (type == NBK_KEPAN) kn *= ND * (ND + 2.) * pow(0.5, ND + 1.);
+    else if (type != NBK_KTH) { type = NBK_KSPH; kn *= ND * (ND + 1.) * (ND + 2.) * (ND + 3.) / (6 * (pow(2., ND + 1) - 1.)); }
+    t.kernnorm = kn;
+    t.h_kernel.resize(t.kernres);
+    double delta = 2.0 / (double)(t.kernres - 1);
+    for (int i = 0; i < t.kernres; i++) t.h_kernel[i] = kn * kern_w(type, i * delta, 1.0);
+    NBK_CHECK(cudaMalloc((void**)&t.d_kernel, sizeof(double) * t.kernres));
+    NBK_CHECK(cudaMemcpy(t.d_kernel, t.h_kernel.data(), sizeof(double) * t.kernres, cudaMemcpyHostToDevice));
+}
+
+struct CallTimer {
+    nbk_tree& t;
+    explicit CallTimer(nbk_tree& tt) : t(tt) { cudaEventRecord(t.ev0, t.stream); }
+    void stop() {
+        cudaEventRecord(t.ev1, t.stream);
+        cudaEventSynchronize(t.ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t.ev0, t.ev1);
+        t.last_call_ms = ms;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* nbk_last_error(void) { return g_err.c_str(); }
+
+int nbk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int kerntype, int kernres, int split,
+               const double* period, int flags, int device, nbk_tree** out) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(out != nullptr && p != nullptr && p->pos != nullptr, NBK_ERR_ARG, "nbk_create: null argument");
+    *out = nullptr;
+    NBK_REQUIRE(n >= 1 && n < ((int64_t)1 << 31) - 64, NBK_ERR_ARG, "nbk_create: particle count must be in [1, 2^31)");
+    NBK_REQUIRE(bucket >= 1 && bucket <= 1024, NBK_ERR_ARG, "nbk_create: bucket size must be in [1,1024]");
+    NBK_REQUIRE(p->real_bytes == 4 || p->real_bytes == 8, NBK_ERR_ARG, "nbk_create: real_bytes must be 4 or 8");
+    // reference TreeTypeCheck (KDTree.cxx:1095-1105) prints and leaves root=NULL; here it is an error code
+    NBK_REQUIRE(treetype >= NBK_TPHYS && treetype <= NBK_TMETRIC, NBK_ERR_ARG, "Error in type of tree specified");
+    NBK_REQUIRE(treetype == NBK_TPHYS || treetype == NBK_TPHS || treetype == NBK_TVEL, NBK_ERR_UNSUPPORTED,
+                "tree types TPROJ / TMETRIC have no device implementation");
+    NBK_REQUIRE(split == 0, NBK_ERR_UNSUPPORTED, "only KDTREE_SPLIT_SPREAD is implemented on the device");
+    NBK_REQUIRE(!(treetype != NBK_TPHYS && p->vel == nullptr), NBK_ERR_ARG, "TVEL / TPHS trees need velocities");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        throw Error(NBK_ERR_CUDA, "no CUDA device: nbk has no CPU fallback");
+    }
+    if (device < 0) NBK_CHECK(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+
+    std::unique_ptr<nbk_tree> t(new nbk_tree);
+    t->device = device;
+    t->n = n; t->bucket = bucket; t->treetype = treetype; t->kerntype = kerntype;
+    if (kernres < 100) kernres = 100;      // KDTree.cxx:1145-1148
+    t->kernres = kernres;
+    t->nd = (treetype == NBK_TPHS) ? 6 : 3;
+    t->periodic = period != nullptr;
+    if (period) for (int d = 0; d < 3; d++) t->period[d] = period[d];
+    NBK_CHECK(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    NBK_CHECK(cudaEventCreate(&t->ev0)); NBK_CHECK(cudaEventCreate(&t->ev1));
+    NBK_CHECK(cudaEventCreate(&t->ev2)); NBK_CHECK(cudaEventCreate(&t->ev3));
+    cudaStream_t st = t->stream;
+    const int tb = 256;
+
+    // ---- stage ------------------------------------------------------------------------------------
+    NBK_CHECK(cudaEventRecord(t->ev0, st));
+    DevBuf<double> rpos((size_t)3 * n), rvel(p->vel ? (size_t)3 * n : 0), rmass(p->mass ? (size_t)n : 0);
+    stage3(p->pos, p->pos_stride, p->real_bytes, p->on_device != 0, n, 3, rpos.p, st);
+    if (p->vel) stage3(p->vel, p->vel_stride, p->real_bytes, p->on_device != 0, n, 3, rvel.p, st);
+    if (p->mass) stage3(p->mass, p->mass_stride, p->real_bytes, p->on_device != 0, n, 1, rmass.p, st);
+    NBK_CHECK(cudaEventRecord(t->ev1, st));
+
+    // ---- storage precision: fp32 when it is exact (or forced), fp64 otherwise ---------------------------
+    int store = 4;
+    if (p->real_bytes == 8) {
+        DevBuf<unsigned long long> cnt(1);
+        NBK_CHECK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), st));
+        count_inexact_kernel<<<div_up(3 * n, tb), tb, 0, st>>>(rpos.p, 3 * n, cnt.p);
+        if (p->vel) count_inexact_kernel<<<div_up(3 * n, tb), tb, 0, st>>>(rvel.p, 3 * n, cnt.p);
+        unsigned long long c = 0;
+        NBK_CHECK(cudaMemcpyAsync(&c, cnt.p, sizeof(c), cudaMemcpyDeviceToHost, st));
+        NBK_CHECK(cudaStreamSynchronize(st));
+        t->inexact = (int64_t)c;
+        if (c > 0) store = 8;
+    }
+    if (flags & NBK_STORE_F64) store = 8;
+    if (flags & NBK_STORE_F32) store = 4;
+    if (store == 8) t->inexact = 0;
+    t->store_bytes = store;
+
+    NBK_CHECK(cudaEventRecord(t->ev2, st));
+    const bool tvel = treetype == NBK_TVEL;
+    const double* prim_raw = tvel ? rvel.p : rpos.p;
+    const double* sec_raw = tvel ? rpos.p : (p->vel ? rvel.p : nullptr);
+    if (store == 4) {
+        DevBuf<Vec4<float>> a(n), b(sec_raw ? n : 0);
+        pack4_kernel<float><<<div_up(n, tb), tb, 0, st>>>(prim_raw, n, a.p);
+        if (sec_raw) pack4_kernel<float><<<div_up(n, tb), tb, 0, st>>>(sec_raw, n, b.p);
+        NBK_CHECK(cudaStreamSynchronize(st));
+        rpos.release(); rvel.release();
+        build_tree<float>(*t, a.p, sec_raw ? b.p : nullptr, p->mass ? rmass.p : nullptr);
+    } else {
+        DevBuf<Vec4<double>> a(n), b(sec_raw ? n : 0);
+        pack4_kernel<double><<<div_up(n, tb), tb, 0, st>>>(prim_raw, n, a.p);
+        if (sec_raw) pack4_kernel<double><<<div_up(n, tb), tb, 0, st>>>(sec_raw, n, b.p);
+        NBK_CHECK(cudaStreamSynchronize(st));
+        rpos.release(); rvel.release();
+        build_tree<double>(*t, a.p, sec_raw ? b.p : nullptr, p->mass ? rmass.p : nullptr);
+    }
+    NBK_CHECK(cudaEventRecord(t->ev3, st));
+    NBK_CHECK(cudaEventSynchronize(t->ev3));
+    float ms = 0;
+    NBK_CHECK(cudaEventElapsedTime(&ms, t->ev0, t->ev1)); t->h2d_ms = ms;
+    NBK_CHECK(cudaEventElapsedTime(&ms, t->ev2, t->ev3)); t->build_ms = ms;
+    build_kernel_table(*t);
+    *out = t.release();
+    NBK_API_END
+}
+
+int nbk_destroy(nbk_tree* t) {
+    NBK_API_BEGIN
+    if (!t) return NBK_OK;
+    DeviceGuard guard(t->device);
+    cudaStreamSynchronize(t->stream);
+    cudaFree(t->prim); cudaFree(t->sec); cudaFree(t->mass); cudaFree(t->order);
+    cudaFree(t->nlo); cudaFree(t->nhi); cudaFree(t->cutdim); cudaFree(t->d_kernel);
+    cudaEventDestroy(t->ev0); cudaEventDestroy(t->ev1); cudaEventDestroy(t->ev2); cudaEventDestroy(t->ev3);
+    cudaStreamDestroy(t->stream);
+    delete t;
+    NBK_API_END
+}
+
+int nbk_get_info(const nbk_tree* t, nbk_info* info) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && info, NBK_ERR_ARG, "nbk_get_info: null argument");
+    memset(info, 0, sizeof(*info));
+    info->n = t->n; info->bucket = t->bucket; info->treetype = t->treetype; info->kerntype = t->kerntype;
+    info->kernres = t->kernres; info->nd = t->nd;
+    info->num_nodes = (int32_t)t->num_nodes; info->num_leaves = (int32_t)t->num_leaves; info->depth = t->depth;
+    info->store_bytes = t->store_bytes; info->periodic = t->periodic ? 1 : 0; info->inexact_coords = t->inexact;
+    info->kernnorm = t->kernnorm;
+    for (int d = 0; d < 3; d++) info->period[d] = t->period[d];
+    info->build_ms = t->build_ms; info->h2d_ms = t->h2d_ms; info->last_kernel_ms = t->last_kernel_ms;
+    info->last_call_ms = t->last_call_ms; info->last_launches = t->last_launches; info->device_bytes = t->device_bytes;
+    NBK_API_END
+}
+
+int nbk_get_order(const nbk_tree* t, int32_t* ids, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && ids, NBK_ERR_ARG, "nbk_get_order: null argument");
+    DeviceGuard guard(t->device);
+    NBK_CHECK(cudaMemcpyAsync(ids, t->order, sizeof(int32_t) * t->n, (flags & NBK_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
+    NBK_CHECK(cudaStreamSynchronize(t->stream));
+    NBK_API_END
+}
+
+int nbk_get_kernel_table(const nbk_tree* t, double* table) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && table, NBK_ERR_ARG, "nbk_get_kernel_table: null argument");
+    memcpy(table, t->h_kernel.data(), sizeof(double) * t->kernres);
+    NBK_API_END
+}
+
+int nbk_get_nodes(const nbk_tree* t, int64_t* num_slots, int32_t* start, int32_t* end, int32_t* cutdim, float* bounds) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && num_slots, NBK_ERR_ARG, "nbk_get_nodes: null argument");
+    *num_slots = t->nslots;
+    if (!start && !end && !cutdim && !bounds) return NBK_OK;
+    DeviceGuard guard(t->device);
+    std::vector<NodeLo> lo(t->nslots);
+    std::vector<NodeHi> hi(t->nslots);
+    std::vector<int8_t> cd(t->nslots);
+    NBK_CHECK(cudaMemcpy(lo.data(), t->nlo, sizeof(NodeLo) * t->nslots, cudaMemcpyDeviceToHost));
+    NBK_CHECK(cudaMemcpy(hi.data(), t->nhi, sizeof(NodeHi) * t->nslots, cudaMemcpyDeviceToHost));
+    NBK_CHECK(cudaMemcpy(cd.data(), t->cutdim, t->nslots, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < t->nslots; i++) {
+        if (start) start[i] = lo[i].start;
+        if (end) end[i] = hi[i].end;
+        if (cutdim) cutdim[i] = cd[i];
+        if (bounds) {
+            bounds[6 * i + 0] = lo[i].x; bounds[6 * i + 1] = hi[i].x; bounds[6 * i + 2] = lo[i].y;
+            bounds[6 * i + 3] = hi[i].y; bounds[6 * i + 4] = lo[i].z; bounds[6 * i + 5] = hi[i].z;
+        }
+    }
+    NBK_API_END
+}
+
+static void require_knn_tree(const nbk_tree* t) {
+    // Q4: TPHS trees with the constructor-default Aniso=0 take the metric path in the reference; no device version.
+    NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TVEL, NBK_ERR_UNSUPPORTED,
+                "kNN / density on a TPHS tree (6D / metric search) has no device implementation");
+}
+
+int nbk_knn_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, double* d2, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t, NBK_ERR_ARG, "nbk_knn_particles: null tree");
+    require_knn_tree(t);
+    NBK_REQUIRE(q0 >= 0 && q1 <= t->n && q0 <= q1, NBK_ERR_ARG, "nbk_knn_particles: bad query range");
+    NBK_REQUIRE(k >= 1, NBK_ERR_ARG, "nbk_knn_particles: k must be >= 1");
+    DeviceGuard guard(t->device);
+    const int64_t rows = q1 - q0;
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    DevBuf<int32_t> dnn;
+    DevBuf<double> dd2;
+    KnnArgs a;
+    a.k = k; a.mode = 0; a.q0 = q0; a.q1 = q1;
+    a.periodic = t->periodic && t->treetype != NBK_TVEL;   // the reference never reflects velocity searches (KDSplitNode.cxx:1082-1085)
+    a.strict = flags & NBK_STRICT_PERIODIC; a.tree_form = flags & NBK_KNN_TREE_FORM; a.out_ids = flags & NBK_OUT_IDS;
+    if (dev) { a.nn = nn; a.d2 = d2; }
+    else {
+        if (nn) { dnn.alloc((size_t)rows * k); a.nn = dnn.p; }
+        if (d2) { dd2.alloc((size_t)rows * k); a.d2 = dd2.p; }
+    }
+    CallTimer tm(*t);
+    launch_knn(*t, a);
+    tm.stop();
+    t->last_kernel_ms = t->last_call_ms; t->last_launches = 1;
+    if (!dev) {
+        if (nn) NBK_CHECK(cudaMemcpyAsync(nn, dnn.p, dnn.bytes(), cudaMemcpyDeviceToHost, t->stream));
+        if (d2) NBK_CHECK(cudaMemcpyAsync(d2, dd2.p, dd2.bytes(), cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+    }
+    NBK_API_END
+}
+
+int nbk_knn_points(nbk_tree* t, int k, int64_t m, const double* x, int32_t* nn, double* d2, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && x, NBK_ERR_ARG, "nbk_knn_points: null argument");
+    require_knn_tree(t);
+    NBK_REQUIRE(k >= 1 && m >= 0, NBK_ERR_ARG, "nbk_knn_points: bad k or m");
+    if (m == 0) return NBK_OK;
+    DeviceGuard guard(t->device);
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    DevBuf<double> dx, dd2;
+    DevBuf<int32_t> dnn;
+    KnnArgs a;
+    a.k = k; a.mode = 1; a.q0 = 0; a.q1 = m;
+    a.periodic = t->periodic && t->treetype != NBK_TVEL;
+    a.strict = flags & NBK_STRICT_PERIODIC; a.out_ids = flags & NBK_OUT_IDS;
+    if (dev) { a.xq = x; a.nn = nn; a.d2 = d2; }
+    else {
+        dx.alloc((size_t)3 * m);
+        NBK_CHECK(cudaMemcpyAsync(dx.p, x, dx.bytes(), cudaMemcpyHostToDevice, t->stream));
+        a.xq = dx.p;
+        if (nn) { dnn.alloc((size_t)m * k); a.nn = dnn.p; }
+        if (d2) { dd2.alloc((size_t)m * k); a.d2 = dd2.p; }
+    }
+    CallTimer tm(*t);
+    launch_knn(*t, a);
+    tm.stop();
+    t->last_kernel_ms = t->last_call_ms; t->last_launches = 1;
+    if (!dev) {
+        if (nn) NBK_CHECK(cudaMemcpyAsync(nn, dnn.p, dnn.bytes(), cudaMemcpyDeviceToHost, t->stream));
+        if (d2) NBK_CHECK(cudaMemcpyAsync(d2, dd2.p, dd2.bytes(), cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+    }
+    NBK_API_END
+}
+
+// per-particle double output: tree-order device buffer -> caller (ID order unless NBK_TREE_ORDER)
+static void deliver_f64(nbk_tree* t, const double* src_tree, double* dst, int flags) {
+    const int64_t n = t->n;
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    if (flags & NBK_TREE_ORDER) {
+        NBK_CHECK(cudaMemcpyAsync(dst, src_tree, sizeof(double) * n, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
+    } else if (dev) {
+        scatter_f64_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, src_tree, dst);
+    } else {
+        DevBuf<double> tmp(n);
+        scatter_f64_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, src_tree, tmp.p);
+        NBK_CHECK(cudaMemcpyAsync(dst, tmp.p, sizeof(double) * n, cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+    }
+    NBK_CHECK(cudaStreamSynchronize(t->stream));
+}
+static void deliver_i32(nbk_tree* t, const int32_t* src_tree, int32_t* dst, int flags) {
+    const int64_t n = t->n;
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    if (flags & NBK_TREE_ORDER) {
+        NBK_CHECK(cudaMemcpyAsync(dst, src_tree, sizeof(int32_t) * n, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
+    } else if (dev) {
+        scatter_i32_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, src_tree, dst);
+    } else {
+        DevBuf<int32_t> tmp(n);
+        scatter_i32_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, src_tree, tmp.p);
+        NBK_CHECK(cudaMemcpyAsync(dst, tmp.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+    }
+    NBK_CHECK(cudaStreamSynchronize(t->stream));
+}
+
+static void smooth_call(nbk_tree* t, int k, int veldens_k, double* rho, double* hsm, int flags) {
+    require_knn_tree(t);
+    NBK_REQUIRE(t->treetype == NBK_TPHYS || veldens_k == 0, NBK_ERR_UNSUPPORTED, "CalcVelDensity needs a physical tree");
+    NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
+    DeviceGuard guard(t->device);
+    const int64_t n = t->n;
+    DevBuf<double> drho(rho ? n : 0), dh(hsm ? n : 0);
+    KnnArgs a;
+    a.k = k; a.mode = 0; a.q0 = 0; a.q1 = n;
+    a.periodic = false;                       // quirk Q2: all Calc* searches ignore the period (KDCalcSmoothQuantities.cxx:227,338)
+    a.rho = rho ? drho.p : nullptr; a.hsm = hsm ? dh.p : nullptr; a.veldens_k = veldens_k;
+    CallTimer tm(*t);
+    if (rho) NBK_CHECK(cudaMemsetAsync(drho.p, 0, drho.bytes(), t->stream));
+    NBK_CHECK(cudaEventRecord(t->ev2, t->stream));
+    launch_knn(*t, a);
+    NBK_CHECK(cudaEventRecord(t->ev3, t->stream));
+    tm.stop();
+    float ms = 0;
+    NBK_CHECK(cudaEventElapsedTime(&ms, t->ev2, t->ev3));
+    t->last_kernel_ms = ms; t->last_launches = 1 + (rho ? 1 : 0);
+    if (rho) deliver_f64(t, drho.p, rho, flags);
+    if (hsm) deliver_f64(t, dh.p, hsm, flags);
+}
+
+int nbk_calc_density(nbk_tree* t, int nsmooth, double* rho, double* hsm, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && rho, NBK_ERR_ARG, "nbk_calc_density: null argument");
+    smooth_call(t, nsmooth, 0, rho, hsm, flags);
+    NBK_API_END
+}
+int nbk_calc_veldensity(nbk_tree* t, int nsmooth, int nsearch, double* rho, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && rho, NBK_ERR_ARG, "nbk_calc_veldensity: null argument");
+    if (nsmooth > nsearch) nsmooth = nsearch;   // KDCalcSmoothQuantities.cxx:319-322
+    NBK_REQUIRE(nsmooth >= 1, NBK_ERR_ARG, "nbk_calc_veldensity: Nsmooth must be >= 1");
+    smooth_call(t, nsearch, nsmooth, rho, nullptr, flags);
+    NBK_API_END
+}
+int nbk_smoothing_scale(nbk_tree* t, int nsmooth, double* hsm, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && hsm, NBK_ERR_ARG, "nbk_smoothing_scale: null argument");
+    smooth_call(t, nsmooth, 0, nullptr, hsm, flags);
+    NBK_API_END
+}
+
+static void fof_call(nbk_tree* t, FofArgs& a, const int32_t* precheck, int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags) {
+    NBK_REQUIRE(group && ngroups, NBK_ERR_ARG, "FOF: null output");
+    NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "FOF needs a TPHYS or TPHS tree");
+    NBK_REQUIRE(!(lists && (lists->head || lists->next || lists->tail)), NBK_ERR_UNSUPPORTED,
+                "FOF pHead/pNext/pTail outputs are not implemented yet (pLen is)");
+    DeviceGuard guard(t->device);
+    const int64_t n = t->n;
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    DevBuf<int32_t> dpre, dpre_tree, dgroup(n), dlen;
+    if (precheck) {
+        const int32_t* src = precheck;
+        if (!dev) {
+            dpre.alloc(n);
+            NBK_CHECK(cudaMemcpyAsync(dpre.p, precheck, sizeof(int32_t) * n, cudaMemcpyHostToDevice, t->stream));
+            src = dpre.p;
+        }
+        if (flags & NBK_TREE_ORDER) a.precheck_tree = src;
+        else {
+            dpre_tree.alloc(n);
+            gather_i32_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, src, dpre_tree.p);
+            a.precheck_tree = dpre_tree.p;
+        }
+    }
+    a.group_tree = dgroup.p;
+    if (lists && lists->len) { dlen.alloc(n + 1); a.len = dlen.p; }
+    CallTimer tm(*t);
+    launch_fof(*t, a);
+    tm.stop();
+    *ngroups = a.ngroups;
+    deliver_i32(t, dgroup.p, group, flags);
+    if (lists && lists->len) {
+        NBK_CHECK(cudaMemcpyAsync(lists->len, dlen.p, sizeof(int32_t) * (a.ngroups + 1), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+    }
+}
+
+int nbk_fof(nbk_tree* t, double fdist, int minnum, int order, const int32_t* precheck, int32_t* group, int64_t* ngroups,
+            nbk_fof_lists* lists, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t, NBK_ERR_ARG, "nbk_fof: null tree");
+    FofArgs a;
+    a.mode = t->treetype == NBK_TPHS ? 1 : 0;
+    a.p0 = fdist * fdist;                       // KDFOF.cxx:33
+    a.prune_x2 = a.p0;
+    a.minnum = minnum; a.order = order;
+    fof_call(t, a, precheck, group, ngroups, lists, flags);
+    NBK_API_END
+}
+
+int nbk_fof_criterion(nbk_tree* t, int criterion, const double* params, int minnum, int order, const int32_t* precheck,
+                      int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && params, NBK_ERR_ARG, "nbk_fof_criterion: null argument");
+    NBK_REQUIRE(criterion == NBK_FOF3D || criterion == NBK_FOF6D, criterion == NBK_FOFVEL ? NBK_ERR_UNSUPPORTED : NBK_ERR_ARG,
+                "nbk_fof_criterion: only FOF3d and FOF6d have device implementations (host FOFcompfunc callbacks cannot run on the GPU)");
+    FofArgs a;
+    a.mode = criterion == NBK_FOF3D ? 2 : 4;
+    a.p0 = params[6]; a.p1 = params[7];
+    // any linked pair has sum(dx^2)/params[6] < 1; the tiny factor covers the rounding of the divided sum
+    a.prune_x2 = params[6] * (1.0 + 1e-12);
+    a.minnum = minnum; a.order = order;
+    fof_call(t, a, precheck, group, ngroups, lists, flags);
+    NBK_API_END
+}
+
+static void ball_call(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx, const double* x, int64_t* offsets, int32_t* idx,
+                      int64_t cap, int64_t* total, int flags) {
+    NBK_REQUIRE(offsets && total, NBK_ERR_ARG, "ball search: null output");
+    NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "SearchBallPos needs positions as tree coordinates");
+    DeviceGuard guard(t->device);
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    DevBuf<int32_t> dq, didx;
+    DevBuf<double> dx;
+    DevBuf<int64_t> doff;
+    BallArgs a;
+    a.r2 = fdist2; a.m = m; a.cap = idx ? cap : 0; a.out_ids = flags & NBK_OUT_IDS;
+    if (dev) { a.qidx = qidx; a.xq = x; a.offsets = offsets; a.idx = idx; }
+    else {
+        if (qidx) { dq.alloc(m); NBK_CHECK(cudaMemcpyAsync(dq.p, qidx, sizeof(int32_t) * m, cudaMemcpyHostToDevice, t->stream)); a.qidx = dq.p; }
+        if (x) { dx.alloc((size_t)3 * m); NBK_CHECK(cudaMemcpyAsync(dx.p, x, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, t->stream)); a.xq = dx.p; }
+        doff.alloc(m + 1); a.offsets = doff.p;
+        if (idx && cap > 0) { didx.alloc(cap); a.idx = didx.p; }
+    }
+    CallTimer tm(*t);
+    launch_ball(*t, a);
+    tm.stop();
+    *total = a.total;
+    if (!dev) {
+        NBK_CHECK(cudaMemcpyAsync(offsets, doff.p, sizeof(int64_t) * (m + 1), cudaMemcpyDeviceToHost, t->stream));
+        if (idx && cap > 0) NBK_CHECK(cudaMemcpyAsync(idx, didx.p, sizeof(int32_t) * std::min(cap, a.total), cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+    }
+    if (idx && a.total > cap) throw Error(NBK_ERR_CAPACITY, "ball search: index buffer too small (see *total)");
+}
+
+int nbk_ball_particles(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx, int64_t* offsets, int32_t* idx, int64_t cap,
+                       int64_t* total, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && (qidx || m == 0), NBK_ERR_ARG, "nbk_ball_particles: null argument");
+    ball_call(t, fdist2, m, qidx, nullptr, offsets, idx, cap, total, flags);
+    NBK_API_END
+}
+int nbk_ball_points(nbk_tree* t, double fdist2, int64_t m, const double* x, int64_t* offsets, int32_t* idx, int64_t cap,
+                    int64_t* total, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && (x || m == 0), NBK_ERR_ARG, "nbk_ball_points: null argument");
+    ball_call(t, fdist2, m, nullptr, x, offsets, idx, cap, total, flags);
+    NBK_API_END
+}
+
+int nbk_device_arrays(const nbk_tree* t, const void** pos4, const void** vel4, const void** mass, const int32_t** order) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t, NBK_ERR_ARG, "nbk_device_arrays: null tree");
+    if (pos4) *pos4 = t->pos4();
+    if (vel4) *vel4 = t->vel4();
+    if (mass) *mass = t->mass;
+    if (order) *order = t->order;
+    NBK_API_END
+}
+
+}  // extern "C"

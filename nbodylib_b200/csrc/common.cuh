@@ -1,0 +1,102 @@
+// common.cuh -- shared helpers for the nbk CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nbk.h"
+
+namespace nbk {
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define NBK_CHECK(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            char _b[512];                                                                            \
+            snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            throw ::nbk::Error(NBK_ERR_CUDA, _b);                                                    \
+        }                                                                                            \
+    } while (0)
+
+#define NBK_REQUIRE(cond, code, msg)                                  \
+    do {                                                              \
+        if (!(cond)) throw ::nbk::Error((code), std::string(msg));    \
+    } while (0)
+
+// RAII device buffer
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) {
+            cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+            if (e != cudaSuccess) {
+                p = nullptr; n = 0;
+                throw Error(NBK_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+            }
+        }
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+    operator T*() const { return p; }
+};
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// 4-wide coordinate records: storage type S is float (16 B) or double (32 B)
+template <class S> struct Vec4;
+template <> struct __align__(16) Vec4<float> { float x, y, z, w; };
+template <> struct __align__(32) Vec4<double> { double x, y, z, w; };
+
+// node record, heap order (root 0, children 2i+1 / 2i+2): tight fp32 bounds rounded outward + range
+struct __align__(16) NodeLo { float x, y, z; int start; };  // start < 0 : node absent
+struct __align__(16) NodeHi { float x, y, z; int end; };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// order preserving bit keys
+__device__ __forceinline__ uint32_t sort_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ uint64_t sort_key(double f) {
+    uint64_t u = (uint64_t)__double_as_longlong(f);
+    return u ^ ((u >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+}
+// outward rounding of storage coordinates to fp32 bounds
+__device__ __forceinline__ float round_down(float v) { return v; }
+__device__ __forceinline__ float round_up(float v) { return v; }
+__device__ __forceinline__ float round_down(double v) { return __double2float_rd(v); }
+__device__ __forceinline__ float round_up(double v) { return __double2float_ru(v); }
+#endif
+
+}  // namespace nbk

@@ -1,0 +1,271 @@
+// fof.cu -- friends-of-friends as lock-free union-find over ball-search links.
+//
+// Replaces the serial breadth-first search of the reference: KDTree::FOF KDFOF.cxx:29-153,
+// KDTree::FOFCriterion :157-265, LeafNode::FOFSearchBall KDLeafNode.cxx:527-590, FOFSearchCriterion :591-619,
+// SplitNode::FOFSearchBall[Periodic] KDSplitNode.cxx:921-988,1602-1681, criteria FOFFunc.h:30-55.
+//
+// The reference's groups are the connected components of the strict '<' link relation;
+// here every particle searches its ball with the shared warp traversal and each link found is merged
+// with atomicCAS hooking (larger root under smaller root, so a component's root is its smallest tree
+// index) and path halving; a second pass flattens, counts, filters by minnum and numbers the groups.
+// The link predicate is evaluated in fp64 with the reference's operation order, so the relation --
+// and therefore the partition -- is bit-identical.
+#include "sort_scan.cuh"
+#include "traverse.cuh"
+#include "tree.h"
+
+namespace nbk {
+
+constexpr int FOF_WARPS = 8;
+
+__device__ __forceinline__ int uf_load(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+__device__ __forceinline__ int uf_find(int* parent, int a) {
+    while (true) {
+        int p = uf_load(parent + a);
+        if (p == a) return a;
+        int gp = uf_load(parent + p);
+        if (gp == p) return p;
+        parent[a] = gp;          // path halving: any ancestor is a valid parent (parents only ever decrease)
+        a = gp;
+    }
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) { int t = a; a = b; b = t; }
+        if (atomicCAS(parent + b, b, a) == b) return;
+    }
+}
+
+struct FofParams {
+    const NodeLo* nlo; const NodeHi* nhi; int bucket;
+    const void* P; const void* V;
+    int64_t n;
+    int mode; double p0, p1; float prune_f;
+    int periodic; double period[3];
+    const int32_t* excl;     // tree order, non-zero => particle takes no part
+    int* parent;
+};
+
+template <class S>
+struct FofVisitor {
+    const Vec4<S>* P; const Vec4<S>* V;
+    double* tile;          // [6][32]
+    int* parent;
+    const int32_t* excl;
+    double qx, qy, qz, vx, vy, vz;
+    double p0, p1;
+    float prune_f;
+    int mode, self;
+    bool on, shifted;
+    unsigned lane;
+
+    __device__ __forceinline__ bool need(float lb) const { return lb < prune_f; }
+    __device__ __forceinline__ bool whole(const QueryBox&, const NodeLo&, const NodeHi&, bool) const { return false; }
+
+    __device__ __forceinline__ bool linked(int j) const {
+        const double cx = tile[j], cy = tile[32 + j], cz = tile[64 + j];
+        if (mode == 0) return dist2_ref(qx, qy, qz, cx, cy, cz) < p0;
+        const double ux = tile[96 + j], uy = tile[128 + j], uz = tile[160 + j];
+        if (mode == 1) {
+            // KDLeafNode.cxx:570-572: dist2 = DistanceSqd(pos); dist2 += DistanceSqd(vel)
+            double d = dist2_ref(qx, qy, qz, cx, cy, cz);
+            d = __dadd_rn(d, dist2_ref(vx, vy, vz, ux, uy, uz));
+            return d < p0;
+        }
+        double dx = __dsub_rn(qx, cx), dy = __dsub_rn(qy, cy), dz = __dsub_rn(qz, cz);
+        if (mode == 2) {
+            // FOF3d, FOFFunc.h:30-35: total += dx*dx/params[6]
+            double t = __ddiv_rn(__dmul_rn(dx, dx), p0);
+            t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dy, dy), p0));
+            t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dz, dz), p0));
+            return t < 1.0;
+        }
+        // FOF6d, FOFFunc.h:48-55: position and velocity terms interleaved per component
+        double wx = __dsub_rn(vx, ux), wy = __dsub_rn(vy, uy), wz = __dsub_rn(vz, uz);
+        double t = __ddiv_rn(__dmul_rn(dx, dx), p0);
+        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wx, wx), p1));
+        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dy, dy), p0));
+        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wy, wy), p1));
+        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dz, dz), p0));
+        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wz, wz), p1));
+        return t < 1.0;
+    }
+
+    __device__ __forceinline__ void leaf(int start, int cnt) {
+        for (int base = 0; base < cnt; base += 32) {
+            int m = min(32, cnt - base);
+            __syncwarp();
+            if ((int)lane < m) {
+                Vec4<S> c = P[start + base + lane];
+                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
+                if (mode == 1 || mode == 4) {
+                    Vec4<S> u = V[start + base + lane];
+                    tile[96 + lane] = (double)u.x; tile[128 + lane] = (double)u.y; tile[160 + lane] = (double)u.z;
+                }
+            }
+            __syncwarp();
+            if (!on) continue;
+            for (int j = 0; j < m; j++) {
+                int c = start + base + j;
+                // the unshifted relation is exactly symmetric, so each pair is merged once (from its lower index)
+                if (shifted ? (c == self) : (c <= self)) continue;
+                if (linked(j)) {
+                    if (excl && excl[c]) continue;
+                    uf_union(parent, self, c);
+                }
+            }
+        }
+    }
+};
+
+template <class S>
+__global__ void __launch_bounds__(FOF_WARPS * 32) fof_link_kernel(FofParams prm) {
+    __shared__ double s_tile[FOF_WARPS][192];
+    __shared__ int s_stack[FOF_WARPS][TRAV_STACK];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    int64_t group = (int64_t)blockIdx.x * FOF_WARPS + w;
+    int64_t qi = group * 32 + lane;
+    if (group * 32 >= prm.n) return;
+    const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
+    const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
+    bool valid = qi < prm.n;
+    if (valid && prm.excl && prm.excl[qi]) valid = false;
+    FofVisitor<S> v;
+    v.P = P; v.V = V; v.tile = s_tile[w]; v.parent = prm.parent; v.excl = prm.excl;
+    v.p0 = prm.p0; v.p1 = prm.p1; v.prune_f = prm.prune_f; v.mode = prm.mode; v.lane = lane;
+    v.self = valid ? (int)qi : -1;
+    v.on = valid; v.shifted = false;
+    double x0 = 0, y0 = 0, z0 = 0;
+    v.vx = v.vy = v.vz = 0;
+    if (valid) {
+        Vec4<S> c = P[qi];
+        x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z;
+        if (prm.mode == 1 || prm.mode == 4) { Vec4<S> u = V[qi]; v.vx = (double)u.x; v.vy = (double)u.y; v.vz = (double)u.z; }
+    }
+    const int nimg = prm.periodic ? 8 : 1;
+    for (int img = 0; img < nimg; img++) {
+        // reflected target positions (DistFunc.h:343-355): +p if x < p/2 else -p.  An image whose ball misses the
+        // root box dies at the first node test, which subsumes the reference's fdist2 > sval*sval tests.
+        v.qx = (img & 1) ? ((x0 < prm.period[0] / 2.0) ? x0 + prm.period[0] : x0 - prm.period[0]) : x0;
+        v.qy = (img & 2) ? ((y0 < prm.period[1] / 2.0) ? y0 + prm.period[1] : y0 - prm.period[1]) : y0;
+        v.qz = (img & 4) ? ((z0 < prm.period[2] / 2.0) ? z0 + prm.period[2] : z0 - prm.period[2]) : z0;
+        v.shifted = img != 0;
+        QueryBox qb = make_qbox(v.qx, v.qy, v.qz);
+        traverse(prm.nlo, prm.nhi, prm.bucket, s_stack[w], v, qb, valid);
+    }
+}
+
+__global__ void fof_init_kernel(int64_t n, int* parent, uint32_t* size) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { parent[i] = (int)i; size[i] = 0; }
+}
+__global__ void fof_flatten_kernel(int64_t n, int* parent, uint32_t* size) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = uf_find(parent, (int)i);
+    atomicAdd(&size[r], 1u);
+}
+// after flatten every chain is short; make parent[i] the root itself
+__global__ void fof_root_kernel(int64_t n, int* parent, const uint32_t* size, int minnum, const int32_t* excl, uint32_t* flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = (int)i;
+    while (true) { int p = parent[r]; if (p == r) break; r = p; }
+    parent[i] = r;   // races only write the same final root
+    bool isroot = (r == (int)i);
+    flag[i] = (isroot && size[i] >= (uint32_t)minnum && !(excl && excl[i])) ? 1u : 0u;
+}
+// flagscan = exclusive scan of flag.  order==0: id = rank in tree order + 1
+__global__ void fof_label_kernel(int64_t n, const int* parent, const uint32_t* flag, const uint32_t* flagscan, const uint32_t* newid, int32_t* group) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = parent[i];
+    int g = 0;
+    if (flag[r]) g = newid ? (int)newid[flagscan[r]] : (int)flagscan[r] + 1;
+    group[i] = g;
+}
+// compact valid roots: keys = ~size (so ascending key == descending size), vals = rank in tree order
+__global__ void fof_compact_kernel(int64_t n, const uint32_t* flag, const uint32_t* flagscan, const uint32_t* size, uint32_t* keys, uint32_t* vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    uint32_t r = flagscan[i];
+    keys[r] = ~size[i];
+    vals[r] = r;
+}
+__global__ void fof_newid_kernel(int64_t ng, const uint32_t* sorted_vals, uint32_t* newid) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ng) newid[sorted_vals[i]] = (uint32_t)i + 1;
+}
+// group lengths pLen[gid] (KDFOF.cxx:74,98-104)
+__global__ void fof_len_kernel(int64_t n, const uint32_t* flag, const uint32_t* flagscan, const uint32_t* newid, const uint32_t* size, int32_t* len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    int g = newid ? (int)newid[flagscan[i]] : (int)flagscan[i] + 1;
+    len[g] = (int)size[i];
+}
+
+void launch_fof(nbk_tree& t, FofArgs& a) {
+    const int64_t n = t.n;
+    cudaStream_t st = t.stream;
+    DevBuf<int> parent(n);
+    DevBuf<uint32_t> size(n), flag(n + 1), flagscan(n + 1), scratch(scan_scratch_elems(n + 1));
+    const int tb = 256;
+    int64_t launches = 0;
+    fof_init_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p);
+    FofParams p;
+    p.nlo = t.nlo; p.nhi = t.nhi; p.bucket = t.bucket;
+    p.P = t.pos4(); p.V = t.vel4(); p.n = n;
+    p.mode = a.mode; p.p0 = a.p0; p.p1 = a.p1;
+    p.prune_f = __builtin_nextafterf((float)a.prune_x2, INFINITY);
+    if ((double)p.prune_f < a.prune_x2) p.prune_f = __builtin_nextafterf(p.prune_f, INFINITY);
+    p.periodic = t.periodic ? 1 : 0;
+    for (int d = 0; d < 3; d++) p.period[d] = t.period[d];
+    p.excl = a.precheck_tree; p.parent = parent.p;
+    if (a.mode == 1 || a.mode == 4) NBK_REQUIRE(p.V != nullptr, NBK_ERR_ARG, "6D FOF needs velocities");
+    int64_t groups = (n + 31) / 32;
+    NBK_CHECK(cudaEventRecord(t.ev2, st));
+    if (t.store_bytes == 4) fof_link_kernel<float><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
+    else fof_link_kernel<double><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
+    NBK_CHECK(cudaEventRecord(t.ev3, st));
+    fof_flatten_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p);
+    fof_root_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p, a.minnum, a.precheck_tree, flag.p);
+    NBK_CHECK(cudaMemsetAsync(flag.p + n, 0, sizeof(uint32_t), st));
+    exclusive_scan_u32(flag.p, flagscan.p, n + 1, scratch.p, st, &launches);
+    uint32_t ng32 = 0;
+    NBK_CHECK(cudaMemcpyAsync(&ng32, flagscan.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    NBK_CHECK(cudaStreamSynchronize(st));
+    a.ngroups = ng32;
+    launches += 5;
+    DevBuf<uint32_t> newid;
+    if (a.order && ng32 > 1) {
+        DevBuf<uint32_t> ka(ng32), kb(ng32), va(ng32), vb(ng32);
+        RadixSortPlan<uint32_t> plan(ng32);
+        DevBuf<uint32_t> temp(plan.temp_u32());
+        newid.alloc(ng32);
+        fof_compact_kernel<<<div_up(n, tb), tb, 0, st>>>(n, flag.p, flagscan.p, size.p, ka.p, va.p);
+        uint32_t *rk, *rv;
+        radix_sort_pairs<uint32_t>(ka.p, va.p, kb.p, vb.p, ng32, 32, false, temp.p, st, &rk, &rv, &launches);
+        fof_newid_kernel<<<div_up(ng32, tb), tb, 0, st>>>(ng32, rv, newid.p);
+        launches += 2;
+        NBK_CHECK(cudaStreamSynchronize(st));
+    }
+    fof_label_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, flag.p, flagscan.p, newid.p, a.group_tree);
+    launches++;
+    if (a.len) {
+        NBK_CHECK(cudaMemsetAsync(a.len, 0, sizeof(int32_t) * (ng32 + 1), st));
+        fof_len_kernel<<<div_up(n, tb), tb, 0, st>>>(n, flag.p, flagscan.p, newid.p, size.p, a.len);
+        launches++;
+    }
+    NBK_CHECK(cudaStreamSynchronize(st));
+    NBK_CHECK(cudaGetLastError());
+    float ms = 0;
+    NBK_CHECK(cudaEventElapsedTime(&ms, t.ev2, t.ev3));
+    t.last_kernel_ms = ms;
+    t.last_launches = launches;
+}
+
+}  // namespace nbk

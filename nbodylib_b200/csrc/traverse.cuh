@@ -1,0 +1,93 @@
+// traverse.cuh -- warp-per-query-bucket traversal shared by kNN, ball search and FOF.
+//
+// One warp owns 32 queries that are adjacent in tree order (spatially compact).  The warp walks the
+// heap-ordered node arrays with ONE shared stack (uniform control flow, one broadcast load per node);
+// every lane tests the node against its own query with a rigorous fp32 LOWER bound of the squared
+// distance to the node box (directed rounding), and the node is opened if any lane needs it.  Leaf
+// particles are staged once per warp into a shared-memory tile (coalesced 16/32-byte loads, widened
+// to fp64) and every lane evaluates the reference's fp64 distance against the broadcast tile.
+//
+// Replaces SplitNode::FindNearestPos / SearchBallPos / FOFSearchBall recursion (reference
+// KDSplitNode.cxx:15-41, 455-690, 921-988) -- pruning there is Arya-Mount incremental offsets; any
+// conservative pruning yields the same result set, so box bounds are used here.
+#pragma once
+#include "common.cuh"
+
+namespace nbk {
+
+constexpr int TRAV_STACK = 64;
+
+// lower bound (rounded toward -inf at every step) of the squared distance from a query known to lie in
+// [qlo,qhi] (component-wise fp32 enclosure of the fp64 query) to the box [lo,hi].
+__device__ __forceinline__ float box_lb(float qlx, float qly, float qlz, float qhx, float qhy, float qhz, const NodeLo& lo, const NodeHi& hi) {
+    float dx = fmaxf(fmaxf(__fsub_rd(lo.x, qhx), __fsub_rd(qlx, hi.x)), 0.f);
+    float dy = fmaxf(fmaxf(__fsub_rd(lo.y, qhy), __fsub_rd(qly, hi.y)), 0.f);
+    float dz = fmaxf(fmaxf(__fsub_rd(lo.z, qhz), __fsub_rd(qlz, hi.z)), 0.f);
+    return __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
+}
+// upper bound (rounded toward +inf) of the squared distance from the query to the farthest box corner
+__device__ __forceinline__ float box_ub(float qlx, float qly, float qlz, float qhx, float qhy, float qhz, const NodeLo& lo, const NodeHi& hi) {
+    float dx = fmaxf(__fsub_ru(qhx, lo.x), __fsub_ru(hi.x, qlx));
+    float dy = fmaxf(__fsub_ru(qhy, lo.y), __fsub_ru(hi.y, qly));
+    float dz = fmaxf(__fsub_ru(qhz, lo.z), __fsub_ru(hi.z, qlz));
+    return __fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz));
+}
+
+// the reference distance: ((dx*dx)+dy*dy)+dz*dz, one rounding per operation (DistFunc.h:14-19)
+__device__ __forceinline__ double dist2_ref(double ax, double ay, double az, double bx, double by, double bz) {
+    double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+struct QueryBox { float lx, ly, lz, hx, hy, hz; };
+__device__ __forceinline__ QueryBox make_qbox(double x, double y, double z) {
+    QueryBox q;
+    q.lx = __double2float_rd(x); q.hx = __double2float_ru(x);
+    q.ly = __double2float_rd(y); q.hy = __double2float_ru(y);
+    q.lz = __double2float_rd(z); q.hz = __double2float_ru(z);
+    return q;
+}
+
+// Visitor interface (all methods called by the full warp):
+//   bool need(float lb)                      per-lane: could this lane accept something at distance^2 >= lb ?
+//   void leaf(int start, int cnt)            process particles [start, start+cnt)
+//   bool whole(q, lo, hi, on)                optional whole-node shortcut; return true (warp-uniform) if the node was consumed
+// ORDERED: always descend left child first so leaves are met in ascending tree-index order.
+template <class V, bool ORDERED = false>
+__device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi, int bucket, int* stack, V& v,
+                                         const QueryBox& q, bool on) {
+    const unsigned lane = lane_id();
+    int sp = 1;
+    if (lane == 0) stack[0] = 0;
+    __syncwarp();
+    while (sp > 0) {
+        int node = stack[--sp];
+        NodeLo lo = nlo[node];
+        NodeHi hi = nhi[node];
+        float lb = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, lo, hi);
+        bool nd = on && v.need(lb);
+        if (!__any_sync(0xffffffffu, nd)) continue;
+        int cnt = hi.end - lo.start;
+        if (v.whole(q, lo, hi, on)) continue;
+        if (cnt <= bucket) { v.leaf(lo.start, cnt); continue; }
+        int c1 = 2 * node + 1, c2 = c1 + 1;
+        NodeLo l1 = nlo[c1]; NodeHi h1 = nhi[c1];
+        NodeLo l2 = nlo[c2]; NodeHi h2 = nhi[c2];
+        float b1 = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, l1, h1);
+        float b2 = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, l2, h2);
+        bool n1 = on && v.need(b1), n2 = on && v.need(b2);
+        unsigned m1 = __ballot_sync(0xffffffffu, n1), m2 = __ballot_sync(0xffffffffu, n2);
+        unsigned p1 = __ballot_sync(0xffffffffu, (n1 || n2) && (b1 <= b2));
+        bool first1 = ORDERED ? true : (2 * __popc(p1) >= __popc(m1 | m2));
+        __syncwarp();
+        if (lane == 0) {
+            int s = sp;
+            if (first1) { if (m2) stack[s++] = c2; if (m1) stack[s++] = c1; }
+            else        { if (m1) stack[s++] = c1; if (m2) stack[s++] = c2; }
+        }
+        sp += (m1 != 0) + (m2 != 0);
+        __syncwarp();
+    }
+}
+
+}  // namespace nbk

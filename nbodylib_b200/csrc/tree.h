@@ -1,0 +1,97 @@
+// tree.h -- the device-resident tree object behind nbk_tree, and the launch entry points each .cu exports.
+#pragma once
+#include "common.cuh"
+
+struct nbk_tree {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+
+    int64_t n = 0;
+    int bucket = 16, treetype = 0, kerntype = 2, kernres = 1000, nd = 3;
+    bool periodic = false;
+    double period[3] = {0, 0, 0};
+    int store_bytes = 4;            // 4: Vec4<float>, 8: Vec4<double>
+    int64_t inexact = 0;
+
+    // tree-order particle arrays (HBM).  prim = coordinates the tree is built on (pos; vel for TVEL),
+    // sec = the other phase-space half (may be null).
+    void* prim = nullptr;
+    void* sec = nullptr;
+    double* mass = nullptr;
+    int32_t* order = nullptr;       // ID at tree index
+
+    // nodes, heap order
+    nbk::NodeLo* nlo = nullptr;
+    nbk::NodeHi* nhi = nullptr;
+    int8_t* cutdim = nullptr;
+    int64_t nslots = 0;
+    int depth = 0;                  // deepest level holding nodes
+    int64_t num_nodes = 0, num_leaves = 0;
+
+    // smoothing kernel table
+    double* d_kernel = nullptr;
+    std::vector<double> h_kernel;
+    double kernnorm = 0;
+
+    // timings
+    double build_ms = 0, h2d_ms = 0, last_kernel_ms = 0, last_call_ms = 0;
+    int64_t last_launches = 0;
+    int64_t device_bytes = 0;
+
+    const void* pos4() const { return treetype == NBK_TVEL ? sec : prim; }
+    const void* vel4() const { return treetype == NBK_TVEL ? prim : sec; }
+};
+
+namespace nbk {
+
+// build.cu : consumes input-order arrays (device), fills t.prim/sec/mass/order/nodes.
+template <class S>
+void build_tree(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* sec_in, const double* mass_in);
+
+// knn.cu
+struct KnnArgs {
+    int k = 0;                 // neighbours wanted
+    int mode = 0;              // 0 particle targets (tree index range), 1 arbitrary points
+    int64_t q0 = 0, q1 = 0;    // particle range (mode 0) or [0,m) (mode 1)
+    const double* xq = nullptr;  // device, m x 3 (mode 1)
+    bool periodic = false;     // run the reference's periodic image schedule
+    bool strict = false;       // NBK_STRICT_PERIODIC
+    bool tree_form = false;    // NBK_KNN_TREE_FORM
+    // outputs (device); any may be null
+    int32_t* nn = nullptr;     // rows x k
+    double* d2 = nullptr;      // rows x k
+    bool out_ids = false;
+    double* rho = nullptr;     // density accumulators, tree order (atomic adds), pre-zeroed
+    double* hsm = nullptr;     // smoothing scale, tree order
+    int veldens_k = 0;         // >0: CalcVelDensity with Nsmooth=veldens_k, Nsearch=k; rho gets the value (no atomics)
+};
+void launch_knn(nbk_tree& t, const KnnArgs& a);
+
+// fof.cu
+struct FofArgs {
+    int mode = 0;              // 0: 3D ball  1: 6D ball (TPHS)  2: FOF3d  3: FOFVel  4: FOF6d  (same codes as oracle)
+    double p0 = 0, p1 = 0;     // mode 0/1: p0 = fdist^2; mode 2/3: p0 = params[6]; mode 4: p0 = params[6], p1 = params[7]
+    double prune_x2 = 0;       // spatial pruning radius^2 (>= any linked pair's position distance^2)
+    int minnum = 8, order = 0;
+    const int32_t* precheck_tree = nullptr;  // device, tree order, may be null
+    int32_t* group_tree = nullptr;           // device out, tree order
+    int64_t ngroups = 0;
+    int32_t *head = nullptr, *next = nullptr, *tail = nullptr, *len = nullptr;  // device, optional
+};
+void launch_fof(nbk_tree& t, FofArgs& a);
+
+// ball.cu
+struct BallArgs {
+    double r2 = 0;
+    int64_t m = 0;
+    const int32_t* qidx = nullptr;  // device, particle form (tree indices) or null
+    const double* xq = nullptr;     // device, point form
+    int64_t* offsets = nullptr;     // device m+1
+    int32_t* idx = nullptr;         // device cap
+    int64_t cap = 0, total = 0;
+    bool out_ids = false;
+};
+void launch_ball(nbk_tree& t, BallArgs& a);
+
+}  // namespace nbk

@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference's ``NBody::KDTree`` interface (reference src/KDTree/KDTree.h:81-657)
+over the C ABI of include/nbk.h.  Method names, argument meaning and index conventions follow the
+reference so that the parity tests read like the reference's own driver (src/tests/test_kdtree.cxx):
+
+* ``FindNearestPos`` returns tree-order indices (KDTree.h:295) unless ``ids=True``;
+* ``CalcDensity`` / ``CalcVelDensity`` / ``FOF`` / ``FOFCriterion`` return arrays indexed by particle ID
+  (= input order, KDTree.h:399,474);
+* periodic trees follow the reference's image schedule including quirk Q1 unless ``strict=True``.
+
+Inputs may be numpy arrays (host, copied) or torch CUDA tensors (device pointers, no copy).
+All computation happens in CUDA kernels; there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+TPHYS, TPROJ, TVEL, TPHS, TMETRIC = 0, 1, 2, 3, 4
+KSPH, KGAUSS, KEPAN, KTH = 0, 1, 2, 3
+FOF3D, FOFVEL, FOF6D = 0, 1, 2
+
+
+def _is_torch(a):
+    return a is not None and type(a).__module__.startswith("torch")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+class KDTree:
+    TPHYS, TPROJ, TVEL, TPHS, TMETRIC = 0, 1, 2, 3, 4
+    KSPH, KGAUSS, KEPAN, KTH = 0, 1, 2, 3
+
+    def __init__(self, pos, vel=None, mass=None, bucket_size=16, TreeType=TPHYS, KernType=KEPAN, KernRes=1000,
+                 SplittingCriterion=0, Period=None, device=-1, flags=0):
+        """Mirror of KDTree(Particle*, numparts, bucket_size, TreeType, KernType, KernRes, SplittingCriterion,
+        Aniso, ScaleSpace, Period) (KDTree.h:229-245) with the particle array given as pos/vel/mass columns."""
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        dev_in = _is_torch(pos)
+        keep = []
+
+        def prep(a, cols):
+            if a is None:
+                return None, 0, 0
+            if _is_torch(a):
+                assert a.is_cuda and a.is_contiguous()
+                rb = a.element_size()
+                keep.append(a)
+                return C.c_void_p(a.data_ptr()), cols * rb, rb
+            a = np.ascontiguousarray(a)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            keep.append(a)
+            return C.c_void_p(a.ctypes.data), cols * a.dtype.itemsize, a.dtype.itemsize
+
+        p = L.NbkParticles()
+        p.pos, p.pos_stride, rb = prep(pos, 3)
+        p.vel, p.vel_stride, rbv = prep(vel, 3)
+        p.mass, p.mass_stride, rbm = prep(mass, 1)
+        for x in (rbv, rbm):
+            if x and x != rb:
+                raise ValueError("pos / vel / mass must share one dtype")
+        p.real_bytes = rb
+        p.on_device = 1 if dev_in else 0
+        n = int(pos.shape[0])
+        per = None
+        if Period is not None:
+            per = np.ascontiguousarray(Period, dtype=np.float64)
+        L.check(self._lib.nbk_create(C.byref(p), n, int(bucket_size), int(TreeType), int(KernType), int(KernRes),
+                                     int(SplittingCriterion), _ptr(per), int(flags), int(device), C.byref(self._h)))
+        self.n = n
+        self.period = per
+        del keep
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.nbk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def info(self):
+        i = L.NbkInfo()
+        L.check(self._lib.nbk_get_info(self._h, C.byref(i)))
+        return i
+
+    def GetNumNodes(self):
+        return self.info.num_nodes
+
+    def GetNumLeafNodes(self):
+        return self.info.num_leaves
+
+    def GetKernNorm(self):
+        return self.info.kernnorm
+
+    def GetBucketSize(self):
+        return self.info.bucket
+
+    def GetTreeType(self):
+        return self.info.treetype
+
+    def GetPeriod(self, j):
+        return self.info.period[j]
+
+    def order(self):
+        """ID of the particle at each tree index (what Particle::GetID returns after the reference's reorder)."""
+        ids = np.empty(self.n, dtype=np.int32)
+        L.check(self._lib.nbk_get_order(self._h, _ptr(ids), 0))
+        return ids
+
+    def kernel_table(self):
+        t = np.empty(self.info.kernres)
+        L.check(self._lib.nbk_get_kernel_table(self._h, _ptr(t)))
+        return t
+
+    def nodes(self):
+        ns = C.c_int64()
+        L.check(self._lib.nbk_get_nodes(self._h, C.byref(ns), None, None, None, None))
+        m = ns.value
+        s, e, c = (np.empty(m, dtype=np.int32) for _ in range(3))
+        b = np.empty((m, 6), dtype=np.float32)
+        L.check(self._lib.nbk_get_nodes(self._h, C.byref(ns), _ptr(s), _ptr(e), _ptr(c), _ptr(b)))
+        return s, e, c, b
+
+    # ---- nearest neighbours -------------------------------------------------------------------
+    def FindNearestPos(self, Nsearch=64, q0=0, q1=None, ids=False, tree_form=False, strict=False, out=None):
+        """Whole-system / range form of FindNearestPos(Int_t tt, ...) (KDFindNearest.cxx:320-334,444-459).
+        Returns (nn, dist2), rows = tree indices q0..q1.  out=(nn, d2) torch CUDA tensors => no copies."""
+        q1 = self.n if q1 is None else q1
+        flags = (L.OUT_IDS if ids else 0) | (L.KNN_TREE_FORM if tree_form else 0) | (L.STRICT_PERIODIC if strict else 0)
+        if out is not None:
+            nn, d2 = out
+            flags |= L.DEVICE_PTRS
+        else:
+            nn = np.empty((q1 - q0, Nsearch), dtype=np.int32)
+            d2 = np.empty((q1 - q0, Nsearch), dtype=np.float64)
+        L.check(self._lib.nbk_knn_particles(self._h, int(Nsearch), int(q0), int(q1), _ptr(nn), _ptr(d2), flags))
+        return nn, d2
+
+    def FindNearest(self, Nsearch=64, **kw):
+        """FindNearest(Int_t tt, ...) (KDFindNearest.cxx:247-318): on a periodic tree the target itself is dropped."""
+        kw.setdefault("tree_form", True)
+        return self.FindNearestPos(Nsearch, **kw)
+
+    def FindNearestPosPoints(self, x, Nsearch=64, ids=False, strict=False):
+        """Batched FindNearestPos(Double_t *x, ...) (KDFindNearest.cxx:462-554)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        m = len(x)
+        nn = np.empty((m, Nsearch), dtype=np.int32)
+        d2 = np.empty((m, Nsearch), dtype=np.float64)
+        flags = (L.OUT_IDS if ids else 0) | (L.STRICT_PERIODIC if strict else 0)
+        L.check(self._lib.nbk_knn_points(self._h, int(Nsearch), m, _ptr(x), _ptr(nn), _ptr(d2), flags))
+        return nn, d2
+
+    # ---- fixed radius -------------------------------------------------------------------------
+    def _ball(self, fn, q, fdist2, ids):
+        m = len(q)
+        off = np.empty(m + 1, dtype=np.int64)
+        tot = C.c_int64()
+        flags = L.OUT_IDS if ids else 0
+        L.check(fn(self._h, float(fdist2), m, _ptr(q), _ptr(off), None, 0, C.byref(tot), flags))
+        idx = np.empty(max(tot.value, 1), dtype=np.int32)
+        L.check(fn(self._h, float(fdist2), m, _ptr(q), _ptr(off), _ptr(idx), len(idx), C.byref(tot), flags))
+        return off, idx[:tot.value]
+
+    def SearchBallPosTagged(self, tt, fdist2, ids=False):
+        """Batched SearchBallPosTagged(Int_t tt, fdist2, tagged) (KDFindNearest.cxx:618-626); tt = tree indices.
+        Returns CSR (offsets, tagged)."""
+        return self._ball(self._lib.nbk_ball_particles, np.ascontiguousarray(tt, dtype=np.int32), fdist2, ids)
+
+    def SearchBallPosTaggedPoints(self, x, fdist2, ids=False):
+        """Batched SearchBallPosTagged(Double_t *x, fdist2, tagged) (KDFindNearest.cxx:628-636)."""
+        return self._ball(self._lib.nbk_ball_points, np.ascontiguousarray(x, dtype=np.float64), fdist2, ids)
+
+    # ---- smoothed estimators ------------------------------------------------------------------
+    def CalcDensity(self, Nsmooth=64, want_h=False, out=None):
+        """KDTree::CalcDensity (KDCalcSmoothQuantities.cxx:203-305); returns rho indexed by ID."""
+        if out is not None:
+            L.check(self._lib.nbk_calc_density(self._h, int(Nsmooth), _ptr(out), None, L.DEVICE_PTRS))
+            return out
+        rho = np.empty(self.n)
+        h = np.empty(self.n) if want_h else None
+        L.check(self._lib.nbk_calc_density(self._h, int(Nsmooth), _ptr(rho), _ptr(h), 0))
+        return (rho, h) if want_h else rho
+
+    def CalcVelDensity(self, Nsmooth=64, Nsearch=64, out=None):
+        """KDTree::CalcVelDensity (KDCalcSmoothQuantities.cxx:309-389)."""
+        if out is not None:
+            L.check(self._lib.nbk_calc_veldensity(self._h, int(Nsmooth), int(Nsearch), _ptr(out), L.DEVICE_PTRS))
+            return out
+        rho = np.empty(self.n)
+        L.check(self._lib.nbk_calc_veldensity(self._h, int(Nsmooth), int(Nsearch), _ptr(rho), 0))
+        return rho
+
+    def CalcSmoothingScale(self, Nsmooth=64):
+        """hi = 0.5*sqrt(d2 of the Nsmooth-th neighbour) (KDCalcSmoothQuantities.cxx:260)."""
+        h = np.empty(self.n)
+        L.check(self._lib.nbk_smoothing_scale(self._h, int(Nsmooth), _ptr(h), 0))
+        return h
+
+    # ---- friends of friends -------------------------------------------------------------------
+    def FOF(self, fdist, minnum=8, order=0, precheck=None, want_len=False, out=None):
+        """KDTree::FOF(fdist, numgroup, minnum, order, ...) (KDFOF.cxx:29-153).  Returns (pfof by ID, numgroup)."""
+        ng = C.c_int64()
+        if out is not None:
+            L.check(self._lib.nbk_fof(self._h, float(fdist), int(minnum), int(order), None, _ptr(out), C.byref(ng), None, L.DEVICE_PTRS))
+            return out, ng.value
+        g = np.empty(self.n, dtype=np.int32)
+        pre = None if precheck is None else np.ascontiguousarray(precheck, dtype=np.int32)
+        lists, plen = None, None
+        if want_len:
+            plen = np.zeros(self.n + 1, dtype=np.int32)
+            lists = L.NbkFofLists(None, None, None, plen.ctypes.data)
+        L.check(self._lib.nbk_fof(self._h, float(fdist), int(minnum), int(order), _ptr(pre), _ptr(g), C.byref(ng),
+                                  C.byref(lists) if lists else None, 0))
+        if want_len:
+            return g, ng.value, plen[:ng.value + 1]
+        return g, ng.value
+
+    def FOFCriterion(self, cmp, params, minnum=8, order=0, precheck=None):
+        """KDTree::FOFCriterion(cmp, params, numgroups, minnum, order) (KDFOF.cxx:157-265) for cmp in
+        {FOF3D, FOF6D} (FOFFunc.h:30-55)."""
+        ng = C.c_int64()
+        g = np.empty(self.n, dtype=np.int32)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        pre = None if precheck is None else np.ascontiguousarray(precheck, dtype=np.int32)
+        L.check(self._lib.nbk_fof_criterion(self._h, int(cmp), _ptr(params), int(minnum), int(order), _ptr(pre), _ptr(g),
+                                            C.byref(ng), None, 0))
+        return g, ng.value
