@@ -26,11 +26,14 @@ namespace {
 
 struct DeviceGuard {
     int prev = -1;
-    explicit DeviceGuard(int dev) {
+    cudaStream_t prev_stream;
+    explicit DeviceGuard(int dev, cudaStream_t st = nullptr) {
         cudaGetDevice(&prev);
         if (dev != prev) NBK_CHECK(cudaSetDevice(dev));
+        prev_stream = cur_stream();
+        cur_stream() = st;
     }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    ~DeviceGuard() { cur_stream() = prev_stream; if (prev >= 0) cudaSetDevice(prev); }
 };
 
 // ---- staging kernels -----------------------------------------------------------------------------
@@ -156,7 +159,8 @@ void build_kernel_table(nbk_tree& t) {
     t.h_kernel.resize(t.kernres);
     double delta = 2.0 / (double)(t.kernres - 1);
     for (int i = 0; i < t.kernres; i++) t.h_kernel[i] = kn * kern_w(type, i * delta, 1.0);
-    NBK_CHECK(cudaMalloc((void**)&t.d_kernel, sizeof(double) * t.kernres));
+    NBK_CHECK(cudaMallocAsync((void**)&t.d_kernel, sizeof(double) * t.kernres, t.stream));
+    NBK_CHECK(cudaStreamSynchronize(t.stream));
     NBK_CHECK(cudaMemcpy(t.d_kernel, t.h_kernel.data(), sizeof(double) * t.kernres, cudaMemcpyHostToDevice));
 }
 
@@ -215,6 +219,13 @@ int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int 
     t->periodic = period != nullptr;
     if (period) for (int d = 0; d < 3; d++) t->period[d] = period[d];
     NBK_CHECK(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    cur_stream() = t->stream;
+    {
+        cudaMemPool_t pool;
+        NBK_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        NBK_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
     NBK_CHECK(cudaEventCreate(&t->ev0)); NBK_CHECK(cudaEventCreate(&t->ev1));
     NBK_CHECK(cudaEventCreate(&t->ev2)); NBK_CHECK(cudaEventCreate(&t->ev3));
     cudaStream_t st = t->stream;
@@ -278,10 +289,15 @@ int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int 
 int nbk_destroy(nbk_tree* t) {
     NBK_API_BEGIN
     if (!t) return NBK_OK;
-    DeviceGuard guard(t->device);
+    DeviceGuard guard(t->device, t->stream);
     cudaStreamSynchronize(t->stream);
-    cudaFree(t->prim); cudaFree(t->sec); cudaFree(t->mass); cudaFree(t->order);
-    cudaFree(t->nlo); cudaFree(t->nhi); cudaFree(t->cutdim); cudaFree(t->d_kernel);
+    void* bufs[] = {t->prim, t->sec, t->mass, t->order, t->nlo, t->nhi, t->cutdim, t->d_kernel};
+    for (void* b : bufs) if (b) cudaFreeAsync(b, t->stream);
+    cudaStreamSynchronize(t->stream);
+    {   // hand the recycled scratch back to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, t->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     cudaEventDestroy(t->ev0); cudaEventDestroy(t->ev1); cudaEventDestroy(t->ev2); cudaEventDestroy(t->ev3);
     cudaStreamDestroy(t->stream);
     delete t;
@@ -306,7 +322,7 @@ int nbk_get_info(const nbk_tree* t, nbk_info* info) {
 int nbk_get_order(const nbk_tree* t, int32_t* ids, int flags) {
     NBK_API_BEGIN
     NBK_REQUIRE(t && ids, NBK_ERR_ARG, "nbk_get_order: null argument");
-    DeviceGuard guard(t->device);
+    DeviceGuard guard(t->device, t->stream);
     NBK_CHECK(cudaMemcpyAsync(ids, t->order, sizeof(int32_t) * t->n, (flags & NBK_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
     NBK_CHECK(cudaStreamSynchronize(t->stream));
     NBK_API_END
@@ -324,7 +340,7 @@ int nbk_get_nodes(const nbk_tree* t, int64_t* num_slots, int32_t* start, int32_t
     NBK_REQUIRE(t && num_slots, NBK_ERR_ARG, "nbk_get_nodes: null argument");
     *num_slots = t->nslots;
     if (!start && !end && !cutdim && !bounds) return NBK_OK;
-    DeviceGuard guard(t->device);
+    DeviceGuard guard(t->device, t->stream);
     std::vector<NodeLo> lo(t->nslots);
     std::vector<NodeHi> hi(t->nslots);
     std::vector<int8_t> cd(t->nslots);
@@ -355,7 +371,7 @@ int nbk_knn_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, d
     require_knn_tree(t);
     NBK_REQUIRE(q0 >= 0 && q1 <= t->n && q0 <= q1, NBK_ERR_ARG, "nbk_knn_particles: bad query range");
     NBK_REQUIRE(k >= 1, NBK_ERR_ARG, "nbk_knn_particles: k must be >= 1");
-    DeviceGuard guard(t->device);
+    DeviceGuard guard(t->device, t->stream);
     const int64_t rows = q1 - q0;
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<int32_t> dnn;
@@ -387,7 +403,7 @@ int nbk_knn_points(nbk_tree* t, int k, int64_t m, const double* x, int32_t* nn, 
     require_knn_tree(t);
     NBK_REQUIRE(k >= 1 && m >= 0, NBK_ERR_ARG, "nbk_knn_points: bad k or m");
     if (m == 0) return NBK_OK;
-    DeviceGuard guard(t->device);
+    DeviceGuard guard(t->device, t->stream);
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<double> dx, dd2;
     DevBuf<int32_t> dnn;
@@ -451,7 +467,7 @@ static void smooth_call(nbk_tree* t, int k, int veldens_k, double* rho, double* 
     require_knn_tree(t);
     NBK_REQUIRE(t->treetype == NBK_TPHYS || veldens_k == 0, NBK_ERR_UNSUPPORTED, "CalcVelDensity needs a physical tree");
     NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
-    DeviceGuard guard(t->device);
+    DeviceGuard guard(t->device, t->stream);
     const int64_t n = t->n;
     DevBuf<double> drho(rho ? n : 0), dh(hsm ? n : 0);
     KnnArgs a;
@@ -497,7 +513,7 @@ static void fof_call(nbk_tree* t, FofArgs& a, const int32_t* precheck, int32_t* 
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "FOF needs a TPHYS or TPHS tree");
     NBK_REQUIRE(!(lists && (lists->head || lists->next || lists->tail)), NBK_ERR_UNSUPPORTED,
                 "FOF pHead/pNext/pTail outputs are not implemented yet (pLen is)");
-    DeviceGuard guard(t->device);
+    DeviceGuard guard(t->device, t->stream);
     const int64_t n = t->n;
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<int32_t> dpre, dpre_tree, dgroup(n), dlen;
@@ -561,7 +577,7 @@ static void ball_call(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx
                       int64_t cap, int64_t* total, int flags) {
     NBK_REQUIRE(offsets && total, NBK_ERR_ARG, "ball search: null output");
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "SearchBallPos needs positions as tree coordinates");
-    DeviceGuard guard(t->device);
+    DeviceGuard guard(t->device, t->stream);
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<int32_t> dq, didx;
     DevBuf<double> dx;

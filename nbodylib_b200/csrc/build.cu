@@ -211,6 +211,7 @@ void build_tree(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* sec_in, cons
     cudaStream_t st = t.stream;
     const int bucket = t.bucket;
     int64_t launches = 0;
+    Tracer tr(st);
 
     // ---- shape (depends only on n and bucket) ------------------------------------------------------
     int depth = 0;
@@ -269,6 +270,7 @@ void build_tree(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* sec_in, cons
         }
         NBK_CHECK(cudaStreamSynchronize(st));
     }
+    tr.point("build: 3 radix sorts");
     if (depth > 0) {
         const int ntiles = div_up(n, PRIM_TILE);
         DevBuf<int32_t> pos_node(n);
@@ -291,6 +293,7 @@ void build_tree(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* sec_in, cons
                                                                            pos_node.p, side.p, tsum.p, ntiles, rcount.p);
             launches += 4;
             for (int d = 0; d < 3; d++) { uint32_t* tp = o[d]; o[d] = nw[d]; nw[d] = tp; }
+            if (tr.on) { char lb[64]; snprintf(lb, sizeof(lb), "build: level %d", l); tr.point(lb); }
         }
         // deepest level: leaves only
         {
@@ -310,6 +313,7 @@ void build_tree(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* sec_in, cons
         NBK_CHECK(cudaStreamSynchronize(st));
     }
     NBK_CHECK(cudaGetLastError());
+    tr.point("build: leaves + gather");
 
     t.device_bytes = (int64_t)(prim.bytes() + sec.bytes() + mass.bytes() + order.bytes() + nlo.bytes() + nhi.bytes() + cutdim.bytes());
     t.prim = prim.p; prim.p = nullptr;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -31,6 +33,11 @@ struct Error : public std::runtime_error {
         if (!(cond)) throw ::nbk::Error((code), std::string(msg));    \
     } while (0)
 
+// Stream the calling API entry point works on: DevBuf allocations are stream-ordered (cudaMallocAsync from the
+// device's default pool, whose release threshold nbk_create raises so that temporaries are recycled, not
+// returned to the driver: cudaMalloc/cudaFree of multi-GB scratch costs more than the kernels using it).
+inline cudaStream_t& cur_stream() { static thread_local cudaStream_t s = nullptr; return s; }
+
 // RAII device buffer
 template <class T>
 struct DevBuf {
@@ -50,19 +57,34 @@ struct DevBuf {
         release();
         n = count;
         if (count) {
-            cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+            cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), cur_stream());
             if (e != cudaSuccess) {
                 p = nullptr; n = 0;
-                throw Error(NBK_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+                throw Error(NBK_ERR_NOMEM, std::string("device allocation failed: ") + cudaGetErrorString(e));
             }
         }
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, cur_stream());
         p = nullptr; n = 0;
     }
     size_t bytes() const { return n * sizeof(T); }
     operator T*() const { return p; }
+};
+
+// NBK_TRACE=1 : print host-side phase timings (each point synchronises the stream; debugging only)
+struct Tracer {
+    cudaStream_t st; bool on; double last;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit Tracer(cudaStream_t s) : st(s), on(getenv("NBK_TRACE") != nullptr), last(0) { if (on) { cudaStreamSynchronize(st); last = now(); } }
+    void point(const char* label) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        double t = now();
+        fprintf(stderr, "[nbk] %-32s %10.3f ms\n", label, t - last);
+        last = t;
+    }
 };
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

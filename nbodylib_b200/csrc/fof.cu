@@ -215,6 +215,7 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     DevBuf<uint32_t> size(n), flag(n + 1), flagscan(n + 1), scratch(scan_scratch_elems(n + 1));
     const int tb = 256;
     int64_t launches = 0;
+    Tracer tr(st);
     fof_init_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p);
     FofParams p;
     p.nlo = t.nlo; p.nhi = t.nhi; p.bucket = t.bucket;
@@ -231,6 +232,7 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     if (t.store_bytes == 4) fof_link_kernel<float><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
     else fof_link_kernel<double><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
     NBK_CHECK(cudaEventRecord(t.ev3, st));
+    tr.point("fof link");
     fof_flatten_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p);
     fof_root_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p, a.minnum, a.precheck_tree, flag.p);
     NBK_CHECK(cudaMemsetAsync(flag.p + n, 0, sizeof(uint32_t), st));
@@ -239,6 +241,7 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     NBK_CHECK(cudaMemcpyAsync(&ng32, flagscan.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     NBK_CHECK(cudaStreamSynchronize(st));
     a.ngroups = ng32;
+    tr.point("fof flatten+root+scan");
     launches += 5;
     DevBuf<uint32_t> newid;
     if (a.order && ng32 > 1) {
@@ -253,6 +256,7 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
         launches += 2;
         NBK_CHECK(cudaStreamSynchronize(st));
     }
+    tr.point("fof order");
     fof_label_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, flag.p, flagscan.p, newid.p, a.group_tree);
     launches++;
     if (a.len) {
@@ -262,6 +266,7 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     }
     NBK_CHECK(cudaStreamSynchronize(st));
     NBK_CHECK(cudaGetLastError());
+    tr.point("fof label");
     float ms = 0;
     NBK_CHECK(cudaEventElapsedTime(&ms, t.ev2, t.ev3));
     t.last_kernel_ms = ms;

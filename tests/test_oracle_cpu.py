@@ -1,0 +1,170 @@
+"""CPU suite (-m "not gpu"): pins the oracle port against the golden vectors produced by the reference, checks
+the port against the live reference build when oracle/_ref exists, the host-side logic, and that the C-ABI
+library loads and exports every symbol include/nbk.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.util import ROOT, canon, csr_rows_sorted, load_golden, rows_equal_as_sets
+
+
+@pytest.fixture(scope="module")
+def G():
+    return load_golden()
+
+
+def test_known_kernel_norms(port, G):
+    # SURVEY.md 8c known answers
+    norm, tab = port.kernel_table(3, 0, 1000)
+    assert norm == pytest.approx(0.31830988618379069, rel=0, abs=1e-16)
+    norm_e, tab_e = port.kernel_table(3, 2, 1000)
+    assert norm_e == pytest.approx(0.074603879574325946, rel=0, abs=1e-16)
+    assert norm == float(G["kernnorm_sph"]) and norm_e == float(G["kernnorm_epan"])
+    assert tab_e[-1] == 0.0 and tab[-1] == 0.0 and tab_e[0] == norm_e
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_port_knn_matches_reference_golden(port, G, tag):
+    period = None if tag == "np" else np.ones(3)
+    k = int(G["k"])
+    for which in (0, 1):
+        ids, d2 = port.knn_particles(G["pos"], k, period=period, which=which)
+        assert np.array_equal(d2, G["knn%d_d2_%s" % (which, tag)])          # bit-exact fp64
+        assert rows_equal_as_sets(ids, G["knn%d_ids_%s" % (which, tag)])
+    ids, d2 = port.knn_points(G["pos"], G["xq"], k, period=period)
+    assert np.array_equal(d2, G["knnx_d2_" + tag]) and rows_equal_as_sets(ids, G["knnx_ids_" + tag])
+
+
+def test_periodic_self_rules_q3(G):
+    # quirk Q3: periodic FindNearestPos(tt) returns self first; FindNearest(tt) never returns self
+    ids0, ids1 = G["knn0_ids_p"], G["knn1_ids_p"]
+    n = len(ids0)
+    assert np.array_equal(ids0[:, 0], np.arange(n)) and np.all(G["knn0_d2_p"][:, 0] == 0)
+    assert not np.any(ids1 == np.arange(n)[:, None])
+    assert not np.any(G["knn0_ids_np"] == np.arange(n)[:, None])
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_port_density_matches_reference_golden(port, G, tag):
+    k = int(G["k"])
+    rho, h = port.density(G["pos"], G["mass"], k)
+    np.testing.assert_allclose(rho, G["rho_" + tag], rtol=1e-13)
+    # quirk Q2: the period is ignored by CalcDensity
+    np.testing.assert_allclose(G["rho_p"], G["rho_np"], rtol=1e-13)
+    vr = port.veldensity(G["pos"], G["vel"], 8, k)
+    np.testing.assert_allclose(vr, G["vrho_" + tag], rtol=1e-13)
+    if tag == "np":
+        rho_s, _ = port.density(G["pos"], G["mass"], k, kerntype=0)
+        np.testing.assert_allclose(rho_s, G["rho_sph_np"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_port_fof_matches_reference_golden(port, G, tag):
+    period = None if tag == "np" else np.ones(3)
+    ll = float(G["ll"])
+    g, ng = port.fof(G["pos"], None, 0, [ll * ll], period, 5, 0)
+    assert ng == G["fof_" + tag].max() and np.array_equal(canon(g), canon(G["fof_" + tag]))
+    g, ng = port.fof(G["pos"], None, 0, [ll * ll], period, 5, 1)
+    assert np.array_equal(canon(g), canon(G["fof_ord_" + tag]))
+    assert np.array_equal(np.bincount(g)[1:], np.bincount(G["fof_ord_" + tag])[1:])   # same size ranking
+    g, ng = port.fof(G["pos"], G["vel"], 4, G["params"], period, 5, 0)
+    assert ng > 0 and np.array_equal(canon(g), canon(G["fof6d_" + tag]))
+    g, ng = port.fof(G["pos"], G["vel"], 2, G["params"], period, 5, 0)
+    assert np.array_equal(canon(g), canon(G["fof3d_" + tag]))
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_port_ball_matches_reference_golden(port, G, tag):
+    period = None if tag == "np" else np.ones(3)
+    off, idx = port.ball_points(G["pos"], G["xq"], (3 * float(G["ll"])) ** 2, period)
+    assert np.array_equal(off, G["ball_off_" + tag])
+    assert np.array_equal(np.concatenate(csr_rows_sorted(off, idx)), G["ball_idx_" + tag])
+
+
+def test_port_vs_live_reference(port):
+    """Where the reference compiles (oracle/_ref), re-check the port on a fresh seed incl. tree shape facts."""
+    from oracle.pyoracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    from nbodylib_b200.synth import clustered_small
+    pos, vel, mass = clustered_small(6000, seed=99)
+    for period in (None, np.ones(3)):
+        R = Ref(pos, vel, mass, period=period)
+        assert (R.num_nodes, R.num_leaves) == (1023, 512)
+        ids, d2 = R.knn_particles(24, which=0)
+        pi, pd = port.knn_particles(pos, 24, period=period, which=0)
+        assert np.array_equal(d2, pd) and rows_equal_as_sets(ids, pi)
+        ll = 0.3 / 6000 ** (1 / 3)
+        g, ng = R.fof(ll, 6, 0)
+        pg, png = port.fof(pos, None, 0, [ll * ll], period, 6, 0)
+        assert ng == png and np.array_equal(canon(g), canon(pg))
+        R.close()
+
+
+def test_reference_tree_shape_known_answer():
+    """N=1e6, b=16 -> 131071 nodes / 65536 leaves: the closed-form shape used by the device build."""
+    def shape(n, b):
+        nodes = leaves = 0
+        level = {n: 1}
+        while level:
+            nxt = {}
+            for s, c in level.items():
+                nodes += c
+                if s <= b:
+                    leaves += c
+                else:
+                    for ch in ((s + 1) // 2, s // 2):
+                        nxt[ch] = nxt.get(ch, 0) + c
+            level = nxt
+        return nodes, leaves
+    assert shape(1000000, 16) == (131071, 65536)
+    assert shape(2500, 16) == (511, 256)
+    assert shape(13, 16) == (1, 1)
+
+
+def test_cabi_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "nbk.h")).read()
+    declared = sorted(set(re.findall(r"\b(nbk_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(os.path.join(ROOT, "nbodylib_b200", "libnbk.so"))
+    for name in declared:
+        assert hasattr(lib, name), "libnbk.so does not export %s" % name
+    from nbodylib_b200 import _lib
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_no_cpu_fallback_without_device(built):
+    """On a machine without a GPU the product must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from nbodylib_b200 import KDTree, NbkError
+    with pytest.raises(NbkError) as e:
+        KDTree(np.random.rand(100, 3))
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under nbodylib_b200/ may import, include, link or dlopen it."""
+    pkg = os.path.join(ROOT, "nbodylib_b200")
+    pat = re.compile(r"(^\s*(from|import)\s+\S*oracle)|(#include\s*[\"<][^\">]*oracle)|(liboracle|libnbref|pyoracle)", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".cxx")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), "%s references the oracle" % f
+
+
+def test_synth_is_fp32_representable_and_deterministic():
+    from nbodylib_b200.synth import clustered_box, clustered_small, uniform_box
+    p, v, m = clustered_small(3000, seed=5)
+    assert np.array_equal(p, p.astype(np.float32).astype(np.float64)) and p.min() >= 0 and p.max() < 1
+    p2, _, _ = clustered_small(3000, seed=5)
+    assert np.array_equal(p, p2)
+    pos, vel, mass = clustered_box(16, seed=3, nhalo=4, min_members=32)
+    assert pos.shape == (4096, 3) and float(pos.min()) >= 0 and float(pos.max()) < 1
+    pu, _, _ = uniform_box(1000)
+    assert pu.shape == (1000, 3)
