@@ -79,59 +79,67 @@ __global__ void gather_i32_kernel(int64_t n, const int32_t* order, const int32_t
     if (i < n) dst[i] = src[order[i]];
 }
 
-// Bring n strided triplets (host or device memory) into a packed device double[n][3].
-// Host arrays are packed by a few threads into pinned chunks and copied asynchronously (double buffered).
+// Bring n strided records of `comps` reals (host or device memory) into a packed device double[n][comps].
+// Device input: converted in place by a gather kernel.  Host input: contiguous arrays are copied as they are
+// (cudaMemcpyAsync straight from the caller's buffer -- pinned buffers run at PCIe speed); strided AoS records
+// (the reference's 88-byte Particle) are packed by a few host threads into pinned chunks, double buffered
+// against the copies.  Widening to fp64 always happens on the device.
 void stage3(const void* src, int64_t stride, int real_bytes, bool on_device, int64_t n, int comps, double* d_out, cudaStream_t st) {
     const int tb = 256;
-    if (on_device) {
+    auto convert = [&](const void* dsrc, int64_t dstride) {
         if (comps == 3) {
-            if (real_bytes == 8) gather3_kernel<double><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)src, stride, n, d_out);
-            else gather3_kernel<float><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)src, stride, n, d_out);
+            if (real_bytes == 8) gather3_kernel<double><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)dsrc, dstride, n, d_out);
+            else gather3_kernel<float><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)dsrc, dstride, n, d_out);
         } else {
-            if (real_bytes == 8) gather1_kernel<double><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)src, stride, n, d_out);
-            else gather1_kernel<float><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)src, stride, n, d_out);
+            if (real_bytes == 8) gather1_kernel<double><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)dsrc, dstride, n, d_out);
+            else gather1_kernel<float><<<div_up(n, tb), tb, 0, st>>>((const unsigned char*)dsrc, dstride, n, d_out);
         }
         NBK_CHECK(cudaGetLastError());
-        return;
-    }
-    if (real_bytes == 8 && stride == (int64_t)comps * 8) {   // already packed doubles
-        NBK_CHECK(cudaMemcpyAsync(d_out, src, (size_t)n * comps * 8, cudaMemcpyHostToDevice, st));
+    };
+    if (on_device) { convert(src, stride); return; }
+    const int64_t rec = (int64_t)comps * real_bytes;
+    if (real_bytes == 8 && stride == rec) {   // packed doubles: no conversion needed
+        NBK_CHECK(cudaMemcpyAsync(d_out, src, (size_t)n * rec, cudaMemcpyHostToDevice, st));
         NBK_CHECK(cudaStreamSynchronize(st));
         return;
     }
-    const int64_t chunk = 1 << 22;
-    double* pin[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
-    for (int b = 0; b < 2; b++) {
-        NBK_CHECK(cudaMallocHost((void**)&pin[b], (size_t)std::min(chunk, n) * comps * 8));
-        NBK_CHECK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
-    }
-    unsigned hw = std::thread::hardware_concurrency();
-    int nth = (int)std::max(1u, std::min(hw ? hw : 4u, 16u));
-    int b = 0;
-    for (int64_t c0 = 0; c0 < n; c0 += chunk, b ^= 1) {
-        int64_t cn = std::min(chunk, n - c0);
-        NBK_CHECK(cudaEventSynchronize(done[b]));
-        auto work = [&](int tid) {
-            int64_t lo = cn * tid / nth, hi = cn * (tid + 1) / nth;
-            const unsigned char* bp = (const unsigned char*)src + (c0 + lo) * stride;
-            double* o = pin[b] + lo * comps;
-            for (int64_t i = lo; i < hi; i++, bp += stride, o += comps) {
-                if (real_bytes == 8) { const double* p = (const double*)bp; for (int k = 0; k < comps; k++) o[k] = p[k]; }
-                else { const float* p = (const float*)bp; for (int k = 0; k < comps; k++) o[k] = (double)p[k]; }
-            }
-        };
-        if (cn < 65536 || nth == 1) { for (int tdx = 0; tdx < nth; tdx++) work(tdx); }
-        else {
-            std::vector<std::thread> th;
-            for (int tdx = 0; tdx < nth; tdx++) th.emplace_back(work, tdx);
-            for (auto& x : th) x.join();
+    DevBuf<unsigned char> raw((size_t)n * rec);
+    if (stride == rec) {
+        NBK_CHECK(cudaMemcpyAsync(raw.p, src, (size_t)n * rec, cudaMemcpyHostToDevice, st));
+    } else {
+        const int64_t chunk = 1 << 22;
+        unsigned char* pin[2] = {nullptr, nullptr};
+        cudaEvent_t done[2];
+        for (int b = 0; b < 2; b++) {
+            NBK_CHECK(cudaMallocHost((void**)&pin[b], (size_t)std::min(chunk, n) * rec));
+            NBK_CHECK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
         }
-        NBK_CHECK(cudaMemcpyAsync(d_out + c0 * comps, pin[b], (size_t)cn * comps * 8, cudaMemcpyHostToDevice, st));
-        NBK_CHECK(cudaEventRecord(done[b], st));
+        unsigned hw = std::thread::hardware_concurrency();
+        int nth = (int)std::max(1u, std::min(hw ? hw : 4u, 16u));
+        int b = 0;
+        for (int64_t c0 = 0; c0 < n; c0 += chunk, b ^= 1) {
+            int64_t cn = std::min(chunk, n - c0);
+            NBK_CHECK(cudaEventSynchronize(done[b]));
+            auto work = [&](int tid) {
+                int64_t lo = cn * tid / nth, hi = cn * (tid + 1) / nth;
+                const unsigned char* bp = (const unsigned char*)src + (c0 + lo) * stride;
+                unsigned char* o = pin[b] + lo * rec;
+                for (int64_t i = lo; i < hi; i++, bp += stride, o += rec) memcpy(o, bp, (size_t)rec);
+            };
+            if (cn < 65536 || nth == 1) { for (int tdx = 0; tdx < nth; tdx++) work(tdx); }
+            else {
+                std::vector<std::thread> th;
+                for (int tdx = 0; tdx < nth; tdx++) th.emplace_back(work, tdx);
+                for (auto& x : th) x.join();
+            }
+            NBK_CHECK(cudaMemcpyAsync(raw.p + c0 * rec, pin[b], (size_t)cn * rec, cudaMemcpyHostToDevice, st));
+            NBK_CHECK(cudaEventRecord(done[b], st));
+        }
+        NBK_CHECK(cudaStreamSynchronize(st));
+        for (int q = 0; q < 2; q++) { cudaFreeHost(pin[q]); cudaEventDestroy(done[q]); }
     }
+    convert(raw.p, rec);
     NBK_CHECK(cudaStreamSynchronize(st));
-    for (int q = 0; q < 2; q++) { cudaFreeHost(pin[q]); cudaEventDestroy(done[q]); }
 }
 
 // KernelConstruction, reference KDTree.cxx:1144-1183 + SmoothingKernels.h:32-56
