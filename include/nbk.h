@@ -83,6 +83,7 @@ typedef struct {
     double  last_call_ms;                    /* device time of the whole last query call (all kernels, no copies)   */
     int64_t last_launches;                   /* kernels launched by the last call                                   */
     int64_t device_bytes;                    /* HBM held by the tree                                                */
+    int64_t last_flagged;                    /* density calls: queries re-run by the exact-heap kernel (fp32 key ties) */
 } nbk_info;
 
 const char* nbk_last_error(void);
@@ -150,6 +151,11 @@ int nbk_fof(nbk_tree* t, double fdist, int minnum, int order, const int32_t* pre
  * pos/vel pruning length^2, [6],[7] criterion parameters). */
 int nbk_fof_criterion(nbk_tree* t, int criterion, const double* params, int minnum, int order,
                       const int32_t* precheck, int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags);
+
+/* Scratch buffers are recycled through the device's stream-ordered memory pool and kept across calls and
+ * trees (allocating and freeing GBs through the driver costs more than the kernels).  This hands the cached
+ * memory back to the driver (e.g. before another library needs the HBM). */
+int nbk_release_cached_memory(int device);
 
 /* Device-resident views for callers that stay on the GPU (sharded driver, benchmarks). */
 int nbk_device_arrays(const nbk_tree* t, const void** pos4, const void** vel4, const void** mass, const int32_t** order);

@@ -25,7 +25,7 @@ class NbkInfo(C.Structure):
                 ("inexact_coords", C.c_int64),
                 ("kernnorm", C.c_double), ("period", C.c_double * 3),
                 ("build_ms", C.c_double), ("h2d_ms", C.c_double), ("last_kernel_ms", C.c_double), ("last_call_ms", C.c_double),
-                ("last_launches", C.c_int64), ("device_bytes", C.c_int64)]
+                ("last_launches", C.c_int64), ("device_bytes", C.c_int64), ("last_flagged", C.c_int64)]
 
 
 class NbkFofLists(C.Structure):
@@ -39,7 +39,7 @@ EXPORTS = [
     "nbk_last_error", "nbk_device_count", "nbk_create", "nbk_destroy", "nbk_get_info", "nbk_get_order",
     "nbk_get_kernel_table", "nbk_get_nodes", "nbk_knn_particles", "nbk_knn_points", "nbk_ball_particles",
     "nbk_ball_points", "nbk_calc_density", "nbk_calc_veldensity", "nbk_smoothing_scale", "nbk_fof",
-    "nbk_fof_criterion", "nbk_device_arrays",
+    "nbk_fof_criterion", "nbk_device_arrays", "nbk_release_cached_memory",
 ]
 
 _lib = None
@@ -72,6 +72,7 @@ def load():
     L.nbk_smoothing_scale.argtypes = [vp, i32, vp, i32]
     L.nbk_fof.argtypes = [vp, dbl, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]
     L.nbk_fof_criterion.argtypes = [vp, i32, vp, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]
+    L.nbk_release_cached_memory.argtypes = [i32]
     L.nbk_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     for name in EXPORTS:
         if name not in ("nbk_last_error", "nbk_device_count"):

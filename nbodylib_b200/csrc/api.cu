@@ -302,10 +302,7 @@ int nbk_destroy(nbk_tree* t) {
     void* bufs[] = {t->prim, t->sec, t->mass, t->order, t->nlo, t->nhi, t->cutdim, t->d_kernel};
     for (void* b : bufs) if (b) cudaFreeAsync(b, t->stream);
     cudaStreamSynchronize(t->stream);
-    {   // hand the recycled scratch back to the driver
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, t->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    }
+
     cudaEventDestroy(t->ev0); cudaEventDestroy(t->ev1); cudaEventDestroy(t->ev2); cudaEventDestroy(t->ev3);
     cudaStreamDestroy(t->stream);
     delete t;
@@ -323,7 +320,7 @@ int nbk_get_info(const nbk_tree* t, nbk_info* info) {
     info->kernnorm = t->kernnorm;
     for (int d = 0; d < 3; d++) info->period[d] = t->period[d];
     info->build_ms = t->build_ms; info->h2d_ms = t->h2d_ms; info->last_kernel_ms = t->last_kernel_ms;
-    info->last_call_ms = t->last_call_ms; info->last_launches = t->last_launches; info->device_bytes = t->device_bytes;
+    info->last_call_ms = t->last_call_ms; info->last_launches = t->last_launches; info->device_bytes = t->device_bytes; info->last_flagged = t->last_flagged;
     NBK_API_END
 }
 
@@ -490,7 +487,7 @@ static void smooth_call(nbk_tree* t, int k, int veldens_k, double* rho, double* 
     tm.stop();
     float ms = 0;
     NBK_CHECK(cudaEventElapsedTime(&ms, t->ev2, t->ev3));
-    t->last_kernel_ms = ms; t->last_launches = 1 + (rho ? 1 : 0);
+    t->last_kernel_ms = ms; t->last_launches += (rho ? 1 : 0);
     if (rho) deliver_f64(t, drho.p, rho, flags);
     if (hsm) deliver_f64(t, dh.p, hsm, flags);
 }
@@ -623,6 +620,16 @@ int nbk_ball_points(nbk_tree* t, double fdist2, int64_t m, const double* x, int6
     NBK_API_BEGIN
     NBK_REQUIRE(t && (x || m == 0), NBK_ERR_ARG, "nbk_ball_points: null argument");
     ball_call(t, fdist2, m, nullptr, x, offsets, idx, cap, total, flags);
+    NBK_API_END
+}
+
+int nbk_release_cached_memory(int device) {
+    NBK_API_BEGIN
+    if (device < 0) NBK_CHECK(cudaGetDevice(&device));
+    cudaMemPool_t pool;
+    NBK_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    NBK_CHECK(cudaDeviceSynchronize());
+    NBK_CHECK(cudaMemPoolTrimTo(pool, 0));
     NBK_API_END
 }
 

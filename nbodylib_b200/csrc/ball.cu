@@ -36,7 +36,6 @@ struct BallVisitor {
     int32_t* idx; int64_t cap; int out_ids;
 
     __device__ __forceinline__ bool need(float lb) const { return lb < r2f; }
-    __device__ __forceinline__ bool whole(const QueryBox&, const NodeLo&, const NodeHi&, bool) const { return false; }
     __device__ __forceinline__ void leaf(int start, int cnt) {
         for (int base = 0; base < cnt; base += 32) {
             int m = min(32, cnt - base);

@@ -64,7 +64,6 @@ struct FofVisitor {
     unsigned lane;
 
     __device__ __forceinline__ bool need(float lb) const { return lb < prune_f; }
-    __device__ __forceinline__ bool whole(const QueryBox&, const NodeLo&, const NodeHi&, bool) const { return false; }
 
     __device__ __forceinline__ bool linked(int j) const {
         const double cx = tile[j], cy = tile[32 + j], cz = tile[64 + j];

@@ -5,11 +5,24 @@
 // KDSplitNode.cxx:15-41; FindNearestPosPeriodic :1119-1148; PriorityQueue.h:14-85; drivers
 // KDFindNearest.cxx:247-334,462-554; KDTree::CalcDensity / CalcVelDensity KDCalcSmoothQuantities.cxx:203-389.
 //
-// Layout: one warp = 32 queries adjacent in tree order; lane l owns query l and a bounded max-heap of
-// (fp64 d2, int32 index) in shared memory, slot-major / lane-minor ([slot][32]) so that lanes touching
-// different slots never bank-conflict.  Candidates come from the shared traversal (traverse.cuh); the
-// distance is the reference's fp64 expression on exactly widened coordinates, so the neighbour set and
-// every d2 are bit-identical to the reference whatever the traversal order.
+// Layout: one warp = 32 queries adjacent in tree order; lane l owns query l and a bounded max-heap in shared
+// memory, slot-major / lane-minor ([slot][32]) so that lanes touching different slots never bank-conflict.
+// Candidates come from the shared traversal (traverse.cuh); the distance is the reference's fp64 expression on
+// exactly widened coordinates, so neighbour sets and every d2 are bit-identical to the reference whatever the
+// traversal order.
+//
+// Two kernels:
+//   knn_exact_kernel  heap of (fp64 d2, int32 index), 12 B/entry.  Used when neighbour lists are materialised
+//                     (FindNearest API), for the periodic image schedule, and as the fallback below.
+//   knn_fast_kernel   the density family (CalcDensity / CalcVelDensity / smoothing scale), non periodic target
+//                     form.  Heap entries are ONE 64-bit word: (fp32 key << 32 | index), key = RN_fp32(d2) of the
+//                     exact fp64 d2.  fp64->fp32 rounding is monotone, so the k smallest keys are the exact k
+//                     nearest unless the k-th and (k+1)-th keys are EQUAL; the heap carries k+1 entries to see that
+//                     case, and such queries (a ~1e-5 fraction on random data) are appended to a list that the
+//                     exact kernel re-runs.  Exact d2 for the SPH weights is recomputed from the indices.
+//                     8 B/entry instead of 12 and half the shared-memory traffic per sift step; the heap is
+//                     bulk-loaded from the k+1 tree-order neighbours of the bucket (heapify) instead of k
+//                     full-depth insertions.
 #include "traverse.cuh"
 #include "tree.h"
 
@@ -18,6 +31,28 @@ namespace nbk {
 constexpr int KNN_WARPS = 4;
 constexpr double KNN_SENTINEL = 1e32;   // reference MAXVALUE (Precision.h:49)
 
+// smoothing kernel interpolation, KDCalcSmoothQuantities.cxx:12-15
+__device__ __forceinline__ double wsm(double r, int i, int size, double delta, const double* __restrict__ x) {
+    if (i < size - 1) { double a = x[i], b = x[i + 1]; return (a + (b - a) * (r - delta * i) / delta); }
+    return x[i];
+}
+
+struct KnnParams {
+    const NodeLo* nlo; const NodeHi* nhi; int bucket;
+    const void* P; const void* V; const double* mass; const int32_t* order;
+    int64_t n;
+    int64_t q0, q1; const double* xq; int mode;      // mode 0: particles [q0,q1) or qlist; 1: points
+    const int32_t* qlist; int64_t nq;                 // optional explicit particle list (exact kernel)
+    int k, kcap;
+    int periodic, strict, tree_form;
+    double period[3];
+    int32_t* nn; double* d2out; int out_ids;
+    double* rho; double* hsm; int veldens_k;
+    const double* kern; int kernres;
+    int* flag_count; int32_t* flag_list;              // fast kernel: queries that need the exact kernel
+};
+
+// ================================================================================================ exact
 struct WarpHeap {
     double* H;   // [kcap][32]
     int* I;      // [kcap][32]
@@ -72,7 +107,6 @@ struct KnnVisitor {
     unsigned lane;
 
     __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
-    __device__ __forceinline__ bool whole(const QueryBox&, const NodeLo&, const NodeHi&, bool) const { return false; }
     __device__ __forceinline__ void settop() { top = hp.h(0); topf = __double2float_ru(top); }
 
     __device__ __forceinline__ void leaf(int start, int cnt) {
@@ -104,26 +138,8 @@ struct KnnVisitor {
     }
 };
 
-// smoothing kernel interpolation, KDCalcSmoothQuantities.cxx:12-15
-__device__ __forceinline__ double wsm(double r, int i, int size, double delta, const double* __restrict__ x) {
-    if (i < size - 1) { double a = x[i], b = x[i + 1]; return (a + (b - a) * (r - delta * i) / delta); }
-    return x[i];
-}
-
-struct KnnParams {
-    const NodeLo* nlo; const NodeHi* nhi; int bucket;
-    const void* P; const void* V; const double* mass; const int32_t* order;
-    int64_t q0, q1; const double* xq; int mode;
-    int k, kcap;
-    int periodic, strict, tree_form;
-    double period[3];
-    int32_t* nn; double* d2out; int out_ids;
-    double* rho; double* hsm; int veldens_k;
-    const double* kern; int kernres;
-};
-
 template <class S>
-__global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(KnnParams prm) {
+__global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
     const size_t warp_bytes = (size_t)prm.kcap * 32 * 12 + 96 * 8 + TRAV_STACK * 4;
@@ -136,10 +152,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(KnnParams prm) {
     hp.k = prm.kcap; hp.lane = lane;
 
     const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
-    int64_t group = (int64_t)blockIdx.x * KNN_WARPS + w;
-    int64_t qi = prm.q0 + group * 32 + lane;
-    if (prm.q0 + group * 32 >= prm.q1) return;       // whole warp out of range
-    const bool valid = qi < prm.q1;
+    const int64_t nrows = prm.qlist ? prm.nq : (prm.q1 - prm.q0);
+    const int64_t group = (int64_t)blockIdx.x * KNN_WARPS + w;
+    const int64_t row = group * 32 + lane;
+    if (group * 32 >= nrows) return;                 // whole warp out of range
+    const bool valid = row < nrows;
+    const int64_t qi = valid ? (prm.qlist ? (int64_t)prm.qlist[row] : prm.q0 + row) : 0;
 
     KnnVisitor<S> v;
     v.P = P; v.tile = tile; v.hp = hp; v.lane = lane;
@@ -258,44 +276,357 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(KnnParams prm) {
         v.hp.sort_ascending(kc);
         // periodic particle searches carry k+1 slots: FindNearestPos(tt) drops the farthest, FindNearest(tt) the nearest (Q3)
         const int off = (prm.kcap > prm.k && prm.tree_form) ? 1 : 0;
-        const int64_t row = (qi - prm.q0) * (int64_t)prm.k;
+        const int64_t orow = row * (int64_t)prm.k;
         for (int j = 0; j < prm.k; j++) {
             int id = v.hp.i(j + off);
-            if (prm.nn) prm.nn[row + j] = (prm.out_ids && id >= 0) ? prm.order[id] : id;
-            if (prm.d2out) prm.d2out[row + j] = v.hp.h(j + off);
+            if (prm.nn) prm.nn[orow + j] = (prm.out_ids && id >= 0) ? prm.order[id] : id;
+            if (prm.d2out) prm.d2out[orow + j] = v.hp.h(j + off);
         }
     }
 }
 
-void launch_knn(nbk_tree& t, const KnnArgs& a) {
-    NBK_REQUIRE(a.k >= 1, NBK_ERR_ARG, "k must be >= 1");
-    KnnParams p;
+// ================================================================================================= fast
+constexpr unsigned FKEY_INF = 0x7f800000u;   // +inf: empty slot
+
+// Per-lane 4-ary max-heap in shared memory.  Node p's four children are nodes 4p+1..4p+4 and their fp32 keys sit
+// in ONE 16-byte group, so a sift step costs one LDS.128 instead of two dependent 8-byte loads, and a 65-entry
+// heap is 3 levels deep instead of 6.  Key of node p: group (p+3)>>2, component (p+3)&3 (node 0 = group 0, comp 3),
+// groups are [group][lane] float4 (conflict-free 16-byte lane stride); indices are [node][lane] int32.
+struct Heap4 {
+    float4* K4;   // [G+1][32]
+    int* I;       // [NN][32]
+    int G;        // internal nodes: 0..G-1 ; NN = 4G+1 nodes
+    unsigned lane;
+    __device__ __forceinline__ float* keyp(int p) const { return reinterpret_cast<float*>(K4 + (((p + 3) >> 2) * 32 + lane)) + ((p + 3) & 3); }
+    __device__ __forceinline__ int& idx(int p) const { return I[p * 32 + lane]; }
+    __device__ __forceinline__ float rootkey() const { return *keyp(0); }
+    // place (xk, xi) at node p and sift it down
+    __device__ __forceinline__ void sift(int p, float xk, int xi) {
+        while (p < G) {
+            const float4 ck = K4[(p + 1) * 32 + lane];
+            const float m = fmaxf(fmaxf(ck.x, ck.y), fmaxf(ck.z, ck.w));
+            if (xk >= m) break;
+            const int j = (ck.x == m) ? 0 : ((ck.y == m) ? 1 : ((ck.z == m) ? 2 : 3));
+            const int c = 4 * p + 1 + j;
+            *keyp(p) = m;
+            idx(p) = idx(c);
+            p = c;
+        }
+        *keyp(p) = xk;
+        idx(p) = xi;
+    }
+};
+
+template <class S>
+struct FastVisitor {
+    const Vec4<S>* P;
+    double* tile;
+    Heap4 hp;
+    double qx, qy, qz;
+    double topd;        // (double) of the heap-top key; 0 for lanes without a query (nothing is ever accepted)
+    float topf;
+    int self;
+    int r0, r1;         // tree-index range already loaded into the heap (skipped during the traversal)
+    unsigned lane;
+
+    __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
+    __device__ __forceinline__ void settop() { topf = hp.rootkey(); topd = (double)topf; }
+
+    template <bool OVERLAP>
+    __device__ __forceinline__ void scan_tile(int first, int m) {
+        unsigned acc = 0;
+#pragma unroll 4
+        for (int j = 0; j < m; j++) {
+            const int c = first + j;
+            double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+            bool ok = d2 < topd && d2 > 0.0 && c != self;
+            if (OVERLAP) ok = ok && (c < r0 || c >= r1);
+            acc |= (ok ? 1u : 0u) << j;
+        }
+        while (__any_sync(0xffffffffu, acc != 0)) {
+            if (acc) {
+                int j = __ffs(acc) - 1;
+                acc &= acc - 1;
+                double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+                if (d2 < topd) { hp.sift(0, __double2float_rn(d2), first + j); settop(); }
+            }
+        }
+    }
+
+    __device__ __forceinline__ void leaf(int start, int cnt) {
+        if (start >= r0 && start + cnt <= r1) return;          // warp-uniform: leaf entirely preloaded
+        const bool overlap = start < r1 && start + cnt > r0;   // warp-uniform
+        for (int base = 0; base < cnt; base += 32) {
+            int m = min(32, cnt - base);
+            __syncwarp();
+            if ((int)lane < m) {
+                Vec4<S> c = P[start + base + lane];
+                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
+            }
+            __syncwarp();
+            if (overlap) scan_tile<true>(start + base, m);
+            else scan_tile<false>(start + base, m);
+        }
+    }
+};
+
+static inline int heap4_groups(int kcap) { return (kcap - 1 + 3) / 4; }
+static inline size_t fast_warp_bytes(int kcap) {
+    int G = heap4_groups(kcap);
+    return (size_t)(G + 1) * 32 * 16 + (size_t)(4 * G + 1) * 32 * 4 + 96 * 8 + TRAV_STACK * 4;
+}
+
+template <class S>
+__global__ void __launch_bounds__(KNN_WARPS * 32) knn_fast_kernel(KnnParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    const int kcap = prm.kcap;                        // k + 1 real slots
+    const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
+    const size_t warp_bytes = (size_t)(G + 1) * 32 * 16 + (size_t)NN * 32 * 4 + 96 * 8 + TRAV_STACK * 4;
+    unsigned char* base = smem_raw + w * warp_bytes;
+    Heap4 hp;
+    hp.K4 = reinterpret_cast<float4*>(base);
+    hp.I = reinterpret_cast<int*>(base + (size_t)(G + 1) * 32 * 16);
+    hp.G = G; hp.lane = lane;
+    double* tile = reinterpret_cast<double*>(base + (size_t)(G + 1) * 32 * 16 + (size_t)NN * 32 * 4);
+    int* stack = reinterpret_cast<int*>(base + (size_t)(G + 1) * 32 * 16 + (size_t)NN * 32 * 4 + 96 * 8);
+
+    const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
+    const int64_t group = (int64_t)blockIdx.x * KNN_WARPS + w;
+    const int64_t g0 = prm.q0 + group * 32;
+    if (g0 >= prm.q1) return;
+    const int64_t qi = g0 + lane;
+    const bool valid = qi < prm.q1;
+
+    FastVisitor<S> v;
+    v.P = P; v.tile = tile; v.hp = hp; v.lane = lane;
+    v.self = valid ? (int)qi : -1;
+    double x0 = 0, y0 = 0, z0 = 0;
+    if (valid) { Vec4<S> c = P[qi]; x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z; }
+    v.qx = x0; v.qy = y0; v.qz = z0;
+
+    // ---- bulk load: the kcap particles around the bucket in tree order, then heapify -----------------------
+    {
+        // exactly kcap tree positions: every one of them is either skipped for good (self, coincident) or stored,
+        // so marking the range as "already seen" for the traversal never loses a candidate
+        int64_t want = (int64_t)kcap;
+        int64_t r0 = g0 + 16 - want / 2;
+        if (r0 + want > prm.n) r0 = prm.n - want;
+        if (r0 < 0) r0 = 0;
+        int64_t r1 = r0 + want;
+        if (r1 > prm.n) r1 = prm.n;
+        v.r0 = (int)r0; v.r1 = (int)r1;
+        int filled = 0;
+        for (int64_t b0 = r0; b0 < r1; b0 += 32) {
+            int m = (int)min((int64_t)32, r1 - b0);
+            __syncwarp();
+            if ((int)lane < m) {
+                Vec4<S> c = P[b0 + lane];
+                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
+            }
+            __syncwarp();
+            for (int j = 0; j < m; j++) {
+                double d2 = dist2_ref(x0, y0, z0, tile[j], tile[32 + j], tile[64 + j]);
+                if (valid && (int)(b0 + j) != v.self && d2 > 0.0) {
+                    *v.hp.keyp(filled) = __double2float_rn(d2);
+                    v.hp.idx(filled) = (int)(b0 + j);
+                    filled++;
+                }
+            }
+        }
+        // empty real slots wait for candidates (+inf); the padding up to 4G+1 nodes, and every slot of a lane without
+        // a query, holds key 0 / index -1: never evicted, never accepted against
+        for (; filled < NN; filled++) {
+            *v.hp.keyp(filled) = (valid && filled < kcap) ? __uint_as_float(FKEY_INF) : 0.f;
+            v.hp.idx(filled) = -1;
+        }
+        for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p), v.hp.idx(p));
+        v.settop();
+    }
+    {
+        QueryBox qb = make_qbox(x0, y0, z0);
+        traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
+    }
+    if (!valid) return;
+
+    // ---- exactness test: drop the (k+1)-th; the k smallest keys are the exact kNN iff key_k < key_{k+1} -------
+    const float key_kp1 = v.hp.rootkey();
+    v.hp.sift(0, 0.f, -1);                                       // the root becomes padding
+    const float key_k = v.hp.rootkey();
+    const bool short_of_k = __float_as_uint(key_k) == FKEY_INF;  // fewer than k candidates exist (n <= k)
+    if (key_k == key_kp1 && !short_of_k) {
+        int slot = atomicAdd(prm.flag_count, 1);
+        prm.flag_list[slot] = (int)qi;
+        return;                                                  // the exact kernel redoes this query entirely
+    }
+    // exact k-th distance: the largest exact d2 among the entries sharing the top key
+    double d2max = 0;
+    for (int s = 0; s < NN; s++) {
+        int id = v.hp.idx(s);
+        if (id >= 0 && *v.hp.keyp(s) == key_k) {
+            Vec4<S> c = P[id];
+            d2max = fmax(d2max, dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z));
+        }
+    }
+    if (short_of_k) d2max = KNN_SENTINEL;
+    if (prm.hsm) prm.hsm[qi] = 0.5 * sqrt(d2max);
+    if (prm.rho && prm.veldens_k == 0) {
+        const double hi = 0.5 * sqrt(d2max);
+        const double norm = 1.0 / pow(hi, 3.0);
+        const double delta = 2.0 / (double)(prm.kernres - 1);
+        const double mi = prm.mass[qi];
+        double acc = 0;
+        for (int s = 0; s < NN; s++) {
+            int id = v.hp.idx(s);
+            if (id < 0) continue;
+            Vec4<S> c = P[id];
+            double rij = sqrt(dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z));
+            double r = rij / hi;
+            double Wij = 0.5 * wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+            acc += Wij * prm.mass[id];
+            atomicAdd(&prm.rho[id], Wij * mi);
+        }
+        atomicAdd(&prm.rho[qi], acc);
+    }
+    if (prm.rho && prm.veldens_k > 0) {
+        // R2.  The fp64 velocity distances (up to k per lane) are written over the lane's own heap storage, which is dead
+        // by now: doubles 0..2G+1 over the lane's key groups, the rest over pairs of the lane's index slots that have
+        // already been consumed (double t >= 2G+2 uses index slots 2u, 2u+1 with u = t-2G-2 <= s-2G-2, and 2u+1 <= s for
+        // every read position s <= 4G).  Everything stays lane-private, so no cross-lane ordering is needed.
+        const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
+        const int nA = 2 * (G + 1);
+        auto dget = [&](int t) -> double {
+            if (t < nA) return reinterpret_cast<const double*>(v.hp.K4 + ((t >> 1) * 32 + lane))[t & 1];
+            const int u = t - nA;
+            return __hiloint2double(v.hp.I[(2 * u + 1) * 32 + lane], v.hp.I[(2 * u) * 32 + lane]);
+        };
+        auto dset = [&](int t, double d) {
+            if (t < nA) { reinterpret_cast<double*>(v.hp.K4 + ((t >> 1) * 32 + lane))[t & 1] = d; return; }
+            const int u = t - nA;
+            v.hp.I[(2 * u) * 32 + lane] = __double2loint(d);
+            v.hp.I[(2 * u + 1) * 32 + lane] = __double2hiint(d);
+        };
+        Vec4<S> vi = V[qi];
+        int kx = 0;
+        for (int s = 0; s < NN; s++) {
+            int id = v.hp.idx(s);
+            if (id < 0) continue;
+            Vec4<S> vj = V[id];
+            dset(kx, sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)));
+            kx++;
+        }
+        auto dsift = [&](int p, int n, double d) {      // binary max-heap on the doubles
+            while (true) {
+                int c = 2 * p + 1;
+                if (c >= n) break;
+                double dc = dget(c);
+                if (c + 1 < n) { double dr = dget(c + 1); if (dr > dc) { c = c + 1; dc = dr; } }
+                if (d >= dc) break;
+                dset(p, dc);
+                p = c;
+            }
+            dset(p, d);
+        };
+        const int kv = min(prm.veldens_k, kx);
+        double rho = 0;
+        if (kv > 0) {
+            for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, dget(p));
+            for (int s = kv; s < kx; s++) {
+                double vd = dget(s);
+                if (vd < dget(0)) dsift(0, kv, vd);
+            }
+            const double hi = 0.5 * dget(0);
+            const double norm = 1.0 / pow(hi, 3.0);
+            const double delta = 2.0 / (double)(prm.kernres - 1);
+            // pop in descending order like the reference so the sum is accumulated in the same order
+            for (int e = kv; e > 0; e--) {
+                double rij = dget(0);
+                double r = rij / hi;
+                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+                dsift(0, e - 1, dget(e - 1));
+            }
+        }
+        prm.rho[qi] = rho;
+    }
+}
+
+static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.nlo = t.nlo; p.nhi = t.nhi; p.bucket = t.bucket;
     p.P = t.prim; p.V = t.vel4(); p.mass = t.mass; p.order = t.order;
+    p.n = t.n;
     p.q0 = a.q0; p.q1 = a.q1; p.xq = a.xq; p.mode = a.mode;
+    p.qlist = nullptr; p.nq = 0;
     p.k = a.k;
-    p.kcap = a.k + ((a.periodic && a.mode == 0) ? 1 : 0);
     p.periodic = a.periodic; p.strict = a.strict; p.tree_form = a.tree_form;
     for (int d = 0; d < 3; d++) p.period[d] = t.period[d];
     p.nn = a.nn; p.d2out = a.d2; p.out_ids = a.out_ids;
     p.rho = a.rho; p.hsm = a.hsm; p.veldens_k = a.veldens_k;
     p.kern = t.d_kernel; p.kernres = t.kernres;
-    if (a.veldens_k > 0) NBK_REQUIRE(p.V != nullptr, NBK_ERR_ARG, "velocity density needs velocities");
-    int64_t rows = a.q1 - a.q0;
-    if (rows <= 0) return;
+    p.flag_count = nullptr; p.flag_list = nullptr;
+}
+
+static void run_exact(nbk_tree& t, KnnParams& p, int64_t rows) {
     size_t warp_bytes = (size_t)p.kcap * 32 * 12 + 96 * 8 + TRAV_STACK * 4;
     size_t smem = warp_bytes * KNN_WARPS;
     NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps (max ~145 at 4 warps/CTA)");
-    int64_t groups = (rows + 31) / 32;
-    int blocks = div_up(groups, KNN_WARPS);
+    int blocks = div_up((rows + 31) / 32, KNN_WARPS);
     if (t.store_bytes == 4) {
-        NBK_CHECK(cudaFuncSetAttribute(knn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
+        NBK_CHECK(cudaFuncSetAttribute(knn_exact_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_exact_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
     } else {
-        NBK_CHECK(cudaFuncSetAttribute(knn_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_kernel<double><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
+        NBK_CHECK(cudaFuncSetAttribute(knn_exact_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_exact_kernel<double><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
     }
     NBK_CHECK(cudaGetLastError());
+}
+
+void launch_knn(nbk_tree& t, const KnnArgs& a) {
+    NBK_REQUIRE(a.k >= 1, NBK_ERR_ARG, "k must be >= 1");
+    KnnParams p;
+    fill_common(p, t, a);
+    if (a.veldens_k > 0) NBK_REQUIRE(p.V != nullptr, NBK_ERR_ARG, "velocity density needs velocities");
+    const int64_t rows = a.q1 - a.q0;
+    if (rows <= 0) return;
+    t.last_launches = 0;
+    t.last_flagged = 0;
+    const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm);
+    if (smooth_only && getenv("NBK_KNN_EXACT_ONLY") == nullptr) {
+        // ---- fast path + exact fallback for the flagged queries ----------------------------------------------
+        p.kcap = a.k + 1;
+        size_t warp_bytes = fast_warp_bytes(p.kcap);
+        size_t smem = warp_bytes * KNN_WARPS;
+        NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");
+        DevBuf<int> fcount(1);
+        DevBuf<int32_t> flist(rows);
+        NBK_CHECK(cudaMemsetAsync(fcount.p, 0, sizeof(int), t.stream));
+        p.flag_count = fcount.p; p.flag_list = flist.p;
+        int blocks = div_up((rows + 31) / 32, KNN_WARPS);
+        if (t.store_bytes == 4) {
+            NBK_CHECK(cudaFuncSetAttribute(knn_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knn_fast_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
+        } else {
+            NBK_CHECK(cudaFuncSetAttribute(knn_fast_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knn_fast_kernel<double><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
+        }
+        NBK_CHECK(cudaGetLastError());
+        t.last_launches += 2;
+        int nflag = 0;
+        NBK_CHECK(cudaMemcpyAsync(&nflag, fcount.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
+        NBK_CHECK(cudaStreamSynchronize(t.stream));
+        t.last_flagged = nflag;
+        if (nflag > 0) {
+            KnnParams pe = p;
+            pe.kcap = a.k;
+            pe.qlist = flist.p; pe.nq = nflag;
+            pe.flag_count = nullptr; pe.flag_list = nullptr;
+            run_exact(t, pe, nflag);
+            t.last_launches += 1;
+        }
+        return;
+    }
+    p.kcap = a.k + ((a.periodic && a.mode == 0) ? 1 : 0);
+    run_exact(t, p, rows);
+    t.last_launches += 1;
 }
 
 }  // namespace nbk

@@ -49,44 +49,67 @@ __device__ __forceinline__ QueryBox make_qbox(double x, double y, double z) {
 }
 
 // Visitor interface (all methods called by the full warp):
-//   bool need(float lb)                      per-lane: could this lane accept something at distance^2 >= lb ?
-//   void leaf(int start, int cnt)            process particles [start, start+cnt)
-//   bool whole(q, lo, hi, on)                optional whole-node shortcut; return true (warp-uniform) if the node was consumed
-// ORDERED: always descend left child first so leaves are met in ascending tree-index order.
+//   bool need(float lb)             per-lane: could this lane accept something at distance^2 >= lb ?
+//   void leaf(int start, int cnt)   process particles [start, start+cnt)
+// ORDERED: always descend the left child first so leaves are met in ascending tree-index order.
+//
+// Control flow: a node is tested when it is reached as a child; the nearer child (by vote of the lanes that
+// need it) is descended into directly and only the other child goes on the stack, to be re-tested against the
+// lanes' current bounds when popped.
 template <class V, bool ORDERED = false>
 __device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi, int bucket, int* stack, V& v,
                                          const QueryBox& q, bool on) {
     const unsigned lane = lane_id();
-    int sp = 1;
-    if (lane == 0) stack[0] = 0;
-    __syncwarp();
-    while (sp > 0) {
-        int node = stack[--sp];
-        NodeLo lo = nlo[node];
-        NodeHi hi = nhi[node];
+    int sp = 0;
+    int node = 0;
+    NodeLo lo = nlo[0];
+    NodeHi hi = nhi[0];
+    {
         float lb = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, lo, hi);
-        bool nd = on && v.need(lb);
-        if (!__any_sync(0xffffffffu, nd)) continue;
-        int cnt = hi.end - lo.start;
-        if (v.whole(q, lo, hi, on)) continue;
-        if (cnt <= bucket) { v.leaf(lo.start, cnt); continue; }
-        int c1 = 2 * node + 1, c2 = c1 + 1;
-        NodeLo l1 = nlo[c1]; NodeHi h1 = nhi[c1];
-        NodeLo l2 = nlo[c2]; NodeHi h2 = nhi[c2];
-        float b1 = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, l1, h1);
-        float b2 = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, l2, h2);
-        bool n1 = on && v.need(b1), n2 = on && v.need(b2);
-        unsigned m1 = __ballot_sync(0xffffffffu, n1), m2 = __ballot_sync(0xffffffffu, n2);
-        unsigned p1 = __ballot_sync(0xffffffffu, (n1 || n2) && (b1 <= b2));
-        bool first1 = ORDERED ? true : (2 * __popc(p1) >= __popc(m1 | m2));
-        __syncwarp();
-        if (lane == 0) {
-            int s = sp;
-            if (first1) { if (m2) stack[s++] = c2; if (m1) stack[s++] = c1; }
-            else        { if (m1) stack[s++] = c1; if (m2) stack[s++] = c2; }
+        if (!__any_sync(0xffffffffu, on && v.need(lb))) return;
+    }
+    while (true) {
+        // invariant: `node` (bounds lo/hi) is needed by at least one lane
+        bool descend = false;
+        if (hi.end - lo.start <= bucket) {
+            v.leaf(lo.start, hi.end - lo.start);
+        } else {
+            const int c1 = 2 * node + 1, c2 = c1 + 1;
+            NodeLo l1 = nlo[c1]; NodeHi h1 = nhi[c1];
+            NodeLo l2 = nlo[c2]; NodeHi h2 = nhi[c2];
+            float b1 = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, l1, h1);
+            float b2 = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, l2, h2);
+            bool n1 = on && v.need(b1), n2 = on && v.need(b2);
+            unsigned m1 = __ballot_sync(0xffffffffu, n1), m2 = __ballot_sync(0xffffffffu, n2);
+            if (m1 | m2) {
+                bool first1;
+                if (ORDERED) first1 = true;
+                else {
+                    unsigned p1 = __ballot_sync(0xffffffffu, (n1 || n2) && (b1 <= b2));
+                    first1 = 2 * __popc(p1) >= __popc(m1 | m2);
+                }
+                if (m1 && m2) {
+                    if (lane == 0) stack[sp] = first1 ? c2 : c1;
+                    sp++;
+                    __syncwarp();
+                }
+                bool take1 = m1 && (first1 || !m2);
+                node = take1 ? c1 : c2;
+                lo = take1 ? l1 : l2;
+                hi = take1 ? h1 : h2;
+                descend = true;
+            }
         }
-        sp += (m1 != 0) + (m2 != 0);
-        __syncwarp();
+        if (descend) continue;
+        // pop until a still-needed node is found
+        bool found = false;
+        while (sp > 0) {
+            node = stack[--sp];
+            lo = nlo[node]; hi = nhi[node];
+            float lb = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, lo, hi);
+            if (__any_sync(0xffffffffu, on && v.need(lb))) { found = true; break; }
+        }
+        if (!found) return;
     }
 }
 

@@ -37,6 +37,7 @@ struct nbk_tree {
     // timings
     double build_ms = 0, h2d_ms = 0, last_kernel_ms = 0, last_call_ms = 0;
     int64_t last_launches = 0;
+    int64_t last_flagged = 0;       // queries the fp32-key kNN kernel handed to the exact kernel
     int64_t device_bytes = 0;
 
     const void* pos4() const { return treetype == NBK_TVEL ? sec : prim; }

@@ -161,6 +161,24 @@ def test_duplicates_and_ties(nb, port):
         assert ng == ong == 100 and np.array_equal(canon(g), canon(og))
 
 
+def test_fp32_key_ties_fall_back_to_exact_heap(nb, port):
+    """The density kernels rank candidates by the fp32 rounding of the exact fp64 d2; queries whose k-th and
+    (k+1)-th keys coincide must be re-run by the exact fp64 heap.  Quadruplets of points 1e-13 apart force that."""
+    rng = np.random.default_rng(12)
+    base = rng.random((1500, 3))
+    pos = np.concatenate([base + np.array([j * 1e-13, 0, 0]) for j in range(4)])
+    mass = 1.0 + rng.random(len(pos))
+    vel = rng.standard_normal((len(pos), 3))
+    with nb.KDTree(pos, vel, mass) as t:
+        assert t.info.store_bytes == 8
+        rho, h = t.CalcDensity(18, want_h=True)
+        assert t.info.last_flagged > 1000
+        orho, oh = port.density(pos, mass, 18)
+        np.testing.assert_allclose(rho, orho, rtol=RTOL_RHO)
+        assert np.array_equal(h, oh)
+        np.testing.assert_allclose(t.CalcVelDensity(7, 18), port.veldensity(pos, vel, 7, 18), rtol=RTOL_RHO)
+
+
 def test_tphs_form_a_equals_fof6d_form_b(nb, port):
     """BASELINE config 4: ScalePhase + TPHS tree + FOF(1.0) == FOFCriterion(FOF6d); scaled coordinates are not
     fp32-representable, so the tree must keep fp64 coordinates to stay bit-exact."""
