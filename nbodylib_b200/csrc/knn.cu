@@ -288,6 +288,15 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
 // ================================================================================================= fast
 constexpr unsigned FKEY_INF = 0x7f800000u;   // +inf: empty slot
 
+#ifdef NBK_STATS
+__device__ unsigned long long g_stats[8];   // 0 tiles, 1 candidate evals (warp-level), 2 rounds, 3 sifts (lane-level), 4 accepted bits, 5 leaves skipped
+#define STAT(i, v) do { if (lane_id() == 0) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
+#define STAT_LANE(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+#else
+#define STAT(i, v)
+#define STAT_LANE(i, v)
+#endif
+
 // Per-lane 4-ary max-heap in shared memory.  Node p's four children are nodes 4p+1..4p+4 and their fp32 keys sit
 // in ONE 16-byte group, so a sift step costs one LDS.128 instead of two dependent 8-byte loads, and a 65-entry
 // heap is 3 levels deep instead of 6.  Key of node p: group (p+3)>>2, component (p+3)&3 (node 0 = group 0, comp 3),
@@ -335,6 +344,7 @@ struct FastVisitor {
     template <bool OVERLAP>
     __device__ __forceinline__ void scan_tile(int first, int m) {
         unsigned acc = 0;
+        STAT(0, 1); STAT(1, m);
 #pragma unroll 4
         for (int j = 0; j < m; j++) {
             const int c = first + j;
@@ -343,12 +353,14 @@ struct FastVisitor {
             if (OVERLAP) ok = ok && (c < r0 || c >= r1);
             acc |= (ok ? 1u : 0u) << j;
         }
+        STAT_LANE(4, __popc(acc));
         while (__any_sync(0xffffffffu, acc != 0)) {
+            STAT(2, 1);
             if (acc) {
                 int j = __ffs(acc) - 1;
                 acc &= acc - 1;
                 double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-                if (d2 < topd) { hp.sift(0, __double2float_rn(d2), first + j); settop(); }
+                if (d2 < topd) { STAT_LANE(3, 1); hp.sift(0, __double2float_rn(d2), first + j); settop(); }
             }
         }
     }
@@ -550,6 +562,287 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_fast_kernel(KnnParams prm)
     }
 }
 
+// ==================================================================================== select-then-collect
+// The density family needs only (a) the exact k-th distance and (b) a sum over the k nearest neighbours, so the
+// search is split in two traversals sharing one small shared-memory region per warp:
+//   select  : per-lane 4-ary max-heap of fp32 KEYS ONLY (k+1 of them) -> key_k, key_{k+1}.  No indices are carried,
+//             so a sift step moves 4 bytes, and the region is half the size of a (key,index) heap: twice the resident
+//             warps for this latency-bound kernel.
+//   collect : fixed-radius pass, every candidate with RN_fp32(d2) <= key_k is appended to the lane's index list
+//             (exactly the k nearest when key_k < key_{k+1}; otherwise the query goes to the exact kernel); appends
+//             are predicated stores, there are no serial insertion rounds.  The exact fp64 k-th distance is the max
+//             over the appended candidates.
+//   epilogue: SPH sums over the list, as before.
+struct KeyHeap4 {
+    float4* K4;   // [G+1][32]
+    int G;
+    unsigned lane;
+    __device__ __forceinline__ float* keyp(int p) const { return reinterpret_cast<float*>(K4 + (((p + 3) >> 2) * 32 + lane)) + ((p + 3) & 3); }
+    __device__ __forceinline__ float rootkey() const { return *keyp(0); }
+    __device__ __forceinline__ void sift(int p, float xk) {
+        while (p < G) {
+            const float4 ck = K4[(p + 1) * 32 + lane];
+            const float m = fmaxf(fmaxf(ck.x, ck.y), fmaxf(ck.z, ck.w));
+            if (xk >= m) break;
+            const int j = (ck.x == m) ? 0 : ((ck.y == m) ? 1 : ((ck.z == m) ? 2 : 3));
+            *keyp(p) = m;
+            p = 4 * p + 1 + j;
+        }
+        *keyp(p) = xk;
+    }
+};
+
+template <class S>
+struct SelectVisitor {
+    const Vec4<S>* P;
+    double* tile;
+    KeyHeap4 hp;
+    double qx, qy, qz;
+    double topd;
+    float topf;
+    int self, r0, r1;
+    unsigned lane;
+    __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
+    __device__ __forceinline__ void settop() { topf = hp.rootkey(); topd = (double)topf; }
+    template <bool OVERLAP>
+    __device__ __forceinline__ void scan_tile(int first, int m) {
+        unsigned acc = 0;
+#pragma unroll 4
+        for (int j = 0; j < m; j++) {
+            const int c = first + j;
+            double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+            bool ok = d2 < topd && d2 > 0.0 && c != self;
+            if (OVERLAP) ok = ok && (c < r0 || c >= r1);
+            acc |= (ok ? 1u : 0u) << j;
+        }
+        while (__any_sync(0xffffffffu, acc != 0)) {
+            if (acc) {
+                int j = __ffs(acc) - 1;
+                acc &= acc - 1;
+                double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+                if (d2 < topd) { hp.sift(0, __double2float_rn(d2)); settop(); }
+            }
+        }
+    }
+    __device__ __forceinline__ void leaf(int start, int cnt) {
+        if (start >= r0 && start + cnt <= r1) return;
+        const bool overlap = start < r1 && start + cnt > r0;
+        for (int base = 0; base < cnt; base += 32) {
+            int m = min(32, cnt - base);
+            __syncwarp();
+            if ((int)lane < m) {
+                Vec4<S> c = P[start + base + lane];
+                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
+            }
+            __syncwarp();
+            if (overlap) scan_tile<true>(start + base, m);
+            else scan_tile<false>(start + base, m);
+        }
+    }
+};
+
+template <class S>
+struct CollectVisitor {
+    const Vec4<S>* P;
+    double* tile;
+    int* L;            // [k][32] index list
+    double qx, qy, qz;
+    double d2max;
+    double thr_d;      // candidates with d2 >= thr_d cannot qualify (cheap fp64 pre-test)
+    float thr;         // qualify iff RN_fp32(d2) <= thr ; -1 for lanes that collect nothing
+    int self, cnt, cap;
+    unsigned lane;
+    __device__ __forceinline__ bool need(float lb) const { return lb <= thr; }
+    __device__ __forceinline__ void leaf(int start, int n) {
+        for (int base = 0; base < n; base += 32) {
+            int m = min(32, n - base);
+            __syncwarp();
+            if ((int)lane < m) {
+                Vec4<S> c = P[start + base + lane];
+                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
+            }
+            __syncwarp();
+#pragma unroll 4
+            for (int j = 0; j < m; j++) {
+                const int c = start + base + j;
+                double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+                if (d2 < thr_d && d2 > 0.0 && c != self && __double2float_rn(d2) <= thr && cnt < cap) {
+                    L[cnt * 32 + lane] = c;
+                    cnt++;
+                    d2max = fmax(d2max, d2);
+                }
+            }
+        }
+    }
+};
+
+static inline size_t sc_warp_bytes(int k, bool want_doubles) {
+    int G = heap4_groups(k + 1);
+    size_t keys = (size_t)(G + 1) * 32 * 16, list = (size_t)k * 32 * 4;
+    size_t region = keys > list ? keys : list;
+    if (want_doubles) region = list + (size_t)k * 32 * 8 > region ? list + (size_t)k * 32 * 8 : region;
+    return region + 96 * 8 + TRAV_STACK * 4;
+}
+
+template <class S>
+__global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, int want_doubles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    const int k = prm.k, kcap = k + 1;
+    const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
+    size_t region = (size_t)(G + 1) * 32 * 16;
+    if ((size_t)k * 32 * 4 > region) region = (size_t)k * 32 * 4;
+    if (want_doubles && (size_t)k * 32 * 12 > region) region = (size_t)k * 32 * 12;
+    const size_t warp_bytes = region + 96 * 8 + TRAV_STACK * 4;
+    unsigned char* base = smem_raw + w * warp_bytes;
+    double* tile = reinterpret_cast<double*>(base + region);
+    int* stack = reinterpret_cast<int*>(base + region + 96 * 8);
+
+    const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
+    const int64_t group = (int64_t)blockIdx.x * KNN_WARPS + w;
+    const int64_t g0 = prm.q0 + group * 32;
+    if (g0 >= prm.q1) return;
+    const int64_t qi = g0 + lane;
+    const bool valid = qi < prm.q1;
+    double x0 = 0, y0 = 0, z0 = 0;
+    if (valid) { Vec4<S> c = P[qi]; x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z; }
+    const QueryBox qb = make_qbox(x0, y0, z0);
+
+    // ---------------------------------------------------------------------------------------------- select
+    float key_k, key_kp1;
+    {
+        SelectVisitor<S> v;
+        v.P = P; v.tile = tile; v.lane = lane;
+        v.hp.K4 = reinterpret_cast<float4*>(base); v.hp.G = G; v.hp.lane = lane;
+        v.self = valid ? (int)qi : -1;
+        v.qx = x0; v.qy = y0; v.qz = z0;
+        int64_t want = (int64_t)kcap;
+        int64_t r0 = g0 + 16 - want / 2;
+        if (r0 + want > prm.n) r0 = prm.n - want;
+        if (r0 < 0) r0 = 0;
+        int64_t r1 = r0 + want;
+        if (r1 > prm.n) r1 = prm.n;
+        v.r0 = (int)r0; v.r1 = (int)r1;
+        int filled = 0;
+        for (int64_t b0 = r0; b0 < r1; b0 += 32) {
+            int m = (int)min((int64_t)32, r1 - b0);
+            __syncwarp();
+            if ((int)lane < m) {
+                Vec4<S> c = P[b0 + lane];
+                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
+            }
+            __syncwarp();
+            for (int j = 0; j < m; j++) {
+                double d2 = dist2_ref(x0, y0, z0, tile[j], tile[32 + j], tile[64 + j]);
+                if (valid && (int)(b0 + j) != v.self && d2 > 0.0) { *v.hp.keyp(filled) = __double2float_rn(d2); filled++; }
+            }
+        }
+        for (; filled < NN; filled++) *v.hp.keyp(filled) = (valid && filled < kcap) ? __uint_as_float(FKEY_INF) : 0.f;
+        for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p));
+        v.settop();
+        traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
+        key_kp1 = v.hp.rootkey();
+        v.hp.sift(0, 0.f);
+        key_k = v.hp.rootkey();
+    }
+    const bool short_of_k = __float_as_uint(key_k) == FKEY_INF;
+    const bool flagged = valid && key_k == key_kp1 && !short_of_k;
+    if (flagged) {
+        int slot = atomicAdd(prm.flag_count, 1);
+        prm.flag_list[slot] = (int)qi;
+    }
+    __syncwarp();   // the key groups are dead from here on: the region is reused for the index list
+
+    // --------------------------------------------------------------------------------------------- collect
+    CollectVisitor<S> c2;
+    c2.P = P; c2.tile = tile; c2.L = reinterpret_cast<int*>(base); c2.lane = lane;
+    c2.qx = x0; c2.qy = y0; c2.qz = z0;
+    c2.self = valid ? (int)qi : -1;
+    c2.cnt = 0; c2.cap = k; c2.d2max = 0;
+    c2.thr = (valid && !flagged) ? key_k : -1.f;
+    c2.thr_d = (valid && !flagged) ? (double)__uint_as_float(__float_as_uint(key_k) + (short_of_k ? 0u : 1u)) : -1.0;   // next float above key_k
+    if (short_of_k && valid) c2.thr_d = 3.0e38 * 10.0;
+    const bool collecting = valid && !flagged;
+    traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, collecting);
+    if (!collecting) return;
+
+    // -------------------------------------------------------------------------------------------- epilogues
+    const int cnt = c2.cnt;
+    const double d2max = short_of_k ? KNN_SENTINEL : c2.d2max;
+    if (prm.hsm) prm.hsm[qi] = 0.5 * sqrt(d2max);
+    if (prm.rho && prm.veldens_k == 0) {
+        const double hi = 0.5 * sqrt(d2max);
+        const double norm = 1.0 / pow(hi, 3.0);
+        const double delta = 2.0 / (double)(prm.kernres - 1);
+        const double mi = prm.mass[qi];
+        double acc = 0;
+        for (int s = 0; s < cnt; s++) {
+            int id = c2.L[s * 32 + lane];
+            Vec4<S> c = P[id];
+            double rij = sqrt(dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z));
+            double r = rij / hi;
+            double Wij = 0.5 * wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+            acc += Wij * prm.mass[id];
+            atomicAdd(&prm.rho[id], Wij * mi);
+        }
+        atomicAdd(&prm.rho[qi], acc);
+    }
+    if (prm.rho && prm.veldens_k > 0) {
+        const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
+        const Vec4<S> vi = V[qi];
+        const double delta = 2.0 / (double)(prm.kernres - 1);
+        const int kv = min(prm.veldens_k, cnt);
+        double rho = 0;
+        if (kv == cnt) {
+            // every spatial neighbour is used: h from the largest velocity distance, then the sum (two passes)
+            double vmax = 0;
+            for (int s = 0; s < cnt; s++) {
+                Vec4<S> vj = V[c2.L[s * 32 + lane]];
+                vmax = fmax(vmax, sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)));
+            }
+            const double hi = 0.5 * vmax;
+            const double norm = 1.0 / pow(hi, 3.0);
+            for (int s = 0; s < cnt; s++) {
+                Vec4<S> vj = V[c2.L[s * 32 + lane]];
+                double r = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)) / hi;
+                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+            }
+        } else if (kv > 0) {
+            // kv < kx: exact fp64 selection on a per-lane array of doubles placed after the list (want_doubles layout)
+            double* D = reinterpret_cast<double*>(base + (size_t)k * 32 * 4);
+            for (int s = 0; s < cnt; s++) {
+                Vec4<S> vj = V[c2.L[s * 32 + lane]];
+                D[s * 32 + lane] = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
+            }
+            auto dsift = [&](int p, int n, double d) {
+                while (true) {
+                    int c = 2 * p + 1;
+                    if (c >= n) break;
+                    double dc = D[c * 32 + lane];
+                    if (c + 1 < n) { double dr = D[(c + 1) * 32 + lane]; if (dr > dc) { c = c + 1; dc = dr; } }
+                    if (d >= dc) break;
+                    D[p * 32 + lane] = dc;
+                    p = c;
+                }
+                D[p * 32 + lane] = d;
+            };
+            for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, D[p * 32 + lane]);
+            for (int s = kv; s < cnt; s++) {
+                double vd = D[s * 32 + lane];
+                if (vd < D[lane]) dsift(0, kv, vd);
+            }
+            const double hi = 0.5 * D[lane];
+            const double norm = 1.0 / pow(hi, 3.0);
+            for (int e = kv; e > 0; e--) {
+                double r = D[lane] / hi;
+                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+                dsift(0, e - 1, D[(e - 1) * 32 + lane]);
+            }
+        }
+        prm.rho[qi] = rho;
+    }
+}
+
 static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.nlo = t.nlo; p.nhi = t.nhi; p.bucket = t.bucket;
     p.P = t.prim; p.V = t.vel4(); p.mass = t.mass; p.order = t.order;
@@ -593,7 +886,16 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     if (smooth_only && getenv("NBK_KNN_EXACT_ONLY") == nullptr) {
         // ---- fast path + exact fallback for the flagged queries ----------------------------------------------
         p.kcap = a.k + 1;
-        size_t warp_bytes = fast_warp_bytes(p.kcap);
+        const char* em = getenv("NBK_KNN_MODE");
+        const int mode = em ? atoi(em) : 1;     // 1: select-then-collect (default), 0: (key,index) heap
+        // nodes of up to `leaf` particles are scanned as one tile: fewer node tests and better balanced insertion rounds
+        {
+            const char* e = getenv("NBK_KNN_LEAF");
+            int leaf = e ? atoi(e) : 32;
+            if (leaf > p.bucket) p.bucket = leaf;
+        }
+        const int want_doubles = (a.veldens_k > 0 && a.veldens_k < a.k) ? 1 : 0;
+        size_t warp_bytes = mode == 1 ? sc_warp_bytes(a.k, want_doubles) : fast_warp_bytes(p.kcap);
         size_t smem = warp_bytes * KNN_WARPS;
         NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");
         DevBuf<int> fcount(1);
@@ -601,7 +903,15 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
         NBK_CHECK(cudaMemsetAsync(fcount.p, 0, sizeof(int), t.stream));
         p.flag_count = fcount.p; p.flag_list = flist.p;
         int blocks = div_up((rows + 31) / 32, KNN_WARPS);
-        if (t.store_bytes == 4) {
+        if (mode == 1) {
+            if (t.store_bytes == 4) {
+                NBK_CHECK(cudaFuncSetAttribute(knn_sc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                knn_sc_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles);
+            } else {
+                NBK_CHECK(cudaFuncSetAttribute(knn_sc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                knn_sc_kernel<double><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles);
+            }
+        } else if (t.store_bytes == 4) {
             NBK_CHECK(cudaFuncSetAttribute(knn_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             knn_fast_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
         } else {
@@ -609,6 +919,18 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             knn_fast_kernel<double><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
         }
         NBK_CHECK(cudaGetLastError());
+#ifdef NBK_STATS
+        {
+            unsigned long long h[8];
+            NBK_CHECK(cudaStreamSynchronize(t.stream));
+            NBK_CHECK(cudaMemcpyFromSymbol(h, g_stats, sizeof(h)));
+            double g = (double)((rows + 31) / 32);
+            fprintf(stderr, "[nbk stats] per warp: tiles %.1f cand %.1f rounds %.1f ; per lane: accepted-bits %.1f sifts %.1f\n",
+                    h[0] / g, h[1] / g, h[2] / g, h[4] / (double)rows, h[3] / (double)rows);
+            unsigned long long z[8] = {0};
+            NBK_CHECK(cudaMemcpyToSymbol(g_stats, z, sizeof(z)));
+        }
+#endif
         t.last_launches += 2;
         int nflag = 0;
         NBK_CHECK(cudaMemcpyAsync(&nflag, fcount.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
