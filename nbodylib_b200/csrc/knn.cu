@@ -574,21 +574,33 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_fast_kernel(KnnParams prm)
 //             over the appended candidates.
 //   epilogue: SPH sums over the list, as before.
 struct KeyHeap4 {
-    float4* K4;   // [G+1][32]
+    unsigned char* kb;   // this lane's byte base inside the [G+1][32] float4 groups (group g of the lane at kb + g*512)
     int G;
-    unsigned lane;
-    __device__ __forceinline__ float* keyp(int p) const { return reinterpret_cast<float*>(K4 + (((p + 3) >> 2) * 32 + lane)) + ((p + 3) & 3); }
-    __device__ __forceinline__ float rootkey() const { return *keyp(0); }
-    __device__ __forceinline__ void sift(int p, float xk) {
+    // key of node p: group (p+3)>>2, component (p+3)&3 ; children of p = the four components of group p+1
+    __device__ __forceinline__ float* keyp(int p) const { return reinterpret_cast<float*>(kb + ((p + 3) >> 2) * 512 + ((p + 3) & 3) * 4); }
+    __device__ __forceinline__ float rootkey() const { return *reinterpret_cast<const float*>(kb + 12); }
+    // place xk at node p and sift it down; returns the key that ends up at node p
+    __device__ __forceinline__ float sift(int p, float xk) {
+        unsigned char* pa = reinterpret_cast<unsigned char*>(keyp(p));
+        unsigned char* ga = kb + (p + 1) * 512;
+        float at_p = xk;
+        bool moved = false;
         while (p < G) {
-            const float4 ck = K4[(p + 1) * 32 + lane];
-            const float m = fmaxf(fmaxf(ck.x, ck.y), fmaxf(ck.z, ck.w));
+            const float4 ck = *reinterpret_cast<const float4*>(ga);
+            const bool a = ck.x >= ck.y, b = ck.z >= ck.w;
+            const float m01 = a ? ck.x : ck.y, m23 = b ? ck.z : ck.w;
+            const bool c = m01 >= m23;
+            const float m = c ? m01 : m23;
             if (xk >= m) break;
-            const int j = (ck.x == m) ? 0 : ((ck.y == m) ? 1 : ((ck.z == m) ? 2 : 3));
-            *keyp(p) = m;
+            const int j = c ? (a ? 0 : 1) : (b ? 2 : 3);
+            *reinterpret_cast<float*>(pa) = m;
+            if (!moved) { at_p = m; moved = true; }
+            pa = ga + 4 * j;
             p = 4 * p + 1 + j;
+            ga = kb + (p + 1) * 512;
         }
-        *keyp(p) = xk;
+        *reinterpret_cast<float*>(pa) = xk;
+        return at_p;
     }
 };
 
@@ -598,29 +610,29 @@ struct SelectVisitor {
     double* tile;
     KeyHeap4 hp;
     double qx, qy, qz;
-    double topd;
+    double topd;        // (double) of the heap-top key; 0 for lanes without a query (nothing is ever accepted)
     float topf;
-    int self, r0, r1;
+    int r0, r1;         // tree-index range bulk-loaded into the heap (skipped during the traversal)
     unsigned lane;
     __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
-    __device__ __forceinline__ void settop() { topf = hp.rootkey(); topd = (double)topf; }
+    __device__ __forceinline__ void settop(float k) { topf = k; topd = (double)k; }
     template <bool OVERLAP>
     __device__ __forceinline__ void scan_tile(int first, int m) {
+        // pass 1: one compare per candidate (the query itself and coincident particles have d2 == 0 and are weeded out in
+        // pass 2, like bulk-loaded candidates); pass 2: serial insertion rounds over the set bits
         unsigned acc = 0;
 #pragma unroll 4
         for (int j = 0; j < m; j++) {
-            const int c = first + j;
             double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-            bool ok = d2 < topd && d2 > 0.0 && c != self;
-            if (OVERLAP) ok = ok && (c < r0 || c >= r1);
-            acc |= (ok ? 1u : 0u) << j;
+            acc |= (d2 < topd ? 1u : 0u) << j;
         }
         while (__any_sync(0xffffffffu, acc != 0)) {
             if (acc) {
-                int j = __ffs(acc) - 1;
+                const int j = __ffs(acc) - 1;
                 acc &= acc - 1;
+                const int c = first + j;
                 double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-                if (d2 < topd) { hp.sift(0, __double2float_rn(d2)); settop(); }
+                if (d2 < topd && d2 > 0.0 && (!OVERLAP || c < r0 || c >= r1)) settop(hp.sift(0, __double2float_rn(d2)));
             }
         }
     }
@@ -645,12 +657,12 @@ template <class S>
 struct CollectVisitor {
     const Vec4<S>* P;
     double* tile;
-    int* L;            // [k][32] index list
+    int* L;            // this lane's column of the [k][32] index list (entry s at L[s*32])
     double qx, qy, qz;
     double d2max;
     double thr_d;      // candidates with d2 >= thr_d cannot qualify (cheap fp64 pre-test)
     float thr;         // qualify iff RN_fp32(d2) <= thr ; -1 for lanes that collect nothing
-    int self, cnt, cap;
+    int cnt, cap;
     unsigned lane;
     __device__ __forceinline__ bool need(float lb) const { return lb <= thr; }
     __device__ __forceinline__ void leaf(int start, int n) {
@@ -662,14 +674,22 @@ struct CollectVisitor {
                 tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
             }
             __syncwarp();
+            unsigned acc = 0;
 #pragma unroll 4
             for (int j = 0; j < m; j++) {
-                const int c = start + base + j;
                 double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-                if (d2 < thr_d && d2 > 0.0 && c != self && __double2float_rn(d2) <= thr && cnt < cap) {
-                    L[cnt * 32 + lane] = c;
-                    cnt++;
-                    d2max = fmax(d2max, d2);
+                acc |= (d2 < thr_d ? 1u : 0u) << j;
+            }
+            while (__any_sync(0xffffffffu, acc != 0)) {
+                if (acc) {
+                    const int j = __ffs(acc) - 1;
+                    acc &= acc - 1;
+                    double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+                    if (d2 > 0.0 && __double2float_rn(d2) <= thr && cnt < cap) {
+                        L[cnt * 32] = start + base + j;
+                        cnt++;
+                        d2max = fmax(d2max, d2);
+                    }
                 }
             }
         }
@@ -713,8 +733,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
     {
         SelectVisitor<S> v;
         v.P = P; v.tile = tile; v.lane = lane;
-        v.hp.K4 = reinterpret_cast<float4*>(base); v.hp.G = G; v.hp.lane = lane;
-        v.self = valid ? (int)qi : -1;
+        v.hp.kb = base + lane * 16; v.hp.G = G;
+        const int self = valid ? (int)qi : -1;
         v.qx = x0; v.qy = y0; v.qz = z0;
         int64_t want = (int64_t)kcap;
         int64_t r0 = g0 + 16 - want / 2;
@@ -734,12 +754,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
             __syncwarp();
             for (int j = 0; j < m; j++) {
                 double d2 = dist2_ref(x0, y0, z0, tile[j], tile[32 + j], tile[64 + j]);
-                if (valid && (int)(b0 + j) != v.self && d2 > 0.0) { *v.hp.keyp(filled) = __double2float_rn(d2); filled++; }
+                if (valid && (int)(b0 + j) != self && d2 > 0.0) { *v.hp.keyp(filled) = __double2float_rn(d2); filled++; }
             }
         }
         for (; filled < NN; filled++) *v.hp.keyp(filled) = (valid && filled < kcap) ? __uint_as_float(FKEY_INF) : 0.f;
         for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p));
-        v.settop();
+        v.settop(v.hp.rootkey());
         traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
         key_kp1 = v.hp.rootkey();
         v.hp.sift(0, 0.f);
@@ -755,9 +775,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
 
     // --------------------------------------------------------------------------------------------- collect
     CollectVisitor<S> c2;
-    c2.P = P; c2.tile = tile; c2.L = reinterpret_cast<int*>(base); c2.lane = lane;
+    c2.P = P; c2.tile = tile; c2.L = reinterpret_cast<int*>(base) + lane; c2.lane = lane;
     c2.qx = x0; c2.qy = y0; c2.qz = z0;
-    c2.self = valid ? (int)qi : -1;
     c2.cnt = 0; c2.cap = k; c2.d2max = 0;
     c2.thr = (valid && !flagged) ? key_k : -1.f;
     c2.thr_d = (valid && !flagged) ? (double)__uint_as_float(__float_as_uint(key_k) + (short_of_k ? 0u : 1u)) : -1.0;   // next float above key_k
@@ -777,7 +796,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
         const double mi = prm.mass[qi];
         double acc = 0;
         for (int s = 0; s < cnt; s++) {
-            int id = c2.L[s * 32 + lane];
+            int id = c2.L[s * 32];
             Vec4<S> c = P[id];
             double rij = sqrt(dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z));
             double r = rij / hi;
@@ -797,13 +816,13 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
             // every spatial neighbour is used: h from the largest velocity distance, then the sum (two passes)
             double vmax = 0;
             for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[c2.L[s * 32 + lane]];
+                Vec4<S> vj = V[c2.L[s * 32]];
                 vmax = fmax(vmax, sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)));
             }
             const double hi = 0.5 * vmax;
             const double norm = 1.0 / pow(hi, 3.0);
             for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[c2.L[s * 32 + lane]];
+                Vec4<S> vj = V[c2.L[s * 32]];
                 double r = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)) / hi;
                 rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
             }
@@ -811,7 +830,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
             // kv < kx: exact fp64 selection on a per-lane array of doubles placed after the list (want_doubles layout)
             double* D = reinterpret_cast<double*>(base + (size_t)k * 32 * 4);
             for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[c2.L[s * 32 + lane]];
+                Vec4<S> vj = V[c2.L[s * 32]];
                 D[s * 32 + lane] = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
             }
             auto dsift = [&](int p, int n, double d) {
