@@ -131,6 +131,11 @@ int nbk_ball_points(nbk_tree* t, double fdist2, int64_t m, const double* x, int6
 /* Replaces KDTree::CalcDensity(Nsmooth) (KDCalcSmoothQuantities.cxx:203-305).  rho[n] by ID
  * (or tree index with NBK_TREE_ORDER); hsm (optional) = 0.5*sqrt(d2_k), the smoothing scale. */
 int nbk_calc_density(nbk_tree* t, int nsmooth, double* rho, double* hsm, int flags);
+/* Same, restricted to the query particles whose `active` byte (n entries, by ID or tree index like rho) is non-zero.
+ * Inactive particles still act as neighbours and still receive the scatter term of the active ones; their own
+ * gather+scatter contribution is left out.  This is what a slab-sharded caller needs: queries for owned particles
+ * only, ghost particles as pure neighbours (nbodylib_b200/sharded.py). */
+int nbk_calc_density_subset(nbk_tree* t, int nsmooth, const uint8_t* active, double* rho, double* hsm, int flags);
 /* Replaces KDTree::CalcVelDensity(Nsmooth, Nsearch) (KDCalcSmoothQuantities.cxx:309-389). */
 int nbk_calc_veldensity(nbk_tree* t, int nsmooth, int nsearch, double* rho, int flags);
 /* "CalcSmoothingScale" (named by the north star; = hi of KDCalcSmoothQuantities.cxx:260). */

@@ -38,7 +38,7 @@ DEVICE_PTRS, TREE_ORDER, STRICT_PERIODIC, KNN_TREE_FORM, STORE_F64, STORE_F32, O
 EXPORTS = [
     "nbk_last_error", "nbk_device_count", "nbk_create", "nbk_destroy", "nbk_get_info", "nbk_get_order",
     "nbk_get_kernel_table", "nbk_get_nodes", "nbk_knn_particles", "nbk_knn_points", "nbk_ball_particles",
-    "nbk_ball_points", "nbk_calc_density", "nbk_calc_veldensity", "nbk_smoothing_scale", "nbk_fof",
+    "nbk_ball_points", "nbk_calc_density", "nbk_calc_density_subset", "nbk_calc_veldensity", "nbk_smoothing_scale", "nbk_fof",
     "nbk_fof_criterion", "nbk_device_arrays", "nbk_release_cached_memory",
 ]
 
@@ -68,6 +68,7 @@ def load():
     L.nbk_ball_particles.argtypes = [vp, dbl, i64, vp, vp, vp, i64, C.POINTER(i64), i32]
     L.nbk_ball_points.argtypes = [vp, dbl, i64, vp, vp, vp, i64, C.POINTER(i64), i32]
     L.nbk_calc_density.argtypes = [vp, i32, vp, vp, i32]
+    L.nbk_calc_density_subset.argtypes = [vp, i32, vp, vp, vp, i32]
     L.nbk_calc_veldensity.argtypes = [vp, i32, i32, vp, i32]
     L.nbk_smoothing_scale.argtypes = [vp, i32, vp, i32]
     L.nbk_fof.argtypes = [vp, dbl, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]

@@ -74,6 +74,10 @@ __global__ void scatter_i32_kernel(int64_t n, const int32_t* order, const int32_
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[order[i]] = src[i];
 }
+__global__ void gather_u8_kernel(int64_t n, const int32_t* order, const uint8_t* src, uint8_t* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[order[i]];
+}
 __global__ void gather_i32_kernel(int64_t n, const int32_t* order, const int32_t* src, int32_t* dst) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[order[i]];
@@ -468,7 +472,7 @@ static void deliver_i32(nbk_tree* t, const int32_t* src_tree, int32_t* dst, int 
     NBK_CHECK(cudaStreamSynchronize(t->stream));
 }
 
-static void smooth_call(nbk_tree* t, int k, int veldens_k, double* rho, double* hsm, int flags) {
+static void smooth_call(nbk_tree* t, int k, int veldens_k, double* rho, double* hsm, int flags, const uint8_t* active = nullptr) {
     require_knn_tree(t);
     NBK_REQUIRE(t->treetype == NBK_TPHYS || veldens_k == 0, NBK_ERR_UNSUPPORTED, "CalcVelDensity needs a physical tree");
     NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
@@ -479,6 +483,22 @@ static void smooth_call(nbk_tree* t, int k, int veldens_k, double* rho, double* 
     a.k = k; a.mode = 0; a.q0 = 0; a.q1 = n;
     a.periodic = false;                       // quirk Q2: all Calc* searches ignore the period (KDCalcSmoothQuantities.cxx:227,338)
     a.rho = rho ? drho.p : nullptr; a.hsm = hsm ? dh.p : nullptr; a.veldens_k = veldens_k;
+    DevBuf<uint8_t> dact, dact_tree;
+    if (active) {
+        const uint8_t* src = active;
+        if (!(flags & NBK_DEVICE_PTRS)) {
+            dact.alloc(n);
+            NBK_CHECK(cudaMemcpyAsync(dact.p, active, (size_t)n, cudaMemcpyHostToDevice, t->stream));
+            src = dact.p;
+        }
+        if (flags & NBK_TREE_ORDER) a.active = src;
+        else {
+            dact_tree.alloc(n);
+            gather_u8_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, src, dact_tree.p);
+            a.active = dact_tree.p;
+        }
+    }
+    if (hsm) NBK_CHECK(cudaMemsetAsync(dh.p, 0, dh.bytes(), t->stream));
     CallTimer tm(*t);
     if (rho) NBK_CHECK(cudaMemsetAsync(drho.p, 0, drho.bytes(), t->stream));
     NBK_CHECK(cudaEventRecord(t->ev2, t->stream));
@@ -496,6 +516,12 @@ int nbk_calc_density(nbk_tree* t, int nsmooth, double* rho, double* hsm, int fla
     NBK_API_BEGIN
     NBK_REQUIRE(t && rho, NBK_ERR_ARG, "nbk_calc_density: null argument");
     smooth_call(t, nsmooth, 0, rho, hsm, flags);
+    NBK_API_END
+}
+int nbk_calc_density_subset(nbk_tree* t, int nsmooth, const uint8_t* active, double* rho, double* hsm, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && rho && active, NBK_ERR_ARG, "nbk_calc_density_subset: null argument");
+    smooth_call(t, nsmooth, 0, rho, hsm, flags, active);
     NBK_API_END
 }
 int nbk_calc_veldensity(nbk_tree* t, int nsmooth, int nsearch, double* rho, int flags) {

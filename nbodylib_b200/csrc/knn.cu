@@ -50,6 +50,7 @@ struct KnnParams {
     double* rho; double* hsm; int veldens_k;
     const double* kern; int kernres;
     int* flag_count; int32_t* flag_list;              // fast kernel: queries that need the exact kernel
+    const uint8_t* active;                            // optional query mask (tree order)
 };
 
 // ================================================================================================ exact
@@ -152,12 +153,15 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
     hp.k = prm.kcap; hp.lane = lane;
 
     const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
+    // explicit query lists (the fast kernels' fallback) hold scattered particles: one query per warp (lane 0) keeps each
+    // warp's traversal short instead of serialising 32 unrelated searches
     const int64_t nrows = prm.qlist ? prm.nq : (prm.q1 - prm.q0);
     const int64_t group = (int64_t)blockIdx.x * KNN_WARPS + w;
-    const int64_t row = group * 32 + lane;
-    if (group * 32 >= nrows) return;                 // whole warp out of range
-    const bool valid = row < nrows;
+    const int64_t row = prm.qlist ? group : group * 32 + lane;
+    if ((prm.qlist ? group : group * 32) >= nrows) return;                 // whole warp out of range
+    bool valid = prm.qlist ? (lane == 0) : (row < nrows);
     const int64_t qi = valid ? (prm.qlist ? (int64_t)prm.qlist[row] : prm.q0 + row) : 0;
+    if (valid && prm.active && prm.mode == 0 && !prm.qlist && !prm.active[qi]) valid = false;
 
     KnnVisitor<S> v;
     v.P = P; v.tile = tile; v.hp = hp; v.lane = lane;
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_fast_kernel(KnnParams prm)
     const int64_t g0 = prm.q0 + group * 32;
     if (g0 >= prm.q1) return;
     const int64_t qi = g0 + lane;
-    const bool valid = qi < prm.q1;
+    const bool valid = qi < prm.q1 && (!prm.active || prm.active[qi]);
 
     FastVisitor<S> v;
     v.P = P; v.tile = tile; v.hp = hp; v.lane = lane;
@@ -723,7 +727,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
     const int64_t g0 = prm.q0 + group * 32;
     if (g0 >= prm.q1) return;
     const int64_t qi = g0 + lane;
-    const bool valid = qi < prm.q1;
+    const bool valid = qi < prm.q1 && (!prm.active || prm.active[qi]);
     double x0 = 0, y0 = 0, z0 = 0;
     if (valid) { Vec4<S> c = P[qi]; x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z; }
     const QueryBox qb = make_qbox(x0, y0, z0);
@@ -875,13 +879,14 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.rho = a.rho; p.hsm = a.hsm; p.veldens_k = a.veldens_k;
     p.kern = t.d_kernel; p.kernres = t.kernres;
     p.flag_count = nullptr; p.flag_list = nullptr;
+    p.active = a.active;
 }
 
 static void run_exact(nbk_tree& t, KnnParams& p, int64_t rows) {
     size_t warp_bytes = (size_t)p.kcap * 32 * 12 + 96 * 8 + TRAV_STACK * 4;
     size_t smem = warp_bytes * KNN_WARPS;
     NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps (max ~145 at 4 warps/CTA)");
-    int blocks = div_up((rows + 31) / 32, KNN_WARPS);
+    int blocks = p.qlist ? div_up(rows, KNN_WARPS) : div_up((rows + 31) / 32, KNN_WARPS);
     if (t.store_bytes == 4) {
         NBK_CHECK(cudaFuncSetAttribute(knn_exact_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_exact_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);

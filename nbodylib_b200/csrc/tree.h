@@ -65,6 +65,7 @@ struct KnnArgs {
     bool out_ids = false;
     double* rho = nullptr;     // density accumulators, tree order (atomic adds), pre-zeroed
     double* hsm = nullptr;     // smoothing scale, tree order
+    const uint8_t* active = nullptr;  // device, tree order, optional: only these particles are queries
     int veldens_k = 0;         // >0: CalcVelDensity with Nsmooth=veldens_k, Nsearch=k; rho gets the value (no atomics)
 };
 void launch_knn(nbk_tree& t, const KnnArgs& a);

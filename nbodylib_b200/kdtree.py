@@ -202,6 +202,13 @@ class KDTree:
         L.check(self._lib.nbk_calc_density(self._h, int(Nsmooth), _ptr(rho), _ptr(h), 0))
         return (rho, h) if want_h else rho
 
+    def CalcDensitySubset(self, Nsmooth, active, rho_out, hsm_out=None):
+        """CalcDensity restricted to the query particles with active[id] != 0 (uint8); ghosts act as neighbours only.
+        active / rho_out / hsm_out: torch CUDA tensors (device pointers) or numpy arrays, all indexed by ID."""
+        flags = L.DEVICE_PTRS if _is_torch(rho_out) else 0
+        L.check(self._lib.nbk_calc_density_subset(self._h, int(Nsmooth), _ptr(active), _ptr(rho_out), _ptr(hsm_out), flags))
+        return rho_out
+
     def CalcVelDensity(self, Nsmooth=64, Nsearch=64, out=None):
         """KDTree::CalcVelDensity (KDCalcSmoothQuantities.cxx:309-389)."""
         if out is not None:

@@ -1,0 +1,342 @@
+"""Slab-sharded driver for the kd-tree hot path: one process per GPU, `torch.distributed` for the plumbing
+(NCCL over NVLink on a B200 box; gloo in the CPU tests of the host logic), the CUDA kernels for all the work.
+
+The reference has no distributed code: VELOCIraptor does its own MPI domain decomposition and
+builds one local `KDTree` per rank.  This module is the B200 replacement for that outer layer on one node:
+
+* **Decomposition.**  The global box is cut into `world` slabs along x; rank r owns the particles with
+  x in [r, r+1) * Lx / world.  Nothing is ever gathered on one rank.
+* **Halo exchange** (the only data-path communication of the density pass): each rank sends the particles within
+  `h` of a slab face to the neighbour across that face (`batch_isend_irecv`, one message per face and direction,
+  x shifted by +-Lx across the periodic wrap when the caller asks for it) and builds ONE local tree over
+  owned + ghost particles.
+* **kNN-density** (`CalcDensity`): queries run for owned particles only (`nbk_calc_density_subset`), ghosts are
+  pure neighbours.  The symmetric scatter term that owned queries deposit on ghosts is sent back to the owners over
+  the same faces and added there, so every pair contributes exactly once -- the result equals the single-tree
+  result.  The halo must contain every owned particle's k-th neighbour ball: after the pass, r_k = 2 h_sm is
+  checked against (distance to the interior face + h); if any rank sees a violation (all-reduce) the halo is
+  widened and the pass repeated.  `Calc*` never wrap (reference quirk Q2), so no ghosts cross the box edge.
+* **FOF**: local union-find over owned + ghosts with halo width just above the linking length (periodic wrap in x
+  through the ghosts, in y/z by the tree).  A ghost's local label and its owner's label for the same particle are
+  one cross-slab edge; edges and the owned sizes of the labels they touch are all-gathered and every rank runs
+  the same small union over boundary labels, then the `minnum` filter and one global numbering (by decreasing
+  size when `order`) are applied.
+
+The per-rank compute engine is pluggable (`engine=`): the product uses `nbodylib_b200.KDTree` (CUDA); the gloo
+tests inject a brute-force engine so the exchange / merge logic is checked without a GPU.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+BIG_PERIOD_FACTOR = 1.0e6
+
+
+class CudaEngine:
+    """Local compute on this rank's GPU through the C ABI."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def build(self, pos, vel, mass, period):
+        from .kdtree import KDTree
+        return KDTree(pos, vel, mass, Period=period, device=self.device)
+
+    def density(self, tree, k, active_u8, rho, hsm):
+        tree.CalcDensitySubset(k, active_u8, rho, hsm)
+        return tree.info
+
+    def fof_labels(self, tree, ll, out):
+        """labels 1..ng for every particle (minnum = 1), by ID"""
+        _, ng = tree.FOF(ll, 1, 0, out=out)
+        return ng
+
+
+class ShardedTree:
+    def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=None, slab_local=True, halo=None,
+                 knn_k=64, engine=None, group=None):
+        """pos/vel/mass: this rank's particles (torch tensors on the rank's device).
+        slab_local=True : `pos` is given in slab-local coordinates [0,1)^3 (each rank generated its own unit box,
+                          the bench's weak-scaling set-up); the global box is [0,world) x [0,1) x [0,1).
+        slab_local=False: `pos` holds global coordinates inside this rank's slab of `box` = (Lx, Ly, Lz).
+        period: None or anything truthy -> the global box is periodic (FOF only; Calc* never wrap)."""
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.group = group
+        self.dev = pos.device
+        self.f = torch.float64
+        self.n_owned = int(pos.shape[0])
+        self.periodic = period is not None
+        W = self.world
+        if slab_local:
+            self.box = np.array([float(W), 1.0, 1.0])
+            gpos = pos.to(self.f).clone()
+            gpos[:, 0] += float(self.rank)
+        else:
+            self.box = np.asarray(box, dtype=np.float64)
+            gpos = pos.to(self.f)
+        self.x0 = self.box[0] * self.rank / W
+        self.x1 = self.box[0] * (self.rank + 1) / W
+        self.pos = gpos.contiguous()
+        self.vel = None if vel is None else vel.to(self.f).contiguous()
+        self.mass = (torch.ones(self.n_owned, dtype=self.f, device=self.dev) if mass is None else mass.to(self.f)).contiguous()
+        counts = torch.zeros(W, dtype=torch.int64, device=self.dev)
+        counts[self.rank] = self.n_owned
+        if W > 1:
+            dist.all_reduce(counts, group=group)
+        self.gid0 = int(counts[:self.rank].sum().item())
+        self.n_global = int(counts.sum().item())
+        self.engine = engine if engine is not None else CudaEngine(self.dev.index if self.dev.type == "cuda" else 0)
+        self.left, self.right = (self.rank - 1) % W, (self.rank + 1) % W
+        # halo for the k-NN ball: a few times the radius that holds k particles at the slab's mean density
+        vol = (self.x1 - self.x0) * self.box[1] * self.box[2]
+        self.h_knn = float(halo) if halo is not None else 2.5 * (knn_k * vol / max(self.n_owned, 1) / (4.0 * np.pi / 3.0)) ** (1.0 / 3.0)
+        self._dens = None       # cached (tree, halo, ghost bookkeeping) for the density pass
+        self.last_info = None
+        self.stats = {}
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def _cols(self, idx, shift):
+        c = [self.pos[idx]]
+        if shift != 0.0:
+            c[0] = c[0].clone()
+            c[0][:, 0] += shift
+        c.append(self.vel[idx] if self.vel is not None else torch.zeros((len(idx), 3), dtype=self.f, device=self.dev))
+        c.append(self.mass[idx][:, None])
+        c.append((idx + self.gid0).to(self.f)[:, None])
+        return torch.cat(c, dim=1).contiguous()
+
+    def _sendrecv(self, to_left, to_right):
+        """Exchange one tensor with each face neighbour; returns (from_left, from_right).  Shapes [m, C]."""
+        W = self.world
+        C = to_left.shape[1]
+        cnt = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=self.dev)
+        table = [torch.zeros(2, dtype=torch.int64, device=self.dev) for _ in range(W)]
+        dist.all_gather(table, cnt, group=self.group)
+        n_from_left = int(table[self.left][1].item())     # what my left neighbour sends to its right
+        n_from_right = int(table[self.right][0].item())
+        buf_l = torch.empty((n_from_left, C), dtype=to_left.dtype, device=self.dev)
+        buf_r = torch.empty((n_from_right, C), dtype=to_left.dtype, device=self.dev)
+        # order matters when left == right (world 2): the peer posts [from_left, from_right], which must match my
+        # [to_right, to_left]
+        ops = []
+        if to_right.numel():
+            ops.append(dist.P2POp(dist.isend, to_right, self.right, self.group))
+        if to_left.numel():
+            ops.append(dist.P2POp(dist.isend, to_left, self.left, self.group))
+        if buf_l.numel():
+            ops.append(dist.P2POp(dist.irecv, buf_l, self.left, self.group))
+        if buf_r.numel():
+            ops.append(dist.P2POp(dist.irecv, buf_r, self.right, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return buf_l, buf_r
+
+    def _halo(self, h, wrap):
+        """Send the particles within h of each face; returns ghost table [m,8] and bookkeeping to send data back."""
+        W, Lx = self.world, self.box[0]
+        x = self.pos[:, 0]
+        send_l = torch.nonzero(x < self.x0 + h).flatten()
+        send_r = torch.nonzero(x >= self.x1 - h).flatten()
+        if not wrap:
+            if self.rank == 0:
+                send_l = send_l[:0]
+            if self.rank == W - 1:
+                send_r = send_r[:0]
+        shift_l = Lx if self.rank == 0 else 0.0          # my left neighbour sits at the far end of the box
+        shift_r = -Lx if self.rank == W - 1 else 0.0
+        from_l, from_r = self._sendrecv(self._cols(send_l, shift_l), self._cols(send_r, shift_r))
+        return {"send_l": send_l, "send_r": send_r, "from_l": from_l, "from_r": from_r, "h": h}
+
+    def _return_to_owners(self, halo, val_l, val_r):
+        """Inverse of _halo for one value per ghost: returns (values for my send_l particles, for my send_r)."""
+        back_l, back_r = self._sendrecv(val_l.contiguous(), val_r.contiguous())
+        # what comes back from my left neighbour concerns the particles I sent to the left, etc.
+        return back_l, back_r
+
+    # ------------------------------------------------------------------------------------------------- density
+    def _density_setup(self, k):
+        halo = self._halo(self.h_knn, wrap=False)
+        g = torch.cat([halo["from_l"], halo["from_r"]], dim=0)
+        pos = torch.cat([self.pos, g[:, 0:3]], dim=0).contiguous()
+        mass = torch.cat([self.mass, g[:, 6]], dim=0).contiguous()
+        n_all = pos.shape[0]
+        tree = self.engine.build(pos, None, mass, None)
+        active = torch.zeros(n_all, dtype=torch.uint8, device=self.dev)
+        active[:self.n_owned] = 1
+        self._dens = {"tree": tree, "halo": halo, "active": active, "n_all": n_all,
+                      "rho": torch.empty(n_all, dtype=self.f, device=self.dev), "hsm": torch.empty(n_all, dtype=self.f, device=self.dev)}
+        self.stats["ghosts_knn"] = int(n_all - self.n_owned)
+
+    def CalcDensity(self, Nsmooth=64, out=None, max_widen=6):
+        """Global KDTree::CalcDensity(Nsmooth) for this rank's owned particles (indexed like the rank's input)."""
+        for attempt in range(max_widen + 1):
+            if self._dens is None:
+                self._density_setup(Nsmooth)
+            d = self._dens
+            self.last_info = self.engine.density(d["tree"], Nsmooth, d["active"], d["rho"], d["hsm"])
+            n = self.n_owned
+            # does every owned k-ball stay inside owned + halo ?
+            x = self.pos[:, 0]
+            rk = 2.0 * d["hsm"][:n]
+            h = d["halo"]["h"]
+            bad = torch.zeros(n, dtype=torch.bool, device=self.dev)
+            if self.rank > 0:
+                bad |= rk > (x - self.x0) + h
+            if self.rank < self.world - 1:
+                bad |= rk > (self.x1 - x) + h
+            nbad = bad.sum().to(torch.int64)
+            dist.all_reduce(nbad, group=self.group)
+            if int(nbad.item()) == 0:
+                break
+            if attempt == max_widen:
+                raise RuntimeError("ShardedTree.CalcDensity: halo still too narrow after %d widenings" % max_widen)
+            self.h_knn *= 1.6
+            self.close_density()
+        # scatter terms deposited on ghosts go home
+        nl = d["halo"]["from_l"].shape[0]
+        gr = d["rho"][n:]
+        back_l, back_r = self._return_to_owners(d["halo"], gr[:nl, None], gr[nl:, None])
+        rho = d["rho"][:n].clone() if out is None else out
+        if out is not None:
+            out.copy_(d["rho"][:n])
+        if back_l.numel():
+            rho.index_add_(0, d["halo"]["send_l"], back_l[:, 0])
+        if back_r.numel():
+            rho.index_add_(0, d["halo"]["send_r"], back_r[:, 0])
+        return rho
+
+    def close_density(self):
+        if self._dens is not None:
+            t = self._dens["tree"]
+            if hasattr(t, "close"):
+                t.close()
+            self._dens = None
+
+    # ----------------------------------------------------------------------------------------------------- FOF
+    def FOF(self, fdist, minnum=8, order=0):
+        """Global KDTree::FOF(fdist, ., minnum, order) on the periodic (or open) box.  Returns (group id per owned
+        particle as int64 tensor, total number of groups).  Group ids are global: 1..ngroups, by decreasing size when
+        `order`, otherwise by (home rank, local label)."""
+        W, n = self.world, self.n_owned
+        halo = self._halo(fdist * (1.0 + 1e-9) + 1e-300, wrap=self.periodic)
+        g = torch.cat([halo["from_l"], halo["from_r"]], dim=0)
+        pos = torch.cat([self.pos, g[:, 0:3]], dim=0).contiguous()
+        n_all = pos.shape[0]
+        self.stats["ghosts_fof"] = int(n_all - n)
+        ext = float(self.x1 - self.x0 + 2 * fdist)
+        period = np.array([BIG_PERIOD_FACTOR * max(ext, self.box[0]), self.box[1], self.box[2]]) if self.periodic else None
+        tree = self.engine.build(pos, None, None, period)
+        lab = torch.empty(n_all, dtype=torch.int32, device=self.dev)
+        ng_local = self.engine.fof_labels(tree, fdist, lab)
+        self.last_info = getattr(tree, "info", None)
+        if hasattr(tree, "close"):
+            tree.close()
+        lab = lab.to(torch.int64)
+        sizes = torch.bincount(lab[:n], minlength=ng_local + 1)          # owned members only: ghosts are counted at home
+        # ---- cross-slab edges: my label of each ghost goes back to its owner --------------------------------------
+        nl = halo["from_l"].shape[0]
+        gl = lab[n:].to(self.f)
+        back_l, back_r = self._return_to_owners(halo, gl[:nl, None], gl[nl:, None])
+        e_mine = torch.cat([lab[halo["send_l"]], lab[halo["send_r"]]])
+        e_peer_rank = torch.cat([torch.full((len(halo["send_l"]),), self.left, dtype=torch.int64, device=self.dev),
+                                 torch.full((len(halo["send_r"]),), self.right, dtype=torch.int64, device=self.dev)])
+        e_peer = torch.cat([back_l[:, 0], back_r[:, 0]]).to(torch.int64)
+        edges = torch.stack([torch.full_like(e_mine, self.rank), e_mine, e_peer_rank, e_peer], dim=1)
+        edges = torch.unique(edges, dim=0) if edges.numel() else edges.reshape(0, 4)
+        # sizes of every label of mine that appears on either side of an edge: mine as source, or mine as a ghost
+        # label on the peer's side is covered by the peer's own edges (peer is the source there)
+        touched = torch.unique(torch.cat([e_mine, lab[n:]])) if (e_mine.numel() + (n_all - n)) else e_mine
+        node_tab = torch.stack([torch.full_like(touched, self.rank), touched, sizes[touched]], dim=1)
+        all_edges = self._allgather_rows(edges)
+        all_nodes = self._allgather_rows(node_tab)
+        # ---- replicated union over boundary labels (host, small) ----------------------------------------------------
+        E = all_edges.cpu().numpy()
+        Nn = all_nodes.cpu().numpy()
+        key = lambda r, l: r.astype(np.int64) * (1 << 40) + l.astype(np.int64)
+        nodes = np.unique(np.concatenate([key(Nn[:, 0], Nn[:, 1]), key(E[:, 0], E[:, 1]), key(E[:, 2], E[:, 3])])) if len(Nn) + len(E) else np.zeros(0, np.int64)
+        nsz = np.zeros(len(nodes), dtype=np.int64)
+        if len(Nn):
+            nsz[np.searchsorted(nodes, key(Nn[:, 0], Nn[:, 1]))] = Nn[:, 2]
+        parent = np.arange(len(nodes))
+        if len(E):
+            a = np.searchsorted(nodes, key(E[:, 0], E[:, 1]))
+            b = np.searchsorted(nodes, key(E[:, 2], E[:, 3]))
+            from scipy.sparse import coo_matrix
+            from scipy.sparse.csgraph import connected_components
+            m = coo_matrix((np.ones(len(a), dtype=np.int8), (a, b)), shape=(len(nodes), len(nodes)))
+            _, comp = connected_components(m, directed=False)
+            # representative = smallest node key in the component (deterministic on every rank)
+            order_ = np.argsort(comp, kind="stable")
+            first = np.r_[0, np.nonzero(np.diff(comp[order_]))[0] + 1]
+            rep_of_comp = np.minimum.reduceat(np.arange(len(nodes))[order_], first)
+            parent = rep_of_comp[np.searchsorted(comp[order_][first], comp)]
+        comp_size = np.bincount(parent, weights=nsz, minlength=len(nodes)).astype(np.int64)
+        # ---- group table: interior labels of this rank + boundary components homed here ------------------------------
+        my_nodes = (nodes >> 40) == self.rank
+        my_labels_in_nodes = (nodes[my_nodes] & ((1 << 40) - 1))
+        is_boundary = torch.zeros(ng_local + 1, dtype=torch.bool, device=self.dev)
+        if len(my_labels_in_nodes):
+            is_boundary[torch.from_numpy(my_labels_in_nodes).to(self.dev)] = True
+        interior_valid = (~is_boundary) & (sizes >= minnum)
+        interior_valid[0] = False
+        int_labels = torch.nonzero(interior_valid).flatten()
+        reps = np.nonzero((parent == np.arange(len(nodes))) & (comp_size >= minnum) & ((nodes >> 40) == self.rank))[0]
+        my_sizes = torch.cat([sizes[int_labels], torch.from_numpy(comp_size[reps]).to(self.dev)])
+        # global numbering
+        tab = torch.stack([my_sizes, torch.full_like(my_sizes, self.rank), torch.arange(len(my_sizes), device=self.dev)], dim=1)
+        all_tab = self._allgather_rows(tab).cpu().numpy()
+        ngroups = len(all_tab)
+        if order:
+            perm = np.lexsort((all_tab[:, 2], all_tab[:, 1], -all_tab[:, 0]))
+        else:
+            perm = np.lexsort((all_tab[:, 2], all_tab[:, 1]))
+        gid_of = np.empty(ngroups, dtype=np.int64)
+        gid_of[perm] = np.arange(1, ngroups + 1)
+        mine = np.nonzero(all_tab[:, 1] == self.rank)[0]
+        my_gid = gid_of[mine]                                      # aligned with my_sizes (allgather keeps row order)
+        # label -> global id
+        lut = torch.zeros(ng_local + 1, dtype=torch.int64, device=self.dev)
+        n_int = len(int_labels)
+        if n_int:
+            lut[int_labels] = torch.from_numpy(my_gid[:n_int]).to(self.dev)
+        # boundary components: every rank needs the id of components homed elsewhere -> gather (rep key, gid)
+        rep_tab = torch.from_numpy(np.stack([nodes[reps], my_gid[n_int:]], axis=1) if len(reps) else np.zeros((0, 2), np.int64)).to(self.dev)
+        all_rep = self._allgather_rows(rep_tab).cpu().numpy()
+        if len(my_labels_in_nodes):
+            node_idx = np.nonzero(my_nodes)[0]
+            rep_key = nodes[parent[node_idx]]
+            gid_b = np.zeros(len(node_idx), dtype=np.int64)
+            if len(all_rep):
+                srt = np.argsort(all_rep[:, 0])
+                pos_ = np.searchsorted(all_rep[srt, 0], rep_key)
+                pos_ = np.clip(pos_, 0, len(srt) - 1)
+                hit = all_rep[srt[pos_], 0] == rep_key
+                gid_b[hit] = all_rep[srt[pos_[hit]], 1]
+            lut[torch.from_numpy(my_labels_in_nodes).to(self.dev)] = torch.from_numpy(gid_b).to(self.dev)
+        return lut[lab[:n]], ngroups
+
+    def _allgather_rows(self, t):
+        """all-gather of [m_r, C] integer tables with different m_r; returns the concatenation in rank order."""
+        W = self.world
+        t = t.to(torch.int64).contiguous()
+        C = t.shape[1]
+        cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=self.dev)
+        cnts = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(W)]
+        dist.all_gather(cnts, cnt, group=self.group)
+        cnts = [int(c.item()) for c in cnts]
+        mx = max(max(cnts), 1)
+        pad = torch.zeros((mx, C), dtype=torch.int64, device=self.dev)
+        pad[:t.shape[0]] = t
+        bufs = [torch.zeros((mx, C), dtype=torch.int64, device=self.dev) for _ in range(W)]
+        dist.all_gather(bufs, pad, group=self.group)
+        return torch.cat([b[:c] for b, c in zip(bufs, cnts)], dim=0)
+
+    # ---------------------------------------------------------------------------------------------------- misc
+    @property
+    def info(self):
+        return self.last_info
+
+    def close(self):
+        self.close_density()
