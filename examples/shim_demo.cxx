@@ -1,0 +1,64 @@
+// examples/shim_demo.cxx -- a program written against the reference's NBody::KDTree interface (it mirrors what
+// reference src/tests/test_kdtree.cxx does: build, per-particle FindNearest, SearchBallPosTagged, FOF), compiled
+// against the shim header and linked with libnbk.so.  Prints a few invariants; exit code 0 on success.
+//   g++ -O2 -std=c++17 -Inbodylib_b200/shim examples/shim_demo.cxx -Lnbodylib_b200 -lnbk -Wl,-rpath,$PWD/nbodylib_b200 -o shim_demo
+#include <KDTree.h>
+
+#include <cmath>
+#include <cstdio>
+#include <random>
+using namespace NBody;
+
+int main() {
+    const Int_t N = 200000;
+    std::vector<Particle> parts(N);
+    std::mt19937_64 rng(4322);
+    std::uniform_real_distribution<double> U(0, 1);
+    std::normal_distribution<double> G(0, 1);
+    for (Int_t i = 0; i < N; i++) {
+        double c[3];
+        if (i % 10 == 0) { c[0] = U(rng); c[1] = U(rng); c[2] = U(rng); }
+        else { double cx = ((i % 100) + 0.5) / 100.0; c[0] = std::fmod(cx + 0.002 * G(rng) + 1, 1.0); c[1] = std::fmod(0.5 + 0.3 * std::sin(i % 100) + 0.002 * G(rng) + 1, 1.0); c[2] = std::fmod(0.5 + 0.002 * G(rng) + 1, 1.0); }
+        parts[i] = Particle(1.0, (float)c[0], (float)c[1], (float)c[2], (float)G(rng), (float)G(rng), (float)G(rng), i);
+        parts[i].SetPID(i);
+    }
+    Double_t period[3] = {1, 1, 1};
+    int bad = 0;
+    {
+        KDTree tree(parts.data(), N, 16, KDTree::TPHYS, KDTree::KEPAN, 1000, 0, 0, 0, period);
+        printf("nodes %d leaves %d kernnorm %.17g\n", tree.GetNumNodes(), tree.GetNumLeafNodes(), tree.GetKernNorm());
+        // the array is now in tree order, ids hold the input index
+        Int_t nn[16]; Double_t d2[16];
+        for (Int_t tt = 0; tt < N; tt += N / 7) {
+            tree.FindNearest(tt, nn, d2, 16);
+            for (int j = 0; j < 16; j++) {
+                double s = 0;
+                for (int k = 0; k < 3; k++) { double d = parts[tt].GetPosition(k) - parts[nn[j]].GetPosition(k); d -= std::round(d); s += d * d; }
+                if (std::fabs(s - d2[j]) > 1e-12 * (s + 1e-30) || nn[j] == tt || (j && d2[j] < d2[j - 1])) bad++;
+            }
+        }
+        std::vector<Int_t> tagged = tree.SearchBallPosTagged(N / 2, 0.01 * 0.01);
+        printf("ball: %zu particles\n", tagged.size());
+        tree.CalcDensity(32);
+        double mean = 0;
+        for (Int_t i = 0; i < N; i++) mean += parts[i].GetDensity();
+        printf("mean density %.6g\n", mean / N);
+        Int_t ng = 0;
+        Int_t* pfof = tree.FOF(0.2 / std::cbrt((double)N), ng, 20, 1);
+        long grouped = 0;
+        for (Int_t i = 0; i < N; i++) grouped += pfof[i] > 0;
+        printf("FOF: %d groups, %ld grouped\n", ng, grouped);
+        delete[] pfof;
+        Double_t params[10] = {0};
+        params[1] = params[6] = std::pow(0.2 / std::cbrt((double)N), 2); params[2] = params[7] = 1.0;
+        Int_t ng6 = 0;
+        Int_t* p6 = tree.FOFCriterion(FOF6d, params, ng6, 20);
+        printf("FOF6d: %d groups\n", ng6);
+        delete[] p6;
+        if (ng <= 0 || !(mean > 0)) bad++;
+    }
+    // destructor restored the input order
+    for (Int_t i = 0; i < N; i++) if (parts[i].GetID() != i || parts[i].GetPID() != i) { bad++; break; }
+    printf(bad ? "FAILED (%d)\n" : "shim demo ok\n", bad);
+    return bad ? 1 : 0;
+}

@@ -70,8 +70,12 @@ class ShardedTree:
         W = self.world
         if slab_local:
             self.box = np.array([float(W), 1.0, 1.0])
-            gpos = pos.to(self.f).clone()
+            # global x = fp32(x_local + rank): every rank sees the same fp32-representable global coordinates, so the
+            # local trees keep exact fp32 storage and ghosts are bit-identical copies of their owners' particles
+            gpos = pos.to(torch.float32).clone()
             gpos[:, 0] += float(self.rank)
+            gpos[:, 0] = torch.clamp(gpos[:, 0], max=float(np.nextafter(np.float32(self.rank + 1), np.float32(0))))
+            gpos = gpos.to(self.f)
         else:
             self.box = np.asarray(box, dtype=np.float64)
             gpos = pos.to(self.f)

@@ -266,3 +266,22 @@ def test_properties_at_scale(nb):
         assert np.all(rho > 0) and np.isfinite(rho).all()
         vol = (1.0 / rho).sum()
         assert 0.5 < vol < 2.0, vol
+
+
+def test_cxx_shim_program(built, tmp_path):
+    """A C++ program written against the reference's NBody::KDTree interface (examples/shim_demo.cxx, modelled on the
+    reference's src/tests/test_kdtree.cxx) compiles against nbodylib_b200/shim/KDTree.h, links libnbk.so and runs."""
+    import os
+    import shutil
+    import subprocess
+    from tests.util import ROOT
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    exe = str(tmp_path / "shim_demo")
+    lib = os.path.join(ROOT, "nbodylib_b200")
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-I" + os.path.join(lib, "shim"), os.path.join(ROOT, "examples", "shim_demo.cxx"),
+                           "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "shim demo ok" in out.stdout, out.stdout + out.stderr
+    assert "nodes 32767 leaves 16384" in out.stdout
