@@ -112,20 +112,28 @@ __global__ void __launch_bounds__(PRIM_THREADS) part_count_kernel(int level, int
                                                                   const uint32_t* __restrict__ o1, const uint32_t* __restrict__ o2,
                                                                   const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi,
                                                                   const int8_t* __restrict__ cutdim, const int32_t* __restrict__ pos_node,
-                                                                  const uint8_t* __restrict__ side, uint32_t* __restrict__ tsum, int ntiles) {
+                                                                  const uint8_t* __restrict__ side, uint32_t* __restrict__ tsum, int ntiles,
+                                                                  uint32_t* __restrict__ fbits) {
+    // also publishes every element's side flag as one bit (one 32-bit ballot per warp and round) so that the scatter
+    // kernel does not have to repeat the random side[] gather
     __shared__ uint32_t swarp[8];
     const int d = blockIdx.y;
     const uint32_t* o = d == 0 ? o0 : (d == 1 ? o1 : o2);
     const int F = (1 << level) - 1;
     int64_t base = (int64_t)blockIdx.x * PRIM_TILE;
+    const size_t words_per_dim = (size_t)ntiles * (PRIM_TILE / 32);
     uint32_t cnt = 0;
 #pragma unroll 4
     for (int r = 0; r < PRIM_ITEMS; r++) {
         int64_t i = base + r * PRIM_THREADS + threadIdx.x;
+        uint32_t f = 0;
         if (i < n) {
             PartNode pn = part_node(pos_node[i], F, bucket, nlo, nhi, cutdim);
-            if (pn.active) cnt += (pn.cd == d) ? ((int)i > pn.m ? 1u : 0u) : (uint32_t)side[o[i]];
+            if (pn.active) f = (pn.cd == d) ? ((int)i > pn.m ? 1u : 0u) : (uint32_t)side[o[i]];
         }
+        uint32_t b = __ballot_sync(0xffffffffu, f != 0);
+        if ((threadIdx.x & 31) == 0) fbits[(size_t)d * words_per_dim + (size_t)((base + r * PRIM_THREADS + threadIdx.x) >> 5)] = b;
+        cnt += f;
     }
     uint32_t tot;
     block_excl_scan_256(cnt, swarp, &tot);
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(PRIM_THREADS) part_scatter_kernel(int level, i
                                                                     uint32_t* __restrict__ n0, uint32_t* __restrict__ n1, uint32_t* __restrict__ n2,
                                                                     const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi,
                                                                     const int8_t* __restrict__ cutdim, const int32_t* __restrict__ pos_node,
-                                                                    const uint8_t* __restrict__ side, const uint32_t* __restrict__ tscan, int ntiles,
+                                                                    const uint32_t* __restrict__ fbits_all, const uint32_t* __restrict__ tscan, int ntiles,
                                                                     const uint32_t* __restrict__ Rb) {
     __shared__ uint32_t cnt[PRIM_ITEMS * 8];
     __shared__ uint32_t swarp[8];
@@ -149,17 +157,13 @@ __global__ void __launch_bounds__(PRIM_THREADS) part_scatter_kernel(int level, i
     int64_t base = (int64_t)blockIdx.x * PRIM_TILE;
     uint32_t bal[PRIM_ITEMS];
     uint32_t fbits = 0;
+    const size_t words_per_dim = (size_t)ntiles * (PRIM_TILE / 32);
 #pragma unroll
     for (int r = 0; r < PRIM_ITEMS; r++) {
-        int64_t i = base + r * PRIM_THREADS + threadIdx.x;
-        uint32_t f = 0;
-        if (i < n) {
-            PartNode pn = part_node(pos_node[i], F, bucket, nlo, nhi, cutdim);
-            if (pn.active) f = (pn.cd == d) ? ((int)i > pn.m ? 1u : 0u) : (uint32_t)side[o[i]];
-        }
-        uint32_t b = __ballot_sync(0xffffffffu, f != 0);
+        // the flag ballots were written by part_count_kernel: one broadcast word per warp and round
+        uint32_t b = fbits_all[(size_t)d * words_per_dim + (size_t)((base + r * PRIM_THREADS + threadIdx.x) >> 5)];
         bal[r] = b;
-        fbits |= f << r;
+        fbits |= ((b >> lane) & 1u) << r;
         if (lane == 0) cnt[r * 8 + w] = __popc(b);
     }
     __syncthreads();
@@ -277,6 +281,7 @@ void build_tree(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* sec_in, cons
         DevBuf<uint8_t> side(n);
         DevBuf<uint32_t> rcount((size_t)1 << (depth > 0 ? depth - 1 : 0));
         DevBuf<uint32_t> tsum((size_t)3 * ntiles);
+        DevBuf<uint32_t> fbits((size_t)3 * ntiles * (PRIM_TILE / 32));
         size_t sc = scan_scratch_elems((int64_t)3 * ntiles);
         size_t sc2 = scan_scratch_elems((int64_t)rcount.n);
         DevBuf<uint32_t> scratch(sc > sc2 ? sc : sc2);
@@ -287,10 +292,10 @@ void build_tree(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* sec_in, cons
             build_level_nodes_kernel<S><<<div_up(C, 128), 128, 0, st>>>(l, n, bucket, prim_in, o[0], o[1], o[2], nlo.p, nhi.p, cutdim.p, rcount.p);
             exclusive_scan_u32(rcount.p, rcount.p, C, scratch.p, st, &launches);
             mark_side_kernel<<<div_up(n, 256), 256, 0, st>>>(l, n, bucket, o[0], o[1], o[2], nlo.p, nhi.p, cutdim.p, pos_node.p, side.p);
-            part_count_kernel<<<dim3(ntiles, 3), PRIM_THREADS, 0, st>>>(l, n, bucket, o[0], o[1], o[2], nlo.p, nhi.p, cutdim.p, pos_node.p, side.p, tsum.p, ntiles);
+            part_count_kernel<<<dim3(ntiles, 3), PRIM_THREADS, 0, st>>>(l, n, bucket, o[0], o[1], o[2], nlo.p, nhi.p, cutdim.p, pos_node.p, side.p, tsum.p, ntiles, fbits.p);
             exclusive_scan_u32(tsum.p, tsum.p, (int64_t)3 * ntiles, scratch.p, st, &launches);
             part_scatter_kernel<<<dim3(ntiles, 3), PRIM_THREADS, 0, st>>>(l, n, bucket, o[0], o[1], o[2], nw[0], nw[1], nw[2], nlo.p, nhi.p, cutdim.p,
-                                                                           pos_node.p, side.p, tsum.p, ntiles, rcount.p);
+                                                                           pos_node.p, fbits.p, tsum.p, ntiles, rcount.p);
             launches += 4;
             for (int d = 0; d < 3; d++) { uint32_t* tp = o[d]; o[d] = nw[d]; nw[d] = tp; }
             if (tr.on) { char lb[64]; snprintf(lb, sizeof(lb), "build: level %d", l); tr.point(lb); }

@@ -194,8 +194,9 @@ class KDTree:
     # ---- smoothed estimators ------------------------------------------------------------------
     def CalcDensity(self, Nsmooth=64, want_h=False, out=None):
         """KDTree::CalcDensity (KDCalcSmoothQuantities.cxx:203-305); returns rho indexed by ID."""
-        if out is not None:
-            L.check(self._lib.nbk_calc_density(self._h, int(Nsmooth), _ptr(out), None, L.DEVICE_PTRS))
+        if out is not None:     # torch CUDA tensor (no copy) or a host buffer (numpy / pinned torch CPU tensor)
+            dev = _is_torch(out) and out.is_cuda
+            L.check(self._lib.nbk_calc_density(self._h, int(Nsmooth), _ptr(out), None, L.DEVICE_PTRS if dev else 0))
             return out
         rho = np.empty(self.n)
         h = np.empty(self.n) if want_h else None
@@ -212,7 +213,8 @@ class KDTree:
     def CalcVelDensity(self, Nsmooth=64, Nsearch=64, out=None):
         """KDTree::CalcVelDensity (KDCalcSmoothQuantities.cxx:309-389)."""
         if out is not None:
-            L.check(self._lib.nbk_calc_veldensity(self._h, int(Nsmooth), int(Nsearch), _ptr(out), L.DEVICE_PTRS))
+            dev = _is_torch(out) and out.is_cuda
+            L.check(self._lib.nbk_calc_veldensity(self._h, int(Nsmooth), int(Nsearch), _ptr(out), L.DEVICE_PTRS if dev else 0))
             return out
         rho = np.empty(self.n)
         L.check(self._lib.nbk_calc_veldensity(self._h, int(Nsmooth), int(Nsearch), _ptr(rho), 0))
