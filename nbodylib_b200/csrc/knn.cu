@@ -608,48 +608,84 @@ struct KeyHeap4 {
     }
 };
 
+// Leaf tile staged in shared memory + the per-candidate tests of the two passes.
+// fp32 storage: the tile keeps the float4 records (one LDS.128 per candidate) and candidates are first screened with
+// an fp32 distance: inputs are exact, the fp32 evaluation has a relative error below 5 * 2^-24, so a candidate whose
+// fp32 d2 exceeds limit * (1 + 2^-20) cannot pass the exact fp64 test, which is then evaluated only for the few
+// survivors.  fp64 storage: no screen (fp32 rounding of the coordinates would not bound the error), exact test only.
+template <class S> struct LeafTile;
+template <> struct LeafTile<float> {
+    float4* t;
+    float qxf, qyf, qzf;
+    __device__ __forceinline__ void init(void* mem, double qx, double qy, double qz) { t = reinterpret_cast<float4*>(mem); qxf = (float)qx; qyf = (float)qy; qzf = (float)qz; }
+    __device__ __forceinline__ void load(const Vec4<float>* P, int first, int m, unsigned lane) {
+        if ((int)lane < m) { Vec4<float> c = P[first + lane]; t[lane] = make_float4(c.x, c.y, c.z, 0.f); }
+    }
+    static __device__ __forceinline__ float screen_limit(float lim) { return __fmul_ru(lim, 1.00000095367431640625f); }
+    __device__ __forceinline__ bool screen(int j, float limf, double) const {
+        const float4 c = t[j];
+        const float dx = qxf - c.x, dy = qyf - c.y, dz = qzf - c.z;
+        return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)) <= limf;
+    }
+    __device__ __forceinline__ double exact(int j, double qx, double qy, double qz) const {
+        const float4 c = t[j];
+        return dist2_ref(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
+    }
+};
+template <> struct LeafTile<double> {
+    double* t;
+    double qx_, qy_, qz_;
+    __device__ __forceinline__ void init(void* mem, double qx, double qy, double qz) { t = reinterpret_cast<double*>(mem); qx_ = qx; qy_ = qy; qz_ = qz; }
+    __device__ __forceinline__ void load(const Vec4<double>* P, int first, int m, unsigned lane) {
+        if ((int)lane < m) { Vec4<double> c = P[first + lane]; t[lane] = c.x; t[32 + lane] = c.y; t[64 + lane] = c.z; }
+    }
+    static __device__ __forceinline__ float screen_limit(float lim) { return lim; }
+    __device__ __forceinline__ bool screen(int j, float, double limd) const { return dist2_ref(qx_, qy_, qz_, t[j], t[32 + j], t[64 + j]) < limd; }
+    __device__ __forceinline__ double exact(int j, double qx, double qy, double qz) const { return dist2_ref(qx, qy, qz, t[j], t[32 + j], t[64 + j]); }
+};
+
+constexpr int SC_LEAFCAP = 120;   // leaves remembered by the select pass for the collect pass (per warp)
+
 template <class S>
 struct SelectVisitor {
     const Vec4<S>* P;
-    double* tile;
+    LeafTile<S> tile;
     KeyHeap4 hp;
     double qx, qy, qz;
     double topd;        // (double) of the heap-top key; 0 for lanes without a query (nothing is ever accepted)
-    float topf;
+    float topf, limf;   // limf: fp32 screening limit derived from topf
     int r0, r1;         // tree-index range bulk-loaded into the heap (skipped during the traversal)
+    int* leaflist;      // [SC_LEAFCAP][2] (start, count) of every leaf scanned, warp-uniform
+    int nleaf;
     unsigned lane;
     __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
-    __device__ __forceinline__ void settop(float k) { topf = k; topd = (double)k; }
+    __device__ __forceinline__ void settop(float k) { topf = k; topd = (double)k; limf = LeafTile<S>::screen_limit(k); }
     template <bool OVERLAP>
     __device__ __forceinline__ void scan_tile(int first, int m) {
-        // pass 1: one compare per candidate (the query itself and coincident particles have d2 == 0 and are weeded out in
-        // pass 2, like bulk-loaded candidates); pass 2: serial insertion rounds over the set bits
+        // pass 1: one cheap test per candidate (the query itself and coincident particles have d2 == 0 and are weeded out
+        // in pass 2, like bulk-loaded candidates); pass 2: serial insertion rounds over the set bits
         unsigned acc = 0;
 #pragma unroll 4
-        for (int j = 0; j < m; j++) {
-            double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-            acc |= (d2 < topd ? 1u : 0u) << j;
-        }
+        for (int j = 0; j < m; j++) acc |= (tile.screen(j, limf, topd) ? 1u : 0u) << j;
         while (__any_sync(0xffffffffu, acc != 0)) {
             if (acc) {
                 const int j = __ffs(acc) - 1;
                 acc &= acc - 1;
                 const int c = first + j;
-                double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+                const double d2 = tile.exact(j, qx, qy, qz);
                 if (d2 < topd && d2 > 0.0 && (!OVERLAP || c < r0 || c >= r1)) settop(hp.sift(0, __double2float_rn(d2)));
             }
         }
     }
     __device__ __forceinline__ void leaf(int start, int cnt) {
         if (start >= r0 && start + cnt <= r1) return;
+        if (nleaf < SC_LEAFCAP && lane == 0) { leaflist[2 * nleaf] = start; leaflist[2 * nleaf + 1] = cnt; }
+        nleaf++;
         const bool overlap = start < r1 && start + cnt > r0;
         for (int base = 0; base < cnt; base += 32) {
             int m = min(32, cnt - base);
             __syncwarp();
-            if ((int)lane < m) {
-                Vec4<S> c = P[start + base + lane];
-                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
-            }
+            tile.load(P, start + base, m, lane);
             __syncwarp();
             if (overlap) scan_tile<true>(start + base, m);
             else scan_tile<false>(start + base, m);
@@ -660,37 +696,34 @@ struct SelectVisitor {
 template <class S>
 struct CollectVisitor {
     const Vec4<S>* P;
-    double* tile;
+    LeafTile<S> tile;
     int* L;            // this lane's column of the [k][32] index list (entry s at L[s*32])
     double qx, qy, qz;
     double d2max;
-    double thr_d;      // candidates with d2 >= thr_d cannot qualify (cheap fp64 pre-test)
-    float thr;         // qualify iff RN_fp32(d2) <= thr ; -1 for lanes that collect nothing
+    double thr_d;      // candidates with d2 >= thr_d cannot qualify (fp64 pre-test)
+    float thr, limf;   // qualify iff RN_fp32(d2) <= thr ; -1 for lanes that collect nothing
     int cnt, cap;
+    int r0, r1;        // with skip_range: candidates in [r0,r1) are left to the separate scan of the bulk range
     unsigned lane;
     __device__ __forceinline__ bool need(float lb) const { return lb <= thr; }
-    __device__ __forceinline__ void leaf(int start, int n) {
+    template <bool SKIP>
+    __device__ __forceinline__ void scan(int start, int n) {
         for (int base = 0; base < n; base += 32) {
             int m = min(32, n - base);
             __syncwarp();
-            if ((int)lane < m) {
-                Vec4<S> c = P[start + base + lane];
-                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
-            }
+            tile.load(P, start + base, m, lane);
             __syncwarp();
             unsigned acc = 0;
 #pragma unroll 4
-            for (int j = 0; j < m; j++) {
-                double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-                acc |= (d2 < thr_d ? 1u : 0u) << j;
-            }
+            for (int j = 0; j < m; j++) acc |= (tile.screen(j, limf, thr_d) ? 1u : 0u) << j;
             while (__any_sync(0xffffffffu, acc != 0)) {
                 if (acc) {
                     const int j = __ffs(acc) - 1;
                     acc &= acc - 1;
-                    double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-                    if (d2 > 0.0 && __double2float_rn(d2) <= thr && cnt < cap) {
-                        L[cnt * 32] = start + base + j;
+                    const int c = start + base + j;
+                    const double d2 = tile.exact(j, qx, qy, qz);
+                    if (d2 < thr_d && d2 > 0.0 && __double2float_rn(d2) <= thr && cnt < cap && (!SKIP || c < r0 || c >= r1)) {
+                        L[cnt * 32] = c;
                         cnt++;
                         d2max = fmax(d2max, d2);
                     }
@@ -698,6 +731,7 @@ struct CollectVisitor {
             }
         }
     }
+    __device__ __forceinline__ void leaf(int start, int n) { scan<false>(start, n); }
 };
 
 static inline size_t sc_warp_bytes(int k, bool want_doubles) {
@@ -705,7 +739,7 @@ static inline size_t sc_warp_bytes(int k, bool want_doubles) {
     size_t keys = (size_t)(G + 1) * 32 * 16, list = (size_t)k * 32 * 4;
     size_t region = keys > list ? keys : list;
     if (want_doubles) region = list + (size_t)k * 32 * 8 > region ? list + (size_t)k * 32 * 8 : region;
-    return region + 96 * 8 + TRAV_STACK * 4;
+    return region + 96 * 8 + TRAV_STACK * 4 + SC_LEAFCAP * 8;
 }
 
 template <class S>
@@ -717,10 +751,11 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
     size_t region = (size_t)(G + 1) * 32 * 16;
     if ((size_t)k * 32 * 4 > region) region = (size_t)k * 32 * 4;
     if (want_doubles && (size_t)k * 32 * 12 > region) region = (size_t)k * 32 * 12;
-    const size_t warp_bytes = region + 96 * 8 + TRAV_STACK * 4;
+    const size_t warp_bytes = region + 96 * 8 + TRAV_STACK * 4 + SC_LEAFCAP * 8;
     unsigned char* base = smem_raw + w * warp_bytes;
-    double* tile = reinterpret_cast<double*>(base + region);
+    void* tile_mem = base + region;
     int* stack = reinterpret_cast<int*>(base + region + 96 * 8);
+    int* leaflist = reinterpret_cast<int*>(base + region + 96 * 8 + TRAV_STACK * 4);
 
     const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
     const int64_t group = (int64_t)blockIdx.x * KNN_WARPS + w;
@@ -731,12 +766,15 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
     double x0 = 0, y0 = 0, z0 = 0;
     if (valid) { Vec4<S> c = P[qi]; x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z; }
     const QueryBox qb = make_qbox(x0, y0, z0);
+    int nleaf, r0i, r1i;
 
     // ---------------------------------------------------------------------------------------------- select
     float key_k, key_kp1;
     {
         SelectVisitor<S> v;
-        v.P = P; v.tile = tile; v.lane = lane;
+        v.P = P; v.lane = lane;
+        v.tile.init(tile_mem, x0, y0, z0);
+        v.leaflist = leaflist; v.nleaf = 0;
         v.hp.kb = base + lane * 16; v.hp.G = G;
         const int self = valid ? (int)qi : -1;
         v.qx = x0; v.qy = y0; v.qz = z0;
@@ -751,13 +789,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
         for (int64_t b0 = r0; b0 < r1; b0 += 32) {
             int m = (int)min((int64_t)32, r1 - b0);
             __syncwarp();
-            if ((int)lane < m) {
-                Vec4<S> c = P[b0 + lane];
-                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
-            }
+            v.tile.load(P, (int)b0, m, lane);
             __syncwarp();
             for (int j = 0; j < m; j++) {
-                double d2 = dist2_ref(x0, y0, z0, tile[j], tile[32 + j], tile[64 + j]);
+                double d2 = v.tile.exact(j, x0, y0, z0);
                 if (valid && (int)(b0 + j) != self && d2 > 0.0) { *v.hp.keyp(filled) = __double2float_rn(d2); filled++; }
             }
         }
@@ -768,6 +803,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
         key_kp1 = v.hp.rootkey();
         v.hp.sift(0, 0.f);
         key_k = v.hp.rootkey();
+        nleaf = v.nleaf; r0i = v.r0; r1i = v.r1;
     }
     const bool short_of_k = __float_as_uint(key_k) == FKEY_INF;
     const bool flagged = valid && key_k == key_kp1 && !short_of_k;
@@ -779,14 +815,24 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
 
     // --------------------------------------------------------------------------------------------- collect
     CollectVisitor<S> c2;
-    c2.P = P; c2.tile = tile; c2.L = reinterpret_cast<int*>(base) + lane; c2.lane = lane;
+    c2.P = P; c2.L = reinterpret_cast<int*>(base) + lane; c2.lane = lane;
+    c2.tile.init(tile_mem, x0, y0, z0);
     c2.qx = x0; c2.qy = y0; c2.qz = z0;
+    c2.r0 = r0i; c2.r1 = r1i;
     c2.cnt = 0; c2.cap = k; c2.d2max = 0;
     c2.thr = (valid && !flagged) ? key_k : -1.f;
     c2.thr_d = (valid && !flagged) ? (double)__uint_as_float(__float_as_uint(key_k) + (short_of_k ? 0u : 1u)) : -1.0;   // next float above key_k
     if (short_of_k && valid) c2.thr_d = 3.0e38 * 10.0;
+    c2.limf = LeafTile<S>::screen_limit(c2.thr);
     const bool collecting = valid && !flagged;
-    traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, collecting);
+    if (nleaf <= SC_LEAFCAP) {
+        // every leaf that can hold one of the k nearest was scanned by the select pass (a lane's final neighbours were
+        // below its bound at all times): re-scan exactly those tiles, plus the bulk-loaded range, without walking the tree
+        c2.template scan<false>(r0i, r1i - r0i);
+        for (int t = 0; t < nleaf; t++) c2.template scan<true>(leaflist[2 * t], leaflist[2 * t + 1]);
+    } else {
+        traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, collecting);
+    }
     if (!collecting) return;
 
     // -------------------------------------------------------------------------------------------- epilogues
