@@ -142,7 +142,10 @@ int nbk_calc_veldensity(nbk_tree* t, int nsmooth, int nsearch, double* rho, int 
 int nbk_smoothing_scale(nbk_tree* t, int nsmooth, double* hsm, int flags);
 
 /* Optional FOF by-products in tree-index space (reference KDFOF.cxx:52-55: pHead,pNext,pTail,pLen).
- * Any pointer may be NULL.  head/next/tail have n entries; len has ngroups+1 entries (index = group id). */
+ * Any pointer may be NULL.  head/next/tail have n entries: the members of a group are chained in ascending tree
+ * index (head[i] = first member, next[i] = following member or -1, tail[i] = last member; a particle outside any
+ * group is its own one-element list).  len needs n+1 entries of room; entries 0..ngroups are written (index = group
+ * id, the reference's pLen[iGroup]). */
 typedef struct { int32_t* head; int32_t* next; int32_t* tail; int32_t* len; } nbk_fof_lists;
 
 /* Replaces KDTree::FOF(fdist, numgroup, minnum, order, pHead,pNext,pTail,pLen, ipcheckflag, check, params)

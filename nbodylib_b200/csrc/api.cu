@@ -542,12 +542,10 @@ int nbk_smoothing_scale(nbk_tree* t, int nsmooth, double* hsm, int flags) {
 static void fof_call(nbk_tree* t, FofArgs& a, const int32_t* precheck, int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags) {
     NBK_REQUIRE(group && ngroups, NBK_ERR_ARG, "FOF: null output");
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "FOF needs a TPHYS or TPHS tree");
-    NBK_REQUIRE(!(lists && (lists->head || lists->next || lists->tail)), NBK_ERR_UNSUPPORTED,
-                "FOF pHead/pNext/pTail outputs are not implemented yet (pLen is)");
     DeviceGuard guard(t->device, t->stream);
     const int64_t n = t->n;
     const bool dev = flags & NBK_DEVICE_PTRS;
-    DevBuf<int32_t> dpre, dpre_tree, dgroup(n), dlen;
+    DevBuf<int32_t> dpre, dpre_tree, dgroup(n), dlen, dhead, dnext, dtail;
     if (precheck) {
         const int32_t* src = precheck;
         if (!dev) {
@@ -564,11 +562,20 @@ static void fof_call(nbk_tree* t, FofArgs& a, const int32_t* precheck, int32_t* 
     }
     a.group_tree = dgroup.p;
     if (lists && lists->len) { dlen.alloc(n + 1); a.len = dlen.p; }
+    if (lists && lists->head) { if (dev) a.head = lists->head; else { dhead.alloc(n); a.head = dhead.p; } }
+    if (lists && lists->next) { if (dev) a.next = lists->next; else { dnext.alloc(n); a.next = dnext.p; } }
+    if (lists && lists->tail) { if (dev) a.tail = lists->tail; else { dtail.alloc(n); a.tail = dtail.p; } }
     CallTimer tm(*t);
     launch_fof(*t, a);
     tm.stop();
     *ngroups = a.ngroups;
     deliver_i32(t, dgroup.p, group, flags);
+    if (lists && !dev) {
+        if (lists->head) NBK_CHECK(cudaMemcpyAsync(lists->head, dhead.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, t->stream));
+        if (lists->next) NBK_CHECK(cudaMemcpyAsync(lists->next, dnext.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, t->stream));
+        if (lists->tail) NBK_CHECK(cudaMemcpyAsync(lists->tail, dtail.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+    }
     if (lists && lists->len) {
         NBK_CHECK(cudaMemcpyAsync(lists->len, dlen.p, sizeof(int32_t) * (a.ngroups + 1), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
         NBK_CHECK(cudaStreamSynchronize(t->stream));

@@ -207,6 +207,51 @@ __global__ void fof_len_kernel(int64_t n, const uint32_t* flag, const uint32_t* 
     len[g] = (int)size[i];
 }
 
+// ---- pHead / pNext / pTail (KDFOF.cxx:52-67): members of a group chained in ascending tree index -------------------
+__global__ void fof_list_keys_kernel(int64_t n, const int32_t* group, uint32_t* keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = (uint32_t)group[i];
+}
+// sorted by group id (stable, so ascending tree index inside a group): chain neighbours, remember each run's ends
+__global__ void fof_list_next_kernel(int64_t n, const uint32_t* sk, const uint32_t* sv, int32_t* next, uint32_t* run_first, uint32_t* run_last) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t g = sk[p], i = sv[p];
+    if (g == 0) { next[i] = -1; return; }
+    bool first = (p == 0) || sk[p - 1] != g;
+    bool last = (p == n - 1) || sk[p + 1] != g;
+    next[i] = last ? -1 : (int32_t)sv[p + 1];
+    if (first) run_first[g] = i;
+    if (last) run_last[g] = i;
+}
+__global__ void fof_list_ends_kernel(int64_t n, const int32_t* group, const uint32_t* run_first, const uint32_t* run_last, int32_t* head, int32_t* tail) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int g = group[i];
+    if (head) head[i] = g > 0 ? (int32_t)run_first[g] : (int32_t)i;
+    if (tail) tail[i] = g > 0 ? (int32_t)run_last[g] : (int32_t)i;
+}
+
+static void build_fof_lists(nbk_tree& t, FofArgs& a, int64_t* launches) {
+    const int64_t n = t.n;
+    cudaStream_t st = t.stream;
+    const int tb = 256;
+    DevBuf<uint32_t> ka(n), kb(n), va(n), vb(n), rf((size_t)a.ngroups + 2), rl((size_t)a.ngroups + 2);
+    DevBuf<int32_t> next_tmp(a.next ? 0 : n);
+    int32_t* next = a.next ? a.next : next_tmp.p;
+    RadixSortPlan<uint32_t> plan(n);
+    DevBuf<uint32_t> temp(plan.temp_u32());
+    fof_list_keys_kernel<<<div_up(n, tb), tb, 0, st>>>(n, a.group_tree, ka.p);
+    int bits = 8;
+    while (bits < 32 && ((uint64_t)1 << bits) <= (uint64_t)a.ngroups) bits += 8;
+    uint32_t *rk, *rv;
+    radix_sort_pairs<uint32_t>(ka.p, va.p, kb.p, vb.p, n, bits, true, temp.p, st, &rk, &rv, launches);
+    fof_list_next_kernel<<<div_up(n, tb), tb, 0, st>>>(n, rk, rv, next, rf.p, rl.p);
+    fof_list_ends_kernel<<<div_up(n, tb), tb, 0, st>>>(n, a.group_tree, rf.p, rl.p, a.head, a.tail);
+    *launches += 3;
+    NBK_CHECK(cudaStreamSynchronize(st));
+}
+
 void launch_fof(nbk_tree& t, FofArgs& a) {
     const int64_t n = t.n;
     cudaStream_t st = t.stream;
@@ -263,6 +308,7 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
         fof_len_kernel<<<div_up(n, tb), tb, 0, st>>>(n, flag.p, flagscan.p, newid.p, size.p, a.len);
         launches++;
     }
+    if (a.head || a.next || a.tail) build_fof_lists(t, a, &launches);
     NBK_CHECK(cudaStreamSynchronize(st));
     NBK_CHECK(cudaGetLastError());
     tr.point("fof label");

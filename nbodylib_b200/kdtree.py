@@ -227,7 +227,7 @@ class KDTree:
         return h
 
     # ---- friends of friends -------------------------------------------------------------------
-    def FOF(self, fdist, minnum=8, order=0, precheck=None, want_len=False, out=None):
+    def FOF(self, fdist, minnum=8, order=0, precheck=None, want_len=False, out=None, want_lists=False):
         """KDTree::FOF(fdist, numgroup, minnum, order, ...) (KDFOF.cxx:29-153).  Returns (pfof by ID, numgroup)."""
         ng = C.c_int64()
         if out is not None:
@@ -236,11 +236,17 @@ class KDTree:
         g = np.empty(self.n, dtype=np.int32)
         pre = None if precheck is None else np.ascontiguousarray(precheck, dtype=np.int32)
         lists, plen = None, None
-        if want_len:
+        if want_lists:
+            plen = np.zeros(self.n + 1, dtype=np.int32)
+            head, nxt, tail = (np.empty(self.n, dtype=np.int32) for _ in range(3))
+            lists = L.NbkFofLists(head.ctypes.data, nxt.ctypes.data, tail.ctypes.data, plen.ctypes.data)
+        elif want_len:
             plen = np.zeros(self.n + 1, dtype=np.int32)
             lists = L.NbkFofLists(None, None, None, plen.ctypes.data)
         L.check(self._lib.nbk_fof(self._h, float(fdist), int(minnum), int(order), _ptr(pre), _ptr(g), C.byref(ng),
                                   C.byref(lists) if lists else None, 0))
+        if want_lists:
+            return g, ng.value, {"pHead": head, "pNext": nxt, "pTail": tail, "pLen": plen[:ng.value + 1]}
         if want_len:
             return g, ng.value, plen[:ng.value + 1]
         return g, ng.value

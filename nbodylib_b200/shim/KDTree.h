@@ -232,13 +232,18 @@ private:
     }
     template <class F>
     Int_t* run_fof(const std::vector<int32_t>& pre, Int_tree_t* pHead, Int_tree_t* pNext, Int_tree_t* pTail, Int_tree_t* pLen, Int_t& numgroup, F call) {
-        if (pHead || pNext || pTail) throw std::runtime_error("nbk shim: pHead/pNext/pTail outputs are not implemented yet");
-        std::vector<int32_t> g(numparts), len(pLen ? (size_t)numparts + 1 : 0);
-        nbk_fof_lists lists = {NULL, NULL, NULL, pLen ? len.data() : NULL};
+        const bool any = pHead || pNext || pTail || pLen;
+        std::vector<int32_t> g(numparts), len(pLen ? (size_t)numparts + 1 : 0), hd(pHead ? numparts : 0), nx(pNext ? numparts : 0), tl(pTail ? numparts : 0);
+        nbk_fof_lists lists = {pHead ? hd.data() : NULL, pNext ? nx.data() : NULL, pTail ? tl.data() : NULL, pLen ? len.data() : NULL};
         int64_t ng = 0;
-        check(call(pre.empty() ? NULL : pre.data(), g.data(), &ng, pLen ? &lists : NULL));
+        check(call(pre.empty() ? NULL : pre.data(), g.data(), &ng, any ? &lists : NULL));
         numgroup = (Int_t)ng;
         if (pLen) for (int64_t i = 0; i <= ng && i < numparts; i++) pLen[i] = len[i];
+        for (Int_t i = 0; i < numparts; i++) {
+            if (pHead) pHead[i] = hd[i];
+            if (pNext) pNext[i] = nx[i];
+            if (pTail) pTail[i] = tl[i];
+        }
         Int_t* out = new Int_t[numparts];
         for (Int_t i = 0; i < numparts; i++) out[i] = g[i];
         return out;

@@ -285,3 +285,111 @@ def test_cxx_shim_program(built, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "shim demo ok" in out.stdout, out.stdout + out.stderr
     assert "nodes 32767 leaves 16384" in out.stdout
+
+
+@pytest.mark.parametrize("bucket,k", [(1, 3), (4, 9), (8, 33), (32, 16), (64, 40), (100, 7)])
+def test_bucket_sizes_and_odd_k(nb, port, bucket, k):
+    """leaf sizes below and above the 32-wide tile, k that is neither a power of two nor a multiple of four"""
+    from nbodylib_b200.synth import clustered_small
+    n = 7001
+    pos, vel, mass = clustered_small(n, seed=bucket * 100 + k)
+    for period in (None, np.ones(3)):
+        with nb.KDTree(pos, vel, mass, bucket_size=bucket, Period=period) as t:
+            order = t.order()
+            nn, d2 = t.FindNearestPos(k, ids=True)
+            oi, od = port.knn_particles(pos, k, period=period, which=0)
+            assert np.array_equal(by_id(order, d2), od) and rows_equal_as_sets(by_id(order, nn), oi)
+            rho, h = t.CalcDensity(k, want_h=True)
+            orho, oh = port.density(pos, mass, k)
+            np.testing.assert_allclose(rho, orho, rtol=RTOL_RHO)
+            assert np.array_equal(h, oh)
+            kv = max(1, k - 2)
+            np.testing.assert_allclose(t.CalcVelDensity(kv, k), port.veldensity(pos, vel, kv, k), rtol=RTOL_RHO)
+            ll = 0.3 / n ** (1.0 / 3)
+            g, ng = t.FOF(ll, 4, 1)
+            og, ong = port.fof(pos, None, 0, [ll * ll], period, 4, 1)
+            assert ng == ong and np.array_equal(canon(g), canon(og))
+            x = np.random.default_rng(k).random((257, 3))
+            off, idx = t.SearchBallPosTaggedPoints(x, (2.5 * ll) ** 2, ids=True)
+            oo, oidx = port.ball_points(pos, x, (2.5 * ll) ** 2, period)
+            assert np.array_equal(off, oo) and np.array_equal(np.concatenate(csr_rows_sorted(off, idx) + [np.zeros(0, np.int32)]), oidx)
+
+
+def test_input_layouts(nb, port):
+    """the same particles through every input path of nbk_create: fp64 / fp32 host arrays, the reference's 88-byte AoS
+    Particle records (strided view), device tensors, no masses (NOMASS build), no velocities"""
+    import ctypes as C
+    import torch
+    from nbodylib_b200 import _lib as L
+    from nbodylib_b200.synth import clustered_small
+    n, k = 5003, 12
+    pos, vel, mass = clustered_small(n, seed=3)
+    orho, _ = port.density(pos, mass, k)
+    orho1, _ = port.density(pos, None, k)
+
+    def rho_of(tree):
+        with tree as t:
+            return t.CalcDensity(k), t.info
+    r, i = rho_of(nb.KDTree(pos, vel, mass))
+    np.testing.assert_allclose(r, orho, rtol=RTOL_RHO)
+    r, i = rho_of(nb.KDTree(pos.astype(np.float32), vel.astype(np.float32), mass.astype(np.float32)))
+    np.testing.assert_allclose(r, orho, rtol=RTOL_RHO)
+    assert i.store_bytes == 4
+    r, i = rho_of(nb.KDTree(torch.from_numpy(pos).cuda(), torch.from_numpy(vel).cuda(), torch.from_numpy(mass).cuda()))
+    np.testing.assert_allclose(r, orho, rtol=RTOL_RHO)
+    r, i = rho_of(nb.KDTree(pos, None, None))
+    np.testing.assert_allclose(r, orho1, rtol=RTOL_RHO)
+    # reference Particle layout (Particle.h:264-354, default build): mass@0 position@8 velocity@32 pid@56 id@60 type@64 rho@72 phi@80
+    rec = np.dtype({"names": ["mass", "pos", "vel", "pid", "id", "type", "rho", "phi"],
+                    "formats": ["f8", ("f8", 3), ("f8", 3), "i4", "i4", "i4", "f8", "f8"],
+                    "offsets": [0, 8, 32, 56, 60, 64, 72, 80], "itemsize": 88})
+    parts = np.zeros(n, dtype=rec)
+    parts["mass"], parts["pos"], parts["vel"] = mass, pos, vel
+    lib = L.load()
+    p = L.NbkParticles()
+    base = parts.ctypes.data
+    p.pos, p.pos_stride = base + 8, 88
+    p.vel, p.vel_stride = base + 32, 88
+    p.mass, p.mass_stride = base + 0, 88
+    p.real_bytes, p.on_device = 8, 0
+    h = C.c_void_p()
+    L.check(lib.nbk_create(C.byref(p), n, 16, 0, 2, 1000, 0, None, 0, -1, C.byref(h)))
+    rho = np.empty(n)
+    L.check(lib.nbk_calc_density(h, k, rho.ctypes.data, None, 0))
+    lib.nbk_destroy(h)
+    np.testing.assert_allclose(rho, orho, rtol=RTOL_RHO)
+
+
+def test_tvel_tree_knn(nb, port):
+    """TVEL trees search in velocity space (KDFindNearest.cxx:336-346) and never reflect (KDSplitNode.cxx:1082-1085)"""
+    from nbodylib_b200.synth import clustered_small
+    pos, vel, mass = clustered_small(6007, seed=8)
+    with nb.KDTree(pos, vel, mass, TreeType=nb.TVEL, Period=np.ones(3)) as t:
+        order = t.order()
+        nn, d2 = t.FindNearestPos(10, ids=True)
+        oi, od = port.knn_particles(vel, 10)
+        assert np.array_equal(by_id(order, d2), od) and rows_equal_as_sets(by_id(order, nn), oi)
+
+
+def test_fof_linked_lists(nb):
+    """pHead / pNext / pTail / pLen (KDFOF.cxx:52-67): walking a group's chain visits exactly its members"""
+    from nbodylib_b200.synth import clustered_small
+    n = 30011
+    pos, vel, mass = clustered_small(n, seed=17)
+    with nb.KDTree(pos, vel, mass, Period=np.ones(3)) as t:
+        order = t.order()
+        g, ng, ls = t.FOF(0.25 / n ** (1 / 3), 6, 1, want_lists=True)
+        gt = g[order]                                   # group by tree index
+        head, nxt, tail, plen = ls["pHead"], ls["pNext"], ls["pTail"], ls["pLen"]
+        assert ng > 10 and np.array_equal(plen[1:], np.bincount(g)[1:])
+        un = np.nonzero(gt == 0)[0]
+        assert np.array_equal(head[un], un) and np.array_equal(tail[un], un) and np.all(nxt[un] == -1)
+        for gid in list(range(1, min(ng, 40) + 1)) + [ng]:
+            members = np.nonzero(gt == gid)[0]
+            i = head[members[0]]
+            chain = []
+            while i != -1:
+                chain.append(i)
+                i = nxt[i]
+            assert np.array_equal(np.array(chain), members)          # ascending tree index
+            assert np.all(head[members] == members[0]) and np.all(tail[members] == members[-1])
