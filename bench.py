@@ -81,7 +81,7 @@ def sample_subvolume(pos, vel, mass, frac_side=0.25):
     return pos[sel].double().cpu().numpy(), vel[sel].double().cpu().numpy(), mass[sel].double().cpu().numpy()
 
 
-def cpu_reference_leg(pos, vel, mass, k, steps=1, warmup=0):
+def cpu_reference_leg(pos, vel, mass, k, steps=1, warmup=0, fof_ll=None):
     """The reference's CPU path on the host cores: full-host OpenMP kNN-density (BASELINE.md section 3 variant ii:
     omp-parallel loop over FindNearestPos + the CalcDensity accumulation) through oracle/_ref when it is present
     ('reference'), else the brute-force port ('port')."""
@@ -97,13 +97,17 @@ def cpu_reference_leg(pos, vel, mass, k, steps=1, warmup=0):
             ts.append(R.last_seconds)
         cores = pyoracle.Ref.max_threads()
         build_s = R.build_seconds
+        fof_s = None
+        if fof_ll is not None:
+            R.fof(fof_ll, 20, 1)               # the library's FOF is serial (KDFOF.cxx:70-107): "full host" == 1 core
+            fof_s = R.last_seconds
         R.close()
-        return {"kind": "reference", "cores": cores, "seconds": ts, "n": n, "build_seconds": build_s}
+        return {"kind": "reference", "cores": cores, "seconds": ts, "n": n, "build_seconds": build_s, "fof_seconds": fof_s}
     P = pyoracle.Port()
     m = min(n, 20000)
     t0 = time.time()
     P.density(pos[:m], mass[:m], k)
-    return {"kind": "port", "cores": os.cpu_count(), "seconds": [time.time() - t0], "n": m, "build_seconds": 0.0}
+    return {"kind": "port", "cores": os.cpu_count(), "seconds": [time.time() - t0], "n": m, "build_seconds": 0.0, "fof_seconds": None}
 
 
 def run_reference_arm(args, rank, world):
@@ -228,6 +232,19 @@ def main():
             tree.CalcVelDensity(K_NN, K_NN, out=rho)
             torch.cuda.synchronize(); ts.append(time.perf_counter() - t1)
         extra["veldensity_particles_per_s"] = n / float(np.mean(ts))
+        # BASELINE config 4: 6D phase-space FOF with the in-tree criterion (FOFFunc.h:48-55)
+        sv2 = float(((vel - vel.mean(0)) ** 2).sum(1).mean().item() / 3.0)
+        params = np.zeros(10)
+        params[1] = params[6] = (0.2 / ng) ** 2
+        params[2] = params[7] = (1.25 ** 2) * sv2
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        g6, ng6 = tree.FOFCriterion(2, params, 20, 1)
+        torch.cuda.synchronize()
+        extra["fof6d_particles_per_s"] = n / (time.perf_counter() - t1)
+        extra["fof6d_link_kernel_ms"] = tree.info.last_kernel_ms
+        extra["fof6d_groups"] = int(ng6)
+        extra["fof6d_note"] = "FOFCriterion(FOF6d), host group array returned (includes 0.5 GB D2H)"
+        del g6
         extra["build_ms"] = info.build_ms
         extra["build_particles_per_s"] = n / (info.build_ms * 1e-3)
         extra["build_hbm_frac"] = n * ALG_BYTES["build"] / (info.build_ms * 1e-3) / 1e9 / peak
@@ -255,8 +272,12 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         frac = 0.25 if ng >= 256 else 1.0
         sp, sv, sm = sample_subvolume(pos, vel, mass, frac)
-        leg = cpu_reference_leg(sp, sv, sm, K_NN)
+        leg = cpu_reference_leg(sp, sv, sm, K_NN, fof_ll=0.2 / ng)
         dt = float(np.mean(leg["seconds"]))
+        if leg.get("fof_seconds"):
+            extra["cpu_fof3d_particles_per_s"] = leg["n"] / leg["fof_seconds"]
+            extra["cpu_fof3d_note"] = "reference KDTree::FOF (serial in the library) on the same sub-cube sample, non periodic"
+            extra["cpu_build_particles_per_s"] = leg["n"] / leg["build_seconds"] if leg["build_seconds"] else None
         cpu = {"value": leg["n"] / dt, "unit": "particles/s", "cores": leg["cores"], "kind": leg["kind"],
                "sample": "all %d particles of the sub-cube [0,%.2f)^3 of the same box, full-host OpenMP kNN(k=%d)+density accumulation (BASELINE.md 3, variant ii), tree built over the sample only" % (leg["n"], frac, K_NN),
                "seconds": dt}

@@ -110,7 +110,7 @@ struct KnnVisitor {
     __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
     __device__ __forceinline__ void settop() { top = hp.h(0); topf = __double2float_ru(top); }
 
-    __device__ __forceinline__ void leaf(int start, int cnt) {
+    __device__ __forceinline__ void leaf(int start, int cnt, int = 0) {
         for (int base = 0; base < cnt; base += 32) {
             int m = min(32, cnt - base);
             __syncwarp();
@@ -369,7 +369,7 @@ struct FastVisitor {
         }
     }
 
-    __device__ __forceinline__ void leaf(int start, int cnt) {
+    __device__ __forceinline__ void leaf(int start, int cnt, int = 0) {
         if (start >= r0 && start + cnt <= r1) return;          // warp-uniform: leaf entirely preloaded
         const bool overlap = start < r1 && start + cnt > r0;   // warp-uniform
         for (int base = 0; base < cnt; base += 32) {
@@ -625,7 +625,7 @@ template <> struct LeafTile<float> {
     __device__ __forceinline__ bool screen(int j, float limf, double) const {
         const float4 c = t[j];
         const float dx = qxf - c.x, dy = qyf - c.y, dz = qzf - c.z;
-        return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)) <= limf;
+        return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) <= limf;     // 3 sub + mul + 2 fma; error < 4 * 2^-24
     }
     __device__ __forceinline__ double exact(int j, double qx, double qy, double qz) const {
         const float4 c = t[j];
@@ -644,7 +644,7 @@ template <> struct LeafTile<double> {
     __device__ __forceinline__ double exact(int j, double qx, double qy, double qz) const { return dist2_ref(qx, qy, qz, t[j], t[32 + j], t[64 + j]); }
 };
 
-constexpr int SC_LEAFCAP = 120;   // leaves remembered by the select pass for the collect pass (per warp)
+constexpr int SC_LEAFCAP = 240;   // leaves remembered by the select pass for the collect pass (per warp)
 
 template <class S>
 struct SelectVisitor {
@@ -655,7 +655,7 @@ struct SelectVisitor {
     double topd;        // (double) of the heap-top key; 0 for lanes without a query (nothing is ever accepted)
     float topf, limf;   // limf: fp32 screening limit derived from topf
     int r0, r1;         // tree-index range bulk-loaded into the heap (skipped during the traversal)
-    int* leaflist;      // [SC_LEAFCAP][2] (start, count) of every leaf scanned, warp-uniform
+    int* leaflist;      // [SC_LEAFCAP] node index of every leaf scanned, warp-uniform
     int nleaf;
     unsigned lane;
     __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
@@ -677,9 +677,9 @@ struct SelectVisitor {
             }
         }
     }
-    __device__ __forceinline__ void leaf(int start, int cnt) {
+    __device__ __forceinline__ void leaf(int start, int cnt, int node) {
         if (start >= r0 && start + cnt <= r1) return;
-        if (nleaf < SC_LEAFCAP && lane == 0) { leaflist[2 * nleaf] = start; leaflist[2 * nleaf + 1] = cnt; }
+        if (nleaf < SC_LEAFCAP && lane == 0) leaflist[nleaf] = node;
         nleaf++;
         const bool overlap = start < r1 && start + cnt > r0;
         for (int base = 0; base < cnt; base += 32) {
@@ -731,7 +731,7 @@ struct CollectVisitor {
             }
         }
     }
-    __device__ __forceinline__ void leaf(int start, int n) { scan<false>(start, n); }
+    __device__ __forceinline__ void leaf(int start, int n, int = 0) { scan<false>(start, n); }
 };
 
 static inline size_t sc_warp_bytes(int k, bool want_doubles) {
@@ -739,7 +739,7 @@ static inline size_t sc_warp_bytes(int k, bool want_doubles) {
     size_t keys = (size_t)(G + 1) * 32 * 16, list = (size_t)k * 32 * 4;
     size_t region = keys > list ? keys : list;
     if (want_doubles) region = list + (size_t)k * 32 * 8 > region ? list + (size_t)k * 32 * 8 : region;
-    return region + 96 * 8 + TRAV_STACK * 4 + SC_LEAFCAP * 8;
+    return region + 96 * 8 + TRAV_STACK * 4 + SC_LEAFCAP * 4;
 }
 
 template <class S>
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
     size_t region = (size_t)(G + 1) * 32 * 16;
     if ((size_t)k * 32 * 4 > region) region = (size_t)k * 32 * 4;
     if (want_doubles && (size_t)k * 32 * 12 > region) region = (size_t)k * 32 * 12;
-    const size_t warp_bytes = region + 96 * 8 + TRAV_STACK * 4 + SC_LEAFCAP * 8;
+    const size_t warp_bytes = region + 96 * 8 + TRAV_STACK * 4 + SC_LEAFCAP * 4;
     unsigned char* base = smem_raw + w * warp_bytes;
     void* tile_mem = base + region;
     int* stack = reinterpret_cast<int*>(base + region + 96 * 8);
@@ -829,7 +829,14 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
         // every leaf that can hold one of the k nearest was scanned by the select pass (a lane's final neighbours were
         // below its bound at all times): re-scan exactly those tiles, plus the bulk-loaded range, without walking the tree
         c2.template scan<false>(r0i, r1i - r0i);
-        for (int t = 0; t < nleaf; t++) c2.template scan<true>(leaflist[2 * t], leaflist[2 * t + 1]);
+        for (int t = 0; t < nleaf; t++) {
+            const int node = leaflist[t];
+            const NodeLo lo = prm.nlo[node];
+            const NodeHi hi = prm.nhi[node];
+            const float lb = box_lb(qb.lx, qb.ly, qb.lz, qb.hx, qb.hy, qb.hz, lo, hi);
+            if (!__any_sync(0xffffffffu, collecting && c2.need(lb))) continue;     // the bounds have tightened since
+            c2.template scan<true>(lo.start, hi.end - lo.start);
+        }
     } else {
         traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, collecting);
     }

@@ -50,7 +50,7 @@ __device__ __forceinline__ QueryBox make_qbox(double x, double y, double z) {
 
 // Visitor interface (all methods called by the full warp):
 //   bool need(float lb)             per-lane: could this lane accept something at distance^2 >= lb ?
-//   void leaf(int start, int cnt)   process particles [start, start+cnt)
+//   void leaf(int start, int cnt, int node)   process particles [start, start+cnt) of node `node`
 // ORDERED: always descend the left child first so leaves are met in ascending tree-index order.
 //
 // Control flow: a node is tested when it is reached as a child; the nearer child (by vote of the lanes that
@@ -72,7 +72,7 @@ __device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const N
         // invariant: `node` (bounds lo/hi) is needed by at least one lane
         bool descend = false;
         if (hi.end - lo.start <= bucket) {
-            v.leaf(lo.start, hi.end - lo.start);
+            v.leaf(lo.start, hi.end - lo.start, node);
         } else {
             const int c1 = 2 * node + 1, c2 = c1 + 1;
             NodeLo l1 = nlo[c1]; NodeHi h1 = nhi[c1];
