@@ -249,6 +249,8 @@ def main():
         extra["build_particles_per_s"] = n / (info.build_ms * 1e-3)
         extra["build_hbm_frac"] = n * ALG_BYTES["build"] / (info.build_ms * 1e-3) / 1e9 / peak
         del g
+    if world > 1:
+        extra["sharded_rank0"] = dict(tree.stats)
     tree.close()
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------

@@ -36,7 +36,7 @@ struct BallVisitor {
     int32_t* idx; int64_t cap; int out_ids;
 
     __device__ __forceinline__ bool need(float lb) const { return lb < r2f; }
-    __device__ __forceinline__ void leaf(int start, int cnt, int = 0) {
+    __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
         for (int base = 0; base < cnt; base += 32) {
             int m = min(32, cnt - base);
             __syncwarp();

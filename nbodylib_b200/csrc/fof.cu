@@ -94,7 +94,7 @@ struct FofVisitor {
         return t < 1.0;
     }
 
-    __device__ __forceinline__ void leaf(int start, int cnt, int = 0) {
+    __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
         for (int base = 0; base < cnt; base += 32) {
             int m = min(32, cnt - base);
             __syncwarp();

@@ -36,6 +36,12 @@ __device__ __forceinline__ double wsm(double r, int i, int size, double delta, c
     if (i < size - 1) { double a = x[i], b = x[i + 1]; return (a + (b - a) * (r - delta * i) / delta); }
     return x[i];
 }
+// the same with 1/delta precomputed: one multiplication instead of an fp64 division per neighbour (differs from the
+// reference expression by one rounding, ~1e-16 relative, inside the density tolerance)
+__device__ __forceinline__ double wsm_fast(double r, int i, int size, double delta, double inv_delta, const double* __restrict__ x) {
+    if (i < size - 1) { double a = x[i], b = x[i + 1]; return (a + (b - a) * ((r - delta * i) * inv_delta)); }
+    return x[i];
+}
 
 struct KnnParams {
     const NodeLo* nlo; const NodeHi* nhi; int bucket;
@@ -110,7 +116,7 @@ struct KnnVisitor {
     __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
     __device__ __forceinline__ void settop() { top = hp.h(0); topf = __double2float_ru(top); }
 
-    __device__ __forceinline__ void leaf(int start, int cnt, int = 0) {
+    __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
         for (int base = 0; base < cnt; base += 32) {
             int m = min(32, cnt - base);
             __syncwarp();
@@ -369,7 +375,7 @@ struct FastVisitor {
         }
     }
 
-    __device__ __forceinline__ void leaf(int start, int cnt, int = 0) {
+    __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
         if (start >= r0 && start + cnt <= r1) return;          // warp-uniform: leaf entirely preloaded
         const bool overlap = start < r1 && start + cnt > r0;   // warp-uniform
         for (int base = 0; base < cnt; base += 32) {
@@ -615,29 +621,42 @@ struct KeyHeap4 {
 // survivors.  fp64 storage: no screen (fp32 rounding of the coordinates would not bound the error), exact test only.
 template <class S> struct LeafTile;
 template <> struct LeafTile<float> {
+    static constexpr int TILE_BYTES = 32 * 16;
     float4* t;
     float qxf, qyf, qzf;
-    __device__ __forceinline__ void init(void* mem, double qx, double qy, double qz) { t = reinterpret_cast<float4*>(mem); qxf = (float)qx; qyf = (float)qy; qzf = (float)qz; }
+    __device__ __forceinline__ void init(void* mem, double qx, double qy, double qz) {
+        t = reinterpret_cast<float4*>(mem);
+        qxf = (float)qx; qyf = (float)qy; qzf = (float)qz;
+    }
     __device__ __forceinline__ void load(const Vec4<float>* P, int first, int m, unsigned lane) {
-        if ((int)lane < m) { Vec4<float> c = P[first + lane]; t[lane] = make_float4(c.x, c.y, c.z, 0.f); }
+        // slots past the end of the leaf hold NaN: every screen / comparison on them is false, so the scan loops can run
+        // over whole groups of 8 without a bound check
+        const float nanf_ = __int_as_float(0x7fc00000);
+        float4 mine = make_float4(nanf_, nanf_, nanf_, 0.f);
+        if ((int)lane < m) { Vec4<float> c = P[first + lane]; mine = make_float4(c.x, c.y, c.z, 0.f); }
+        t[lane] = mine;
     }
     static __device__ __forceinline__ float screen_limit(float lim) { return __fmul_ru(lim, 1.00000095367431640625f); }
-    __device__ __forceinline__ bool screen(int j, float limf, double) const {
-        const float4 c = t[j];
-        const float dx = qxf - c.x, dy = qyf - c.y, dz = qzf - c.z;
+    static __device__ __forceinline__ bool screen_one(float qx, float qy, float qz, const float4& c, float limf) {
+        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
         return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) <= limf;     // 3 sub + mul + 2 fma; error < 4 * 2^-24
     }
+    __device__ __forceinline__ bool screen(int j, float limf, double) const { return screen_one(qxf, qyf, qzf, t[j], limf); }
     __device__ __forceinline__ double exact(int j, double qx, double qy, double qz) const {
         const float4 c = t[j];
         return dist2_ref(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
     }
 };
 template <> struct LeafTile<double> {
+    static constexpr int TILE_BYTES = 96 * 8;
     double* t;
     double qx_, qy_, qz_;
     __device__ __forceinline__ void init(void* mem, double qx, double qy, double qz) { t = reinterpret_cast<double*>(mem); qx_ = qx; qy_ = qy; qz_ = qz; }
     __device__ __forceinline__ void load(const Vec4<double>* P, int first, int m, unsigned lane) {
-        if ((int)lane < m) { Vec4<double> c = P[first + lane]; t[lane] = c.x; t[32 + lane] = c.y; t[64 + lane] = c.z; }
+        const double nan_ = __longlong_as_double(0x7ff8000000000000ll);
+        double cx = nan_, cy = nan_, cz = nan_;
+        if ((int)lane < m) { Vec4<double> c = P[first + lane]; cx = c.x; cy = c.y; cz = c.z; }
+        t[lane] = cx; t[32 + lane] = cy; t[64 + lane] = cz;
     }
     static __device__ __forceinline__ float screen_limit(float lim) { return lim; }
     __device__ __forceinline__ bool screen(int j, float, double limd) const { return dist2_ref(qx_, qy_, qz_, t[j], t[32 + j], t[64 + j]) < limd; }
@@ -646,8 +665,10 @@ template <> struct LeafTile<double> {
 
 constexpr int SC_LEAFCAP = 240;   // leaves remembered by the select pass for the collect pass (per warp)
 
-template <class S>
+template <class S, bool LOG = false>
 struct SelectVisitor {
+    int* log;           // LOG: this lane's column of the warp's [logcap][32] insertion log (global scratch)
+    int nlog, logcap;
     const Vec4<S>* P;
     LeafTile<S> tile;
     KeyHeap4 hp;
@@ -661,34 +682,43 @@ struct SelectVisitor {
     __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
     __device__ __forceinline__ void settop(float k) { topf = k; topd = (double)k; limf = LeafTile<S>::screen_limit(k); }
     template <bool OVERLAP>
-    __device__ __forceinline__ void scan_tile(int first, int m) {
+    __device__ __forceinline__ void scan_tile(int first, int m, unsigned nmask) {
         // pass 1: one cheap test per candidate (the query itself and coincident particles have d2 == 0 and are weeded out
         // in pass 2, like bulk-loaded candidates); pass 2: serial insertion rounds over the set bits
         unsigned acc = 0;
-#pragma unroll 4
-        for (int j = 0; j < m; j++) acc |= (tile.screen(j, limf, topd) ? 1u : 0u) << j;
+        for (int j0 = 0; j0 < m; j0 += 8) {
+            unsigned a8 = 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) if (tile.screen(j0 + jj, limf, topd)) a8 |= 1u << jj;
+            acc |= a8 << j0;
+        }
         while (__any_sync(0xffffffffu, acc != 0)) {
             if (acc) {
                 const int j = __ffs(acc) - 1;
                 acc &= acc - 1;
                 const int c = first + j;
                 const double d2 = tile.exact(j, qx, qy, qz);
-                if (d2 < topd && d2 > 0.0 && (!OVERLAP || c < r0 || c >= r1)) settop(hp.sift(0, __double2float_rn(d2)));
+                if (d2 < topd && d2 > 0.0 && (!OVERLAP || c < r0 || c >= r1)) {
+                    settop(hp.sift(0, __double2float_rn(d2)));
+                    if (LOG) { if (nlog < logcap) { *log = c; log += 32; } nlog++; }
+                }
             }
         }
     }
-    __device__ __forceinline__ void leaf(int start, int cnt, int node) {
+    __device__ __forceinline__ void leaf(int start, int cnt, int node, unsigned nmask) {
         if (start >= r0 && start + cnt <= r1) return;
-        if (nleaf < SC_LEAFCAP && lane == 0) leaflist[nleaf] = node;
-        nleaf++;
+        if (!LOG) {
+            if (nleaf < SC_LEAFCAP && lane == 0) leaflist[nleaf] = node;
+            nleaf++;
+        }
         const bool overlap = start < r1 && start + cnt > r0;
         for (int base = 0; base < cnt; base += 32) {
             int m = min(32, cnt - base);
             __syncwarp();
             tile.load(P, start + base, m, lane);
             __syncwarp();
-            if (overlap) scan_tile<true>(start + base, m);
-            else scan_tile<false>(start + base, m);
+            if (overlap) scan_tile<true>(start + base, m, nmask);
+            else scan_tile<false>(start + base, m, nmask);
         }
     }
 };
@@ -704,18 +734,23 @@ struct CollectVisitor {
     float thr, limf;   // qualify iff RN_fp32(d2) <= thr ; -1 for lanes that collect nothing
     int cnt, cap;
     int r0, r1;        // with skip_range: candidates in [r0,r1) are left to the separate scan of the bulk range
+    bool skip_bulk;    // traversal form: leave [r0,r1) out (it was scanned separately)
     unsigned lane;
     __device__ __forceinline__ bool need(float lb) const { return lb <= thr; }
     template <bool SKIP>
-    __device__ __forceinline__ void scan(int start, int n) {
+    __device__ __forceinline__ void scan(int start, int n, unsigned nmask) {
         for (int base = 0; base < n; base += 32) {
             int m = min(32, n - base);
             __syncwarp();
             tile.load(P, start + base, m, lane);
             __syncwarp();
             unsigned acc = 0;
-#pragma unroll 4
-            for (int j = 0; j < m; j++) acc |= (tile.screen(j, limf, thr_d) ? 1u : 0u) << j;
+            for (int j0 = 0; j0 < m; j0 += 8) {
+                unsigned a8 = 0;
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) if (tile.screen(j0 + jj, limf, thr_d)) a8 |= 1u << jj;
+                acc |= a8 << j0;
+            }
             while (__any_sync(0xffffffffu, acc != 0)) {
                 if (acc) {
                     const int j = __ffs(acc) - 1;
@@ -731,8 +766,100 @@ struct CollectVisitor {
             }
         }
     }
-    __device__ __forceinline__ void leaf(int start, int n, int = 0) { scan<false>(start, n); }
+    __device__ __forceinline__ void leaf(int start, int n, int, unsigned nmask) {
+        if (skip_bulk) scan<true>(start, n, nmask);
+        else scan<false>(start, n, nmask);
+    }
 };
+
+// SPH epilogues over a lane's neighbour list L (entry s at L[s*32]; `base` = the warp's shared region, whose part after
+// the list holds the per-lane doubles of the kv < kx velocity-density selection).
+template <class S>
+__device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>* __restrict__ P, const int* L, unsigned char* base, unsigned lane,
+                                            int k, int cnt, double d2max, double x0, double y0, double z0, int64_t qi) {
+    if (prm.hsm) prm.hsm[qi] = 0.5 * sqrt(d2max);
+    if (prm.rho && prm.veldens_k == 0) {
+        const double hi = 0.5 * sqrt(d2max);
+        const double norm = 1.0 / pow(hi, 3.0);
+        const double delta = 2.0 / (double)(prm.kernres - 1);
+        const double mi = prm.mass[qi];
+        const double inv_hi = 1.0 / hi, inv_delta = 1.0 / delta, half_res = 0.5 * (prm.kernres - 1), half_norm = 0.5 * norm;
+        double acc = 0;
+        for (int s0 = 0; s0 < cnt; s0 += 4) {
+            // four neighbours per trip: the gathers of P and mass are issued together
+            int id[4]; Vec4<S> c[4]; double mj[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) id[u] = (s0 + u < cnt) ? L[(s0 + u) * 32] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (id[u] >= 0) { c[u] = P[id[u]]; mj[u] = prm.mass[id[u]]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (id[u] >= 0) {
+                    const double rij = sqrt(dist2_ref(x0, y0, z0, (double)c[u].x, (double)c[u].y, (double)c[u].z));
+                    const double r = rij * inv_hi;
+                    const double Wij = wsm_fast(r, (int)(r * half_res), prm.kernres, delta, inv_delta, prm.kern) * half_norm;
+                    acc += Wij * mj[u];
+                    atomicAdd(&prm.rho[id[u]], Wij * mi);
+                }
+            }
+        }
+        atomicAdd(&prm.rho[qi], acc);
+    }
+    if (prm.rho && prm.veldens_k > 0) {
+        const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
+        const Vec4<S> vi = V[qi];
+        const double delta = 2.0 / (double)(prm.kernres - 1);
+        const int kv = min(prm.veldens_k, cnt);
+        double rho = 0;
+        if (kv == cnt) {
+            // every spatial neighbour is used: h from the largest velocity distance, then the sum (two passes)
+            double vmax = 0;
+            for (int s = 0; s < cnt; s++) {
+                Vec4<S> vj = V[L[s * 32]];
+                vmax = fmax(vmax, sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)));
+            }
+            const double hi = 0.5 * vmax;
+            const double norm = 1.0 / pow(hi, 3.0);
+            for (int s = 0; s < cnt; s++) {
+                Vec4<S> vj = V[L[s * 32]];
+                double r = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)) / hi;
+                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+            }
+        } else if (kv > 0) {
+            // kv < kx: exact fp64 selection on a per-lane array of doubles placed after the list (want_doubles layout)
+            double* D = reinterpret_cast<double*>(base + (size_t)k * 32 * 4);
+            for (int s = 0; s < cnt; s++) {
+                Vec4<S> vj = V[L[s * 32]];
+                D[s * 32 + lane] = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
+            }
+            auto dsift = [&](int p, int n, double d) {
+                while (true) {
+                    int c = 2 * p + 1;
+                    if (c >= n) break;
+                    double dc = D[c * 32 + lane];
+                    if (c + 1 < n) { double dr = D[(c + 1) * 32 + lane]; if (dr > dc) { c = c + 1; dc = dr; } }
+                    if (d >= dc) break;
+                    D[p * 32 + lane] = dc;
+                    p = c;
+                }
+                D[p * 32 + lane] = d;
+            };
+            for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, D[p * 32 + lane]);
+            for (int s = kv; s < cnt; s++) {
+                double vd = D[s * 32 + lane];
+                if (vd < D[lane]) dsift(0, kv, vd);
+            }
+            const double hi = 0.5 * D[lane];
+            const double norm = 1.0 / pow(hi, 3.0);
+            for (int e = kv; e > 0; e--) {
+                double r = D[lane] / hi;
+                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+                dsift(0, e - 1, D[(e - 1) * 32 + lane]);
+            }
+        }
+        prm.rho[qi] = rho;
+    }
+}
 
 static inline size_t sc_warp_bytes(int k, bool want_doubles) {
     int G = heap4_groups(k + 1);
@@ -815,7 +942,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
 
     // --------------------------------------------------------------------------------------------- collect
     CollectVisitor<S> c2;
-    c2.P = P; c2.L = reinterpret_cast<int*>(base) + lane; c2.lane = lane;
+    c2.P = P; c2.L = reinterpret_cast<int*>(base) + lane; c2.lane = lane; c2.skip_bulk = false;
     c2.tile.init(tile_mem, x0, y0, z0);
     c2.qx = x0; c2.qy = y0; c2.qz = z0;
     c2.r0 = r0i; c2.r1 = r1i;
@@ -828,14 +955,15 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
     if (nleaf <= SC_LEAFCAP) {
         // every leaf that can hold one of the k nearest was scanned by the select pass (a lane's final neighbours were
         // below its bound at all times): re-scan exactly those tiles, plus the bulk-loaded range, without walking the tree
-        c2.template scan<false>(r0i, r1i - r0i);
+        c2.template scan<false>(r0i, r1i - r0i, 0xffffffffu);
         for (int t = 0; t < nleaf; t++) {
             const int node = leaflist[t];
             const NodeLo lo = prm.nlo[node];
             const NodeHi hi = prm.nhi[node];
             const float lb = box_lb(qb.lx, qb.ly, qb.lz, qb.hx, qb.hy, qb.hz, lo, hi);
-            if (!__any_sync(0xffffffffu, collecting && c2.need(lb))) continue;     // the bounds have tightened since
-            c2.template scan<true>(lo.start, hi.end - lo.start);
+            const unsigned nmask = __ballot_sync(0xffffffffu, collecting && c2.need(lb));
+            if (!nmask) continue;                                                  // the bounds have tightened since
+            c2.template scan<true>(lo.start, hi.end - lo.start, nmask);
         }
     } else {
         traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, collecting);
@@ -843,81 +971,155 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, i
     if (!collecting) return;
 
     // -------------------------------------------------------------------------------------------- epilogues
-    const int cnt = c2.cnt;
-    const double d2max = short_of_k ? KNN_SENTINEL : c2.d2max;
-    if (prm.hsm) prm.hsm[qi] = 0.5 * sqrt(d2max);
-    if (prm.rho && prm.veldens_k == 0) {
-        const double hi = 0.5 * sqrt(d2max);
-        const double norm = 1.0 / pow(hi, 3.0);
-        const double delta = 2.0 / (double)(prm.kernres - 1);
-        const double mi = prm.mass[qi];
-        double acc = 0;
-        for (int s = 0; s < cnt; s++) {
-            int id = c2.L[s * 32];
-            Vec4<S> c = P[id];
-            double rij = sqrt(dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z));
-            double r = rij / hi;
-            double Wij = 0.5 * wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
-            acc += Wij * prm.mass[id];
-            atomicAdd(&prm.rho[id], Wij * mi);
-        }
-        atomicAdd(&prm.rho[qi], acc);
-    }
-    if (prm.rho && prm.veldens_k > 0) {
-        const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
-        const Vec4<S> vi = V[qi];
-        const double delta = 2.0 / (double)(prm.kernres - 1);
-        const int kv = min(prm.veldens_k, cnt);
-        double rho = 0;
-        if (kv == cnt) {
-            // every spatial neighbour is used: h from the largest velocity distance, then the sum (two passes)
-            double vmax = 0;
-            for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[c2.L[s * 32]];
-                vmax = fmax(vmax, sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)));
-            }
-            const double hi = 0.5 * vmax;
-            const double norm = 1.0 / pow(hi, 3.0);
-            for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[c2.L[s * 32]];
-                double r = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)) / hi;
-                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
-            }
-        } else if (kv > 0) {
-            // kv < kx: exact fp64 selection on a per-lane array of doubles placed after the list (want_doubles layout)
-            double* D = reinterpret_cast<double*>(base + (size_t)k * 32 * 4);
-            for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[c2.L[s * 32]];
-                D[s * 32 + lane] = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
-            }
-            auto dsift = [&](int p, int n, double d) {
-                while (true) {
-                    int c = 2 * p + 1;
-                    if (c >= n) break;
-                    double dc = D[c * 32 + lane];
-                    if (c + 1 < n) { double dr = D[(c + 1) * 32 + lane]; if (dr > dc) { c = c + 1; dc = dr; } }
-                    if (d >= dc) break;
-                    D[p * 32 + lane] = dc;
-                    p = c;
+    sc_epilogue<S>(prm, P, c2.L, base, lane, k, c2.cnt, short_of_k ? KNN_SENTINEL : c2.d2max, x0, y0, z0, qi);
+}
+
+// =========================================================================================== select + log
+// Same select pass, but every candidate that enters a lane's heap is also appended to the lane's insertion LOG in a
+// global scratch (one [logcap][32] block per resident warp, written once and read once, so it lives in L2).  Every one of
+// the final k nearest was inserted at some point (its d2 was below the lane's bound at all times), so the collect pass
+// is a filter over the log (~1.4 k entries per lane) plus the bulk-loaded range instead of a second scan of ~65 leaf tiles.
+// Persistent grid: warps draw 32-query groups from a global counter, so a warp's scratch block is reused and the
+// grid is exactly one wave whatever the particle count.
+static inline size_t sl_warp_bytes(int k, bool want_doubles, int tile_bytes) {
+    int G = heap4_groups(k + 1);
+    size_t keys = (size_t)(G + 1) * 32 * 16, list = (size_t)k * 32 * 4;
+    size_t region = keys > list ? keys : list;
+    if (want_doubles) region = list + (size_t)k * 32 * 8 > region ? list + (size_t)k * 32 * 8 : region;
+    return region + tile_bytes + TRAV_STACK * 4;
+}
+
+template <class S, int MB>
+__global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams prm, int want_doubles, int* __restrict__ work_counter,
+                                                                int32_t* __restrict__ logbuf, int logcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    const int k = prm.k, kcap = k + 1;
+    const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
+    size_t region = (size_t)(G + 1) * 32 * 16;
+    if ((size_t)k * 32 * 4 > region) region = (size_t)k * 32 * 4;
+    if (want_doubles && (size_t)k * 32 * 12 > region) region = (size_t)k * 32 * 12;
+    const size_t warp_bytes = region + LeafTile<S>::TILE_BYTES + TRAV_STACK * 4;
+    unsigned char* base = smem_raw + w * warp_bytes;
+    void* tile_mem = base + region;
+    int* stack = reinterpret_cast<int*>(base + region + LeafTile<S>::TILE_BYTES);
+    int* log = logbuf + ((size_t)blockIdx.x * KNN_WARPS + w) * (size_t)logcap * 32 + lane;
+
+    const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
+    const int64_t ngroups = (prm.q1 - prm.q0 + 31) >> 5;
+    while (true) {
+        int64_t group = 0;
+        if (lane == 0) group = (int64_t)atomicAdd(work_counter, 1);
+        group = __shfl_sync(0xffffffffu, group, 0);
+        if (group >= ngroups) break;
+        const int64_t g0 = prm.q0 + group * 32;
+        const int64_t qi = g0 + lane;
+        const bool valid = qi < prm.q1 && (!prm.active || prm.active[qi]);
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        double x0 = 0, y0 = 0, z0 = 0;
+        if (valid) { Vec4<S> c = P[qi]; x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z; }
+        const QueryBox qb = make_qbox(x0, y0, z0);
+        int r0i, r1i, nlog;
+
+        // ------------------------------------------------------------------------------------------ select
+        float key_k, key_kp1;
+        {
+            SelectVisitor<S, true> v;
+            v.P = P; v.lane = lane;
+            v.tile.init(tile_mem, x0, y0, z0);
+            v.leaflist = nullptr; v.nleaf = 0;
+            v.log = log; v.nlog = 0; v.logcap = logcap;
+            v.hp.kb = base + lane * 16; v.hp.G = G;
+            const int self = valid ? (int)qi : -1;
+            v.qx = x0; v.qy = y0; v.qz = z0;
+            int64_t want = (int64_t)kcap;
+            int64_t r0 = g0 + 16 - want / 2;
+            if (r0 + want > prm.n) r0 = prm.n - want;
+            if (r0 < 0) r0 = 0;
+            int64_t r1 = r0 + want;
+            if (r1 > prm.n) r1 = prm.n;
+            v.r0 = (int)r0; v.r1 = (int)r1;
+            int filled = 0;
+            for (int64_t b0 = r0; b0 < r1; b0 += 32) {
+                int m = (int)min((int64_t)32, r1 - b0);
+                __syncwarp();
+                v.tile.load(P, (int)b0, m, lane);
+                __syncwarp();
+                for (int j = 0; j < m; j++) {
+                    double d2 = v.tile.exact(j, x0, y0, z0);
+                    if (valid && (int)(b0 + j) != self && d2 > 0.0) { *v.hp.keyp(filled) = __double2float_rn(d2); filled++; }
                 }
-                D[p * 32 + lane] = d;
-            };
-            for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, D[p * 32 + lane]);
-            for (int s = kv; s < cnt; s++) {
-                double vd = D[s * 32 + lane];
-                if (vd < D[lane]) dsift(0, kv, vd);
             }
-            const double hi = 0.5 * D[lane];
-            const double norm = 1.0 / pow(hi, 3.0);
-            for (int e = kv; e > 0; e--) {
-                double r = D[lane] / hi;
-                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
-                dsift(0, e - 1, D[(e - 1) * 32 + lane]);
-            }
+            for (; filled < NN; filled++) *v.hp.keyp(filled) = (valid && filled < kcap) ? __uint_as_float(FKEY_INF) : 0.f;
+            for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p));
+            v.settop(v.hp.rootkey());
+            traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
+            key_kp1 = v.hp.rootkey();
+            v.hp.sift(0, 0.f);
+            key_k = v.hp.rootkey();
+            r0i = v.r0; r1i = v.r1; nlog = v.nlog;
         }
-        prm.rho[qi] = rho;
+        const bool short_of_k = __float_as_uint(key_k) == FKEY_INF;
+        // inexact key order: the exact kernel redoes the query
+        const bool flagged = valid && key_k == key_kp1 && !short_of_k;
+        if (flagged) {
+            int slot = atomicAdd(prm.flag_count, 1);
+            prm.flag_list[slot] = (int)qi;
+        }
+        __syncwarp();   // the key groups are dead from here on: the region is reused for the index list
+
+        // ----------------------------------------------------------------------------------------- collect
+        const bool collecting = valid && !flagged;
+        CollectVisitor<S> c2;
+        c2.P = P; c2.L = reinterpret_cast<int*>(base) + lane; c2.lane = lane; c2.skip_bulk = true;
+        c2.tile.init(tile_mem, x0, y0, z0);
+        c2.qx = x0; c2.qy = y0; c2.qz = z0;
+        c2.r0 = r0i; c2.r1 = r1i;
+        c2.cnt = 0; c2.cap = k; c2.d2max = 0;
+        c2.thr = collecting ? key_k : -1.f;
+        c2.thr_d = collecting ? (double)__uint_as_float(__float_as_uint(key_k) + (short_of_k ? 0u : 1u)) : -1.0;   // next float above key_k
+        if (short_of_k && collecting) c2.thr_d = 3.0e38 * 10.0;
+        c2.limf = LeafTile<S>::screen_limit(c2.thr);
+        c2.template scan<false>(r0i, r1i - r0i, 0xffffffffu);      // the bulk-loaded range
+        const bool overflowed = collecting && nlog > logcap;      // log incomplete: this lane collects by a second traversal
+        {
+            const int mynl = (collecting && !overflowed) ? nlog : 0;
+            const int nmax = __reduce_max_sync(0xffffffffu, mynl);
+            int cnt = c2.cnt;
+            double d2max = c2.d2max;
+            for (int s0 = 0; s0 < nmax; s0 += 4) {
+                int cidx[4];
+                Vec4<S> pc[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) cidx[u] = (s0 + u < mynl) ? log[(s0 + u) * 32] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (cidx[u] >= 0) pc[u] = P[cidx[u]];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (cidx[u] >= 0) {
+                        const double d2 = dist2_ref(x0, y0, z0, (double)pc[u].x, (double)pc[u].y, (double)pc[u].z);
+                        if (d2 < c2.thr_d && __double2float_rn(d2) <= c2.thr && cnt < k) {
+                            c2.L[cnt * 32] = cidx[u];
+                            cnt++;
+                            d2max = fmax(d2max, d2);
+                        }
+                    }
+                }
+            }
+            c2.cnt = cnt; c2.d2max = d2max;
+        }
+        if (__any_sync(0xffffffffu, overflowed)) {
+            const float thr_keep = c2.thr, limf_keep = c2.limf;
+            const double thrd_keep = c2.thr_d;
+            if (!overflowed) { c2.thr = -1.f; c2.thr_d = -1.0; c2.limf = -1.f; }      // the other lanes are complete
+            traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, overflowed);
+            c2.thr = thr_keep; c2.limf = limf_keep; c2.thr_d = thrd_keep;
+        }
+        if (collecting) sc_epilogue<S>(prm, P, c2.L, base, lane, k, c2.cnt, short_of_k ? KNN_SENTINEL : c2.d2max, x0, y0, z0, qi);
+        __syncwarp();
     }
 }
+
 
 static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.nlo = t.nlo; p.nhi = t.nhi; p.bucket = t.bucket;
@@ -964,7 +1166,7 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
         // ---- fast path + exact fallback for the flagged queries ----------------------------------------------
         p.kcap = a.k + 1;
         const char* em = getenv("NBK_KNN_MODE");
-        const int mode = em ? atoi(em) : 1;     // 1: select-then-collect (default), 0: (key,index) heap
+        const int mode = em ? atoi(em) : 2;     // 2: select + insertion log (default), 1: select-then-collect, 0: (key,index) heap
         // nodes of up to `leaf` particles are scanned as one tile: fewer node tests and better balanced insertion rounds
         {
             const char* e = getenv("NBK_KNN_LEAF");
@@ -972,6 +1174,56 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             if (leaf > p.bucket) p.bucket = leaf;
         }
         const int want_doubles = (a.veldens_k > 0 && a.veldens_k < a.k) ? 1 : 0;
+        if (mode == 2) {
+            size_t smem = sl_warp_bytes(a.k, want_doubles, t.store_bytes == 4 ? 32 * 16 : 96 * 8) * KNN_WARPS;
+            NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");
+            const char* e = getenv("NBK_KNN_LOGCAP");
+            int logcap = e ? atoi(e) : 4 * a.k;
+            if (logcap < 64) logcap = 64;
+            int nsm = 0, per_sm = 0;
+            NBK_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, t.device));
+            // register budget follows the shared-memory budget: MB = CTAs per SM the kernel is compiled for (5: 96, 6: 80, 8: 64 regs)
+            int fit = (int)(233472 / (smem + 1024));
+            const char* emb = getenv("NBK_KNN_MB");
+            if (emb) fit = atoi(emb);
+            const int mb = fit >= 8 ? 8 : (fit >= 6 ? 6 : 5);
+            const int64_t ngroups = (rows + 31) / 32;
+            DevBuf<int> counters(2);
+            DevBuf<int32_t> flist(rows);
+            DevBuf<int32_t> logbuf;
+            NBK_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), t.stream));
+            p.flag_count = counters.p; p.flag_list = flist.p;
+            auto go = [&](auto kern) {
+                NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                NBK_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KNN_WARPS * 32, smem));
+                NBK_REQUIRE(per_sm >= 1, NBK_ERR_ARG, "k too large for the shared-memory heaps");
+                int64_t blocks = (int64_t)nsm * per_sm;
+                if (blocks > (ngroups + KNN_WARPS - 1) / KNN_WARPS) blocks = (ngroups + KNN_WARPS - 1) / KNN_WARPS;
+                logbuf.alloc((size_t)blocks * KNN_WARPS * logcap * 32);
+                kern<<<(int)blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles, counters.p + 1, logbuf.p, logcap);
+            };
+            if (t.store_bytes == 4) {
+                if (mb == 8) go(knn_sl_kernel<float, 8>); else if (mb == 6) go(knn_sl_kernel<float, 6>); else go(knn_sl_kernel<float, 5>);
+            } else {
+                if (mb == 8) go(knn_sl_kernel<double, 8>); else if (mb == 6) go(knn_sl_kernel<double, 6>); else go(knn_sl_kernel<double, 5>);
+            }
+            NBK_CHECK(cudaGetLastError());
+            t.last_launches += 2;
+            int nflag = 0;
+            NBK_CHECK(cudaMemcpyAsync(&nflag, counters.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
+            NBK_CHECK(cudaStreamSynchronize(t.stream));
+            t.last_flagged = nflag;
+            if (nflag > 0) {
+                KnnParams pe = p;
+                pe.kcap = a.k;
+                pe.bucket = t.bucket;
+                pe.qlist = flist.p; pe.nq = nflag;
+                pe.flag_count = nullptr; pe.flag_list = nullptr;
+                run_exact(t, pe, nflag);
+                t.last_launches += 1;
+            }
+            return;
+        }
         size_t warp_bytes = mode == 1 ? sc_warp_bytes(a.k, want_doubles) : fast_warp_bytes(p.kcap);
         size_t smem = warp_bytes * KNN_WARPS;
         NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");

@@ -50,7 +50,8 @@ __device__ __forceinline__ QueryBox make_qbox(double x, double y, double z) {
 
 // Visitor interface (all methods called by the full warp):
 //   bool need(float lb)             per-lane: could this lane accept something at distance^2 >= lb ?
-//   void leaf(int start, int cnt, int node)   process particles [start, start+cnt) of node `node`
+//   void leaf(int start, int cnt, int node, unsigned nmask)   process particles [start, start+cnt) of node `node`;
+//                                   nmask = ballot of the lanes whose bound still reaches the node's box
 // ORDERED: always descend the left child first so leaves are met in ascending tree-index order.
 //
 // Control flow: a node is tested when it is reached as a child; the nearer child (by vote of the lanes that
@@ -64,15 +65,17 @@ __device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const N
     int node = 0;
     NodeLo lo = nlo[0];
     NodeHi hi = nhi[0];
+    unsigned nmask;     // lanes that need `node`
     {
         float lb = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, lo, hi);
-        if (!__any_sync(0xffffffffu, on && v.need(lb))) return;
+        nmask = __ballot_sync(0xffffffffu, on && v.need(lb));
+        if (!nmask) return;
     }
     while (true) {
         // invariant: `node` (bounds lo/hi) is needed by at least one lane
         bool descend = false;
         if (hi.end - lo.start <= bucket) {
-            v.leaf(lo.start, hi.end - lo.start, node);
+            v.leaf(lo.start, hi.end - lo.start, node, nmask);
         } else {
             const int c1 = 2 * node + 1, c2 = c1 + 1;
             NodeLo l1 = nlo[c1]; NodeHi h1 = nhi[c1];
@@ -97,6 +100,7 @@ __device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const N
                 node = take1 ? c1 : c2;
                 lo = take1 ? l1 : l2;
                 hi = take1 ? h1 : h2;
+                nmask = take1 ? m1 : m2;
                 descend = true;
             }
         }
@@ -107,7 +111,8 @@ __device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const N
             node = stack[--sp];
             lo = nlo[node]; hi = nhi[node];
             float lb = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, lo, hi);
-            if (__any_sync(0xffffffffu, on && v.need(lb))) { found = true; break; }
+            nmask = __ballot_sync(0xffffffffu, on && v.need(lb));
+            if (nmask) { found = true; break; }
         }
         if (!found) return;
     }

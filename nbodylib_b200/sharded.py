@@ -172,6 +172,8 @@ class ShardedTree:
         self._dens = {"tree": tree, "halo": halo, "active": active, "n_all": n_all,
                       "rho": torch.empty(n_all, dtype=self.f, device=self.dev), "hsm": torch.empty(n_all, dtype=self.f, device=self.dev)}
         self.stats["ghosts_knn"] = int(n_all - self.n_owned)
+        self.stats["h_knn"] = float(self.h_knn)
+        self.stats["density_setups"] = self.stats.get("density_setups", 0) + 1
 
     def CalcDensity(self, Nsmooth=64, out=None, max_widen=6):
         """Global KDTree::CalcDensity(Nsmooth) for this rank's owned particles (indexed like the rank's input)."""

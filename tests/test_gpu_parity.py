@@ -179,6 +179,27 @@ def test_fp32_key_ties_fall_back_to_exact_heap(nb, port):
         np.testing.assert_allclose(t.CalcVelDensity(7, 18), port.veldensity(pos, vel, 7, 18), rtol=RTOL_RHO)
 
 
+@pytest.mark.parametrize("env", [{"NBK_KNN_LOGCAP": "64"}, {"NBK_KNN_MODE": "1"}, {"NBK_KNN_MODE": "0"},
+                                 {"NBK_KNN_LEAF": "16"}, {"NBK_KNN_EXACT_ONLY": "1"}])
+def test_density_kernel_variants(nb, port, monkeypatch, env):
+    """Every variant of the density kernel gives the oracle's answer: insertion log too small for most lanes (they collect
+    by a second traversal), the older select-then-collect and (key,index)-heap kernels, unmerged leaves, exact fp64 heap only.  Both storage widths."""
+    from nbodylib_b200.synth import clustered_small
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n, k = 30011, 40
+    pos, vel, mass = clustered_small(n, seed=77)
+    orho, oh = port.density(pos, mass, k)
+    ovd = port.veldensity(pos, vel, 13, k)
+    for flags in (0, 1 << 4):
+        with nb.KDTree(pos, vel, mass, flags=flags) as t:
+            rho, h = t.CalcDensity(k, want_h=True)
+            np.testing.assert_allclose(rho, orho, rtol=RTOL_RHO)
+            assert np.array_equal(h, oh)
+            np.testing.assert_allclose(t.CalcVelDensity(13, k), ovd, rtol=RTOL_RHO)
+            np.testing.assert_allclose(t.CalcVelDensity(k, k), port.veldensity(pos, vel, k, k), rtol=RTOL_RHO)
+
+
 def test_tphs_form_a_equals_fof6d_form_b(nb, port):
     """BASELINE config 4: ScalePhase + TPHS tree + FOF(1.0) == FOFCriterion(FOF6d); scaled coordinates are not
     fp32-representable, so the tree must keep fp64 coordinates to stay bit-exact."""
