@@ -127,25 +127,36 @@ __global__ void __launch_bounds__(PRIM_THREADS) rs_hist_kernel(const K* __restri
 }
 
 // Stable scatter.  Warp w owns tile items [w*512, w*512+512); item j of lane l is w*512 + j*32 + l, so
-// (warp, round, lane) order == index order and ranks computed round by round are stable.
+// (warp, round, lane) order == index order and ranks computed round by round are stable.  The tile is first
+// sorted by digit inside shared memory and then written out in sorted order, so consecutive threads write
+// consecutive addresses of a digit's run (a direct scatter would touch 32 sectors per store instruction).
 template <class K>
 __global__ void __launch_bounds__(PRIM_THREADS) rs_scatter_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, int shift,
                                                                   const uint32_t* __restrict__ table, int ntiles, K* __restrict__ okeys,
                                                                   uint32_t* __restrict__ ovals) {
     __shared__ uint32_t whist[8][256];
-    __shared__ uint32_t gofs[256];
+    __shared__ uint32_t gofs[256];       // global position of sorted-tile slot t of digit d = gofs[d] + t
+    __shared__ uint32_t dstart[256];     // first sorted-tile slot of digit d
+    __shared__ uint32_t swarp[8];
+    __shared__ uint64_t stage64[PRIM_TILE];
+    K* stage_k = reinterpret_cast<K*>(stage64);
+    uint32_t* stage_v = reinterpret_cast<uint32_t*>(stage64);
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < 8; i++) whist[i][threadIdx.x] = 0;
     __syncthreads();
-    int64_t base = (int64_t)blockIdx.x * PRIM_TILE + w * 512;
+    const int64_t tile_base = (int64_t)blockIdx.x * PRIM_TILE;
+    const int tile_count = (int)((n - tile_base) < (int64_t)PRIM_TILE ? (n - tile_base) : (int64_t)PRIM_TILE);
+    int64_t base = tile_base + w * 512;
     K key[PRIM_ITEMS];
+    uint32_t val[PRIM_ITEMS];
     uint32_t rank[PRIM_ITEMS];
 #pragma unroll
     for (int j = 0; j < PRIM_ITEMS; j++) {
         int64_t i = base + j * 32 + lane;
         key[j] = (i < n) ? keys[i] : (K)0;
+        val[j] = (i < n) ? (vals ? vals[i] : (uint32_t)i) : 0u;
     }
 #pragma unroll
     for (int j = 0; j < PRIM_ITEMS; j++) {
@@ -168,7 +179,10 @@ __global__ void __launch_bounds__(PRIM_THREADS) rs_scatter_kernel(const K* __res
             whist[i][threadIdx.x] = run;
             run += c;
         }
-        gofs[threadIdx.x] = table[(size_t)threadIdx.x * ntiles + blockIdx.x];
+        uint32_t tot;
+        const uint32_t ds = block_excl_scan_256(run, swarp, &tot);
+        dstart[threadIdx.x] = ds;
+        gofs[threadIdx.x] = table[(size_t)threadIdx.x * ntiles + blockIdx.x] - ds;
     }
     __syncthreads();
 #pragma unroll
@@ -176,10 +190,33 @@ __global__ void __launch_bounds__(PRIM_THREADS) rs_scatter_kernel(const K* __res
         int64_t i = base + j * 32 + lane;
         if (i < n) {
             uint32_t d = (uint32_t)(key[j] >> shift) & 255u;
-            uint32_t dst = gofs[d] + whist[w][d] + rank[j];
-            okeys[dst] = key[j];
-            ovals[dst] = vals ? vals[i] : (uint32_t)i;
+            rank[j] = dstart[d] + whist[w][d] + rank[j];       // slot in the sorted tile
+            stage_k[rank[j]] = key[j];
         }
+    }
+    __syncthreads();
+    uint32_t gpos[PRIM_ITEMS];
+#pragma unroll
+    for (int r = 0; r < PRIM_ITEMS; r++) {
+        const int tpos = r * PRIM_THREADS + threadIdx.x;
+        gpos[r] = 0;
+        if (tpos < tile_count) {
+            const K k = stage_k[tpos];
+            gpos[r] = gofs[(uint32_t)(k >> shift) & 255u] + (uint32_t)tpos;
+            okeys[gpos[r]] = k;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PRIM_ITEMS; j++) {
+        int64_t i = base + j * 32 + lane;
+        if (i < n) stage_v[rank[j]] = val[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PRIM_ITEMS; r++) {
+        const int tpos = r * PRIM_THREADS + threadIdx.x;
+        if (tpos < tile_count) ovals[gpos[r]] = stage_v[tpos];
     }
 }
 

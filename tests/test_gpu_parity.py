@@ -414,3 +414,30 @@ def test_fof_linked_lists(nb):
                 i = nxt[i]
             assert np.array_equal(np.array(chain), members)          # ascending tree index
             assert np.all(head[members] == members[0]) and np.all(tail[members] == members[-1])
+
+
+@pytest.mark.parametrize("n,bucket,flags", [(1, 16, 0), (15, 16, 0), (4096, 16, 0), (4097, 16, 0), (8193, 1, 0), (50021, 16, 0), (50021, 3, 1 << 4),
+                                            (300007, 16, 0), (300007, 100, 1 << 4), (131072, 1024, 0)])
+def test_build_v2_equals_v1(nb, monkeypatch, n, bucket, flags):
+    """The rank-space build (global levels + one shared-memory kernel for nodes <= 4096 particles) produces exactly the
+    tree of the first level-parallel build: same particle order, same node ranges, bounds and cut dimensions.
+    Sizes straddle the shared-memory capacity, ties come from a coarse coordinate grid."""
+    rng = np.random.default_rng(n + bucket)
+    pos = rng.random((n, 3))
+    pos[: n // 3] = np.round(pos[: n // 3] * 64) / 64           # many exactly equal coordinates -> ties at the medians
+    pos = pos.astype(np.float32).astype(np.float64)
+    out = []
+    for mode in ("1", "2"):
+        monkeypatch.setenv("NBK_BUILD", mode)
+        with nb.KDTree(pos, None, None, bucket_size=bucket, flags=flags) as t:
+            out.append((t.order(), t.nodes(), t.GetNumNodes(), t.GetNumLeafNodes()))
+    (o1, nd1, nn1, nl1), (o2, nd2, nn2, nl2) = out
+    assert (nn1, nl1) == (nn2, nl2)
+    assert np.array_equal(o1, o2)
+    s1, e1, c1, b1 = nd1
+    s2, e2, c2, b2 = nd2
+    present = s1 >= 0
+    assert np.array_equal(present, s2 >= 0)
+    assert np.array_equal(s1[present], s2[present]) and np.array_equal(e1[present], e2[present]) and np.array_equal(c1[present], c2[present])
+    assert np.array_equal(b1[present], b2[present])
+    assert int(present.sum()) == nn1
