@@ -160,6 +160,16 @@ int nbk_fof(nbk_tree* t, double fdist, int minnum, int order, const int32_t* pre
 int nbk_fof_criterion(nbk_tree* t, int criterion, const double* params, int minnum, int order,
                       const int32_t* precheck, int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags);
 
+/* Replaces KDTree::FOFCriterionSetBasisForLinks(cmp, params, numgroup, minnum, order, ipcheckflag, check, ...)
+ * (KDFOF.cxx:268-378, KDLeafNode.cxx:620-652).  check (n entries by ID, the values of the caller's FOFcheckfunc): only
+ * particles with check == 0 start or extend groups; the others can be linked into a group but never link further.
+ * The groups of the check == 0 particles are the connected components of their mutual links (identical to the
+ * reference).  A particle with check != 0 that is linked by members of several groups joins the group whose first
+ * member comes first in tree order -- the group the reference's serial search reaches it from -- so the assignment
+ * can differ from the reference only where the two tree orders differ inside a leaf. */
+int nbk_fof_criterion_basis(nbk_tree* t, int criterion, const double* params, int minnum, int order,
+                            const int32_t* check, int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags);
+
 /* Scratch buffers are recycled through the device's stream-ordered memory pool and kept across calls and
  * trees (allocating and freeing GBs through the driver costs more than the kernels).  This hands the cached
  * memory back to the driver (e.g. before another library needs the HBM). */

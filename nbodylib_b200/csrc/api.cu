@@ -244,20 +244,33 @@ int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int 
     const int tb = 256;
 
     // ---- stage ------------------------------------------------------------------------------------
+    // The tree is built on one phase-space half only (positions; velocities for TVEL).  With host input whose storage
+    // width is known up front, the other half and the masses are staged by a side thread on its own stream while the main
+    // stream sorts and partitions; the build joins it right before the final particle gather.
     NBK_CHECK(cudaEventRecord(t->ev0, st));
-    DevBuf<double> rpos((size_t)3 * n), rvel(p->vel ? (size_t)3 * n : 0), rmass(p->mass ? (size_t)n : 0);
-    stage3(p->pos, p->pos_stride, p->real_bytes, p->on_device != 0, n, 3, rpos.p, st);
-    if (p->vel) stage3(p->vel, p->vel_stride, p->real_bytes, p->on_device != 0, n, 3, rvel.p, st);
-    if (p->mass) stage3(p->mass, p->mass_stride, p->real_bytes, p->on_device != 0, n, 1, rmass.p, st);
+    const bool tvel = treetype == NBK_TVEL;
+    const void* prim_src = tvel ? p->vel : p->pos;
+    const int64_t prim_stride = tvel ? p->vel_stride : p->pos_stride;
+    const void* sec_src = tvel ? p->pos : p->vel;
+    const int64_t sec_stride = tvel ? p->pos_stride : p->vel_stride;
+    const bool host_in = p->on_device == 0;
+    const bool width_known = p->real_bytes == 4 || (flags & (NBK_STORE_F64 | NBK_STORE_F32));
+    const bool overlap = host_in && width_known && (sec_src || p->mass) && getenv("NBK_NO_OVERLAP") == nullptr;
+    DevBuf<double> rprim((size_t)3 * n), rsec, rmass;
+    stage3(prim_src, prim_stride, p->real_bytes, !host_in, n, 3, rprim.p, st);
+    if (!overlap) {
+        if (sec_src) { rsec.alloc((size_t)3 * n); stage3(sec_src, sec_stride, p->real_bytes, !host_in, n, 3, rsec.p, st); }
+        if (p->mass) { rmass.alloc((size_t)n); stage3(p->mass, p->mass_stride, p->real_bytes, !host_in, n, 1, rmass.p, st); }
+    }
     NBK_CHECK(cudaEventRecord(t->ev1, st));
 
     // ---- storage precision: fp32 when it is exact (or forced), fp64 otherwise ---------------------------
     int store = 4;
-    if (p->real_bytes == 8) {
+    if (p->real_bytes == 8 && !width_known) {
         DevBuf<unsigned long long> cnt(1);
         NBK_CHECK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), st));
-        count_inexact_kernel<<<div_up(3 * n, tb), tb, 0, st>>>(rpos.p, 3 * n, cnt.p);
-        if (p->vel) count_inexact_kernel<<<div_up(3 * n, tb), tb, 0, st>>>(rvel.p, 3 * n, cnt.p);
+        count_inexact_kernel<<<div_up(3 * n, tb), tb, 0, st>>>(rprim.p, 3 * n, cnt.p);
+        if (sec_src) count_inexact_kernel<<<div_up(3 * n, tb), tb, 0, st>>>(rsec.p, 3 * n, cnt.p);
         unsigned long long c = 0;
         NBK_CHECK(cudaMemcpyAsync(&c, cnt.p, sizeof(c), cudaMemcpyDeviceToHost, st));
         NBK_CHECK(cudaStreamSynchronize(st));
@@ -270,24 +283,47 @@ int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int 
     t->store_bytes = store;
 
     NBK_CHECK(cudaEventRecord(t->ev2, st));
-    const bool tvel = treetype == NBK_TVEL;
-    const double* prim_raw = tvel ? rvel.p : rpos.p;
-    const double* sec_raw = tvel ? rpos.p : (p->vel ? rvel.p : nullptr);
-    if (store == 4) {
-        DevBuf<Vec4<float>> a(n), b(sec_raw ? n : 0);
-        pack4_kernel<float><<<div_up(n, tb), tb, 0, st>>>(prim_raw, n, a.p);
-        if (sec_raw) pack4_kernel<float><<<div_up(n, tb), tb, 0, st>>>(sec_raw, n, b.p);
-        NBK_CHECK(cudaStreamSynchronize(st));
-        rpos.release(); rvel.release();
-        build_tree<float>(*t, a.p, sec_raw ? b.p : nullptr, p->mass ? rmass.p : nullptr);
-    } else {
-        DevBuf<Vec4<double>> a(n), b(sec_raw ? n : 0);
-        pack4_kernel<double><<<div_up(n, tb), tb, 0, st>>>(prim_raw, n, a.p);
-        if (sec_raw) pack4_kernel<double><<<div_up(n, tb), tb, 0, st>>>(sec_raw, n, b.p);
-        NBK_CHECK(cudaStreamSynchronize(st));
-        rpos.release(); rvel.release();
-        build_tree<double>(*t, a.p, sec_raw ? b.p : nullptr, p->mass ? rmass.p : nullptr);
-    }
+    auto run = [&](auto tag) {
+        typedef decltype(tag) S;
+        DevBuf<Vec4<S>> a(n), b(sec_src ? n : 0);
+        if (p->mass && overlap) rmass.alloc((size_t)n);
+        pack4_kernel<S><<<div_up(n, tb), tb, 0, st>>>(rprim.p, n, a.p);
+        rprim.release();                                   // stream ordered: freed once the pack has run
+        std::thread side;
+        std::exception_ptr side_err;
+        cudaStream_t s2 = nullptr;
+        if (overlap) {
+            NBK_CHECK(cudaStreamSynchronize(st));          // the buffers the side stream fills exist from here on
+            NBK_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+            Vec4<S>* bp = b.p; double* mp = rmass.p;
+            const int dev = device;
+            side = std::thread([&, bp, mp, dev, s2]() {
+                try {
+                    NBK_CHECK(cudaSetDevice(dev));
+                    cur_stream() = s2;
+                    if (sec_src) {
+                        DevBuf<double> tmp((size_t)3 * n);
+                        stage3(sec_src, sec_stride, p->real_bytes, false, n, 3, tmp.p, s2);
+                        pack4_kernel<S><<<div_up(n, tb), tb, 0, s2>>>(tmp.p, n, bp);
+                        NBK_CHECK(cudaStreamSynchronize(s2));
+                    }
+                    if (p->mass) stage3(p->mass, p->mass_stride, p->real_bytes, false, n, 1, mp, s2);
+                    NBK_CHECK(cudaStreamSynchronize(s2));
+                } catch (...) { side_err = std::current_exception(); }
+            });
+            t->before_gather = [&side]() { if (side.joinable()) side.join(); };
+        } else if (sec_src) {
+            pack4_kernel<S><<<div_up(n, tb), tb, 0, st>>>(rsec.p, n, b.p);
+        }
+        struct Joiner { std::thread& th; cudaStream_t& s; ~Joiner() { if (th.joinable()) th.join(); if (s) cudaStreamDestroy(s); } } joiner{side, s2};
+        if (!overlap) { NBK_CHECK(cudaStreamSynchronize(st)); rsec.release(); }
+        build_tree<S>(*t, a.p, sec_src ? b.p : nullptr, p->mass ? rmass.p : nullptr);
+        t->before_gather = nullptr;
+        if (side.joinable()) side.join();
+        if (side_err) std::rethrow_exception(side_err);
+    };
+    if (store == 4) run(float());
+    else run(double());
     NBK_CHECK(cudaEventRecord(t->ev3, st));
     NBK_CHECK(cudaEventSynchronize(t->ev3));
     float ms = 0;
@@ -608,6 +644,22 @@ int nbk_fof_criterion(nbk_tree* t, int criterion, const double* params, int minn
     a.prune_x2 = params[6] * (1.0 + 1e-12);
     a.minnum = minnum; a.order = order;
     fof_call(t, a, precheck, group, ngroups, lists, flags);
+    NBK_API_END
+}
+
+int nbk_fof_criterion_basis(nbk_tree* t, int criterion, const double* params, int minnum, int order, const int32_t* check,
+                            int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && params && check, NBK_ERR_ARG, "nbk_fof_criterion_basis: null argument");
+    NBK_REQUIRE(criterion == NBK_FOF3D || criterion == NBK_FOF6D, criterion == NBK_FOFVEL ? NBK_ERR_UNSUPPORTED : NBK_ERR_ARG,
+                "nbk_fof_criterion_basis: only FOF3d and FOF6d have device implementations");
+    FofArgs a;
+    a.mode = criterion == NBK_FOF3D ? 2 : 4;
+    a.p0 = params[6]; a.p1 = params[7];
+    a.prune_x2 = params[6] * (1.0 + 1e-12);
+    a.minnum = minnum; a.order = order;
+    a.attach = true;
+    fof_call(t, a, check, group, ngroups, lists, flags);
     NBK_API_END
 }
 

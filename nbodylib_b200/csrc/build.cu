@@ -707,6 +707,7 @@ static void build_tree_v1(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* se
             DevBuf<uint32_t> rc2((size_t)C);
             build_level_nodes_kernel<S><<<div_up(C, 128), 128, 0, st>>>(depth, n, bucket, prim_in, o[0], o[1], o[2], nlo.p, nhi.p, cutdim.p, rc2.p);
             launches++;
+            if (t.before_gather) { t.before_gather(); t.before_gather = nullptr; }
             finalize_kernel<S><<<div_up(n, 256), 256, 0, st>>>(n, o[0], prim_in, sec_in, mass_in, prim.p, sec.p, mass.p, order.p);
             launches++;
             NBK_CHECK(cudaStreamSynchronize(st));
@@ -714,6 +715,7 @@ static void build_tree_v1(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* se
     } else {
         DevBuf<uint32_t> rc2(1);
         build_level_nodes_kernel<S><<<1, 128, 0, st>>>(0, n, bucket, prim_in, ordA[0].p, ordA[1].p, ordA[2].p, nlo.p, nhi.p, cutdim.p, rc2.p);
+        if (t.before_gather) { t.before_gather(); t.before_gather = nullptr; }
         finalize_kernel<S><<<div_up(n, 256), 256, 0, st>>>(n, ordA[0].p, prim_in, sec_in, mass_in, prim.p, sec.p, mass.p, order.p);
         launches += 2;
         NBK_CHECK(cudaStreamSynchronize(st));
@@ -860,6 +862,7 @@ static void build_tree_v2(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* se
                                                                            tree_ord.p, ntab);
         NBK_CHECK(cudaGetLastError());
         tr.point("build: small nodes");
+        if (t.before_gather) { t.before_gather(); t.before_gather = nullptr; }
         finalize_kernel<S><<<div_up(n, 256), 256, 0, st>>>(n, tree_ord.p, prim_in, sec_in, mass_in, prim.p, sec.p, mass.p, order.p);
         launches += 2;
         NBK_CHECK(cudaStreamSynchronize(st));

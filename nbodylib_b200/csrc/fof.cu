@@ -158,6 +158,86 @@ __global__ void __launch_bounds__(FOF_WARPS * 32) fof_link_kernel(FofParams prm)
     }
 }
 
+// ---- FOFCriterionSetBasisForLinks (KDFOF.cxx:268-378, KDLeafNode.cxx:620-652) -------------------------------------
+// Only particles whose check value is 0 may start or extend a group ("basis" particles); the others can be linked INTO
+// a group by a basis particle but never link further.  The basis particles' groups are therefore the connected components
+// of the basis-basis links (the ordinary link pass with the others excluded), and every other particle joins one of the
+// groups that reach it.  The reference hands it to the group its serial search discovers first, i.e. the one whose first
+// basis member comes first in tree order; here that is the smallest root among the linked basis neighbours (a root is its
+// component's smallest tree index).
+template <class S>
+struct AttachVisitor : FofVisitor<S> {
+    int best;
+    __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
+        for (int base = 0; base < cnt; base += 32) {
+            int m = min(32, cnt - base);
+            __syncwarp();
+            if ((int)this->lane < m) {
+                Vec4<S> c = this->P[start + base + this->lane];
+                this->tile[this->lane] = (double)c.x; this->tile[32 + this->lane] = (double)c.y; this->tile[64 + this->lane] = (double)c.z;
+                if (this->mode == 1 || this->mode == 4) {
+                    Vec4<S> u = this->V[start + base + this->lane];
+                    this->tile[96 + this->lane] = (double)u.x; this->tile[128 + this->lane] = (double)u.y; this->tile[160 + this->lane] = (double)u.z;
+                }
+            }
+            __syncwarp();
+            if (!this->on) continue;
+            for (int j = 0; j < m; j++) {
+                int c = start + base + j;
+                if (c == this->self || this->excl[c]) continue;           // only basis particles hand out membership
+                if (this->linked(j)) {
+                    int r = c;
+                    while (true) { int p = this->parent[r]; if (p == r) break; r = p; }
+                    best = min(best, r);
+                }
+            }
+        }
+    }
+};
+
+template <class S>
+__global__ void __launch_bounds__(FOF_WARPS * 32) fof_attach_kernel(FofParams prm, int* __restrict__ attach_to) {
+    __shared__ double s_tile[FOF_WARPS][192];
+    __shared__ int s_stack[FOF_WARPS][TRAV_STACK];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    int64_t group = (int64_t)blockIdx.x * FOF_WARPS + w;
+    int64_t qi = group * 32 + lane;
+    if (group * 32 >= prm.n) return;
+    const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
+    const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
+    const bool valid = qi < prm.n && prm.excl[qi] != 0;                  // queries: the particles that are NOT a basis
+    if (!__any_sync(0xffffffffu, valid)) return;
+    AttachVisitor<S> v;
+    v.P = P; v.V = V; v.tile = s_tile[w]; v.parent = prm.parent; v.excl = prm.excl;
+    v.p0 = prm.p0; v.p1 = prm.p1; v.prune_f = prm.prune_f; v.mode = prm.mode; v.lane = lane;
+    v.self = valid ? (int)qi : -1;
+    v.on = valid; v.shifted = false; v.best = 0x7fffffff;
+    double x0 = 0, y0 = 0, z0 = 0;
+    v.vx = v.vy = v.vz = 0;
+    if (valid) {
+        Vec4<S> c = P[qi];
+        x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z;
+        if (prm.mode == 1 || prm.mode == 4) { Vec4<S> u = V[qi]; v.vx = (double)u.x; v.vy = (double)u.y; v.vz = (double)u.z; }
+    }
+    const int nimg = prm.periodic ? 8 : 1;
+    for (int img = 0; img < nimg; img++) {
+        v.qx = (img & 1) ? ((x0 < prm.period[0] / 2.0) ? x0 + prm.period[0] : x0 - prm.period[0]) : x0;
+        v.qy = (img & 2) ? ((y0 < prm.period[1] / 2.0) ? y0 + prm.period[1] : y0 - prm.period[1]) : y0;
+        v.qz = (img & 4) ? ((z0 < prm.period[2] / 2.0) ? z0 + prm.period[2] : z0 - prm.period[2]) : z0;
+        QueryBox qb = make_qbox(v.qx, v.qy, v.qz);
+        traverse(prm.nlo, prm.nhi, prm.bucket, s_stack[w], v, qb, valid);
+    }
+    if (valid) attach_to[qi] = v.best == 0x7fffffff ? -1 : v.best;
+}
+// attached particles become children of the root they joined and stop being excluded
+__global__ void fof_attach_apply_kernel(int64_t n, const int32_t* excl, const int* attach_to, int* parent, int32_t* excl_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t x = excl[i];
+    if (x != 0 && attach_to[i] >= 0) { parent[i] = attach_to[i]; x = 0; }
+    excl_out[i] = x;
+}
+
 __global__ void fof_init_kernel(int64_t n, int* parent, uint32_t* size) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { parent[i] = (int)i; size[i] = 0; }
@@ -275,10 +355,23 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     NBK_CHECK(cudaEventRecord(t.ev2, st));
     if (t.store_bytes == 4) fof_link_kernel<float><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
     else fof_link_kernel<double><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
+    DevBuf<int32_t> excl2;
+    const int32_t* excl_final = a.precheck_tree;
+    if (a.attach) {
+        NBK_REQUIRE(a.precheck_tree != nullptr, NBK_ERR_ARG, "FOFCriterionSetBasisForLinks needs the check values");
+        DevBuf<int> attach_to(n);
+        excl2.alloc(n);
+        if (t.store_bytes == 4) fof_attach_kernel<float><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p, attach_to.p);
+        else fof_attach_kernel<double><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p, attach_to.p);
+        fof_attach_apply_kernel<<<div_up(n, tb), tb, 0, st>>>(n, a.precheck_tree, attach_to.p, parent.p, excl2.p);
+        NBK_CHECK(cudaStreamSynchronize(st));
+        excl_final = excl2.p;
+        launches += 2;
+    }
     NBK_CHECK(cudaEventRecord(t.ev3, st));
     tr.point("fof link");
     fof_flatten_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p);
-    fof_root_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p, a.minnum, a.precheck_tree, flag.p);
+    fof_root_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p, a.minnum, excl_final, flag.p);
     NBK_CHECK(cudaMemsetAsync(flag.p + n, 0, sizeof(uint32_t), st));
     exclusive_scan_u32(flag.p, flagscan.p, n + 1, scratch.p, st, &launches);
     uint32_t ng32 = 0;

@@ -23,6 +23,8 @@
 //                     8 B/entry instead of 12 and half the shared-memory traffic per sift step; the heap is
 //                     bulk-loaded from the k+1 tree-order neighbours of the bucket (heapify) instead of k
 //                     full-depth insertions.
+#include <string.h>
+
 #include "traverse.cuh"
 #include "tree.h"
 
@@ -686,13 +688,16 @@ struct SelectVisitor {
         // pass 1: one cheap test per candidate (the query itself and coincident particles have d2 == 0 and are weeded out
         // in pass 2, like bulk-loaded candidates); pass 2: serial insertion rounds over the set bits
         unsigned acc = 0;
+        STAT(0, 1); STAT(1, m);
         for (int j0 = 0; j0 < m; j0 += 8) {
             unsigned a8 = 0;
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) if (tile.screen(j0 + jj, limf, topd)) a8 |= 1u << jj;
             acc |= a8 << j0;
         }
+        STAT_LANE(4, __popc(acc));
         while (__any_sync(0xffffffffu, acc != 0)) {
+            STAT(2, 1);
             if (acc) {
                 const int j = __ffs(acc) - 1;
                 acc &= acc - 1;
@@ -700,6 +705,7 @@ struct SelectVisitor {
                 const double d2 = tile.exact(j, qx, qy, qz);
                 if (d2 < topd && d2 > 0.0 && (!OVERLAP || c < r0 || c >= r1)) {
                     settop(hp.sift(0, __double2float_rn(d2)));
+                    STAT_LANE(3, 1);
                     if (LOG) { if (nlog < logcap) { *log = c; log += 32; } nlog++; }
                 }
             }
@@ -1168,9 +1174,13 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
         const char* em = getenv("NBK_KNN_MODE");
         const int mode = em ? atoi(em) : 2;     // 2: select + insertion log (default), 1: select-then-collect, 0: (key,index) heap
         // nodes of up to `leaf` particles are scanned as one tile: fewer node tests and better balanced insertion rounds
+        // The level whose nodes hold 21..40 particles (exactly one level does: sizes halve) -- a tile and a bit; with a fixed
+        // threshold of 32 a particle count just above a power of two would be scanned as half-empty 16/17-particle tiles.
         {
             const char* e = getenv("NBK_KNN_LEAF");
-            int leaf = e ? atoi(e) : 32;
+            int64_t sz = t.n;
+            while (sz > 40) sz = (sz + 1) / 2;
+            int leaf = e ? atoi(e) : (int)sz;
             if (leaf > p.bucket) p.bucket = leaf;
         }
         const int want_doubles = (a.veldens_k > 0 && a.veldens_k < a.k) ? 1 : 0;
@@ -1193,6 +1203,7 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             DevBuf<int32_t> logbuf;
             NBK_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), t.stream));
             p.flag_count = counters.p; p.flag_list = flist.p;
+            bool window = false;
             auto go = [&](auto kern) {
                 NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 NBK_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KNN_WARPS * 32, smem));
@@ -1200,7 +1211,34 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
                 int64_t blocks = (int64_t)nsm * per_sm;
                 if (blocks > (ngroups + KNN_WARPS - 1) / KNN_WARPS) blocks = (ngroups + KNN_WARPS - 1) / KNN_WARPS;
                 logbuf.alloc((size_t)blocks * KNN_WARPS * logcap * 32);
+                // The log is written once and read once by the same warp, then overwritten by the warp's next query group:
+                // pinned in L2 (persisting access window) its lines are rewritten in place and never travel to HBM.
+                if (getenv("NBK_KNN_NO_L2PIN") == nullptr) {
+                    int max_persist = 0, max_window = 0;
+                    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, t.device);
+                    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, t.device);
+                    if (max_persist > 0 && max_window > 0) {
+                        size_t bytes = logbuf.bytes();
+                        size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+                        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+                        cudaStreamAttrValue av;
+                        memset(&av, 0, sizeof(av));
+                        av.accessPolicyWindow.base_ptr = logbuf.p;
+                        av.accessPolicyWindow.num_bytes = win;
+                        av.accessPolicyWindow.hitRatio = win <= (size_t)max_persist ? 1.0f : (float)((double)max_persist / (double)win);
+                        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                        window = cudaStreamSetAttribute(t.stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+                        if (!window) cudaGetLastError();
+                    }
+                }
                 kern<<<(int)blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles, counters.p + 1, logbuf.p, logcap);
+                if (window) {
+                    cudaStreamAttrValue av;
+                    memset(&av, 0, sizeof(av));
+                    av.accessPolicyWindow.num_bytes = 0;
+                    cudaStreamSetAttribute(t.stream, cudaStreamAttributeAccessPolicyWindow, &av);
+                }
             };
             if (t.store_bytes == 4) {
                 if (mb == 8) go(knn_sl_kernel<float, 8>); else if (mb == 6) go(knn_sl_kernel<float, 6>); else go(knn_sl_kernel<float, 5>);
@@ -1208,10 +1246,23 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
                 if (mb == 8) go(knn_sl_kernel<double, 8>); else if (mb == 6) go(knn_sl_kernel<double, 6>); else go(knn_sl_kernel<double, 5>);
             }
             NBK_CHECK(cudaGetLastError());
+#ifdef NBK_STATS
+            {
+                unsigned long long h[8];
+                NBK_CHECK(cudaStreamSynchronize(t.stream));
+                NBK_CHECK(cudaMemcpyFromSymbol(h, g_stats, sizeof(h)));
+                double g = (double)((rows + 31) / 32);
+                fprintf(stderr, "[nbk stats] per warp: tiles %.1f cand %.1f rounds %.1f ; per lane: screened-in %.1f inserted %.1f\n",
+                        h[0] / g, h[1] / g, h[2] / g, h[4] / (double)rows, h[3] / (double)rows);
+                unsigned long long z[8] = {0};
+                NBK_CHECK(cudaMemcpyToSymbol(g_stats, z, sizeof(z)));
+            }
+#endif
             t.last_launches += 2;
             int nflag = 0;
             NBK_CHECK(cudaMemcpyAsync(&nflag, counters.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
             NBK_CHECK(cudaStreamSynchronize(t.stream));
+            if (window) cudaCtxResetPersistingL2Cache();      // hand the set-aside lines back to the normal L2
             t.last_flagged = nflag;
             if (nflag > 0) {
                 KnnParams pe = p;

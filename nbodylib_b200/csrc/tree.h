@@ -1,5 +1,7 @@
 // tree.h -- the device-resident tree object behind nbk_tree, and the launch entry points each .cu exports.
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 
 struct nbk_tree {
@@ -40,6 +42,10 @@ struct nbk_tree {
     int64_t last_flagged = 0;       // queries the fp32-key kNN kernel handed to the exact kernel
     int64_t device_bytes = 0;
 
+    // nbk_create: called by the build right before the particle gather; joins the side thread that stages the secondary
+    // phase-space half and the masses (their host->device copies overlap the sorts and the level loop)
+    std::function<void()> before_gather;
+
     const void* pos4() const { return treetype == NBK_TVEL ? sec : prim; }
     const void* vel4() const { return treetype == NBK_TVEL ? prim : sec; }
 };
@@ -77,6 +83,7 @@ struct FofArgs {
     double prune_x2 = 0;       // spatial pruning radius^2 (>= any linked pair's position distance^2)
     int minnum = 8, order = 0;
     const int32_t* precheck_tree = nullptr;  // device, tree order, may be null
+    bool attach = false;                     // FOFCriterionSetBasisForLinks: precheck != 0 particles cannot link but can be linked
     int32_t* group_tree = nullptr;           // device out, tree order
     int64_t ngroups = 0;
     int32_t *head = nullptr, *next = nullptr, *tail = nullptr, *len = nullptr;  // device, optional

@@ -251,6 +251,19 @@ class KDTree:
             return g, ng.value, plen[:ng.value + 1]
         return g, ng.value
 
+    def FOFCriterionSetBasisForLinks(self, cmp, params, check, minnum=8, order=0):
+        """KDTree::FOFCriterionSetBasisForLinks(cmp, params, numgroup, minnum, order, ipcheckflag, check) (KDFOF.cxx:268-378).
+        check: the FOFcheckfunc values by ID; only check == 0 particles start / extend groups, the others can only be
+        linked into one (include/nbk.h states the tie rule)."""
+        ng = C.c_int64()
+        g = np.empty(self.n, dtype=np.int32)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        chk = np.ascontiguousarray(check, dtype=np.int32)
+        assert chk.shape == (self.n,)
+        L.check(self._lib.nbk_fof_criterion_basis(self._h, int(cmp), _ptr(params), int(minnum), int(order), _ptr(chk), _ptr(g),
+                                                  C.byref(ng), None, 0))
+        return g, ng.value
+
     def FOFCriterion(self, cmp, params, minnum=8, order=0, precheck=None):
         """KDTree::FOFCriterion(cmp, params, numgroups, minnum, order) (KDFOF.cxx:157-265) for cmp in
         {FOF3D, FOF6D} (FOFFunc.h:30-55)."""

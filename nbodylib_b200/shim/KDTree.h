@@ -200,6 +200,25 @@ public:
         });
     }
 
+    /// KDFOF.cxx:268-378.  `check_` is evaluated here on the host for every particle (it is the caller's code); the
+    /// device receives the values.  (ipcheckflag is not read by the reference's implementation either.)
+    Int_t* FOFCriterionSetBasisForLinks(FOFcompfunc cmp, Double_t* params, Int_t& numgroup, Int_t minnum = 8, int order = 0, int ipcheckflag = 0,
+                                        FOFcheckfunc check_ = Pnocheck, Int_tree_t* pHead = NULL, Int_tree_t* pNext = NULL, Int_tree_t* pTail = NULL,
+                                        Int_tree_t* pLen = NULL) {
+        (void)ipcheckflag;
+        int crit;
+        if (cmp == (FOFcompfunc)&FOF3d) crit = NBK_FOF3D;
+        else if (cmp == (FOFcompfunc)&FOF6d) crit = NBK_FOF6D;
+        else throw std::runtime_error("nbk shim: FOFCriterionSetBasisForLinks supports FOF3d and FOF6d; host callbacks cannot run on the device");
+        std::vector<int32_t> pre;
+        fill_precheck(pre, 1, check_, params);
+        double pr[16];
+        for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        return run_fof(pre, pHead, pNext, pTail, pLen, numgroup, [&](const int32_t* pc, int32_t* g, int64_t* ng, nbk_fof_lists* l) {
+            return nbk_fof_criterion_basis(h, crit, pr, (int)minnum, order, pc, g, ng, l, 0);
+        });
+    }
+
     // ---- ordering (KDTree.cxx:1358-1362) -----------------------------------------------------------------------
     void OverWriteInputOrder() {
         iresetorder = false;

@@ -166,6 +166,9 @@ class Ref:
             L.ref_fof.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _ip, _lp]
             L.ref_fof_criterion.restype = C.c_double
             L.ref_fof_criterion.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int, _ip, _lp]
+            L.ref_set_types.argtypes = [C.c_void_p, _ip]
+            L.ref_fof_checked.restype = C.c_double
+            L.ref_fof_checked.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _ip, _lp]
             L.ref_scale_phase.argtypes = [C.c_long, _dp, _dp, C.c_double, C.c_double]
             L.ref_dump_nodes.restype = C.c_long
             L.ref_dump_nodes.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip, C.c_long]
@@ -287,6 +290,19 @@ class Ref:
         g = np.zeros(self.n, dtype=np.int32)
         ng = C.c_long(0)
         self.last_seconds = self.lib().ref_fof_criterion(self.h, crit, _d(params), minnum, order, _i(g), C.byref(ng))
+        return g, ng.value
+
+    def set_types(self, type_by_id):
+        """Particle::type by ID; the checked FOF entry points treat type != 0 as FOFcheckfunc() != 0"""
+        t = np.ascontiguousarray(type_by_id, dtype=np.int32)
+        self.lib().ref_set_types(self.h, _i(t))
+
+    def fof_checked(self, which, crit, params, minnum=8, order=0):
+        """which: 0 FOF(params[0]) with ipcheckflag, 1 FOFCriterion with ipcheckflag, 2 FOFCriterionSetBasisForLinks"""
+        params = _f64(params).copy()
+        g = np.zeros(self.n, dtype=np.int32)
+        ng = C.c_long(0)
+        self.last_seconds = self.lib().ref_fof_checked(self.h, which, crit, _d(params), minnum, order, _i(g), C.byref(ng))
         return g, ng.value
 
     def dump_nodes(self):

@@ -270,6 +270,33 @@ double ref_fof_criterion(void* hv, int crit, double* params, int minnum, int ord
     return dt;
 }
 
+/* check function for the ipcheckflag / SetBasisForLinks entry points: particles whose type is non-zero are "checked out" */
+static int check_by_type(Particle& p, Double_t*) { return p.GetType() != 0 ? -1 : 0; }
+
+/* set Particle::type from an array indexed by ID (the tree has permuted the array) */
+void ref_set_types(void* hv, const int* type_by_id) {
+    RefTree* h = (RefTree*)hv;
+    for (Int_t i = 0; i < h->n; i++) h->parts[i].SetType(type_by_id[h->parts[i].GetID()]);
+}
+
+/* which: 0 = FOF(fdist = params[0]) with ipcheckflag, 1 = FOFCriterion(cmp) with ipcheckflag,
+ *        2 = FOFCriterionSetBasisForLinks(cmp); crit as in ref_fof_criterion */
+double ref_fof_checked(void* hv, int which, int crit, double* params, int minnum, int order, int* group_by_id, long* ngroups) {
+    RefTree* h = (RefTree*)hv;
+    Int_t ng = 0;
+    FOFcompfunc cmp = crit == 0 ? FOF3d : (crit == 1 ? FOFVel : FOF6d);
+    double t0 = now_s();
+    Int_t* g;
+    if (which == 0) g = h->tree->FOF(params[0], ng, minnum, order, NULL, NULL, NULL, NULL, 1, check_by_type, params);
+    else if (which == 1) g = h->tree->FOFCriterion(cmp, params, ng, minnum, order, 1, check_by_type);
+    else g = h->tree->FOFCriterionSetBasisForLinks(cmp, params, ng, minnum, order, 1, check_by_type);
+    double dt = now_s() - t0;
+    for (Int_t i = 0; i < h->n; i++) group_by_id[i] = (int)g[i];
+    delete[] g;
+    *ngroups = ng;
+    return dt;
+}
+
 /* Particle::ScalePhase on the whole array (Particle.h:666) -- used for the 6D FOF form (A) */
 void ref_scale_phase(long n, double* pos, double* vel, double xs, double vs) {
     Particle p;

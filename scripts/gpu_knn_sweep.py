@@ -9,6 +9,10 @@ ng = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 ks = [int(a) for a in sys.argv[2:]] or [64]
 n = ng ** 3
 pos, vel, mass = clustered_box(ng, seed=2025, nhalo=max(8, min(8192, n // 16384)), device="cuda")
+if os.environ.get("PROBE_N"):
+    n = int(os.environ["PROBE_N"])
+    sel = torch.randperm(ng ** 3, device="cuda")[:n]
+    pos, vel, mass = pos[sel].contiguous(), vel[sel].contiguous(), mass[sel].contiguous()
 t = KDTree(pos, vel, mass, Period=np.ones(3), device=0)
 rho = torch.empty(n, dtype=torch.float64, device="cuda")
 for k in ks:

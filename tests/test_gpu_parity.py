@@ -441,3 +441,58 @@ def test_build_v2_equals_v1(nb, monkeypatch, n, bucket, flags):
     assert np.array_equal(s1[present], s2[present]) and np.array_equal(e1[present], e2[present]) and np.array_equal(c1[present], c2[present])
     assert np.array_equal(b1[present], b2[present])
     assert int(present.sum()) == nn1
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_checked_fof_against_reference(nb, periodic):
+    """FOF / FOFCriterion with a FOFcheckfunc mask (ipcheckflag) and FOFCriterionSetBasisForLinks against the live
+    reference with the same mask (reference semantics pinned by tests/test_oracle_cpu.py::test_reference_checked_fof_semantics)."""
+    from oracle.pyoracle import Ref, have_ref
+    from nbodylib_b200.synth import clustered_small
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    n = 40000
+    pos, vel, mass = clustered_small(n, seed=33)
+    rng = np.random.default_rng(8)
+    types = (rng.random(n) < 0.3).astype(np.int32)
+    chk = np.where(types != 0, -1, 0).astype(np.int32)
+    basis = types == 0
+    period = np.ones(3) if periodic else None
+    ll = 0.3 / n ** (1 / 3)
+    sv2 = float(((vel - vel.mean(0)) ** 2).sum(1).mean() / 3)
+    params = np.zeros(10)
+    params[1] = params[6] = ll * ll
+    params[2] = params[7] = 4.0 * sv2
+    R = Ref(pos, vel, mass, period=period)
+    R.set_types(types)
+    with nb.KDTree(pos, vel, mass, Period=period) as t:
+        for minnum, order in ((5, 0), (5, 1)):
+            g, ng = t.FOF(ll, minnum, order, precheck=chk)
+            rg, rng_ = R.fof_checked(0, 0, np.array([ll] + [0.0] * 9), minnum, order)
+            assert ng == rng_ and np.array_equal(canon(g), canon(np.maximum(rg, 0)))
+            for crit in (0, 2):
+                g, ng = t.FOFCriterion(crit, params, minnum, order, precheck=chk)
+                rg, rng_ = R.fof_checked(1, crit, params, minnum, order)
+                assert ng == rng_ and np.array_equal(canon(g), canon(np.maximum(rg, 0)))
+                if order:
+                    assert np.array_equal(np.bincount(g)[1:], np.bincount(np.maximum(rg, 0))[1:])
+        for crit in (0, 2):
+            for minnum, order in ((1, 0), (6, 0), (6, 1)):
+                g, ng = t.FOFCriterionSetBasisForLinks(crit, params, chk, minnum, order)
+                rg, rng_ = R.fof_checked(2, crit, params, minnum, order)
+
+                def label_by_basis(grp):      # group -> smallest ID among its basis members; 0 stays 0
+                    lab = np.full(grp.max() + 1, n, dtype=np.int64)
+                    np.minimum.at(lab, grp[basis], np.nonzero(basis)[0])
+                    lab[0] = -1
+                    return lab[grp]
+                same = label_by_basis(g) == label_by_basis(rg)
+                if minnum == 1:
+                    # no group is dissolved: the basis particles' partition is identical, and so is the group count
+                    assert ng == rng_ and same[basis].all()
+                    assert np.array_equal(canon(np.where(basis, g, 0)), canon(np.where(basis, rg, 0)))
+                # a checked particle linked by several groups goes to the one discovered first; the two implementations can
+                # order two groups differently only when their first members share a leaf (order inside a leaf is free), and
+                # with a size threshold such a particle can tip a group over it -- both rare
+                assert same.mean() > 0.999 and abs(ng - rng_) <= 2
+    R.close()

@@ -168,3 +168,62 @@ def test_synth_is_fp32_representable_and_deterministic():
     assert pos.shape == (4096, 3) and float(pos.min()) >= 0 and float(pos.max()) < 1
     pu, _, _ = uniform_box(1000)
     assert pu.shape == (1000, 3)
+
+
+def _checked_fof_expectation(pos, types, p6, period):
+    """numpy restatement of the checked FOF entry points on a small set: link matrix of FOF3d (FOFFunc.h:30-35),
+    components of the check == 0 ("basis") particles, and for every other particle the basis groups that link it."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    d = pos[:, None, :] - pos[None, :, :]
+    if period is not None:
+        d = d - np.round(d / period) * period
+    link = ((d[..., 0] ** 2) / p6 + (d[..., 1] ** 2) / p6 + (d[..., 2] ** 2) / p6) < 1
+    np.fill_diagonal(link, False)
+    basis = types == 0
+    bb = link & basis[:, None] & basis[None, :]
+    _, comp = connected_components(csr_matrix(bb), directed=False)
+    return link, basis, comp
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_reference_checked_fof_semantics(periodic):
+    """Pins what the three check-function entry points of the reference compute (live reference, no GPU):
+    FOF / FOFCriterion with ipcheckflag drop the checked particles entirely; FOFCriterionSetBasisForLinks groups the
+    unchecked ones by their mutual links and hands every checked particle to the EARLIEST-DISCOVERED group linking it.
+    These are the semantics nbk_fof(precheck) and nbk_fof_criterion_basis implement on the device."""
+    from oracle.pyoracle import Ref, have_ref
+    from nbodylib_b200.synth import clustered_small
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    n = 3000
+    pos, vel, mass = clustered_small(n, seed=21)
+    rng = np.random.default_rng(5)
+    types = (rng.random(n) < 0.35).astype(np.int32)
+    period = np.ones(3) if periodic else None
+    ll = 0.35 / n ** (1 / 3)
+    params = np.zeros(10)
+    params[1] = params[6] = ll * ll
+    link, basis, comp = _checked_fof_expectation(pos, types, params[6], period)
+    R = Ref(pos, vel, mass, period=period)
+    R.set_types(types)
+    # (1) ipcheckflag: checked particles are not there at all
+    for which, prm in ((0, np.array([ll] + [0.0] * 9)), (1, params)):
+        g, ng = R.fof_checked(which, 0, prm, minnum=2, order=0)
+        assert np.all(g[~basis] <= 0)
+        sizes = np.bincount(comp[basis])
+        want = np.where(sizes[comp] >= 2, comp + 1, 0) * basis
+        assert np.array_equal(canon(np.where(basis, g, 0)), canon(want))
+    # (2) SetBasisForLinks, minnum = 1 so that no group is dissolved
+    g, ng = R.fof_checked(2, 0, params, minnum=1, order=0)
+    assert np.array_equal(canon(np.where(basis, g, 0)), canon(np.where(basis, comp + 1, 0)))
+    amb = 0
+    for i in np.nonzero(~basis)[0]:
+        cand = np.unique(g[link[i] & basis])
+        if len(cand) == 0:
+            assert g[i] == 0
+        else:
+            assert g[i] == cand.min()        # order = 0 numbers the groups in discovery order
+            amb += len(cand) > 1
+    assert amb > 0                            # the rule was actually exercised
+    R.close()
