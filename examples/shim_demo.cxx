@@ -37,6 +37,23 @@ int main() {
                 if (std::fabs(s - d2[j]) > 1e-12 * (s + 1e-30) || nn[j] == tt || (j && d2[j] < d2[j - 1])) bad++;
             }
         }
+        // the reference's own usage pattern (tests/test_kdtree.cxx:279-301): an OpenMP loop over the per-particle call.  The
+        // shim serves it from per-thread block caches filled by batched device queries; it must agree with the whole-system form
+        {
+            const int K = 8;
+            std::vector<Int_t> nn_loop((size_t)N * K);
+            std::vector<Double_t> d2_loop((size_t)N * K);
+#pragma omp parallel for schedule(guided)
+            for (Int_t i = 0; i < N; i++) tree.FindNearestPos(i, &nn_loop[(size_t)i * K], &d2_loop[(size_t)i * K], K);
+            std::vector<Int_t*> nnp(N); std::vector<Double_t*> d2p(N);
+            std::vector<Int_t> nn_all((size_t)N * K); std::vector<Double_t> d2_all((size_t)N * K);
+            for (Int_t i = 0; i < N; i++) { nnp[i] = &nn_all[(size_t)i * K]; d2p[i] = &d2_all[(size_t)i * K]; }
+            tree.FindNearestPos(nnp.data(), d2p.data(), K);
+            long diff = 0;
+            for (size_t q = 0; q < nn_all.size(); q++) diff += (nn_all[q] != nn_loop[q]) || (d2_all[q] != d2_loop[q]);
+            printf("per-particle loop vs whole system: %ld differences\n", diff);
+            if (diff) bad++;
+        }
         std::vector<Int_t> tagged = tree.SearchBallPosTagged(N / 2, 0.01 * 0.01);
         printf("ball: %zu particles\n", tagged.size());
         tree.CalcDensity(32);

@@ -26,6 +26,7 @@
 #include "Particle.h"
 #endif
 #include <algorithm>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -49,8 +50,30 @@ private:
     nbk_info info{};
     Double_t* period = nullptr;
 
+    std::mutex dev_mutex;          // device calls on one tree are serialised (callers may sit inside an OpenMP loop)
+    unsigned long long serial = 0;  // distinguishes trees that reuse an address (per-thread caches key on it)
+
     static void check(int rc) {
         if (rc != NBK_OK) throw std::runtime_error(std::string("nbk: ") + nbk_last_error());
+    }
+    static unsigned long long next_serial() { static std::mutex m; static unsigned long long c = 0; std::lock_guard<std::mutex> g(m); return ++c; }
+
+    // Per-thread block cache behind the per-particle FindNearest*(Int_t tt) calls.  The reference's callers loop over
+    // every particle (often inside `omp parallel for`, e.g. reference tests/test_kdtree.cxx:279-301) and call the
+    // per-particle form; one kernel launch per call would waste the device.  The first call of a thread computes the
+    // neighbours of the whole block of consecutive tree indices around tt in ONE batched device query; the following
+    // calls of that thread (static / dynamic / guided chunks are runs of consecutive indices) are served from host memory.
+    struct KnnBlock {
+        unsigned long long serial = 0; Int_t b0 = 0, b1 = 0, k = 0; int flags = -1;
+        std::vector<int32_t> nn; std::vector<double> d2;
+    };
+    static KnnBlock& tls_block() { static thread_local KnnBlock b; return b; }
+    Int_t block_size(Int_t k) const {
+        Int_t b = numparts / 64;
+        if (b < 4096) b = 4096;
+        if (b > 65536) b = 65536;
+        while ((size_t)b * (size_t)k * 12 > ((size_t)64 << 20) && b > 1024) b >>= 1;     // <= 64 MiB of host cache per thread
+        return b;
     }
     void refresh() { check(nbk_get_info(h, &info)); }
 
@@ -75,6 +98,7 @@ public:
         double per[3] = {0, 0, 0};
         if (period) for (int k = 0; k < 3; k++) per[k] = (double)period[k];
         check(nbk_create(&np, numparts, (int)bucket_size, TreeType, KernType, KernRes, SplittingCriterion, period ? per : NULL, 0, -1, &h));
+        serial = next_serial();
         refresh();
         // bring the caller's array into tree order (the reference does this with in-place quickselect swaps)
         std::vector<int32_t> order(numparts);
@@ -109,8 +133,8 @@ public:
     nbk_tree* GetHandle() { return h; }
 
     // ---- nearest neighbours (KDFindNearest.cxx:247-334, 444-554) ----------------------------------------------
-    void FindNearestPos(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { knn_range(tt, tt + 1, nn, dist2, Nsearch, 0); }
-    void FindNearest(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { knn_range(tt, tt + 1, nn, dist2, Nsearch, NBK_KNN_TREE_FORM); }
+    void FindNearestPos(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { knn_cached(tt, nn, dist2, Nsearch, 0); }
+    void FindNearest(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { knn_cached(tt, nn, dist2, Nsearch, NBK_KNN_TREE_FORM); }
     void FindNearestPos(Double_t* x, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
         std::vector<double> d2(Nsearch);
         std::vector<int32_t> n32(Nsearch);
@@ -227,6 +251,23 @@ public:
     void SetResetOrder(bool a) { iresetorder = a; }
 
 private:
+    void knn_cached(Int_t tt, Int_t* nn, Double_t* dist2, Int_t k, int flags) {
+        if (tt < 0 || tt >= numparts) throw std::runtime_error("nbk shim: particle index out of range");
+        KnnBlock& c = tls_block();
+        if (c.serial != serial || c.k != k || c.flags != flags || tt < c.b0 || tt >= c.b1) {
+            const Int_t B = block_size(k);
+            const Int_t b0 = (tt / B) * B, b1 = std::min(numparts, b0 + B);
+            c.nn.resize((size_t)(b1 - b0) * k);
+            c.d2.resize((size_t)(b1 - b0) * k);
+            {
+                std::lock_guard<std::mutex> g(dev_mutex);
+                check(nbk_knn_particles(h, (int)k, b0, b1, c.nn.data(), c.d2.data(), flags));
+            }
+            c.serial = serial; c.b0 = b0; c.b1 = b1; c.k = k; c.flags = flags;
+        }
+        const size_t row = (size_t)(tt - c.b0) * k;
+        for (Int_t j = 0; j < k; j++) { nn[j] = c.nn[row + j]; dist2[j] = c.d2[row + j]; }
+    }
     void knn_range(Int_t q0, Int_t q1, Int_t* nn, Double_t* dist2, Int_t k, int flags) {
         std::vector<int32_t> n32((size_t)(q1 - q0) * k);
         std::vector<double> d2((size_t)(q1 - q0) * k);

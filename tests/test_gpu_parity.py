@@ -301,11 +301,12 @@ def test_cxx_shim_program(built, tmp_path):
         pytest.skip("no host C++ compiler")
     exe = str(tmp_path / "shim_demo")
     lib = os.path.join(ROOT, "nbodylib_b200")
-    subprocess.check_call([gxx, "-O2", "-std=c++17", "-I" + os.path.join(lib, "shim"), os.path.join(ROOT, "examples", "shim_demo.cxx"),
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-fopenmp", "-I" + os.path.join(lib, "shim"), os.path.join(ROOT, "examples", "shim_demo.cxx"),
                            "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "shim demo ok" in out.stdout, out.stdout + out.stderr
     assert "nodes 32767 leaves 16384" in out.stdout
+    assert "per-particle loop vs whole system: 0 differences" in out.stdout
 
 
 @pytest.mark.parametrize("bucket,k", [(1, 3), (4, 9), (8, 33), (32, 16), (64, 40), (100, 7)])
