@@ -165,6 +165,7 @@ def main():
     from nbodylib_b200 import KDTree
     from nbodylib_b200.synth import clustered_box
 
+    t_start = time.perf_counter()
     ng = args.ng
     n = ng ** 3
     nh = max(8, min(8192, n // 16384))
@@ -177,6 +178,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def progress(msg):
+        if os.environ.get("BENCH_VERBOSE"):
+            print("[bench rank %d %.1fs] %s" % (rank, time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
+
     if world > 1:
         from nbodylib_b200.sharded import ShardedTree
         tree = ShardedTree(pos, vel, mass, period=period, rank=rank, world=world)
@@ -188,8 +193,10 @@ def main():
     def step():
         tree.CalcDensity(K_NN, out=rho)
 
+    progress("tree ready")
     for _ in range(args.warmup):
         step()
+        progress("warm-up step done")
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     kernel_ms, call_ms, launches = [], [], 0
@@ -201,6 +208,7 @@ def main():
         kernel_ms.append(i.last_kernel_ms)
         call_ms.append(i.last_call_ms)
         launches += int(i.last_launches)
+    progress("timed steps done")
     barrier()
     wall = time.perf_counter() - t0
     # device time of the timed region: the library times its own stream with CUDA events (last_call_ms); the wall
@@ -258,6 +266,25 @@ def main():
         extra["build_hbm_frac"] = n * ALG_BYTES["build"] / (extra["build_ms"] * 1e-3) / 1e9 / peak
     if world > 1:
         extra["sharded_rank0"] = dict(tree.stats)
+    if world > 1 and os.environ.get("BENCH_SHARDED_FOF"):
+        # BASELINE config 5: 3D FOF of the whole slab-sharded periodic box (halo exchange, local union-find, cross-slab merge).
+        # Off by default: a rank-local failure between two collectives would hang the other ranks.
+        try:
+            tree.close_density()
+            progress("sharded FOF starts")
+            barrier(); t1 = time.perf_counter()
+            gfof, ngl = tree.FOF(0.2 / ng, 20, 1)
+            barrier()
+            tf = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            extra["fof3d_particles_per_s"] = n * world / float(tf.item())
+            extra["fof3d_ms"] = float(tf.item()) * 1e3
+            extra["fof3d_groups"] = int(ngl)
+            extra["fof3d_note"] = "ShardedTree.FOF: halo exchange + local tree build + union-find + cross-slab merge, all inside the timed region"
+            del gfof
+            progress("sharded FOF done")
+        except Exception as ex:  # the headline line must survive a failure of this extra
+            extra["fof3d_error"] = repr(ex)[:300]
     tree.close()
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------
@@ -308,7 +335,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "knn_sl_kernel<float,6>", "kernel_ms": kms,
                          "algorithmic_bytes_per_particle": ALG_BYTES["knn_density"],
-                         "note": "issue-slot bound tree traversal (58% of peak issue rate), not HBM bound: see DESIGN.md section 4; traffic = measured DRAM bytes of one launch (ncu), dominated by the insertion log"},
+                         "note": "issue-slot bound tree traversal, not HBM bound: see DESIGN.md section 4; traffic = measured DRAM bytes of one launch (ncu), dominated by the insertion log",
+                         "issue_active_pct_ncu": 65.7, "warp_instructions_per_particle_ncu": 2404,
+                         "ncu_source": "profiles/r1_07_knn_select_log_512cube_k64.txt"},
             "timer": "host clock around K steps, barrier + device synchronize on both sides, max over ranks; device_ms_per_step = the library's CUDA events around the same calls on its own stream",
             "device_ms_per_step": float(np.mean(call_ms)),
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra,

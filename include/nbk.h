@@ -170,6 +170,16 @@ int nbk_fof_criterion(nbk_tree* t, int criterion, const double* params, int minn
 int nbk_fof_criterion_basis(nbk_tree* t, int criterion, const double* params, int minnum, int order,
                             const int32_t* check, int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags);
 
+/* Domain decomposition support (no counterpart in the reference, which has no distributed code: VELOCIraptor builds one
+ * KDTree per MPI rank over local + imported particles).  Appends the particles of `halo` (a second TPHYS tree on the same
+ * device, e.g. the ghost layer received from the neighbouring ranks) to `t` as a SECOND tree: IDs of the halo particles
+ * follow t's (n_main .. n_main + n_halo - 1), `halo` is consumed.  nbk_calc_density / nbk_calc_veldensity /
+ * nbk_smoothing_scale then run their queries for t's own particles only and search both trees; output arrays have
+ * n_main + n_halo entries (the symmetric scatter term of CalcDensity is deposited on halo particles too, for the caller
+ * to send home).  Keeping the halo out of the main tree leaves the main tree's shape -- and the alignment of the warp
+ * query groups with its nodes -- independent of the halo size.  Other queries return NBK_ERR_UNSUPPORTED on such a tree. */
+int nbk_attach_halo(nbk_tree* t, nbk_tree* halo);
+
 /* Scratch buffers are recycled through the device's stream-ordered memory pool and kept across calls and
  * trees (allocating and freeing GBs through the driver costs more than the kernels).  This hands the cached
  * memory back to the driver (e.g. before another library needs the HBM). */

@@ -39,7 +39,7 @@ EXPORTS = [
     "nbk_last_error", "nbk_device_count", "nbk_create", "nbk_destroy", "nbk_get_info", "nbk_get_order",
     "nbk_get_kernel_table", "nbk_get_nodes", "nbk_knn_particles", "nbk_knn_points", "nbk_ball_particles",
     "nbk_ball_points", "nbk_calc_density", "nbk_calc_density_subset", "nbk_calc_veldensity", "nbk_smoothing_scale", "nbk_fof",
-    "nbk_fof_criterion", "nbk_fof_criterion_basis", "nbk_device_arrays", "nbk_release_cached_memory",
+    "nbk_fof_criterion", "nbk_fof_criterion_basis", "nbk_attach_halo", "nbk_device_arrays", "nbk_release_cached_memory",
 ]
 
 _lib = None
@@ -74,6 +74,7 @@ def load():
     L.nbk_fof.argtypes = [vp, dbl, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]
     L.nbk_fof_criterion.argtypes = [vp, i32, vp, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]
     L.nbk_fof_criterion_basis.argtypes = [vp, i32, vp, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]
+    L.nbk_attach_halo.argtypes = [vp, vp]
     L.nbk_release_cached_memory.argtypes = [i32]
     L.nbk_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     for name in EXPORTS:

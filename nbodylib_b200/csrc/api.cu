@@ -339,13 +339,67 @@ int nbk_destroy(nbk_tree* t) {
     if (!t) return NBK_OK;
     DeviceGuard guard(t->device, t->stream);
     cudaStreamSynchronize(t->stream);
-    void* bufs[] = {t->prim, t->sec, t->mass, t->order, t->nlo, t->nhi, t->cutdim, t->d_kernel};
+    void* bufs[] = {t->prim, t->sec, t->mass, t->order, t->nlo, t->nhi, t->cutdim, t->d_kernel, t->nlo2, t->nhi2};
     for (void* b : bufs) if (b) cudaFreeAsync(b, t->stream);
     cudaStreamSynchronize(t->stream);
 
     cudaEventDestroy(t->ev0); cudaEventDestroy(t->ev1); cudaEventDestroy(t->ev2); cudaEventDestroy(t->ev3);
     cudaStreamDestroy(t->stream);
     delete t;
+    NBK_API_END
+}
+
+namespace {
+__global__ void offset_nodes_kernel(int64_t nslots, NodeLo* nlo, NodeHi* nhi, int off) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nslots && nlo[i].start >= 0) { nlo[i].start += off; nhi[i].end += off; }
+}
+__global__ void offset_i32_kernel(int64_t n, int32_t* a, int off) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += off;
+}
+}  // namespace
+
+int nbk_attach_halo(nbk_tree* t, nbk_tree* halo) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && halo && t != halo, NBK_ERR_ARG, "nbk_attach_halo: null argument");
+    NBK_REQUIRE(t->n_main == 0 && halo->n_main == 0, NBK_ERR_ARG, "nbk_attach_halo: a halo is already attached");
+    NBK_REQUIRE(t->device == halo->device && t->store_bytes == halo->store_bytes && t->treetype == NBK_TPHYS && halo->treetype == NBK_TPHYS &&
+                    t->bucket == halo->bucket && (t->sec == nullptr) == (halo->sec == nullptr),
+                NBK_ERR_ARG, "nbk_attach_halo: the two trees must be TPHYS trees on one device with the same storage width, bucket size and columns");
+    NBK_REQUIRE(t->n + halo->n < ((int64_t)1 << 31) - 64, NBK_ERR_ARG, "nbk_attach_halo: too many particles");
+    DeviceGuard guard(t->device, t->stream);
+    cudaStream_t st = t->stream;
+    NBK_CHECK(cudaStreamSynchronize(halo->stream));
+    const int64_t n1 = t->n, n2 = halo->n, n = n1 + n2;
+    const size_t vb = (size_t)t->store_bytes * 4;
+    DevBuf<unsigned char> prim((size_t)n * vb), sec(t->sec ? (size_t)n * vb : 0);
+    DevBuf<double> mass(n);
+    DevBuf<int32_t> order(n);
+    auto cat = [&](void* dst, const void* a, const void* b, size_t elem) {
+        NBK_CHECK(cudaMemcpyAsync(dst, a, (size_t)n1 * elem, cudaMemcpyDeviceToDevice, st));
+        NBK_CHECK(cudaMemcpyAsync((unsigned char*)dst + (size_t)n1 * elem, b, (size_t)n2 * elem, cudaMemcpyDeviceToDevice, st));
+    };
+    cat(prim.p, t->prim, halo->prim, vb);
+    if (t->sec) cat(sec.p, t->sec, halo->sec, vb);
+    cat(mass.p, t->mass, halo->mass, sizeof(double));
+    cat(order.p, t->order, halo->order, sizeof(int32_t));
+    offset_i32_kernel<<<div_up(n2, 256), 256, 0, st>>>(n2, order.p + n1, (int)n1);            // halo IDs follow the main IDs
+    offset_nodes_kernel<<<div_up(halo->nslots, 256), 256, 0, st>>>(halo->nslots, halo->nlo, halo->nhi, (int)n1);
+    NBK_CHECK(cudaGetLastError());
+    void* old[] = {t->prim, t->sec, t->mass, t->order, halo->prim, halo->sec, halo->mass, halo->order, halo->cutdim, halo->d_kernel};
+    for (void* b : old) if (b) cudaFreeAsync(b, st);
+    NBK_CHECK(cudaStreamSynchronize(st));
+    t->prim = prim.p; prim.p = nullptr;
+    t->sec = sec.p; sec.p = nullptr;
+    t->mass = mass.p; mass.p = nullptr;
+    t->order = order.p; order.p = nullptr;
+    t->nlo2 = halo->nlo; t->nhi2 = halo->nhi;
+    t->n_main = n1; t->n = n;
+    t->device_bytes += halo->device_bytes;
+    cudaEventDestroy(halo->ev0); cudaEventDestroy(halo->ev1); cudaEventDestroy(halo->ev2); cudaEventDestroy(halo->ev3);
+    cudaStreamDestroy(halo->stream);
+    delete halo;
     NBK_API_END
 }
 
@@ -404,6 +458,9 @@ int nbk_get_nodes(const nbk_tree* t, int64_t* num_slots, int32_t* start, int32_t
     NBK_API_END
 }
 
+static void require_no_halo(const nbk_tree* t, const char* what) {
+    if (t->n_main) throw Error(NBK_ERR_UNSUPPORTED, std::string(what) + ": a tree with an attached halo serves the Calc* family only");
+}
 static void require_knn_tree(const nbk_tree* t) {
     // Q4: TPHS trees with the constructor-default Aniso=0 take the metric path in the reference; no device version.
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TVEL, NBK_ERR_UNSUPPORTED,
@@ -414,6 +471,7 @@ int nbk_knn_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, d
     NBK_API_BEGIN
     NBK_REQUIRE(t, NBK_ERR_ARG, "nbk_knn_particles: null tree");
     require_knn_tree(t);
+    require_no_halo(t, "nbk_knn_particles");
     NBK_REQUIRE(q0 >= 0 && q1 <= t->n && q0 <= q1, NBK_ERR_ARG, "nbk_knn_particles: bad query range");
     NBK_REQUIRE(k >= 1, NBK_ERR_ARG, "nbk_knn_particles: k must be >= 1");
     DeviceGuard guard(t->device, t->stream);
@@ -446,6 +504,7 @@ int nbk_knn_points(nbk_tree* t, int k, int64_t m, const double* x, int32_t* nn, 
     NBK_API_BEGIN
     NBK_REQUIRE(t && x, NBK_ERR_ARG, "nbk_knn_points: null argument");
     require_knn_tree(t);
+    require_no_halo(t, "nbk_knn_points");
     NBK_REQUIRE(k >= 1 && m >= 0, NBK_ERR_ARG, "nbk_knn_points: bad k or m");
     if (m == 0) return NBK_OK;
     DeviceGuard guard(t->device, t->stream);
@@ -516,7 +575,7 @@ static void smooth_call(nbk_tree* t, int k, int veldens_k, double* rho, double* 
     const int64_t n = t->n;
     DevBuf<double> drho(rho ? n : 0), dh(hsm ? n : 0);
     KnnArgs a;
-    a.k = k; a.mode = 0; a.q0 = 0; a.q1 = n;
+    a.k = k; a.mode = 0; a.q0 = 0; a.q1 = t->n_main ? t->n_main : n;      // with a halo attached only the main particles are queries
     a.periodic = false;                       // quirk Q2: all Calc* searches ignore the period (KDCalcSmoothQuantities.cxx:227,338)
     a.rho = rho ? drho.p : nullptr; a.hsm = hsm ? dh.p : nullptr; a.veldens_k = veldens_k;
     DevBuf<uint8_t> dact, dact_tree;
@@ -577,6 +636,7 @@ int nbk_smoothing_scale(nbk_tree* t, int nsmooth, double* hsm, int flags) {
 
 static void fof_call(nbk_tree* t, FofArgs& a, const int32_t* precheck, int32_t* group, int64_t* ngroups, nbk_fof_lists* lists, int flags) {
     NBK_REQUIRE(group && ngroups, NBK_ERR_ARG, "FOF: null output");
+    require_no_halo(t, "FOF");
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "FOF needs a TPHYS or TPHS tree");
     DeviceGuard guard(t->device, t->stream);
     const int64_t n = t->n;
@@ -666,6 +726,7 @@ int nbk_fof_criterion_basis(nbk_tree* t, int criterion, const double* params, in
 static void ball_call(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx, const double* x, int64_t* offsets, int32_t* idx,
                       int64_t cap, int64_t* total, int flags) {
     NBK_REQUIRE(offsets && total, NBK_ERR_ARG, "ball search: null output");
+    require_no_halo(t, "ball search");
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "SearchBallPos needs positions as tree coordinates");
     DeviceGuard guard(t->device, t->stream);
     const bool dev = flags & NBK_DEVICE_PTRS;

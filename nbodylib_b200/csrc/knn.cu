@@ -47,6 +47,7 @@ __device__ __forceinline__ double wsm_fast(double r, int i, int size, double del
 
 struct KnnParams {
     const NodeLo* nlo; const NodeHi* nhi; int bucket;
+    const NodeLo* nlo2; const NodeHi* nhi2; int bucket2;   // attached halo tree (or null)
     const void* P; const void* V; const double* mass; const int32_t* order;
     int64_t n;
     int64_t q0, q1; const double* xq; int mode;      // mode 0: particles [q0,q1) or qlist; 1: points
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
     {
         QueryBox qb = make_qbox(x0, y0, z0);
         traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
+        if (prm.nlo2) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);
     }
     if (prm.periodic) {
         // reference image schedule: 3 faces, 3 edges, corner; each tested against the CURRENT top
@@ -1060,6 +1062,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams pr
             for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p));
             v.settop(v.hp.rootkey());
             traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
+            if (prm.nlo2) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);
             key_kp1 = v.hp.rootkey();
             v.hp.sift(0, 0.f);
             key_k = v.hp.rootkey();
@@ -1119,6 +1122,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams pr
             const double thrd_keep = c2.thr_d;
             if (!overflowed) { c2.thr = -1.f; c2.thr_d = -1.0; c2.limf = -1.f; }      // the other lanes are complete
             traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, overflowed);
+            if (prm.nlo2) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, c2, qb, overflowed);
             c2.thr = thr_keep; c2.limf = limf_keep; c2.thr_d = thrd_keep;
         }
         if (collecting) sc_epilogue<S>(prm, P, c2.L, base, lane, k, c2.cnt, short_of_k ? KNN_SENTINEL : c2.d2max, x0, y0, z0, qi);
@@ -1129,6 +1133,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams pr
 
 static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.nlo = t.nlo; p.nhi = t.nhi; p.bucket = t.bucket;
+    p.nlo2 = t.nlo2; p.nhi2 = t.nhi2; p.bucket2 = t.bucket;
     p.P = t.prim; p.V = t.vel4(); p.mass = t.mass; p.order = t.order;
     p.n = t.n;
     p.q0 = a.q0; p.q1 = a.q1; p.xq = a.xq; p.mode = a.mode;
@@ -1172,16 +1177,23 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
         // ---- fast path + exact fallback for the flagged queries ----------------------------------------------
         p.kcap = a.k + 1;
         const char* em = getenv("NBK_KNN_MODE");
-        const int mode = em ? atoi(em) : 2;     // 2: select + insertion log (default), 1: select-then-collect, 0: (key,index) heap
+        int mode = em ? atoi(em) : 2;           // 2: select + insertion log (default), 1: select-then-collect, 0: (key,index) heap
+        if (t.nlo2) mode = 2;                   // only the default kernel (and the exact one) walk an attached halo tree
         // nodes of up to `leaf` particles are scanned as one tile: fewer node tests and better balanced insertion rounds
         // The level whose nodes hold 21..40 particles (exactly one level does: sizes halve) -- a tile and a bit; with a fixed
         // threshold of 32 a particle count just above a power of two would be scanned as half-empty 16/17-particle tiles.
         {
             const char* e = getenv("NBK_KNN_LEAF");
-            int64_t sz = t.n;
+            int64_t sz = t.n_main ? t.n_main : t.n;
             while (sz > 40) sz = (sz + 1) / 2;
             int leaf = e ? atoi(e) : (int)sz;
             if (leaf > p.bucket) p.bucket = leaf;
+            if (t.nlo2) {
+                sz = t.n - t.n_main;
+                while (sz > 40) sz = (sz + 1) / 2;
+                leaf = e ? atoi(e) : (int)sz;
+                if (leaf > p.bucket2) p.bucket2 = leaf;
+            }
         }
         const int want_doubles = (a.veldens_k > 0 && a.veldens_k < a.k) ? 1 : 0;
         if (mode == 2) {
@@ -1267,7 +1279,7 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             if (nflag > 0) {
                 KnnParams pe = p;
                 pe.kcap = a.k;
-                pe.bucket = t.bucket;
+                pe.bucket = t.bucket; pe.bucket2 = t.bucket;
                 pe.qlist = flist.p; pe.nq = nflag;
                 pe.flag_count = nullptr; pe.flag_list = nullptr;
                 run_exact(t, pe, nflag);

@@ -31,6 +31,13 @@ struct nbk_tree {
     int depth = 0;                  // deepest level holding nodes
     int64_t num_nodes = 0, num_leaves = 0;
 
+    // optional second tree over "halo" particles (nbk_attach_halo): its particles are appended to the arrays above at
+    // positions [n_main, n), its nodes live in nlo2/nhi2 with ranges already offset by n_main.  Queries of the Calc* family
+    // then run for the main particles only and traverse both trees with the same per-query state.
+    int64_t n_main = 0;             // 0: no halo attached
+    nbk::NodeLo* nlo2 = nullptr;
+    nbk::NodeHi* nhi2 = nullptr;
+
     // smoothing kernel table
     double* d_kernel = nullptr;
     std::vector<double> h_kernel;

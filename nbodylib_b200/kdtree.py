@@ -26,9 +26,15 @@ def _is_torch(a):
 
 
 def _ptr(a):
+    """raw pointer of a numpy array or torch tensor.  The library works on its own CUDA stream: a torch tensor handed to it
+    must be complete, so torch's current stream is drained first (results are complete when a call returns: every entry
+    point synchronises the library's stream before returning)."""
     if a is None:
         return None
     if _is_torch(a):
+        if a.is_cuda:
+            import torch
+            torch.cuda.current_stream(a.device).synchronize()
         return C.c_void_p(a.data_ptr())
     return C.c_void_p(a.ctypes.data)
 
@@ -51,6 +57,8 @@ class KDTree:
                 return None, 0, 0
             if _is_torch(a):
                 assert a.is_cuda and a.is_contiguous()
+                import torch
+                torch.cuda.current_stream(a.device).synchronize()     # the library reads it on its own stream
                 rb = a.element_size()
                 keep.append(a)
                 return C.c_void_p(a.data_ptr()), cols * rb, rb
@@ -96,6 +104,14 @@ class KDTree:
 
     def __exit__(self, *a):
         self.close()
+
+    def attach_halo(self, halo):
+        """nbk_attach_halo: `halo` (another KDTree on the same device) becomes this tree's second tree and is consumed.
+        IDs of its particles follow this tree's; Calc* then query this tree's own particles against both."""
+        L.check(self._lib.nbk_attach_halo(self._h, halo._h))
+        halo._h = C.c_void_p()
+        self.n_main = self.n
+        self.n = int(self.info.n)
 
     @property
     def info(self):
@@ -202,6 +218,13 @@ class KDTree:
         h = np.empty(self.n) if want_h else None
         L.check(self._lib.nbk_calc_density(self._h, int(Nsmooth), _ptr(rho), _ptr(h), 0))
         return (rho, h) if want_h else rho
+
+    def CalcDensityInto(self, Nsmooth, rho_out, hsm_out=None):
+        """CalcDensity into caller arrays indexed by ID (torch CUDA tensors => device pointers, no copies).  On a tree with
+        an attached halo the arrays have n_main + n_halo entries and only the main particles are queries."""
+        flags = L.DEVICE_PTRS if _is_torch(rho_out) else 0
+        L.check(self._lib.nbk_calc_density(self._h, int(Nsmooth), _ptr(rho_out), _ptr(hsm_out), flags))
+        return rho_out
 
     def CalcDensitySubset(self, Nsmooth, active, rho_out, hsm_out=None):
         """CalcDensity restricted to the query particles with active[id] != 0 (uint8); ghosts act as neighbours only.

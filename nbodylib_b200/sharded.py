@@ -10,8 +10,9 @@ builds one local `KDTree` per rank.  This module is the B200 replacement for tha
   `h` of a slab face to the neighbour across that face (`batch_isend_irecv`, one message per face and direction,
   x shifted by +-Lx across the periodic wrap when the caller asks for it) and builds ONE local tree over
   owned + ghost particles.
-* **kNN-density** (`CalcDensity`): queries run for owned particles only (`nbk_calc_density_subset`), ghosts are
-  pure neighbours.  The symmetric scatter term that owned queries deposit on ghosts is sent back to the owners over
+* **kNN-density** (`CalcDensity`): queries run for owned particles only, ghosts are pure neighbours.  The ghosts live
+  in a SECOND tree attached to the owned particles' tree (`nbk_attach_halo`; `two_trees=False` builds one tree over
+  owned + ghosts and masks the queries with `nbk_calc_density_subset` instead).  The symmetric scatter term that owned queries deposit on ghosts is sent back to the owners over
   the same faces and added there, so every pair contributes exactly once -- the result equals the single-tree
   result.  The halo must contain every owned particle's k-th neighbour ball: after the pass, r_k = 2 h_sm is
   checked against (distance to the interior face + h); if any rank sees a violation (all-reduce) the halo is
@@ -42,8 +43,21 @@ class CudaEngine:
         from .kdtree import KDTree
         return KDTree(pos, vel, mass, Period=period, device=self.device)
 
+    def build_with_halo(self, pos, mass, gpos, gmass):
+        """owned particles in the main tree, ghosts in an attached second tree (nbk_attach_halo): the main tree's shape
+        does not depend on the halo, and a halo that has to be widened does not rebuild it"""
+        from .kdtree import KDTree
+        tree = KDTree(pos, None, mass, Period=None, device=self.device)
+        if gpos.shape[0] > 0:
+            halo = KDTree(gpos, None, gmass, Period=None, device=self.device)
+            tree.attach_halo(halo)
+        return tree
+
     def density(self, tree, k, active_u8, rho, hsm):
-        tree.CalcDensitySubset(k, active_u8, rho, hsm)
+        if getattr(tree, "n_main", None) is not None or active_u8 is None:
+            tree.CalcDensityInto(k, rho, hsm)       # queries = the main tree's particles by construction
+        else:
+            tree.CalcDensitySubset(k, active_u8, rho, hsm)
         return tree.info
 
     def fof_labels(self, tree, ll, out):
@@ -54,7 +68,7 @@ class CudaEngine:
 
 class ShardedTree:
     def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=None, slab_local=True, halo=None,
-                 knn_k=64, engine=None, group=None):
+                 knn_k=64, engine=None, group=None, two_trees=True):
         """pos/vel/mass: this rank's particles (torch tensors on the rank's device).
         slab_local=True : `pos` is given in slab-local coordinates [0,1)^3 (each rank generated its own unit box,
                           the bench's weak-scaling set-up); the global box is [0,world) x [0,1) x [0,1).
@@ -96,6 +110,7 @@ class ShardedTree:
         vol = (self.x1 - self.x0) * self.box[1] * self.box[2]
         self.h_knn = float(halo) if halo is not None else 2.5 * (knn_k * vol / max(self.n_owned, 1) / (4.0 * np.pi / 3.0)) ** (1.0 / 3.0)
         self._dens = None       # cached (tree, halo, ghost bookkeeping) for the density pass
+        self.two_trees = two_trees
         self.last_info = None
         self.stats = {}
 
@@ -163,12 +178,16 @@ class ShardedTree:
     def _density_setup(self, k):
         halo = self._halo(self.h_knn, wrap=False)
         g = torch.cat([halo["from_l"], halo["from_r"]], dim=0)
-        pos = torch.cat([self.pos, g[:, 0:3]], dim=0).contiguous()
-        mass = torch.cat([self.mass, g[:, 6]], dim=0).contiguous()
-        n_all = pos.shape[0]
-        tree = self.engine.build(pos, None, mass, None)
-        active = torch.zeros(n_all, dtype=torch.uint8, device=self.dev)
-        active[:self.n_owned] = 1
+        n_all = self.n_owned + g.shape[0]
+        if hasattr(self.engine, "build_with_halo") and self.two_trees:
+            tree = self.engine.build_with_halo(self.pos, self.mass, g[:, 0:3].contiguous(), g[:, 6].contiguous())
+            active = None
+        else:
+            pos = torch.cat([self.pos, g[:, 0:3]], dim=0).contiguous()
+            mass = torch.cat([self.mass, g[:, 6]], dim=0).contiguous()
+            tree = self.engine.build(pos, None, mass, None)
+            active = torch.zeros(n_all, dtype=torch.uint8, device=self.dev)
+            active[:self.n_owned] = 1
         self._dens = {"tree": tree, "halo": halo, "active": active, "n_all": n_all,
                       "rho": torch.empty(n_all, dtype=self.f, device=self.dev), "hsm": torch.empty(n_all, dtype=self.f, device=self.dev)}
         self.stats["ghosts_knn"] = int(n_all - self.n_owned)

@@ -497,3 +497,35 @@ def test_checked_fof_against_reference(nb, periodic):
                 # with a size threshold such a particle can tip a group over it -- both rare
                 assert same.mean() > 0.999 and abs(ng - rng_) <= 2
     R.close()
+
+
+@pytest.mark.parametrize("flags", [0, 1 << 4])
+def test_attached_halo_tree_equals_masked_single_tree(nb, flags):
+    """nbk_attach_halo: main particles in one tree, halo particles in a second one; CalcDensity queries the main particles
+    against both.  Must equal the single tree over main + halo with the queries masked to the main particles
+    (nbk_calc_density_subset), which is itself checked against the oracle by the sharded tests."""
+    from nbodylib_b200.synth import clustered_small
+    n, k = 60000, 48
+    pos, vel, mass = clustered_small(n, seed=91)
+    halo_sel = pos[:, 0] > 0.93                       # a slab face worth of "ghosts"
+    main_idx, halo_idx = np.nonzero(~halo_sel)[0], np.nonzero(halo_sel)[0]
+    allpos = np.concatenate([pos[main_idx], pos[halo_idx]])
+    allmass = np.concatenate([mass[main_idx], mass[halo_idx]])
+    n1 = len(main_idx)
+    active = np.zeros(n, dtype=np.uint8)
+    active[:n1] = 1
+    rho_ref, h_ref = np.zeros(n), np.zeros(n)
+    with nb.KDTree(allpos, None, allmass, flags=flags) as t:
+        t.CalcDensitySubset(k, active, rho_ref, h_ref)
+    t1 = nb.KDTree(pos[main_idx], None, mass[main_idx], flags=flags)
+    t2 = nb.KDTree(pos[halo_idx], None, mass[halo_idx], flags=flags)
+    t1.attach_halo(t2)
+    assert t1.n == n and t1.n_main == n1
+    rho, h = np.zeros(n), np.zeros(n)
+    t1.CalcDensityInto(k, rho, h)
+    assert np.array_equal(h[:n1], h_ref[:n1])
+    np.testing.assert_allclose(rho, rho_ref, rtol=RTOL_RHO, atol=1e-300)
+    assert rho[n1:].max() > 0                          # scatter terms did land on halo particles
+    with pytest.raises(nb.NbkError):
+        t1.FOF(0.01, 8, 0)
+    t1.close()
