@@ -147,6 +147,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # fail fast instead of hanging the caller: a healthy run ends within ~2 minutes at any N
+    import signal
+    signal.alarm(int(os.environ.get("BENCH_WATCHDOG_S", "900")))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
