@@ -5,9 +5,12 @@
 #include <KDTree.h>
 
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <random>
 using namespace NBody;
+
+static int type_check(Particle& p, Double_t*) { return p.GetType() != 0 ? -1 : 0; }
 
 int main() {
     const Int_t N = 200000;
@@ -73,6 +76,77 @@ int main() {
         printf("FOF6d: %d groups\n", ng6);
         delete[] p6;
         if (ng <= 0 || !(mean > 0)) bad++;
+    }
+    // second tree, non periodic: the single-target estimators, criterion search, dense ball search and the node mirror
+    {
+        KDTree tree(parts.data(), N, 16, KDTree::TPHYS, KDTree::KEPAN, 1000);
+        const int K = 32;
+        Int_t nn[K]; Double_t d2[K], dist[K], weight[K];
+        double worst = 0;
+        for (Int_t tt = 3; tt < N; tt += N / 11) {
+            // CalcDensityParticle == CalcSmoothLocalValue over the target's own neighbour list with the masses as weights
+            tree.FindNearestPos(tt, nn, d2, K);
+            for (int j = 0; j < K; j++) { dist[j] = std::sqrt(d2[K - 1 - j]); weight[j] = parts[nn[K - 1 - j]].GetMass(); }
+            double v1 = tree.CalcSmoothLocalValue(K, dist, weight), v2 = tree.CalcDensityParticle(tt, K);
+            PriorityQueue pq(K);
+            for (int j = 0; j < K; j++) pq.Push(nn[j], d2[j]);
+            for (int j = 0; j < K; j++) weight[j] = 1.0;                       // unit masses: the pop order does not matter
+            double v3 = tree.CalcSmoothLocalValue(K, &pq, weight);
+            worst = std::fmax(worst, std::fmax(std::fabs(v1 - v2), std::fabs(v3 - v2)) / v2);
+            // the position form at the particle's own position sees the particle itself as the nearest neighbour
+            Double_t x[3] = {parts[tt].X(), parts[tt].Y(), parts[tt].Z()}, v[3] = {parts[tt].GetVelocity(0), parts[tt].GetVelocity(1), parts[tt].GetVelocity(2)};
+            if (!(tree.CalcDensityPosition(x, K) > 0) || !(tree.CalcVelDensityPosition(x, v, K / 2, K) > 0) || !(tree.CalcVelDensityParticle(tt, K / 2, K) > 0)) bad++;
+            // criterion search with FOF3d == ball search of the same radius; dense form marks the same particles
+            const double r2 = 0.01 * 0.01;
+            Double_t params[10] = {0};
+            params[1] = params[6] = r2;
+            std::vector<Int_t> a = tree.SearchBallPosTagged(tt, r2), b = tree.SearchCriterionTagged(tt, FOF3d, params);
+            std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+            if (a != b) bad++;
+            std::vector<Int_t> mark(N, 0); std::vector<Double_t> md2(N, -1.0);
+            tree.SearchBallPos(tt, r2, 7, mark.data(), md2.data());
+            size_t marked = 0;
+            for (Int_t i = 0; i < N; i++) if (mark[i] == 7) { marked++; if (!(md2[i] >= 0 && md2[i] < r2)) bad++; }
+            if (marked != a.size()) bad++;
+            for (Int_t j : a) if (mark[parts[j].GetID()] != 7) bad++;
+            // node mirror
+            Node* leaf = tree.FindLeafNode(tt);
+            if (!(leaf->GetLeaf() && leaf->GetStart() <= tt && tt < leaf->GetEnd() && leaf->GetCount() <= 16)) bad++;
+            for (int k = 0; k < 3; k++) if (!(leaf->GetBoundary(k, 0) <= x[k] && x[k] <= leaf->GetBoundary(k, 1))) bad++;
+            if (tree.FindLeafNode(x) != leaf && tree.FindLeafNode(x)->GetCount() > 16) bad++;
+        }
+        // filtered neighbours: FindNearestCheck only returns particles passing the caller's check, FindNearestCriterion only
+        // particles meeting the criterion; both are subsets of the unfiltered ordering
+        {
+            for (Int_t i = 0; i < N; i++) parts[i].SetType(parts[i].GetPID() % 3 == 0 ? 1 : 0);
+            Double_t params[10] = {0};
+            params[1] = params[6] = 0.02 * 0.02; params[2] = params[7] = 4.0;
+            Int_t n8[8], n8c[8]; Double_t d8[8], d8c[8], dall[8]; Int_t nall[8];
+            for (Int_t tt = 5; tt < N; tt += N / 13) {
+                tree.FindNearestCheck(tt, type_check, params, n8, d8, 8);
+                tree.FindNearestPos(tt, nall, dall, 8);
+                for (int j = 0; j < 8; j++) {
+                    if (n8[j] < 0 || parts[n8[j]].GetType() != 0 || n8[j] == tt || (j && d8[j] < d8[j - 1]) || d8[j] < dall[j]) bad++;
+                }
+                tree.FindNearestCriterion(tt, FOF6d, params, n8c, d8c, 8);
+                for (int j = 0; j < 8; j++) {
+                    if (n8c[j] < 0) { if (d8c[j] < 1e31) bad++; continue; }
+                    if (!FOF6d(parts[tt], parts[n8c[j]], params) || n8c[j] == tt || (j && d8c[j] < d8c[j - 1])) bad++;
+                }
+            }
+            for (Int_t i = 0; i < N; i++) parts[i].SetType(0);
+        }
+        printf("single-target density vs CalcSmoothLocalValue: worst relative difference %.3g\n", worst);
+        if (!(worst < 1e-12)) bad++;
+        long leaves = 0, count = 0;
+        std::vector<Node*> st(1, tree.GetRoot());
+        while (!st.empty()) {
+            Node* nd = st.back(); st.pop_back();
+            if (nd->GetLeaf()) { leaves++; count += nd->GetCount(); }
+            else { st.push_back(((SplitNode*)nd)->GetRight()); st.push_back(((SplitNode*)nd)->GetLeft()); }
+        }
+        printf("node mirror: %ld leaves, %ld particles\n", leaves, count);
+        if (leaves != tree.GetNumLeafNodes() || count != N || tree.GetRoot()->GetCount() != N) bad++;
     }
     // destructor restored the input order
     for (Int_t i = 0; i < N; i++) if (parts[i].GetID() != i || parts[i].GetPID() != i) { bad++; break; }

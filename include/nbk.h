@@ -118,15 +118,47 @@ int nbk_knn_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, d
  * for m query points x[m][3]. */
 int nbk_knn_points(nbk_tree* t, int k, int64_t m, const double* x, int32_t* nn, double* d2, int flags);
 
+/* Replaces KDTree::FindNearestCheck(Int_t tt | Particle p | Coordinate x, check, params, nn, dist2, Nsearch) and
+ * KDTree::FindNearestCriterion(Int_t tt | Particle p, cmp, params, nn, dist2, Nsearch) (KDFindNearest.cxx:363-441; leaf code
+ * KDLeafNode.cxx:88-118,202-246): the k nearest among the particles i != target with 0 < d2 that pass the filters --
+ *   check  (optional, n entries by ID, or tree order with NBK_TREE_ORDER): the caller's FOFcheckfunc values; only
+ *          check == 0 particles can be neighbours;
+ *   criterion (NBK_FOF3D / NBK_FOF6D, or -1 for none) with the reference's params[] (criterion parameters at [6], [7]):
+ *          only particles with cmp(target, i, params) == 1 can be neighbours.  Point form: v = query velocities (FOF6d).
+ * Rows ascending in d2; missing neighbours are (-1, 1e32) like the reference's sentinels.  Periodic trees: minimum image
+ * over the reference's reflections.  The reference's periodic forms search Nsearch+1 and then drop the NEAREST entry
+ * (KDFindNearest.cxx:365,376: LoadNN leaves the smallest of k+1 in the queue, although the target is never queued);
+ * NBK_KNN_TREE_FORM reproduces that, without it the k nearest are returned. */
+int nbk_knn_filtered_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int criterion, const double* params,
+                               const int32_t* check, int32_t* nn, double* d2, int flags);
+int nbk_knn_filtered_points(nbk_tree* t, int k, int64_t m, const double* x, const double* v, int criterion, const double* params,
+                            const int32_t* check, int32_t* nn, double* d2, int flags);
+
 /* Replaces KDTree::SearchBallPosTagged(Int_t tt / Double_t* x, fdist2, tagged) (KDFindNearest.cxx:618-688)
  * for a batch: CSR rows; offsets[m+1]; idx capacity cap; *total = entries required.
  * Rows hold every particle with d2 < fdist2 (strict; minimum image over the reference's reflections
  * when periodic).  Particle form (qidx = tree indices): the query itself is excluded when non periodic,
- * included when periodic (quirk Q5).  Rows are sorted ascending. */
+ * included when periodic (quirk Q5).  Rows are sorted ascending.
+ * d2 (optional, cap entries, same layout as idx): squared position distance of every entry -- what the dense forms
+ * KDTree::SearchBallPos(tt / x, fdist2, imark, nn, dist2) (KDFindNearest.cxx:567-587) write into dist2[ID]; the shim
+ * builds the dense nn[] / dist2[] arrays from a row.  idx == NULL (or cap == 0): count pass only. */
 int nbk_ball_particles(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx, int64_t* offsets,
-                       int32_t* idx, int64_t cap, int64_t* total, int flags);
+                       int32_t* idx, double* d2, int64_t cap, int64_t* total, int flags);
 int nbk_ball_points(nbk_tree* t, double fdist2, int64_t m, const double* x, int64_t* offsets,
-                    int32_t* idx, int64_t cap, int64_t* total, int flags);
+                    int32_t* idx, double* d2, int64_t cap, int64_t* total, int flags);
+
+/* Replaces KDTree::SearchCriterionTagged(Int_t tt | Particle& p, cmp, params, tagged) and the dense
+ * KDTree::SearchCriterion(tt, cmp, params, imark, nn[, dist2]) (KDFindNearest.cxx:590-603,643-706; leaf code
+ * KDLeafNode.cxx:414-492) for a batch and the in-tree criteria NBK_FOF3D / NBK_FOF6D: every particle i != target with
+ * cmp(target, i, params) true, CSR like nbk_ball_*.  The reference prunes the tree walk with params[1] (position
+ * distance^2) and evaluates cmp on every particle of a visited leaf; here pruning uses the radius the criterion itself
+ * implies (params[6]), which gives the same set whenever params[1] >= params[6] (the way callers set it) and the full
+ * criterion set otherwise.  Point form: v = query velocities (m x 3, needed by FOF6d, may be NULL for FOF3d);
+ * nothing is excluded (a Particle that is not in the tree never compares equal to a tree particle). */
+int nbk_search_criterion_particles(nbk_tree* t, int criterion, const double* params, int64_t m, const int32_t* qidx,
+                                   int64_t* offsets, int32_t* idx, double* d2, int64_t cap, int64_t* total, int flags);
+int nbk_search_criterion_points(nbk_tree* t, int criterion, const double* params, int64_t m, const double* x, const double* v,
+                                int64_t* offsets, int32_t* idx, double* d2, int64_t cap, int64_t* total, int flags);
 
 /* Replaces KDTree::CalcDensity(Nsmooth) (KDCalcSmoothQuantities.cxx:203-305).  rho[n] by ID
  * (or tree index with NBK_TREE_ORDER); hsm (optional) = 0.5*sqrt(d2_k), the smoothing scale. */
@@ -140,6 +172,17 @@ int nbk_calc_density_subset(nbk_tree* t, int nsmooth, const uint8_t* active, dou
 int nbk_calc_veldensity(nbk_tree* t, int nsmooth, int nsearch, double* rho, int flags);
 /* "CalcSmoothingScale" (named by the north star; = hi of KDCalcSmoothQuantities.cxx:260). */
 int nbk_smoothing_scale(nbk_tree* t, int nsmooth, double* hsm, int flags);
+
+/* Replace the single-target forms KDTree::CalcDensityParticle(target, Nsmooth) / CalcVelDensityParticle(target, Nsmooth,
+ * Nsearch) (KDCalcSmoothQuantities.cxx:768-921) and CalcDensityPosition(x, Nsmooth) / CalcVelDensityPosition(x, v, Nsmooth,
+ * Nsearch) (:1092-1207) for a batch of m queries: gather-only sums (weight 1.0 * W, no scatter term, no 0.5 factor), one
+ * value per query in rho[m].  Particle forms: qidx = tree indices (target search: the particle itself and coincident
+ * particles are not neighbours); qidx == NULL means tree indices 0..m-1.  Point forms: coordinate search (d2 = 0 counts).
+ * Like every Calc* call they ignore the period (quirk Q2). */
+int nbk_calc_density_particles(nbk_tree* t, int nsmooth, int64_t m, const int32_t* qidx, double* rho, int flags);
+int nbk_calc_veldensity_particles(nbk_tree* t, int nsmooth, int nsearch, int64_t m, const int32_t* qidx, double* rho, int flags);
+int nbk_calc_density_points(nbk_tree* t, int nsmooth, int64_t m, const double* x, double* rho, int flags);
+int nbk_calc_veldensity_points(nbk_tree* t, int nsmooth, int nsearch, int64_t m, const double* x, const double* v, double* rho, int flags);
 
 /* Optional FOF by-products in tree-index space (reference KDFOF.cxx:52-55: pHead,pNext,pTail,pLen).
  * Any pointer may be NULL.  head/next/tail have n entries: the members of a group are chained in ascending tree

@@ -40,6 +40,9 @@ EXPORTS = [
     "nbk_get_kernel_table", "nbk_get_nodes", "nbk_knn_particles", "nbk_knn_points", "nbk_ball_particles",
     "nbk_ball_points", "nbk_calc_density", "nbk_calc_density_subset", "nbk_calc_veldensity", "nbk_smoothing_scale", "nbk_fof",
     "nbk_fof_criterion", "nbk_fof_criterion_basis", "nbk_attach_halo", "nbk_device_arrays", "nbk_release_cached_memory",
+    "nbk_search_criterion_particles", "nbk_search_criterion_points", "nbk_calc_density_particles",
+    "nbk_calc_veldensity_particles", "nbk_calc_density_points", "nbk_calc_veldensity_points",
+    "nbk_knn_filtered_particles", "nbk_knn_filtered_points",
 ]
 
 _lib = None
@@ -65,8 +68,16 @@ def load():
     L.nbk_get_nodes.argtypes = [vp, C.POINTER(i64), vp, vp, vp, vp]
     L.nbk_knn_particles.argtypes = [vp, i32, i64, i64, vp, vp, i32]
     L.nbk_knn_points.argtypes = [vp, i32, i64, vp, vp, vp, i32]
-    L.nbk_ball_particles.argtypes = [vp, dbl, i64, vp, vp, vp, i64, C.POINTER(i64), i32]
-    L.nbk_ball_points.argtypes = [vp, dbl, i64, vp, vp, vp, i64, C.POINTER(i64), i32]
+    L.nbk_knn_filtered_particles.argtypes = [vp, i32, i64, i64, i32, vp, vp, vp, vp, i32]
+    L.nbk_knn_filtered_points.argtypes = [vp, i32, i64, vp, vp, i32, vp, vp, vp, vp, i32]
+    L.nbk_ball_particles.argtypes = [vp, dbl, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]
+    L.nbk_ball_points.argtypes = [vp, dbl, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]
+    L.nbk_search_criterion_particles.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]
+    L.nbk_search_criterion_points.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, i64, C.POINTER(i64), i32]
+    L.nbk_calc_density_particles.argtypes = [vp, i32, i64, vp, vp, i32]
+    L.nbk_calc_veldensity_particles.argtypes = [vp, i32, i32, i64, vp, vp, i32]
+    L.nbk_calc_density_points.argtypes = [vp, i32, i64, vp, vp, i32]
+    L.nbk_calc_veldensity_points.argtypes = [vp, i32, i32, i64, vp, vp, vp, i32]
     L.nbk_calc_density.argtypes = [vp, i32, vp, vp, i32]
     L.nbk_calc_density_subset.argtypes = [vp, i32, vp, vp, vp, i32]
     L.nbk_calc_veldensity.argtypes = [vp, i32, i32, vp, i32]

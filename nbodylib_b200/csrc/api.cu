@@ -78,6 +78,10 @@ __global__ void gather_u8_kernel(int64_t n, const int32_t* order, const uint8_t*
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[order[i]];
 }
+__global__ void check_indices_kernel(int64_t m, const int32_t* q, int32_t n, int* bad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m && (q[i] < 0 || q[i] >= n)) *bad = 1;
+}
 __global__ void gather_i32_kernel(int64_t n, const int32_t* order, const int32_t* src, int32_t* dst) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[order[i]];
@@ -449,7 +453,7 @@ int nbk_get_nodes(const nbk_tree* t, int64_t* num_slots, int32_t* start, int32_t
     for (int64_t i = 0; i < t->nslots; i++) {
         if (start) start[i] = lo[i].start;
         if (end) end[i] = hi[i].end;
-        if (cutdim) cutdim[i] = cd[i];
+        if (cutdim) cutdim[i] = (lo[i].start >= 0 && hi[i].end - lo[i].start > t->bucket) ? cd[i] : -1;   // leaf iff size <= bucket
         if (bounds) {
             bounds[6 * i + 0] = lo[i].x; bounds[6 * i + 1] = hi[i].x; bounds[6 * i + 2] = lo[i].y;
             bounds[6 * i + 3] = hi[i].y; bounds[6 * i + 4] = lo[i].z; bounds[6 * i + 5] = hi[i].z;
@@ -532,6 +536,95 @@ int nbk_knn_points(nbk_tree* t, int k, int64_t m, const double* x, int32_t* nn, 
         if (d2) NBK_CHECK(cudaMemcpyAsync(d2, dd2.p, dd2.bytes(), cudaMemcpyDeviceToHost, t->stream));
         NBK_CHECK(cudaStreamSynchronize(t->stream));
     }
+    NBK_API_END
+}
+
+// FindNearestCheck / FindNearestCriterion: the exact kernel with candidate filters
+static void knn_filtered_call(nbk_tree* t, int k, int64_t q0, int64_t q1, int64_t m, const double* x, const double* v, int criterion,
+                              const double* params, const int32_t* check, int32_t* nn, double* d2, int flags) {
+    require_knn_tree(t);
+    require_no_halo(t, "filtered kNN");
+    NBK_REQUIRE(t->treetype == NBK_TPHYS, NBK_ERR_UNSUPPORTED, "FindNearestCheck / FindNearestCriterion need a physical tree");
+    NBK_REQUIRE(k >= 1, NBK_ERR_ARG, "filtered kNN: k must be >= 1");
+    NBK_REQUIRE(criterion >= 0 || check, NBK_ERR_ARG, "filtered kNN: neither a criterion nor check values given");
+    DeviceGuard guard(t->device, t->stream);
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    const int64_t n = t->n;
+    KnnArgs a;
+    a.k = k;
+    a.periodic = t->periodic;
+    a.strict = true;            // the reference walks all 8 images unconditionally (KDSplitNode.cxx:1255-1340): any exact schedule agrees
+    a.tree_form = flags & NBK_KNN_TREE_FORM;
+    a.out_ids = flags & NBK_OUT_IDS;
+    if (criterion >= 0) {
+        NBK_REQUIRE(params, NBK_ERR_ARG, "filtered kNN: criterion without params");
+        if (!(criterion == NBK_FOF3D || criterion == NBK_FOF6D))
+            throw Error(criterion == NBK_FOFVEL ? NBK_ERR_UNSUPPORTED : NBK_ERR_ARG, "FindNearestCriterion: only FOF3d and FOF6d have device implementations");
+        a.crit_mode = criterion == NBK_FOF3D ? 2 : 4;
+        a.cp0 = params[6]; a.cp1 = params[7];
+    }
+    DevBuf<int32_t> dchk, dchk_tree, dnn;
+    DevBuf<double> dx, dv, dd2;
+    if (check) {
+        const int32_t* src = check;
+        if (!dev) {
+            dchk.alloc(n);
+            NBK_CHECK(cudaMemcpyAsync(dchk.p, check, sizeof(int32_t) * n, cudaMemcpyHostToDevice, t->stream));
+            src = dchk.p;
+        }
+        if (flags & NBK_TREE_ORDER) a.cand_excl = src;
+        else {
+            dchk_tree.alloc(n);
+            gather_i32_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, src, dchk_tree.p);
+            a.cand_excl = dchk_tree.p;
+        }
+    }
+    int64_t rows;
+    if (x) {
+        a.mode = 1; a.q0 = 0; a.q1 = m; rows = m;
+        if (dev) { a.xq = x; a.vq = v; }
+        else {
+            dx.alloc((size_t)3 * m);
+            NBK_CHECK(cudaMemcpyAsync(dx.p, x, dx.bytes(), cudaMemcpyHostToDevice, t->stream));
+            a.xq = dx.p;
+            if (v) { dv.alloc((size_t)3 * m); NBK_CHECK(cudaMemcpyAsync(dv.p, v, dv.bytes(), cudaMemcpyHostToDevice, t->stream)); a.vq = dv.p; }
+        }
+        NBK_REQUIRE(a.crit_mode != 4 || a.vq, NBK_ERR_ARG, "FindNearestCriterion(FOF6d) at a point needs the query velocity");
+    } else {
+        NBK_REQUIRE(q0 >= 0 && q1 <= n && q0 <= q1, NBK_ERR_ARG, "filtered kNN: bad query range");
+        a.mode = 0; a.q0 = q0; a.q1 = q1; rows = q1 - q0;
+    }
+    if (rows == 0) return;
+    if (dev) { a.nn = nn; a.d2 = d2; }
+    else {
+        if (nn) { dnn.alloc((size_t)rows * k); a.nn = dnn.p; }
+        if (d2) { dd2.alloc((size_t)rows * k); a.d2 = dd2.p; }
+    }
+    NBK_REQUIRE(a.nn || a.d2, NBK_ERR_ARG, "filtered kNN: no output requested");
+    CallTimer tm(*t);
+    launch_knn(*t, a);
+    tm.stop();
+    t->last_kernel_ms = t->last_call_ms; t->last_launches = 1;
+    if (!dev) {
+        if (nn) NBK_CHECK(cudaMemcpyAsync(nn, dnn.p, dnn.bytes(), cudaMemcpyDeviceToHost, t->stream));
+        if (d2) NBK_CHECK(cudaMemcpyAsync(d2, dd2.p, dd2.bytes(), cudaMemcpyDeviceToHost, t->stream));
+    }
+    NBK_CHECK(cudaStreamSynchronize(t->stream));
+}
+
+int nbk_knn_filtered_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int criterion, const double* params, const int32_t* check,
+                               int32_t* nn, double* d2, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t, NBK_ERR_ARG, "nbk_knn_filtered_particles: null tree");
+    knn_filtered_call(t, k, q0, q1, 0, nullptr, nullptr, criterion, params, check, nn, d2, flags);
+    NBK_API_END
+}
+int nbk_knn_filtered_points(nbk_tree* t, int k, int64_t m, const double* x, const double* v, int criterion, const double* params,
+                            const int32_t* check, int32_t* nn, double* d2, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && (x || m == 0) && m >= 0, NBK_ERR_ARG, "nbk_knn_filtered_points: null argument");
+    if (m == 0) return NBK_OK;
+    knn_filtered_call(t, k, 0, 0, m, x, v, criterion, params, check, nn, d2, flags);
     NBK_API_END
 }
 
@@ -723,24 +816,53 @@ int nbk_fof_criterion_basis(nbk_tree* t, int criterion, const double* params, in
     NBK_API_END
 }
 
-static void ball_call(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx, const double* x, int64_t* offsets, int32_t* idx,
-                      int64_t cap, int64_t* total, int flags) {
+struct CritSpec { int mode = 0; double p0 = 0, p1 = 0, prune_x2 = 0; };
+
+// criterion code + reference params[] -> device predicate (shared by FOFCriterion* and SearchCriterion*)
+static CritSpec crit_from_params(int criterion, const double* params, const char* who) {
+    if (!(criterion == NBK_FOF3D || criterion == NBK_FOF6D))
+        throw Error(criterion == NBK_FOFVEL ? NBK_ERR_UNSUPPORTED : NBK_ERR_ARG,
+                    std::string(who) + ": only FOF3d and FOF6d have device implementations (host FOFcompfunc callbacks cannot run on the GPU; "
+                                       "FOFVel's result depends on the reference's traversal order, see DESIGN.md)");
+    CritSpec c;
+    c.mode = criterion == NBK_FOF3D ? 2 : 4;
+    c.p0 = params[6]; c.p1 = params[7];
+    // any accepted pair has sum(dx^2)/params[6] < 1; the tiny factor covers the rounding of the divided sum
+    c.prune_x2 = params[6] * (1.0 + 1e-12);
+    return c;
+}
+
+static void ball_call(nbk_tree* t, double fdist2, const CritSpec* crit, int64_t m, const int32_t* qidx, const double* x, const double* vq,
+                      int64_t* offsets, int32_t* idx, double* d2, int64_t cap, int64_t* total, int flags) {
     NBK_REQUIRE(offsets && total, NBK_ERR_ARG, "ball search: null output");
+    NBK_REQUIRE(m >= 0 && cap >= 0, NBK_ERR_ARG, "ball search: negative count");
     require_no_halo(t, "ball search");
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "SearchBallPos needs positions as tree coordinates");
     DeviceGuard guard(t->device, t->stream);
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<int32_t> dq, didx;
-    DevBuf<double> dx;
+    DevBuf<double> dx, dv, dd2;
     DevBuf<int64_t> doff;
     BallArgs a;
     a.r2 = fdist2; a.m = m; a.cap = idx ? cap : 0; a.out_ids = flags & NBK_OUT_IDS;
-    if (dev) { a.qidx = qidx; a.xq = x; a.offsets = offsets; a.idx = idx; }
+    if (crit) { a.mode = crit->mode; a.p0 = crit->p0; a.p1 = crit->p1; a.prune_x2 = crit->prune_x2; }
+    if (dev) { a.qidx = qidx; a.xq = x; a.vq = vq; a.offsets = offsets; a.idx = idx; a.d2 = idx ? d2 : nullptr; }
     else {
         if (qidx) { dq.alloc(m); NBK_CHECK(cudaMemcpyAsync(dq.p, qidx, sizeof(int32_t) * m, cudaMemcpyHostToDevice, t->stream)); a.qidx = dq.p; }
         if (x) { dx.alloc((size_t)3 * m); NBK_CHECK(cudaMemcpyAsync(dx.p, x, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, t->stream)); a.xq = dx.p; }
+        if (vq) { dv.alloc((size_t)3 * m); NBK_CHECK(cudaMemcpyAsync(dv.p, vq, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, t->stream)); a.vq = dv.p; }
         doff.alloc(m + 1); a.offsets = doff.p;
-        if (idx && cap > 0) { didx.alloc(cap); a.idx = didx.p; }
+        if (idx && cap > 0) { didx.alloc(cap); a.idx = didx.p; if (d2) { dd2.alloc(cap); a.d2 = dd2.p; } }
+    }
+    if (qidx && m > 0) {
+        // tree indices come from the caller: check them on the device side of the boundary
+        DevBuf<int> bad(1);
+        NBK_CHECK(cudaMemsetAsync(bad.p, 0, sizeof(int), t->stream));
+        check_indices_kernel<<<div_up(m, 256), 256, 0, t->stream>>>(m, a.qidx, (int32_t)t->n, bad.p);
+        int hb = 0;
+        NBK_CHECK(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+        NBK_REQUIRE(hb == 0, NBK_ERR_ARG, "ball search: particle index out of range");
     }
     CallTimer tm(*t);
     launch_ball(*t, a);
@@ -749,23 +871,120 @@ static void ball_call(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx
     if (!dev) {
         NBK_CHECK(cudaMemcpyAsync(offsets, doff.p, sizeof(int64_t) * (m + 1), cudaMemcpyDeviceToHost, t->stream));
         if (idx && cap > 0) NBK_CHECK(cudaMemcpyAsync(idx, didx.p, sizeof(int32_t) * std::min(cap, a.total), cudaMemcpyDeviceToHost, t->stream));
+        if (idx && d2 && cap > 0) NBK_CHECK(cudaMemcpyAsync(d2, dd2.p, sizeof(double) * std::min(cap, a.total), cudaMemcpyDeviceToHost, t->stream));
         NBK_CHECK(cudaStreamSynchronize(t->stream));
     }
     if (idx && a.total > cap) throw Error(NBK_ERR_CAPACITY, "ball search: index buffer too small (see *total)");
 }
 
-int nbk_ball_particles(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx, int64_t* offsets, int32_t* idx, int64_t cap,
+int nbk_ball_particles(nbk_tree* t, double fdist2, int64_t m, const int32_t* qidx, int64_t* offsets, int32_t* idx, double* d2, int64_t cap,
                        int64_t* total, int flags) {
     NBK_API_BEGIN
     NBK_REQUIRE(t && (qidx || m == 0), NBK_ERR_ARG, "nbk_ball_particles: null argument");
-    ball_call(t, fdist2, m, qidx, nullptr, offsets, idx, cap, total, flags);
+    ball_call(t, fdist2, nullptr, m, qidx, nullptr, nullptr, offsets, idx, d2, cap, total, flags);
     NBK_API_END
 }
-int nbk_ball_points(nbk_tree* t, double fdist2, int64_t m, const double* x, int64_t* offsets, int32_t* idx, int64_t cap,
+int nbk_ball_points(nbk_tree* t, double fdist2, int64_t m, const double* x, int64_t* offsets, int32_t* idx, double* d2, int64_t cap,
                     int64_t* total, int flags) {
     NBK_API_BEGIN
     NBK_REQUIRE(t && (x || m == 0), NBK_ERR_ARG, "nbk_ball_points: null argument");
-    ball_call(t, fdist2, m, nullptr, x, offsets, idx, cap, total, flags);
+    ball_call(t, fdist2, nullptr, m, nullptr, x, nullptr, offsets, idx, d2, cap, total, flags);
+    NBK_API_END
+}
+int nbk_search_criterion_particles(nbk_tree* t, int criterion, const double* params, int64_t m, const int32_t* qidx, int64_t* offsets,
+                                   int32_t* idx, double* d2, int64_t cap, int64_t* total, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && params && (qidx || m == 0), NBK_ERR_ARG, "nbk_search_criterion_particles: null argument");
+    CritSpec c = crit_from_params(criterion, params, "nbk_search_criterion_particles");
+    ball_call(t, 0.0, &c, m, qidx, nullptr, nullptr, offsets, idx, d2, cap, total, flags);
+    NBK_API_END
+}
+int nbk_search_criterion_points(nbk_tree* t, int criterion, const double* params, int64_t m, const double* x, const double* v,
+                                int64_t* offsets, int32_t* idx, double* d2, int64_t cap, int64_t* total, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && params && (x || m == 0), NBK_ERR_ARG, "nbk_search_criterion_points: null argument");
+    CritSpec c = crit_from_params(criterion, params, "nbk_search_criterion_points");
+    NBK_REQUIRE(c.mode != 4 || v || m == 0, NBK_ERR_ARG, "nbk_search_criterion_points: FOF6d needs the query velocities");
+    ball_call(t, 0.0, &c, m, nullptr, x, v, offsets, idx, d2, cap, total, flags);
+    NBK_API_END
+}
+
+// ---- *Particle / *Position forms of the smoothed estimators ------------------------------------------------------
+static void smooth_gather_call(nbk_tree* t, int k, int veldens_k, int64_t m, const int32_t* qidx, const double* x, const double* v,
+                               double* out, int flags) {
+    require_knn_tree(t);
+    require_no_halo(t, "Calc*Particle / Calc*Position");
+    NBK_REQUIRE(t->treetype == NBK_TPHYS || veldens_k == 0, NBK_ERR_UNSUPPORTED, "CalcVelDensity needs a physical tree");
+    NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
+    NBK_REQUIRE(m >= 0 && out, NBK_ERR_ARG, "Calc*Particle / Calc*Position: bad count or null output");
+    if (m == 0) return;
+    DeviceGuard guard(t->device, t->stream);
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    DevBuf<int32_t> dq;
+    DevBuf<double> dx, dv, dout;
+    KnnArgs a;
+    a.k = k; a.veldens_k = veldens_k; a.gather = true;
+    a.periodic = false;                       // quirk Q2: every Calc* search ignores the period (KDCalcSmoothQuantities.cxx:784,1108)
+    if (x) {
+        a.mode = 1; a.q0 = 0; a.q1 = m;
+        if (dev) { a.xq = x; a.vq = v; }
+        else {
+            dx.alloc((size_t)3 * m);
+            NBK_CHECK(cudaMemcpyAsync(dx.p, x, dx.bytes(), cudaMemcpyHostToDevice, t->stream));
+            a.xq = dx.p;
+            if (v) { dv.alloc((size_t)3 * m); NBK_CHECK(cudaMemcpyAsync(dv.p, v, dv.bytes(), cudaMemcpyHostToDevice, t->stream)); a.vq = dv.p; }
+        }
+    } else if (qidx) {
+        a.mode = 0; a.nq = m;
+        if (dev) a.qlist = qidx;
+        else { dq.alloc(m); NBK_CHECK(cudaMemcpyAsync(dq.p, qidx, dq.bytes(), cudaMemcpyHostToDevice, t->stream)); a.qlist = dq.p; }
+        DevBuf<int> bad(1);
+        NBK_CHECK(cudaMemsetAsync(bad.p, 0, sizeof(int), t->stream));
+        check_indices_kernel<<<div_up(m, 256), 256, 0, t->stream>>>(m, a.qlist, (int32_t)t->n, bad.p);
+        int hb = 0;
+        NBK_CHECK(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+        NBK_CHECK(cudaStreamSynchronize(t->stream));
+        NBK_REQUIRE(hb == 0, NBK_ERR_ARG, "Calc*Particle: particle index out of range");
+    } else {
+        NBK_REQUIRE(m <= t->n, NBK_ERR_ARG, "Calc*Particle: more queries than particles");
+        a.mode = 0; a.q0 = 0; a.q1 = m;       // no list: tree indices 0..m-1 (m = n: every particle, 32 neighbouring queries per warp)
+    }
+    if (dev) a.rho = out;
+    else { dout.alloc(m); a.rho = dout.p; }
+    CallTimer tm(*t);
+    launch_knn(*t, a);
+    tm.stop();
+    t->last_kernel_ms = t->last_call_ms;
+    if (!dev) NBK_CHECK(cudaMemcpyAsync(out, dout.p, sizeof(double) * m, cudaMemcpyDeviceToHost, t->stream));
+    NBK_CHECK(cudaStreamSynchronize(t->stream));
+}
+
+int nbk_calc_density_particles(nbk_tree* t, int nsmooth, int64_t m, const int32_t* qidx, double* rho, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t, NBK_ERR_ARG, "nbk_calc_density_particles: null tree");
+    smooth_gather_call(t, nsmooth, 0, m, qidx, nullptr, nullptr, rho, flags);
+    NBK_API_END
+}
+int nbk_calc_veldensity_particles(nbk_tree* t, int nsmooth, int nsearch, int64_t m, const int32_t* qidx, double* rho, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t, NBK_ERR_ARG, "nbk_calc_veldensity_particles: null tree");
+    if (nsmooth > nsearch) nsmooth = nsearch;   // KDCalcSmoothQuantities.cxx:855-858
+    NBK_REQUIRE(nsmooth >= 1, NBK_ERR_ARG, "nbk_calc_veldensity_particles: Nsmooth must be >= 1");
+    smooth_gather_call(t, nsearch, nsmooth, m, qidx, nullptr, nullptr, rho, flags);
+    NBK_API_END
+}
+int nbk_calc_density_points(nbk_tree* t, int nsmooth, int64_t m, const double* x, double* rho, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && (x || m == 0), NBK_ERR_ARG, "nbk_calc_density_points: null argument");
+    smooth_gather_call(t, nsmooth, 0, m, nullptr, x, nullptr, rho, flags);
+    NBK_API_END
+}
+int nbk_calc_veldensity_points(nbk_tree* t, int nsmooth, int nsearch, int64_t m, const double* x, const double* v, double* rho, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && ((x && v) || m == 0), NBK_ERR_ARG, "nbk_calc_veldensity_points: null argument");
+    if (nsmooth > nsearch) nsmooth = nsearch;   // KDCalcSmoothQuantities.cxx:1160-1163
+    NBK_REQUIRE(nsmooth >= 1, NBK_ERR_ARG, "nbk_calc_veldensity_points: Nsmooth must be >= 1");
+    smooth_gather_call(t, nsearch, nsmooth, m, nullptr, x, v, rho, flags);
     NBK_API_END
 }
 

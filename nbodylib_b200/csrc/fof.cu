@@ -66,32 +66,9 @@ struct FofVisitor {
     __device__ __forceinline__ bool need(float lb) const { return lb < prune_f; }
 
     __device__ __forceinline__ bool linked(int j) const {
-        const double cx = tile[j], cy = tile[32 + j], cz = tile[64 + j];
-        if (mode == 0) return dist2_ref(qx, qy, qz, cx, cy, cz) < p0;
-        const double ux = tile[96 + j], uy = tile[128 + j], uz = tile[160 + j];
-        if (mode == 1) {
-            // KDLeafNode.cxx:570-572: dist2 = DistanceSqd(pos); dist2 += DistanceSqd(vel)
-            double d = dist2_ref(qx, qy, qz, cx, cy, cz);
-            d = __dadd_rn(d, dist2_ref(vx, vy, vz, ux, uy, uz));
-            return d < p0;
-        }
-        double dx = __dsub_rn(qx, cx), dy = __dsub_rn(qy, cy), dz = __dsub_rn(qz, cz);
-        if (mode == 2) {
-            // FOF3d, FOFFunc.h:30-35: total += dx*dx/params[6]
-            double t = __ddiv_rn(__dmul_rn(dx, dx), p0);
-            t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dy, dy), p0));
-            t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dz, dz), p0));
-            return t < 1.0;
-        }
-        // FOF6d, FOFFunc.h:48-55: position and velocity terms interleaved per component
-        double wx = __dsub_rn(vx, ux), wy = __dsub_rn(vy, uy), wz = __dsub_rn(vz, uz);
-        double t = __ddiv_rn(__dmul_rn(dx, dx), p0);
-        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wx, wx), p1));
-        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dy, dy), p0));
-        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wy, wy), p1));
-        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dz, dz), p0));
-        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wz, wz), p1));
-        return t < 1.0;
+        const bool wv = crit_needs_vel(mode);
+        return crit_linked(mode, p0, p1, qx, qy, qz, vx, vy, vz, tile[j], tile[32 + j], tile[64 + j],
+                           wv ? tile[96 + j] : 0.0, wv ? tile[128 + j] : 0.0, wv ? tile[160 + j] : 0.0);
     }
 
     __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {

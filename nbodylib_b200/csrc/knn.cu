@@ -60,6 +60,11 @@ struct KnnParams {
     const double* kern; int kernres;
     int* flag_count; int32_t* flag_list;              // fast kernel: queries that need the exact kernel
     const uint8_t* active;                            // optional query mask (tree order)
+    int gather;                                       // *Particle / *Position forms: gather-only sum, result per ROW in rho
+    const double* vq;                                 // point forms that need a query velocity (velocity density, FOF6d filter), m x 3
+    // filtered search (FindNearestCheck / FindNearestCriterion): candidates must have cand_excl[c] == 0 and / or meet the
+    // criterion crit_mode (0: none, 2: FOF3d, 4: FOF6d; crit_linked in traverse.cuh) relative to the query
+    const int32_t* cand_excl; int crit_mode; double cp0, cp1;
 };
 
 // ================================================================================================ exact
@@ -103,12 +108,15 @@ struct WarpHeap {
     }
 };
 
-template <class S>
+template <class S, bool FILTER = false>
 struct KnnVisitor {
     const Vec4<S>* P;
-    double* tile;       // [3][32]
+    const Vec4<S>* V;   // FILTER with a 6D criterion only
+    double* tile;       // [6][32]
     WarpHeap hp;
     double qx, qy, qz;
+    double vx, vy, vz;  // query velocity (FILTER, FOF6d)
+    const int32_t* excl; int crit_mode; double cp0, cp1;
     double top;         // heap top (current k-th distance^2)
     float topf;         // top rounded up
     int self;           // tree index of the query particle, or -1 (coordinate form)
@@ -126,6 +134,10 @@ struct KnnVisitor {
             if ((int)lane < m) {
                 Vec4<S> c = P[start + base + lane];
                 tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
+                if (FILTER && crit_mode == 4) {
+                    Vec4<S> u = V[start + base + lane];
+                    tile[96 + lane] = (double)u.x; tile[128 + lane] = (double)u.y; tile[160 + lane] = (double)u.z;
+                }
             }
             __syncwarp();
             unsigned acc = 0;
@@ -134,6 +146,16 @@ struct KnnVisitor {
                 double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
                 bool ok = on && d2 < top;
                 if (target_form) ok = ok && (start + base + j != self) && d2 > 0.0;
+                if (FILTER) {
+                    // KDLeafNode.cxx:88-118,202-246: i != target, 0 < d2 < top, check(bucket[i]) == 0 / cmp(target, bucket[i]) == 1
+                    ok = ok && (start + base + j != self) && d2 > 0.0;
+                    if (ok && excl) ok = excl[start + base + j] == 0;
+                    if (ok && crit_mode) {
+                        const bool wv = crit_mode == 4;
+                        ok = crit_linked(crit_mode, cp0, cp1, qx, qy, qz, vx, vy, vz, tile[j], tile[32 + j], tile[64 + j],
+                                         wv ? tile[96 + j] : 0.0, wv ? tile[128 + j] : 0.0, wv ? tile[160 + j] : 0.0);
+                    }
+                }
                 acc |= (ok ? 1u : 0u) << j;
             }
             while (__any_sync(0xffffffffu, acc != 0)) {
@@ -148,17 +170,20 @@ struct KnnVisitor {
     }
 };
 
-template <class S>
+constexpr int EXACT_TILE_DOUBLES = 192;   // [6][32]: positions, and velocities for the FOF6d-filtered search
+static __host__ __device__ inline size_t exact_warp_bytes(int kcap) { return (size_t)kcap * 32 * 12 + EXACT_TILE_DOUBLES * 8 + TRAV_STACK * 4; }
+
+template <class S, bool FILTER>
 __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    const size_t warp_bytes = (size_t)prm.kcap * 32 * 12 + 96 * 8 + TRAV_STACK * 4;
+    const size_t warp_bytes = exact_warp_bytes(prm.kcap);
     unsigned char* base = smem_raw + w * warp_bytes;
     WarpHeap hp;
     hp.H = reinterpret_cast<double*>(base);
     hp.I = reinterpret_cast<int*>(base + (size_t)prm.kcap * 32 * 8);
     double* tile = reinterpret_cast<double*>(base + (size_t)prm.kcap * 32 * 12);
-    int* stack = reinterpret_cast<int*>(base + (size_t)prm.kcap * 32 * 12 + 96 * 8);
+    int* stack = reinterpret_cast<int*>(base + (size_t)prm.kcap * 32 * 12 + EXACT_TILE_DOUBLES * 8);
     hp.k = prm.kcap; hp.lane = lane;
 
     const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
@@ -172,8 +197,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
     const int64_t qi = valid ? (prm.qlist ? (int64_t)prm.qlist[row] : prm.q0 + row) : 0;
     if (valid && prm.active && prm.mode == 0 && !prm.qlist && !prm.active[qi]) valid = false;
 
-    KnnVisitor<S> v;
-    v.P = P; v.tile = tile; v.hp = hp; v.lane = lane;
+    KnnVisitor<S, FILTER> v;
+    v.P = P; v.V = reinterpret_cast<const Vec4<S>*>(prm.V); v.tile = tile; v.hp = hp; v.lane = lane;
+    v.excl = prm.cand_excl; v.crit_mode = prm.crit_mode; v.cp0 = prm.cp0; v.cp1 = prm.cp1;
+    v.vx = v.vy = v.vz = 0;
     v.on = valid;
     v.self = -1; v.target_form = false;
     double x0 = 0, y0 = 0, z0 = 0;
@@ -183,8 +210,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
             x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z;
             v.self = (int)qi;
             v.target_form = !prm.periodic;      // periodic particle searches use the coordinate form (KDSplitNode.cxx:1075-1080)
+            if (FILTER && prm.crit_mode == 4) { Vec4<S> u = v.V[qi]; v.vx = (double)u.x; v.vy = (double)u.y; v.vz = (double)u.z; }
         } else {
             x0 = prm.xq[3 * qi]; y0 = prm.xq[3 * qi + 1]; z0 = prm.xq[3 * qi + 2];
+            if (FILTER && prm.crit_mode == 4) { v.vx = prm.vq[3 * qi]; v.vy = prm.vq[3 * qi + 1]; v.vz = prm.vq[3 * qi + 2]; }
         }
     }
     v.qx = x0; v.qy = y0; v.qz = z0;
@@ -233,8 +262,28 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
 
     // ------------------------------------------------------------------------------------ epilogues
     const int kc = prm.kcap;
-    if (prm.hsm) prm.hsm[qi] = 0.5 * sqrt(v.top);
-    if (prm.rho && prm.veldens_k == 0) {
+    if (prm.hsm) prm.hsm[prm.gather ? row : qi] = 0.5 * sqrt(v.top);
+    bool sorted = false;
+    if (prm.rho && prm.veldens_k == 0 && prm.gather) {
+        // CalcDensityParticle / CalcDensityPosition (KDCalcSmoothQuantities.cxx:768-844, 1092-1148): gather only, weight
+        // 1.0 * W, no scatter.  The reference pops its heap, i.e. sums from the farthest neighbour inwards: same order here.
+        const double hi = 0.5 * sqrt(v.top);
+        const double norm = 1.0 / pow(hi, 3.0);
+        const double delta = 2.0 / (double)(prm.kernres - 1);
+        v.hp.sort_ascending(kc);
+        sorted = true;
+        double acc = 0;
+        for (int s = kc - 1; s >= 0; s--) {
+            int id = v.hp.i(s);
+            if (id < 0) continue;
+            double rij = sqrt(v.hp.h(s));
+            double r = rij / hi;
+            double Wij = wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+            acc += Wij * prm.mass[id];
+        }
+        prm.rho[row] = acc;
+    }
+    if (prm.rho && prm.veldens_k == 0 && !prm.gather) {
         // R1: CalcDensity (KDCalcSmoothQuantities.cxx:260-300), symmetric gather + scatter
         const double hi = 0.5 * sqrt(v.top);
         const double norm = 1.0 / pow(hi, 3.0);
@@ -253,15 +302,18 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
         atomicAdd(&prm.rho[qi], acc);
     }
     if (prm.rho && prm.veldens_k > 0) {
-        // R2: CalcVelDensity (KDCalcSmoothQuantities.cxx:335-383)
+        // R2: CalcVelDensity (KDCalcSmoothQuantities.cxx:335-383); the *Particle / *Position forms (:845-921, :1150-1207)
+        // compute the same number for one target (gather: result per row; point form: query velocity from vq)
         const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
-        Vec4<S> vi = V[qi];
+        double vix, viy, viz;
+        if (prm.mode == 1) { vix = prm.vq[3 * qi]; viy = prm.vq[3 * qi + 1]; viz = prm.vq[3 * qi + 2]; }
+        else { Vec4<S> vi = V[qi]; vix = (double)vi.x; viy = (double)vi.y; viz = (double)vi.z; }
         int kx = 0;
         for (int s = 0; s < kc; s++) {
             int id = v.hp.i(s);
             if (id < 0) continue;
             Vec4<S> vj = V[id];
-            double vd = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
+            double vd = sqrt(dist2_ref(vix, viy, viz, (double)vj.x, (double)vj.y, (double)vj.z));
             v.hp.h(kx) = vd; v.hp.i(kx) = id; kx++;
         }
         int kv = min(prm.veldens_k, kx);
@@ -284,10 +336,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
                 v.hp.sift_down(0, e - 1, dl, il);
             }
         }
-        prm.rho[qi] = rho;
+        prm.rho[prm.gather ? row : qi] = rho;
     }
     if (prm.nn || prm.d2out) {
-        v.hp.sort_ascending(kc);
+        if (!sorted) v.hp.sort_ascending(kc);
         // periodic particle searches carry k+1 slots: FindNearestPos(tt) drops the farthest, FindNearest(tt) the nearest (Q3)
         const int off = (prm.kcap > prm.k && prm.tree_form) ? 1 : 0;
         const int64_t orow = row * (int64_t)prm.k;
@@ -1137,7 +1189,9 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.P = t.prim; p.V = t.vel4(); p.mass = t.mass; p.order = t.order;
     p.n = t.n;
     p.q0 = a.q0; p.q1 = a.q1; p.xq = a.xq; p.mode = a.mode;
-    p.qlist = nullptr; p.nq = 0;
+    p.qlist = a.qlist; p.nq = a.nq;
+    p.gather = a.gather ? 1 : 0; p.vq = a.vq;
+    p.cand_excl = a.cand_excl; p.crit_mode = a.crit_mode; p.cp0 = a.cp0; p.cp1 = a.cp1;
     p.k = a.k;
     p.periodic = a.periodic; p.strict = a.strict; p.tree_form = a.tree_form;
     for (int d = 0; d < 3; d++) p.period[d] = t.period[d];
@@ -1149,17 +1203,16 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
 }
 
 static void run_exact(nbk_tree& t, KnnParams& p, int64_t rows) {
-    size_t warp_bytes = (size_t)p.kcap * 32 * 12 + 96 * 8 + TRAV_STACK * 4;
-    size_t smem = warp_bytes * KNN_WARPS;
+    size_t smem = exact_warp_bytes(p.kcap) * KNN_WARPS;
     NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps (max ~145 at 4 warps/CTA)");
     int blocks = p.qlist ? div_up(rows, KNN_WARPS) : div_up((rows + 31) / 32, KNN_WARPS);
-    if (t.store_bytes == 4) {
-        NBK_CHECK(cudaFuncSetAttribute(knn_exact_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_exact_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
-    } else {
-        NBK_CHECK(cudaFuncSetAttribute(knn_exact_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_exact_kernel<double><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
-    }
+    const bool filter = p.cand_excl != nullptr || p.crit_mode != 0;
+    auto go = [&](auto kern) {
+        NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
+    };
+    if (t.store_bytes == 4) { if (filter) go(knn_exact_kernel<float, true>); else go(knn_exact_kernel<float, false>); }
+    else { if (filter) go(knn_exact_kernel<double, true>); else go(knn_exact_kernel<double, false>); }
     NBK_CHECK(cudaGetLastError());
 }
 
@@ -1168,11 +1221,14 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     KnnParams p;
     fill_common(p, t, a);
     if (a.veldens_k > 0) NBK_REQUIRE(p.V != nullptr, NBK_ERR_ARG, "velocity density needs velocities");
-    const int64_t rows = a.q1 - a.q0;
+    if (a.qlist) NBK_REQUIRE(a.mode == 0, NBK_ERR_ARG, "explicit query lists hold particle indices");
+    if (a.veldens_k > 0 && a.mode == 1) NBK_REQUIRE(a.vq != nullptr && a.gather, NBK_ERR_ARG, "point form of the velocity density needs query velocities");
+    const int64_t rows = a.qlist ? a.nq : a.q1 - a.q0;
     if (rows <= 0) return;
     t.last_launches = 0;
     t.last_flagged = 0;
-    const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm);
+    if (a.crit_mode == 4) NBK_REQUIRE(p.V != nullptr && (a.mode == 0 || a.vq != nullptr), NBK_ERR_ARG, "FOF6d-filtered search needs velocities");
+    const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm) && !a.gather && !a.qlist && !a.cand_excl && !a.crit_mode;
     if (smooth_only && getenv("NBK_KNN_EXACT_ONLY") == nullptr) {
         // ---- fast path + exact fallback for the flagged queries ----------------------------------------------
         p.kcap = a.k + 1;
@@ -1339,6 +1395,8 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
         return;
     }
     p.kcap = a.k + ((a.periodic && a.mode == 0) ? 1 : 0);
+    // the reference's periodic FindNearestCheck / FindNearestCriterion search k+1 and drop the nearest in every form
+    if ((a.cand_excl || a.crit_mode) && a.periodic && a.tree_form) p.kcap = a.k + 1;
     run_exact(t, p, rows);
     t.last_launches += 1;
 }

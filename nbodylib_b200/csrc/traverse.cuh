@@ -39,6 +39,39 @@ __device__ __forceinline__ double dist2_ref(double ax, double ay, double az, dou
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+// Link / search predicates shared by FOF, FOFCriterion, SearchBall* and SearchCriterion* (strict '<', fp64, the
+// reference's operation order):
+//   mode 0  3D ball            DistanceSqd(pos) < p0                               DistFunc.h:14-19
+//   mode 1  6D ball (TPHS)     DistanceSqd(pos) + DistanceSqd(vel) < p0            KDLeafNode.cxx:570-572
+//   mode 2  FOF3d              sum dx*dx/p0 < 1                                    FOFFunc.h:30-35
+//   mode 4  FOF6d              sum (dx*dx/p0 + dv*dv/p1), interleaved, < 1         FOFFunc.h:48-55
+// (mode 3, FOFVel, is not implemented: see DESIGN.md)
+__device__ __forceinline__ bool crit_needs_vel(int mode) { return mode == 1 || mode == 4; }
+__device__ __forceinline__ bool crit_linked(int mode, double p0, double p1, double qx, double qy, double qz, double vx, double vy, double vz,
+                                            double cx, double cy, double cz, double ux, double uy, double uz) {
+    if (mode == 0) return dist2_ref(qx, qy, qz, cx, cy, cz) < p0;
+    if (mode == 1) {
+        double d = dist2_ref(qx, qy, qz, cx, cy, cz);
+        d = __dadd_rn(d, dist2_ref(vx, vy, vz, ux, uy, uz));
+        return d < p0;
+    }
+    double dx = __dsub_rn(qx, cx), dy = __dsub_rn(qy, cy), dz = __dsub_rn(qz, cz);
+    if (mode == 2) {
+        double t = __ddiv_rn(__dmul_rn(dx, dx), p0);
+        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dy, dy), p0));
+        t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dz, dz), p0));
+        return t < 1.0;
+    }
+    double wx = __dsub_rn(vx, ux), wy = __dsub_rn(vy, uy), wz = __dsub_rn(vz, uz);
+    double t = __ddiv_rn(__dmul_rn(dx, dx), p0);
+    t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wx, wx), p1));
+    t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dy, dy), p0));
+    t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wy, wy), p1));
+    t = __dadd_rn(t, __ddiv_rn(__dmul_rn(dz, dz), p0));
+    t = __dadd_rn(t, __ddiv_rn(__dmul_rn(wz, wz), p1));
+    return t < 1.0;
+}
+
 struct QueryBox { float lx, ly, lz, hx, hy, hz; };
 __device__ __forceinline__ QueryBox make_qbox(double x, double y, double z) {
     QueryBox q;

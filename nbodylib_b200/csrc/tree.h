@@ -80,6 +80,15 @@ struct KnnArgs {
     double* hsm = nullptr;     // smoothing scale, tree order
     const uint8_t* active = nullptr;  // device, tree order, optional: only these particles are queries
     int veldens_k = 0;         // >0: CalcVelDensity with Nsmooth=veldens_k, Nsearch=k; rho gets the value (no atomics)
+    // *Particle / *Position forms (KDCalcSmoothQuantities.cxx:768-921, 1092-1207): gather-only sums, one value per query ROW
+    bool gather = false;       // rho (and hsm) are indexed by row, weight 1.0 * W, no scatter
+    const int32_t* qlist = nullptr;  // device, explicit tree indices (mode 0) instead of the range [q0,q1)
+    int64_t nq = 0;
+    const double* vq = nullptr;      // device, m x 3 query velocities (mode 1 velocity density / FOF6d filter)
+    // FindNearestCheck / FindNearestCriterion (KDFindNearest.cxx:363-441): candidate filters of the exact kernel
+    const int32_t* cand_excl = nullptr;  // device, tree order: non-zero => never a neighbour
+    int crit_mode = 0;                   // 0 none, 2 FOF3d, 4 FOF6d (predicate codes of FofArgs::mode)
+    double cp0 = 0, cp1 = 0;
 };
 void launch_knn(nbk_tree& t, const KnnArgs& a);
 
@@ -105,8 +114,13 @@ struct BallArgs {
     const double* xq = nullptr;     // device, point form
     int64_t* offsets = nullptr;     // device m+1
     int32_t* idx = nullptr;         // device cap
+    double* d2 = nullptr;           // device cap, optional: position distance^2 of every entry (dense forms)
     int64_t cap = 0, total = 0;
     bool out_ids = false;
+    // criterion search (SearchCriterion*): predicate codes of FofArgs::mode (2: FOF3d, 4: FOF6d); mode 0 = ball of radius^2 r2
+    int mode = 0;
+    double p0 = 0, p1 = 0, prune_x2 = 0;
+    const double* vq = nullptr;     // device, point form with velocities (SearchCriterionTagged(Particle&))
 };
 void launch_ball(nbk_tree& t, BallArgs& a);
 

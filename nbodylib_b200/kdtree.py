@@ -157,6 +157,23 @@ class KDTree:
         L.check(self._lib.nbk_get_nodes(self._h, C.byref(ns), _ptr(s), _ptr(e), _ptr(c), _ptr(b)))
         return s, e, c, b
 
+    def FindLeafNode(self, q):
+        """KDTree::FindLeafNode(Int_t tt) / FindLeafNode(Double_t *x) (KDFindNearest.cxx:709-736) on the host mirror of the
+        node arrays: returns (slot, start, end) of the leaf holding tree index q, or the one a position descends into
+        (left while x[cut] < the left child's upper boundary)."""
+        if getattr(self, "_nodes", None) is None:
+            self._nodes = self.nodes()
+        s, e, c, b = self._nodes
+        slot = 0
+        while c[slot] >= 0:
+            left = 2 * slot + 1
+            if np.ndim(q) == 0:
+                slot = left if q < e[left] else left + 1
+            else:
+                k = c[slot]
+                slot = left if q[k] < b[left, 2 * k + 1] else left + 1
+        return slot, int(s[slot]), int(e[slot])
+
     # ---- nearest neighbours -------------------------------------------------------------------
     def FindNearestPos(self, Nsearch=64, q0=0, q1=None, ids=False, tree_form=False, strict=False, out=None):
         """Whole-system / range form of FindNearestPos(Int_t tt, ...) (KDFindNearest.cxx:320-334,444-459).
@@ -187,25 +204,102 @@ class KDTree:
         L.check(self._lib.nbk_knn_points(self._h, int(Nsearch), m, _ptr(x), _ptr(nn), _ptr(d2), flags))
         return nn, d2
 
+    def _knn_filtered(self, Nsearch, cmp, params, check, q0, q1, x, v, ids, tree_form):
+        flags = (L.OUT_IDS if ids else 0) | (L.KNN_TREE_FORM if tree_form else 0)
+        pr = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        chk = None if check is None else np.ascontiguousarray(check, dtype=np.int32)
+        if chk is not None:
+            assert chk.shape == (self.n,)
+        crit = -1 if cmp is None else int(cmp)
+        if x is not None:
+            x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+            v = None if v is None else np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
+            rows = len(x)
+        else:
+            q1 = self.n if q1 is None else q1
+            rows = q1 - q0
+        nn = np.empty((rows, Nsearch), dtype=np.int32)
+        d2 = np.empty((rows, Nsearch), dtype=np.float64)
+        if x is not None:
+            L.check(self._lib.nbk_knn_filtered_points(self._h, int(Nsearch), rows, _ptr(x), _ptr(v), crit, _ptr(pr), _ptr(chk), _ptr(nn), _ptr(d2), flags))
+        else:
+            L.check(self._lib.nbk_knn_filtered_particles(self._h, int(Nsearch), int(q0), int(q1), crit, _ptr(pr), _ptr(chk), _ptr(nn), _ptr(d2), flags))
+        return nn, d2
+
+    def FindNearestCheck(self, check, Nsearch=64, q0=0, q1=None, x=None, ids=False, tree_form=None):
+        """Range / batched form of KDTree::FindNearestCheck(Int_t tt | Coordinate x, check, params, nn, dist2, Nsearch)
+        (KDFindNearest.cxx:396-441): the Nsearch nearest among the particles whose check value (array by ID, the caller's
+        FOFcheckfunc evaluated per particle) is 0.  tree_form (default: on for periodic trees) reproduces the reference's
+        periodic forms, which search Nsearch+1 and drop the nearest."""
+        tree_form = (self.period is not None) if tree_form is None else tree_form
+        return self._knn_filtered(Nsearch, None, None, check, q0, q1, x, None, ids, tree_form)
+
+    def FindNearestCriterion(self, cmp, params, Nsearch=64, q0=0, q1=None, x=None, v=None, ids=False, tree_form=None):
+        """Range / batched form of KDTree::FindNearestCriterion(Int_t tt | Particle p, cmp, params, nn, dist2, Nsearch)
+        (KDFindNearest.cxx:363-394) for cmp in {FOF3D, FOF6D}: the Nsearch nearest among the particles meeting the
+        criterion relative to the target; rows are padded with (-1, 1e32) when fewer qualify."""
+        tree_form = (self.period is not None) if tree_form is None else tree_form
+        return self._knn_filtered(Nsearch, cmp, params, None, q0, q1, x, v, ids, tree_form)
+
     # ---- fixed radius -------------------------------------------------------------------------
-    def _ball(self, fn, q, fdist2, ids):
-        m = len(q)
+    def _csr(self, call, m, ids, want_d2):
+        """two-pass CSR protocol of nbk_ball_* / nbk_search_criterion_*: count, allocate, fill"""
         off = np.empty(m + 1, dtype=np.int64)
         tot = C.c_int64()
         flags = L.OUT_IDS if ids else 0
-        L.check(fn(self._h, float(fdist2), m, _ptr(q), _ptr(off), None, 0, C.byref(tot), flags))
+        L.check(call(_ptr(off), None, None, 0, C.byref(tot), flags))
         idx = np.empty(max(tot.value, 1), dtype=np.int32)
-        L.check(fn(self._h, float(fdist2), m, _ptr(q), _ptr(off), _ptr(idx), len(idx), C.byref(tot), flags))
+        d2 = np.empty(max(tot.value, 1), dtype=np.float64) if want_d2 else None
+        L.check(call(_ptr(off), _ptr(idx), _ptr(d2), len(idx), C.byref(tot), flags))
+        if want_d2:
+            return off, idx[:tot.value], d2[:tot.value]
         return off, idx[:tot.value]
 
-    def SearchBallPosTagged(self, tt, fdist2, ids=False):
+    def SearchBallPosTagged(self, tt, fdist2, ids=False, want_d2=False):
         """Batched SearchBallPosTagged(Int_t tt, fdist2, tagged) (KDFindNearest.cxx:618-626); tt = tree indices.
-        Returns CSR (offsets, tagged)."""
-        return self._ball(self._lib.nbk_ball_particles, np.ascontiguousarray(tt, dtype=np.int32), fdist2, ids)
+        Returns CSR (offsets, tagged[, dist2])."""
+        q = np.ascontiguousarray(tt, dtype=np.int32)
+        return self._csr(lambda *a: self._lib.nbk_ball_particles(self._h, float(fdist2), len(q), _ptr(q), *a), len(q), ids, want_d2)
 
-    def SearchBallPosTaggedPoints(self, x, fdist2, ids=False):
+    def SearchBallPosTaggedPoints(self, x, fdist2, ids=False, want_d2=False):
         """Batched SearchBallPosTagged(Double_t *x, fdist2, tagged) (KDFindNearest.cxx:628-636)."""
-        return self._ball(self._lib.nbk_ball_points, np.ascontiguousarray(x, dtype=np.float64), fdist2, ids)
+        q = np.ascontiguousarray(x, dtype=np.float64)
+        return self._csr(lambda *a: self._lib.nbk_ball_points(self._h, float(fdist2), len(q), _ptr(q), *a), len(q), ids, want_d2)
+
+    def SearchBallPos(self, tt, fdist2, imark, nn, dist2):
+        """Dense KDTree::SearchBallPos(Int_t tt | Double_t *x, fdist2, imark, nn, dist2) (KDFindNearest.cxx:567-587): marks
+        nn[ID] = imark and dist2[ID] = d2 for every particle within the ball; nn / dist2 are the caller's N-entry arrays
+        (indexed by ID) and are updated in place.  tt: a tree index, or a position (3 floats)."""
+        if np.ndim(tt) == 0:
+            off, idx, d2 = self.SearchBallPosTagged([int(tt)], fdist2, ids=True, want_d2=True)
+        else:
+            off, idx, d2 = self.SearchBallPosTaggedPoints(np.asarray(tt, dtype=np.float64).reshape(1, 3), fdist2, ids=True, want_d2=True)
+        nn[idx] = imark
+        dist2[idx] = d2
+        return len(idx)
+
+    def SearchCriterionTagged(self, tt, cmp, params, ids=False, want_d2=False):
+        """Batched KDTree::SearchCriterionTagged(Int_t tt, cmp, params, tagged) (KDFindNearest.cxx:660-668) for cmp in
+        {FOF3D, FOF6D}; tt = tree indices.  Returns CSR (offsets, tagged[, dist2])."""
+        q = np.ascontiguousarray(tt, dtype=np.int32)
+        pr = np.ascontiguousarray(params, dtype=np.float64)
+        return self._csr(lambda *a: self._lib.nbk_search_criterion_particles(self._h, int(cmp), _ptr(pr), len(q), _ptr(q), *a), len(q), ids, want_d2)
+
+    def SearchCriterionTaggedPoints(self, x, v, cmp, params, ids=False, want_d2=False):
+        """Batched KDTree::SearchCriterionTagged(Particle &p, cmp, params, tagged) (KDFindNearest.cxx:669-677) for particles
+        that are not in the tree, given as positions x and velocities v (v may be None for FOF3D)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        v = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        pr = np.ascontiguousarray(params, dtype=np.float64)
+        return self._csr(lambda *a: self._lib.nbk_search_criterion_points(self._h, int(cmp), _ptr(pr), len(x), _ptr(x), _ptr(v), *a), len(x), ids, want_d2)
+
+    def SearchCriterion(self, tt, cmp, params, imark, nn, dist2=None):
+        """Dense KDTree::SearchCriterion(Int_t tt, cmp, params, imark, nn[, dist2]) (KDFindNearest.cxx:590-603)."""
+        off, idx, d2 = self.SearchCriterionTagged([int(tt)], cmp, params, ids=True, want_d2=True)
+        nn[idx] = imark
+        if dist2 is not None:
+            dist2[idx] = d2
+        return len(idx)
 
     # ---- smoothed estimators ------------------------------------------------------------------
     def CalcDensity(self, Nsmooth=64, want_h=False, out=None):
@@ -242,6 +336,63 @@ class KDTree:
         rho = np.empty(self.n)
         L.check(self._lib.nbk_calc_veldensity(self._h, int(Nsmooth), int(Nsearch), _ptr(rho), 0))
         return rho
+
+    def CalcDensityParticle(self, target, Nsmooth=64):
+        """KDTree::CalcDensityParticle(target, Nsmooth) (KDCalcSmoothQuantities.cxx:768-844) for a batch of tree indices
+        (None: every particle, in tree order): gather-only density, one value per query."""
+        if target is None:
+            q, m = None, self.n
+        else:
+            q = np.ascontiguousarray(np.atleast_1d(target), dtype=np.int32)
+            m = len(q)
+        out = np.empty(m)
+        L.check(self._lib.nbk_calc_density_particles(self._h, int(Nsmooth), m, _ptr(q), _ptr(out), 0))
+        return out if target is None or np.ndim(target) else float(out[0])
+
+    def CalcVelDensityParticle(self, target, Nsmooth=64, Nsearch=64):
+        """KDTree::CalcVelDensityParticle(target, Nsmooth, Nsearch) (KDCalcSmoothQuantities.cxx:845-921), batched."""
+        if target is None:
+            q, m = None, self.n
+        else:
+            q = np.ascontiguousarray(np.atleast_1d(target), dtype=np.int32)
+            m = len(q)
+        out = np.empty(m)
+        L.check(self._lib.nbk_calc_veldensity_particles(self._h, int(Nsmooth), int(Nsearch), m, _ptr(q), _ptr(out), 0))
+        return out if target is None or np.ndim(target) else float(out[0])
+
+    def CalcDensityPosition(self, x, Nsmooth=64):
+        """KDTree::CalcDensityPosition(Double_t *x, Nsmooth) (KDCalcSmoothQuantities.cxx:1092-1148), batched: x is (m, 3)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(x))
+        L.check(self._lib.nbk_calc_density_points(self._h, int(Nsmooth), len(x), _ptr(x), _ptr(out), 0))
+        return out
+
+    def CalcVelDensityPosition(self, x, v, Nsmooth=64, Nsearch=64):
+        """KDTree::CalcVelDensityPosition(Double_t *x, Double_t *v, Nsmooth, Nsearch) (KDCalcSmoothQuantities.cxx:1150-1207)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
+        assert x.shape == v.shape
+        out = np.empty(len(x))
+        L.check(self._lib.nbk_calc_veldensity_points(self._h, int(Nsmooth), int(Nsearch), len(x), _ptr(x), _ptr(v), _ptr(out), 0))
+        return out
+
+    def CalcSmoothLocalValue(self, Nsmooth, dist, weight):
+        """KDTree::CalcSmoothLocalValue(Nsmooth, Double_t *dist, Double_t *weight) (KDCalcSmoothQuantities.cxx:1721-1735):
+        kernel-weighted sum over a caller-supplied list of Nsmooth distances (descending, dist[0] the largest) and
+        weights.  Host data in, one number out: evaluated here with the tree's kernel table (nbk_get_kernel_table), the
+        same few lines the C++ shim carries."""
+        info = self.info
+        kern, kernres, nd = self.kernel_table(), info.kernres, info.nd
+        hi = 0.5 * dist[0]
+        norm = 1.0 / hi ** float(nd)
+        delta = 2.0 / (kernres - 1)
+        value = 0.0
+        for j in range(Nsmooth):
+            r = dist[j] / hi
+            i = int(r * 0.5 * (kernres - 1))
+            w = kern[i] + (kern[i + 1] - kern[i]) * (r - delta * i) / delta if i < kernres - 1 else kern[i]
+            value += w * norm * weight[j]
+        return value
 
     def CalcSmoothingScale(self, Nsmooth=64):
         """hi = 0.5*sqrt(d2 of the Nsmooth-th neighbour) (KDCalcSmoothQuantities.cxx:260)."""

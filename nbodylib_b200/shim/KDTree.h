@@ -6,8 +6,11 @@
  *    ctor (Particle*, numparts, bucket_size, TreeType, KernType, KernRes, SplittingCriterion, Aniso, ScaleSpace, Period)
  *    GetNumNodes / GetNumLeafNodes / GetBucketSize / GetTreeType / GetKernType / GetKernNorm / GetPeriod
  *    FindNearest / FindNearestPos (Int_t tt | Double_t* x | Coordinate | whole system)
- *    SearchBallPosTagged (Int_t tt | Double_t* x | Coordinate; array and vector forms)
- *    CalcDensity, CalcVelDensity, CalcSmoothingScale (new: north star), FOF, FOFCriterion (FOF3d / FOF6d)
+ *    SearchBallPosTagged (Int_t tt | Double_t* x | Coordinate; array and vector forms), dense SearchBall / SearchBallPos
+ *    SearchCriterionTagged (Int_t tt | Particle&; array and vector forms), dense SearchCriterion (FOF3d / FOF6d)
+ *    CalcDensity, CalcVelDensity, CalcSmoothingScale (new: north star), CalcDensityParticle, CalcVelDensityParticle,
+ *    CalcDensityPosition, CalcVelDensityPosition, CalcSmoothLocalValue
+ *    FOF, FOFCriterion, FOFCriterionSetBasisForLinks (FOF3d / FOF6d), GetRoot / FindLeafNode (host mirror of the node arrays)
  *    OverWriteInputOrder, SetResetOrder, ~KDTree (restores the caller's particle order)
  *
  *  Semantics kept from the reference: the caller's Particle array is permuted IN PLACE into tree order and
@@ -26,6 +29,8 @@
 #include "Particle.h"
 #endif
 #include <algorithm>
+#include <cmath>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -35,6 +40,37 @@
 #include "../../include/nbk.h"
 
 namespace NBody {
+
+/// Host mirror of one tree node (reference KDNode.h:45-334 Node, :343-484 SplitNode, :492-610 LeafNode): what callers of
+/// KDTree::GetRoot() / FindLeafNode() read.  IDs number the nodes depth first, left before right, like the reference's
+/// BuildNodes.  Boundaries are the node's particle bounding box (fp32, rounded outward when the tree stores fp64
+/// coordinates); the cut value of a split node is the largest cut-dimension coordinate of its left child, i.e. the median
+/// particle's coordinate (KDTree.cxx:1012-1013).
+class Node {
+    friend class KDTree;
+protected:
+    Int_t nid = 0, bucket_start = 0, bucket_end = 0, numdim = 3;
+    Double_t xbnd[6][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    int cut_dim = -1;
+    Double_t cut_val = 0;
+    Node *left = nullptr, *right = nullptr;
+public:
+    virtual ~Node() {}
+    Int_t GetID() const { return nid; }
+    Int_t GetCount() const { return bucket_end - bucket_start; }
+    Int_t GetStart() const { return bucket_start; }
+    Int_t GetEnd() const { return bucket_end; }
+    Double_t GetBoundary(int i, int j) const { return xbnd[i][j]; }
+    bool GetLeaf() const { return left == nullptr; }
+};
+class SplitNode : public Node {
+public:
+    int GetCutDim() const { return cut_dim; }
+    Double_t GetCutValue() const { return cut_val; }
+    Node* GetLeft() const { return left; }
+    Node* GetRight() const { return right; }
+};
+class LeafNode : public Node {};
 
 class KDTree {
 public:
@@ -65,6 +101,7 @@ private:
     // calls of that thread (static / dynamic / guided chunks are runs of consecutive indices) are served from host memory.
     struct KnnBlock {
         unsigned long long serial = 0; Int_t b0 = 0, b1 = 0, k = 0; int flags = -1;
+        int crit = -2; FOFcheckfunc checkfn = nullptr; double params[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // filtered searches
         std::vector<int32_t> nn; std::vector<double> d2;
     };
     static KnnBlock& tls_block() { static thread_local KnnBlock b; return b; }
@@ -76,6 +113,55 @@ private:
         return b;
     }
     void refresh() { check(nbk_get_info(h, &info)); }
+
+    // host mirror of the node arrays, built on the first GetRoot() / FindLeafNode() call
+    std::vector<std::unique_ptr<Node>> nodes;
+    Node* root = nullptr;
+    std::vector<Double_t> kernel;   // KernelConstruction table (nbk_get_kernel_table), fetched on first use
+    Node* mirror(int64_t slot, const std::vector<int32_t>& st, const std::vector<int32_t>& en, const std::vector<int32_t>& cd,
+                 const std::vector<float>& bd, Int_t& next_id) {
+        Node* nd;
+        const bool leaf = cd[slot] < 0;
+        if (leaf) nd = new LeafNode(); else nd = new SplitNode();
+        nodes.emplace_back(nd);
+        nd->nid = next_id++;
+        nd->bucket_start = st[slot]; nd->bucket_end = en[slot];
+        for (int j = 0; j < 3; j++) { nd->xbnd[j][0] = bd[6 * slot + 2 * j]; nd->xbnd[j][1] = bd[6 * slot + 2 * j + 1]; }
+        if (!leaf) {
+            nd->cut_dim = cd[slot];
+            nd->left = mirror(2 * slot + 1, st, en, cd, bd, next_id);
+            nd->right = mirror(2 * slot + 2, st, en, cd, bd, next_id);
+            nd->cut_val = nd->left->xbnd[nd->cut_dim][1];
+        }
+        return nd;
+    }
+    void build_mirror() {
+        std::lock_guard<std::mutex> g(dev_mutex);
+        if (root) return;
+        int64_t ns = 0;
+        check(nbk_get_nodes(h, &ns, NULL, NULL, NULL, NULL));
+        std::vector<int32_t> st(ns), en(ns), cd(ns);
+        std::vector<float> bd((size_t)6 * ns);
+        check(nbk_get_nodes(h, &ns, st.data(), en.data(), cd.data(), bd.data()));
+        Int_t next_id = 0;
+        nodes.reserve((size_t)info.num_nodes);
+        root = mirror(0, st, en, cd, bd, next_id);
+    }
+    const std::vector<Double_t>& kernel_table() {
+        std::lock_guard<std::mutex> g(dev_mutex);
+        if (kernel.empty()) {
+            std::vector<double> kt(info.kernres);
+            check(nbk_get_kernel_table(h, kt.data()));
+            kernel.assign(kt.begin(), kt.end());
+        }
+        return kernel;
+    }
+    int crit_code(FOFcompfunc cmp, const char* who) {
+        // inline criteria are recognised by address inside the caller's translation unit (SURVEY.md 8b)
+        if (cmp == (FOFcompfunc)&FOF3d) return NBK_FOF3D;
+        if (cmp == (FOFcompfunc)&FOF6d) return NBK_FOF6D;
+        throw std::runtime_error(std::string("nbk shim: ") + who + " supports FOF3d and FOF6d; host callbacks cannot run on the device");
+    }
 
 public:
     KDTree(Particle* p, Int_t nparts, Int_t bucket_size = 16, int TreeType = TPHYS, int KernType = KEPAN, int KernRes = 1000,
@@ -148,7 +234,27 @@ public:
     void FindNearestPos(Int_t** nn, Double_t** dist2, Int_t Nsearch = 64) { knn_all(nn, dist2, Nsearch, 0); }
     void FindNearest(Int_t** nn, Double_t** dist2, Int_t Nsearch = 64) { knn_all(nn, dist2, Nsearch, NBK_KNN_TREE_FORM); }
 
-    // ---- fixed radius (KDFindNearest.cxx:618-688) ------------------------------------------------------------
+    // ---- filtered nearest neighbours (KDFindNearest.cxx:363-441) ------------------------------------------------
+    /// Per-particle forms are served from the per-thread block cache like FindNearest(tt).  The caller's FOFcheckfunc runs on
+    /// the host for every particle when a block is computed (its values are what the device receives); params are read when
+    /// the block is computed and compared by value afterwards.
+    void FindNearestCheck(Int_t tt, FOFcheckfunc check_, Double_t* params, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        knn_cached(tt, nn, dist2, Nsearch, period ? NBK_KNN_TREE_FORM : 0, -1, check_, params);
+    }
+    void FindNearestCriterion(Int_t tt, FOFcompfunc cmp, Double_t* params, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        knn_cached(tt, nn, dist2, Nsearch, period ? NBK_KNN_TREE_FORM : 0, crit_code(cmp, "FindNearestCriterion"), nullptr, params);
+    }
+    void FindNearestCheck(Coordinate x, FOFcheckfunc check_, Double_t* params, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        knn_filtered_point(x.GetCoord(), NULL, -1, check_, params, nn, dist2, Nsearch);
+    }
+    void FindNearestCheck(Particle p, FOFcheckfunc check_, Double_t* params, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        knn_filtered_point(p.GetPosition(), NULL, -1, check_, params, nn, dist2, Nsearch);
+    }
+    void FindNearestCriterion(Particle p, FOFcompfunc cmp, Double_t* params, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        knn_filtered_point(p.GetPosition(), p.GetVelocity(), crit_code(cmp, "FindNearestCriterion"), nullptr, params, nn, dist2, Nsearch);
+    }
+
+    // ---- fixed radius (KDFindNearest.cxx:567-688) ------------------------------------------------------------
     Int_t SearchBallPosTagged(Int_t tt, Double_t fdist2, Int_t* tagged) {
         std::vector<Int_t> v = SearchBallPosTagged(tt, fdist2);
         std::copy(v.begin(), v.end(), tagged);
@@ -162,21 +268,99 @@ public:
     Int_t SearchBallPosTagged(Coordinate x, Double_t fdist2, Int_t* tagged) { return SearchBallPosTagged(x.GetCoord(), fdist2, tagged); }
     std::vector<Int_t> SearchBallPosTagged(Int_t tt, Double_t fdist2) {
         int32_t q = (int32_t)tt;
-        int64_t off[2], tot = 0;
-        check(nbk_ball_particles(h, (double)fdist2, 1, &q, off, NULL, 0, &tot, 0));
-        std::vector<int32_t> idx((size_t)std::max<int64_t>(tot, 1));
-        check(nbk_ball_particles(h, (double)fdist2, 1, &q, off, idx.data(), (int64_t)idx.size(), &tot, 0));
-        return std::vector<Int_t>(idx.begin(), idx.begin() + tot);
+        std::vector<int32_t> idx;
+        csr_row([&](int64_t* off, int32_t* ix, double* d2, int64_t cap, int64_t* tot, int fl) {
+            return nbk_ball_particles(h, (double)fdist2, 1, &q, off, ix, d2, cap, tot, fl); }, 0, idx, NULL);
+        return std::vector<Int_t>(idx.begin(), idx.end());
     }
     std::vector<Int_t> SearchBallPosTagged(Double_t* x, Double_t fdist2) {
         double xx[3] = {(double)x[0], (double)x[1], (double)x[2]};
-        int64_t off[2], tot = 0;
-        check(nbk_ball_points(h, (double)fdist2, 1, xx, off, NULL, 0, &tot, 0));
-        std::vector<int32_t> idx((size_t)std::max<int64_t>(tot, 1));
-        check(nbk_ball_points(h, (double)fdist2, 1, xx, off, idx.data(), (int64_t)idx.size(), &tot, 0));
-        return std::vector<Int_t>(idx.begin(), idx.begin() + tot);
+        std::vector<int32_t> idx;
+        csr_row([&](int64_t* off, int32_t* ix, double* d2, int64_t cap, int64_t* tot, int fl) {
+            return nbk_ball_points(h, (double)fdist2, 1, xx, off, ix, d2, cap, tot, fl); }, 0, idx, NULL);
+        return std::vector<Int_t>(idx.begin(), idx.end());
     }
     std::vector<Int_t> SearchBallPosTagged(Coordinate x, Double_t fdist2) { return SearchBallPosTagged(x.GetCoord(), fdist2); }
+
+    /// dense forms (KDFindNearest.cxx:567-587): nn[ID] = imark, dist2[ID] = d2 for every particle inside the ball; nn and
+    /// dist2 are the caller's numparts-sized arrays, indexed by particle ID.  Non periodic target form: the target itself is
+    /// not marked (the reference marks it only when a whole node containing it is swallowed, quirk Q5).
+    void SearchBallPos(Int_t tt, Double_t fdist2, Int_t imark, Int_t* nn, Double_t* dist2) {
+        int32_t q = (int32_t)tt;
+        std::vector<int32_t> idx; std::vector<double> d2;
+        csr_row([&](int64_t* off, int32_t* ix, double* dd, int64_t cap, int64_t* tot, int fl) {
+            return nbk_ball_particles(h, (double)fdist2, 1, &q, off, ix, dd, cap, tot, fl); }, NBK_OUT_IDS, idx, &d2);
+        for (size_t j = 0; j < idx.size(); j++) { nn[idx[j]] = imark; dist2[idx[j]] = d2[j]; }
+    }
+    void SearchBallPos(Double_t* x, Double_t fdist2, Int_t imark, Int_t* nn, Double_t* dist2) {
+        double xx[3] = {(double)x[0], (double)x[1], (double)x[2]};
+        std::vector<int32_t> idx; std::vector<double> d2;
+        csr_row([&](int64_t* off, int32_t* ix, double* dd, int64_t cap, int64_t* tot, int fl) {
+            return nbk_ball_points(h, (double)fdist2, 1, xx, off, ix, dd, cap, tot, fl); }, NBK_OUT_IDS, idx, &d2);
+        for (size_t j = 0; j < idx.size(); j++) { nn[idx[j]] = imark; dist2[idx[j]] = d2[j]; }
+    }
+    void SearchBallPos(Coordinate x, Double_t fdist2, Int_t imark, Int_t* nn, Double_t* dist2) { SearchBallPos(x.GetCoord(), fdist2, imark, nn, dist2); }
+    /// SearchBall dispatches on the tree type (KDFindNearest.cxx:557-565); only position trees have a device ball search
+    void SearchBall(Int_t tt, Double_t fdist2, Int_t imark, Int_t* nn, Double_t* dist2) { require_pos_tree("SearchBall"); SearchBallPos(tt, fdist2, imark, nn, dist2); }
+    void SearchBall(Double_t* x, Double_t fdist2, Int_t imark, Int_t* nn, Double_t* dist2) { require_pos_tree("SearchBall"); SearchBallPos(x, fdist2, imark, nn, dist2); }
+    void SearchBall(Coordinate x, Double_t fdist2, Int_t imark, Int_t* nn, Double_t* dist2) { require_pos_tree("SearchBall"); SearchBallPos(x.GetCoord(), fdist2, imark, nn, dist2); }
+
+    // ---- criterion search (KDFindNearest.cxx:590-603, 660-706; FOF3d / FOF6d) ----------------------------------
+    std::vector<Int_t> SearchCriterionTagged(Int_t tt, FOFcompfunc cmp, Double_t* params) {
+        const int crit = crit_code(cmp, "SearchCriterionTagged");
+        double pr[16]; for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        int32_t q = (int32_t)tt;
+        std::vector<int32_t> idx;
+        csr_row([&](int64_t* off, int32_t* ix, double* d2, int64_t cap, int64_t* tot, int fl) {
+            return nbk_search_criterion_particles(h, crit, pr, 1, &q, off, ix, d2, cap, tot, fl); }, 0, idx, NULL);
+        return std::vector<Int_t>(idx.begin(), idx.end());
+    }
+    std::vector<Int_t> SearchCriterionTagged(Particle& p, FOFcompfunc cmp, Double_t* params) {
+        const int crit = crit_code(cmp, "SearchCriterionTagged");
+        double pr[16]; for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        double xx[3] = {(double)p.GetPosition(0), (double)p.GetPosition(1), (double)p.GetPosition(2)};
+        double vv[3] = {(double)p.GetVelocity(0), (double)p.GetVelocity(1), (double)p.GetVelocity(2)};
+        std::vector<int32_t> idx;
+        csr_row([&](int64_t* off, int32_t* ix, double* d2, int64_t cap, int64_t* tot, int fl) {
+            return nbk_search_criterion_points(h, crit, pr, 1, xx, vv, off, ix, d2, cap, tot, fl); }, 0, idx, NULL);
+        return std::vector<Int_t>(idx.begin(), idx.end());
+    }
+    Int_t SearchCriterionTagged(Int_t tt, FOFcompfunc cmp, Double_t* params, Int_t* tagged) {
+        std::vector<Int_t> v = SearchCriterionTagged(tt, cmp, params);
+        std::copy(v.begin(), v.end(), tagged);
+        return (Int_t)v.size();
+    }
+    Int_t SearchCriterionTagged(Particle& p, FOFcompfunc cmp, Double_t* params, Int_t* tagged) {
+        std::vector<Int_t> v = SearchCriterionTagged(p, cmp, params);
+        std::copy(v.begin(), v.end(), tagged);
+        return (Int_t)v.size();
+    }
+    /// dense forms: nn[ID] = imark (and dist2[ID] = position distance^2) for every particle meeting the criterion.  The
+    /// reference additionally skips particles whose nn[ID] is non-zero and <= imark (KDLeafNode.cxx:418): same here.
+    void SearchCriterion(Int_t tt, FOFcompfunc cmp, Double_t* params, Int_t imark, Int_t* nn, Double_t* dist2) {
+        const int crit = crit_code(cmp, "SearchCriterion");
+        double pr[16]; for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        int32_t q = (int32_t)tt;
+        std::vector<int32_t> idx; std::vector<double> d2;
+        csr_row([&](int64_t* off, int32_t* ix, double* dd, int64_t cap, int64_t* tot, int fl) {
+            return nbk_search_criterion_particles(h, crit, pr, 1, &q, off, ix, dd, cap, tot, fl); }, NBK_OUT_IDS, idx, &d2);
+        for (size_t j = 0; j < idx.size(); j++)
+            if (nn[idx[j]] > imark || nn[idx[j]] == 0) { nn[idx[j]] = imark; if (dist2) dist2[idx[j]] = d2[j]; }
+    }
+    void SearchCriterion(Int_t tt, FOFcompfunc cmp, Double_t* params, Int_t imark, Int_t* nn) { SearchCriterion(tt, cmp, params, imark, nn, NULL); }
+
+    // ---- node mirrors (KDTree.h:288, KDFindNearest.cxx:709-749) -------------------------------------------------
+    Node* GetRoot() { if (!root) build_mirror(); return root; }
+    Node* FindLeafNode(Int_t tt) {
+        Node* np = GetRoot();
+        while (!np->GetLeaf()) np = (tt < np->left->GetEnd()) ? np->left : np->right;
+        return np;
+    }
+    Node* FindLeafNode(Double_t* x) {
+        Node* np = GetRoot();
+        while (!np->GetLeaf()) { const int k = np->cut_dim; np = (x[k] < np->left->GetBoundary(k, 1)) ? np->left : np->right; }
+        return np;
+    }
 
     // ---- smoothed estimators (KDCalcSmoothQuantities.cxx:203-389) ----------------------------------------------
     void CalcDensity(Int_t Nsmooth = 64) {
@@ -198,6 +382,56 @@ public:
         return out;
     }
 
+    /// single-target forms (KDCalcSmoothQuantities.cxx:768-921, 1092-1207): gather-only, value returned.  One small device
+    /// query per call; loops over many targets should use nbk_calc_density_particles / nbk_calc_veldensity_particles.
+    Double_t CalcDensityParticle(Int_t target, Int_t Nsmooth = 64) {
+        int32_t q = (int32_t)target; double out = 0;
+        std::lock_guard<std::mutex> g(dev_mutex);
+        check(nbk_calc_density_particles(h, (int)Nsmooth, 1, &q, &out, 0));
+        return out;
+    }
+    Double_t CalcVelDensityParticle(Int_t target, Int_t Nsmooth = 64, Int_t Nsearch = 64, int iflag = 0, PriorityQueue* pq = NULL,
+                                    PriorityQueue* pq2 = NULL, Int_t* nnIDs = NULL, Double_t* vdist = NULL) {
+        (void)iflag; (void)pq; (void)pq2; (void)nnIDs; (void)vdist;     // caller-provided scratch of the reference: not needed
+        int32_t q = (int32_t)target; double out = 0;
+        std::lock_guard<std::mutex> g(dev_mutex);
+        check(nbk_calc_veldensity_particles(h, (int)Nsmooth, (int)Nsearch, 1, &q, &out, 0));
+        return out;
+    }
+    Double_t CalcDensityPosition(Double_t* x, Int_t Nsmooth = 64, Double_t* v = NULL) {
+        (void)v;                                                          // only read by the reference's phase-space trees
+        double xx[3] = {(double)x[0], (double)x[1], (double)x[2]}, out = 0;
+        std::lock_guard<std::mutex> g(dev_mutex);
+        check(nbk_calc_density_points(h, (int)Nsmooth, 1, xx, &out, 0));
+        return out;
+    }
+    Double_t CalcVelDensityPosition(Double_t* x, Double_t* v, Int_t Nsmooth = 64, Int_t Nsearch = 64) {
+        double xx[3] = {(double)x[0], (double)x[1], (double)x[2]}, vv[3] = {(double)v[0], (double)v[1], (double)v[2]}, out = 0;
+        std::lock_guard<std::mutex> g(dev_mutex);
+        check(nbk_calc_veldensity_points(h, (int)Nsmooth, (int)Nsearch, 1, xx, vv, &out, 0));
+        return out;
+    }
+    Double_t CalcDensityPosition(Coordinate x, Int_t Nsmooth = 64, Coordinate v = Coordinate(0.)) { (void)v; return CalcDensityPosition(x.GetCoord(), Nsmooth); }
+    Double_t CalcVelDensityPosition(Coordinate x, Coordinate v, Int_t Nsmooth = 64, Int_t Nsearch = 64) { return CalcVelDensityPosition(x.GetCoord(), v.GetCoord(), Nsmooth, Nsearch); }
+
+    /// KDCalcSmoothQuantities.cxx:1704-1735: kernel-weighted sum over a caller-supplied neighbour list (host data in, one
+    /// number out), evaluated with the tree's kernel table exactly as the reference's Wsm does (:12-15).  The queue form
+    /// holds squared distances and is emptied; the array form holds distances in descending order.
+    Double_t CalcSmoothLocalValue(Int_t Nsmooth, PriorityQueue* pq, Double_t* weight) {
+        const Double_t hi = 0.5 * std::sqrt(pq->TopPriority());
+        const Double_t norm = 1.0 / std::pow(hi, (Double_t)(info.nd * 1.));
+        Double_t value = 0;
+        for (Int_t j = 0; j < Nsmooth; j++) { value += wsm(std::sqrt(pq->TopPriority()) / hi) * norm * weight[j]; pq->Pop(); }
+        return value;
+    }
+    Double_t CalcSmoothLocalValue(Int_t Nsmooth, Double_t* dist, Double_t* weight) {
+        const Double_t hi = 0.5 * dist[0];
+        const Double_t norm = 1.0 / std::pow(hi, (Double_t)(info.nd * 1.));
+        Double_t value = 0;
+        for (Int_t j = 0; j < Nsmooth; j++) value += wsm(dist[j] / hi) * norm * weight[j];
+        return value;
+    }
+
     // ---- FOF (KDFOF.cxx:29-265) --------------------------------------------------------------------------------
     Int_t* FOF(Double_t fdist, Int_t& numgroup, Int_t minnum = 8, int order = 0, Int_tree_t* pHead = NULL, Int_tree_t* pNext = NULL,
                Int_tree_t* pTail = NULL, Int_tree_t* pLen = NULL, int ipcheckflag = 0, FOFcheckfunc check_ = Pnocheck, Double_t* params = NULL) {
@@ -210,11 +444,7 @@ public:
     Int_t* FOFCriterion(FOFcompfunc cmp, Double_t* params, Int_t& numgroups, Int_t minnum = 8, int order = 0, int ipcheckflag = 0,
                         FOFcheckfunc check_ = Pnocheck, Int_tree_t* pHead = NULL, Int_tree_t* pNext = NULL, Int_tree_t* pTail = NULL,
                         Int_tree_t* pLen = NULL) {
-        // inline criteria are recognised by address inside the caller's translation unit (SURVEY.md 8b)
-        int crit;
-        if (cmp == (FOFcompfunc)&FOF3d) crit = NBK_FOF3D;
-        else if (cmp == (FOFcompfunc)&FOF6d) crit = NBK_FOF6D;
-        else throw std::runtime_error("nbk shim: FOFCriterion supports FOF3d and FOF6d; host callbacks cannot run on the device");
+        const int crit = crit_code(cmp, "FOFCriterion");
         std::vector<int32_t> pre;
         fill_precheck(pre, ipcheckflag, check_, params);
         double pr[16];
@@ -230,10 +460,7 @@ public:
                                         FOFcheckfunc check_ = Pnocheck, Int_tree_t* pHead = NULL, Int_tree_t* pNext = NULL, Int_tree_t* pTail = NULL,
                                         Int_tree_t* pLen = NULL) {
         (void)ipcheckflag;
-        int crit;
-        if (cmp == (FOFcompfunc)&FOF3d) crit = NBK_FOF3D;
-        else if (cmp == (FOFcompfunc)&FOF6d) crit = NBK_FOF6D;
-        else throw std::runtime_error("nbk shim: FOFCriterionSetBasisForLinks supports FOF3d and FOF6d; host callbacks cannot run on the device");
+        const int crit = crit_code(cmp, "FOFCriterionSetBasisForLinks");
         std::vector<int32_t> pre;
         fill_precheck(pre, 1, check_, params);
         double pr[16];
@@ -251,22 +478,71 @@ public:
     void SetResetOrder(bool a) { iresetorder = a; }
 
 private:
-    void knn_cached(Int_t tt, Int_t* nn, Double_t* dist2, Int_t k, int flags) {
+    void require_pos_tree(const char* who) {
+        if (info.treetype != TPHYS && info.treetype != TPHS) throw std::runtime_error(std::string("nbk shim: ") + who + " has a device implementation on position trees only");
+    }
+    /// Wsm of the reference (KDCalcSmoothQuantities.cxx:12-15) on the tree's kernel table, r = rij/hi
+    Double_t wsm(Double_t r) {
+        const std::vector<Double_t>& K = kernel_table();
+        const int size = info.kernres;
+        const Double_t delta = 2.0 / (Double_t)(size - 1);
+        const int i = (int)(r * 0.5 * (size - 1));
+        if (i < size - 1) return K[i] + (K[i + 1] - K[i]) * (r - delta * i) / delta;
+        return K[i];
+    }
+    /// two-pass CSR protocol for a single query row: count, allocate, fill
+    template <class F>
+    void csr_row(F call, int flags, std::vector<int32_t>& idx, std::vector<double>* d2) {
+        int64_t off[2], tot = 0;
+        std::lock_guard<std::mutex> g(dev_mutex);
+        check(call(off, (int32_t*)NULL, (double*)NULL, (int64_t)0, &tot, flags));
+        idx.resize((size_t)std::max<int64_t>(tot, 1));
+        if (d2) d2->resize(idx.size());
+        check(call(off, idx.data(), d2 ? d2->data() : (double*)NULL, (int64_t)idx.size(), &tot, flags));
+        idx.resize((size_t)tot);
+        if (d2) d2->resize((size_t)tot);
+    }
+    /// crit == -2: plain search; otherwise filtered (crit -1: check function only, >= 0: NBK_FOF3D / NBK_FOF6D)
+    void knn_cached(Int_t tt, Int_t* nn, Double_t* dist2, Int_t k, int flags, int crit = -2, FOFcheckfunc checkfn = nullptr, Double_t* params = NULL) {
         if (tt < 0 || tt >= numparts) throw std::runtime_error("nbk shim: particle index out of range");
         KnnBlock& c = tls_block();
-        if (c.serial != serial || c.k != k || c.flags != flags || tt < c.b0 || tt >= c.b1) {
+        double pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (crit >= 0 && params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        bool same = c.serial == serial && c.k == k && c.flags == flags && c.crit == crit && c.checkfn == checkfn && tt >= c.b0 && tt < c.b1;
+        for (int j = 0; same && j < 8; j++) same = c.params[j] == pr[j];
+        if (!same) {
             const Int_t B = block_size(k);
             const Int_t b0 = (tt / B) * B, b1 = std::min(numparts, b0 + B);
             c.nn.resize((size_t)(b1 - b0) * k);
             c.d2.resize((size_t)(b1 - b0) * k);
-            {
+            if (crit == -2) {
                 std::lock_guard<std::mutex> g(dev_mutex);
                 check(nbk_knn_particles(h, (int)k, b0, b1, c.nn.data(), c.d2.data(), flags));
+            } else {
+                std::vector<int32_t> chk;
+                if (checkfn) { chk.resize(numparts); for (Int_t i = 0; i < numparts; i++) chk[i] = checkfn(bucket[i], params); }   // tree order
+                std::lock_guard<std::mutex> g(dev_mutex);
+                check(nbk_knn_filtered_particles(h, (int)k, b0, b1, crit, pr, checkfn ? chk.data() : NULL, c.nn.data(), c.d2.data(), flags | NBK_TREE_ORDER));
             }
-            c.serial = serial; c.b0 = b0; c.b1 = b1; c.k = k; c.flags = flags;
+            c.serial = serial; c.b0 = b0; c.b1 = b1; c.k = k; c.flags = flags; c.crit = crit; c.checkfn = checkfn;
+            for (int j = 0; j < 8; j++) c.params[j] = pr[j];
         }
         const size_t row = (size_t)(tt - c.b0) * k;
         for (Int_t j = 0; j < k; j++) { nn[j] = c.nn[row + j]; dist2[j] = c.d2[row + j]; }
+    }
+    void knn_filtered_point(const Double_t* x, const Double_t* v, int crit, FOFcheckfunc checkfn, Double_t* params, Int_t* nn, Double_t* dist2, Int_t k) {
+        double xx[3] = {(double)x[0], (double)x[1], (double)x[2]}, vv[3] = {0, 0, 0}, pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (v) for (int j = 0; j < 3; j++) vv[j] = (double)v[j];
+        if (crit >= 0 && params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        std::vector<int32_t> chk, n32(k);
+        std::vector<double> d2(k);
+        if (checkfn) { chk.resize(numparts); for (Int_t i = 0; i < numparts; i++) chk[i] = checkfn(bucket[i], params); }
+        {
+            std::lock_guard<std::mutex> g(dev_mutex);
+            check(nbk_knn_filtered_points(h, (int)k, 1, xx, v ? vv : NULL, crit, pr, checkfn ? chk.data() : NULL, n32.data(), d2.data(),
+                                          NBK_TREE_ORDER | (period ? NBK_KNN_TREE_FORM : 0)));
+        }
+        for (Int_t j = 0; j < k; j++) { nn[j] = n32[j]; dist2[j] = d2[j]; }
     }
     void knn_range(Int_t q0, Int_t q1, Int_t* nn, Double_t* dist2, Int_t k, int flags) {
         std::vector<int32_t> n32((size_t)(q1 - q0) * k);

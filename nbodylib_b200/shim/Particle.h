@@ -8,6 +8,10 @@
 #ifndef NBK_SHIM_PARTICLE_H
 #define NBK_SHIM_PARTICLE_H
 #include <cstddef>
+#include <queue>
+#include <stdexcept>
+#include <utility>
+#include <vector>
 
 namespace NBody {
 typedef double Double_t;
@@ -83,6 +87,29 @@ public:
     Particle* Parts() { return particle; }
     Int_t GetNumParts() const { return numparts; }
     Coordinate GetPeriod() const { return period; }
+};
+
+/// Bounded max-priority queue with the interface of the reference's NBody::PriorityQueue (PriorityQueue.h:14-85: Push / Pop /
+/// TopPriority / TopQueue / Size / MaxSize / Reset / Empty): the argument type of CalcSmoothLocalValue and the scratch type of
+/// CalcVelDensityParticle.  Built on std::priority_queue; among equal priorities the pop order is unspecified, as it is in
+/// the reference (an implicit binary heap).
+class PriorityQueue {
+    typedef std::pair<Double_t, Int_t> item;
+    std::priority_queue<item> q;
+    Int_t max_size;
+public:
+    explicit PriorityQueue(Int_t max) : max_size(max) {}
+    bool Empty() const { return q.empty(); }
+    Int_t Size() const { return (Int_t)q.size(); }
+    Int_t MaxSize() const { return max_size; }
+    void Reset() { q = std::priority_queue<item>(); }
+    void Push(Int_t p, Double_t dist) {
+        if ((Int_t)q.size() >= max_size) throw std::runtime_error("PriorityQueue: pushing beyond the allocated size");   // reference: exit()
+        q.push(item(dist, p));
+    }
+    void Pop() { q.pop(); }
+    Double_t TopPriority() const { return q.top().first; }
+    Int_t TopQueue() const { return q.top().second; }
 };
 
 // FOF criteria of the reference (FOFFunc.h:24-57).  Only their ADDRESSES matter to the device tree: the shim maps

@@ -172,6 +172,23 @@ class Ref:
             L.ref_scale_phase.argtypes = [C.c_long, _dp, _dp, C.c_double, C.c_double]
             L.ref_dump_nodes.restype = C.c_long
             L.ref_dump_nodes.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip, C.c_long]
+            L.ref_calc_density_particles.argtypes = [C.c_void_p, C.c_int, C.c_long, _ip, _dp]
+            L.ref_calc_veldensity_particles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, _ip, _dp]
+            L.ref_calc_density_points.argtypes = [C.c_void_p, C.c_int, C.c_long, _dp, _dp]
+            L.ref_calc_veldensity_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, _dp, _dp, _dp]
+            L.ref_smooth_local_value.restype = C.c_double
+            L.ref_smooth_local_value.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+            L.ref_search_criterion_particles.restype = C.c_long
+            L.ref_search_criterion_particles.argtypes = [C.c_void_p, C.c_int, _dp, C.c_long, _ip, _lp, _ip, C.c_long]
+            L.ref_search_criterion_points.restype = C.c_long
+            L.ref_search_criterion_points.argtypes = [C.c_void_p, C.c_int, _dp, C.c_long, _dp, _dp, _lp, _ip, C.c_long]
+            L.ref_search_ball_dense.argtypes = [C.c_void_p, C.c_long, _dp, C.c_double, C.c_int, _ip, _dp]
+            L.ref_search_criterion_dense.argtypes = [C.c_void_p, C.c_int, _dp, C.c_long, C.c_int, _ip, _dp]
+            L.ref_find_leaf.restype = C.c_long
+            L.ref_find_leaf.argtypes = [C.c_void_p, C.c_long, _dp, _ip, C.c_long]
+            L.ref_dump_cuts.restype = C.c_long
+            L.ref_dump_cuts.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, C.c_long]
+            L.ref_knn_filtered.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_long, C.c_long, C.c_long, _dp, _dp, _ip, _dp]
             L.ref_max_threads.restype = C.c_int
             L.ref_sizeof_particle.restype = C.c_int
             cls._lib = L
@@ -278,6 +295,96 @@ class Ref:
         rho = np.zeros(self.n) if want else None
         self.last_seconds = self.lib().ref_calc_density_omp(self.h, k, i0, i1, self.kernres, self.kerntype, _d(rho))
         return rho
+
+    # ---- single-target estimators, criterion search, dense forms, node getters -------------------------------
+    def calc_density_particles(self, qids, k):
+        q = np.ascontiguousarray(qids, dtype=np.int32)
+        out = np.zeros(len(q))
+        self.lib().ref_calc_density_particles(self.h, k, len(q), _i(q), _d(out))
+        return out
+
+    def calc_veldensity_particles(self, qids, kv, kx):
+        q = np.ascontiguousarray(qids, dtype=np.int32)
+        out = np.zeros(len(q))
+        self.lib().ref_calc_veldensity_particles(self.h, kv, kx, len(q), _i(q), _d(out))
+        return out
+
+    def calc_density_points(self, x, k):
+        x = _f64(x)
+        out = np.zeros(len(x))
+        self.lib().ref_calc_density_points(self.h, k, len(x), _d(x), _d(out))
+        return out
+
+    def calc_veldensity_points(self, x, v, kv, kx):
+        x, v = _f64(x), _f64(v)
+        out = np.zeros(len(x))
+        self.lib().ref_calc_veldensity_points(self.h, kv, kx, len(x), _d(x), _d(v), _d(out))
+        return out
+
+    def smooth_local_value(self, dist, weight):
+        dist, weight = _f64(dist).copy(), _f64(weight).copy()
+        return self.lib().ref_smooth_local_value(self.h, len(dist), _d(dist), _d(weight))
+
+    def _csr(self, call, m):
+        cap = 64 * m + 1024
+        while True:
+            off = np.zeros(m + 1, dtype=np.int64)
+            ids = np.zeros(cap, dtype=np.int32)
+            tot = call(_l(off), _i(ids), cap)
+            if tot <= cap:
+                return off, ids[:tot]
+            cap = tot
+
+    def search_criterion_particles(self, qids, crit, params):
+        q = np.ascontiguousarray(qids, dtype=np.int32)
+        pr = _f64(params).copy()
+        return self._csr(lambda off, ids, cap: self.lib().ref_search_criterion_particles(self.h, crit, _d(pr), len(q), _i(q), off, ids, cap), len(q))
+
+    def search_criterion_points(self, x, v, crit, params):
+        x = _f64(x)
+        v = _f64(v)
+        pr = _f64(params).copy()
+        return self._csr(lambda off, ids, cap: self.lib().ref_search_criterion_points(self.h, crit, _d(pr), len(x), _d(x), _d(v), off, ids, cap), len(x))
+
+    def search_ball_dense(self, q, r2, imark, nn, dist2):
+        """q: particle ID (int) or a position; nn (int32) / dist2 (float64) by ID, updated in place"""
+        if np.ndim(q) == 0:
+            self.lib().ref_search_ball_dense(self.h, int(q), None, r2, imark, _i(nn), _d(dist2))
+        else:
+            x = _f64(q)
+            self.lib().ref_search_ball_dense(self.h, -1, _d(x), r2, imark, _i(nn), _d(dist2))
+
+    def search_criterion_dense(self, qid, crit, params, imark, nn, dist2):
+        pr = _f64(params).copy()
+        self.lib().ref_search_criterion_dense(self.h, crit, _d(pr), int(qid), imark, _i(nn), _d(dist2))
+
+    def find_leaf(self, q):
+        ids = np.zeros(4096, dtype=np.int32)
+        if np.ndim(q) == 0:
+            c = self.lib().ref_find_leaf(self.h, int(q), None, _i(ids), len(ids))
+        else:
+            x = _f64(q)
+            c = self.lib().ref_find_leaf(self.h, -1, _d(x), _i(ids), len(ids))
+        return np.sort(ids[:c])
+
+    def knn_filtered(self, k, crit=-1, params=None, q0=0, q1=None, x=None, v=None):
+        """FindNearestCheck (crit < 0; Particle::type != 0 excluded, see set_types) / FindNearestCriterion (crit 0 | 2) for the
+        particle IDs q0..q1, or for the points x (velocities v)"""
+        pr = _f64(np.zeros(10) if params is None else params).copy()
+        x, v = _f64(x), _f64(v)
+        q1 = self.n if q1 is None else q1
+        rows = len(x) if x is not None else q1 - q0
+        ids = np.zeros((rows, k), dtype=np.int32)
+        d2 = np.zeros((rows, k))
+        self.lib().ref_knn_filtered(self.h, crit, _d(pr), k, q0, q1, rows, _d(x), _d(v), _i(ids), _d(d2))
+        return ids, d2
+
+    def dump_cuts(self):
+        cap = self.n + 64
+        ids, dims = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+        vals, lmax = np.zeros(cap), np.zeros(cap)
+        m = self.lib().ref_dump_cuts(self.h, _i(ids), _i(dims), _d(vals), _d(lmax), cap)
+        return ids[:m], dims[:m], vals[:m], lmax[:m]
 
     def fof(self, fdist, minnum=8, order=0):
         g = np.zeros(self.n, dtype=np.int32)

@@ -16,6 +16,10 @@
  *   SearchBallPosTagged       src/KDTree/KDFindNearest.cxx:618-688
  *   CalcDensity/CalcVelDensity src/KDTree/KDCalcSmoothQuantities.cxx:203-389
  *   FOF / FOFCriterion        src/KDTree/KDFOF.cxx:29-265
+ *   CalcDensityParticle / CalcVelDensityParticle / Calc*Position / CalcSmoothLocalValue
+ *                             src/KDTree/KDCalcSmoothQuantities.cxx:768-921, 1092-1207, 1704-1735
+ *   SearchCriterionTagged, dense SearchBallPos / SearchCriterion   src/KDTree/KDFindNearest.cxx:567-603, 660-706
+ *   FindLeafNode, node getters   src/KDTree/KDFindNearest.cxx:709-736, KDNode.h
  */
 #include <KDTree.h>
 #include <omp.h>
@@ -327,6 +331,185 @@ long ref_dump_nodes(void* hv, int* start, int* end, int* isleaf, int* cutdim, lo
     long m = (long)s.size();
     for (long i = 0; i < m && i < cap; i++) { start[i] = s[i]; end[i] = e[i]; isleaf[i] = l[i]; cutdim[i] = c[i]; }
     return m;
+}
+
+/* ---- single-target estimators (KDCalcSmoothQuantities.cxx:768-921, 1092-1207), looped over query IDs / points ---- */
+void ref_calc_density_particles(void* hv, int k, long m, const int* qids, double* out) {
+    RefTree* h = (RefTree*)hv;
+    vector<Int_t> where(h->n);
+    for (Int_t i = 0; i < h->n; i++) where[h->parts[i].GetID()] = i;
+#pragma omp parallel for schedule(guided)
+    for (long q = 0; q < m; q++) out[q] = h->tree->CalcDensityParticle(where[qids[q]], k);
+}
+void ref_calc_veldensity_particles(void* hv, int kv, int kx, long m, const int* qids, double* out) {
+    RefTree* h = (RefTree*)hv;
+    vector<Int_t> where(h->n);
+    for (Int_t i = 0; i < h->n; i++) where[h->parts[i].GetID()] = i;
+#pragma omp parallel for schedule(guided)
+    for (long q = 0; q < m; q++) out[q] = h->tree->CalcVelDensityParticle(where[qids[q]], kv, kx);
+}
+void ref_calc_density_points(void* hv, int k, long m, const double* x, double* out) {
+    RefTree* h = (RefTree*)hv;
+#pragma omp parallel for schedule(guided)
+    for (long q = 0; q < m; q++) {
+        Double_t xx[3] = {x[3 * q], x[3 * q + 1], x[3 * q + 2]};
+        out[q] = h->tree->CalcDensityPosition(xx, k);
+    }
+}
+void ref_calc_veldensity_points(void* hv, int kv, int kx, long m, const double* x, const double* v, double* out) {
+    RefTree* h = (RefTree*)hv;
+#pragma omp parallel for schedule(guided)
+    for (long q = 0; q < m; q++) {
+        Double_t xx[3] = {x[3 * q], x[3 * q + 1], x[3 * q + 2]}, vv[3] = {v[3 * q], v[3 * q + 1], v[3 * q + 2]};
+        out[q] = h->tree->CalcVelDensityPosition(xx, vv, kv, kx);
+    }
+}
+/* CalcSmoothLocalValue(Nsmooth, Double_t* dist, Double_t* weight): dist descending (KDCalcSmoothQuantities.cxx:1721-1735) */
+double ref_smooth_local_value(void* hv, int k, double* dist, double* weight) {
+    RefTree* h = (RefTree*)hv;
+    return h->tree->CalcSmoothLocalValue(k, dist, weight);
+}
+
+/* SearchCriterionTagged(tt, cmp, params, tagged) for the given query IDs; CSR like ref_ball_particles */
+long ref_search_criterion_particles(void* hv, int crit, double* params, long m, const int* qids, long* offsets, int* out_ids, long cap) {
+    RefTree* h = (RefTree*)hv;
+    FOFcompfunc cmp = crit == 0 ? FOF3d : (crit == 1 ? FOFVel : FOF6d);
+    vector<Int_t> where(h->n);
+    for (Int_t i = 0; i < h->n; i++) where[h->parts[i].GetID()] = i;
+    long tot = 0;
+    vector<Int_t> tagged(8 * (size_t)h->n + 8);       // the periodic form can report a particle once per image
+    for (long q = 0; q < m; q++) {
+        offsets[q] = tot;
+        Int_t nt = h->tree->SearchCriterionTagged(where[qids[q]], cmp, params, tagged.data());
+        for (Int_t j = 0; j < nt; j++) {
+            if (tot < cap) out_ids[tot] = (int)h->parts[tagged[j]].GetID();
+            tot++;
+        }
+    }
+    offsets[m] = tot;
+    return tot;
+}
+/* SearchCriterionTagged(Particle& p, ...) for particles that are not in the tree (positions x, velocities v) */
+long ref_search_criterion_points(void* hv, int crit, double* params, long m, const double* x, const double* v, long* offsets, int* out_ids, long cap) {
+    RefTree* h = (RefTree*)hv;
+    FOFcompfunc cmp = crit == 0 ? FOF3d : (crit == 1 ? FOFVel : FOF6d);
+    long tot = 0;
+    vector<Int_t> tagged(8 * (size_t)h->n + 8);
+    for (long q = 0; q < m; q++) {
+        offsets[q] = tot;
+        Particle p;
+        p.SetPosition(x[3 * q], x[3 * q + 1], x[3 * q + 2]);
+        if (v) p.SetVelocity(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
+        p.SetID(-1); p.SetPID(-1);
+        Int_t nt = h->tree->SearchCriterionTagged(p, cmp, params, tagged.data());
+        for (Int_t j = 0; j < nt; j++) {
+            if (tot < cap) out_ids[tot] = (int)h->parts[tagged[j]].GetID();
+            tot++;
+        }
+    }
+    offsets[m] = tot;
+    return tot;
+}
+/* dense SearchBallPos(tt | x, fdist2, imark, nn, dist2) (KDFindNearest.cxx:567-587): nn / dist2 have n entries (by ID)
+ * and are updated in place; qid < 0 selects the position form. */
+void ref_search_ball_dense(void* hv, long qid, const double* x, double r2, int imark, int* nn_by_id, double* d2_by_id) {
+    RefTree* h = (RefTree*)hv;
+    vector<Int_t> nn(nn_by_id, nn_by_id + h->n);
+    vector<Double_t> d2(d2_by_id, d2_by_id + h->n);
+    if (qid >= 0) {
+        Int_t tt = -1;
+        for (Int_t i = 0; i < h->n; i++) if (h->parts[i].GetID() == qid) { tt = i; break; }
+        h->tree->SearchBallPos(tt, r2, imark, nn.data(), d2.data());
+    } else {
+        Double_t xx[3] = {x[0], x[1], x[2]};
+        h->tree->SearchBallPos(xx, r2, imark, nn.data(), d2.data());
+    }
+    for (Int_t i = 0; i < h->n; i++) { nn_by_id[i] = (int)nn[i]; d2_by_id[i] = d2[i]; }
+}
+/* dense SearchCriterion(tt, cmp, params, imark, nn, dist2) (KDFindNearest.cxx:590-596) */
+void ref_search_criterion_dense(void* hv, int crit, double* params, long qid, int imark, int* nn_by_id, double* d2_by_id) {
+    RefTree* h = (RefTree*)hv;
+    FOFcompfunc cmp = crit == 0 ? FOF3d : (crit == 1 ? FOFVel : FOF6d);
+    vector<Int_t> nn(nn_by_id, nn_by_id + h->n);
+    vector<Double_t> d2(d2_by_id, d2_by_id + h->n);
+    Int_t tt = -1;
+    for (Int_t i = 0; i < h->n; i++) if (h->parts[i].GetID() == qid) { tt = i; break; }
+    h->tree->SearchCriterion(tt, cmp, params, imark, nn.data(), d2.data());
+    for (Int_t i = 0; i < h->n; i++) { nn_by_id[i] = (int)nn[i]; d2_by_id[i] = d2[i]; }
+}
+/* FindLeafNode(tt) / FindLeafNode(x): the leaf's particle IDs (sorted by the caller), count returned */
+long ref_find_leaf(void* hv, long qid, const double* x, int* member_ids, long cap) {
+    RefTree* h = (RefTree*)hv;
+    Node* nd;
+    if (qid >= 0) {
+        Int_t tt = -1;
+        for (Int_t i = 0; i < h->n; i++) if (h->parts[i].GetID() == qid) { tt = i; break; }
+        nd = h->tree->FindLeafNode(tt);
+    } else {
+        Double_t xx[3] = {x[0], x[1], x[2]};
+        nd = h->tree->FindLeafNode(xx);
+    }
+    long c = 0;
+    for (Int_t i = nd->GetStart(); i < nd->GetEnd(); i++, c++) if (c < cap) member_ids[c] = (int)h->parts[i].GetID();
+    return c;
+}
+/* split nodes in depth-first order (left before right): node ID, cut dimension, cut value, left child's upper boundary in
+ * the cut dimension */
+static void walk_cuts(Node* nd, vector<int>& ids, vector<int>& dims, vector<double>& vals, vector<double>& leftmax) {
+    if (nd->GetLeaf()) return;
+    SplitNode* sp = (SplitNode*)nd;
+    ids.push_back((int)sp->GetID()); dims.push_back(sp->GetCutDim()); vals.push_back(sp->GetCutValue());
+    leftmax.push_back(sp->GetLeft()->GetBoundary(sp->GetCutDim(), 1));
+    walk_cuts(sp->GetLeft(), ids, dims, vals, leftmax);
+    walk_cuts(sp->GetRight(), ids, dims, vals, leftmax);
+}
+long ref_dump_cuts(void* hv, int* ids, int* dims, double* vals, double* leftmax, long cap) {
+    RefTree* h = (RefTree*)hv;
+    vector<int> a, b; vector<double> c, d;
+    walk_cuts(h->tree->GetRoot(), a, b, c, d);
+    long m = (long)a.size();
+    for (long i = 0; i < m && i < cap; i++) { ids[i] = a[i]; dims[i] = b[i]; vals[i] = c[i]; leftmax[i] = d[i]; }
+    return m;
+}
+
+/* FindNearestCheck(tt | Coordinate x, check_by_type, ...) and FindNearestCriterion(tt | Particle p, cmp, params, ...)
+ * (KDFindNearest.cxx:363-441).  Queries are particle IDs q0..q1 (x == NULL) or m points x (with velocities v for the
+ * Particle form); crit < 0 selects the check form (Particle::type != 0 => excluded, set with ref_set_types). */
+void ref_knn_filtered(void* hv, int crit, double* params, int k, long q0, long q1, long m, const double* x, const double* v,
+                      int* out_ids, double* out_d2) {
+    RefTree* h = (RefTree*)hv;
+    FOFcompfunc cmp = crit == 0 ? FOF3d : (crit == 1 ? FOFVel : FOF6d);
+    vector<Int_t> where(h->n);
+    for (Int_t i = 0; i < h->n; i++) where[h->parts[i].GetID()] = i;
+    const long rows = x ? m : q1 - q0;
+#pragma omp parallel
+    {
+        vector<Int_t> nn(k);
+        vector<Double_t> d2(k);
+#pragma omp for schedule(guided)
+        for (long r = 0; r < rows; r++) {
+            if (x) {
+                if (crit < 0) {
+                    Coordinate c(x[3 * r], x[3 * r + 1], x[3 * r + 2]);
+                    h->tree->FindNearestCheck(c, check_by_type, params, nn.data(), d2.data(), k);
+                } else {
+                    Particle p;
+                    p.SetPosition(x[3 * r], x[3 * r + 1], x[3 * r + 2]);
+                    if (v) p.SetVelocity(v[3 * r], v[3 * r + 1], v[3 * r + 2]);
+                    p.SetID(-1); p.SetPID(-1);
+                    h->tree->FindNearestCriterion(p, cmp, params, nn.data(), d2.data(), k);
+                }
+            } else {
+                Int_t tt = where[q0 + r];
+                if (crit < 0) h->tree->FindNearestCheck(tt, check_by_type, params, nn.data(), d2.data(), k);
+                else h->tree->FindNearestCriterion(tt, cmp, params, nn.data(), d2.data(), k);
+            }
+            for (int j = 0; j < k; j++) {
+                out_ids[r * k + j] = nn[j] >= 0 ? (int)h->parts[nn[j]].GetID() : -1;
+                out_d2[r * k + j] = d2[j];
+            }
+        }
+    }
 }
 
 }  // extern "C"

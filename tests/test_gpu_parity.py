@@ -8,7 +8,7 @@ Bars: neighbour sets, d2 values, FOF partitions, ball-search sets: bit-exact.  D
 import numpy as np
 import pytest
 
-from tests.util import canon, csr_rows_sorted, load_golden, rows_equal_as_sets
+from tests.util import canon, csr_rows_sorted, load_golden, load_golden_extra, rows_equal_as_sets
 
 pytestmark = pytest.mark.gpu
 
@@ -529,3 +529,161 @@ def test_attached_halo_tree_equals_masked_single_tree(nb, flags):
     with pytest.raises(nb.NbkError):
         t1.FOF(0.01, 8, 0)
     t1.close()
+
+
+# ---- single-target estimators, criterion search, dense forms, node mirror (a11, a13; 8f rank 2) ---------
+@pytest.fixture(scope="module")
+def X():
+    return load_golden_extra()
+
+
+def _where(order):
+    w = np.empty_like(order)
+    w[order] = np.arange(len(order), dtype=order.dtype)
+    return w
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_golden_single_target_estimators(nb, G, X, tag):
+    """CalcDensityParticle / CalcVelDensityParticle / CalcDensityPosition / CalcVelDensityPosition against the reference's
+    values (tests/golden/ref_extra.npz).  Same operation order as the reference; pow() is the only library call that may
+    round differently, hence 1e-13 instead of bit equality."""
+    period = None if tag == "np" else np.ones(3)
+    k, kv = int(G["k"]), int(X["kv"])
+    with nb.KDTree(G["pos"], G["vel"], X["mass2"], Period=period) as t:
+        where = _where(t.order())
+        tt = where[X["qsel"]]
+        np.testing.assert_allclose(t.CalcDensityParticle(tt, k), X["dens_part_" + tag], rtol=1e-13)
+        np.testing.assert_allclose(t.CalcVelDensityParticle(tt, kv, k), X["vdens_part_" + tag], rtol=1e-13)
+        np.testing.assert_allclose(t.CalcDensityPosition(G["xq"], k), X["dens_pos_" + tag], rtol=1e-13)
+        np.testing.assert_allclose(t.CalcVelDensityPosition(G["xq"], X["vq"], kv, k), X["vdens_pos_" + tag], rtol=1e-13)
+        # whole-system form (no list: tree indices 0..n-1, 32 neighbouring queries per warp) and the scalar form
+        alln = t.CalcDensityParticle(None, k)
+        np.testing.assert_allclose(alln[tt], X["dens_part_" + tag], rtol=1e-13)
+        allv = t.CalcVelDensityParticle(None, kv, k)
+        np.testing.assert_allclose(allv[tt], X["vdens_part_" + tag], rtol=1e-13)
+        one = t.CalcDensityParticle(int(tt[5]), k)
+        assert isinstance(one, float) and one == pytest.approx(float(X["dens_part_" + tag][5]), rel=1e-13)
+        # the gather-only density is the whole-system CalcVelDensity's single-target twin: identical numbers
+        np.testing.assert_allclose(allv[where], t.CalcVelDensity(kv, k), rtol=1e-13)
+        assert t.CalcSmoothLocalValue(k, X["slv_dist"], X["slv_weight"]) == pytest.approx(float(X["slv_value"]), rel=1e-14)
+        with pytest.raises(nb.NbkError) as e:
+            t.CalcDensityParticle(np.array([0, len(where)]), k)
+        assert e.value.code == -1
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_golden_criterion_search(nb, G, X, tag):
+    """SearchCriterionTagged(Int_t tt | Particle&, FOF3d | FOF6d): rows identical to the reference's"""
+    period = None if tag == "np" else np.ones(3)
+    with nb.KDTree(G["pos"], G["vel"], G["mass"], Period=period) as t:
+        order = t.order()
+        tt = _where(order)[X["qsel"]]
+        for crit, name in ((nb.FOF3D, "c3"), (nb.FOF6D, "c6")):
+            off, idx = t.SearchCriterionTagged(tt, crit, G["params"], ids=True)
+            assert np.array_equal(off, X["%s_off_%s" % (name, tag)])
+            assert np.array_equal(np.concatenate(csr_rows_sorted(off, idx)), X["%s_idx_%s" % (name, tag)])
+            off2, idx2 = t.SearchCriterionTagged(tt, crit, G["params"])                 # tree indices map to the same IDs
+            assert np.array_equal(off2, off) and np.array_equal(order[idx2], idx)
+            off, idx = t.SearchCriterionTaggedPoints(X["xn"], X["vn"], crit, G["params"], ids=True)
+            assert np.array_equal(off, X["%sx_off_%s" % (name, tag)])
+            assert np.array_equal(np.concatenate(csr_rows_sorted(off, idx)), X["%sx_idx_%s" % (name, tag)])
+        with pytest.raises(nb.NbkError) as e:
+            t.SearchCriterionTagged(tt[:4], nb.FOFVEL, G["params"])
+        assert e.value.code == -3
+        with pytest.raises(nb.NbkError) as e:
+            t.SearchBallPosTagged([-1], 0.01)
+        assert e.value.code == -1
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_golden_dense_search_forms(nb, G, X, tag):
+    """dense SearchBallPos(tt | x, fdist2, imark, nn, dist2) and SearchCriterion(tt, cmp, params, imark, nn, dist2): the
+    caller's N-entry arrays end up as the reference leaves them (the target's own entry aside, quirk Q5)."""
+    period = None if tag == "np" else np.ones(3)
+    n = len(G["pos"])
+    r2 = (2.5 * float(G["ll"])) ** 2
+    with nb.KDTree(G["pos"], G["vel"], G["mass"], Period=period) as t:
+        where = _where(t.order())
+        dq = X["dense_q"]
+        nn, d2 = np.zeros(n, dtype=np.int32), np.zeros(n)
+        for j, q in enumerate(dq):
+            t.SearchBallPos(int(where[q]), r2, j + 1, nn, d2)
+        keep = np.ones(n, dtype=bool)
+        keep[dq] = False
+        assert np.array_equal(nn[keep], X["dense_ball_nn_" + tag][keep]) and np.array_equal(d2[keep], X["dense_ball_d2_" + tag][keep])
+        nn[:] = 0
+        d2[:] = 0
+        for j, x in enumerate(G["xq"][:12]):
+            t.SearchBallPos(x, r2, j + 1, nn, d2)
+        assert np.array_equal(nn, X["dense_ballx_nn_" + tag]) and np.array_equal(d2, X["dense_ballx_d2_" + tag])
+        nn[:] = 0
+        d2[:] = 0
+        for j, q in enumerate(dq):
+            off, idx, dd = t.SearchCriterionTagged([int(where[q])], nb.FOF6D, G["params"], ids=True, want_d2=True)
+            take = (nn[idx] > j + 1) | (nn[idx] == 0)                      # KDLeafNode.cxx:418
+            nn[idx[take]] = j + 1
+            d2[idx[take]] = dd[take]
+        assert np.array_equal(nn, X["dense_c6_nn_" + tag])
+        if tag == "np":
+            assert np.array_equal(d2, X["dense_c6_d2_" + tag])
+        nn2 = np.zeros(n, dtype=np.int32)
+        t.SearchCriterion(int(where[dq[0]]), nb.FOF6D, G["params"], 3, nn2)
+        assert np.array_equal(nn2 == 3, X["dense_c6_nn_" + tag] == 1)
+
+
+def test_node_mirror_against_reference(nb, G, X):
+    """GetRoot() / FindLeafNode() consumers: the host mirror of the node arrays has the reference's split dimensions and
+    cut values (depth-first order) and its leaves hold the same particles"""
+    with nb.KDTree(G["pos"], G["vel"], G["mass"]) as t:
+        order = t.order()
+        where = _where(order)
+        s, e, c, b = t.nodes()
+        dims, vals = [], []
+        stack = [0]
+        while stack:
+            slot = stack.pop()
+            if c[slot] < 0:
+                continue
+            dims.append(int(c[slot]))
+            vals.append(float(b[2 * slot + 1, 2 * c[slot] + 1]))
+            stack.append(2 * slot + 2)
+            stack.append(2 * slot + 1)
+        assert np.array_equal(dims, X["cut_dims"]) and np.array_equal(vals, X["cut_vals"])
+        off, ids = X["leaf_off"], X["leaf_ids"]
+        for j, q in enumerate(X["dense_q"]):
+            _, a, z = t.FindLeafNode(int(where[q]))
+            assert np.array_equal(np.sort(order[a:z]), ids[off[j]:off[j + 1]])
+        off, ids = X["leafx_off"], X["leafx_ids"]
+        for j, x in enumerate(G["xq"][:12]):
+            _, a, z = t.FindLeafNode(x)
+            assert np.array_equal(np.sort(order[a:z]), ids[off[j]:off[j + 1]])
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_golden_filtered_knn(nb, G, X, tag):
+    """FindNearestCheck (tt | Coordinate) and FindNearestCriterion (tt | Particle; FOF3d, FOF6d) against the reference: same
+    d2 rows bit for bit, same neighbour sets, (-1, 1e32) padding where fewer than k particles qualify.  Periodic trees
+    reproduce the reference's drop-the-nearest behaviour by default; tree_form=False returns the k nearest instead."""
+    period = None if tag == "np" else np.ones(3)
+    kf = int(X["kf"])
+    with nb.KDTree(G["pos"], G["vel"], G["mass"], Period=period) as t:
+        order = t.order()
+        nn, d2 = t.FindNearestCheck(X["types"], kf, ids=True)
+        assert np.array_equal(by_id(order, d2), X["nnchk_d2_" + tag]) and rows_equal_as_sets(by_id(order, nn), X["nnchk_ids_" + tag])
+        assert np.all(X["types"][nn] == 0)
+        nn, d2 = t.FindNearestCheck(X["types"], kf, x=G["xq"], ids=True)
+        assert np.array_equal(d2, X["nnchkx_d2_" + tag]) and rows_equal_as_sets(nn, X["nnchkx_ids_" + tag])
+        for crit, name in ((nb.FOF3D, "c3"), (nb.FOF6D, "c6")):
+            nn, d2 = t.FindNearestCriterion(crit, G["params"], kf, ids=True)
+            assert np.array_equal(by_id(order, d2), X["nn%s_d2_%s" % (name, tag)])
+            assert rows_equal_as_sets(by_id(order, nn), X["nn%s_ids_%s" % (name, tag)])
+            nn, d2 = t.FindNearestCriterion(crit, G["params"], kf, x=X["xn"], v=X["vn"], ids=True)
+            assert np.array_equal(d2, X["nn%sx_d2_%s" % (name, tag)]) and rows_equal_as_sets(nn, X["nn%sx_ids_%s" % (name, tag)])
+        if tag == "p":
+            # without the reference's off-by-one the rows start one neighbour earlier
+            nn1, d21 = t.FindNearestCheck(X["types"], kf + 1, ids=True, tree_form=False)
+            assert np.array_equal(by_id(order, d21)[:, 1:], X["nnchk_d2_p"])
+        with pytest.raises(nb.NbkError) as e:
+            t.FindNearestCriterion(nb.FOFVEL, G["params"], kf)
+        assert e.value.code == -3

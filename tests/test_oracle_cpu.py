@@ -227,3 +227,121 @@ def test_reference_checked_fof_semantics(periodic):
             amb += len(cand) > 1
     assert amb > 0                            # the rule was actually exercised
     R.close()
+
+
+# ---- extra golden vectors (single-target estimators, criterion search, dense forms, node getters) -------------------
+@pytest.fixture(scope="module")
+def X():
+    from tests.util import load_golden_extra
+    return load_golden_extra()
+
+
+def test_single_target_estimators_restatement(port, G, X):
+    """CalcDensityParticle / CalcVelDensityParticle / CalcSmoothLocalValue of the reference == the gather-only restatement
+    the CUDA epilogue follows (KDCalcSmoothQuantities.cxx:768-921, 1704-1735), bit for bit; the period is ignored (Q2)."""
+    from tests.util import gather_density, gather_veldensity
+    k, kv = int(G["k"]), int(X["kv"])
+    _, kern = port.kernel_table(3, 2, 1000)
+    ids, d2 = G["knn0_ids_np"], G["knn0_d2_np"]
+    q = X["qsel"]
+    mine = np.array([gather_density(kern, d2[i], X["mass2"][ids[i]]) for i in q])
+    assert np.array_equal(mine, X["dens_part_np"])
+    assert np.array_equal(X["dens_part_p"], X["dens_part_np"]) and np.array_equal(X["vdens_part_p"], X["vdens_part_np"])
+    vmine = np.array([gather_veldensity(kern, G["vel"][i], G["vel"][ids[i]], kv) for i in q])
+    np.testing.assert_allclose(vmine, X["vdens_part_np"], rtol=1e-14)
+    # position forms: coordinate search (a particle at distance 0 counts), same sums
+    idx, d2x = G["knnx_ids_np"], G["knnx_d2_np"]
+    pm = np.array([gather_density(kern, d2x[i], X["mass2"][idx[i]]) for i in range(len(idx))])
+    assert np.array_equal(pm, X["dens_pos_np"]) and np.array_equal(X["dens_pos_p"], X["dens_pos_np"])
+    pv = np.array([gather_veldensity(kern, X["vq"][i], G["vel"][idx[i]], kv) for i in range(len(idx))])
+    np.testing.assert_allclose(pv, X["vdens_pos_np"], rtol=1e-14)
+    # CalcSmoothLocalValue(Nsmooth, dist, weight): dist descending
+    assert gather_density(kern, X["slv_dist"][::-1] ** 2, X["slv_weight"][::-1]) == pytest.approx(float(X["slv_value"]), rel=1e-15)
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_criterion_search_restatement(G, X, tag):
+    """SearchCriterionTagged of the reference == every particle other than the target meeting the criterion over the
+    reference's periodic images (KDFindNearest.cxx:660-706, KDLeafNode.cxx:445-492, KDSplitNode.cxx:1496-1529)."""
+    from tests.util import crit_rows
+    period = None if tag == "np" else np.ones(3)
+    pos, vel, params, q = G["pos"], G["vel"], G["params"], X["qsel"]
+    for crit, name in ((0, "c3"), (2, "c6")):
+        rows = crit_rows(pos, vel, pos[q], vel[q], crit, params, period, exclude=q)
+        off, idx = X["%s_off_%s" % (name, tag)], X["%s_idx_%s" % (name, tag)]
+        assert all(np.array_equal(rows[i], idx[off[i]:off[i + 1]]) for i in range(len(q)))
+        rows = crit_rows(pos, vel, X["xn"], X["vn"], crit, params, period)
+        off, idx = X["%sx_off_%s" % (name, tag)], X["%sx_idx_%s" % (name, tag)]
+        assert all(np.array_equal(rows[i], idx[off[i]:off[i + 1]]) for i in range(len(rows)))
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_dense_search_restatement(G, X, tag):
+    """dense SearchBallPos / SearchCriterion (KDFindNearest.cxx:567-603): nn[ID] = imark, dist2[ID] = position d2; later
+    calls overwrite earlier marks in the ball form, the criterion form only claims unmarked or later-marked particles.
+    The target itself is marked only when the reference swallows a whole node around it (quirk Q5): masked out here."""
+    from tests.util import ball_min_d2, crit_rows
+    period = None if tag == "np" else np.ones(3)
+    pos, vel, ll = G["pos"], G["vel"], float(G["ll"])
+    r2 = (2.5 * ll) ** 2
+    n = len(pos)
+    for key, queries, targets in (("dense_ball", pos[X["dense_q"]], X["dense_q"]), ("dense_ballx", G["xq"][:12], None)):
+        nn, d2 = np.zeros(n, dtype=np.int32), np.zeros(n)
+        for j, x in enumerate(queries):
+            b = ball_min_d2(pos, x, period)
+            hit = b < r2
+            nn[hit] = j + 1
+            d2[hit] = b[hit]
+        ref_nn, ref_d2 = X[key + "_nn_" + tag].copy(), X[key + "_d2_" + tag].copy()
+        keep = np.ones(n, dtype=bool)
+        if targets is not None:
+            keep[targets] = False
+        assert np.array_equal(nn[keep], ref_nn[keep]) and np.array_equal(d2[keep], ref_d2[keep])
+    nn, d2 = np.zeros(n, dtype=np.int32), np.zeros(n)
+    q = X["dense_q"]
+    rows = crit_rows(pos, vel, pos[q], vel[q], 2, G["params"], period, exclude=q)
+    for j, row in enumerate(rows):
+        take = row[(nn[row] > j + 1) | (nn[row] == 0)]
+        nn[take] = j + 1
+        d = pos[q[j]][None, :] - pos[take]
+        d2[take] = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    assert np.array_equal(nn, X["dense_c6_nn_" + tag])
+    if tag == "np":      # periodic: the reference reports the distance to the image that matched; pinned for the marks only
+        assert np.array_equal(d2, X["dense_c6_d2_" + tag])
+
+
+def test_node_getters_known_answers(G, X):
+    """cut values are the median particle's coordinate = the left child's upper boundary (KDTree.cxx:1012-1013); node IDs
+    number the nodes depth first; FindLeafNode(tt) returns the <= bucket-sized leaf holding tt (KDFindNearest.cxx:709-722)"""
+    assert np.array_equal(X["cut_ids"][:3], [0, 1, 2]) and len(X["cut_ids"]) == int(G["nodes"][0]) - int(G["nodes"][1])
+    off, ids = X["leaf_off"], X["leaf_ids"]
+    for j, q in enumerate(X["dense_q"]):
+        leaf = ids[off[j]:off[j + 1]]
+        assert q in leaf and len(leaf) <= 16
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_filtered_knn_restatement(G, X, tag):
+    """FindNearestCheck / FindNearestCriterion of the reference (KDFindNearest.cxx:363-441) == k nearest (minimum image over
+    the reference's reflections) among the particles other than the target that pass the filter; the periodic forms search
+    k+1 and drop the nearest; rows are padded with (-1, 1e32)."""
+    from tests.util import ball_min_d2, crit_rows
+    period = None if tag == "np" else np.ones(3)
+    pos, vel, kf, types = G["pos"], G["vel"], int(X["kf"]), X["types"]
+    drop = 0 if period is None else 1
+    for i in range(0, len(pos), 97):
+        d2 = ball_min_d2(pos, pos[i], period)
+        d2[i] = np.inf
+        d2[types != 0] = np.inf
+        want = np.sort(d2)[drop:kf + drop]
+        assert np.array_equal(want, X["nnchk_d2_" + tag][i])
+    q = np.arange(0, len(pos), 97)
+    for crit, name in ((0, "c3"), (2, "c6")):
+        rows = crit_rows(pos, vel, pos[q], vel[q], crit, G["params"], period, exclude=q)
+        for j, i in enumerate(q):
+            d2 = np.sort(ball_min_d2(pos, pos[i], period)[rows[j]])
+            want = np.full(kf, 1e32)
+            got = d2[drop:kf + drop]
+            want[:len(got)] = got
+            assert np.array_equal(want, X["nn%s_d2_%s" % (name, tag)][i])
+            assert np.all(X["nn%s_ids_%s" % (name, tag)][i][len(got):] == -1)
