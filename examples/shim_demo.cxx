@@ -136,6 +136,21 @@ int main() {
             }
             for (Int_t i = 0; i < N; i++) parts[i].SetType(0);
         }
+        // smoothed velocity field: with densities set, the mean velocity of a particle is a weighted mean of its neighbours'
+        {
+            tree.CalcDensity(32);
+            Coordinate* sv = tree.CalcSmoothVel(32);
+            Matrix* sd = tree.CalcSmoothVelDisp(sv, 32);
+            double tr = 0;
+            for (Int_t i = 0; i < N; i += 997) {
+                for (int j = 0; j < 3; j++) if (!(std::fabs(sv[i][j]) < 50.0) || !(sd[i](j, j) >= 0)) bad++;
+                if (std::fabs(sd[i](0, 1) - sd[i](1, 0)) > 1e-9 * (sd[i](0, 0) + sd[i](1, 1) + 1e-30)) bad++;
+                tr += sd[i](0, 0) + sd[i](1, 1) + sd[i](2, 2);
+            }
+            printf("smoothed velocity dispersion: mean trace %.4g\n", tr / ((N + 996) / 997));
+            if (!(tr > 0)) bad++;
+            delete[] sv; delete[] sd;
+        }
         printf("single-target density vs CalcSmoothLocalValue: worst relative difference %.3g\n", worst);
         if (!(worst < 1e-12)) bad++;
         long leaves = 0, count = 0;

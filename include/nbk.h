@@ -184,6 +184,15 @@ int nbk_calc_veldensity_particles(nbk_tree* t, int nsmooth, int nsearch, int64_t
 int nbk_calc_density_points(nbk_tree* t, int nsmooth, int64_t m, const double* x, double* rho, int flags);
 int nbk_calc_veldensity_points(nbk_tree* t, int nsmooth, int nsearch, int64_t m, const double* x, const double* v, double* rho, int flags);
 
+/* Replace KDTree::CalcSmoothVel(Nsmooth, densityset) and KDTree::CalcSmoothVelDisp(smvel, Nsmooth, densityset, meanvelset)
+ * (KDCalcSmoothQuantities.cxx:480-614): kernel-smoothed mean velocity (n x 3) and velocity dispersion tensor (n x 9, row-major
+ * 3x3) of every particle, symmetric gather + scatter like CalcDensity with weights 0.5 W(r_ij, h_i) m / rho of the
+ * contributing particle; the dispersion is taken about the receiving particle's smoothed mean velocity.
+ * rho: the particles' densities (n, what CalcDensity left in Particle::rho); NULL = compute CalcDensity(nsmooth) first (the
+ * reference's densityset != 1).  smvel: the result of nbk_calc_smooth_vel.  All arrays by ID (tree order with NBK_TREE_ORDER). */
+int nbk_calc_smooth_vel(nbk_tree* t, int nsmooth, const double* rho, double* smvel, int flags);
+int nbk_calc_smooth_veldisp(nbk_tree* t, int nsmooth, const double* rho, const double* smvel, double* smveldisp, int flags);
+
 /* Optional FOF by-products in tree-index space (reference KDFOF.cxx:52-55: pHead,pNext,pTail,pLen).
  * Any pointer may be NULL.  head/next/tail have n entries: the members of a group are chained in ascending tree
  * index (head[i] = first member, next[i] = following member or -1, tail[i] = last member; a particle outside any

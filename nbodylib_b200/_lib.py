@@ -42,7 +42,7 @@ EXPORTS = [
     "nbk_fof_criterion", "nbk_fof_criterion_basis", "nbk_attach_halo", "nbk_device_arrays", "nbk_release_cached_memory",
     "nbk_search_criterion_particles", "nbk_search_criterion_points", "nbk_calc_density_particles",
     "nbk_calc_veldensity_particles", "nbk_calc_density_points", "nbk_calc_veldensity_points",
-    "nbk_knn_filtered_particles", "nbk_knn_filtered_points",
+    "nbk_knn_filtered_particles", "nbk_knn_filtered_points", "nbk_calc_smooth_vel", "nbk_calc_smooth_veldisp",
 ]
 
 _lib = None
@@ -70,6 +70,8 @@ def load():
     L.nbk_knn_points.argtypes = [vp, i32, i64, vp, vp, vp, i32]
     L.nbk_knn_filtered_particles.argtypes = [vp, i32, i64, i64, i32, vp, vp, vp, vp, i32]
     L.nbk_knn_filtered_points.argtypes = [vp, i32, i64, vp, vp, i32, vp, vp, vp, vp, i32]
+    L.nbk_calc_smooth_vel.argtypes = [vp, i32, vp, vp, i32]
+    L.nbk_calc_smooth_veldisp.argtypes = [vp, i32, vp, vp, vp, i32]
     L.nbk_ball_particles.argtypes = [vp, dbl, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]
     L.nbk_ball_points.argtypes = [vp, dbl, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]
     L.nbk_search_criterion_particles.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]

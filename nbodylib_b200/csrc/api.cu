@@ -78,6 +78,19 @@ __global__ void gather_u8_kernel(int64_t n, const int32_t* order, const uint8_t*
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[order[i]];
 }
+// per-particle rows of w doubles: caller order (by ID) <-> tree order
+__global__ void gather_rows_f64_kernel(int64_t n, int w, const int32_t* order, const double* src_by_id, double* dst_tree) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * w) return;
+    int64_t p = i / w; int c = (int)(i - p * w);
+    dst_tree[i] = src_by_id[(int64_t)order[p] * w + c];
+}
+__global__ void scatter_rows_f64_kernel(int64_t n, int w, const int32_t* order, const double* src_tree, double* dst_by_id) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * w) return;
+    int64_t p = i / w; int c = (int)(i - p * w);
+    dst_by_id[(int64_t)order[p] * w + c] = src_tree[i];
+}
 __global__ void check_indices_kernel(int64_t m, const int32_t* q, int32_t n, int* bad) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m && (q[i] < 0 || q[i] >= n)) *bad = 1;
@@ -724,6 +737,81 @@ int nbk_smoothing_scale(nbk_tree* t, int nsmooth, double* hsm, int flags) {
     NBK_API_BEGIN
     NBK_REQUIRE(t && hsm, NBK_ERR_ARG, "nbk_smoothing_scale: null argument");
     smooth_call(t, nsmooth, 0, nullptr, hsm, flags);
+    NBK_API_END
+}
+
+// CalcSmoothVel / CalcSmoothVelDisp: rows of `width` doubles per particle (3: mean velocity, 9: dispersion tensor)
+static void smooth_moments_call(nbk_tree* t, int k, const double* rho, const double* smvel, double* out, int width, int flags) {
+    require_knn_tree(t);
+    require_no_halo(t, "CalcSmoothVel*");
+    NBK_REQUIRE(t->treetype == NBK_TPHYS, NBK_ERR_UNSUPPORTED, "CalcSmoothVel* need a physical tree");      // KDCalcSmoothQuantities.cxx:488-491
+    NBK_REQUIRE(t->sec != nullptr, NBK_ERR_ARG, "CalcSmoothVel* need velocities");
+    NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
+    NBK_REQUIRE(out && (width == 3 || smvel), NBK_ERR_ARG, "CalcSmoothVel*: null argument");
+    DeviceGuard guard(t->device, t->stream);
+    const int64_t n = t->n;
+    const bool dev = flags & NBK_DEVICE_PTRS, tree_order = flags & NBK_TREE_ORDER;
+    const int tb = 256;
+    // inputs -> device, tree order
+    auto stage_rows = [&](const double* src, int w, DevBuf<double>& hostcopy, DevBuf<double>& tree) -> const double* {
+        const double* d = src;
+        if (!dev) {
+            hostcopy.alloc((size_t)n * w);
+            NBK_CHECK(cudaMemcpyAsync(hostcopy.p, src, sizeof(double) * n * w, cudaMemcpyHostToDevice, t->stream));
+            d = hostcopy.p;
+        }
+        if (tree_order) return d;
+        tree.alloc((size_t)n * w);
+        gather_rows_f64_kernel<<<div_up(n * w, tb), tb, 0, t->stream>>>(n, w, t->order, d, tree.p);
+        return tree.p;
+    };
+    DevBuf<double> rho_h, rho_t, sv_h, sv_t, acc((size_t)n * width), out_id;
+    KnnArgs a;
+    a.k = k; a.mode = 0; a.q0 = 0; a.q1 = n; a.periodic = false;      // quirk Q2
+    CallTimer tm(*t);
+    t->last_launches = 0;
+    if (rho) a.rho_in = stage_rows(rho, 1, rho_h, rho_t);
+    else {
+        // densityset != 1: the reference calls CalcDensity(Nsmooth) first (KDCalcSmoothQuantities.cxx:492)
+        rho_t.alloc(n);
+        NBK_CHECK(cudaMemsetAsync(rho_t.p, 0, rho_t.bytes(), t->stream));
+        KnnArgs d = a;
+        d.rho = rho_t.p;
+        launch_knn(*t, d);
+        a.rho_in = rho_t.p;
+    }
+    if (width == 9) a.smvel_in = stage_rows(smvel, 3, sv_h, sv_t);
+    NBK_CHECK(cudaMemsetAsync(acc.p, 0, acc.bytes(), t->stream));
+    if (width == 3) a.smvel_out = acc.p; else a.smdisp_out = acc.p;
+    const int64_t before = t->last_launches;
+    launch_knn(*t, a);
+    t->last_launches += before;
+    tm.stop();
+    t->last_kernel_ms = t->last_call_ms;
+    const double* res = acc.p;
+    if (!tree_order) {
+        if (dev) { scatter_rows_f64_kernel<<<div_up(n * width, tb), tb, 0, t->stream>>>(n, width, t->order, acc.p, out); res = nullptr; }
+        else {
+            out_id.alloc((size_t)n * width);
+            scatter_rows_f64_kernel<<<div_up(n * width, tb), tb, 0, t->stream>>>(n, width, t->order, acc.p, out_id.p);
+            res = out_id.p;
+        }
+    }
+    if (res) NBK_CHECK(cudaMemcpyAsync(out, res, sizeof(double) * n * width, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
+    NBK_CHECK(cudaStreamSynchronize(t->stream));
+    NBK_CHECK(cudaGetLastError());
+}
+
+int nbk_calc_smooth_vel(nbk_tree* t, int nsmooth, const double* rho, double* smvel, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && smvel, NBK_ERR_ARG, "nbk_calc_smooth_vel: null argument");
+    smooth_moments_call(t, nsmooth, rho, nullptr, smvel, 3, flags);
+    NBK_API_END
+}
+int nbk_calc_smooth_veldisp(nbk_tree* t, int nsmooth, const double* rho, const double* smvel, double* smveldisp, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && smvel && smveldisp, NBK_ERR_ARG, "nbk_calc_smooth_veldisp: null argument");
+    smooth_moments_call(t, nsmooth, rho, smvel, smveldisp, 9, flags);
     NBK_API_END
 }
 

@@ -65,6 +65,8 @@ struct KnnParams {
     // filtered search (FindNearestCheck / FindNearestCriterion): candidates must have cand_excl[c] == 0 and / or meet the
     // criterion crit_mode (0: none, 2: FOF3d, 4: FOF6d; crit_linked in traverse.cuh) relative to the query
     const int32_t* cand_excl; int crit_mode; double cp0, cp1;
+    // smoothed velocity moments (CalcSmoothVel / CalcSmoothVelDisp): densities in, accumulators out, all tree order
+    const double* rho_in; const double* smvel_in; double* smvel_out; double* smdisp_out;
 };
 
 // ================================================================================================ exact
@@ -300,6 +302,44 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
             atomicAdd(&prm.rho[id], Wij * mi);
         }
         atomicAdd(&prm.rho[qi], acc);
+    }
+    if (prm.smvel_out || prm.smdisp_out) {
+        // CalcSmoothVel / CalcSmoothVelDisp (KDCalcSmoothQuantities.cxx:480-614): symmetric gather + scatter with weights
+        // 0.5 * W(r_ij, h_i) * m / rho of the CONTRIBUTING particle; the dispersion is taken about the smoothed mean velocity
+        // of the RECEIVING particle (:594-611)
+        const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
+        const double hi = 0.5 * sqrt(v.top);
+        const double norm = 1.0 / pow(hi, 3.0);
+        const double delta = 2.0 / (double)(prm.kernres - 1);
+        const Vec4<S> vq4 = V[qi];
+        const double vi[3] = {(double)vq4.x, (double)vq4.y, (double)vq4.z};
+        const double wi = prm.mass[qi] / prm.rho_in[qi];        // temp = Wij / rho * m, evaluated as Wij * (m / rho): one extra rounding
+        double mi[3] = {0, 0, 0};
+        if (prm.smdisp_out) { mi[0] = prm.smvel_in[3 * qi]; mi[1] = prm.smvel_in[3 * qi + 1]; mi[2] = prm.smvel_in[3 * qi + 2]; }
+        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < kc; s++) {
+            int id = v.hp.i(s);
+            if (id < 0) continue;
+            double rij = sqrt(v.hp.h(s));
+            double r = rij / hi;
+            double Wij = 0.5 * wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+            const Vec4<S> vj4 = V[id];
+            const double vj[3] = {(double)vj4.x, (double)vj4.y, (double)vj4.z};
+            const double tj = Wij * (prm.mass[id] / prm.rho_in[id]);
+            const double ti = Wij * wi;
+            if (prm.smvel_out) {
+                for (int a = 0; a < 3; a++) { acc[a] += tj * vj[a]; atomicAdd(&prm.smvel_out[3 * (int64_t)id + a], ti * vi[a]); }
+            } else {
+                const double mj[3] = {prm.smvel_in[3 * (int64_t)id], prm.smvel_in[3 * (int64_t)id + 1], prm.smvel_in[3 * (int64_t)id + 2]};
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++) {
+                        acc[3 * a + b] += tj * (vj[a] - mi[a]) * (vj[b] - mi[b]);
+                        atomicAdd(&prm.smdisp_out[9 * (int64_t)id + 3 * a + b], ti * (vi[a] - mj[a]) * (vi[b] - mj[b]));
+                    }
+            }
+        }
+        if (prm.smvel_out) { for (int a = 0; a < 3; a++) atomicAdd(&prm.smvel_out[3 * qi + a], acc[a]); }
+        else { for (int a = 0; a < 9; a++) atomicAdd(&prm.smdisp_out[9 * qi + a], acc[a]); }
     }
     if (prm.rho && prm.veldens_k > 0) {
         // R2: CalcVelDensity (KDCalcSmoothQuantities.cxx:335-383); the *Particle / *Position forms (:845-921, :1150-1207)
@@ -1192,6 +1232,7 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.qlist = a.qlist; p.nq = a.nq;
     p.gather = a.gather ? 1 : 0; p.vq = a.vq;
     p.cand_excl = a.cand_excl; p.crit_mode = a.crit_mode; p.cp0 = a.cp0; p.cp1 = a.cp1;
+    p.rho_in = a.rho_in; p.smvel_in = a.smvel_in; p.smvel_out = a.smvel_out; p.smdisp_out = a.smdisp_out;
     p.k = a.k;
     p.periodic = a.periodic; p.strict = a.strict; p.tree_form = a.tree_form;
     for (int d = 0; d < 3; d++) p.period[d] = t.period[d];
@@ -1228,7 +1269,12 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     t.last_launches = 0;
     t.last_flagged = 0;
     if (a.crit_mode == 4) NBK_REQUIRE(p.V != nullptr && (a.mode == 0 || a.vq != nullptr), NBK_ERR_ARG, "FOF6d-filtered search needs velocities");
-    const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm) && !a.gather && !a.qlist && !a.cand_excl && !a.crit_mode;
+    if (a.smvel_out || a.smdisp_out) {
+        NBK_REQUIRE(a.mode == 0 && !a.qlist && a.rho_in && p.V, NBK_ERR_ARG, "smoothed velocity moments need particle queries, densities and velocities");
+        NBK_REQUIRE(!a.smdisp_out || a.smvel_in, NBK_ERR_ARG, "CalcSmoothVelDisp needs the smoothed mean velocities");
+    }
+    const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm) && !a.gather && !a.qlist && !a.cand_excl && !a.crit_mode &&
+                             !a.smvel_out && !a.smdisp_out;
     if (smooth_only && getenv("NBK_KNN_EXACT_ONLY") == nullptr) {
         // ---- fast path + exact fallback for the flagged queries ----------------------------------------------
         p.kcap = a.k + 1;

@@ -89,6 +89,11 @@ struct KnnArgs {
     const int32_t* cand_excl = nullptr;  // device, tree order: non-zero => never a neighbour
     int crit_mode = 0;                   // 0 none, 2 FOF3d, 4 FOF6d (predicate codes of FofArgs::mode)
     double cp0 = 0, cp1 = 0;
+    // CalcSmoothVel / CalcSmoothVelDisp (KDCalcSmoothQuantities.cxx:480-614); device, tree order, accumulators pre-zeroed
+    const double* rho_in = nullptr;      // densities (n)
+    const double* smvel_in = nullptr;    // smoothed mean velocities (n x 3), input of the dispersion
+    double* smvel_out = nullptr;         // n x 3
+    double* smdisp_out = nullptr;        // n x 9 (row-major 3x3)
 };
 void launch_knn(nbk_tree& t, const KnnArgs& a);
 

@@ -394,6 +394,23 @@ class KDTree:
             value += w * norm * weight[j]
         return value
 
+    def CalcSmoothVel(self, Nsmooth=64, rho=None):
+        """KDTree::CalcSmoothVel(Nsmooth, densityset) (KDCalcSmoothQuantities.cxx:480-541): smoothed mean velocity of every
+        particle, (n, 3) by ID.  rho = the particles' densities by ID (None: CalcDensity(Nsmooth) is computed first)."""
+        r = None if rho is None else np.ascontiguousarray(rho, dtype=np.float64)
+        out = np.empty((self.n, 3))
+        L.check(self._lib.nbk_calc_smooth_vel(self._h, int(Nsmooth), _ptr(r), _ptr(out), 0))
+        return out
+
+    def CalcSmoothVelDisp(self, smvel, Nsmooth=64, rho=None):
+        """KDTree::CalcSmoothVelDisp(smvel, Nsmooth, densityset) (KDCalcSmoothQuantities.cxx:542-614): (n, 3, 3) by ID."""
+        r = None if rho is None else np.ascontiguousarray(rho, dtype=np.float64)
+        sv = np.ascontiguousarray(smvel, dtype=np.float64)
+        assert sv.shape == (self.n, 3)
+        out = np.empty((self.n, 3, 3))
+        L.check(self._lib.nbk_calc_smooth_veldisp(self._h, int(Nsmooth), _ptr(r), _ptr(sv), _ptr(out), 0))
+        return out
+
     def CalcSmoothingScale(self, Nsmooth=64):
         """hi = 0.5*sqrt(d2 of the Nsmooth-th neighbour) (KDCalcSmoothQuantities.cxx:260)."""
         h = np.empty(self.n)

@@ -9,7 +9,8 @@
  *    SearchBallPosTagged (Int_t tt | Double_t* x | Coordinate; array and vector forms), dense SearchBall / SearchBallPos
  *    SearchCriterionTagged (Int_t tt | Particle&; array and vector forms), dense SearchCriterion (FOF3d / FOF6d)
  *    CalcDensity, CalcVelDensity, CalcSmoothingScale (new: north star), CalcDensityParticle, CalcVelDensityParticle,
- *    CalcDensityPosition, CalcVelDensityPosition, CalcSmoothLocalValue
+ *    CalcDensityPosition, CalcVelDensityPosition, CalcSmoothLocalValue, CalcSmoothVel, CalcSmoothVelDisp
+ *    FindNearestCheck, FindNearestCriterion (Int_t tt | Particle | Coordinate)
  *    FOF, FOFCriterion, FOFCriterionSetBasisForLinks (FOF3d / FOF6d), GetRoot / FindLeafNode (host mirror of the node arrays)
  *    OverWriteInputOrder, SetResetOrder, ~KDTree (restores the caller's particle order)
  *
@@ -18,7 +19,7 @@
  *  FOF results are new[]-allocated arrays indexed by ID that the caller delete[]s; the destructor sorts the array
  *  back by ID unless OverWriteInputOrder() was called (KDTree.cxx:1340-1362).
  *  Differences: errors throw std::runtime_error instead of printf+exit; calls without a device implementation
- *  (TPROJ/TMETRIC trees, host FOFcompfunc callbacks other than FOF3d/FOF6d, CalcSmoothVel*, FOFNN*) throw -- there is
+ *  (TPROJ/TMETRIC trees, host FOFcompfunc callbacks other than FOF3d/FOF6d, CalcSmoothVelSkew/Kurtosis, FOFNN*) are absent or throw -- there is
  *  no CPU fallback.  Per-particle calls launch one small kernel each; loops over all particles should use the
  *  whole-system forms.
  */
@@ -379,6 +380,35 @@ public:
         check(nbk_smoothing_scale(h, (int)Nsmooth, hs.data(), 0));
         Double_t* out = new Double_t[numparts];
         for (Int_t i = 0; i < numparts; i++) out[i] = hs[i];
+        return out;
+    }
+
+    /// KDCalcSmoothQuantities.cxx:480-614: smoothed mean velocity / velocity dispersion tensor of every particle, new[] arrays
+    /// indexed by particle ID that the caller delete[]s.  densityset != 1 recomputes the densities first (and stores them in the
+    /// particles like the reference's CalcDensity call does); meanvelset != 1 recomputes smvel (the argument is then ignored).
+    Coordinate* CalcSmoothVel(Int_t Nsmooth = 64, int densityset = 1) {
+        if (densityset != 1) CalcDensity(Nsmooth);
+        std::vector<double> rho(numparts), sv((size_t)3 * numparts);
+        for (Int_t i = 0; i < numparts; i++) rho[i] = bucket[i].GetDensity();                 // tree order
+        check(nbk_calc_smooth_vel(h, (int)Nsmooth, rho.data(), sv.data(), NBK_TREE_ORDER));
+        Coordinate* out = new Coordinate[numparts];
+        for (Int_t i = 0; i < numparts; i++) { Coordinate& c = out[bucket[i].GetID()]; for (int j = 0; j < 3; j++) c[j] = sv[(size_t)3 * i + j]; }
+        return out;
+    }
+    Matrix* CalcSmoothVelDisp(Coordinate* smvel, Int_t Nsmooth = 64, int densityset = 1, int meanvelset = 1) {
+        if (densityset != 1) CalcDensity(Nsmooth);
+        Coordinate* own = NULL;
+        if (meanvelset != 1 || smvel == NULL) smvel = own = CalcSmoothVel(Nsmooth);
+        std::vector<double> rho(numparts), sv((size_t)3 * numparts), sd((size_t)9 * numparts);
+        for (Int_t i = 0; i < numparts; i++) {
+            rho[i] = bucket[i].GetDensity();
+            const Coordinate& c = smvel[bucket[i].GetID()];
+            for (int j = 0; j < 3; j++) sv[(size_t)3 * i + j] = c[j];
+        }
+        if (own) delete[] own;
+        check(nbk_calc_smooth_veldisp(h, (int)Nsmooth, rho.data(), sv.data(), sd.data(), NBK_TREE_ORDER));
+        Matrix* out = new Matrix[numparts];
+        for (Int_t i = 0; i < numparts; i++) { Matrix& mm = out[bucket[i].GetID()]; for (int j = 0; j < 3; j++) for (int l = 0; l < 3; l++) mm(j, l) = sd[(size_t)9 * i + 3 * j + l]; }
         return out;
     }
 

@@ -32,6 +32,15 @@ public:
     const Double_t* GetCoord() const { return c; }
 };
 
+/// 3x3 matrix with the element access of the reference's Math::Matrix (Matrix.h): the return type of CalcSmoothVelDisp
+class Matrix {
+    Double_t m[3][3];
+public:
+    Matrix(Double_t a = 0) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m[i][j] = a; }
+    Double_t& operator()(int i, int j) { return m[i][j]; }
+    const Double_t& operator()(int i, int j) const { return m[i][j]; }
+};
+
 class Particle {
 protected:
     Double_t mass;

@@ -189,6 +189,7 @@ class Ref:
             L.ref_dump_cuts.restype = C.c_long
             L.ref_dump_cuts.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, C.c_long]
             L.ref_knn_filtered.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_long, C.c_long, C.c_long, _dp, _dp, _ip, _dp]
+            L.ref_calc_smooth_vel.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
             L.ref_max_threads.restype = C.c_int
             L.ref_sizeof_particle.restype = C.c_int
             cls._lib = L
@@ -378,6 +379,12 @@ class Ref:
         d2 = np.zeros((rows, k))
         self.lib().ref_knn_filtered(self.h, crit, _d(pr), k, q0, q1, rows, _d(x), _d(v), _i(ids), _d(d2))
         return ids, d2
+
+    def calc_smooth_vel(self, k):
+        """CalcDensity(k), CalcSmoothVel(k), CalcSmoothVelDisp(smvel, k): (rho, smvel (n,3), smdisp (n,3,3)) by ID"""
+        rho, sv, sd = np.zeros(self.n), np.zeros((self.n, 3)), np.zeros((self.n, 3, 3))
+        self.lib().ref_calc_smooth_vel(self.h, k, _d(rho), _d(sv), _d(sd))
+        return rho, sv, sd
 
     def dump_cuts(self):
         cap = self.n + 64

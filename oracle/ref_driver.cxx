@@ -512,4 +512,20 @@ void ref_knn_filtered(void* hv, int crit, double* params, int k, long q0, long q
     }
 }
 
+/* CalcDensity(k) followed by CalcSmoothVel(k) and CalcSmoothVelDisp(smvel, k) (KDCalcSmoothQuantities.cxx:480-614); outputs by ID:
+ * rho[n], smvel[n][3], smdisp[n][9] (row-major) */
+void ref_calc_smooth_vel(void* hv, int k, double* rho_by_id, double* smvel_by_id, double* smdisp_by_id) {
+    RefTree* h = (RefTree*)hv;
+    h->tree->CalcDensity(k);
+    for (Int_t i = 0; i < h->n; i++) rho_by_id[h->parts[i].GetID()] = h->parts[i].GetDensity();
+    Coordinate* sv = h->tree->CalcSmoothVel(k, 1);
+    for (Int_t i = 0; i < h->n; i++) for (int j = 0; j < 3; j++) smvel_by_id[3 * i + j] = sv[i][j];
+    if (smdisp_by_id) {
+        Matrix* sd = h->tree->CalcSmoothVelDisp(sv, k, 1, 1);
+        for (Int_t i = 0; i < h->n; i++) for (int j = 0; j < 3; j++) for (int l = 0; l < 3; l++) smdisp_by_id[9 * i + 3 * j + l] = sd[i](j, l);
+        delete[] sd;
+    }
+    delete[] sv;
+}
+
 }  // extern "C"

@@ -73,6 +73,7 @@ for tag, period in (("np", None), ("p", np.ones(3))):
         R.search_criterion_dense(int(q), 2, params, j + 1, nn, d2)
     out["dense_c6_nn_" + tag], out["dense_c6_d2_" + tag] = nn.copy(), d2.copy()
     if tag == "np":
+        out["sm_rho"], out["sm_vel"], out["sm_disp"] = R.calc_smooth_vel(k)
         ids, d2k = R.knn_particles(k)
         dist = np.sqrt(d2k[7][::-1]).copy()
         w = mass2[ids[7][::-1]].copy()

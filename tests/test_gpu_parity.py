@@ -687,3 +687,19 @@ def test_golden_filtered_knn(nb, G, X, tag):
         with pytest.raises(nb.NbkError) as e:
             t.FindNearestCriterion(nb.FOFVEL, G["params"], kf)
         assert e.value.code == -3
+
+
+def test_golden_smoothed_velocity_moments(nb, G, X):
+    """CalcSmoothVel / CalcSmoothVelDisp against the reference (fp64 atomics: only the summation order differs)"""
+    k = int(G["k"])
+    with nb.KDTree(G["pos"], G["vel"], X["mass2"]) as t:
+        rho = t.CalcDensity(k)
+        np.testing.assert_allclose(rho, X["sm_rho"], rtol=RTOL_RHO)
+        sv = t.CalcSmoothVel(k, rho=X["sm_rho"])
+        np.testing.assert_allclose(sv, X["sm_vel"], rtol=0, atol=1e-11 * np.abs(X["sm_vel"]).max())
+        sd = t.CalcSmoothVelDisp(X["sm_vel"], k, rho=X["sm_rho"])
+        np.testing.assert_allclose(sd, X["sm_disp"], rtol=0, atol=1e-11 * np.abs(X["sm_disp"]).max())
+        np.testing.assert_allclose(sd, np.transpose(sd, (0, 2, 1)), rtol=0, atol=1e-12 * np.abs(sd).max())
+        # densityset != 1: the density is computed first
+        sv2 = t.CalcSmoothVel(k)
+        np.testing.assert_allclose(sv2, X["sm_vel"], rtol=0, atol=1e-9 * np.abs(X["sm_vel"]).max())

@@ -345,3 +345,26 @@ def test_filtered_knn_restatement(G, X, tag):
             want[:len(got)] = got
             assert np.array_equal(want, X["nn%s_d2_%s" % (name, tag)][i])
             assert np.all(X["nn%s_ids_%s" % (name, tag)][i][len(got):] == -1)
+
+
+def test_smoothed_velocity_moments_restatement(port, G, X):
+    """CalcSmoothVel / CalcSmoothVelDisp of the reference (KDCalcSmoothQuantities.cxx:480-614) == symmetric gather + scatter
+    with weights 0.5 W(r_ij, h_i) m / rho of the contributing particle; dispersion about the receiver's smoothed mean."""
+    from tests.util import wsm_table
+    _, kern = port.kernel_table(3, 2, 1000)
+    ids, d2, k = G["knn0_ids_np"], G["knn0_d2_np"], int(G["k"])
+    n, rho, m, vel = len(ids), X["sm_rho"], X["mass2"], G["vel"]
+    hi = 0.5 * np.sqrt(d2[:, -1])
+    W = np.array([[0.5 * wsm_table(kern, np.sqrt(d2[i, j]) / hi[i]) / hi[i] ** 3 for j in range(k)] for i in range(n)])
+    sv, sd = np.zeros((n, 3)), np.zeros((n, 3, 3))
+    ii = np.repeat(np.arange(n), k)
+    jj = ids.ravel()
+    w = W.ravel()
+    np.add.at(sv, ii, (w / rho[jj] * m[jj])[:, None] * vel[jj])
+    np.add.at(sv, jj, (w / rho[ii] * m[ii])[:, None] * vel[ii])
+    np.testing.assert_allclose(sv, X["sm_vel"], rtol=0, atol=1e-12 * np.abs(X["sm_vel"]).max())
+    a = vel[jj] - X["sm_vel"][ii]
+    b = vel[ii] - X["sm_vel"][jj]
+    np.add.at(sd, ii, (w / rho[jj] * m[jj])[:, None, None] * a[:, :, None] * a[:, None, :])
+    np.add.at(sd, jj, (w / rho[ii] * m[ii])[:, None, None] * b[:, :, None] * b[:, None, :])
+    np.testing.assert_allclose(sd, X["sm_disp"], rtol=0, atol=1e-12 * np.abs(X["sm_disp"]).max())
