@@ -57,12 +57,10 @@ struct BallVisitor {
             }
             __syncwarp();
             if (!on) continue;
-            const bool wv = crit_needs_vel(mode);
             for (int j = 0; j < m; j++) {
                 int c = start + base + j;
                 if (c == self) continue;
-                if (crit_linked(mode, p0, p1, qx, qy, qz, vx, vy, vz, tile[j], tile[32 + j], tile[64 + j],
-                                wv ? tile[96 + j] : 0.0, wv ? tile[128 + j] : 0.0, wv ? tile[160 + j] : 0.0)) {
+                if (crit_linked(mode, p0, p1, qx, qy, qz, vx, vy, vz, tile, j)) {
                     if (FILL) {
                         if ((int64_t)count < cap) {
                             idx[count] = out_ids ? order[c] : c;

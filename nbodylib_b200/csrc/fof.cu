@@ -65,11 +65,7 @@ struct FofVisitor {
 
     __device__ __forceinline__ bool need(float lb) const { return lb < prune_f; }
 
-    __device__ __forceinline__ bool linked(int j) const {
-        const bool wv = crit_needs_vel(mode);
-        return crit_linked(mode, p0, p1, qx, qy, qz, vx, vy, vz, tile[j], tile[32 + j], tile[64 + j],
-                           wv ? tile[96 + j] : 0.0, wv ? tile[128 + j] : 0.0, wv ? tile[160 + j] : 0.0);
-    }
+    __device__ __forceinline__ bool linked(int j) const { return crit_linked(mode, p0, p1, qx, qy, qz, vx, vy, vz, tile, j); }
 
     __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
         for (int base = 0; base < cnt; base += 32) {

@@ -152,11 +152,7 @@ struct KnnVisitor {
                     // KDLeafNode.cxx:88-118,202-246: i != target, 0 < d2 < top, check(bucket[i]) == 0 / cmp(target, bucket[i]) == 1
                     ok = ok && (start + base + j != self) && d2 > 0.0;
                     if (ok && excl) ok = excl[start + base + j] == 0;
-                    if (ok && crit_mode) {
-                        const bool wv = crit_mode == 4;
-                        ok = crit_linked(crit_mode, cp0, cp1, qx, qy, qz, vx, vy, vz, tile[j], tile[32 + j], tile[64 + j],
-                                         wv ? tile[96 + j] : 0.0, wv ? tile[128 + j] : 0.0, wv ? tile[160 + j] : 0.0);
-                    }
+                    if (ok && crit_mode) ok = crit_linked(crit_mode, cp0, cp1, qx, qy, qz, vx, vy, vz, tile, j);
                 }
                 acc |= (ok ? 1u : 0u) << j;
             }
@@ -1089,7 +1085,7 @@ static inline size_t sl_warp_bytes(int k, bool want_doubles, int tile_bytes) {
     return region + tile_bytes + TRAV_STACK * 4;
 }
 
-template <class S, int MB>
+template <class S, int MB, bool HALO>
 __global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams prm, int want_doubles, int* __restrict__ work_counter,
                                                                 int32_t* __restrict__ logbuf, int logcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1154,7 +1150,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams pr
             for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p));
             v.settop(v.hp.rootkey());
             traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
-            if (prm.nlo2) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);
+            if (HALO) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);     // attached halo tree: its own instantiation,
+                                                                                          // the second inlined walk costs the plain kernel 3 %
             key_kp1 = v.hp.rootkey();
             v.hp.sift(0, 0.f);
             key_k = v.hp.rootkey();
@@ -1214,7 +1211,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams pr
             const double thrd_keep = c2.thr_d;
             if (!overflowed) { c2.thr = -1.f; c2.thr_d = -1.0; c2.limf = -1.f; }      // the other lanes are complete
             traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, overflowed);
-            if (prm.nlo2) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, c2, qb, overflowed);
+            if (HALO) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, c2, qb, overflowed);
             c2.thr = thr_keep; c2.limf = limf_keep; c2.thr_d = thrd_keep;
         }
         if (collecting) sc_epilogue<S>(prm, P, c2.L, base, lane, k, c2.cnt, short_of_k ? KNN_SENTINEL : c2.d2max, x0, y0, z0, qi);
@@ -1318,6 +1315,7 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             NBK_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), t.stream));
             p.flag_count = counters.p; p.flag_list = flist.p;
             bool window = false;
+            size_t old_persist_limit = 0;
             auto go = [&](auto kern) {
                 NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 NBK_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KNN_WARPS * 32, smem));
@@ -1334,6 +1332,7 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
                     if (max_persist > 0 && max_window > 0) {
                         size_t bytes = logbuf.bytes();
                         size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+                        cudaDeviceGetLimit(&old_persist_limit, cudaLimitPersistingL2CacheSize);
                         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
                         cudaStreamAttrValue av;
                         memset(&av, 0, sizeof(av));
@@ -1355,9 +1354,11 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
                 }
             };
             if (t.store_bytes == 4) {
-                if (mb == 8) go(knn_sl_kernel<float, 8>); else if (mb == 6) go(knn_sl_kernel<float, 6>); else go(knn_sl_kernel<float, 5>);
+                if (t.nlo2) { if (mb == 8) go(knn_sl_kernel<float, 8, true>); else if (mb == 6) go(knn_sl_kernel<float, 6, true>); else go(knn_sl_kernel<float, 5, true>); }
+                else if (mb == 8) go(knn_sl_kernel<float, 8, false>); else if (mb == 6) go(knn_sl_kernel<float, 6, false>); else go(knn_sl_kernel<float, 5, false>);
             } else {
-                if (mb == 8) go(knn_sl_kernel<double, 8>); else if (mb == 6) go(knn_sl_kernel<double, 6>); else go(knn_sl_kernel<double, 5>);
+                if (t.nlo2) { if (mb == 8) go(knn_sl_kernel<double, 8, true>); else if (mb == 6) go(knn_sl_kernel<double, 6, true>); else go(knn_sl_kernel<double, 5, true>); }
+                else if (mb == 8) go(knn_sl_kernel<double, 8, false>); else if (mb == 6) go(knn_sl_kernel<double, 6, false>); else go(knn_sl_kernel<double, 5, false>);
             }
             NBK_CHECK(cudaGetLastError());
 #ifdef NBK_STATS
@@ -1376,7 +1377,12 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             int nflag = 0;
             NBK_CHECK(cudaMemcpyAsync(&nflag, counters.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
             NBK_CHECK(cudaStreamSynchronize(t.stream));
-            if (window) cudaCtxResetPersistingL2Cache();      // hand the set-aside lines back to the normal L2
+            if (window) {
+                // hand the set-aside lines back to the normal L2: the carve-out would otherwise stay in force for every later
+                // kernel of the process (builds and FOF lose ~2/3 of the L2 they stream their node / rank arrays through)
+                cudaCtxResetPersistingL2Cache();
+                if (getenv("NBK_KNN_KEEP_L2_LIMIT") == nullptr) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, old_persist_limit);
+            }
             t.last_flagged = nflag;
             if (nflag > 0) {
                 KnnParams pe = p;

@@ -47,9 +47,12 @@ __device__ __forceinline__ double dist2_ref(double ax, double ay, double az, dou
 //   mode 4  FOF6d              sum (dx*dx/p0 + dv*dv/p1), interleaved, < 1         FOFFunc.h:48-55
 // (mode 3, FOFVel, is not implemented: see DESIGN.md)
 __device__ __forceinline__ bool crit_needs_vel(int mode) { return mode == 1 || mode == 4; }
+// candidate j of a staged tile ([6][32] doubles: x, y, z, vx, vy, vz rows); velocities are read only by the 6D predicates
 __device__ __forceinline__ bool crit_linked(int mode, double p0, double p1, double qx, double qy, double qz, double vx, double vy, double vz,
-                                            double cx, double cy, double cz, double ux, double uy, double uz) {
+                                            const double* __restrict__ tile, int j) {
+    const double cx = tile[j], cy = tile[32 + j], cz = tile[64 + j];
     if (mode == 0) return dist2_ref(qx, qy, qz, cx, cy, cz) < p0;
+    const double ux = tile[96 + j], uy = tile[128 + j], uz = tile[160 + j];
     if (mode == 1) {
         double d = dist2_ref(qx, qy, qz, cx, cy, cz);
         d = __dadd_rn(d, dist2_ref(vx, vy, vz, ux, uy, uz));
