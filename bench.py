@@ -204,25 +204,29 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     kernel_ms, call_ms, launches = [], [], 0
     t0 = time.perf_counter()
+    # CUDA events on torch's current stream bracket the K steps.  The library works on its own stream, drains torch's
+    # stream before every call and synchronises its own before returning, so everything a step launches (library kernels,
+    # the sharded driver's torch ops and NCCL transfers) completes between the two records.
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     for _ in range(args.steps):
         step()
         i = tree.info
         kernel_ms.append(i.last_kernel_ms)
         call_ms.append(i.last_call_ms)
         launches += int(i.last_launches)
+    ev1.record()
     progress("timed steps done")
     barrier()
     wall = time.perf_counter() - t0
-    # device time of the timed region: the library times its own stream with CUDA events (last_call_ms); the wall
-    # clock above brackets the same region with synchronisation on both sides, max over ranks below.
-    tmax = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    tmax = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    wall = float(tmax.item())
+    dev_s, wall = float(tmax[0].item()), float(tmax[1].item())
     clocks = sampler.stop() if sampler else None
-    ms_step = wall * 1e3 / args.steps
-    value = n * world / (wall / args.steps)
+    ms_step = dev_s * 1e3 / args.steps
+    value = n * world / (dev_s / args.steps)
 
     # ---- other stages of the same resident tree (rank-local), each K steps ------------------------------------
     extra = {}
@@ -292,6 +296,28 @@ def main():
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------
     e2e = None
+    if not args.no_e2e and world > 1:
+        # every rank: pinned host arrays -> its GPU -> slab-sharded tree (halo exchange, local build) -> CalcDensity -> rho on the host
+        hp, hm = (x.cpu().pin_memory() for x in (pos, mass))
+        out = torch.empty(n, dtype=torch.float64).pin_memory()
+        del pos, vel, mass
+        ts = []
+        for it in range(1 + max(1, args.steps // 2)):
+            barrier(); t1 = time.perf_counter()
+            dp, dm = hp.to("cuda", non_blocking=True), hm.to("cuda", non_blocking=True)
+            st = ShardedTree(dp, None, dm, period=period, rank=rank, world=world)
+            r = st.CalcDensity(K_NN)
+            out.copy_(r)
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            st.close()
+            del st, dp, dm, r
+            if it > 0:
+                ts.append(float(tt.item()))
+        e2e = {"value": n * world / float(np.mean(ts)), "unit": "particles/s", "h2d_bytes_per_step": int((hp.numel() * hp.element_size() + hm.numel() * hm.element_size()) * world),
+               "d2h_bytes_per_step": int(out.numel() * 8 * world), "ms_per_step": float(np.mean(ts)) * 1e3,
+               "includes": "per rank: H2D of pos/mass (fp32, pinned host arrays), halo exchange, tree builds (owned + halo), CalcDensity(64) with scatter return, D2H of rho (fp64, pinned); max over ranks"}
     if not args.no_e2e and world == 1:
         hp, hv, hm = (x.cpu().pin_memory().numpy() for x in (pos, vel, mass))
         out = torch.empty(n, dtype=torch.float64).pin_memory().numpy()      # the caller's (pinned) result buffer
@@ -341,8 +367,8 @@ def main():
                          "note": "issue-slot bound tree traversal, not HBM bound: see DESIGN.md section 4; traffic = measured DRAM bytes of one launch (ncu), dominated by the insertion log",
                          "issue_active_pct_ncu": 65.7, "warp_instructions_per_particle_ncu": 2404,
                          "ncu_source": "profiles/r1_07_knn_select_log_512cube_k64.txt"},
-            "timer": "host clock around K steps, barrier + device synchronize on both sides, max over ranks; device_ms_per_step = the library's CUDA events around the same calls on its own stream",
-            "device_ms_per_step": float(np.mean(call_ms)),
+            "timer": "CUDA events around the K steps (barrier + device synchronize on both sides), max over ranks; wall_ms_per_step = host clock around the same region; library_ms_per_step = the library's own CUDA events around each call on its stream",
+            "wall_ms_per_step": wall * 1e3 / args.steps, "library_ms_per_step": float(np.mean(call_ms)),
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
