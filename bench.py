@@ -362,11 +362,11 @@ def main():
                        "particles_per_gpu": n, "k": K_NN, "storage": "fp32 coordinates (exact), fp64 distance arithmetic",
                        "l2": "inputs (%.1f GB) exceed L2, no flush needed" % (n * 16 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "knn_sl_kernel<float,6>", "kernel_ms": kms,
+                         "peak_source": peak_src, "kernel": "knn_sl_kernel<float,6,false>", "kernel_ms": kms,
                          "algorithmic_bytes_per_particle": ALG_BYTES["knn_density"],
                          "note": "issue-slot bound tree traversal, not HBM bound: see DESIGN.md section 4; traffic = measured DRAM bytes of one launch (ncu), dominated by the insertion log",
                          "issue_active_pct_ncu": 65.7, "warp_instructions_per_particle_ncu": 2404,
-                         "ncu_source": "profiles/r1_07_knn_select_log_512cube_k64.txt"},
+                         "ncu_source": "profiles/r1_07_knn_select_log_512cube_k64.txt (full capture of this kernel body), profiles/r1_09_launches_bench_512cube_final_summary.txt (launch list of this command)"},
             "timer": "CUDA events around the K steps (barrier + device synchronize on both sides), max over ranks; wall_ms_per_step = host clock around the same region; library_ms_per_step = the library's own CUDA events around each call on its stream",
             "wall_ms_per_step": wall * 1e3 / args.steps, "library_ms_per_step": float(np.mean(call_ms)),
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra,
