@@ -75,6 +75,18 @@ class ClockSampler:
         return out
 
 
+def workload_name(ng, nh):
+    return "clustered periodic box %d^3 per GPU (ZA lattice + %d Plummer halos), KDTree bucket=16, CalcDensity(%d): kNN + SPH density" % (ng, nh, K_NN)
+
+
+def sample_fraction(ng):
+    """side of the sub-cube the CPU legs work on: ~16.8 M particles (about 20 s of host work: build + kNN-density + FOF)"""
+    f = 1.0
+    while (ng * f) ** 3 > 1.7e7 and f > 1.0 / 64:
+        f *= 0.5
+    return f
+
+
 def sample_subvolume(pos, vel, mass, frac_side=0.25):
     """bounded CPU sample of the same workload: every particle inside the sub-cube [0, frac_side)^3"""
     sel = (pos[:, 0] < frac_side) & (pos[:, 1] < frac_side) & (pos[:, 2] < frac_side)
@@ -117,18 +129,18 @@ def run_reference_arm(args, rank, world):
     from nbodylib_b200.synth import clustered_box
     ng = args.ng
     pos, vel, mass = clustered_box(ng, seed=2025, nhalo=max(8, min(8192, ng ** 3 // 16384)), device="cuda" if torch.cuda.is_available() else "cpu")
-    frac = 0.25 if ng >= 256 else 1.0
+    frac = sample_fraction(ng)
     sp, sv, sm = sample_subvolume(pos, vel, mass, frac)
     del pos, vel, mass
     leg = cpu_reference_leg(sp, sv, sm, K_NN, steps=args.steps, warmup=min(args.warmup, 1))
     dt = float(np.mean(leg["seconds"]))
     val = leg["n"] / dt
-    sample = "all %d particles of the sub-cube [0,%.2f)^3 of the %d^3 clustered box (tree built over the sample only; per-query cost grows ~log N, so this flatters the CPU by ~20%% at 512^3)" % (leg["n"], frac, ng)
+    sample = "all %d particles of the sub-cube [0,%.2f)^3 of the %d^3 clustered box (tree built over the sample only; per-query cost grows ~log N, so this flatters the CPU by ~10%% at 512^3)" % (leg["n"], frac, ng)
     line = {
         "impl": "reference", "metric": "knn_density_particles_per_s", "value": val, "unit": "particles/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "clustered periodic box %d^3 (ZA lattice + Plummer halos), KDTree bucket=16, CalcDensity(%d)" % (ng, K_NN)},
+        "config": {"workload": workload_name(ng, max(8, min(8192, ng ** 3 // 16384))), "particles_per_gpu": ng ** 3, "k": K_NN},
         "cpu_baseline": {"value": val, "unit": "particles/s", "cores": leg["cores"], "kind": leg["kind"], "sample": sample,
                          "build_seconds_sample": leg["build_seconds"]},
         "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -335,7 +347,7 @@ def main():
     # ---- CPU baseline on the host cores (rank 0, N=1 only) -------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        frac = 0.25 if ng >= 256 else 1.0
+        frac = sample_fraction(ng)
         sp, sv, sm = sample_subvolume(pos, vel, mass, frac)
         leg = cpu_reference_leg(sp, sv, sm, K_NN, fof_ll=0.2 / ng)
         dt = float(np.mean(leg["seconds"]))
@@ -358,7 +370,7 @@ def main():
             "metric": "knn_density_particles_per_s", "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "clustered periodic box %d^3 per GPU (ZA lattice + %d Plummer halos), KDTree bucket=16, CalcDensity(%d): fused kNN + SPH density" % (ng, nh, K_NN),
+            "config": {"workload": workload_name(ng, nh),
                        "particles_per_gpu": n, "k": K_NN, "storage": "fp32 coordinates (exact), fp64 distance arithmetic",
                        "l2": "inputs (%.1f GB) exceed L2, no flush needed" % (n * 16 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
