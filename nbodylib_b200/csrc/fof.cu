@@ -131,6 +131,83 @@ __global__ void __launch_bounds__(FOF_WARPS * 32) fof_link_kernel(FofParams prm)
     }
 }
 
+// ---- 3D ball on fp32 storage: fp32 screen, exact fp64 test for the survivors ------------------------------------------------
+// Stored coordinates are exact fp32 values, so for the unshifted query the fp32 evaluation of d2 (3 subtractions, one
+// multiplication, two FMAs) has a relative error below 4 * 2^-24: a candidate whose fp32 d2 exceeds fdist2 * (1 + 2^-20)
+// cannot pass the exact test.  Only the few candidates near or inside the ball get the reference's fp64 expression, so the
+// link relation -- and the partition -- stay bit-identical.  A periodic image of the query (x +- period) is not an fp32
+// value in general: shifted images skip the screen (almost all of them die at the root box test anyway).
+struct FofVisitor3F {
+    const Vec4<float>* P;
+    float4* tile;          // [32]
+    int* parent;
+    const int32_t* excl;
+    double qx, qy, qz, p0;
+    float qxf, qyf, qzf, limf, prune_f;
+    int self;
+    bool on, shifted;
+    unsigned lane;
+
+    __device__ __forceinline__ bool need(float lb) const { return lb < prune_f; }
+    __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
+        for (int base = 0; base < cnt; base += 32) {
+            const int m = min(32, cnt - base);
+            __syncwarp();
+            if ((int)lane < m) { Vec4<float> c = P[start + base + lane]; tile[lane] = make_float4(c.x, c.y, c.z, 0.f); }
+            __syncwarp();
+            if (!on) continue;
+            for (int j = 0; j < m; j++) {
+                const int c = start + base + j;
+                // the unshifted relation is exactly symmetric, so each pair is merged once (from its lower index)
+                if (shifted ? (c == self) : (c <= self)) continue;
+                const float4 t = tile[j];
+                if (!shifted) {
+                    const float dx = qxf - t.x, dy = qyf - t.y, dz = qzf - t.z;
+                    if (!(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) <= limf)) continue;
+                }
+                if (dist2_ref(qx, qy, qz, (double)t.x, (double)t.y, (double)t.z) < p0) {
+                    if (excl && excl[c]) continue;
+                    uf_union(parent, self, c);
+                }
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(FOF_WARPS * 32) fof_link3f_kernel(FofParams prm) {
+    __shared__ float4 s_tile[FOF_WARPS][32];
+    __shared__ int s_stack[FOF_WARPS][TRAV_STACK];
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    const int64_t group = (int64_t)blockIdx.x * FOF_WARPS + w;
+    const int64_t qi = group * 32 + lane;
+    if (group * 32 >= prm.n) return;
+    const Vec4<float>* P = reinterpret_cast<const Vec4<float>*>(prm.P);
+    bool valid = qi < prm.n;
+    if (valid && prm.excl && prm.excl[qi]) valid = false;
+    FofVisitor3F v;
+    v.P = P; v.tile = s_tile[w]; v.parent = prm.parent; v.excl = prm.excl;
+    v.p0 = prm.p0; v.prune_f = prm.prune_f; v.lane = lane;
+    v.limf = __fmul_ru(__double2float_ru(prm.p0), 1.00000095367431640625f);
+    v.self = valid ? (int)qi : -1;
+    v.on = valid; v.shifted = false;
+    double x0 = 0, y0 = 0, z0 = 0;
+    v.qxf = v.qyf = v.qzf = 0.f;
+    if (valid) {
+        Vec4<float> c = P[qi];
+        x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z;
+        v.qxf = c.x; v.qyf = c.y; v.qzf = c.z;
+    }
+    const int nimg = prm.periodic ? 8 : 1;
+    for (int img = 0; img < nimg; img++) {
+        v.qx = (img & 1) ? ((x0 < prm.period[0] / 2.0) ? x0 + prm.period[0] : x0 - prm.period[0]) : x0;
+        v.qy = (img & 2) ? ((y0 < prm.period[1] / 2.0) ? y0 + prm.period[1] : y0 - prm.period[1]) : y0;
+        v.qz = (img & 4) ? ((z0 < prm.period[2] / 2.0) ? z0 + prm.period[2] : z0 - prm.period[2]) : z0;
+        v.shifted = img != 0;
+        QueryBox qb = make_qbox(v.qx, v.qy, v.qz);
+        traverse(prm.nlo, prm.nhi, prm.bucket, s_stack[w], v, qb, valid);
+    }
+}
+
 // ---- FOFCriterionSetBasisForLinks (KDFOF.cxx:268-378, KDLeafNode.cxx:620-652) -------------------------------------
 // Only particles whose check value is 0 may start or extend a group ("basis" particles); the others can be linked INTO
 // a group by a basis particle but never link further.  The basis particles' groups are therefore the connected components
@@ -326,7 +403,8 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     if (a.mode == 1 || a.mode == 4) NBK_REQUIRE(p.V != nullptr, NBK_ERR_ARG, "6D FOF needs velocities");
     int64_t groups = (n + 31) / 32;
     NBK_CHECK(cudaEventRecord(t.ev2, st));
-    if (t.store_bytes == 4) fof_link_kernel<float><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
+    if (t.store_bytes == 4 && a.mode == 0 && getenv("NBK_FOF_NO_SCREEN") == nullptr) fof_link3f_kernel<<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
+    else if (t.store_bytes == 4) fof_link_kernel<float><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
     else fof_link_kernel<double><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
     DevBuf<int32_t> excl2;
     const int32_t* excl_final = a.precheck_tree;

@@ -368,3 +368,21 @@ def test_smoothed_velocity_moments_restatement(port, G, X):
     np.add.at(sd, ii, (w / rho[jj] * m[jj])[:, None, None] * a[:, :, None] * a[:, None, :])
     np.add.at(sd, jj, (w / rho[ii] * m[ii])[:, None, None] * b[:, :, None] * b[:, None, :])
     np.testing.assert_allclose(sd, X["sm_disp"], rtol=0, atol=1e-12 * np.abs(X["sm_disp"]).max())
+
+
+def test_header_is_plain_c_and_shim_links(built, tmp_path):
+    """include/nbk.h must be consumable from C (the boundary is a C ABI); the C++ shim and the demo written against the
+    reference's interface must compile and link against libnbk.so (running it needs a GPU: tests/test_gpu_parity.py)."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if gcc is None or gxx is None:
+        pytest.skip("no host compiler")
+    csrc = tmp_path / "use_nbk.c"
+    csrc.write_text('#include "nbk.h"\nint main(void) { nbk_info i; nbk_particles p; (void)i; (void)p; return nbk_device_count() < 0; }\n')
+    lib = os.path.join(ROOT, "nbodylib_b200")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), str(csrc),
+                           "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", str(tmp_path / "use_nbk")])
+    subprocess.check_call([gxx, "-O1", "-std=c++17", "-fopenmp", "-Wall", "-I" + os.path.join(lib, "shim"), os.path.join(ROOT, "examples", "shim_demo.cxx"),
+                           "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", str(tmp_path / "shim_demo")])
