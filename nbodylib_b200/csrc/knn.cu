@@ -67,6 +67,7 @@ struct KnnParams {
     const int32_t* cand_excl; int crit_mode; double cp0, cp1;
     // smoothed velocity moments (CalcSmoothVel / CalcSmoothVelDisp): densities in, accumulators out, all tree order
     const double* rho_in; const double* smvel_in; double* smvel_out; double* smdisp_out;
+    int bulk_align;                                   // select + log kernel: the bulk-loaded range starts at a multiple of this (0: centred window)
 };
 
 // ================================================================================================ exact
@@ -1130,6 +1131,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams pr
             v.qx = x0; v.qy = y0; v.qz = z0;
             int64_t want = (int64_t)kcap;
             int64_t r0 = g0 + 16 - want / 2;
+            // ... or, better, the node-aligned block that holds the group: with 2^m particles the tree positions [j*64, (j+1)*64)
+            // are one node, a compact set, whereas a window centred on the group straddles three nodes whose tree-order
+            // neighbours can lie across a high-level cut plane -- a looser first bound and more insertions (k = 64: 428 -> 413 ms)
+            if (prm.bulk_align > 0) r0 = g0 - (g0 % prm.bulk_align);
             if (r0 + want > prm.n) r0 = prm.n - want;
             if (r0 < 0) r0 = 0;
             int64_t r1 = r0 + want;
@@ -1230,6 +1235,11 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.gather = a.gather ? 1 : 0; p.vq = a.vq;
     p.cand_excl = a.cand_excl; p.crit_mode = a.crit_mode; p.cp0 = a.cp0; p.cp1 = a.cp1;
     p.rho_in = a.rho_in; p.smvel_in = a.smvel_in; p.smvel_out = a.smvel_out; p.smdisp_out = a.smdisp_out;
+    {
+        int al = 32;
+        while (al * 2 <= a.k) al *= 2;                     // largest power of two <= k, at least the 32-query group
+        p.bulk_align = getenv("NBK_KNN_BULK_ALIGN") ? atoi(getenv("NBK_KNN_BULK_ALIGN")) : al;
+    }
     p.k = a.k;
     p.periodic = a.periodic; p.strict = a.strict; p.tree_form = a.tree_form;
     for (int d = 0; d < 3; d++) p.period[d] = t.period[d];
