@@ -15,6 +15,12 @@ if os.environ.get("PROBE_N"):
     pos, vel, mass = pos[sel].contiguous(), vel[sel].contiguous(), mass[sel].contiguous()
 t = KDTree(pos, vel, mass, Period=np.ones(3), device=0)
 rho = torch.empty(n, dtype=torch.float64, device="cuda")
+if os.environ.get("PROBE_TRIM"):
+    # before an ncu capture: hand cached blocks back to the driver (torch's allocator, the library's stream-ordered pool), so
+    # that the profiler's per-pass save / restore of device memory covers the live arrays only
+    del pos, vel, mass
+    torch.cuda.empty_cache()
+    t._lib.nbk_release_cached_memory(0)
 for k in ks:
     for rep in range(2):
         t.CalcDensity(k, out=rho)
