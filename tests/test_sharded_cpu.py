@@ -74,7 +74,7 @@ def _worker(rank, world, port, tmp, halo):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,halo", [(2, None), (2, 0.01), (3, None)])
+@pytest.mark.parametrize("world,halo", [(2, None), (2, 0.01), (3, None), (4, None)])
 def test_sharded_host_logic_matches_single_domain(port, world, halo):
     from nbodylib_b200.synth import clustered_small
     pos, vel, mass = clustered_small(5000, seed=77)
