@@ -928,6 +928,12 @@ static void ball_call(nbk_tree* t, double fdist2, const CritSpec* crit, int64_t 
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "SearchBallPos needs positions as tree coordinates");
     DeviceGuard guard(t->device, t->stream);
     const bool dev = flags & NBK_DEVICE_PTRS;
+    if (m == 0) {                               // no queries: one row offset (0), nothing else
+        *total = 0;
+        if (dev) { NBK_CHECK(cudaMemsetAsync(offsets, 0, sizeof(int64_t), t->stream)); NBK_CHECK(cudaStreamSynchronize(t->stream)); }
+        else offsets[0] = 0;
+        return;
+    }
     DevBuf<int32_t> dq, didx;
     DevBuf<double> dx, dv, dd2;
     DevBuf<int64_t> doff;
