@@ -386,3 +386,42 @@ def test_header_is_plain_c_and_shim_links(built, tmp_path):
                            "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", str(tmp_path / "use_nbk")])
     subprocess.check_call([gxx, "-O1", "-std=c++17", "-fopenmp", "-Wall", "-I" + os.path.join(lib, "shim"), os.path.join(ROOT, "examples", "shim_demo.cxx"),
                            "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", str(tmp_path / "shim_demo")])
+
+
+def test_restatements_vs_live_reference(port):
+    """The numpy restatements (oracle/restate_np.py) against the reference itself on a second, seeded input (not the golden
+    one): single-target estimators, criterion search, filtered kNN.  Skipped where oracle/_ref did not travel."""
+    from oracle import pyoracle
+    from oracle.restate_np import ball_min_d2, crit_rows, gather_density, gather_veldensity
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from nbodylib_b200.synth import clustered_small
+    n, k, kv = 4000, 24, 10
+    pos, vel, mass = clustered_small(n, seed=5, nhalo=12)
+    rng = np.random.default_rng(9)
+    mass = (mass * (1.0 + rng.random(n))).astype(np.float32).astype(np.float64)
+    types = (rng.random(n) < 0.4).astype(np.int32)
+    ll = 0.3 / n ** (1.0 / 3)
+    params = np.zeros(10)
+    params[1] = params[6] = ll * ll
+    params[2] = params[7] = float(((vel - vel.mean(0)) ** 2).sum(1).mean() / 3) * 0.5
+    q = rng.choice(n, 60, replace=False).astype(np.int32)
+    _, kern = port.kernel_table(3, 2, 1000)
+    for period in (None, np.ones(3)):
+        R = pyoracle.Ref(pos, vel, mass, period=period)
+        ids, d2 = port.knn_particles(pos, k)                       # Calc* never wrap (Q2): the non periodic lists
+        assert np.array_equal(np.array([gather_density(kern, d2[i], mass[ids[i]]) for i in q]), R.calc_density_particles(q, k))
+        np.testing.assert_allclose(np.array([gather_veldensity(kern, vel[i], vel[ids[i]], kv) for i in q]), R.calc_veldensity_particles(q, kv, k), rtol=1e-14)
+        for crit in (0, 2):
+            off, idx = R.search_criterion_particles(q, crit, params)
+            rows = crit_rows(pos, vel, pos[q], vel[q], crit, params, period, exclude=q)
+            assert all(np.array_equal(rows[j], np.sort(idx[off[j]:off[j + 1]])) for j in range(len(q)))
+        R.set_types(types)
+        nn, dd = R.knn_filtered(8)
+        drop = 0 if period is None else 1
+        for i in q:
+            b = ball_min_d2(pos, pos[i], period)
+            b[i] = np.inf
+            b[types != 0] = np.inf
+            assert np.array_equal(np.sort(b)[drop:8 + drop], dd[i])
+        R.close()
