@@ -237,6 +237,15 @@ int nbk_attach_halo(nbk_tree* t, nbk_tree* halo);
  * memory back to the driver (e.g. before another library needs the HBM). */
 int nbk_release_cached_memory(int device);
 
+/* Process-wide tuning overrides (none is needed for correct results; the defaults are what the benchmarks run).  No
+ * reference counterpart: the reference's only knobs are constructor arguments.  Names:
+ *   "knn_cap"     per-query candidate buffer of the density kernel (entries; 0 = default max(2k, k+48))
+ *   "knn_leaf"    particles per scanned tile of the density kernel (0 = the tree level holding 21..40 particles)
+ *   "knn_exact"   1: the Calc* family runs on the fp64-heap kernel only
+ *   "fof_screen"  0: the 3D link kernel skips its fp32 screen
+ * Unknown names return NBK_ERR_ARG. */
+int nbk_set_option(const char* name, int64_t value);
+
 /* Device-resident views for callers that stay on the GPU (sharded driver, benchmarks). */
 int nbk_device_arrays(const nbk_tree* t, const void** pos4, const void** vel4, const void** mass, const int32_t** order);
 

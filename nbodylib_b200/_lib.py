@@ -43,6 +43,7 @@ EXPORTS = [
     "nbk_search_criterion_particles", "nbk_search_criterion_points", "nbk_calc_density_particles",
     "nbk_calc_veldensity_particles", "nbk_calc_density_points", "nbk_calc_veldensity_points",
     "nbk_knn_filtered_particles", "nbk_knn_filtered_points", "nbk_calc_smooth_vel", "nbk_calc_smooth_veldisp",
+    "nbk_set_option",
 ]
 
 _lib = None
@@ -89,12 +90,18 @@ def load():
     L.nbk_fof_criterion_basis.argtypes = [vp, i32, vp, i32, i32, vp, vp, C.POINTER(i64), C.POINTER(NbkFofLists), i32]
     L.nbk_attach_halo.argtypes = [vp, vp]
     L.nbk_release_cached_memory.argtypes = [i32]
+    L.nbk_set_option.argtypes = [C.c_char_p, i64]
     L.nbk_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     for name in EXPORTS:
         if name not in ("nbk_last_error", "nbk_device_count"):
             getattr(L, name).restype = i32
     _lib = L
     return L
+
+
+def set_option(name, value):
+    """nbk_set_option: process-wide tuning overrides (include/nbk.h lists the names)"""
+    check(load().nbk_set_option(name.encode(), int(value)))
 
 
 class NbkError(RuntimeError):

@@ -1082,6 +1082,13 @@ int nbk_calc_veldensity_points(nbk_tree* t, int nsmooth, int nsearch, int64_t m,
     NBK_API_END
 }
 
+int nbk_set_option(const char* name, int64_t value) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(name != nullptr, NBK_ERR_ARG, "nbk_set_option: null name");
+    NBK_REQUIRE(set_knn_option(name, value) || set_fof_option(name, value), NBK_ERR_ARG, std::string("nbk_set_option: unknown option ") + name);
+    NBK_API_END
+}
+
 int nbk_release_cached_memory(int device) {
     NBK_API_BEGIN
     if (device < 0) NBK_CHECK(cudaGetDevice(&device));

@@ -382,6 +382,12 @@ static void build_fof_lists(nbk_tree& t, FofArgs& a, int64_t* launches) {
     NBK_CHECK(cudaStreamSynchronize(st));
 }
 
+static int g_fof_screen = 1;
+bool set_fof_option(const char* name, int64_t value) {
+    if (std::string(name) == "fof_screen") { g_fof_screen = (int)value; return true; }
+    return false;
+}
+
 void launch_fof(nbk_tree& t, FofArgs& a) {
     const int64_t n = t.n;
     cudaStream_t st = t.stream;
@@ -403,7 +409,7 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     if (a.mode == 1 || a.mode == 4) NBK_REQUIRE(p.V != nullptr, NBK_ERR_ARG, "6D FOF needs velocities");
     int64_t groups = (n + 31) / 32;
     NBK_CHECK(cudaEventRecord(t.ev2, st));
-    if (t.store_bytes == 4 && a.mode == 0 && getenv("NBK_FOF_NO_SCREEN") == nullptr) fof_link3f_kernel<<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
+    if (t.store_bytes == 4 && a.mode == 0 && g_fof_screen) fof_link3f_kernel<<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
     else if (t.store_bytes == 4) fof_link_kernel<float><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
     else fof_link_kernel<double><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
     DevBuf<int32_t> excl2;

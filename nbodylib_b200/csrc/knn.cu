@@ -14,15 +14,10 @@
 // Two kernels:
 //   knn_exact_kernel  heap of (fp64 d2, int32 index), 12 B/entry.  Used when neighbour lists are materialised
 //                     (FindNearest API), for the periodic image schedule, and as the fallback below.
-//   knn_fast_kernel   the density family (CalcDensity / CalcVelDensity / smoothing scale), non periodic target
-//                     form.  Heap entries are ONE 64-bit word: (fp32 key << 32 | index), key = RN_fp32(d2) of the
-//                     exact fp64 d2.  fp64->fp32 rounding is monotone, so the k smallest keys are the exact k
-//                     nearest unless the k-th and (k+1)-th keys are EQUAL; the heap carries k+1 entries to see that
-//                     case, and such queries (a ~1e-5 fraction on random data) are appended to a list that the
-//                     exact kernel re-runs.  Exact d2 for the SPH weights is recomputed from the indices.
-//                     8 B/entry instead of 12 and half the shared-memory traffic per sift step; the heap is
-//                     bulk-loaded from the k+1 tree-order neighbours of the bucket (heapify) instead of k
-//                     full-depth insertions.
+//   knn_ap_kernel     the density family (CalcDensity / CalcVelDensity / smoothing scale), non periodic target
+//                     form: append + prune selection on fp32 keys with a rigorous error bound, no heap and no
+//                     serial insertion rounds (described at the kernel).  Queries whose k-th / (k+1)-th keys are
+//                     closer than the error band are re-run by the exact kernel.
 #include <string.h>
 
 #include "traverse.cuh"
@@ -67,7 +62,7 @@ struct KnnParams {
     const int32_t* cand_excl; int crit_mode; double cp0, cp1;
     // smoothed velocity moments (CalcSmoothVel / CalcSmoothVelDisp): densities in, accumulators out, all tree order
     const double* rho_in; const double* smvel_in; double* smvel_out; double* smdisp_out;
-    int bulk_align;                                   // select + log kernel: the bulk-loaded range starts at a multiple of this (0: centred window)
+    int64_t n_tree;                                   // particles of the main tree (= n unless a halo is attached)
 };
 
 // ================================================================================================ exact
@@ -388,11 +383,39 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
     }
 }
 
-// ================================================================================================= fast
-constexpr unsigned FKEY_INF = 0x7f800000u;   // +inf: empty slot
+// ====================================================================================== append + prune select
+// The density family needs (a) the exact set of the k nearest, (b) the exact k-th distance and (c) a sum over the set.
+// Per lane (= query) the kernel keeps an APPEND BUFFER of fp32 keys in shared memory ([cap][32], slot-major) and, entry
+// for entry, the candidates' tree indices in a global scratch block ([cap][32] per resident warp, L2 resident).  A
+// candidate is screened with ONE fp32 distance and, if it is below the lane's bound, appended by two predicated stores:
+// there is no heap and no SIMT-serial insertion round -- every lane works on every instruction of the tile scan.
+// When some lane's buffer is nearly full, the whole warp PRUNES in lock step: a 32-bin histogram of the lane's keys
+// finds the bin holding rank R = k+1, one compaction pass keeps the bins below it, and the (<= 8) members of that bin
+// are ranked by a sorting network in registers; the lane's bound becomes its exact R-th smallest key.  The last prune
+// leaves exactly the k+1 smallest keys.
+//
+// Exactness.  Keys are a = fl32(d2) evaluated with 3 subtractions, 1 multiplication, 2 FMAs on exact fp32 coordinates:
+// |a - d2| <= 5.01 * 2^-24 * d2 =: eps * d2 (fp64 storage: a = RN_fp32 of the reference's fp64 d2, eps = 2^-24).
+//   * Every candidate that is dropped -- screened out (a > bound * (1 + 2^-20)), in a subtree whose box lower bound
+//     reaches bound * (1 + 2^-20), or pruned -- has a >= the lane's final (k+1)-th smallest key m1.
+//   * If m1 > m2 * (1 + 2^-20) (m2 = k-th smallest key), every dropped candidate and the (k+1)-th itself are farther in
+//     exact arithmetic than each of the k kept ones, because 2^-20 > 2 eps: the k smallest keys ARE the k nearest.
+//   * The exact k-th distance is the reference fp64 d2 of the entry with key m2 provided the third largest key m3 is
+//     below m2 * (1 - 2^-20); the SPH sums use fp64 d2 recomputed from the indices.
+//   * Queries failing either gap test (~2e-4 of them), meeting an under/overflowing key or a degenerate histogram are
+//     appended to a list and re-run by knn_exact_kernel (fp64 heap).
+// Traversal: bottom-up (traverse_bottom_up): the group's own node first, then the sibling subtrees of its ancestors.
+// Persistent grid: warps draw 32-query groups from a global counter, so the grid is one wave whatever the particle count.
+constexpr float AP_TINY = 7.888609052210118e-31f;           // 2^-100: below it the relative error bound of a key is not guaranteed
+constexpr float AP_HUGE = 1.0e37f;
+constexpr float AP_WIDEN = 1.00000095367431640625f;          // 1 + 2^-20
+constexpr float AP_NARROW = 0.99999904632568359375f;         // 1 - 2^-20
+constexpr int AP_STASH = 8;
+constexpr int AP_AUX_BYTES = 2048;                           // histogram u16 [32][32]; then the stash: float [8][32] + int [8][32]
+constexpr int AP_MAX_LEVELS = 6;
 
 #ifdef NBK_STATS
-__device__ unsigned long long g_stats[8];   // 0 tiles, 1 candidate evals (warp-level), 2 rounds, 3 sifts (lane-level), 4 accepted bits, 5 leaves skipped
+__device__ unsigned long long g_stats[8];   // 0 tiles, 1 prunes, 2 prune levels, 3 appended (lane-level), 4 flagged, 5 failed
 #define STAT(i, v) do { if (lane_id() == 0) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
 #define STAT_LANE(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
 #else
@@ -400,480 +423,224 @@ __device__ unsigned long long g_stats[8];   // 0 tiles, 1 candidate evals (warp-
 #define STAT_LANE(i, v)
 #endif
 
-// Per-lane 4-ary max-heap in shared memory.  Node p's four children are nodes 4p+1..4p+4 and their fp32 keys sit
-// in ONE 16-byte group, so a sift step costs one LDS.128 instead of two dependent 8-byte loads, and a 65-entry
-// heap is 3 levels deep instead of 6.  Key of node p: group (p+3)>>2, component (p+3)&3 (node 0 = group 0, comp 3),
-// groups are [group][lane] float4 (conflict-free 16-byte lane stride); indices are [node][lane] int32.
-struct Heap4 {
-    float4* K4;   // [G+1][32]
-    int* I;       // [NN][32]
-    int G;        // internal nodes: 0..G-1 ; NN = 4G+1 nodes
-    unsigned lane;
-    __device__ __forceinline__ float* keyp(int p) const { return reinterpret_cast<float*>(K4 + (((p + 3) >> 2) * 32 + lane)) + ((p + 3) & 3); }
-    __device__ __forceinline__ int& idx(int p) const { return I[p * 32 + lane]; }
-    __device__ __forceinline__ float rootkey() const { return *keyp(0); }
-    // place (xk, xi) at node p and sift it down
-    __device__ __forceinline__ void sift(int p, float xk, int xi) {
-        while (p < G) {
-            const float4 ck = K4[(p + 1) * 32 + lane];
-            const float m = fmaxf(fmaxf(ck.x, ck.y), fmaxf(ck.z, ck.w));
-            if (xk >= m) break;
-            const int j = (ck.x == m) ? 0 : ((ck.y == m) ? 1 : ((ck.z == m) ? 2 : 3));
-            const int c = 4 * p + 1 + j;
-            *keyp(p) = m;
-            idx(p) = idx(c);
-            p = c;
-        }
-        *keyp(p) = xk;
-        idx(p) = xi;
-    }
-};
-
-template <class S>
-struct FastVisitor {
-    const Vec4<S>* P;
-    double* tile;
-    Heap4 hp;
-    double qx, qy, qz;
-    double topd;        // (double) of the heap-top key; 0 for lanes without a query (nothing is ever accepted)
-    float topf;
-    int self;
-    int r0, r1;         // tree-index range already loaded into the heap (skipped during the traversal)
-    unsigned lane;
-
-    __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
-    __device__ __forceinline__ void settop() { topf = hp.rootkey(); topd = (double)topf; }
-
-    template <bool OVERLAP>
-    __device__ __forceinline__ void scan_tile(int first, int m) {
-        unsigned acc = 0;
-        STAT(0, 1); STAT(1, m);
-#pragma unroll 4
-        for (int j = 0; j < m; j++) {
-            const int c = first + j;
-            double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-            bool ok = d2 < topd && d2 > 0.0 && c != self;
-            if (OVERLAP) ok = ok && (c < r0 || c >= r1);
-            acc |= (ok ? 1u : 0u) << j;
-        }
-        STAT_LANE(4, __popc(acc));
-        while (__any_sync(0xffffffffu, acc != 0)) {
-            STAT(2, 1);
-            if (acc) {
-                int j = __ffs(acc) - 1;
-                acc &= acc - 1;
-                double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
-                if (d2 < topd) { STAT_LANE(3, 1); hp.sift(0, __double2float_rn(d2), first + j); settop(); }
-            }
-        }
-    }
-
-    __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
-        if (start >= r0 && start + cnt <= r1) return;          // warp-uniform: leaf entirely preloaded
-        const bool overlap = start < r1 && start + cnt > r0;   // warp-uniform
-        for (int base = 0; base < cnt; base += 32) {
-            int m = min(32, cnt - base);
-            __syncwarp();
-            if ((int)lane < m) {
-                Vec4<S> c = P[start + base + lane];
-                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
-            }
-            __syncwarp();
-            if (overlap) scan_tile<true>(start + base, m);
-            else scan_tile<false>(start + base, m);
-        }
-    }
-};
-
-static inline int heap4_groups(int kcap) { return (kcap - 1 + 3) / 4; }
-static inline size_t fast_warp_bytes(int kcap) {
-    int G = heap4_groups(kcap);
-    return (size_t)(G + 1) * 32 * 16 + (size_t)(4 * G + 1) * 32 * 4 + 96 * 8 + TRAV_STACK * 4;
-}
-
-template <class S>
-__global__ void __launch_bounds__(KNN_WARPS * 32) knn_fast_kernel(KnnParams prm) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    const int kcap = prm.kcap;                        // k + 1 real slots
-    const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
-    const size_t warp_bytes = (size_t)(G + 1) * 32 * 16 + (size_t)NN * 32 * 4 + 96 * 8 + TRAV_STACK * 4;
-    unsigned char* base = smem_raw + w * warp_bytes;
-    Heap4 hp;
-    hp.K4 = reinterpret_cast<float4*>(base);
-    hp.I = reinterpret_cast<int*>(base + (size_t)(G + 1) * 32 * 16);
-    hp.G = G; hp.lane = lane;
-    double* tile = reinterpret_cast<double*>(base + (size_t)(G + 1) * 32 * 16 + (size_t)NN * 32 * 4);
-    int* stack = reinterpret_cast<int*>(base + (size_t)(G + 1) * 32 * 16 + (size_t)NN * 32 * 4 + 96 * 8);
-
-    const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
-    const int64_t group = (int64_t)blockIdx.x * KNN_WARPS + w;
-    const int64_t g0 = prm.q0 + group * 32;
-    if (g0 >= prm.q1) return;
-    const int64_t qi = g0 + lane;
-    const bool valid = qi < prm.q1 && (!prm.active || prm.active[qi]);
-
-    FastVisitor<S> v;
-    v.P = P; v.tile = tile; v.hp = hp; v.lane = lane;
-    v.self = valid ? (int)qi : -1;
-    double x0 = 0, y0 = 0, z0 = 0;
-    if (valid) { Vec4<S> c = P[qi]; x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z; }
-    v.qx = x0; v.qy = y0; v.qz = z0;
-
-    // ---- bulk load: the kcap particles around the bucket in tree order, then heapify -----------------------
-    {
-        // exactly kcap tree positions: every one of them is either skipped for good (self, coincident) or stored,
-        // so marking the range as "already seen" for the traversal never loses a candidate
-        int64_t want = (int64_t)kcap;
-        int64_t r0 = g0 + 16 - want / 2;
-        if (r0 + want > prm.n) r0 = prm.n - want;
-        if (r0 < 0) r0 = 0;
-        int64_t r1 = r0 + want;
-        if (r1 > prm.n) r1 = prm.n;
-        v.r0 = (int)r0; v.r1 = (int)r1;
-        int filled = 0;
-        for (int64_t b0 = r0; b0 < r1; b0 += 32) {
-            int m = (int)min((int64_t)32, r1 - b0);
-            __syncwarp();
-            if ((int)lane < m) {
-                Vec4<S> c = P[b0 + lane];
-                tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
-            }
-            __syncwarp();
-            for (int j = 0; j < m; j++) {
-                double d2 = dist2_ref(x0, y0, z0, tile[j], tile[32 + j], tile[64 + j]);
-                if (valid && (int)(b0 + j) != v.self && d2 > 0.0) {
-                    *v.hp.keyp(filled) = __double2float_rn(d2);
-                    v.hp.idx(filled) = (int)(b0 + j);
-                    filled++;
-                }
-            }
-        }
-        // empty real slots wait for candidates (+inf); the padding up to 4G+1 nodes, and every slot of a lane without
-        // a query, holds key 0 / index -1: never evicted, never accepted against
-        for (; filled < NN; filled++) {
-            *v.hp.keyp(filled) = (valid && filled < kcap) ? __uint_as_float(FKEY_INF) : 0.f;
-            v.hp.idx(filled) = -1;
-        }
-        for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p), v.hp.idx(p));
-        v.settop();
-    }
-    {
-        QueryBox qb = make_qbox(x0, y0, z0);
-        traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
-    }
-    if (!valid) return;
-
-    // ---- exactness test: drop the (k+1)-th; the k smallest keys are the exact kNN iff key_k < key_{k+1} -------
-    const float key_kp1 = v.hp.rootkey();
-    v.hp.sift(0, 0.f, -1);                                       // the root becomes padding
-    const float key_k = v.hp.rootkey();
-    const bool short_of_k = __float_as_uint(key_k) == FKEY_INF;  // fewer than k candidates exist (n <= k)
-    if (key_k == key_kp1 && !short_of_k) {
-        int slot = atomicAdd(prm.flag_count, 1);
-        prm.flag_list[slot] = (int)qi;
-        return;                                                  // the exact kernel redoes this query entirely
-    }
-    // exact k-th distance: the largest exact d2 among the entries sharing the top key
-    double d2max = 0;
-    for (int s = 0; s < NN; s++) {
-        int id = v.hp.idx(s);
-        if (id >= 0 && *v.hp.keyp(s) == key_k) {
-            Vec4<S> c = P[id];
-            d2max = fmax(d2max, dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z));
-        }
-    }
-    if (short_of_k) d2max = KNN_SENTINEL;
-    if (prm.hsm) prm.hsm[qi] = 0.5 * sqrt(d2max);
-    if (prm.rho && prm.veldens_k == 0) {
-        const double hi = 0.5 * sqrt(d2max);
-        const double norm = 1.0 / pow(hi, 3.0);
-        const double delta = 2.0 / (double)(prm.kernres - 1);
-        const double mi = prm.mass[qi];
-        double acc = 0;
-        for (int s = 0; s < NN; s++) {
-            int id = v.hp.idx(s);
-            if (id < 0) continue;
-            Vec4<S> c = P[id];
-            double rij = sqrt(dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z));
-            double r = rij / hi;
-            double Wij = 0.5 * wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
-            acc += Wij * prm.mass[id];
-            atomicAdd(&prm.rho[id], Wij * mi);
-        }
-        atomicAdd(&prm.rho[qi], acc);
-    }
-    if (prm.rho && prm.veldens_k > 0) {
-        // R2.  The fp64 velocity distances (up to k per lane) are written over the lane's own heap storage, which is dead
-        // by now: doubles 0..2G+1 over the lane's key groups, the rest over pairs of the lane's index slots that have
-        // already been consumed (double t >= 2G+2 uses index slots 2u, 2u+1 with u = t-2G-2 <= s-2G-2, and 2u+1 <= s for
-        // every read position s <= 4G).  Everything stays lane-private, so no cross-lane ordering is needed.
-        const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
-        const int nA = 2 * (G + 1);
-        auto dget = [&](int t) -> double {
-            if (t < nA) return reinterpret_cast<const double*>(v.hp.K4 + ((t >> 1) * 32 + lane))[t & 1];
-            const int u = t - nA;
-            return __hiloint2double(v.hp.I[(2 * u + 1) * 32 + lane], v.hp.I[(2 * u) * 32 + lane]);
-        };
-        auto dset = [&](int t, double d) {
-            if (t < nA) { reinterpret_cast<double*>(v.hp.K4 + ((t >> 1) * 32 + lane))[t & 1] = d; return; }
-            const int u = t - nA;
-            v.hp.I[(2 * u) * 32 + lane] = __double2loint(d);
-            v.hp.I[(2 * u + 1) * 32 + lane] = __double2hiint(d);
-        };
-        Vec4<S> vi = V[qi];
-        int kx = 0;
-        for (int s = 0; s < NN; s++) {
-            int id = v.hp.idx(s);
-            if (id < 0) continue;
-            Vec4<S> vj = V[id];
-            dset(kx, sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)));
-            kx++;
-        }
-        auto dsift = [&](int p, int n, double d) {      // binary max-heap on the doubles
-            while (true) {
-                int c = 2 * p + 1;
-                if (c >= n) break;
-                double dc = dget(c);
-                if (c + 1 < n) { double dr = dget(c + 1); if (dr > dc) { c = c + 1; dc = dr; } }
-                if (d >= dc) break;
-                dset(p, dc);
-                p = c;
-            }
-            dset(p, d);
-        };
-        const int kv = min(prm.veldens_k, kx);
-        double rho = 0;
-        if (kv > 0) {
-            for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, dget(p));
-            for (int s = kv; s < kx; s++) {
-                double vd = dget(s);
-                if (vd < dget(0)) dsift(0, kv, vd);
-            }
-            const double hi = 0.5 * dget(0);
-            const double norm = 1.0 / pow(hi, 3.0);
-            const double delta = 2.0 / (double)(prm.kernres - 1);
-            // pop in descending order like the reference so the sum is accumulated in the same order
-            for (int e = kv; e > 0; e--) {
-                double rij = dget(0);
-                double r = rij / hi;
-                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
-                dsift(0, e - 1, dget(e - 1));
-            }
-        }
-        prm.rho[qi] = rho;
-    }
-}
-
-// ==================================================================================== select-then-collect
-// The density family needs only (a) the exact k-th distance and (b) a sum over the k nearest neighbours, so the
-// search is split in two traversals sharing one small shared-memory region per warp:
-//   select  : per-lane 4-ary max-heap of fp32 KEYS ONLY (k+1 of them) -> key_k, key_{k+1}.  No indices are carried,
-//             so a sift step moves 4 bytes, and the region is half the size of a (key,index) heap: twice the resident
-//             warps for this latency-bound kernel.
-//   collect : fixed-radius pass, every candidate with RN_fp32(d2) <= key_k is appended to the lane's index list
-//             (exactly the k nearest when key_k < key_{k+1}; otherwise the query goes to the exact kernel); appends
-//             are predicated stores, there are no serial insertion rounds.  The exact fp64 k-th distance is the max
-//             over the appended candidates.
-//   epilogue: SPH sums over the list, as before.
-struct KeyHeap4 {
-    unsigned char* kb;   // this lane's byte base inside the [G+1][32] float4 groups (group g of the lane at kb + g*512)
-    int G;
-    // key of node p: group (p+3)>>2, component (p+3)&3 ; children of p = the four components of group p+1
-    __device__ __forceinline__ float* keyp(int p) const { return reinterpret_cast<float*>(kb + ((p + 3) >> 2) * 512 + ((p + 3) & 3) * 4); }
-    __device__ __forceinline__ float rootkey() const { return *reinterpret_cast<const float*>(kb + 12); }
-    // place xk at node p and sift it down; returns the key that ends up at node p
-    __device__ __forceinline__ float sift(int p, float xk) {
-        unsigned char* pa = reinterpret_cast<unsigned char*>(keyp(p));
-        unsigned char* ga = kb + (p + 1) * 512;
-        float at_p = xk;
-        bool moved = false;
-        while (p < G) {
-            const float4 ck = *reinterpret_cast<const float4*>(ga);
-            const bool a = ck.x >= ck.y, b = ck.z >= ck.w;
-            const float m01 = a ? ck.x : ck.y, m23 = b ? ck.z : ck.w;
-            const bool c = m01 >= m23;
-            const float m = c ? m01 : m23;
-            if (xk >= m) break;
-            const int j = c ? (a ? 0 : 1) : (b ? 2 : 3);
-            *reinterpret_cast<float*>(pa) = m;
-            if (!moved) { at_p = m; moved = true; }
-            pa = ga + 4 * j;
-            p = 4 * p + 1 + j;
-            ga = kb + (p + 1) * 512;
-        }
-        *reinterpret_cast<float*>(pa) = xk;
-        return at_p;
-    }
-};
-
-// Leaf tile staged in shared memory + the per-candidate tests of the two passes.
-// fp32 storage: the tile keeps the float4 records (one LDS.128 per candidate) and candidates are first screened with
-// an fp32 distance: inputs are exact, the fp32 evaluation has a relative error below 5 * 2^-24, so a candidate whose
-// fp32 d2 exceeds limit * (1 + 2^-20) cannot pass the exact fp64 test, which is then evaluated only for the few
-// survivors.  fp64 storage: no screen (fp32 rounding of the coordinates would not bound the error), exact test only.
-template <class S> struct LeafTile;
-template <> struct LeafTile<float> {
+// Leaf tile staged in shared memory and the per-candidate key.
+template <class S> struct ApTile;
+template <> struct ApTile<float> {
     static constexpr int TILE_BYTES = 32 * 16;
     float4* t;
-    float qxf, qyf, qzf;
-    __device__ __forceinline__ void init(void* mem, double qx, double qy, double qz) {
+    float qx, qy, qz;
+    __device__ __forceinline__ void init(void* mem, double x, double y, double z) {
         t = reinterpret_cast<float4*>(mem);
-        qxf = (float)qx; qyf = (float)qy; qzf = (float)qz;
+        qx = (float)x; qy = (float)y; qz = (float)z;     // exact: fp32 storage
     }
-    __device__ __forceinline__ void load(const Vec4<float>* P, int first, int m, unsigned lane) {
-        // slots past the end of the leaf hold NaN: every screen / comparison on them is false, so the scan loops can run
-        // over whole groups of 8 without a bound check
+    __device__ __forceinline__ void load(const Vec4<float>* __restrict__ P, int first, int m, unsigned lane) {
+        // slots past the end of the leaf hold NaN: every comparison on them is false, so the scan runs over whole groups of 8
         const float nanf_ = __int_as_float(0x7fc00000);
         float4 mine = make_float4(nanf_, nanf_, nanf_, 0.f);
         if ((int)lane < m) { Vec4<float> c = P[first + lane]; mine = make_float4(c.x, c.y, c.z, 0.f); }
         t[lane] = mine;
     }
-    static __device__ __forceinline__ float screen_limit(float lim) { return __fmul_ru(lim, 1.00000095367431640625f); }
-    static __device__ __forceinline__ bool screen_one(float qx, float qy, float qz, const float4& c, float limf) {
-        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-        return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) <= limf;     // 3 sub + mul + 2 fma; error < 4 * 2^-24
-    }
-    __device__ __forceinline__ bool screen(int j, float limf, double) const { return screen_one(qxf, qyf, qzf, t[j], limf); }
-    __device__ __forceinline__ double exact(int j, double qx, double qy, double qz) const {
+    __device__ __forceinline__ float key(int j) const {
         const float4 c = t[j];
-        return dist2_ref(qx, qy, qz, (double)c.x, (double)c.y, (double)c.z);
+        const float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
+        return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
     }
+    __device__ __forceinline__ bool coincident(int j) const { const float4 c = t[j]; return qx == c.x && qy == c.y && qz == c.z; }
 };
-template <> struct LeafTile<double> {
+template <> struct ApTile<double> {
     static constexpr int TILE_BYTES = 96 * 8;
     double* t;
-    double qx_, qy_, qz_;
-    __device__ __forceinline__ void init(void* mem, double qx, double qy, double qz) { t = reinterpret_cast<double*>(mem); qx_ = qx; qy_ = qy; qz_ = qz; }
-    __device__ __forceinline__ void load(const Vec4<double>* P, int first, int m, unsigned lane) {
+    double qx, qy, qz;
+    __device__ __forceinline__ void init(void* mem, double x, double y, double z) { t = reinterpret_cast<double*>(mem); qx = x; qy = y; qz = z; }
+    __device__ __forceinline__ void load(const Vec4<double>* __restrict__ P, int first, int m, unsigned lane) {
         const double nan_ = __longlong_as_double(0x7ff8000000000000ll);
         double cx = nan_, cy = nan_, cz = nan_;
         if ((int)lane < m) { Vec4<double> c = P[first + lane]; cx = c.x; cy = c.y; cz = c.z; }
         t[lane] = cx; t[32 + lane] = cy; t[64 + lane] = cz;
     }
-    static __device__ __forceinline__ float screen_limit(float lim) { return lim; }
-    __device__ __forceinline__ bool screen(int j, float, double limd) const { return dist2_ref(qx_, qy_, qz_, t[j], t[32 + j], t[64 + j]) < limd; }
-    __device__ __forceinline__ double exact(int j, double qx, double qy, double qz) const { return dist2_ref(qx, qy, qz, t[j], t[32 + j], t[64 + j]); }
+    __device__ __forceinline__ float key(int j) const { return __double2float_rn(dist2_ref(qx, qy, qz, t[j], t[32 + j], t[64 + j])); }
+    __device__ __forceinline__ bool coincident(int j) const { return qx == t[j] && qy == t[32 + j] && qz == t[64 + j]; }
 };
 
-constexpr int SC_LEAFCAP = 240;   // leaves remembered by the select pass for the collect pass (per warp)
+__device__ __forceinline__ void ap_cex(float& ka, int& ia, float& kb, int& ib) {
+    const bool sw = ka > kb;
+    const float k0 = sw ? kb : ka, k1 = sw ? ka : kb;
+    const int i0 = sw ? ib : ia, i1 = sw ? ia : ib;
+    ka = k0; kb = k1; ia = i0; ib = i1;
+}
 
-template <class S, bool LOG = false>
-struct SelectVisitor {
-    int* log;           // LOG: this lane's column of the warp's [logcap][32] insertion log (global scratch)
-    int nlog, logcap;
-    const Vec4<S>* P;
-    LeafTile<S> tile;
-    KeyHeap4 hp;
-    double qx, qy, qz;
-    double topd;        // (double) of the heap-top key; 0 for lanes without a query (nothing is ever accepted)
-    float topf, limf;   // limf: fp32 screening limit derived from topf
-    int r0, r1;         // tree-index range bulk-loaded into the heap (skipped during the traversal)
-    int* leaflist;      // [SC_LEAFCAP] node index of every leaf scanned, warp-uniform
-    int nleaf;
-    unsigned lane;
-    __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
-    __device__ __forceinline__ void settop(float k) { topf = k; topd = (double)k; limf = LeafTile<S>::screen_limit(k); }
-    template <bool OVERLAP>
-    __device__ __forceinline__ void scan_tile(int first, int m, unsigned nmask) {
-        // pass 1: one cheap test per candidate (the query itself and coincident particles have d2 == 0 and are weeded out
-        // in pass 2, like bulk-loaded candidates); pass 2: serial insertion rounds over the set bits
-        unsigned acc = 0;
-        STAT(0, 1); STAT(1, m);
-        for (int j0 = 0; j0 < m; j0 += 8) {
-            unsigned a8 = 0;
+// Lock-step prune of the lanes' append buffers (all 32 lanes call it).  Lane state: cnt entries (keys kb[s*32], indices
+// lg[s*32]), all keys <= bound * (1 + 2^-20).  Lanes with cnt > R keep their R smallest keys (FINAL: exactly; otherwise
+// possibly a few more when the rank-R bin holds more than 8 keys) and get bound = largest kept key.  Returns
+// (bound bits << 32 | cnt); cnt = -1: the lane could not be resolved (degenerate keys) and goes to the exact kernel.
+template <bool FINAL>
+__device__ __noinline__ unsigned long long ap_prune(float* kb, int* lg, unsigned char* aux, int cnt, int R, float bound) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = lane_id();
+    bool act = cnt > R;
+    if (!__any_sync(full, act)) return ((unsigned long long)__float_as_uint(bound) << 32) | (unsigned)cnt;
+    STAT(1, 1);
+    float tlo = 0.f, thi = __fmul_ru(bound, AP_WIDEN);
+    int cbelow = 0, level = 0;
+    if (__any_sync(full, act && !(thi <= 3.0e38f))) {
+        // lanes still on the infinite bound: the range is their largest key
+        const int nmax = __reduce_max_sync(full, act ? cnt : 0);
+        float mx = 0.f;
+#pragma unroll 4
+        for (int s = 0; s < nmax; s++) if (s < cnt) mx = fmaxf(mx, kb[s * 32]);
+        if (!(thi <= 3.0e38f)) thi = mx;
+    }
+    unsigned short* myh = reinterpret_cast<unsigned short*>(aux) + lane;      // histogram column: bin b at myh[b*32]
+    float* sk = reinterpret_cast<float*>(aux) + lane;                         // stash keys [8][32]
+    int* si = reinterpret_cast<int*>(aux) + 256 + lane;                       // stash indices [8][32]
+    while (__any_sync(full, act)) {
+        STAT(2, 1);
+        const int nmax = __reduce_max_sync(full, act ? cnt : 0);
+        __syncwarp();
+        {
+            uint4* h4 = reinterpret_cast<uint4*>(aux);
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) if (tile.screen(j0 + jj, limf, topd)) a8 |= 1u << jj;
-            acc |= a8 << j0;
+            for (int i = 0; i < AP_AUX_BYTES / 512; i++) h4[i * 32 + lane] = z;
         }
-        STAT_LANE(4, __popc(acc));
-        while (__any_sync(0xffffffffu, acc != 0)) {
-            STAT(2, 1);
-            if (acc) {
-                const int j = __ffs(acc) - 1;
-                acc &= acc - 1;
-                const int c = first + j;
-                const double d2 = tile.exact(j, qx, qy, qz);
-                if (d2 < topd && d2 > 0.0 && (!OVERLAP || c < r0 || c >= r1)) {
-                    settop(hp.sift(0, __double2float_rn(d2)));
-                    STAT_LANE(3, 1);
-                    if (LOG) { if (nlog < logcap) { *log = c; log += 32; } nlog++; }
+        __syncwarp();
+        const float scale = (thi > tlo) ? 31.99f / (thi - tlo) : 0.f;
+        // ---- histogram of the keys inside [tlo, thi] ------------------------------------------------------
+#pragma unroll 4
+        for (int s = 0; s < nmax; s++) {
+            if (act && s < cnt) {
+                const float key = kb[s * 32];
+                if (key >= tlo && key <= thi) {
+                    const int b = min(__float2int_rz((key - tlo) * scale), 31);
+                    myh[b * 32] += 1;
                 }
             }
         }
-    }
-    __device__ __forceinline__ void leaf(int start, int cnt, int node, unsigned nmask) {
-        if (start >= r0 && start + cnt <= r1) return;
-        if (!LOG) {
-            if (nleaf < SC_LEAFCAP && lane == 0) leaflist[nleaf] = node;
-            nleaf++;
+        // ---- the bin that holds rank R --------------------------------------------------------------------
+        int bstar = -1, cbefore = 0, p = 0;
+        {
+            int cum = cbelow;
+#pragma unroll 8
+            for (int b = 0; b < 32; b++) {
+                const int h = myh[b * 32];
+                if (bstar < 0 && cum + h >= R) { bstar = b; cbefore = cum; p = h; }
+                cum += h;
+            }
         }
-        const bool overlap = start < r1 && start + cnt > r0;
-        for (int base = 0; base < cnt; base += 32) {
-            int m = min(32, cnt - base);
-            __syncwarp();
-            tile.load(P, start + base, m, lane);
-            __syncwarp();
-            if (overlap) scan_tile<true>(start + base, m, nmask);
-            else scan_tile<false>(start + base, m, nmask);
+        if (act && bstar < 0) { cnt = -1; act = false; }            // cannot happen for consistent state; never loop on it
+        const int need = R - cbefore;                                // members of bin bstar that complete the R smallest
+        const bool small = p <= AP_STASH;
+        __syncwarp();                                                // histogram columns are dead: the region becomes the stash
+        // ---- compaction: bins below bstar stay, bins above go, members of bstar go to the stash (or stay) -----
+        int wp = 0, ns = 0;
+        float mn = __int_as_float(0x7f800000), mx = 0.f;
+        for (int s0 = 0; s0 < nmax; s0 += 8) {
+            int id[8];
+            float ky[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const bool in = act && s0 + u < cnt;
+                id[u] = in ? lg[(s0 + u) * 32] : 0;
+                ky[u] = in ? kb[(s0 + u) * 32] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (act && s0 + u < cnt) {
+                    const float key = ky[u];
+                    bool keep = key < tlo, member = false;
+                    if (!keep && key <= thi) {
+                        const int b = min(__float2int_rz((key - tlo) * scale), 31);
+                        keep = b < bstar; member = b == bstar;
+                    }
+                    if (member) {
+                        if (small) { sk[ns * 32] = key; si[ns * 32] = id[u]; ns++; }
+                        else { keep = true; mn = fminf(mn, key); mx = fmaxf(mx, key); }
+                    }
+                    if (keep) { kb[wp * 32] = key; lg[wp * 32] = id[u]; wp++; }
+                }
+            }
+        }
+        if (act) {
+            if (small) {
+                float k8[8]; int i8[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const bool in = u < ns; k8[u] = in ? sk[u * 32] : __int_as_float(0x7f800000); i8[u] = in ? si[u * 32] : -1; }
+                // 19-comparator network for 8 keys (Batcher odd-even merge sort)
+                ap_cex(k8[0], i8[0], k8[1], i8[1]); ap_cex(k8[2], i8[2], k8[3], i8[3]); ap_cex(k8[4], i8[4], k8[5], i8[5]); ap_cex(k8[6], i8[6], k8[7], i8[7]);
+                ap_cex(k8[0], i8[0], k8[2], i8[2]); ap_cex(k8[1], i8[1], k8[3], i8[3]); ap_cex(k8[4], i8[4], k8[6], i8[6]); ap_cex(k8[5], i8[5], k8[7], i8[7]);
+                ap_cex(k8[1], i8[1], k8[2], i8[2]); ap_cex(k8[5], i8[5], k8[6], i8[6]);
+                ap_cex(k8[0], i8[0], k8[4], i8[4]); ap_cex(k8[1], i8[1], k8[5], i8[5]); ap_cex(k8[2], i8[2], k8[6], i8[6]); ap_cex(k8[3], i8[3], k8[7], i8[7]);
+                ap_cex(k8[2], i8[2], k8[4], i8[4]); ap_cex(k8[3], i8[3], k8[5], i8[5]);
+                ap_cex(k8[1], i8[1], k8[2], i8[2]); ap_cex(k8[3], i8[3], k8[4], i8[4]); ap_cex(k8[5], i8[5], k8[6], i8[6]);
+                float b = bound;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (u < need) { kb[wp * 32] = k8[u]; lg[wp * 32] = i8[u]; wp++; b = k8[u]; }
+                }
+                bound = b; cnt = wp; act = false;
+            } else {
+                // more than 8 keys in the rank-R bin: keep the whole bin; the bound is its largest key
+                cnt = wp;
+                if (FINAL) {
+                    cbelow = cbefore; tlo = mn; thi = mx;
+                    if (!(mx > mn) || ++level >= AP_MAX_LEVELS) { cnt = -1; act = false; }      // all keys of the bin equal: exact kernel
+                } else { bound = mx; act = false; }
+            }
         }
     }
-};
+    __syncwarp();
+    return ((unsigned long long)__float_as_uint(bound) << 32) | (unsigned)cnt;
+}
 
 template <class S>
-struct CollectVisitor {
+struct ApVisitor {
     const Vec4<S>* P;
-    LeafTile<S> tile;
-    int* L;            // this lane's column of the [k][32] index list (entry s at L[s*32])
-    double qx, qy, qz;
-    double d2max;
-    double thr_d;      // candidates with d2 >= thr_d cannot qualify (fp64 pre-test)
-    float thr, limf;   // qualify iff RN_fp32(d2) <= thr ; -1 for lanes that collect nothing
-    int cnt, cap;
-    int r0, r1;        // with skip_range: candidates in [r0,r1) are left to the separate scan of the bulk range
-    bool skip_bulk;    // traversal form: leave [r0,r1) out (it was scanned separately)
+    ApTile<S> tile;
+    float* kb;            // shared: this lane's key column, entry s at kb[s*32]
+    int* lg;              // global: this lane's index column, entry s at lg[s*32]
+    unsigned char* aux;   // shared: the warp's histogram / stash region
+    int cnt, cap, R;
+    float bound, limf;    // bound: largest kept key after the last prune (or +inf); limf = bound * (1 + 2^-20), -1: lane accepts nothing
+    bool failed;
     unsigned lane;
-    __device__ __forceinline__ bool need(float lb) const { return lb <= thr; }
-    template <bool SKIP>
-    __device__ __forceinline__ void scan(int start, int n, unsigned nmask) {
+    __device__ __forceinline__ bool need(float lb) const { return lb < limf; }
+    __device__ __forceinline__ void fail() { failed = true; limf = -1.f; cnt = 0; }
+    template <bool FINAL>
+    __device__ __forceinline__ void prune() {
+        const unsigned long long r = ap_prune<FINAL>(kb, lg, aux, failed ? 0 : cnt, R, bound);
+        const int c = (int)(unsigned)(r & 0xffffffffull);
+        if (!failed) {
+            if (c < 0 || (!FINAL && c > cap - 8)) fail();
+            else { cnt = c; bound = __uint_as_float((unsigned)(r >> 32)); limf = __fmul_ru(bound, AP_WIDEN); }
+        }
+    }
+    __device__ __forceinline__ void leaf(int start, int n, int, unsigned) {
         for (int base = 0; base < n; base += 32) {
-            int m = min(32, n - base);
+            const int m = min(32, n - base);
             __syncwarp();
             tile.load(P, start + base, m, lane);
             __syncwarp();
-            unsigned acc = 0;
+            STAT(0, 1);
             for (int j0 = 0; j0 < m; j0 += 8) {
-                unsigned a8 = 0;
+                if (__any_sync(0xffffffffu, cnt > cap - 8)) prune<false>();
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) if (tile.screen(j0 + jj, limf, thr_d)) a8 |= 1u << jj;
-                acc |= a8 << j0;
-            }
-            while (__any_sync(0xffffffffu, acc != 0)) {
-                if (acc) {
-                    const int j = __ffs(acc) - 1;
-                    acc &= acc - 1;
-                    const int c = start + base + j;
-                    const double d2 = tile.exact(j, qx, qy, qz);
-                    if (d2 < thr_d && d2 > 0.0 && __double2float_rn(d2) <= thr && cnt < cap && (!SKIP || c < r0 || c >= r1)) {
-                        L[cnt * 32] = c;
-                        cnt++;
-                        d2max = fmax(d2max, d2);
+                for (int jj = 0; jj < 8; jj++) {
+                    const float a = tile.key(j0 + jj);
+                    if (a <= limf) {
+                        if (a >= AP_TINY && a <= AP_HUGE) { kb[cnt * 32] = a; lg[cnt * 32] = start + base + j0 + jj; cnt++; STAT_LANE(3, 1); }
+                        else if (!tile.coincident(j0 + jj)) fail();     // the query itself and coincident particles are never neighbours
                     }
                 }
             }
         }
     }
-    __device__ __forceinline__ void leaf(int start, int n, int, unsigned nmask) {
-        if (skip_bulk) scan<true>(start, n, nmask);
-        else scan<false>(start, n, nmask);
-    }
 };
 
-// SPH epilogues over a lane's neighbour list L (entry s at L[s*32]; `base` = the warp's shared region, whose part after
-// the list holds the per-lane doubles of the kv < kx velocity-density selection).
+// SPH epilogues over a lane's neighbour list L (entry s at L[s*32], global or shared); D: per-lane doubles [k][32] in shared
+// memory for the kv < kx velocity-density selection.
 template <class S>
-__device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>* __restrict__ P, const int* L, unsigned char* base, unsigned lane,
-                                            int k, int cnt, double d2max, double x0, double y0, double z0, int64_t qi) {
+__device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>* __restrict__ P, const int* L, double* Dbase, unsigned lane,
+                                            int cnt, double d2max, double x0, double y0, double z0, int64_t qi) {
     if (prm.hsm) prm.hsm[qi] = 0.5 * sqrt(d2max);
     if (prm.rho && prm.veldens_k == 0) {
         const double hi = 0.5 * sqrt(d2max);
@@ -923,303 +690,143 @@ __device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>*
                 rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
             }
         } else if (kv > 0) {
-            // kv < kx: exact fp64 selection on a per-lane array of doubles placed after the list (want_doubles layout)
-            double* D = reinterpret_cast<double*>(base + (size_t)k * 32 * 4);
+            // kv < kx: exact fp64 selection on a per-lane array of doubles in shared memory
+            double* D = Dbase + lane;
             for (int s = 0; s < cnt; s++) {
                 Vec4<S> vj = V[L[s * 32]];
-                D[s * 32 + lane] = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
+                D[s * 32] = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
             }
             auto dsift = [&](int p, int n, double d) {
                 while (true) {
                     int c = 2 * p + 1;
                     if (c >= n) break;
-                    double dc = D[c * 32 + lane];
-                    if (c + 1 < n) { double dr = D[(c + 1) * 32 + lane]; if (dr > dc) { c = c + 1; dc = dr; } }
+                    double dc = D[c * 32];
+                    if (c + 1 < n) { double dr = D[(c + 1) * 32]; if (dr > dc) { c = c + 1; dc = dr; } }
                     if (d >= dc) break;
-                    D[p * 32 + lane] = dc;
+                    D[p * 32] = dc;
                     p = c;
                 }
-                D[p * 32 + lane] = d;
+                D[p * 32] = d;
             };
-            for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, D[p * 32 + lane]);
+            for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, D[p * 32]);
             for (int s = kv; s < cnt; s++) {
-                double vd = D[s * 32 + lane];
-                if (vd < D[lane]) dsift(0, kv, vd);
+                double vd = D[s * 32];
+                if (vd < D[0]) dsift(0, kv, vd);
             }
-            const double hi = 0.5 * D[lane];
+            const double hi = 0.5 * D[0];
             const double norm = 1.0 / pow(hi, 3.0);
             for (int e = kv; e > 0; e--) {
-                double r = D[lane] / hi;
+                double r = D[0] / hi;
                 rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
-                dsift(0, e - 1, D[(e - 1) * 32 + lane]);
+                dsift(0, e - 1, D[(e - 1) * 32]);
             }
         }
         prm.rho[qi] = rho;
     }
 }
 
-static inline size_t sc_warp_bytes(int k, bool want_doubles) {
-    int G = heap4_groups(k + 1);
-    size_t keys = (size_t)(G + 1) * 32 * 16, list = (size_t)k * 32 * 4;
-    size_t region = keys > list ? keys : list;
-    if (want_doubles) region = list + (size_t)k * 32 * 8 > region ? list + (size_t)k * 32 * 8 : region;
-    return region + 96 * 8 + TRAV_STACK * 4 + SC_LEAFCAP * 4;
+static inline int ap_capacity(int k) {
+    int c = 2 * k > k + 48 ? 2 * k : k + 48;
+    return (c + 7) & ~7;
+}
+static inline size_t ap_warp_bytes(int k, int cap, bool want_doubles, int tile_bytes) {
+    size_t region = (size_t)cap * 32 * 4;
+    if (want_doubles && (size_t)k * 32 * 8 > region) region = (size_t)k * 32 * 8;
+    return region + AP_AUX_BYTES + tile_bytes + TRAV_STACK * 4;
 }
 
-template <class S>
-__global__ void __launch_bounds__(KNN_WARPS * 32) knn_sc_kernel(KnnParams prm, int want_doubles) {
+template <class S, bool HALO>
+__global__ void __launch_bounds__(KNN_WARPS * 32) knn_ap_kernel(KnnParams prm, int want_doubles, int cap, int* __restrict__ work_counter,
+                                                                int32_t* __restrict__ logbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned full = 0xffffffffu;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    const int k = prm.k, kcap = k + 1;
-    const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
-    size_t region = (size_t)(G + 1) * 32 * 16;
-    if ((size_t)k * 32 * 4 > region) region = (size_t)k * 32 * 4;
-    if (want_doubles && (size_t)k * 32 * 12 > region) region = (size_t)k * 32 * 12;
-    const size_t warp_bytes = region + 96 * 8 + TRAV_STACK * 4 + SC_LEAFCAP * 4;
+    const int k = prm.k, R = k + 1;
+    size_t region = (size_t)cap * 32 * 4;
+    if (want_doubles && (size_t)k * 32 * 8 > region) region = (size_t)k * 32 * 8;
+    const size_t warp_bytes = region + AP_AUX_BYTES + ApTile<S>::TILE_BYTES + TRAV_STACK * 4;
     unsigned char* base = smem_raw + w * warp_bytes;
-    void* tile_mem = base + region;
-    int* stack = reinterpret_cast<int*>(base + region + 96 * 8);
-    int* leaflist = reinterpret_cast<int*>(base + region + 96 * 8 + TRAV_STACK * 4);
-
-    const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
-    const int64_t group = (int64_t)blockIdx.x * KNN_WARPS + w;
-    const int64_t g0 = prm.q0 + group * 32;
-    if (g0 >= prm.q1) return;
-    const int64_t qi = g0 + lane;
-    const bool valid = qi < prm.q1 && (!prm.active || prm.active[qi]);
-    double x0 = 0, y0 = 0, z0 = 0;
-    if (valid) { Vec4<S> c = P[qi]; x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z; }
-    const QueryBox qb = make_qbox(x0, y0, z0);
-    int nleaf, r0i, r1i;
-
-    // ---------------------------------------------------------------------------------------------- select
-    float key_k, key_kp1;
-    {
-        SelectVisitor<S> v;
-        v.P = P; v.lane = lane;
-        v.tile.init(tile_mem, x0, y0, z0);
-        v.leaflist = leaflist; v.nleaf = 0;
-        v.hp.kb = base + lane * 16; v.hp.G = G;
-        const int self = valid ? (int)qi : -1;
-        v.qx = x0; v.qy = y0; v.qz = z0;
-        int64_t want = (int64_t)kcap;
-        int64_t r0 = g0 + 16 - want / 2;
-        if (r0 + want > prm.n) r0 = prm.n - want;
-        if (r0 < 0) r0 = 0;
-        int64_t r1 = r0 + want;
-        if (r1 > prm.n) r1 = prm.n;
-        v.r0 = (int)r0; v.r1 = (int)r1;
-        int filled = 0;
-        for (int64_t b0 = r0; b0 < r1; b0 += 32) {
-            int m = (int)min((int64_t)32, r1 - b0);
-            __syncwarp();
-            v.tile.load(P, (int)b0, m, lane);
-            __syncwarp();
-            for (int j = 0; j < m; j++) {
-                double d2 = v.tile.exact(j, x0, y0, z0);
-                if (valid && (int)(b0 + j) != self && d2 > 0.0) { *v.hp.keyp(filled) = __double2float_rn(d2); filled++; }
-            }
-        }
-        for (; filled < NN; filled++) *v.hp.keyp(filled) = (valid && filled < kcap) ? __uint_as_float(FKEY_INF) : 0.f;
-        for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p));
-        v.settop(v.hp.rootkey());
-        traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
-        key_kp1 = v.hp.rootkey();
-        v.hp.sift(0, 0.f);
-        key_k = v.hp.rootkey();
-        nleaf = v.nleaf; r0i = v.r0; r1i = v.r1;
-    }
-    const bool short_of_k = __float_as_uint(key_k) == FKEY_INF;
-    const bool flagged = valid && key_k == key_kp1 && !short_of_k;
-    if (flagged) {
-        int slot = atomicAdd(prm.flag_count, 1);
-        prm.flag_list[slot] = (int)qi;
-    }
-    __syncwarp();   // the key groups are dead from here on: the region is reused for the index list
-
-    // --------------------------------------------------------------------------------------------- collect
-    CollectVisitor<S> c2;
-    c2.P = P; c2.L = reinterpret_cast<int*>(base) + lane; c2.lane = lane; c2.skip_bulk = false;
-    c2.tile.init(tile_mem, x0, y0, z0);
-    c2.qx = x0; c2.qy = y0; c2.qz = z0;
-    c2.r0 = r0i; c2.r1 = r1i;
-    c2.cnt = 0; c2.cap = k; c2.d2max = 0;
-    c2.thr = (valid && !flagged) ? key_k : -1.f;
-    c2.thr_d = (valid && !flagged) ? (double)__uint_as_float(__float_as_uint(key_k) + (short_of_k ? 0u : 1u)) : -1.0;   // next float above key_k
-    if (short_of_k && valid) c2.thr_d = 3.0e38 * 10.0;
-    c2.limf = LeafTile<S>::screen_limit(c2.thr);
-    const bool collecting = valid && !flagged;
-    if (nleaf <= SC_LEAFCAP) {
-        // every leaf that can hold one of the k nearest was scanned by the select pass (a lane's final neighbours were
-        // below its bound at all times): re-scan exactly those tiles, plus the bulk-loaded range, without walking the tree
-        c2.template scan<false>(r0i, r1i - r0i, 0xffffffffu);
-        for (int t = 0; t < nleaf; t++) {
-            const int node = leaflist[t];
-            const NodeLo lo = prm.nlo[node];
-            const NodeHi hi = prm.nhi[node];
-            const float lb = box_lb(qb.lx, qb.ly, qb.lz, qb.hx, qb.hy, qb.hz, lo, hi);
-            const unsigned nmask = __ballot_sync(0xffffffffu, collecting && c2.need(lb));
-            if (!nmask) continue;                                                  // the bounds have tightened since
-            c2.template scan<true>(lo.start, hi.end - lo.start, nmask);
-        }
-    } else {
-        traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, collecting);
-    }
-    if (!collecting) return;
-
-    // -------------------------------------------------------------------------------------------- epilogues
-    sc_epilogue<S>(prm, P, c2.L, base, lane, k, c2.cnt, short_of_k ? KNN_SENTINEL : c2.d2max, x0, y0, z0, qi);
-}
-
-// =========================================================================================== select + log
-// Same select pass, but every candidate that enters a lane's heap is also appended to the lane's insertion LOG in a
-// global scratch (one [logcap][32] block per resident warp, written once and read once, so it lives in L2).  Every one of
-// the final k nearest was inserted at some point (its d2 was below the lane's bound at all times), so the collect pass
-// is a filter over the log (~1.4 k entries per lane) plus the bulk-loaded range instead of a second scan of ~65 leaf tiles.
-// Persistent grid: warps draw 32-query groups from a global counter, so a warp's scratch block is reused and the
-// grid is exactly one wave whatever the particle count.
-static inline size_t sl_warp_bytes(int k, bool want_doubles, int tile_bytes) {
-    int G = heap4_groups(k + 1);
-    size_t keys = (size_t)(G + 1) * 32 * 16, list = (size_t)k * 32 * 4;
-    size_t region = keys > list ? keys : list;
-    if (want_doubles) region = list + (size_t)k * 32 * 8 > region ? list + (size_t)k * 32 * 8 : region;
-    return region + tile_bytes + TRAV_STACK * 4;
-}
-
-template <class S, int MB, bool HALO>
-__global__ void __launch_bounds__(KNN_WARPS * 32, MB) knn_sl_kernel(KnnParams prm, int want_doubles, int* __restrict__ work_counter,
-                                                                int32_t* __restrict__ logbuf, int logcap) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    const int k = prm.k, kcap = k + 1;
-    const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
-    size_t region = (size_t)(G + 1) * 32 * 16;
-    if ((size_t)k * 32 * 4 > region) region = (size_t)k * 32 * 4;
-    if (want_doubles && (size_t)k * 32 * 12 > region) region = (size_t)k * 32 * 12;
-    const size_t warp_bytes = region + LeafTile<S>::TILE_BYTES + TRAV_STACK * 4;
-    unsigned char* base = smem_raw + w * warp_bytes;
-    void* tile_mem = base + region;
-    int* stack = reinterpret_cast<int*>(base + region + LeafTile<S>::TILE_BYTES);
-    int* log = logbuf + ((size_t)blockIdx.x * KNN_WARPS + w) * (size_t)logcap * 32 + lane;
+    unsigned char* aux = base + region;
+    void* tile_mem = base + region + AP_AUX_BYTES;
+    int* stack = reinterpret_cast<int*>(base + region + AP_AUX_BYTES + ApTile<S>::TILE_BYTES);
+    int* lg = logbuf + ((size_t)blockIdx.x * KNN_WARPS + w) * (size_t)cap * 32 + lane;
+    float* kb = reinterpret_cast<float*>(base) + lane;
 
     const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
     const int64_t ngroups = (prm.q1 - prm.q0 + 31) >> 5;
     while (true) {
         int64_t group = 0;
         if (lane == 0) group = (int64_t)atomicAdd(work_counter, 1);
-        group = __shfl_sync(0xffffffffu, group, 0);
+        group = __shfl_sync(full, group, 0);
         if (group >= ngroups) break;
         const int64_t g0 = prm.q0 + group * 32;
+        const int64_t g1 = g0 + 32 < prm.q1 ? g0 + 32 : prm.q1;
         const int64_t qi = g0 + lane;
         const bool valid = qi < prm.q1 && (!prm.active || prm.active[qi]);
-        if (!__any_sync(0xffffffffu, valid)) continue;
+        if (!__any_sync(full, valid)) continue;
         double x0 = 0, y0 = 0, z0 = 0;
         if (valid) { Vec4<S> c = P[qi]; x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z; }
         const QueryBox qb = make_qbox(x0, y0, z0);
-        int r0i, r1i, nlog;
 
         // ------------------------------------------------------------------------------------------ select
-        float key_k, key_kp1;
+        ApVisitor<S> v;
+        v.P = P; v.lane = lane;
+        v.tile.init(tile_mem, x0, y0, z0);
+        v.kb = kb; v.lg = lg; v.aux = aux;
+        v.cnt = 0; v.cap = cap; v.R = R;
+        v.bound = __int_as_float(0x7f800000);
+        v.limf = valid ? v.bound : -1.f;
+        v.failed = false;
+        traverse_bottom_up(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid, prm.n_tree, g0, g1);
+        if (HALO) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);
+        v.template prune<true>();
+
+        // ------------------------------------------------------------------------ the k nearest and the k-th
+        // three largest keys (m1 >= m2 >= m3) and the slots of the first two
+        int cnt = v.cnt;
+        float m1 = -1.f, m2 = -1.f, m3 = -1.f;
+        int s1 = -1, s2 = -1;
         {
-            SelectVisitor<S, true> v;
-            v.P = P; v.lane = lane;
-            v.tile.init(tile_mem, x0, y0, z0);
-            v.leaflist = nullptr; v.nleaf = 0;
-            v.log = log; v.nlog = 0; v.logcap = logcap;
-            v.hp.kb = base + lane * 16; v.hp.G = G;
-            const int self = valid ? (int)qi : -1;
-            v.qx = x0; v.qy = y0; v.qz = z0;
-            int64_t want = (int64_t)kcap;
-            int64_t r0 = g0 + 16 - want / 2;
-            // ... or, better, the node-aligned block that holds the group: with 2^m particles the tree positions [j*64, (j+1)*64)
-            // are one node, a compact set, whereas a window centred on the group straddles three nodes whose tree-order
-            // neighbours can lie across a high-level cut plane -- a looser first bound and more insertions (k = 64: 428 -> 413 ms)
-            if (prm.bulk_align > 0) r0 = g0 - (g0 % prm.bulk_align);
-            if (r0 + want > prm.n) r0 = prm.n - want;
-            if (r0 < 0) r0 = 0;
-            int64_t r1 = r0 + want;
-            if (r1 > prm.n) r1 = prm.n;
-            v.r0 = (int)r0; v.r1 = (int)r1;
-            int filled = 0;
-            for (int64_t b0 = r0; b0 < r1; b0 += 32) {
-                int m = (int)min((int64_t)32, r1 - b0);
-                __syncwarp();
-                v.tile.load(P, (int)b0, m, lane);
-                __syncwarp();
-                for (int j = 0; j < m; j++) {
-                    double d2 = v.tile.exact(j, x0, y0, z0);
-                    if (valid && (int)(b0 + j) != self && d2 > 0.0) { *v.hp.keyp(filled) = __double2float_rn(d2); filled++; }
+            const int nmax = __reduce_max_sync(full, valid ? cnt : 0);
+#pragma unroll 4
+            for (int s = 0; s < nmax; s++) {
+                if (s < cnt) {
+                    const float key = kb[s * 32];
+                    if (key > m1) { m3 = m2; m2 = m1; s2 = s1; m1 = key; s1 = s; }
+                    else if (key > m2) { m3 = m2; m2 = key; s2 = s; }
+                    else if (key > m3) m3 = key;
                 }
             }
-            for (; filled < NN; filled++) *v.hp.keyp(filled) = (valid && filled < kcap) ? __uint_as_float(FKEY_INF) : 0.f;
-            for (int p = G - 1; p >= 0; p--) v.hp.sift(p, *v.hp.keyp(p));
-            v.settop(v.hp.rootkey());
-            traverse(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid);
-            if (HALO) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);     // attached halo tree: its own instantiation,
-                                                                                          // the second inlined walk costs the plain kernel 3 %
-            key_kp1 = v.hp.rootkey();
-            v.hp.sift(0, 0.f);
-            key_k = v.hp.rootkey();
-            r0i = v.r0; r1i = v.r1; nlog = v.nlog;
         }
-        const bool short_of_k = __float_as_uint(key_k) == FKEY_INF;
-        // inexact key order: the exact kernel redoes the query
-        const bool flagged = valid && key_k == key_kp1 && !short_of_k;
-        if (flagged) {
+        bool flagged = v.failed;
+        int nk = cnt, skth = s1;
+        float kth = m1, below = m2;
+        if (valid && !flagged && cnt == R) {
+            // k+1 entries: the largest is the (k+1)-th neighbour; it leaves, and certifies the set if the gap is wide enough
+            if (!(m1 > __fmul_ru(m2, AP_WIDEN))) flagged = true;
+            const int last = cnt - 1;
+            if (s1 != last) lg[s1 * 32] = lg[last * 32];
+            if (s2 == last) s2 = s1;
+            nk = cnt - 1; skth = s2; kth = m2; below = m3;
+        }
+        const bool short_of_k = nk < k;                     // fewer than k candidates exist: the reference's heap keeps sentinels
+        if (valid && !flagged && !short_of_k && nk >= 2 && !(below < __fmul_rd(kth, AP_NARROW))) flagged = true;
+        if (valid && flagged) {
+            STAT_LANE(4, 1);
             int slot = atomicAdd(prm.flag_count, 1);
             prm.flag_list[slot] = (int)qi;
         }
-        __syncwarp();   // the key groups are dead from here on: the region is reused for the index list
+        __syncwarp();   // the key buffer is dead from here on (the velocity-density selection reuses it)
 
-        // ----------------------------------------------------------------------------------------- collect
-        const bool collecting = valid && !flagged;
-        CollectVisitor<S> c2;
-        c2.P = P; c2.L = reinterpret_cast<int*>(base) + lane; c2.lane = lane; c2.skip_bulk = true;
-        c2.tile.init(tile_mem, x0, y0, z0);
-        c2.qx = x0; c2.qy = y0; c2.qz = z0;
-        c2.r0 = r0i; c2.r1 = r1i;
-        c2.cnt = 0; c2.cap = k; c2.d2max = 0;
-        c2.thr = collecting ? key_k : -1.f;
-        c2.thr_d = collecting ? (double)__uint_as_float(__float_as_uint(key_k) + (short_of_k ? 0u : 1u)) : -1.0;   // next float above key_k
-        if (short_of_k && collecting) c2.thr_d = 3.0e38 * 10.0;
-        c2.limf = LeafTile<S>::screen_limit(c2.thr);
-        c2.template scan<false>(r0i, r1i - r0i, 0xffffffffu);      // the bulk-loaded range
-        const bool overflowed = collecting && nlog > logcap;      // log incomplete: this lane collects by a second traversal
-        {
-            const int mynl = (collecting && !overflowed) ? nlog : 0;
-            const int nmax = __reduce_max_sync(0xffffffffu, mynl);
-            int cnt = c2.cnt;
-            double d2max = c2.d2max;
-            for (int s0 = 0; s0 < nmax; s0 += 4) {
-                int cidx[4];
-                Vec4<S> pc[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) cidx[u] = (s0 + u < mynl) ? log[(s0 + u) * 32] : -1;
-#pragma unroll
-                for (int u = 0; u < 4; u++) if (cidx[u] >= 0) pc[u] = P[cidx[u]];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (cidx[u] >= 0) {
-                        const double d2 = dist2_ref(x0, y0, z0, (double)pc[u].x, (double)pc[u].y, (double)pc[u].z);
-                        if (d2 < c2.thr_d && __double2float_rn(d2) <= c2.thr && cnt < k) {
-                            c2.L[cnt * 32] = cidx[u];
-                            cnt++;
-                            d2max = fmax(d2max, d2);
-                        }
-                    }
-                }
+        // -------------------------------------------------------------------------------------- epilogues
+        if (valid && !flagged) {
+            double d2max = KNN_SENTINEL;
+            if (!short_of_k) {
+                const Vec4<S> c = P[lg[skth * 32]];
+                d2max = dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z);
             }
-            c2.cnt = cnt; c2.d2max = d2max;
+            sc_epilogue<S>(prm, P, lg, reinterpret_cast<double*>(base), lane, nk, d2max, x0, y0, z0, qi);
         }
-        if (__any_sync(0xffffffffu, overflowed)) {
-            const float thr_keep = c2.thr, limf_keep = c2.limf;
-            const double thrd_keep = c2.thr_d;
-            if (!overflowed) { c2.thr = -1.f; c2.thr_d = -1.0; c2.limf = -1.f; }      // the other lanes are complete
-            traverse(prm.nlo, prm.nhi, prm.bucket, stack, c2, qb, overflowed);
-            if (HALO) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, c2, qb, overflowed);
-            c2.thr = thr_keep; c2.limf = limf_keep; c2.thr_d = thrd_keep;
-        }
-        if (collecting) sc_epilogue<S>(prm, P, c2.L, base, lane, k, c2.cnt, short_of_k ? KNN_SENTINEL : c2.d2max, x0, y0, z0, qi);
         __syncwarp();
     }
 }
@@ -1230,16 +837,12 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.nlo2 = t.nlo2; p.nhi2 = t.nhi2; p.bucket2 = t.bucket;
     p.P = t.prim; p.V = t.vel4(); p.mass = t.mass; p.order = t.order;
     p.n = t.n;
+    p.n_tree = t.n_main ? t.n_main : t.n;
     p.q0 = a.q0; p.q1 = a.q1; p.xq = a.xq; p.mode = a.mode;
     p.qlist = a.qlist; p.nq = a.nq;
     p.gather = a.gather ? 1 : 0; p.vq = a.vq;
     p.cand_excl = a.cand_excl; p.crit_mode = a.crit_mode; p.cp0 = a.cp0; p.cp1 = a.cp1;
     p.rho_in = a.rho_in; p.smvel_in = a.smvel_in; p.smvel_out = a.smvel_out; p.smdisp_out = a.smdisp_out;
-    {
-        int al = 32;
-        while (al * 2 <= a.k) al *= 2;                     // largest power of two <= k, at least the 32-query group
-        p.bulk_align = getenv("NBK_KNN_BULK_ALIGN") ? atoi(getenv("NBK_KNN_BULK_ALIGN")) : al;
-    }
     p.k = a.k;
     p.periodic = a.periodic; p.strict = a.strict; p.tree_form = a.tree_form;
     for (int d = 0; d < 3; d++) p.period[d] = t.period[d];
@@ -1264,6 +867,16 @@ static void run_exact(nbk_tree& t, KnnParams& p, int64_t rows) {
     NBK_CHECK(cudaGetLastError());
 }
 
+// tuning overrides of the density kernel (nbk_set_option); the defaults are what ships
+static int g_knn_cap = 0, g_knn_leaf = 0, g_knn_exact = 0;
+bool set_knn_option(const char* name, int64_t value) {
+    const std::string s(name);
+    if (s == "knn_cap") { g_knn_cap = (int)value; return true; }
+    if (s == "knn_leaf") { g_knn_leaf = (int)value; return true; }
+    if (s == "knn_exact") { g_knn_exact = (int)value; return true; }
+    return false;
+}
+
 void launch_knn(nbk_tree& t, const KnnArgs& a) {
     NBK_REQUIRE(a.k >= 1, NBK_ERR_ARG, "k must be >= 1");
     KnnParams p;
@@ -1282,152 +895,50 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     }
     const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm) && !a.gather && !a.qlist && !a.cand_excl && !a.crit_mode &&
                              !a.smvel_out && !a.smdisp_out;
-    if (smooth_only && getenv("NBK_KNN_EXACT_ONLY") == nullptr) {
-        // ---- fast path + exact fallback for the flagged queries ----------------------------------------------
-        p.kcap = a.k + 1;
-        const char* em = getenv("NBK_KNN_MODE");
-        int mode = em ? atoi(em) : 2;           // 2: select + insertion log (default), 1: select-then-collect, 0: (key,index) heap
-        if (t.nlo2) mode = 2;                   // only the default kernel (and the exact one) walk an attached halo tree
-        // nodes of up to `leaf` particles are scanned as one tile: fewer node tests and better balanced insertion rounds
-        // The level whose nodes hold 21..40 particles (exactly one level does: sizes halve) -- a tile and a bit; with a fixed
-        // threshold of 32 a particle count just above a power of two would be scanned as half-empty 16/17-particle tiles.
+    if (smooth_only && !g_knn_exact) {
+        // ---- append + prune kernel, exact kernel for the flagged queries -----------------------------------------
+        p.kcap = a.k;
+        // Nodes of up to `leaf` particles are scanned as one tile: the level whose nodes hold 21..40 particles (exactly one
+        // level does: sizes halve) -- a tile and a bit; with a fixed threshold of 32 a particle count just above a power of
+        // two would be scanned as half-empty 16/17-particle tiles.
         {
-            const char* e = getenv("NBK_KNN_LEAF");
             int64_t sz = t.n_main ? t.n_main : t.n;
             while (sz > 40) sz = (sz + 1) / 2;
-            int leaf = e ? atoi(e) : (int)sz;
+            int leaf = g_knn_leaf > 0 ? g_knn_leaf : (int)sz;
             if (leaf > p.bucket) p.bucket = leaf;
             if (t.nlo2) {
                 sz = t.n - t.n_main;
                 while (sz > 40) sz = (sz + 1) / 2;
-                leaf = e ? atoi(e) : (int)sz;
+                leaf = g_knn_leaf > 0 ? g_knn_leaf : (int)sz;
                 if (leaf > p.bucket2) p.bucket2 = leaf;
             }
         }
         const int want_doubles = (a.veldens_k > 0 && a.veldens_k < a.k) ? 1 : 0;
-        if (mode == 2) {
-            size_t smem = sl_warp_bytes(a.k, want_doubles, t.store_bytes == 4 ? 32 * 16 : 96 * 8) * KNN_WARPS;
-            NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");
-            const char* e = getenv("NBK_KNN_LOGCAP");
-            int logcap = e ? atoi(e) : 4 * a.k;
-            if (logcap < 64) logcap = 64;
-            int nsm = 0, per_sm = 0;
-            NBK_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, t.device));
-            // register budget follows the shared-memory budget: MB = CTAs per SM the kernel is compiled for (5: 96, 6: 80, 8: 64 regs)
-            int fit = (int)(233472 / (smem + 1024));
-            const char* emb = getenv("NBK_KNN_MB");
-            if (emb) fit = atoi(emb);
-            const int mb = fit >= 8 ? 8 : (fit >= 6 ? 6 : 5);
-            const int64_t ngroups = (rows + 31) / 32;
-            DevBuf<int> counters(2);
-            DevBuf<int32_t> flist(rows);
-            DevBuf<int32_t> logbuf;
-            NBK_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), t.stream));
-            p.flag_count = counters.p; p.flag_list = flist.p;
-            bool window = false;
-            size_t old_persist_limit = 0;
-            auto go = [&](auto kern) {
-                NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                NBK_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KNN_WARPS * 32, smem));
-                NBK_REQUIRE(per_sm >= 1, NBK_ERR_ARG, "k too large for the shared-memory heaps");
-                int64_t blocks = (int64_t)nsm * per_sm;
-                if (blocks > (ngroups + KNN_WARPS - 1) / KNN_WARPS) blocks = (ngroups + KNN_WARPS - 1) / KNN_WARPS;
-                logbuf.alloc((size_t)blocks * KNN_WARPS * logcap * 32);
-                // The log is written once and read once by the same warp, then overwritten by the warp's next query group:
-                // pinned in L2 (persisting access window) its lines are rewritten in place and never travel to HBM.
-                if (getenv("NBK_KNN_NO_L2PIN") == nullptr) {
-                    int max_persist = 0, max_window = 0;
-                    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, t.device);
-                    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, t.device);
-                    if (max_persist > 0 && max_window > 0) {
-                        size_t bytes = logbuf.bytes();
-                        size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
-                        cudaDeviceGetLimit(&old_persist_limit, cudaLimitPersistingL2CacheSize);
-                        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-                        cudaStreamAttrValue av;
-                        memset(&av, 0, sizeof(av));
-                        av.accessPolicyWindow.base_ptr = logbuf.p;
-                        av.accessPolicyWindow.num_bytes = win;
-                        av.accessPolicyWindow.hitRatio = win <= (size_t)max_persist ? 1.0f : (float)((double)max_persist / (double)win);
-                        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                        window = cudaStreamSetAttribute(t.stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
-                        if (!window) cudaGetLastError();
-                    }
-                }
-                kern<<<(int)blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles, counters.p + 1, logbuf.p, logcap);
-                if (window) {
-                    cudaStreamAttrValue av;
-                    memset(&av, 0, sizeof(av));
-                    av.accessPolicyWindow.num_bytes = 0;
-                    cudaStreamSetAttribute(t.stream, cudaStreamAttributeAccessPolicyWindow, &av);
-                }
-            };
-            if (t.store_bytes == 4) {
-                if (t.nlo2) { if (mb == 8) go(knn_sl_kernel<float, 8, true>); else if (mb == 6) go(knn_sl_kernel<float, 6, true>); else go(knn_sl_kernel<float, 5, true>); }
-                else if (mb == 8) go(knn_sl_kernel<float, 8, false>); else if (mb == 6) go(knn_sl_kernel<float, 6, false>); else go(knn_sl_kernel<float, 5, false>);
-            } else {
-                if (t.nlo2) { if (mb == 8) go(knn_sl_kernel<double, 8, true>); else if (mb == 6) go(knn_sl_kernel<double, 6, true>); else go(knn_sl_kernel<double, 5, true>); }
-                else if (mb == 8) go(knn_sl_kernel<double, 8, false>); else if (mb == 6) go(knn_sl_kernel<double, 6, false>); else go(knn_sl_kernel<double, 5, false>);
-            }
-            NBK_CHECK(cudaGetLastError());
-#ifdef NBK_STATS
-            {
-                unsigned long long h[8];
-                NBK_CHECK(cudaStreamSynchronize(t.stream));
-                NBK_CHECK(cudaMemcpyFromSymbol(h, g_stats, sizeof(h)));
-                double g = (double)((rows + 31) / 32);
-                fprintf(stderr, "[nbk stats] per warp: tiles %.1f cand %.1f rounds %.1f ; per lane: screened-in %.1f inserted %.1f\n",
-                        h[0] / g, h[1] / g, h[2] / g, h[4] / (double)rows, h[3] / (double)rows);
-                unsigned long long z[8] = {0};
-                NBK_CHECK(cudaMemcpyToSymbol(g_stats, z, sizeof(z)));
-            }
-#endif
-            t.last_launches += 2;
-            int nflag = 0;
-            NBK_CHECK(cudaMemcpyAsync(&nflag, counters.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
-            NBK_CHECK(cudaStreamSynchronize(t.stream));
-            if (window) {
-                // hand the set-aside lines back to the normal L2: the carve-out would otherwise stay in force for every later
-                // kernel of the process (builds and FOF lose ~2/3 of the L2 they stream their node / rank arrays through)
-                cudaCtxResetPersistingL2Cache();
-                if (getenv("NBK_KNN_KEEP_L2_LIMIT") == nullptr) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, old_persist_limit);
-            }
-            t.last_flagged = nflag;
-            if (nflag > 0) {
-                KnnParams pe = p;
-                pe.kcap = a.k;
-                pe.bucket = t.bucket; pe.bucket2 = t.bucket;
-                pe.qlist = flist.p; pe.nq = nflag;
-                pe.flag_count = nullptr; pe.flag_list = nullptr;
-                run_exact(t, pe, nflag);
-                t.last_launches += 1;
-            }
-            return;
-        }
-        size_t warp_bytes = mode == 1 ? sc_warp_bytes(a.k, want_doubles) : fast_warp_bytes(p.kcap);
-        size_t smem = warp_bytes * KNN_WARPS;
-        NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");
-        DevBuf<int> fcount(1);
+        int cap = ap_capacity(a.k);
+        if (g_knn_cap > a.k + 16) cap = (g_knn_cap + 7) & ~7;
+        NBK_REQUIRE(cap < 65536, NBK_ERR_ARG, "k too large");
+        const size_t smem = ap_warp_bytes(a.k, cap, want_doubles, t.store_bytes == 4 ? 32 * 16 : 96 * 8) * KNN_WARPS;
+        NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory candidate buffers");
+        int nsm = 0, per_sm = 0;
+        NBK_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, t.device));
+        const int64_t ngroups = (rows + 31) / 32;
+        DevBuf<int> counters(2);
         DevBuf<int32_t> flist(rows);
-        NBK_CHECK(cudaMemsetAsync(fcount.p, 0, sizeof(int), t.stream));
-        p.flag_count = fcount.p; p.flag_list = flist.p;
-        int blocks = div_up((rows + 31) / 32, KNN_WARPS);
-        if (mode == 1) {
-            if (t.store_bytes == 4) {
-                NBK_CHECK(cudaFuncSetAttribute(knn_sc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                knn_sc_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles);
-            } else {
-                NBK_CHECK(cudaFuncSetAttribute(knn_sc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                knn_sc_kernel<double><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles);
-            }
-        } else if (t.store_bytes == 4) {
-            NBK_CHECK(cudaFuncSetAttribute(knn_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knn_fast_kernel<float><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
-        } else {
-            NBK_CHECK(cudaFuncSetAttribute(knn_fast_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knn_fast_kernel<double><<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
-        }
+        DevBuf<int32_t> logbuf;
+        NBK_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), t.stream));
+        p.flag_count = counters.p; p.flag_list = flist.p;
+        auto go = [&](auto kern) {
+            NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NBK_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KNN_WARPS * 32, smem));
+            NBK_REQUIRE(per_sm >= 1, NBK_ERR_ARG, "k too large for the shared-memory candidate buffers");
+            int64_t blocks = (int64_t)nsm * per_sm;
+            if (blocks > (ngroups + KNN_WARPS - 1) / KNN_WARPS) blocks = (ngroups + KNN_WARPS - 1) / KNN_WARPS;
+            // index log: one [cap][32] block per resident warp, rewritten in place group after group (stays in L2)
+            logbuf.alloc((size_t)blocks * KNN_WARPS * cap * 32);
+            kern<<<(int)blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles, cap, counters.p + 1, logbuf.p);
+        };
+        if (t.store_bytes == 4) { if (t.nlo2) go(knn_ap_kernel<float, true>); else go(knn_ap_kernel<float, false>); }
+        else { if (t.nlo2) go(knn_ap_kernel<double, true>); else go(knn_ap_kernel<double, false>); }
         NBK_CHECK(cudaGetLastError());
 #ifdef NBK_STATS
         {
@@ -1435,20 +946,21 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             NBK_CHECK(cudaStreamSynchronize(t.stream));
             NBK_CHECK(cudaMemcpyFromSymbol(h, g_stats, sizeof(h)));
             double g = (double)((rows + 31) / 32);
-            fprintf(stderr, "[nbk stats] per warp: tiles %.1f cand %.1f rounds %.1f ; per lane: accepted-bits %.1f sifts %.1f\n",
-                    h[0] / g, h[1] / g, h[2] / g, h[4] / (double)rows, h[3] / (double)rows);
+            fprintf(stderr, "[nbk stats] per warp: tiles %.1f prunes %.2f levels %.2f ; per lane: appended %.1f ; flagged %llu\n",
+                    h[0] / g, h[1] / g, h[2] / g, h[3] / (double)rows, h[4]);
             unsigned long long z[8] = {0};
             NBK_CHECK(cudaMemcpyToSymbol(g_stats, z, sizeof(z)));
         }
 #endif
         t.last_launches += 2;
         int nflag = 0;
-        NBK_CHECK(cudaMemcpyAsync(&nflag, fcount.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
+        NBK_CHECK(cudaMemcpyAsync(&nflag, counters.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
         NBK_CHECK(cudaStreamSynchronize(t.stream));
         t.last_flagged = nflag;
         if (nflag > 0) {
             KnnParams pe = p;
             pe.kcap = a.k;
+            pe.bucket = t.bucket; pe.bucket2 = t.bucket;
             pe.qlist = flist.p; pe.nq = nflag;
             pe.flag_count = nullptr; pe.flag_list = nullptr;
             run_exact(t, pe, nflag);

@@ -94,13 +94,11 @@ __device__ __forceinline__ QueryBox make_qbox(double x, double y, double z) {
 // need it) is descended into directly and only the other child goes on the stack, to be re-tested against the
 // lanes' current bounds when popped.
 template <class V, bool ORDERED = false>
-__device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi, int bucket, int* stack, V& v,
-                                         const QueryBox& q, bool on) {
+__device__ __forceinline__ void traverse_from(const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi, int bucket, int* stack, V& v,
+                                              const QueryBox& q, bool on, int root, NodeLo lo, NodeHi hi) {
     const unsigned lane = lane_id();
     int sp = 0;
-    int node = 0;
-    NodeLo lo = nlo[0];
-    NodeHi hi = nhi[0];
+    int node = root;
     unsigned nmask;     // lanes that need `node`
     {
         float lb = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, lo, hi);
@@ -151,6 +149,46 @@ __device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const N
             if (nmask) { found = true; break; }
         }
         if (!found) return;
+    }
+}
+
+template <class V, bool ORDERED = false>
+__device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi, int bucket, int* stack, V& v,
+                                         const QueryBox& q, bool on) {
+    traverse_from<V, ORDERED>(nlo, nhi, bucket, stack, v, q, on, 0, nlo[0], nhi[0]);
+}
+
+// Bottom-up walk for queries that are particles of the tree: `first` .. `last` (tree positions, inclusive range end
+// exclusive) all lie in one node A0, the deepest node that holds the whole group (found by arithmetic: the tree's shape is a
+// function of (n, bucket) only, left = ceil(size / 2)).  A0's subtree is walked first, then the sibling subtree of A0 and of
+// every ancestor up to the root: the near field comes first whatever the lanes' bounds are (they may still be infinite), and
+// the upper levels cost one independent box test each instead of a chain of dependent node loads from the root.  The next
+// sibling's record is loaded before the current subtree is walked.
+template <class V>
+__device__ __forceinline__ void traverse_bottom_up(const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi, int bucket, int* stack, V& v,
+                                                   const QueryBox& q, bool on, int64_t ntree, int64_t first, int64_t last) {
+    int node = 0;
+    {
+        int64_t s = 0, e = ntree;
+        while (e - s > bucket) {
+            const int64_t mid = s + ((e - s + 1) >> 1);
+            if (last <= mid) { node = 2 * node + 1; e = mid; }
+            else if (first >= mid) { node = 2 * node + 2; s = mid; }
+            else break;
+        }
+    }
+    int visit = node, cur = node;
+    NodeLo lo = nlo[node];
+    NodeHi hi = nhi[node];
+    while (true) {
+        const bool more = cur != 0;
+        int nxt = 0;
+        NodeLo lon = lo; NodeHi hin = hi;
+        if (more) { nxt = (cur & 1) ? cur + 1 : cur - 1; lon = nlo[nxt]; hin = nhi[nxt]; }
+        traverse_from(nlo, nhi, bucket, stack, v, q, on, visit, lo, hi);
+        if (!more) break;
+        visit = nxt; lo = lon; hi = hin;
+        cur = (cur - 1) >> 1;
     }
 }
 

@@ -96,6 +96,7 @@ struct KnnArgs {
     double* smdisp_out = nullptr;        // n x 9 (row-major 3x3)
 };
 void launch_knn(nbk_tree& t, const KnnArgs& a);
+bool set_knn_option(const char* name, int64_t value);   // nbk_set_option names starting with "knn_"
 
 // fof.cu
 struct FofArgs {
@@ -110,6 +111,7 @@ struct FofArgs {
     int32_t *head = nullptr, *next = nullptr, *tail = nullptr, *len = nullptr;  // device, optional
 };
 void launch_fof(nbk_tree& t, FofArgs& a);
+bool set_fof_option(const char* name, int64_t value);   // nbk_set_option names starting with "fof_"
 
 // ball.cu
 struct BallArgs {

@@ -150,6 +150,9 @@ class Ref:
             L.ref_order.argtypes = [C.c_void_p, _ip]
             L.ref_knn_particles.restype = C.c_double
             L.ref_knn_particles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_long, _ip, _dp]
+            L.ref_knn_particle_list.restype = C.c_double
+            L.ref_knn_particle_list.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, _ip, _ip, _dp]
+            L.ref_set_threads.argtypes = [C.c_int]
             L.ref_knn_points.restype = C.c_double
             L.ref_knn_points.argtypes = [C.c_void_p, C.c_int, C.c_long, _dp, _ip, _dp]
             L.ref_ball_particles.restype = C.c_long
@@ -250,6 +253,19 @@ class Ref:
         sec = self.lib().ref_knn_particles(self.h, which, k, q0, q1, _i(ids), _d(d2))
         self.last_seconds = sec
         return ids, d2
+
+    def knn_particle_list(self, qids, k, which=0):
+        """FindNearestPos(tt) / FindNearest(tt) for an explicit list of particle IDs"""
+        q = np.ascontiguousarray(qids, dtype=np.int32)
+        ids = np.zeros((len(q), k), dtype=np.int32)
+        d2 = np.zeros((len(q), k))
+        self.last_seconds = self.lib().ref_knn_particle_list(self.h, which, k, len(q), _i(q), _i(ids), _d(d2))
+        return ids, d2
+
+    @classmethod
+    def set_threads(cls, n):
+        """OpenMP thread count of the reference's loops (torchrun exports OMP_NUM_THREADS=1 to its workers)"""
+        cls.lib().ref_set_threads(int(n))
 
     def knn_points(self, x, k):
         x = _f64(x)

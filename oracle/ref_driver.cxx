@@ -117,6 +117,32 @@ double ref_knn_particles(void* hv, int which, int k, long q0, long q1, int* out_
     return now_s() - t0;
 }
 
+/* the same for an explicit list of query IDs (sampled parity checks at sizes where the whole system is too much) */
+double ref_knn_particle_list(void* hv, int which, int k, long m, const int* qids, int* out_ids, double* out_d2) {
+    RefTree* h = (RefTree*)hv;
+    vector<Int_t> where(h->n);
+    for (Int_t i = 0; i < h->n; i++) where[h->parts[i].GetID()] = i;
+    double t0 = now_s();
+#pragma omp parallel
+    {
+        vector<Int_t> nn(k);
+        vector<Double_t> d2(k);
+#pragma omp for schedule(guided)
+        for (long q = 0; q < m; q++) {
+            Int_t tt = where[qids[q]];
+            if (which == 0) h->tree->FindNearestPos(tt, nn.data(), d2.data(), k);
+            else h->tree->FindNearest(tt, nn.data(), d2.data(), k);
+            for (int j = 0; j < k; j++) {
+                out_ids[q * k + j] = nn[j] >= 0 ? (int)h->parts[nn[j]].GetID() : -1;
+                out_d2[q * k + j] = d2[j];
+            }
+        }
+    }
+    return now_s() - t0;
+}
+
+void ref_set_threads(int n) { omp_set_num_threads(n); }
+
 /* kNN around arbitrary positions (m x 3 doubles), FindNearestPos(Double_t*) */
 double ref_knn_points(void* hv, int k, long m, const double* x, int* out_ids, double* out_d2) {
     RefTree* h = (RefTree*)hv;

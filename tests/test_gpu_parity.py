@@ -179,25 +179,49 @@ def test_fp32_key_ties_fall_back_to_exact_heap(nb, port):
         np.testing.assert_allclose(t.CalcVelDensity(7, 18), port.veldensity(pos, vel, 7, 18), rtol=RTOL_RHO)
 
 
-@pytest.mark.parametrize("env", [{"NBK_KNN_LOGCAP": "64"}, {"NBK_KNN_MODE": "1"}, {"NBK_KNN_MODE": "0"},
-                                 {"NBK_KNN_LEAF": "16"}, {"NBK_KNN_EXACT_ONLY": "1"}])
-def test_density_kernel_variants(nb, port, monkeypatch, env):
-    """Every variant of the density kernel gives the oracle's answer: insertion log too small for most lanes (they collect
-    by a second traversal), the older select-then-collect and (key,index)-heap kernels, unmerged leaves, exact fp64 heap only.  Both storage widths."""
+@pytest.mark.parametrize("opt", [{"knn_cap": 56}, {"knn_cap": 64, "knn_leaf": 16}, {"knn_leaf": 64}, {"knn_exact": 1}, {}])
+def test_density_kernel_variants(nb, port, opt):
+    """Every configuration of the density kernel gives the oracle's answer: a candidate buffer barely larger than k (a prune
+    every few candidates), unmerged 16-particle leaves, two-tile leaves, the exact fp64 heap only, and the defaults.  Both
+    storage widths."""
     from nbodylib_b200.synth import clustered_small
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
     n, k = 30011, 40
     pos, vel, mass = clustered_small(n, seed=77)
     orho, oh = port.density(pos, mass, k)
     ovd = port.veldensity(pos, vel, 13, k)
-    for flags in (0, 1 << 4):
-        with nb.KDTree(pos, vel, mass, flags=flags) as t:
+    try:
+        for name, v in opt.items():
+            nb.set_option(name, v)
+        for flags in (0, 1 << 4):
+            with nb.KDTree(pos, vel, mass, flags=flags) as t:
+                rho, h = t.CalcDensity(k, want_h=True)
+                np.testing.assert_allclose(rho, orho, rtol=RTOL_RHO)
+                assert np.array_equal(h, oh)
+                np.testing.assert_allclose(t.CalcVelDensity(13, k), ovd, rtol=RTOL_RHO)
+                np.testing.assert_allclose(t.CalcVelDensity(k, k), port.veldensity(pos, vel, k, k), rtol=RTOL_RHO)
+    finally:
+        for name in opt:
+            nb.set_option(name, 0)
+    with pytest.raises(nb.NbkError):
+        nb.set_option("no_such_option", 1)
+
+
+def test_density_kernel_degenerate_inputs(nb, port):
+    """Inputs that defeat the fp32 keys of the density kernel go to the exact kernel and still match the oracle: many exactly
+    equal distances (a lattice), distances that underflow fp32 (coordinates 1e-25 apart), fewer candidates than k because of
+    coincident particles."""
+    g = np.arange(12, dtype=np.float64) / 16.0
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    rng = np.random.default_rng(3)
+    tiny = (rng.random((700, 3)) * 1e-25).astype(np.float32).astype(np.float64)
+    dup = np.repeat(rng.random((40, 3)).astype(np.float32).astype(np.float64), 30, axis=0)
+    for pos, k in ((lat, 20), (tiny, 12), (dup, 45)):
+        mass = 1.0 + rng.random(len(pos))
+        orho, oh = port.density(pos, mass, k)
+        with nb.KDTree(pos, None, mass) as t:
             rho, h = t.CalcDensity(k, want_h=True)
-            np.testing.assert_allclose(rho, orho, rtol=RTOL_RHO)
             assert np.array_equal(h, oh)
-            np.testing.assert_allclose(t.CalcVelDensity(13, k), ovd, rtol=RTOL_RHO)
-            np.testing.assert_allclose(t.CalcVelDensity(k, k), port.veldensity(pos, vel, k, k), rtol=RTOL_RHO)
+            np.testing.assert_allclose(rho, orho, rtol=RTOL_RHO)
 
 
 def test_tphs_form_a_equals_fof6d_form_b(nb, port):
@@ -419,29 +443,40 @@ def test_fof_linked_lists(nb):
 
 @pytest.mark.parametrize("n,bucket,flags", [(1, 16, 0), (15, 16, 0), (4096, 16, 0), (4097, 16, 0), (8193, 1, 0), (50021, 16, 0), (50021, 3, 1 << 4),
                                             (300007, 16, 0), (300007, 100, 1 << 4), (131072, 1024, 0)])
-def test_build_v2_equals_v1(nb, monkeypatch, n, bucket, flags):
-    """The rank-space build (global levels + one shared-memory kernel for nodes <= 4096 particles) produces exactly the
-    tree of the first level-parallel build: same particle order, same node ranges, bounds and cut dimensions.
-    Sizes straddle the shared-memory capacity, ties come from a coarse coordinate grid."""
+def test_build_structure(nb, n, bucket, flags):
+    """The rank-space build (global levels + one shared-memory kernel for nodes <= 4096 particles) obeys the reference's
+    build rule node by node (KDTree.cxx:459-504, 994, 1012): ranges from left = ceil(size / 2), leaf iff size <= bucket, cut
+    dimension = largest extent (ties -> lowest dimension), tight bounds, every left particle <= every right particle in the
+    cut dimension.  Sizes straddle the shared-memory capacity, ties come from a coarse coordinate grid."""
     rng = np.random.default_rng(n + bucket)
     pos = rng.random((n, 3))
     pos[: n // 3] = np.round(pos[: n // 3] * 64) / 64           # many exactly equal coordinates -> ties at the medians
     pos = pos.astype(np.float32).astype(np.float64)
-    out = []
-    for mode in ("1", "2"):
-        monkeypatch.setenv("NBK_BUILD", mode)
-        with nb.KDTree(pos, None, None, bucket_size=bucket, flags=flags) as t:
-            out.append((t.order(), t.nodes(), t.GetNumNodes(), t.GetNumLeafNodes()))
-    (o1, nd1, nn1, nl1), (o2, nd2, nn2, nl2) = out
-    assert (nn1, nl1) == (nn2, nl2)
-    assert np.array_equal(o1, o2)
-    s1, e1, c1, b1 = nd1
-    s2, e2, c2, b2 = nd2
-    present = s1 >= 0
-    assert np.array_equal(present, s2 >= 0)
-    assert np.array_equal(s1[present], s2[present]) and np.array_equal(e1[present], e2[present]) and np.array_equal(c1[present], c2[present])
-    assert np.array_equal(b1[present], b2[present])
-    assert int(present.sum()) == nn1
+    with nb.KDTree(pos, None, None, bucket_size=bucket, flags=flags) as t:
+        order, (s, e, c, b), nn, nl = t.order(), t.nodes(), t.GetNumNodes(), t.GetNumLeafNodes()
+    assert np.array_equal(np.sort(order), np.arange(n))
+    P = pos[order]
+    present = s >= 0
+    assert int(present.sum()) == nn
+    stack, seen, leaves = [(0, 0, n)], 0, 0
+    while stack:
+        node, lo, hi = stack.pop()
+        assert (s[node], e[node]) == (lo, hi)
+        seen += 1
+        Q = P[lo:hi]
+        assert np.array_equal(b[node, 0::2], Q.min(0).astype(np.float32)) and np.array_equal(b[node, 1::2], Q.max(0).astype(np.float32))
+        if hi - lo <= bucket:
+            assert c[node] < 0
+            leaves += 1
+            continue
+        ext = Q.max(0) - Q.min(0)
+        cd = int(np.argmax(ext))                                # first maximum = lowest dimension on ties
+        assert c[node] == cd
+        mid = lo + (hi - lo + 1) // 2
+        assert P[lo:mid, cd].max() <= P[mid:hi, cd].min()
+        stack.append((2 * node + 1, lo, mid))
+        stack.append((2 * node + 2, mid, hi))
+    assert (seen, leaves) == (nn, nl)
 
 
 @pytest.mark.parametrize("periodic", [False, True])

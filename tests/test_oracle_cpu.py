@@ -104,6 +104,28 @@ def test_port_vs_live_reference(port):
         R.close()
 
 
+def test_full_host_density_loop_equals_library_calcdensity():
+    """The full-host OpenMP kNN-density loop that bench.py times and the scale-parity tests check against (oracle/ref_driver.cxx
+    ref_calc_density_omp: the caller-side omp loop over FindNearestPos of src/tests/test_kdtree.cxx:279-301 + the accumulation
+    of KDCalcSmoothQuantities.cxx:260-300) gives the library's serial CalcDensity up to the summation order; the explicit-list
+    kNN entry point equals the range form."""
+    from oracle.pyoracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    from nbodylib_b200.synth import clustered_small
+    pos, vel, mass = clustered_small(20000, seed=314)
+    R = Ref(pos, vel, mass, period=None)
+    Ref.set_threads(4)
+    a = R.calc_density_omp(32)
+    b = R.calc_density(32)
+    np.testing.assert_allclose(a, b, rtol=1e-12)
+    q = np.random.default_rng(0).permutation(20000)[:500].astype(np.int32)
+    ids, d2 = R.knn_particle_list(q, 32)
+    ids_all, d2_all = R.knn_particles(32)
+    assert np.array_equal(ids, ids_all[q]) and np.array_equal(d2, d2_all[q])
+    R.close()
+
+
 def test_reference_tree_shape_known_answer():
     """N=1e6, b=16 -> 131071 nodes / 65536 leaves: the closed-form shape used by the device build."""
     def shape(n, b):
