@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K_NN = 64
-ALG_BYTES = {"knn_density": 24, "veldensity": 36, "fof3d": 24, "build": 36}
+ALG_BYTES = {"knn_density": 24, "veldensity": 36, "fof3d": 24, "fof6d": 36, "build": 36}
 
 
 def measured_peak():
@@ -101,10 +101,11 @@ def sample_subvolume(pos, vel, mass, frac_side=0.25):
     return pos[sel].double().cpu().numpy(), vel[sel].double().cpu().numpy(), mass[sel].double().cpu().numpy()
 
 
-def cpu_reference_leg(pos, vel, mass, k, steps=1, warmup=0, fof_ll=None):
+def cpu_reference_leg(pos, vel, mass, k, steps=1, warmup=0, fof_ll=None, fof6d_params=None, check_queries=0):
     """The reference's CPU path on the host cores: full-host OpenMP kNN-density (BASELINE.md section 3 variant ii:
     omp-parallel loop over FindNearestPos + the CalcDensity accumulation) through oracle/_ref when it is present
-    ('reference'), else the brute-force port ('port')."""
+    ('reference'), else the brute-force port ('port').  Optionally the library's (serial) FOF / FOFCriterion(FOF6d), and the
+    reference's neighbour distances of `check_queries` sample particles + its FOF labels for bench.py's self-check."""
     from oracle import pyoracle
     n = len(pos)
     if pyoracle.have_ref():
@@ -119,17 +120,32 @@ def cpu_reference_leg(pos, vel, mass, k, steps=1, warmup=0, fof_ll=None):
             ts.append(R.last_seconds)
         cores = pyoracle.Ref.max_threads()
         build_s = R.build_seconds
-        fof_s = None
+        out = {"kind": "reference", "cores": cores, "seconds": ts, "n": n, "build_seconds": build_s, "fof_seconds": None, "check": None}
+        if check_queries:
+            q = np.sort(np.random.default_rng(7).choice(n, min(check_queries, n), replace=False)).astype(np.int32)
+            _, d2 = R.knn_particle_list(q, k)
+            out["check"] = {"qids": q, "d2": d2}
         if fof_ll is not None:
-            R.fof(fof_ll, 20, 1)               # the library's FOF is serial (KDFOF.cxx:70-107): "full host" == 1 core
-            fof_s = R.last_seconds
+            g, _ = R.fof(fof_ll, 20, 1)               # the library's FOF is serial (KDFOF.cxx:70-107): "full host" == 1 core
+            out["fof_seconds"] = R.last_seconds
+            if out["check"] is not None:
+                out["check"]["fof"] = g
         R.close()
-        return {"kind": "reference", "cores": cores, "seconds": ts, "n": n, "build_seconds": build_s, "fof_seconds": fof_s}
+        if fof6d_params is not None:
+            # FOFCriterion walks every leaf its pruning radius touches with the criterion: ~5x the cost of FOF per particle, so a
+            # smaller sample (1/8 of the sub-cube) keeps the leg bounded
+            half = pos.max() / 2.0
+            s6 = (pos[:, 0] < half) & (pos[:, 1] < half) & (pos[:, 2] < half)
+            R6 = pyoracle.Ref(pos[s6], vel[s6], mass[s6], period=None)
+            R6.fof_criterion(2, fof6d_params, 20, 1)
+            out["fof6d_seconds"], out["fof6d_n"] = R6.last_seconds, int(s6.sum())
+            R6.close()
+        return out
     P = pyoracle.Port()
     m = min(n, 20000)
     t0 = time.time()
     P.density(pos[:m], mass[:m], k)
-    return {"kind": "port", "cores": os.cpu_count(), "seconds": [time.time() - t0], "n": m, "build_seconds": 0.0, "fof_seconds": None}
+    return {"kind": "port", "cores": os.cpu_count(), "seconds": [time.time() - t0], "n": m, "build_seconds": 0.0, "fof_seconds": None, "check": None}
 
 
 def run_reference_arm(args, rank, world):
@@ -251,20 +267,48 @@ def main():
     ms_step = dev_s * 1e3 / args.steps
     value = n * world / (dev_s / args.steps)
 
+    # ---- untimed self-check of the timed step (N = 1): the same CalcDensity through the INDEPENDENT fp64-heap kernel ------
+    checked = None
+    if world == 1:
+        from nbodylib_b200 import set_option
+        h1 = torch.empty(n, dtype=torch.float64, device="cuda")
+        rho2 = torch.empty(n, dtype=torch.float64, device="cuda")
+        h2 = torch.empty(n, dtype=torch.float64, device="cuda")
+        tree.CalcDensityInto(K_NN, rho, h1)
+        flagged = int(tree.info.last_flagged)
+        set_option("knn_exact", 1)
+        try:
+            tree.CalcDensityInto(K_NN, rho2, h2)
+            heap_ms = float(tree.info.last_kernel_ms)
+        finally:
+            set_option("knn_exact", 0)
+        checked = {"against": "knn_exact_kernel (fp64 (d2, index) heap per query, the kernel behind FindNearest; bit-exact against the reference at 1 M in tests/)",
+                   "particles": n, "h_mismatches": int((h1 != h2).sum().item()),
+                   "rho_max_rel_diff": float(((rho - rho2).abs() / rho2.abs().clamp_min(1e-300)).max().item()),
+                   "queries_rerun_by_exact_kernel": flagged, "exact_kernel_ms": heap_ms}
+        checked["ok"] = checked["h_mismatches"] == 0 and checked["rho_max_rel_diff"] < 1e-10
+        del rho2, h2
+        progress("self-check done")
+
     # ---- other stages of the same resident tree (rank-local), each K steps ------------------------------------
     extra = {}
+    rows = {}
     if world == 1:
         g = torch.empty(n, dtype=torch.int32, device="cuda")
-        ts = []
-        for _ in range(args.steps):
+        ts, ks = [], []
+        for it in range(2 + args.steps):
             torch.cuda.synchronize(); t1 = time.perf_counter()
             _, ngroups = tree.FOF(0.2 / ng, 20, 1, out=g)
-            torch.cuda.synchronize(); ts.append(time.perf_counter() - t1)
-        extra["fof3d_particles_per_s"] = n / float(np.mean(ts))
-        extra["fof3d_ms"] = float(np.mean(ts)) * 1e3
-        extra["fof3d_link_kernel_ms"] = tree.info.last_kernel_ms
-        extra["fof3d_groups"] = int(ngroups)
-        extra["fof3d_hbm_frac"] = n * ALG_BYTES["fof3d"] / (tree.info.last_kernel_ms * 1e-3) / 1e9 / peak
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(time.perf_counter() - t1); ks.append(tree.info.last_kernel_ms)
+        fof_ms, fof_kms = float(np.mean(ts)) * 1e3, float(np.mean(ks))
+        rows["fof3d"] = {"metric": "fof3d_particles_per_s", "value": n / (fof_ms * 1e-3), "unit": "particles/s", "ms_per_step": fof_ms,
+                         "call": "KDTree::FOF(0.2 mean spacings, minnum 20, order 1), periodic; group ids stay on the device", "groups": int(ngroups),
+                         "roofline": {"bound": "hbm", "kernel": "fof_link3f_kernel", "kernel_ms": fof_kms, "algorithmic_bytes_per_particle": ALG_BYTES["fof3d"],
+                                      "achieved": n * ALG_BYTES["fof3d"] / (fof_kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": n * ALG_BYTES["fof3d"] / (fof_kms * 1e-3) / 1e9 / peak, "traffic": None}}
+        g_fof3d = g
         ts = []
         for _ in range(max(1, args.steps // 2)):
             torch.cuda.synchronize(); t1 = time.perf_counter()
@@ -276,24 +320,34 @@ def main():
         params = np.zeros(10)
         params[1] = params[6] = (0.2 / ng) ** 2
         params[2] = params[7] = (1.25 ** 2) * sv2
-        torch.cuda.synchronize(); t1 = time.perf_counter()
-        g6, ng6 = tree.FOFCriterion(2, params, 20, 1)
-        torch.cuda.synchronize()
-        extra["fof6d_particles_per_s"] = n / (time.perf_counter() - t1)
-        extra["fof6d_link_kernel_ms"] = tree.info.last_kernel_ms
-        extra["fof6d_groups"] = int(ng6)
-        extra["fof6d_note"] = "FOFCriterion(FOF6d), host group array returned (includes 0.5 GB D2H)"
+        g6 = torch.empty(n, dtype=torch.int32, device="cuda")
+        ts, ks = [], []
+        for it in range(1 + max(2, args.steps // 2)):
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            _, ng6 = tree.FOFCriterion(2, params, 20, 1, out=g6)
+            torch.cuda.synchronize()
+            if it >= 1:
+                ts.append(time.perf_counter() - t1); ks.append(tree.info.last_kernel_ms)
+        f6_ms, f6_kms = float(np.mean(ts)) * 1e3, float(np.mean(ks))
+        rows["fof6d"] = {"metric": "fof6d_particles_per_s", "value": n / (f6_ms * 1e-3), "unit": "particles/s", "ms_per_step": f6_ms,
+                         "call": "KDTree::FOFCriterion(FOF6d, ll_x = 0.2 spacings, ll_v = 1.25 sigma_v, minnum 20, order 1), periodic; group ids stay on the device",
+                         "groups": int(ng6),
+                         "roofline": {"bound": "hbm", "kernel": "fof_link_kernel<float> (6D predicate)", "kernel_ms": f6_kms, "algorithmic_bytes_per_particle": ALG_BYTES["fof6d"],
+                                      "achieved": n * ALG_BYTES["fof6d"] / (f6_kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": n * ALG_BYTES["fof6d"] / (f6_kms * 1e-3) / 1e9 / peak, "traffic": None}}
         del g6
-        del g
         # tree build from device-resident arrays, K times (the first build of the process also pays for growing the memory pool)
         bms = []
         for _ in range(max(2, args.steps)):
             with KDTree(pos, vel, mass, Period=period, device=local) as tb:
                 bms.append(tb.info.build_ms)
-        extra["build_ms"] = float(np.mean(bms[1:]))
-        extra["build_ms_first"] = float(info.build_ms)
-        extra["build_particles_per_s"] = n / (extra["build_ms"] * 1e-3)
-        extra["build_hbm_frac"] = n * ALG_BYTES["build"] / (extra["build_ms"] * 1e-3) / 1e9 / peak
+        build_ms = float(np.mean(bms[1:]))
+        rows["build"] = {"metric": "build_particles_per_s", "value": n / (build_ms * 1e-3), "unit": "particles/s", "ms_per_step": build_ms,
+                         "call": "KDTree(Particle*, N, bucket 16): radix sorts + rank-space level loop + shared-memory small-node kernel, device-resident input",
+                         "first_build_ms": float(info.build_ms),
+                         "roofline": {"bound": "hbm", "kernel": "whole build (28 launches; v2_scatter_kernel dominates)", "kernel_ms": build_ms,
+                                      "algorithmic_bytes_per_particle": ALG_BYTES["build"], "achieved": n * ALG_BYTES["build"] / (build_ms * 1e-3) / 1e9,
+                                      "peak": peak, "unit": "GB/s", "frac": n * ALG_BYTES["build"] / (build_ms * 1e-3) / 1e9 / peak, "traffic": None}}
     if world > 1:
         extra["sharded_rank0"] = dict(tree.stats)
     if world > 1 and os.environ.get("BENCH_SHARDED_FOF"):
@@ -344,39 +398,112 @@ def main():
     if not args.no_e2e and world == 1:
         hp, hv, hm = (x.cpu().pin_memory().numpy() for x in (pos, vel, mass))
         out = torch.empty(n, dtype=torch.float64).pin_memory().numpy()      # the caller's (pinned) result buffer
-        ts = []
-        for it in range(1 + max(1, args.steps // 2)):
-            t1 = time.perf_counter()
+        outg = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
+        reps = 1 + max(1, args.steps // 2)
+
+        def e2e_loop(body):
+            ts = []
+            for it in range(reps):
+                t1 = time.perf_counter()
+                body()
+                if it > 0:
+                    ts.append(time.perf_counter() - t1)
+            return float(np.mean(ts))
+
+        def e2e_density():
             with KDTree(hp, hv, hm, Period=period, device=local) as t2:
                 t2.CalcDensity(K_NN, out=out)
-            if it > 0:
-                ts.append(time.perf_counter() - t1)
-        e2e = {"value": n / float(np.mean(ts)), "unit": "particles/s", "h2d_bytes_per_step": int(hp.nbytes + hv.nbytes + hm.nbytes),
-               "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": float(np.mean(ts)) * 1e3,
+
+        def e2e_fof3d():
+            with KDTree(hp, None, None, Period=period, device=local) as t2:
+                t2.FOF(0.2 / ng, 20, 1, out=outg)
+
+        def e2e_fof6d():
+            with KDTree(hp, hv, None, Period=period, device=local) as t2:
+                t2.FOFCriterion(2, params, 20, 1, out=outg)
+
+        def e2e_build():
+            with KDTree(hp, hv, hm, Period=period, device=local):
+                pass
+
+        dt = e2e_loop(e2e_density)
+        e2e = {"value": n / dt, "unit": "particles/s", "h2d_bytes_per_step": int(hp.nbytes + hv.nbytes + hm.nbytes),
+               "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": dt * 1e3,
                "includes": "H2D of pos/vel/mass (fp32, pinned host arrays), tree build, CalcDensity(64), D2H of rho (fp64, pinned host array)"}
+        dt = e2e_loop(e2e_fof3d)
+        rows["fof3d"]["e2e"] = {"value": n / dt, "unit": "particles/s", "h2d_bytes_per_step": int(hp.nbytes), "d2h_bytes_per_step": int(outg.nbytes),
+                                "ms_per_step": dt * 1e3, "includes": "H2D of pos (fp32, pinned), tree build, FOF, D2H of the group ids (int32, pinned)"}
+        dt = e2e_loop(e2e_fof6d)
+        rows["fof6d"]["e2e"] = {"value": n / dt, "unit": "particles/s", "h2d_bytes_per_step": int(hp.nbytes + hv.nbytes), "d2h_bytes_per_step": int(outg.nbytes),
+                                "ms_per_step": dt * 1e3, "includes": "H2D of pos/vel (fp32, pinned), tree build, FOFCriterion(FOF6d), D2H of the group ids (int32, pinned)"}
+        dt = e2e_loop(e2e_build)
+        rows["build"]["e2e"] = {"value": n / dt, "unit": "particles/s", "h2d_bytes_per_step": int(hp.nbytes + hv.nbytes + hm.nbytes), "d2h_bytes_per_step": 0,
+                                "ms_per_step": dt * 1e3, "includes": "H2D of pos/vel/mass (fp32, pinned), tree build (nothing is read back: the tree stays on the device)"}
+        del hp, hv, hm, out, outg
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only) -------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         frac = sample_fraction(ng)
-        sp, sv, sm = sample_subvolume(pos, vel, mass, frac)
-        leg = cpu_reference_leg(sp, sv, sm, K_NN, fof_ll=0.2 / ng)
+        sel = (pos[:, 0] < frac) & (pos[:, 1] < frac) & (pos[:, 2] < frac)
+        sp, sv, sm = pos[sel].double().cpu().numpy(), vel[sel].double().cpu().numpy(), mass[sel].double().cpu().numpy()
+        leg = cpu_reference_leg(sp, sv, sm, K_NN, fof_ll=0.2 / ng, fof6d_params=params, check_queries=200000)
         dt = float(np.mean(leg["seconds"]))
-        if leg.get("fof_seconds"):
-            extra["cpu_fof3d_particles_per_s"] = leg["n"] / leg["fof_seconds"]
-            extra["cpu_fof3d_note"] = "reference KDTree::FOF (serial in the library) on the same sub-cube sample, non periodic"
-            extra["cpu_build_particles_per_s"] = leg["n"] / leg["build_seconds"] if leg["build_seconds"] else None
+        sample_txt = "all %d particles of the sub-cube [0,%.2f)^3 of the same box, tree built over the sample only" % (leg["n"], frac)
         cpu = {"value": leg["n"] / dt, "unit": "particles/s", "cores": leg["cores"], "kind": leg["kind"],
-               "sample": "all %d particles of the sub-cube [0,%.2f)^3 of the same box, full-host OpenMP kNN(k=%d)+density accumulation (BASELINE.md 3, variant ii), tree built over the sample only" % (leg["n"], frac, K_NN),
-               "seconds": dt}
+               "sample": sample_txt + "; full-host OpenMP kNN(k=%d)+density accumulation (BASELINE.md 3, variant ii)" % K_NN, "seconds": dt}
+        if leg.get("fof_seconds"):
+            rows["fof3d"]["cpu_baseline"] = {"value": leg["n"] / leg["fof_seconds"], "unit": "particles/s", "cores": 1, "kind": leg["kind"],
+                                             "sample": sample_txt + "; KDTree::FOF is serial in the library (KDFOF.cxx:70-107), non periodic", "seconds": leg["fof_seconds"]}
+        if leg.get("fof6d_seconds"):
+            rows["fof6d"]["cpu_baseline"] = {"value": leg["fof6d_n"] / leg["fof6d_seconds"], "unit": "particles/s", "cores": 1, "kind": leg["kind"],
+                                             "sample": "the first %d particles of that sample's tree order region [0,%.3f)^3; KDTree::FOFCriterion(FOF6d) is serial in the library, non periodic" % (leg["fof6d_n"], frac / 2),
+                                             "seconds": leg["fof6d_seconds"]}
+        if leg.get("build_seconds"):
+            rows["build"]["cpu_baseline"] = {"value": leg["n"] / leg["build_seconds"], "unit": "particles/s", "cores": leg["cores"], "kind": leg["kind"],
+                                             "sample": sample_txt + "; KDTree constructor (OpenMP tasks over subtrees, KDTree.cxx:1015-1053)", "seconds": leg["build_seconds"]}
+        # ---- the device results against the reference on the sample, where the sample's answer is the whole box's answer --------
+        if checked is not None and leg.get("check") is not None:
+            ck = leg["check"]
+            sid = torch.nonzero(sel).flatten()
+            face = np.minimum(sp, frac - sp).min(1)                     # distance of every sample particle to the sub-cube's faces
+            q = ck["qids"]
+            rk = np.sqrt(ck["d2"][:, -1])
+            inner = rk < face[q]                                         # the reference's k-ball lies inside the sub-cube: its k nearest in the sample are its k nearest in the box
+            h_dev = h1[sid[torch.from_numpy(q[inner].astype(np.int64)).cuda()]].cpu().numpy()
+            checked["reference_on_sample"] = {
+                "queries": int(len(q)), "with_k_ball_inside_the_sample": int(inner.sum()),
+                "h_mismatches": int((h_dev != 0.5 * rk[inner]).sum())}
+            checked["ok"] = checked["ok"] and checked["reference_on_sample"]["h_mismatches"] == 0 and int(inner.sum()) > 0
+            # FOF: a sample group none of whose members lies within one linking length of a sub-cube face is a group of the box
+            gs = ck["fof"]
+            gd = g_fof3d[sid].cpu().numpy()
+            ll = 0.2 / ng
+            ngs = int(gs.max())
+            near = np.zeros(ngs + 1, dtype=bool)
+            near[np.unique(gs[face < ll])] = True
+            near[0] = True
+            safe = ~near[gs]                                              # members of interior sample groups
+            lab_s, lab_d = gs[safe], gd[safe]
+            first = np.full(ngs + 1, -1, dtype=np.int64)
+            first[lab_s] = lab_d
+            same_label = bool(np.array_equal(first[lab_s], lab_d)) and bool((lab_d > 0).all())
+            size_s = np.bincount(lab_s, minlength=ngs + 1)
+            size_d_all = torch.bincount(g_fof3d.long()).cpu().numpy()
+            grp = np.nonzero(size_s)[0]
+            same_size = bool(np.array_equal(size_s[grp], size_d_all[first[grp]])) if same_label else False
+            checked["reference_fof_on_sample"] = {"interior_groups": int(len(grp)), "members": int(safe.sum()), "one_device_group_each": same_label,
+                                                  "sizes_equal": same_size}
+            checked["ok"] = checked["ok"] and same_label and same_size and len(grp) > 0
 
     if rank == 0:
         kms = float(np.mean(kernel_ms))
         achieved = n * ALG_BYTES["knn_density"] / (kms * 1e-3) / 1e9
-        traffic = None
+        traffic, ncu_facts = None, {}
         tp = os.path.join(ROOT, "profiles", "knn_density_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_particle", 0) * n
+            ncu_facts = json.load(open(tp))
+            traffic = ncu_facts.get("dram_bytes_per_particle", 0) * n
         line = {
             "metric": "knn_density_particles_per_s", "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -385,15 +512,16 @@ def main():
                        "particles_per_gpu": n, "k": K_NN, "storage": "fp32 coordinates (exact), fp64 distance arithmetic",
                        "l2": "inputs (%.1f GB) exceed L2, no flush needed" % (n * 16 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "knn_sl_kernel<float,6,false>", "kernel_ms": kms,
+                         "peak_source": peak_src, "kernel": "knn_ap_kernel<float,false>", "kernel_ms": kms,
                          "algorithmic_bytes_per_particle": ALG_BYTES["knn_density"],
-                         "note": "issue-slot bound tree traversal, not HBM bound: see DESIGN.md section 4; traffic = measured DRAM bytes of one launch (ncu), dominated by the insertion log",
-                         "issue_active_pct_ncu": 65.7, "warp_instructions_per_particle_ncu": 2404,
-                         "ncu_source": "profiles/r1_07_knn_select_log_512cube_k64.txt (full capture of this kernel body), profiles/r1_09_launches_bench_512cube_final_summary.txt (launch list of this command)"},
+                         "note": "issue-slot bound tree traversal + selection, not HBM bound: see DESIGN.md section 4; traffic = measured DRAM bytes of one launch (ncu)",
+                         **ncu_facts},
             "timer": "CUDA events around the K steps (barrier + device synchronize on both sides), max over ranks; wall_ms_per_step = host clock around the same region; library_ms_per_step = the library's own CUDA events around each call on its stream",
             "wall_ms_per_step": wall * 1e3 / args.steps, "library_ms_per_step": float(np.mean(call_ms)),
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checked": checked, "rows": rows, "extra": extra,
         }
+        for r in rows.values():
+            r["roofline"]["peak_source"] = peak_src
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -237,9 +237,18 @@ int nbk_attach_halo(nbk_tree* t, nbk_tree* halo);
  * memory back to the driver (e.g. before another library needs the HBM). */
 int nbk_release_cached_memory(int device);
 
+/* Building blocks of a domain-decomposed FOF (VELOCIraptor stitches its MPI domains outside the library; here
+ * the slab-sharded driver does): the components of FOF (criterion < 0: KDTree::FOF(fdist), KDFOF.cxx:29-153) or FOFCriterion
+ * (NBK_FOF3D / NBK_FOF6D with the reference's params[], KDFOF.cxx:157-265) WITHOUT the minnum filter and the numbering:
+ * root[ID] = ID of one fixed member of the particle's component (the same for all its members), -1 for particles excluded
+ * by precheck.  NBK_DEVICE_PTRS: precheck / root are device pointers. */
+int nbk_fof_roots(nbk_tree* t, int criterion, double fdist, const double* params, const int32_t* precheck, int32_t* root, int flags);
+/* Connected components of an explicit edge list on the device (the cross-domain merge step): nodes 0..nnodes-1, edges
+ * (a[i], b[i]); root[v] = smallest node of v's component.  a, b, root are DEVICE pointers on `device` (-1: the current one). */
+int nbk_union_pairs(int device, int64_t nnodes, int64_t npairs, const int32_t* a, const int32_t* b, int32_t* root);
+
 /* Process-wide tuning overrides (none is needed for correct results; the defaults are what the benchmarks run).  No
  * reference counterpart: the reference's only knobs are constructor arguments.  Names:
- *   "knn_cap"     per-query candidate buffer of the density kernel (entries; 0 = default max(2k, k+48))
  *   "knn_leaf"    particles per scanned tile of the density kernel (0 = the tree level holding 21..40 particles)
  *   "knn_exact"   1: the Calc* family runs on the fp64-heap kernel only
  *   "fof_screen"  0: the 3D link kernel skips its fp32 screen

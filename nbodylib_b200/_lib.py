@@ -43,7 +43,7 @@ EXPORTS = [
     "nbk_search_criterion_particles", "nbk_search_criterion_points", "nbk_calc_density_particles",
     "nbk_calc_veldensity_particles", "nbk_calc_density_points", "nbk_calc_veldensity_points",
     "nbk_knn_filtered_particles", "nbk_knn_filtered_points", "nbk_calc_smooth_vel", "nbk_calc_smooth_veldisp",
-    "nbk_set_option",
+    "nbk_set_option", "nbk_fof_roots", "nbk_union_pairs",
 ]
 
 _lib = None
@@ -91,6 +91,8 @@ def load():
     L.nbk_attach_halo.argtypes = [vp, vp]
     L.nbk_release_cached_memory.argtypes = [i32]
     L.nbk_set_option.argtypes = [C.c_char_p, i64]
+    L.nbk_fof_roots.argtypes = [vp, i32, dbl, vp, vp, vp, i32]
+    L.nbk_union_pairs.argtypes = [i32, i64, i64, vp, vp, vp]
     L.nbk_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     for name in EXPORTS:
         if name not in ("nbk_last_error", "nbk_device_count"):

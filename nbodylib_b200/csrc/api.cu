@@ -193,6 +193,14 @@ void build_kernel_table(nbk_tree& t) {
     NBK_CHECK(cudaMemcpy(t.d_kernel, t.h_kernel.data(), sizeof(double) * t.kernres, cudaMemcpyHostToDevice));
 }
 
+// root representatives (nbk_fof_roots): tree-order root indices -> IDs, delivered by ID
+__global__ void roots_to_ids_kernel(int64_t n, const int32_t* __restrict__ order, const int32_t* __restrict__ root_tree, int32_t* __restrict__ out_by_id) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t r = root_tree[i];
+    out_by_id[order[i]] = r < 0 ? -1 : order[r];
+}
+
 struct CallTimer {
     nbk_tree& t;
     explicit CallTimer(nbk_tree& tt) : t(tt) { cudaEventRecord(t.ev0, t.stream); }
@@ -412,6 +420,7 @@ int nbk_attach_halo(nbk_tree* t, nbk_tree* halo) {
     t->mass = mass.p; mass.p = nullptr;
     t->order = order.p; order.p = nullptr;
     t->nlo2 = halo->nlo; t->nhi2 = halo->nhi;
+    t->knn_fp32_ok = -1;
     t->n_main = n1; t->n = n;
     t->device_bytes += halo->device_bytes;
     cudaEventDestroy(halo->ev0); cudaEventDestroy(halo->ev1); cudaEventDestroy(halo->ev2); cudaEventDestroy(halo->ev3);
@@ -918,6 +927,55 @@ static CritSpec crit_from_params(int criterion, const double* params, const char
     // any accepted pair has sum(dx^2)/params[6] < 1; the tiny factor covers the rounding of the divided sum
     c.prune_x2 = params[6] * (1.0 + 1e-12);
     return c;
+}
+
+int nbk_fof_roots(nbk_tree* t, int criterion, double fdist, const double* params, const int32_t* precheck, int32_t* root, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && root, NBK_ERR_ARG, "nbk_fof_roots: null argument");
+    require_no_halo(t, "FOF");
+    NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "FOF needs a TPHYS or TPHS tree");
+    FofArgs a;
+    if (criterion < 0) {
+        NBK_REQUIRE(fdist > 0, NBK_ERR_ARG, "nbk_fof_roots: linking length must be positive");
+        a.mode = t->treetype == NBK_TPHS ? 1 : 0;
+        a.p0 = fdist * fdist; a.prune_x2 = a.p0;
+    } else {
+        NBK_REQUIRE(params, NBK_ERR_ARG, "nbk_fof_roots: null params");
+        CritSpec c = crit_from_params(criterion, params, "nbk_fof_roots");
+        a.mode = c.mode; a.p0 = c.p0; a.p1 = c.p1; a.prune_x2 = c.prune_x2;
+    }
+    a.minnum = 1; a.order = 0;
+    DeviceGuard guard(t->device, t->stream);
+    const int64_t n = t->n;
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    DevBuf<int32_t> dpre, dpre_tree, droot(n), dout;
+    if (precheck) {
+        const int32_t* src = precheck;
+        if (!dev) { dpre.alloc(n); NBK_CHECK(cudaMemcpyAsync(dpre.p, precheck, sizeof(int32_t) * n, cudaMemcpyHostToDevice, t->stream)); src = dpre.p; }
+        dpre_tree.alloc(n);
+        gather_i32_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, src, dpre_tree.p);
+        a.precheck_tree = dpre_tree.p;
+    }
+    a.roots_tree = droot.p;
+    CallTimer tm(*t);
+    launch_fof(*t, a);
+    tm.stop();
+    int32_t* out = root;
+    if (!dev) { dout.alloc(n); out = dout.p; }
+    roots_to_ids_kernel<<<div_up(n, 256), 256, 0, t->stream>>>(n, t->order, droot.p, out);
+    if (!dev) NBK_CHECK(cudaMemcpyAsync(root, dout.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, t->stream));
+    NBK_CHECK(cudaStreamSynchronize(t->stream));
+    NBK_API_END
+}
+
+int nbk_union_pairs(int device, int64_t nnodes, int64_t npairs, const int32_t* a, const int32_t* b, int32_t* root) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(nnodes >= 0 && npairs >= 0 && (npairs == 0 || (a && b)) && (nnodes == 0 || root), NBK_ERR_ARG, "nbk_union_pairs: bad argument");
+    int dev = device;
+    if (dev < 0) NBK_CHECK(cudaGetDevice(&dev));
+    DeviceGuard guard(dev, nullptr);
+    launch_union_pairs(nullptr, nnodes, npairs, a, b, root);
+    NBK_API_END
 }
 
 static void ball_call(nbk_tree* t, double fdist2, const CritSpec* crit, int64_t m, const int32_t* qidx, const double* x, const double* vq,

@@ -288,6 +288,35 @@ __global__ void fof_attach_apply_kernel(int64_t n, const int32_t* excl, const in
     excl_out[i] = x;
 }
 
+// root (tree index) of every particle, with path halving; excluded particles get -1
+__global__ void fof_roots_kernel(int64_t n, int* parent, const int32_t* excl, int32_t* root) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    root[i] = (excl && excl[i]) ? -1 : uf_find(parent, (int)i);
+}
+// connected components of an explicit edge list (nbk_union_pairs): the cross-slab merge of the sharded FOF
+__global__ void uf_init_kernel(int64_t n, int* parent) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) parent[i] = (int)i;
+}
+__global__ void uf_pairs_kernel(int64_t m, const int32_t* __restrict__ a, const int32_t* __restrict__ b, int* parent) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) uf_union(parent, a[i], b[i]);
+}
+__global__ void uf_flatten_kernel(int64_t n, int* parent, int32_t* root) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) root[i] = uf_find(parent, (int)i);
+}
+void launch_union_pairs(cudaStream_t st, int64_t nnodes, int64_t npairs, const int32_t* a, const int32_t* b, int32_t* root) {
+    if (nnodes <= 0) return;
+    DevBuf<int> parent(nnodes);
+    uf_init_kernel<<<div_up(nnodes, 256), 256, 0, st>>>(nnodes, parent.p);
+    if (npairs > 0) uf_pairs_kernel<<<div_up(npairs, 256), 256, 0, st>>>(npairs, a, b, parent.p);
+    uf_flatten_kernel<<<div_up(nnodes, 256), 256, 0, st>>>(nnodes, parent.p, root);
+    NBK_CHECK(cudaGetLastError());
+    NBK_CHECK(cudaStreamSynchronize(st));
+}
+
 __global__ void fof_init_kernel(int64_t n, int* parent, uint32_t* size) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { parent[i] = (int)i; size[i] = 0; }
@@ -427,6 +456,19 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     }
     NBK_CHECK(cudaEventRecord(t.ev3, st));
     tr.point("fof link");
+    if (a.roots_tree) {
+        // representatives only (nbk_fof_roots): every particle's root = the smallest tree index of its component, -1 for
+        // particles that take no part; no minnum filter, no numbering
+        fof_roots_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, excl_final, a.roots_tree);
+        NBK_CHECK(cudaStreamSynchronize(st));
+        NBK_CHECK(cudaGetLastError());
+        float ms = 0;
+        NBK_CHECK(cudaEventElapsedTime(&ms, t.ev2, t.ev3));
+        t.last_kernel_ms = ms;
+        t.last_launches = launches + 3;
+        a.ngroups = 0;
+        return;
+    }
     fof_flatten_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p);
     fof_root_kernel<<<div_up(n, tb), tb, 0, st>>>(n, parent.p, size.p, a.minnum, excl_final, flag.p);
     NBK_CHECK(cudaMemsetAsync(flag.p + n, 0, sizeof(uint32_t), st));

@@ -14,10 +14,10 @@
 // Two kernels:
 //   knn_exact_kernel  heap of (fp64 d2, int32 index), 12 B/entry.  Used when neighbour lists are materialised
 //                     (FindNearest API), for the periodic image schedule, and as the fallback below.
-//   knn_ap_kernel     the density family (CalcDensity / CalcVelDensity / smoothing scale), non periodic target
-//                     form: append + prune selection on fp32 keys with a rigorous error bound, no heap and no
-//                     serial insertion rounds (described at the kernel).  Queries whose k-th / (k+1)-th keys are
-//                     closer than the error band are re-run by the exact kernel.
+//   knn_hp_kernel     the density family (CalcDensity / CalcVelDensity / smoothing scale), non periodic target
+//                     form: heap of packed (fp32 key | candidate id) words with a rigorous error bound (described
+//                     at the kernel).  Queries whose k-th / (k+1)-th keys are closer than the error band are
+//                     re-run by the exact kernel.
 #include <string.h>
 
 #include "traverse.cuh"
@@ -383,39 +383,44 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
     }
 }
 
-// ====================================================================================== append + prune select
+// ========================================================================= density kernel: heap of packed words
 // The density family needs (a) the exact set of the k nearest, (b) the exact k-th distance and (c) a sum over the set.
-// Per lane (= query) the kernel keeps an APPEND BUFFER of fp32 keys in shared memory ([cap][32], slot-major) and, entry
-// for entry, the candidates' tree indices in a global scratch block ([cap][32] per resident warp, L2 resident).  A
-// candidate is screened with ONE fp32 distance and, if it is below the lane's bound, appended by two predicated stores:
-// there is no heap and no SIMT-serial insertion round -- every lane works on every instruction of the tile scan.
-// When some lane's buffer is nearly full, the whole warp PRUNES in lock step: a 32-bin histogram of the lane's keys
-// finds the bin holding rank R = k+1, one compaction pass keeps the bins below it, and the (<= 8) members of that bin
-// are ranked by a sorting network in registers; the lane's bound becomes its exact R-th smallest key.  The last prune
-// leaves exactly the k+1 smallest keys.
+// Per lane (= query) the kernel keeps the k+1 smallest candidates seen so far as 32-bit WORDS in a 4-ary max-heap in shared
+// memory:
+//     word = (fp32 key & ~0xfff) | candidate id,      candidate id = (tile sequence number << 5) | slot in the tile
+// (the warp's tile list maps a sequence number back to a tree index; words order like their keys, so the heap needs no
+// separate index array and the kernel no global scratch).  A tile is screened with ONE fp32 distance and one unsigned
+// comparison per candidate into a bit mask; the set bits are inserted in SIMT-serial rounds.  After the traversal the full
+// keys of the k+1 survivors are recomputed from their indices.
 //
-// Exactness.  Keys are a = fl32(d2) evaluated with 3 subtractions, 1 multiplication, 2 FMAs on exact fp32 coordinates:
-// |a - d2| <= 5.01 * 2^-24 * d2 =: eps * d2 (fp64 storage: a = RN_fp32 of the reference's fp64 d2, eps = 2^-24).
-//   * Every candidate that is dropped -- screened out (a > bound * (1 + 2^-20)), in a subtree whose box lower bound
-//     reaches bound * (1 + 2^-20), or pruned -- has a >= the lane's final (k+1)-th smallest key m1.
-//   * If m1 > m2 * (1 + 2^-20) (m2 = k-th smallest key), every dropped candidate and the (k+1)-th itself are farther in
-//     exact arithmetic than each of the k kept ones, because 2^-20 > 2 eps: the k smallest keys ARE the k nearest.
-//   * The exact k-th distance is the reference fp64 d2 of the entry with key m2 provided the third largest key m3 is
-//     below m2 * (1 - 2^-20); the SPH sums use fp64 d2 recomputed from the indices.
-//   * Queries failing either gap test (~2e-4 of them), meeting an under/overflowing key or a degenerate histogram are
-//     appended to a list and re-run by knn_exact_kernel (fp64 heap).
+// Exactness.  Full keys are a = fl32(d2) evaluated with 3 subtractions, 1 multiplication, 2 FMAs on exact fp32
+// coordinates: |a - d2| <= 5.01 * 2^-24 * d2 =: eps * d2 (fp64 storage: a = RN_fp32 of the reference's fp64 d2, eps = 2^-24).
+//   * A candidate screened out (a > edge * (1 + 2^-20), edge = upper edge of the root word's 2^-11-wide bin) or lying in a
+//     subtree whose box lower bound reaches that limit is farther, in exact arithmetic, than every word the heap holds then
+//     and later (2^-20 > 2 eps).
+//   * A candidate that reaches a round and is rejected, or a root that is evicted, lies in the root's bin or above; the lane
+//     remembers the smallest such word (`mindrop`).
+//   * Among the k+1 survivors let m1 be the largest full key and m2 the second largest.  If m1 > m2 * (1 + 2^-20) -- and, when
+//     some dropped word shares the final root's bin, if that bin's lower edge exceeds m2 * (1 + 2^-20) as well -- every
+//     dropped candidate and the (k+1)-th itself are farther in exact arithmetic than each of the k kept ones: the k smallest
+//     full keys ARE the k nearest.
+//   * The exact k-th distance is the reference fp64 d2 of the entry with key m2 provided the next smaller key is below
+//     m2 * (1 - 2^-20); the SPH sums use fp64 d2 recomputed from the indices.
+//   * Queries failing a gap test (~4e-4 of them), meeting an underflowing key or more than 128 tiles are appended to a list
+//     and re-run by knn_exact_kernel (fp64 heap).
 // Traversal: bottom-up (traverse_bottom_up): the group's own node first, then the sibling subtrees of its ancestors.
 // Persistent grid: warps draw 32-query groups from a global counter, so the grid is one wave whatever the particle count.
 constexpr float AP_TINY = 7.888609052210118e-31f;           // 2^-100: below it the relative error bound of a key is not guaranteed
-constexpr float AP_HUGE = 1.0e37f;
+constexpr float AP_HUGE = 1.0e37f;                           // launch_knn sends boxes that could exceed it to the exact kernel
 constexpr float AP_WIDEN = 1.00000095367431640625f;          // 1 + 2^-20
 constexpr float AP_NARROW = 0.99999904632568359375f;         // 1 - 2^-20
-constexpr int AP_STASH = 8;
-constexpr int AP_AUX_BYTES = 2048;                           // histogram u16 [32][32]; then the stash: float [8][32] + int [8][32]
-constexpr int AP_MAX_LEVELS = 6;
+constexpr unsigned AP_CIDMASK = 0xfffu;                      // 12 bits: 7 bits tile sequence number, 5 bits slot
+constexpr unsigned AP_KEYMASK = ~AP_CIDMASK;
+constexpr int AP_MAXTILES = 128;
+constexpr float AP_INF = __builtin_huge_valf();
 
 #ifdef NBK_STATS
-__device__ unsigned long long g_stats[8];   // 0 tiles, 1 prunes, 2 prune levels, 3 appended (lane-level), 4 flagged, 5 failed
+__device__ unsigned long long g_stats[8];   // 0 tiles, 2 insertion rounds, 3 candidates past the screen (lane-level), 4 flagged, 6 tile list overflows
 #define STAT(i, v) do { if (lane_id() == 0) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
 #define STAT_LANE(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
 #else
@@ -423,7 +428,16 @@ __device__ unsigned long long g_stats[8];   // 0 tiles, 1 prunes, 2 prune levels
 #define STAT_LANE(i, v)
 #endif
 
-// Leaf tile staged in shared memory and the per-candidate key.
+// the key of a candidate: the same expression in the tile scan and in the final pass over the survivors
+__device__ __forceinline__ float ap_key(float qx, float qy, float qz, float cx, float cy, float cz) {
+    const float dx = __fsub_rn(qx, cx), dy = __fsub_rn(qy, cy), dz = __fsub_rn(qz, cz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+__device__ __forceinline__ float ap_key(double qx, double qy, double qz, double cx, double cy, double cz) {
+    return __double2float_rn(dist2_ref(qx, qy, qz, cx, cy, cz));
+}
+
+// Leaf tile staged in shared memory.
 template <class S> struct ApTile;
 template <> struct ApTile<float> {
     static constexpr int TILE_BYTES = 32 * 16;
@@ -440,11 +454,8 @@ template <> struct ApTile<float> {
         if ((int)lane < m) { Vec4<float> c = P[first + lane]; mine = make_float4(c.x, c.y, c.z, 0.f); }
         t[lane] = mine;
     }
-    __device__ __forceinline__ float key(int j) const {
-        const float4 c = t[j];
-        const float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
-        return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-    }
+    __device__ __forceinline__ float key(int j) const { const float4 c = t[j]; return ap_key(qx, qy, qz, c.x, c.y, c.z); }
+    __device__ __forceinline__ float key_of(const Vec4<float>& c) const { return ap_key(qx, qy, qz, c.x, c.y, c.z); }
     __device__ __forceinline__ bool coincident(int j) const { const float4 c = t[j]; return qx == c.x && qy == c.y && qz == c.z; }
 };
 template <> struct ApTile<double> {
@@ -458,191 +469,19 @@ template <> struct ApTile<double> {
         if ((int)lane < m) { Vec4<double> c = P[first + lane]; cx = c.x; cy = c.y; cz = c.z; }
         t[lane] = cx; t[32 + lane] = cy; t[64 + lane] = cz;
     }
-    __device__ __forceinline__ float key(int j) const { return __double2float_rn(dist2_ref(qx, qy, qz, t[j], t[32 + j], t[64 + j])); }
+    __device__ __forceinline__ float key(int j) const { return ap_key(qx, qy, qz, t[j], t[32 + j], t[64 + j]); }
+    __device__ __forceinline__ float key_of(const Vec4<double>& c) const { return ap_key(qx, qy, qz, c.x, c.y, c.z); }
     __device__ __forceinline__ bool coincident(int j) const { return qx == t[j] && qy == t[32 + j] && qz == t[64 + j]; }
 };
 
-__device__ __forceinline__ void ap_cex(float& ka, int& ia, float& kb, int& ib) {
-    const bool sw = ka > kb;
-    const float k0 = sw ? kb : ka, k1 = sw ? ka : kb;
-    const int i0 = sw ? ib : ia, i1 = sw ? ia : ib;
-    ka = k0; kb = k1; ia = i0; ib = i1;
-}
-
-// Lock-step prune of the lanes' append buffers (all 32 lanes call it).  Lane state: cnt entries (keys kb[s*32], indices
-// lg[s*32]), all keys <= bound * (1 + 2^-20).  Lanes with cnt > R keep their R smallest keys (FINAL: exactly; otherwise
-// possibly a few more when the rank-R bin holds more than 8 keys) and get bound = largest kept key.  Returns
-// (bound bits << 32 | cnt); cnt = -1: the lane could not be resolved (degenerate keys) and goes to the exact kernel.
-template <bool FINAL>
-__device__ __noinline__ unsigned long long ap_prune(float* kb, int* lg, unsigned char* aux, int cnt, int R, float bound) {
-    const unsigned full = 0xffffffffu;
-    const unsigned lane = lane_id();
-    bool act = cnt > R;
-    if (!__any_sync(full, act)) return ((unsigned long long)__float_as_uint(bound) << 32) | (unsigned)cnt;
-    STAT(1, 1);
-    float tlo = 0.f, thi = __fmul_ru(bound, AP_WIDEN);
-    int cbelow = 0, level = 0;
-    if (__any_sync(full, act && !(thi <= 3.0e38f))) {
-        // lanes still on the infinite bound: the range is their largest key
-        const int nmax = __reduce_max_sync(full, act ? cnt : 0);
-        float mx = 0.f;
-#pragma unroll 4
-        for (int s = 0; s < nmax; s++) if (s < cnt) mx = fmaxf(mx, kb[s * 32]);
-        if (!(thi <= 3.0e38f)) thi = mx;
-    }
-    unsigned short* myh = reinterpret_cast<unsigned short*>(aux) + lane;      // histogram column: bin b at myh[b*32]
-    float* sk = reinterpret_cast<float*>(aux) + lane;                         // stash keys [8][32]
-    int* si = reinterpret_cast<int*>(aux) + 256 + lane;                       // stash indices [8][32]
-    while (__any_sync(full, act)) {
-        STAT(2, 1);
-        const int nmax = __reduce_max_sync(full, act ? cnt : 0);
-        __syncwarp();
-        {
-            uint4* h4 = reinterpret_cast<uint4*>(aux);
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int i = 0; i < AP_AUX_BYTES / 512; i++) h4[i * 32 + lane] = z;
-        }
-        __syncwarp();
-        const float scale = (thi > tlo) ? 31.99f / (thi - tlo) : 0.f;
-        // ---- histogram of the keys inside [tlo, thi] ------------------------------------------------------
-#pragma unroll 4
-        for (int s = 0; s < nmax; s++) {
-            if (act && s < cnt) {
-                const float key = kb[s * 32];
-                if (key >= tlo && key <= thi) {
-                    const int b = min(__float2int_rz((key - tlo) * scale), 31);
-                    myh[b * 32] += 1;
-                }
-            }
-        }
-        // ---- the bin that holds rank R --------------------------------------------------------------------
-        int bstar = -1, cbefore = 0, p = 0;
-        {
-            int cum = cbelow;
-#pragma unroll 8
-            for (int b = 0; b < 32; b++) {
-                const int h = myh[b * 32];
-                if (bstar < 0 && cum + h >= R) { bstar = b; cbefore = cum; p = h; }
-                cum += h;
-            }
-        }
-        if (act && bstar < 0) { cnt = -1; act = false; }            // cannot happen for consistent state; never loop on it
-        const int need = R - cbefore;                                // members of bin bstar that complete the R smallest
-        const bool small = p <= AP_STASH;
-        __syncwarp();                                                // histogram columns are dead: the region becomes the stash
-        // ---- compaction: bins below bstar stay, bins above go, members of bstar go to the stash (or stay) -----
-        int wp = 0, ns = 0;
-        float mn = __int_as_float(0x7f800000), mx = 0.f;
-        for (int s0 = 0; s0 < nmax; s0 += 8) {
-            int id[8];
-            float ky[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const bool in = act && s0 + u < cnt;
-                id[u] = in ? lg[(s0 + u) * 32] : 0;
-                ky[u] = in ? kb[(s0 + u) * 32] : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                if (act && s0 + u < cnt) {
-                    const float key = ky[u];
-                    bool keep = key < tlo, member = false;
-                    if (!keep && key <= thi) {
-                        const int b = min(__float2int_rz((key - tlo) * scale), 31);
-                        keep = b < bstar; member = b == bstar;
-                    }
-                    if (member) {
-                        if (small) { sk[ns * 32] = key; si[ns * 32] = id[u]; ns++; }
-                        else { keep = true; mn = fminf(mn, key); mx = fmaxf(mx, key); }
-                    }
-                    if (keep) { kb[wp * 32] = key; lg[wp * 32] = id[u]; wp++; }
-                }
-            }
-        }
-        if (act) {
-            if (small) {
-                float k8[8]; int i8[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) { const bool in = u < ns; k8[u] = in ? sk[u * 32] : __int_as_float(0x7f800000); i8[u] = in ? si[u * 32] : -1; }
-                // 19-comparator network for 8 keys (Batcher odd-even merge sort)
-                ap_cex(k8[0], i8[0], k8[1], i8[1]); ap_cex(k8[2], i8[2], k8[3], i8[3]); ap_cex(k8[4], i8[4], k8[5], i8[5]); ap_cex(k8[6], i8[6], k8[7], i8[7]);
-                ap_cex(k8[0], i8[0], k8[2], i8[2]); ap_cex(k8[1], i8[1], k8[3], i8[3]); ap_cex(k8[4], i8[4], k8[6], i8[6]); ap_cex(k8[5], i8[5], k8[7], i8[7]);
-                ap_cex(k8[1], i8[1], k8[2], i8[2]); ap_cex(k8[5], i8[5], k8[6], i8[6]);
-                ap_cex(k8[0], i8[0], k8[4], i8[4]); ap_cex(k8[1], i8[1], k8[5], i8[5]); ap_cex(k8[2], i8[2], k8[6], i8[6]); ap_cex(k8[3], i8[3], k8[7], i8[7]);
-                ap_cex(k8[2], i8[2], k8[4], i8[4]); ap_cex(k8[3], i8[3], k8[5], i8[5]);
-                ap_cex(k8[1], i8[1], k8[2], i8[2]); ap_cex(k8[3], i8[3], k8[4], i8[4]); ap_cex(k8[5], i8[5], k8[6], i8[6]);
-                float b = bound;
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if (u < need) { kb[wp * 32] = k8[u]; lg[wp * 32] = i8[u]; wp++; b = k8[u]; }
-                }
-                bound = b; cnt = wp; act = false;
-            } else {
-                // more than 8 keys in the rank-R bin: keep the whole bin; the bound is its largest key
-                cnt = wp;
-                if (FINAL) {
-                    cbelow = cbefore; tlo = mn; thi = mx;
-                    if (!(mx > mn) || ++level >= AP_MAX_LEVELS) { cnt = -1; act = false; }      // all keys of the bin equal: exact kernel
-                } else { bound = mx; act = false; }
-            }
-        }
-    }
-    __syncwarp();
-    return ((unsigned long long)__float_as_uint(bound) << 32) | (unsigned)cnt;
-}
-
-template <class S>
-struct ApVisitor {
-    const Vec4<S>* P;
-    ApTile<S> tile;
-    float* kb;            // shared: this lane's key column, entry s at kb[s*32]
-    int* lg;              // global: this lane's index column, entry s at lg[s*32]
-    unsigned char* aux;   // shared: the warp's histogram / stash region
-    int cnt, cap, R;
-    float bound, limf;    // bound: largest kept key after the last prune (or +inf); limf = bound * (1 + 2^-20), -1: lane accepts nothing
-    bool failed;
-    unsigned lane;
-    __device__ __forceinline__ bool need(float lb) const { return lb < limf; }
-    __device__ __forceinline__ void fail() { failed = true; limf = -1.f; cnt = 0; }
-    template <bool FINAL>
-    __device__ __forceinline__ void prune() {
-        const unsigned long long r = ap_prune<FINAL>(kb, lg, aux, failed ? 0 : cnt, R, bound);
-        const int c = (int)(unsigned)(r & 0xffffffffull);
-        if (!failed) {
-            if (c < 0 || (!FINAL && c > cap - 8)) fail();
-            else { cnt = c; bound = __uint_as_float((unsigned)(r >> 32)); limf = __fmul_ru(bound, AP_WIDEN); }
-        }
-    }
-    __device__ __forceinline__ void leaf(int start, int n, int, unsigned) {
-        for (int base = 0; base < n; base += 32) {
-            const int m = min(32, n - base);
-            __syncwarp();
-            tile.load(P, start + base, m, lane);
-            __syncwarp();
-            STAT(0, 1);
-            for (int j0 = 0; j0 < m; j0 += 8) {
-                if (__any_sync(0xffffffffu, cnt > cap - 8)) prune<false>();
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) {
-                    const float a = tile.key(j0 + jj);
-                    if (a <= limf) {
-                        if (a >= AP_TINY && a <= AP_HUGE) { kb[cnt * 32] = a; lg[cnt * 32] = start + base + j0 + jj; cnt++; STAT_LANE(3, 1); }
-                        else if (!tile.coincident(j0 + jj)) fail();     // the query itself and coincident particles are never neighbours
-                    }
-                }
-            }
-        }
-    }
-};
-
-// SPH epilogues over a lane's neighbour list L (entry s at L[s*32], global or shared); D: per-lane doubles [k][32] in shared
-// memory for the kv < kx velocity-density selection.
-template <class S>
-__device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>* __restrict__ P, const int* L, double* Dbase, unsigned lane,
+// SPH epilogues over a lane's neighbour list: entry s (0 <= s < cnt) is tree index idx_at(s).  All 32 lanes call it (`on`:
+// this lane has a result to compute); D: per-lane doubles [k][32] in shared memory for the kv < kx velocity-density
+// selection -- it may overlap the storage idx_at reads, which is consumed from the last entry down, row by row.
+template <class S, class IdxAt>
+__device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>* __restrict__ P, IdxAt idx_at, double* Dbase, unsigned lane, bool on,
                                             int cnt, double d2max, double x0, double y0, double z0, int64_t qi) {
-    if (prm.hsm) prm.hsm[qi] = 0.5 * sqrt(d2max);
-    if (prm.rho && prm.veldens_k == 0) {
+    if (on && prm.hsm) prm.hsm[qi] = 0.5 * sqrt(d2max);
+    if (on && prm.rho && prm.veldens_k == 0) {
         const double hi = 0.5 * sqrt(d2max);
         const double norm = 1.0 / pow(hi, 3.0);
         const double delta = 2.0 / (double)(prm.kernres - 1);
@@ -653,14 +492,15 @@ __device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>*
             // four neighbours per trip: the gathers of P and mass are issued together
             int id[4]; Vec4<S> c[4]; double mj[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) id[u] = (s0 + u < cnt) ? L[(s0 + u) * 32] : -1;
+            for (int u = 0; u < 4; u++) id[u] = (s0 + u < cnt) ? idx_at(s0 + u) : -1;
 #pragma unroll
-            for (int u = 0; u < 4; u++) if (id[u] >= 0) { c[u] = P[id[u]]; mj[u] = prm.mass[id[u]]; }
+            for (int u = 0; u < 4; u++) { const int ci = id[u] >= 0 ? id[u] : 0; c[u] = P[ci]; mj[u] = prm.mass[ci]; }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if (id[u] >= 0) {
-                    const double rij = sqrt(dist2_ref(x0, y0, z0, (double)c[u].x, (double)c[u].y, (double)c[u].z));
-                    const double r = rij * inv_hi;
+                    const double d2 = dist2_ref(x0, y0, z0, (double)c[u].x, (double)c[u].y, (double)c[u].z);
+                    // r = rij / hi with one rounding more than the reference's division; the k-th neighbour sits at exactly 2
+                    const double r = d2 == d2max ? 2.0 : sqrt(d2) * inv_hi;
                     const double Wij = wsm_fast(r, (int)(r * half_res), prm.kernres, delta, inv_delta, prm.kern) * half_norm;
                     acc += Wij * mj[u];
                     atomicAdd(&prm.rho[id[u]], Wij * mi);
@@ -671,30 +511,42 @@ __device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>*
     }
     if (prm.rho && prm.veldens_k > 0) {
         const Vec4<S>* V = reinterpret_cast<const Vec4<S>*>(prm.V);
-        const Vec4<S> vi = V[qi];
+        Vec4<S> vi = on ? V[qi] : Vec4<S>();
         const double delta = 2.0 / (double)(prm.kernres - 1);
-        const int kv = min(prm.veldens_k, cnt);
+        const int kv = on ? min(prm.veldens_k, cnt) : 0;
         double rho = 0;
-        if (kv == cnt) {
+        if (prm.veldens_k >= prm.k) {
             // every spatial neighbour is used: h from the largest velocity distance, then the sum (two passes)
-            double vmax = 0;
-            for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[L[s * 32]];
-                vmax = fmax(vmax, sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)));
+            if (on && kv > 0) {
+                double vmax = 0;
+                for (int s = 0; s < cnt; s++) {
+                    Vec4<S> vj = V[idx_at(s)];
+                    vmax = fmax(vmax, sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)));
+                }
+                const double hi = 0.5 * vmax;
+                const double norm = 1.0 / pow(hi, 3.0);
+                for (int s = 0; s < cnt; s++) {
+                    Vec4<S> vj = V[idx_at(s)];
+                    double r = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)) / hi;
+                    rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+                }
             }
-            const double hi = 0.5 * vmax;
-            const double norm = 1.0 / pow(hi, 3.0);
-            for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[L[s * 32]];
-                double r = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z)) / hi;
-                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
-            }
-        } else if (kv > 0) {
-            // kv < kx: exact fp64 selection on a per-lane array of doubles in shared memory
+        } else {
+            // kv < kx: exact fp64 selection on a per-lane array of doubles in shared memory.  The array overlaps the list's own
+            // storage: row s of the doubles covers rows 2s, 2s+1 of the list, so the list is consumed from its last row down,
+            // all lanes in step.
             double* D = Dbase + lane;
-            for (int s = 0; s < cnt; s++) {
-                Vec4<S> vj = V[L[s * 32]];
-                D[s * 32] = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
+            const int nmax = __reduce_max_sync(0xffffffffu, on ? cnt : 0);
+            for (int s = nmax - 1; s >= 0; s--) {
+                const bool in = on && s < cnt;
+                double vd = 0;
+                if (in) {
+                    Vec4<S> vj = V[idx_at(s)];
+                    vd = sqrt(dist2_ref((double)vi.x, (double)vi.y, (double)vi.z, (double)vj.x, (double)vj.y, (double)vj.z));
+                }
+                __syncwarp();
+                if (in) D[s * 32] = vd;
+                __syncwarp();
             }
             auto dsift = [&](int p, int n, double d) {
                 while (true) {
@@ -708,49 +560,167 @@ __device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>*
                 }
                 D[p * 32] = d;
             };
-            for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, D[p * 32]);
-            for (int s = kv; s < cnt; s++) {
-                double vd = D[s * 32];
-                if (vd < D[0]) dsift(0, kv, vd);
-            }
-            const double hi = 0.5 * D[0];
-            const double norm = 1.0 / pow(hi, 3.0);
-            for (int e = kv; e > 0; e--) {
-                double r = D[0] / hi;
-                rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
-                dsift(0, e - 1, D[(e - 1) * 32]);
+            if (kv > 0) {
+                for (int p = kv / 2 - 1; p >= 0; p--) dsift(p, kv, D[p * 32]);
+                for (int s = kv; s < cnt; s++) {
+                    double vd = D[s * 32];
+                    if (vd < D[0]) dsift(0, kv, vd);
+                }
+                const double hi = 0.5 * D[0];
+                const double norm = 1.0 / pow(hi, 3.0);
+                for (int e = kv; e > 0; e--) {
+                    double r = D[0] / hi;
+                    rho = rho + wsm(r, (int)(r * 0.5 * (prm.kernres - 1)), prm.kernres, delta, prm.kern) * norm;
+                    dsift(0, e - 1, D[(e - 1) * 32]);
+                }
             }
         }
-        prm.rho[qi] = rho;
+        if (on) prm.rho[qi] = rho;
     }
 }
 
-static inline int ap_capacity(int k) {
-    int c = 2 * k > k + 48 ? 2 * k : k + 48;
-    return (c + 7) & ~7;
-}
-static inline size_t ap_warp_bytes(int k, int cap, bool want_doubles, int tile_bytes) {
-    size_t region = (size_t)cap * 32 * 4;
-    if (want_doubles && (size_t)k * 32 * 8 > region) region = (size_t)k * 32 * 8;
-    return region + AP_AUX_BYTES + tile_bytes + TRAV_STACK * 4;
+// Per-lane 4-ary max-heap of words in shared memory: node p's four children are the components of ONE 16-byte group (one
+// LDS.128 per level, 3 levels for 65 entries); (G+1)*512 bytes per warp.
+struct WordHeap4 {
+    unsigned char* kb;   // this lane's byte base inside the [G+1][32] float4 groups (group g of the lane at kb + g*512)
+    int G;
+    // key of node p: group (p+3)>>2, component (p+3)&3 ; children of p = the four components of group p+1
+    __device__ __forceinline__ float* keyp(int p) const { return reinterpret_cast<float*>(kb + ((p + 3) >> 2) * 512 + ((p + 3) & 3) * 4); }
+    __device__ __forceinline__ float rootkey() const { return *reinterpret_cast<const float*>(kb + 12); }
+    // place xk at node p and sift it down; returns the key that ends up at node p
+    __device__ __forceinline__ float sift(int p, float xk) {
+        unsigned char* pa = reinterpret_cast<unsigned char*>(keyp(p));
+        unsigned char* ga = kb + (p + 1) * 512;
+        float at_p = xk;
+        bool moved = false;
+        while (p < G) {
+            const float4 ck = *reinterpret_cast<const float4*>(ga);
+            const bool a = ck.x >= ck.y, b = ck.z >= ck.w;
+            const float m01 = a ? ck.x : ck.y, m23 = b ? ck.z : ck.w;
+            const bool c = m01 >= m23;
+            const float m = c ? m01 : m23;
+            if (xk >= m) break;
+            const int j = c ? (a ? 0 : 1) : (b ? 2 : 3);
+            *reinterpret_cast<float*>(pa) = m;
+            if (!moved) { at_p = m; moved = true; }
+            pa = ga + 4 * j;
+            p = 4 * p + 1 + j;
+            ga = kb + (p + 1) * 512;
+        }
+        *reinterpret_cast<float*>(pa) = xk;
+        return at_p;
+    }
+};
+
+template <class S>
+struct HpVisitor {
+    const Vec4<S>* P;
+    ApTile<S> tile;
+    WordHeap4 hp;
+    int* tl;              // shared: the warp's tile list (tile sequence number -> first tree index)
+    int nt;               // tiles scanned so far (warp-uniform)
+    float topw;           // heap root: the lane's (k+1)-th smallest word so far (+inf while it has fewer)
+    float limf;           // screen / node-test limit: upper edge of the root's bin * (1 + 2^-20); -1: the lane accepts nothing
+    unsigned limu;        // the same limit for the unsigned screen test (bits(a) - bits(AP_TINY) < limu); 0: nothing passes
+    unsigned mindrop;     // smallest word rejected or evicted in a round once the heap was full
+    int filled, kcap;     // heap slots taken so far (the first k+1 candidates are stored without sifting), k + 1
+    bool failed;
+    unsigned lane;
+    static constexpr unsigned TINY_BITS = 0x0d800000u;      // bits of AP_TINY = 2^-100
+    __device__ __forceinline__ bool need(float lb) const { return lb < limf; }
+    __device__ __forceinline__ void set_limit(float lim) { limf = lim; limu = __float_as_uint(lim) - TINY_BITS + 1u; }
+    __device__ __forceinline__ void settop(float w) {
+        topw = w;
+        set_limit(w < AP_HUGE ? fminf(__fmul_ru(__uint_as_float(__float_as_uint(w) | AP_CIDMASK), AP_WIDEN), AP_HUGE) : AP_HUGE);
+    }
+    __device__ __forceinline__ void fail() { failed = true; limf = -1.f; limu = 0u; }
+    __device__ __forceinline__ void leaf(int start, int n, int, unsigned) {
+        for (int base = 0; base < n; base += 32) {
+            const int m = min(32, n - base);
+            if (nt >= AP_MAXTILES) { if (limu != 0u) { STAT(6, 1); fail(); } return; }      // tile list full: the whole group goes to the exact kernel
+            __syncwarp();
+            tile.load(P, start + base, m, lane);
+            if (lane == 0) tl[nt] = start + base;
+            __syncwarp();
+            const unsigned cid0 = (unsigned)nt << 5;
+            nt++;
+            STAT(0, 1);
+            // pass 1: one unsigned comparison per candidate (NaN padding, keys below 2^-100 -- the query itself, coincident
+            // particles, underflow -- and keys above the limit all fail it)
+            unsigned acc = 0u, tiny = 0u;
+            for (int j0 = 0; j0 < m; j0 += 8) {
+                float a[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) a[jj] = tile.key(j0 + jj);
+                unsigned a8 = 0u;
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const unsigned u = __float_as_uint(a[jj]) - TINY_BITS;
+                    tiny |= u;
+                    if (u < limu) a8 |= 1u << jj;
+                }
+                acc |= a8 << j0;
+            }
+            if ((int)tiny < 0 && limu != 0u) {
+                // rare: the query itself and coincident particles (never neighbours), or a distance that underflows fp32
+#pragma unroll 1
+                for (int j = 0; j < m; j++) {
+                    const float a = tile.key(j);
+                    if (a < AP_TINY && !tile.coincident(j)) fail();
+                }
+                if (failed) acc = 0u;
+            }
+            STAT_LANE(3, __popc(acc));
+            // pass 2: SIMT-serial insertion rounds over the set bits.  The first k+1 candidates of a lane fill the heap's slots
+            // directly (the bound is still infinite) and are heapified together when the last slot is taken.
+            while (__any_sync(0xffffffffu, acc != 0u)) {
+                STAT(2, 1);
+                if (acc) {
+                    const int j = __ffs(acc) - 1;
+                    acc &= acc - 1u;
+                    const unsigned wb = (__float_as_uint(tile.key(j)) & AP_KEYMASK) | (cid0 + (unsigned)j);
+                    const float w = __uint_as_float(wb);
+                    if (filled < kcap) {
+                        *hp.keyp(filled) = w;
+                        filled++;
+                        if (filled == kcap) {
+                            for (int p = hp.G - 1; p >= 0; p--) hp.sift(p, *hp.keyp(p));
+                            settop(hp.rootkey());
+                        }
+                    } else {
+                        // the word that does not stay in the heap: the candidate itself, or the root it evicts
+                        const unsigned out = w < topw ? __float_as_uint(topw) : wb;
+                        mindrop = min(mindrop, out);
+                        if (w < topw) settop(hp.sift(0, w));
+                    }
+                }
+            }
+        }
+    }
+};
+
+static inline int hp_groups(int k) { return (k + 3) / 4; }            // internal nodes of the heap of k+1 words
+static inline size_t hp_warp_bytes(int k, bool want_doubles, int tile_bytes) {
+    size_t region = (size_t)(hp_groups(k) + 1) * 512;
+    if (want_doubles) region += (size_t)k * 32 * 8;
+    return region + tile_bytes + TRAV_STACK * 4 + AP_MAXTILES * 4;
 }
 
 template <class S, bool HALO>
-__global__ void __launch_bounds__(KNN_WARPS * 32) knn_ap_kernel(KnnParams prm, int want_doubles, int cap, int* __restrict__ work_counter,
-                                                                int32_t* __restrict__ logbuf) {
+__global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm, int want_doubles, int* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    const int k = prm.k, R = k + 1;
-    size_t region = (size_t)cap * 32 * 4;
-    if (want_doubles && (size_t)k * 32 * 8 > region) region = (size_t)k * 32 * 8;
-    const size_t warp_bytes = region + AP_AUX_BYTES + ApTile<S>::TILE_BYTES + TRAV_STACK * 4;
+    const int k = prm.k, kcap = k + 1;
+    const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
+    const size_t heap_bytes = (size_t)(G + 1) * 512;
+    const size_t region = heap_bytes + (want_doubles ? (size_t)k * 32 * 8 : 0);
+    const size_t warp_bytes = region + ApTile<S>::TILE_BYTES + TRAV_STACK * 4 + AP_MAXTILES * 4;
     unsigned char* base = smem_raw + w * warp_bytes;
-    unsigned char* aux = base + region;
-    void* tile_mem = base + region + AP_AUX_BYTES;
-    int* stack = reinterpret_cast<int*>(base + region + AP_AUX_BYTES + ApTile<S>::TILE_BYTES);
-    int* lg = logbuf + ((size_t)blockIdx.x * KNN_WARPS + w) * (size_t)cap * 32 + lane;
-    float* kb = reinterpret_cast<float*>(base) + lane;
+    void* tile_mem = base + region;
+    int* stack = reinterpret_cast<int*>(base + region + ApTile<S>::TILE_BYTES);
+    int* tl = stack + TRAV_STACK;
+    unsigned char* kb = base + lane * 16;
 
     const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
     const int64_t ngroups = (prm.q1 - prm.q0 + 31) >> 5;
@@ -769,64 +739,89 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_ap_kernel(KnnParams prm, i
         const QueryBox qb = make_qbox(x0, y0, z0);
 
         // ------------------------------------------------------------------------------------------ select
-        ApVisitor<S> v;
+        HpVisitor<S> v;
         v.P = P; v.lane = lane;
         v.tile.init(tile_mem, x0, y0, z0);
-        v.kb = kb; v.lg = lg; v.aux = aux;
-        v.cnt = 0; v.cap = cap; v.R = R;
-        v.bound = __int_as_float(0x7f800000);
-        v.limf = valid ? v.bound : -1.f;
+        v.hp.kb = kb; v.hp.G = G;
+        v.tl = tl; v.nt = 0;
+        v.mindrop = 0xffffffffu;
+        v.filled = 0; v.kcap = kcap;
         v.failed = false;
+        // empty real slots hold +inf, the padding up to 4G+1 nodes holds 0 (never evicted, never accepted against)
+        for (int p = 0; p < NN; p++) *v.hp.keyp(p) = p < kcap ? AP_INF : 0.f;
+        v.topw = AP_INF;
+        if (valid) v.set_limit(AP_HUGE); else { v.limf = -1.f; v.limu = 0u; }
         traverse_bottom_up(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid, prm.n_tree, g0, g1);
         if (HALO) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);
-        v.template prune<true>();
 
         // ------------------------------------------------------------------------ the k nearest and the k-th
-        // three largest keys (m1 >= m2 >= m3) and the slots of the first two
-        int cnt = v.cnt;
-        float m1 = -1.f, m2 = -1.f, m3 = -1.f;
-        int s1 = -1, s2 = -1;
+        // linearise: the valid words of the heap nodes move to the front (slot s = storage of node s)
+        auto word_at = [kb](int s) -> unsigned* { return reinterpret_cast<unsigned*>(kb + ((s + 3) >> 2) * 512 + ((s + 3) & 3) * 4); };
+        const unsigned rootw = *word_at(0);
+        int cnt = 0;
+        if (valid && !v.failed) {
+            for (int s = 0; s < NN; s++) {
+                const unsigned wd = *word_at(s);
+                if (wd != 0x7f800000u && wd != 0u) { *word_at(cnt) = wd; cnt++; }
+            }
+        }
+        auto idx_at = [kb, tl](int s) -> int {
+            const unsigned wd = *reinterpret_cast<const unsigned*>(kb + ((s + 3) >> 2) * 512 + ((s + 3) & 3) * 4);
+            return tl[(wd >> 5) & (AP_MAXTILES - 1)] + (int)(wd & 31u);
+        };
+        // full keys of the survivors: the three largest f0 >= f1 >= f2 and the slots of the first two
+        float f0 = -1.f, f1 = -1.f, f2 = -1.f;
+        int t0 = -1, t1 = -1;
         {
-            const int nmax = __reduce_max_sync(full, valid ? cnt : 0);
-#pragma unroll 4
-            for (int s = 0; s < nmax; s++) {
-                if (s < cnt) {
-                    const float key = kb[s * 32];
-                    if (key > m1) { m3 = m2; m2 = m1; s2 = s1; m1 = key; s1 = s; }
-                    else if (key > m2) { m3 = m2; m2 = key; s2 = s; }
-                    else if (key > m3) m3 = key;
+            const int nmax = __reduce_max_sync(full, cnt);
+            for (int s0 = 0; s0 < nmax; s0 += 4) {
+                Vec4<S> c[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) c[u] = P[s0 + u < cnt ? idx_at(s0 + u) : 0];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (s0 + u < cnt) {
+                        const float a = v.tile.key_of(c[u]);
+                        const int s = s0 + u;
+                        const bool g0_ = a > f0, g1_ = a > f1, g2_ = a > f2;
+                        f2 = g1_ ? f1 : (g2_ ? a : f2);
+                        f1 = g0_ ? f0 : (g1_ ? a : f1);  t1 = g0_ ? t0 : (g1_ ? s : t1);
+                        f0 = g0_ ? a : f0;               t0 = g0_ ? s : t0;
+                    }
                 }
             }
         }
         bool flagged = v.failed;
-        int nk = cnt, skth = s1;
-        float kth = m1, below = m2;
-        if (valid && !flagged && cnt == R) {
-            // k+1 entries: the largest is the (k+1)-th neighbour; it leaves, and certifies the set if the gap is wide enough
-            if (!(m1 > __fmul_ru(m2, AP_WIDEN))) flagged = true;
-            const int last = cnt - 1;
-            if (s1 != last) lg[s1 * 32] = lg[last * 32];
-            if (s2 == last) s2 = s1;
-            nk = cnt - 1; skth = s2; kth = m2; below = m3;
-        }
+        const int drop = cnt > k ? 1 : 0;                   // k+1 survivors: the largest is the (k+1)-th neighbour
+        float kth = f0, below = f1;
+        int skth = t0;
+        if (drop) { kth = f1; below = f2; skth = t1; }
+        const int nk = cnt - drop;
         const bool short_of_k = nk < k;                     // fewer than k candidates exist: the reference's heap keeps sentinels
-        if (valid && !flagged && !short_of_k && nk >= 2 && !(below < __fmul_rd(kth, AP_NARROW))) flagged = true;
+        if (valid && !flagged) {
+            const float kth_band = __fmul_ru(kth, AP_WIDEN);
+            if (drop && !(f0 > kth_band)) flagged = true;
+            // a candidate dropped in a round may lie anywhere in the root's bin: the k-th has to stay below that bin
+            if (drop && (v.mindrop & AP_KEYMASK) <= (rootw & AP_KEYMASK) && !(__uint_as_float(rootw & AP_KEYMASK) > kth_band)) flagged = true;
+            if (!short_of_k && nk >= 2 && !(below < __fmul_rd(kth, AP_NARROW))) flagged = true;
+        }
+        if (valid && !flagged && drop) {
+            const int last = cnt - 1;
+            if (t0 != last) { *word_at(t0) = *word_at(last); if (skth == last) skth = t0; }
+        }
         if (valid && flagged) {
             STAT_LANE(4, 1);
             int slot = atomicAdd(prm.flag_count, 1);
             prm.flag_list[slot] = (int)qi;
         }
-        __syncwarp();   // the key buffer is dead from here on (the velocity-density selection reuses it)
-
         // -------------------------------------------------------------------------------------- epilogues
-        if (valid && !flagged) {
-            double d2max = KNN_SENTINEL;
-            if (!short_of_k) {
-                const Vec4<S> c = P[lg[skth * 32]];
-                d2max = dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z);
-            }
-            sc_epilogue<S>(prm, P, lg, reinterpret_cast<double*>(base), lane, nk, d2max, x0, y0, z0, qi);
+        const bool on = valid && !flagged;
+        double d2max = KNN_SENTINEL;
+        if (on && !short_of_k) {
+            const Vec4<S> c = P[idx_at(skth)];
+            d2max = dist2_ref(x0, y0, z0, (double)c.x, (double)c.y, (double)c.z);
         }
+        sc_epilogue<S>(prm, P, idx_at, reinterpret_cast<double*>(base + heap_bytes), lane, on, on ? nk : 0, d2max, x0, y0, z0, qi);
         __syncwarp();
     }
 }
@@ -868,13 +863,38 @@ static void run_exact(nbk_tree& t, KnnParams& p, int64_t rows) {
 }
 
 // tuning overrides of the density kernel (nbk_set_option); the defaults are what ships
-static int g_knn_cap = 0, g_knn_leaf = 0, g_knn_exact = 0;
+static int g_knn_leaf = 0, g_knn_exact = 0;
 bool set_knn_option(const char* name, int64_t value) {
     const std::string s(name);
-    if (s == "knn_cap") { g_knn_cap = (int)value; return true; }
     if (s == "knn_leaf") { g_knn_leaf = (int)value; return true; }
     if (s == "knn_exact") { g_knn_exact = (int)value; return true; }
     return false;
+}
+
+// The fp32 keys of the density kernel must not overflow: squared distances inside the union of the root boxes stay below
+// AP_HUGE (decided once per tree; anything larger, or non finite, runs on the fp64-heap kernel).
+static bool ap_range_ok(nbk_tree& t) {
+    if (t.knn_fp32_ok < 0) {
+        NodeLo lo[2]; NodeHi hi[2];
+        int nb = 1;
+        NBK_CHECK(cudaMemcpyAsync(&lo[0], t.nlo, sizeof(NodeLo), cudaMemcpyDeviceToHost, t.stream));
+        NBK_CHECK(cudaMemcpyAsync(&hi[0], t.nhi, sizeof(NodeHi), cudaMemcpyDeviceToHost, t.stream));
+        if (t.nlo2) {
+            NBK_CHECK(cudaMemcpyAsync(&lo[1], t.nlo2, sizeof(NodeLo), cudaMemcpyDeviceToHost, t.stream));
+            NBK_CHECK(cudaMemcpyAsync(&hi[1], t.nhi2, sizeof(NodeHi), cudaMemcpyDeviceToHost, t.stream));
+            nb = 2;
+        }
+        NBK_CHECK(cudaStreamSynchronize(t.stream));
+        double mn[3] = {lo[0].x, lo[0].y, lo[0].z}, mx[3] = {hi[0].x, hi[0].y, hi[0].z};
+        if (nb == 2) {
+            const double l2[3] = {lo[1].x, lo[1].y, lo[1].z}, h2[3] = {hi[1].x, hi[1].y, hi[1].z};
+            for (int d = 0; d < 3; d++) { mn[d] = l2[d] < mn[d] ? l2[d] : mn[d]; mx[d] = h2[d] > mx[d] ? h2[d] : mx[d]; }
+        }
+        double ext2 = 0;
+        for (int d = 0; d < 3; d++) ext2 += (mx[d] - mn[d]) * (mx[d] - mn[d]);
+        t.knn_fp32_ok = (ext2 < 1.0e36) ? 1 : 0;             // false for NaN / inf as well
+    }
+    return t.knn_fp32_ok == 1;
 }
 
 void launch_knn(nbk_tree& t, const KnnArgs& a) {
@@ -895,7 +915,7 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     }
     const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm) && !a.gather && !a.qlist && !a.cand_excl && !a.crit_mode &&
                              !a.smvel_out && !a.smdisp_out;
-    if (smooth_only && !g_knn_exact) {
+    if (smooth_only && !g_knn_exact && ap_range_ok(t)) {
         // ---- append + prune kernel, exact kernel for the flagged queries -----------------------------------------
         p.kcap = a.k;
         // Nodes of up to `leaf` particles are scanned as one tile: the level whose nodes hold 21..40 particles (exactly one
@@ -914,31 +934,26 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             }
         }
         const int want_doubles = (a.veldens_k > 0 && a.veldens_k < a.k) ? 1 : 0;
-        int cap = ap_capacity(a.k);
-        if (g_knn_cap > a.k + 16) cap = (g_knn_cap + 7) & ~7;
-        NBK_REQUIRE(cap < 65536, NBK_ERR_ARG, "k too large");
-        const size_t smem = ap_warp_bytes(a.k, cap, want_doubles, t.store_bytes == 4 ? 32 * 16 : 96 * 8) * KNN_WARPS;
-        NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory candidate buffers");
+        const int tile_bytes = t.store_bytes == 4 ? 32 * 16 : 96 * 8;
+        const size_t smem = hp_warp_bytes(a.k, want_doubles, tile_bytes) * KNN_WARPS;
+        NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");
         int nsm = 0, per_sm = 0;
         NBK_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, t.device));
         const int64_t ngroups = (rows + 31) / 32;
         DevBuf<int> counters(2);
         DevBuf<int32_t> flist(rows);
-        DevBuf<int32_t> logbuf;
         NBK_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), t.stream));
         p.flag_count = counters.p; p.flag_list = flist.p;
         auto go = [&](auto kern) {
             NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             NBK_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KNN_WARPS * 32, smem));
-            NBK_REQUIRE(per_sm >= 1, NBK_ERR_ARG, "k too large for the shared-memory candidate buffers");
+            NBK_REQUIRE(per_sm >= 1, NBK_ERR_ARG, "k too large for the shared-memory heaps");
             int64_t blocks = (int64_t)nsm * per_sm;
             if (blocks > (ngroups + KNN_WARPS - 1) / KNN_WARPS) blocks = (ngroups + KNN_WARPS - 1) / KNN_WARPS;
-            // index log: one [cap][32] block per resident warp, rewritten in place group after group (stays in L2)
-            logbuf.alloc((size_t)blocks * KNN_WARPS * cap * 32);
-            kern<<<(int)blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles, cap, counters.p + 1, logbuf.p);
+            kern<<<(int)blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles, counters.p + 1);
         };
-        if (t.store_bytes == 4) { if (t.nlo2) go(knn_ap_kernel<float, true>); else go(knn_ap_kernel<float, false>); }
-        else { if (t.nlo2) go(knn_ap_kernel<double, true>); else go(knn_ap_kernel<double, false>); }
+        if (t.store_bytes == 4) { if (t.nlo2) go(knn_hp_kernel<float, true>); else go(knn_hp_kernel<float, false>); }
+        else { if (t.nlo2) go(knn_hp_kernel<double, true>); else go(knn_hp_kernel<double, false>); }
         NBK_CHECK(cudaGetLastError());
 #ifdef NBK_STATS
         {
@@ -946,8 +961,8 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             NBK_CHECK(cudaStreamSynchronize(t.stream));
             NBK_CHECK(cudaMemcpyFromSymbol(h, g_stats, sizeof(h)));
             double g = (double)((rows + 31) / 32);
-            fprintf(stderr, "[nbk stats] per warp: tiles %.1f prunes %.2f levels %.2f ; per lane: appended %.1f ; flagged %llu\n",
-                    h[0] / g, h[1] / g, h[2] / g, h[3] / (double)rows, h[4]);
+            fprintf(stderr, "[nbk stats] per warp: tiles %.1f rounds %.1f ; per lane: past the screen %.1f ; flagged %llu tile-list overflows %llu\n",
+                    h[0] / g, h[2] / g, h[3] / (double)rows, h[4], h[6]);
             unsigned long long z[8] = {0};
             NBK_CHECK(cudaMemcpyToSymbol(g_stats, z, sizeof(z)));
         }

@@ -15,6 +15,7 @@ struct nbk_tree {
     double period[3] = {0, 0, 0};
     int store_bytes = 4;            // 4: Vec4<float>, 8: Vec4<double>
     int64_t inexact = 0;
+    int knn_fp32_ok = -1;           // density kernel: squared distances inside the root box fit fp32 (-1: not decided yet)
 
     // tree-order particle arrays (HBM).  prim = coordinates the tree is built on (pos; vel for TVEL),
     // sec = the other phase-space half (may be null).
@@ -107,10 +108,12 @@ struct FofArgs {
     const int32_t* precheck_tree = nullptr;  // device, tree order, may be null
     bool attach = false;                     // FOFCriterionSetBasisForLinks: precheck != 0 particles cannot link but can be linked
     int32_t* group_tree = nullptr;           // device out, tree order
+    int32_t* roots_tree = nullptr;           // device out, tree order: when set, only each particle's root (tree index) is produced
     int64_t ngroups = 0;
     int32_t *head = nullptr, *next = nullptr, *tail = nullptr, *len = nullptr;  // device, optional
 };
 void launch_fof(nbk_tree& t, FofArgs& a);
+void launch_union_pairs(cudaStream_t st, int64_t nnodes, int64_t npairs, const int32_t* a, const int32_t* b, int32_t* root);
 bool set_fof_option(const char* name, int64_t value);   // nbk_set_option names starting with "fof_"
 
 // ball.cu

@@ -442,6 +442,19 @@ class KDTree:
             return g, ng.value, plen[:ng.value + 1]
         return g, ng.value
 
+    def FOFRoots(self, fdist=0.0, cmp=-1, params=None, precheck=None, out=None):
+        """nbk_fof_roots: the components of FOF(fdist) (cmp < 0) or FOFCriterion(cmp, params) without the minnum filter and the
+        numbering: root[ID] = ID of one fixed member of the particle's component (-1: excluded by precheck).  The building
+        block of the slab-sharded FOF.  out: int32 torch CUDA tensor => the result stays on the device."""
+        pr = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        if out is not None:
+            L.check(self._lib.nbk_fof_roots(self._h, int(cmp), float(fdist), _ptr(pr), None, _ptr(out), L.DEVICE_PTRS))
+            return out
+        pre = None if precheck is None else np.ascontiguousarray(precheck, dtype=np.int32)
+        root = np.empty(self.n, dtype=np.int32)
+        L.check(self._lib.nbk_fof_roots(self._h, int(cmp), float(fdist), _ptr(pr), _ptr(pre), _ptr(root), 0))
+        return root
+
     def FOFCriterionSetBasisForLinks(self, cmp, params, check, minnum=8, order=0):
         """KDTree::FOFCriterionSetBasisForLinks(cmp, params, numgroup, minnum, order, ipcheckflag, check) (KDFOF.cxx:268-378).
         check: the FOFcheckfunc values by ID; only check == 0 particles start / extend groups, the others can only be
@@ -455,12 +468,16 @@ class KDTree:
                                                   C.byref(ng), None, 0))
         return g, ng.value
 
-    def FOFCriterion(self, cmp, params, minnum=8, order=0, precheck=None):
+    def FOFCriterion(self, cmp, params, minnum=8, order=0, precheck=None, out=None):
         """KDTree::FOFCriterion(cmp, params, numgroups, minnum, order) (KDFOF.cxx:157-265) for cmp in
-        {FOF3D, FOF6D} (FOFFunc.h:30-55)."""
+        {FOF3D, FOF6D} (FOFFunc.h:30-55).  out: int32 torch CUDA tensor (by ID) => the group ids stay on the device."""
         ng = C.c_int64()
-        g = np.empty(self.n, dtype=np.int32)
         params = np.ascontiguousarray(params, dtype=np.float64)
+        if out is not None:
+            L.check(self._lib.nbk_fof_criterion(self._h, int(cmp), _ptr(params), int(minnum), int(order), None, _ptr(out),
+                                                C.byref(ng), None, L.DEVICE_PTRS))
+            return out, ng.value
+        g = np.empty(self.n, dtype=np.int32)
         pre = None if precheck is None else np.ascontiguousarray(precheck, dtype=np.int32)
         L.check(self._lib.nbk_fof_criterion(self._h, int(cmp), _ptr(params), int(minnum), int(order), _ptr(pre), _ptr(g),
                                             C.byref(ng), None, 0))

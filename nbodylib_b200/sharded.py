@@ -4,33 +4,33 @@
 The reference has no distributed code: VELOCIraptor does its own MPI domain decomposition and
 builds one local `KDTree` per rank.  This module is the B200 replacement for that outer layer on one node:
 
-* **Decomposition.**  The global box is cut into `world` slabs along x; rank r owns the particles with
-  x in [r, r+1) * Lx / world.  Nothing is ever gathered on one rank.
-* **Halo exchange** (the only data-path communication of the density pass): each rank sends the particles within
-  `h` of a slab face to the neighbour across that face (`batch_isend_irecv`, one message per face and direction,
-  x shifted by +-Lx across the periodic wrap when the caller asks for it) and builds ONE local tree over
-  owned + ghost particles.
-* **kNN-density** (`CalcDensity`): queries run for owned particles only, ghosts are pure neighbours.  The ghosts live
-  in a SECOND tree attached to the owned particles' tree (`nbk_attach_halo`; `two_trees=False` builds one tree over
-  owned + ghosts and masks the queries with `nbk_calc_density_subset` instead).  The symmetric scatter term that owned queries deposit on ghosts is sent back to the owners over
-  the same faces and added there, so every pair contributes exactly once -- the result equals the single-tree
-  result.  The halo must contain every owned particle's k-th neighbour ball: after the pass, r_k = 2 h_sm is
-  checked against (distance to the interior face + h); if any rank sees a violation (all-reduce) the halo is
+* **Decomposition.**  The global box (Lx, Ly, Lz) is cut into `world` slabs along x; rank r owns the particles with
+  x in [r, r+1) * Lx / world, given in GLOBAL coordinates.  Nothing is ever gathered on one rank, coordinates are never
+  shifted (ghosts keep their owners' exact values, so fp32-exact inputs stay fp32-exact and the local trees keep the
+  fp32 storage and the screened kernels).
+* **Halo exchange** (the only data-path communication): each rank sends the particles within `h` of a slab face to the
+  neighbour across that face (`batch_isend_irecv`, one message per face and direction).  `h` is ONE number for the whole
+  group (all-reduce MAX), and with three or more ranks it must stay below the slab width: a wider halo would need particles
+  from two slabs away, which this driver refuses instead of returning wrong results.
+* **kNN-density** (`CalcDensity`): queries run for owned particles only, ghosts are pure neighbours and live in a SECOND
+  tree attached to the owned particles' tree (`nbk_attach_halo`).  The symmetric scatter term that owned queries deposit
+  on ghosts is sent back to the owners over the same faces and added there, so every pair contributes exactly once -- the
+  result equals the single-tree result.  The halo must contain every owned particle's k-th neighbour ball: after the pass,
+  r_k = 2 h_sm is checked against (distance to the interior face + h); if any rank sees a violation the common halo is
   widened and the pass repeated.  `Calc*` never wrap (reference quirk Q2), so no ghosts cross the box edge.
-* **FOF**: local union-find over owned + ghosts with halo width just above the linking length (periodic wrap in x
-  through the ghosts, in y/z by the tree).  A ghost's local label and its owner's label for the same particle are
-  one cross-slab edge; edges and the owned sizes of the labels they touch are all-gathered and every rank runs
-  the same small union over boundary labels, then the `minnum` filter and one global numbering (by decreasing
-  size when `order`) are applied.
+* **FOF / FOFCriterion(FOF6d)**: one local tree over owned + ghosts (halo width just above the linking length), PERIODIC
+  with the global periods: a ghost from across the periodic wrap is found through the tree's own image search.  The tree
+  stays resident across calls.  The local pass returns every particle's component representative (`nbk_fof_roots`).  A
+  ghost's representative on this rank and its owner's representative for the same particle are one cross-slab edge; the
+  edges are all-gathered and every rank runs the same union on the device (`nbk_union_pairs`), then the `minnum` filter and
+  one global numbering (by decreasing size when `order`) are applied.  Only group-table-sized data ever visits the host.
 
-The per-rank compute engine is pluggable (`engine=`): the product uses `nbodylib_b200.KDTree` (CUDA); the gloo
-tests inject a brute-force engine so the exchange / merge logic is checked without a GPU.
+The per-rank compute engine is pluggable (`engine=`): the product uses `nbodylib_b200.KDTree` (CUDA); the gloo tests
+inject a brute-force engine so the exchange / merge logic is checked without a GPU.
 """
 import numpy as np
 import torch
 import torch.distributed as dist
-
-BIG_PERIOD_FACTOR = 1.0e6
 
 
 class CudaEngine:
@@ -53,49 +53,41 @@ class CudaEngine:
             tree.attach_halo(halo)
         return tree
 
-    def density(self, tree, k, active_u8, rho, hsm):
-        if getattr(tree, "n_main", None) is not None or active_u8 is None:
-            tree.CalcDensityInto(k, rho, hsm)       # queries = the main tree's particles by construction
-        else:
-            tree.CalcDensitySubset(k, active_u8, rho, hsm)
+    def density(self, tree, k, rho, hsm):
+        tree.CalcDensityInto(k, rho, hsm)       # queries = the main tree's particles by construction
         return tree.info
 
-    def fof_labels(self, tree, ll, out):
-        """labels 1..ng for every particle (minnum = 1), by ID"""
-        _, ng = tree.FOF(ll, 1, 0, out=out)
-        return ng
+    def fof_roots(self, tree, fdist, criterion, params, out):
+        """component representative (local particle index) of every particle of the local tree; int32 tensor `out`"""
+        tree.FOFRoots(fdist, criterion, params, out=out)
+        return tree.info
+
+    def union_pairs(self, nnodes, a, b):
+        from . import _lib as L
+        root = torch.empty(nnodes, dtype=torch.int32, device=a.device)
+        torch.cuda.current_stream(a.device).synchronize()
+        L.check(L.load().nbk_union_pairs(int(self.device), int(nnodes), int(a.numel()), a.data_ptr(), b.data_ptr(), root.data_ptr()))
+        return root
 
 
 class ShardedTree:
-    def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=None, slab_local=True, halo=None,
-                 knn_k=64, engine=None, group=None, two_trees=True):
-        """pos/vel/mass: this rank's particles (torch tensors on the rank's device).
-        slab_local=True : `pos` is given in slab-local coordinates [0,1)^3 (each rank generated its own unit box,
-                          the bench's weak-scaling set-up); the global box is [0,world) x [0,1) x [0,1).
-        slab_local=False: `pos` holds global coordinates inside this rank's slab of `box` = (Lx, Ly, Lz).
-        period: None or anything truthy -> the global box is periodic (FOF only; Calc* never wrap)."""
+    def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=None, halo=None, knn_k=64, engine=None, group=None):
+        """pos/vel/mass: this rank's particles (torch tensors on the rank's device, fp32 or fp64), GLOBAL coordinates inside
+        this rank's slab of `box` = (Lx, Ly, Lz).  period: None -> open box; anything else -> the global box is periodic with
+        periods `box` (FOF only; Calc* never wrap)."""
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.group = group
         self.dev = pos.device
-        self.f = torch.float64
         self.n_owned = int(pos.shape[0])
         self.periodic = period is not None
         W = self.world
-        if slab_local:
-            self.box = np.array([float(W), 1.0, 1.0])
-            # global x = fp32(x_local + rank): every rank sees the same fp32-representable global coordinates, so the
-            # local trees keep exact fp32 storage and ghosts are bit-identical copies of their owners' particles
-            gpos = pos.to(torch.float32).clone()
-            gpos[:, 0] += float(self.rank)
-            gpos[:, 0] = torch.clamp(gpos[:, 0], max=float(np.nextafter(np.float32(self.rank + 1), np.float32(0))))
-            gpos = gpos.to(self.f)
-        else:
-            self.box = np.asarray(box, dtype=np.float64)
-            gpos = pos.to(self.f)
+        self.box = np.asarray(box if box is not None else (1.0, 1.0, 1.0), dtype=np.float64)
         self.x0 = self.box[0] * self.rank / W
         self.x1 = self.box[0] * (self.rank + 1) / W
-        self.pos = gpos.contiguous()
+        self.slab_width = float(self.box[0] / W)
+        self.pos = pos.contiguous()
+        self.f = self.pos.dtype
         self.vel = None if vel is None else vel.to(self.f).contiguous()
         self.mass = (torch.ones(self.n_owned, dtype=self.f, device=self.dev) if mass is None else mass.to(self.f)).contiguous()
         counts = torch.zeros(W, dtype=torch.int64, device=self.dev)
@@ -106,27 +98,32 @@ class ShardedTree:
         self.n_global = int(counts.sum().item())
         self.engine = engine if engine is not None else CudaEngine(self.dev.index if self.dev.type == "cuda" else 0)
         self.left, self.right = (self.rank - 1) % W, (self.rank + 1) % W
-        # halo for the k-NN ball: a few times the radius that holds k particles at the slab's mean density
+        # halo for the k-NN ball: a few times the radius that holds k particles at the slab's mean density -- the LARGEST such
+        # radius over the ranks, so that what a rank receives is what its own completeness test assumes
         vol = (self.x1 - self.x0) * self.box[1] * self.box[2]
-        self.h_knn = float(halo) if halo is not None else 2.5 * (knn_k * vol / max(self.n_owned, 1) / (4.0 * np.pi / 3.0)) ** (1.0 / 3.0)
+        h = float(halo) if halo is not None else 2.5 * (knn_k * vol / max(self.n_owned, 1) / (4.0 * np.pi / 3.0)) ** (1.0 / 3.0)
+        self.h_knn = self._group_max(h)
         self._dens = None       # cached (tree, halo, ghost bookkeeping) for the density pass
-        self.two_trees = two_trees
+        self._fof = None        # cached local tree over owned + ghosts for the FOF passes
         self.last_info = None
         self.stats = {}
 
     # ------------------------------------------------------------------------------------------------ plumbing
-    def _cols(self, idx, shift):
-        c = [self.pos[idx]]
-        if shift != 0.0:
-            c[0] = c[0].clone()
-            c[0][:, 0] += shift
-        c.append(self.vel[idx] if self.vel is not None else torch.zeros((len(idx), 3), dtype=self.f, device=self.dev))
-        c.append(self.mass[idx][:, None])
-        c.append((idx + self.gid0).to(self.f)[:, None])
-        return torch.cat(c, dim=1).contiguous()
+    def _group_max(self, v):
+        if self.world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def _check_halo(self, h, what):
+        # two ranks: the one neighbour's whole slab is everything there is, so any width is complete
+        if self.world > 2 and not (h < self.slab_width):
+            raise ValueError("%s needs a halo of %.6g but a slab is only %.6g wide: particles two slabs away would be missing "
+                             "(use fewer ranks or a smaller %s)" % (what, h, self.slab_width, "k" if what == "CalcDensity" else "linking length"))
 
     def _sendrecv(self, to_left, to_right):
-        """Exchange one tensor with each face neighbour; returns (from_left, from_right).  Shapes [m, C]."""
+        """Exchange one tensor with each face neighbour; returns (from_left, from_right).  Shapes [m, C], any dtype."""
         W = self.world
         C = to_left.shape[1]
         cnt = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=self.dev)
@@ -152,9 +149,14 @@ class ShardedTree:
                 w.wait()
         return buf_l, buf_r
 
-    def _halo(self, h, wrap):
-        """Send the particles within h of each face; returns ghost table [m,8] and bookkeeping to send data back."""
-        W, Lx = self.world, self.box[0]
+    def _halo(self, h, wrap, with_vel=False, with_mass=True):
+        """Send the particles within h of each face.  Ghost columns: pos(3) [vel(3)] [mass(1)], and their global ids separately.
+        Returns the ghost tables and the bookkeeping to send per-ghost values back."""
+        W = self.world
+        if W == 1:
+            z = torch.zeros((0, 3 + (3 if with_vel else 0) + (1 if with_mass else 0)), dtype=self.f, device=self.dev)
+            e = torch.zeros(0, dtype=torch.int64, device=self.dev)
+            return {"send_l": e, "send_r": e, "from_l": z, "from_r": z, "gid_l": e, "gid_r": e, "h": h}
         x = self.pos[:, 0]
         send_l = torch.nonzero(x < self.x0 + h).flatten()
         send_r = torch.nonzero(x >= self.x1 - h).flatten()
@@ -163,33 +165,35 @@ class ShardedTree:
                 send_l = send_l[:0]
             if self.rank == W - 1:
                 send_r = send_r[:0]
-        shift_l = Lx if self.rank == 0 else 0.0          # my left neighbour sits at the far end of the box
-        shift_r = -Lx if self.rank == W - 1 else 0.0
-        from_l, from_r = self._sendrecv(self._cols(send_l, shift_l), self._cols(send_r, shift_r))
-        return {"send_l": send_l, "send_r": send_r, "from_l": from_l, "from_r": from_r, "h": h}
 
-    def _return_to_owners(self, halo, val_l, val_r):
-        """Inverse of _halo for one value per ghost: returns (values for my send_l particles, for my send_r)."""
-        back_l, back_r = self._sendrecv(val_l.contiguous(), val_r.contiguous())
+        def cols(idx):
+            c = [self.pos[idx]]
+            if with_vel:
+                c.append(self.vel[idx])
+            if with_mass:
+                c.append(self.mass[idx][:, None])
+            return torch.cat(c, dim=1).contiguous()
+
+        from_l, from_r = self._sendrecv(cols(send_l), cols(send_r))
+        gid_l, gid_r = self._sendrecv((send_l + self.gid0)[:, None].contiguous(), (send_r + self.gid0)[:, None].contiguous())
+        return {"send_l": send_l, "send_r": send_r, "from_l": from_l, "from_r": from_r, "gid_l": gid_l[:, 0], "gid_r": gid_r[:, 0], "h": h}
+
+    def _return_to_owners(self, val_l, val_r):
+        """Inverse of _halo for one row per ghost: returns (rows for my send_l particles, for my send_r particles)."""
+        if self.world == 1:
+            return val_l[:0], val_r[:0]
         # what comes back from my left neighbour concerns the particles I sent to the left, etc.
-        return back_l, back_r
+        return self._sendrecv(val_l.contiguous(), val_r.contiguous())
 
     # ------------------------------------------------------------------------------------------------- density
     def _density_setup(self, k):
+        self._check_halo(self.h_knn, "CalcDensity")
         halo = self._halo(self.h_knn, wrap=False)
         g = torch.cat([halo["from_l"], halo["from_r"]], dim=0)
         n_all = self.n_owned + g.shape[0]
-        if hasattr(self.engine, "build_with_halo") and self.two_trees:
-            tree = self.engine.build_with_halo(self.pos, self.mass, g[:, 0:3].contiguous(), g[:, 6].contiguous())
-            active = None
-        else:
-            pos = torch.cat([self.pos, g[:, 0:3]], dim=0).contiguous()
-            mass = torch.cat([self.mass, g[:, 6]], dim=0).contiguous()
-            tree = self.engine.build(pos, None, mass, None)
-            active = torch.zeros(n_all, dtype=torch.uint8, device=self.dev)
-            active[:self.n_owned] = 1
-        self._dens = {"tree": tree, "halo": halo, "active": active, "n_all": n_all,
-                      "rho": torch.empty(n_all, dtype=self.f, device=self.dev), "hsm": torch.empty(n_all, dtype=self.f, device=self.dev)}
+        tree = self.engine.build_with_halo(self.pos, self.mass, g[:, 0:3].contiguous(), g[:, 3].contiguous())
+        self._dens = {"tree": tree, "halo": halo, "n_all": n_all,
+                      "rho": torch.empty(n_all, dtype=torch.float64, device=self.dev), "hsm": torch.empty(n_all, dtype=torch.float64, device=self.dev)}
         self.stats["ghosts_knn"] = int(n_all - self.n_owned)
         self.stats["h_knn"] = float(self.h_knn)
         self.stats["density_setups"] = self.stats.get("density_setups", 0) + 1
@@ -200,10 +204,13 @@ class ShardedTree:
             if self._dens is None:
                 self._density_setup(Nsmooth)
             d = self._dens
-            self.last_info = self.engine.density(d["tree"], Nsmooth, d["active"], d["rho"], d["hsm"])
+            self.last_info = self.engine.density(d["tree"], Nsmooth, d["rho"], d["hsm"])
             n = self.n_owned
-            # does every owned k-ball stay inside owned + halo ?
-            x = self.pos[:, 0]
+            if self.world == 1:
+                break
+            # does every owned k-ball stay inside owned + halo ?  (h is the same on every rank, so what this rank received
+            # from a neighbour is everything within h of the shared face)
+            x = self.pos[:, 0].to(torch.float64)
             rk = 2.0 * d["hsm"][:n]
             h = d["halo"]["h"]
             bad = torch.zeros(n, dtype=torch.bool, device=self.dev)
@@ -217,12 +224,12 @@ class ShardedTree:
                 break
             if attempt == max_widen:
                 raise RuntimeError("ShardedTree.CalcDensity: halo still too narrow after %d widenings" % max_widen)
-            self.h_knn *= 1.6
+            self.h_knn = self._group_max(self.h_knn * 1.6)
             self.close_density()
         # scatter terms deposited on ghosts go home
         nl = d["halo"]["from_l"].shape[0]
         gr = d["rho"][n:]
-        back_l, back_r = self._return_to_owners(d["halo"], gr[:nl, None], gr[nl:, None])
+        back_l, back_r = self._return_to_owners(gr[:nl, None], gr[nl:, None])
         rho = d["rho"][:n].clone() if out is None else out
         if out is not None:
             out.copy_(d["rho"][:n])
@@ -240,112 +247,115 @@ class ShardedTree:
             self._dens = None
 
     # ----------------------------------------------------------------------------------------------------- FOF
-    def FOF(self, fdist, minnum=8, order=0):
-        """Global KDTree::FOF(fdist, ., minnum, order) on the periodic (or open) box.  Returns (group id per owned
-        particle as int64 tensor, total number of groups).  Group ids are global: 1..ngroups, by decreasing size when
-        `order`, otherwise by (home rank, local label)."""
-        W, n = self.world, self.n_owned
-        halo = self._halo(fdist * (1.0 + 1e-9) + 1e-300, wrap=self.periodic)
+    def _fof_setup(self, hw, with_vel):
+        key = (float(hw), bool(with_vel))
+        if self._fof is not None and self._fof["key"] == key:
+            return self._fof
+        self.close_fof()
+        self._check_halo(hw, "FOF")
+        halo = self._halo(hw, wrap=self.periodic, with_vel=with_vel, with_mass=False)
         g = torch.cat([halo["from_l"], halo["from_r"]], dim=0)
-        pos = torch.cat([self.pos, g[:, 0:3]], dim=0).contiguous()
-        n_all = pos.shape[0]
+        n, n_all = self.n_owned, self.n_owned + g.shape[0]
+        pos = torch.cat([self.pos, g[:, 0:3]], dim=0).contiguous() if g.shape[0] else self.pos
+        vel = None
+        if with_vel:
+            vel = torch.cat([self.vel, g[:, 3:6]], dim=0).contiguous() if g.shape[0] else self.vel
+        # the local tree wraps with the GLOBAL periods: ghosts keep their true coordinates
+        tree = self.engine.build(pos, vel, None, self.box.copy() if self.periodic else None)
+        gid = torch.cat([torch.arange(n, dtype=torch.int64, device=self.dev) + self.gid0, halo["gid_l"], halo["gid_r"]])
+        self._fof = {"key": key, "tree": tree, "halo": halo, "n_all": n_all, "gid": gid,
+                     "roots": torch.empty(n_all, dtype=torch.int32, device=self.dev)}
         self.stats["ghosts_fof"] = int(n_all - n)
-        ext = float(self.x1 - self.x0 + 2 * fdist)
-        period = np.array([BIG_PERIOD_FACTOR * max(ext, self.box[0]), self.box[1], self.box[2]]) if self.periodic else None
-        tree = self.engine.build(pos, None, None, period)
-        lab = torch.empty(n_all, dtype=torch.int32, device=self.dev)
-        ng_local = self.engine.fof_labels(tree, fdist, lab)
-        self.last_info = getattr(tree, "info", None)
-        if hasattr(tree, "close"):
-            tree.close()
-        lab = lab.to(torch.int64)
-        sizes = torch.bincount(lab[:n], minlength=ng_local + 1)          # owned members only: ghosts are counted at home
-        # ---- cross-slab edges: my label of each ghost goes back to its owner --------------------------------------
+        self.stats["fof_setups"] = self.stats.get("fof_setups", 0) + 1
+        return self._fof
+
+    def FOF(self, fdist, minnum=8, order=0):
+        """Global KDTree::FOF(fdist, ., minnum, order) on the periodic (or open) box.  Returns (group id per owned particle,
+        int32 tensor, and the total number of groups).  Group ids are global: 1..ngroups, by decreasing size when `order`,
+        otherwise cross-slab groups first, then by (home rank, representative)."""
+        return self._fof_run(float(fdist), -1, None, float(fdist), minnum, order)
+
+    def FOFCriterion(self, cmp, params, minnum=8, order=0):
+        """Global KDTree::FOFCriterion(cmp, params, ., minnum, order) for cmp in {FOF3D (0), FOF6D (2)}: params[6] / params[7] are
+        the squared position / velocity linking lengths (FOFFunc.h:30-55).  Velocities travel with the ghosts."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        return self._fof_run(0.0, int(cmp), params, float(np.sqrt(params[6])), minnum, order)
+
+    def _fof_run(self, fdist, criterion, params, reach, minnum, order):
+        W, n = self.world, self.n_owned
+        with_vel = criterion == 2
+        if with_vel and self.vel is None:
+            raise ValueError("FOF6d needs velocities")
+        F = self._fof_setup(reach * (1.0 + 1e-9) + 1e-300, with_vel)
+        n_all, roots, gid, halo = F["n_all"], F["roots"], F["gid"], F["halo"]
+        self.last_info = self.engine.fof_roots(F["tree"], fdist, criterion, params, roots)
+        rl = roots.long()
+        cnt_root = torch.bincount(rl[:n], minlength=n_all)               # owned members of every local component (ghosts count at home)
+        # ---- cross-slab edges: (name of my component holding a particle I sent) -- (name of the neighbour's component holding
+        #      its ghost copy); a component's name is the global id of its representative particle ---------------------------------
         nl = halo["from_l"].shape[0]
-        gl = lab[n:].to(self.f)
-        back_l, back_r = self._return_to_owners(halo, gl[:nl, None], gl[nl:, None])
-        e_mine = torch.cat([lab[halo["send_l"]], lab[halo["send_r"]]])
-        e_peer_rank = torch.cat([torch.full((len(halo["send_l"]),), self.left, dtype=torch.int64, device=self.dev),
-                                 torch.full((len(halo["send_r"]),), self.right, dtype=torch.int64, device=self.dev)])
-        e_peer = torch.cat([back_l[:, 0], back_r[:, 0]]).to(torch.int64)
-        edges = torch.stack([torch.full_like(e_mine, self.rank), e_mine, e_peer_rank, e_peer], dim=1)
-        edges = torch.unique(edges, dim=0) if edges.numel() else edges.reshape(0, 4)
-        # sizes of every label of mine that appears on either side of an edge: mine as source, or mine as a ghost
-        # label on the peer's side is covered by the peer's own edges (peer is the source there)
-        touched = torch.unique(torch.cat([e_mine, lab[n:]])) if (e_mine.numel() + (n_all - n)) else e_mine
-        node_tab = torch.stack([torch.full_like(touched, self.rank), touched, sizes[touched]], dim=1)
+        ghost_name = gid[rl[n:]]
+        back_l, back_r = self._return_to_owners(ghost_name[:nl, None], ghost_name[nl:, None])
+        sent = torch.cat([halo["send_l"], halo["send_r"]])
+        e_mine = gid[rl[sent]]
+        e_peer = torch.cat([back_l[:, 0], back_r[:, 0]]) if W > 1 else e_mine[:0]
+        keep = e_mine != e_peer
+        edges = torch.stack([e_mine[keep], e_peer[keep]], dim=1)
+        edges = torch.unique(edges, dim=0) if edges.shape[0] else edges.reshape(0, 2)
+        # the local components that touch the boundary (hold a sent particle or a ghost), with their owned sizes
+        touch_idx = torch.unique(torch.cat([rl[sent], rl[n:]])) if (sent.numel() + n_all - n) else rl[:0]
+        node_tab = torch.stack([gid[touch_idx], cnt_root[touch_idx]], dim=1)
         all_edges = self._allgather_rows(edges)
         all_nodes = self._allgather_rows(node_tab)
-        # ---- replicated union over boundary labels (host, small) ----------------------------------------------------
-        E = all_edges.cpu().numpy()
-        Nn = all_nodes.cpu().numpy()
-        key = lambda r, l: r.astype(np.int64) * (1 << 40) + l.astype(np.int64)
-        nodes = np.unique(np.concatenate([key(Nn[:, 0], Nn[:, 1]), key(E[:, 0], E[:, 1]), key(E[:, 2], E[:, 3])])) if len(Nn) + len(E) else np.zeros(0, np.int64)
-        nsz = np.zeros(len(nodes), dtype=np.int64)
-        if len(Nn):
-            nsz[np.searchsorted(nodes, key(Nn[:, 0], Nn[:, 1]))] = Nn[:, 2]
-        parent = np.arange(len(nodes))
-        if len(E):
-            a = np.searchsorted(nodes, key(E[:, 0], E[:, 1]))
-            b = np.searchsorted(nodes, key(E[:, 2], E[:, 3]))
-            from scipy.sparse import coo_matrix
-            from scipy.sparse.csgraph import connected_components
-            m = coo_matrix((np.ones(len(a), dtype=np.int8), (a, b)), shape=(len(nodes), len(nodes)))
-            _, comp = connected_components(m, directed=False)
-            # representative = smallest node key in the component (deterministic on every rank)
-            order_ = np.argsort(comp, kind="stable")
-            first = np.r_[0, np.nonzero(np.diff(comp[order_]))[0] + 1]
-            rep_of_comp = np.minimum.reduceat(np.arange(len(nodes))[order_], first)
-            parent = rep_of_comp[np.searchsorted(comp[order_][first], comp)]
-        comp_size = np.bincount(parent, weights=nsz, minlength=len(nodes)).astype(np.int64)
-        # ---- group table: interior labels of this rank + boundary components homed here ------------------------------
-        my_nodes = (nodes >> 40) == self.rank
-        my_labels_in_nodes = (nodes[my_nodes] & ((1 << 40) - 1))
-        is_boundary = torch.zeros(ng_local + 1, dtype=torch.bool, device=self.dev)
-        if len(my_labels_in_nodes):
-            is_boundary[torch.from_numpy(my_labels_in_nodes).to(self.dev)] = True
-        interior_valid = (~is_boundary) & (sizes >= minnum)
-        interior_valid[0] = False
-        int_labels = torch.nonzero(interior_valid).flatten()
-        reps = np.nonzero((parent == np.arange(len(nodes))) & (comp_size >= minnum) & ((nodes >> 40) == self.rank))[0]
-        my_sizes = torch.cat([sizes[int_labels], torch.from_numpy(comp_size[reps]).to(self.dev)])
-        # global numbering
-        tab = torch.stack([my_sizes, torch.full_like(my_sizes, self.rank), torch.arange(len(my_sizes), device=self.dev)], dim=1)
-        all_tab = self._allgather_rows(tab).cpu().numpy()
-        ngroups = len(all_tab)
-        if order:
-            perm = np.lexsort((all_tab[:, 2], all_tab[:, 1], -all_tab[:, 0]))
+        # ---- replicated union over the boundary components, on the device -----------------------------------------------------------
+        names = torch.unique(torch.cat([all_nodes[:, 0], all_edges.reshape(-1)]))            # sorted
+        nn = int(names.numel())
+        comp_size = torch.zeros(nn, dtype=torch.int64, device=self.dev)
+        if nn:
+            a = torch.searchsorted(names, all_edges[:, 0].contiguous()).to(torch.int32)
+            b = torch.searchsorted(names, all_edges[:, 1].contiguous()).to(torch.int32)
+            comp = self.engine.union_pairs(nn, a, b).long()                                  # smallest node of the component
+            comp_size.index_add_(0, comp[torch.searchsorted(names, all_nodes[:, 0].contiguous())], all_nodes[:, 1])
         else:
-            perm = np.lexsort((all_tab[:, 2], all_tab[:, 1]))
+            comp = torch.zeros(0, dtype=torch.int64, device=self.dev)
+        is_rep = comp == torch.arange(nn, device=self.dev)
+        valid_comp = torch.nonzero(is_rep & (comp_size >= minnum)).flatten()                  # the same on every rank
+        # ---- interior components of this rank ---------------------------------------------------------------------------------------
+        is_root = rl == torch.arange(n_all, device=self.dev)
+        touching = torch.zeros(n_all, dtype=torch.bool, device=self.dev)
+        touching[touch_idx] = True
+        int_roots = torch.nonzero(is_root & ~touching & (cnt_root >= minnum)).flatten()
+        int_sizes = cnt_root[int_roots]
+        # ---- one global numbering (small tables: on the host) ---------------------------------------------------------------------
+        tab = torch.stack([int_sizes, torch.full_like(int_sizes, self.rank), torch.arange(len(int_sizes), device=self.dev)], dim=1)
+        all_int = self._allgather_rows(tab).cpu().numpy()
+        bsz = comp_size[valid_comp].cpu().numpy()
+        nb = len(bsz)
+        size = np.concatenate([bsz, all_int[:, 0]])
+        kind = np.concatenate([np.zeros(nb, np.int64), np.ones(len(all_int), np.int64)])
+        rk = np.concatenate([np.zeros(nb, np.int64), all_int[:, 1]])
+        ix = np.concatenate([np.arange(nb, dtype=np.int64), all_int[:, 2]])
+        ngroups = len(size)
+        perm = np.lexsort((ix, rk, kind, -size)) if order else np.lexsort((ix, rk, kind))
         gid_of = np.empty(ngroups, dtype=np.int64)
         gid_of[perm] = np.arange(1, ngroups + 1)
-        mine = np.nonzero(all_tab[:, 1] == self.rank)[0]
-        my_gid = gid_of[mine]                                      # aligned with my_sizes (allgather keeps row order)
-        # label -> global id
-        lut = torch.zeros(ng_local + 1, dtype=torch.int64, device=self.dev)
-        n_int = len(int_labels)
-        if n_int:
-            lut[int_labels] = torch.from_numpy(my_gid[:n_int]).to(self.dev)
-        # boundary components: every rank needs the id of components homed elsewhere -> gather (rep key, gid)
-        rep_tab = torch.from_numpy(np.stack([nodes[reps], my_gid[n_int:]], axis=1) if len(reps) else np.zeros((0, 2), np.int64)).to(self.dev)
-        all_rep = self._allgather_rows(rep_tab).cpu().numpy()
-        if len(my_labels_in_nodes):
-            node_idx = np.nonzero(my_nodes)[0]
-            rep_key = nodes[parent[node_idx]]
-            gid_b = np.zeros(len(node_idx), dtype=np.int64)
-            if len(all_rep):
-                srt = np.argsort(all_rep[:, 0])
-                pos_ = np.searchsorted(all_rep[srt, 0], rep_key)
-                pos_ = np.clip(pos_, 0, len(srt) - 1)
-                hit = all_rep[srt[pos_], 0] == rep_key
-                gid_b[hit] = all_rep[srt[pos_[hit]], 1]
-            lut[torch.from_numpy(my_labels_in_nodes).to(self.dev)] = torch.from_numpy(gid_b).to(self.dev)
-        return lut[lab[:n]], ngroups
+        # ---- labels of the owned particles ------------------------------------------------------------------------------------------
+        lut = torch.zeros(n_all, dtype=torch.int32, device=self.dev)
+        mine = np.nonzero((kind == 1) & (rk == self.rank))[0]
+        if len(mine):
+            lut[int_roots] = torch.from_numpy(gid_of[mine].astype(np.int32)).to(self.dev)
+        if nn and len(touch_idx):
+            comp_gid = torch.zeros(nn, dtype=torch.int32, device=self.dev)
+            comp_gid[valid_comp] = torch.from_numpy(gid_of[:nb].astype(np.int32)).to(self.dev)
+            lut[touch_idx] = comp_gid[comp[torch.searchsorted(names, gid[touch_idx].contiguous())]]
+        return lut[rl[:n]], ngroups
 
     def _allgather_rows(self, t):
         """all-gather of [m_r, C] integer tables with different m_r; returns the concatenation in rank order."""
         W = self.world
         t = t.to(torch.int64).contiguous()
+        if W == 1:
+            return t
         C = t.shape[1]
         cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=self.dev)
         cnts = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(W)]
@@ -358,6 +368,13 @@ class ShardedTree:
         dist.all_gather(bufs, pad, group=self.group)
         return torch.cat([b[:c] for b, c in zip(bufs, cnts)], dim=0)
 
+    def close_fof(self):
+        if self._fof is not None:
+            t = self._fof["tree"]
+            if hasattr(t, "close"):
+                t.close()
+            self._fof = None
+
     # ---------------------------------------------------------------------------------------------------- misc
     @property
     def info(self):
@@ -365,3 +382,4 @@ class ShardedTree:
 
     def close(self):
         self.close_density()
+        self.close_fof()

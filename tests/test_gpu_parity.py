@@ -179,11 +179,10 @@ def test_fp32_key_ties_fall_back_to_exact_heap(nb, port):
         np.testing.assert_allclose(t.CalcVelDensity(7, 18), port.veldensity(pos, vel, 7, 18), rtol=RTOL_RHO)
 
 
-@pytest.mark.parametrize("opt", [{"knn_cap": 56}, {"knn_cap": 64, "knn_leaf": 16}, {"knn_leaf": 64}, {"knn_exact": 1}, {}])
+@pytest.mark.parametrize("opt", [{"knn_leaf": 16}, {"knn_leaf": 64}, {"knn_exact": 1}, {}])
 def test_density_kernel_variants(nb, port, opt):
-    """Every configuration of the density kernel gives the oracle's answer: a candidate buffer barely larger than k (a prune
-    every few candidates), unmerged 16-particle leaves, two-tile leaves, the exact fp64 heap only, and the defaults.  Both
-    storage widths."""
+    """Every configuration of the density kernel gives the oracle's answer: unmerged 16-particle leaves, two-tile leaves, the
+    exact fp64 heap only, and the defaults.  Both storage widths."""
     from nbodylib_b200.synth import clustered_small
     n, k = 30011, 40
     pos, vel, mass = clustered_small(n, seed=77)

@@ -1,5 +1,6 @@
-"""Multi-GPU parity (-m gpu, needs >= 2 GPUs, skipped otherwise): the slab-sharded driver with the CUDA engine over
-NCCL against the single-GPU tree on the same global particle set."""
+"""Multi-GPU parity (-m gpu): the slab-sharded driver with the CUDA engine over NCCL against the single-GPU tree on the same
+global particle set (needs >= 2 GPUs, skipped otherwise), and its single-GPU building blocks (nbk_fof_roots, nbk_union_pairs,
+the world-1 driver) on one GPU."""
 import os
 import tempfile
 
@@ -14,6 +15,15 @@ from tests.util import canon
 pytestmark = pytest.mark.gpu
 
 
+def _params6d(pos, vel, n):
+    ll = 0.25 / n ** (1 / 3)
+    sv2 = ((vel - vel.mean(0)) ** 2).sum(1).mean() / 3.0
+    params = np.zeros(10)
+    params[1] = params[6] = ll * ll
+    params[2] = params[7] = sv2
+    return params
+
+
 def _worker(rank, world, port, tmp, n):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -26,35 +36,82 @@ def _worker(rank, world, port, tmp, n):
         slab = np.minimum((pos[:, 0] * world).astype(int), world - 1)
         mine = np.nonzero(slab == rank)[0]
         dev = torch.device("cuda", rank)
-        st = ShardedTree(torch.from_numpy(pos[mine]).to(dev), torch.from_numpy(vel[mine]).to(dev), torch.from_numpy(mass[mine]).to(dev),
-                         period=np.ones(3), rank=rank, world=world, box=(1.0, 1.0, 1.0), slab_local=False, knn_k=32)
+        f = torch.float32                       # clustered_small is fp32-representable: the slab trees keep fp32 storage
+        st = ShardedTree(torch.from_numpy(pos[mine]).to(dev, f), torch.from_numpy(vel[mine]).to(dev, f), torch.from_numpy(mass[mine]).to(dev, f),
+                         period=np.ones(3), rank=rank, world=world, box=(1.0, 1.0, 1.0), knn_k=32)
         rho = st.CalcDensity(32)
         ll = 0.25 / n ** (1 / 3)
         g, ng = st.FOF(ll, 8, 1)
-        np.savez(os.path.join(tmp, "r%d.npz" % rank), idx=mine, rho=rho.cpu().numpy(), g=g.cpu().numpy(), ng=np.array([ng]))
+        g6, ng6 = st.FOFCriterion(2, _params6d(pos, vel, n), 8, 1)
+        assert st.stats["fof_setups"] == 2      # one slab tree without, one with velocities
+        np.savez(os.path.join(tmp, "r%d.npz" % rank), idx=mine, rho=rho.cpu().numpy(), g=g.cpu().numpy(), g6=g6.cpu().numpy(), ng=np.array([ng, ng6]))
         st.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_matches_single_gpu(built):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_matches_single_gpu(built, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import nbodylib_b200 as nb
     from nbodylib_b200.synth import clustered_small
-    n, world = 200000, 2
+    n = 200000
     pos, vel, mass = clustered_small(n, seed=5)
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_worker, args=(world, 29500 + np.random.randint(0, 2000), tmp, n), nprocs=world, join=True)
         res = [np.load(os.path.join(tmp, "r%d.npz" % r)) for r in range(world)]
     rho = np.zeros(n)
-    g = np.zeros(n, dtype=np.int64)
+    g, g6 = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
     for r in res:
         rho[r["idx"]] = r["rho"]
         g[r["idx"]] = r["g"]
+        g6[r["idx"]] = r["g6"]
     ll = 0.25 / n ** (1 / 3)
     with nb.KDTree(pos, vel, mass, Period=np.ones(3)) as t:
         np.testing.assert_allclose(rho, t.CalcDensity(32), rtol=1e-10)
         g1, ng1 = t.FOF(ll, 8, 1)
+        h1, nh1 = t.FOFCriterion(nb.FOF6D, _params6d(pos, vel, n), 8, 1)
     assert int(res[0]["ng"][0]) == ng1 and np.array_equal(canon(g), canon(g1))
     assert np.array_equal(np.bincount(g)[1:], np.bincount(g1)[1:])
+    assert int(res[0]["ng"][1]) == nh1 and np.array_equal(canon(g6), canon(h1))
+
+
+def test_world1_driver_and_building_blocks(built):
+    """One GPU: the sharded driver with a single rank (no process group needed) equals the plain tree, which exercises
+    nbk_fof_roots; nbk_union_pairs is checked on a random edge list against SciPy."""
+    import nbodylib_b200 as nb
+    from nbodylib_b200.sharded import CudaEngine, ShardedTree
+    from nbodylib_b200.synth import clustered_small
+    n = 60000
+    pos, vel, mass = clustered_small(n, seed=9)
+    dev = torch.device("cuda", 0)
+    st = ShardedTree(torch.from_numpy(pos).to(dev, torch.float32), torch.from_numpy(vel).to(dev, torch.float32), torch.from_numpy(mass).to(dev, torch.float32),
+                     period=np.ones(3), rank=0, world=1, box=(1.0, 1.0, 1.0), knn_k=24)
+    ll = 0.25 / n ** (1 / 3)
+    rho = st.CalcDensity(24).cpu().numpy()
+    g, ng = st.FOF(ll, 6, 1)
+    g6, ng6 = st.FOFCriterion(2, _params6d(pos, vel, n), 6, 0)
+    st.close()
+    with nb.KDTree(pos, vel, mass, Period=np.ones(3)) as t:
+        np.testing.assert_allclose(rho, t.CalcDensity(24), rtol=1e-10)
+        g1, ng1 = t.FOF(ll, 6, 1)
+        h1, nh1 = t.FOFCriterion(nb.FOF6D, _params6d(pos, vel, n), 6, 0)
+        roots = t.FOFRoots(ll)
+    assert ng == ng1 and np.array_equal(canon(g.cpu().numpy()), canon(g1)) and np.array_equal(np.bincount(g.cpu().numpy())[1:], np.bincount(g1)[1:])
+    assert ng6 == nh1 and np.array_equal(canon(g6.cpu().numpy()), canon(h1))
+    # roots: every member of a group shares one representative, which is a member itself
+    assert np.array_equal(roots[roots], roots)
+    sel = g1 > 0
+    assert len(np.unique(roots[sel])) == ng1
+    # connected components of a random graph
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    rng = np.random.default_rng(1)
+    nn, ne = 50000, 40000
+    a, b = rng.integers(0, nn, ne).astype(np.int32), rng.integers(0, nn, ne).astype(np.int32)
+    root = CudaEngine(0).union_pairs(nn, torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)).cpu().numpy()
+    ncomp, comp = connected_components(coo_matrix((np.ones(ne, dtype=np.int8), (a, b)), shape=(nn, nn)), directed=False)
+    first = np.full(ncomp, nn, dtype=np.int64)
+    np.minimum.at(first, comp, np.arange(nn))
+    assert np.array_equal(root, first[comp])
