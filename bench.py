@@ -28,6 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K_NN = 64
+# global lattice (in units of the per-GPU cube) for N ranks: N * ng^3 particles in all, slabs along x
+SHARD_DIMS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 ALG_BYTES = {"knn_density": 24, "veldensity": 36, "fof3d": 24, "fof6d": 36, "build": 36}
 
 
@@ -209,10 +211,23 @@ def main():
 
     t_start = time.perf_counter()
     ng = args.ng
-    n = ng ** 3
-    nh = max(8, min(8192, n // 16384))
-    pos, vel, mass = clustered_box(ng, seed=2025 + 10 * rank, nhalo=nh, device="cuda")
-    period = np.ones(3)
+    nh = max(8, min(8192, ng ** 3 // 16384))
+    # N GPUs: ONE periodic box of N * ng^3 particles (8 GPUs at ng = 512: the 1024^3 cube of BASELINE config 5), cut into N
+    # slabs along x; every rank generates the same global field and keeps its slab
+    dims = SHARD_DIMS[world]
+    box = np.array(dims, dtype=np.float64)
+    if world > 1:
+        pos, vel, mass = clustered_box(ng, seed=2025, nhalo=nh * world, device="cuda", dims=dims, slab=(rank, world))
+        torch.cuda.empty_cache()
+    else:
+        pos, vel, mass = clustered_box(ng, seed=2025, nhalo=nh, device="cuda")
+    n = int(pos.shape[0])                       # this rank's particles
+    n_total = n
+    if world > 1:
+        tcount = torch.tensor([n], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tcount)
+        n_total = int(tcount.item())
+    period = box.copy()
     peak, peak_src = measured_peak()
 
     def barrier():
@@ -226,7 +241,7 @@ def main():
 
     if world > 1:
         from nbodylib_b200.sharded import ShardedTree
-        tree = ShardedTree(pos, vel, mass, period=period, rank=rank, world=world)
+        tree = ShardedTree(pos, vel, mass, period=period, rank=rank, world=world, box=box)
     else:
         tree = KDTree(pos, vel, mass, Period=period, device=local)
     info = tree.info
@@ -265,7 +280,7 @@ def main():
     dev_s, wall = float(tmax[0].item()), float(tmax[1].item())
     clocks = sampler.stop() if sampler else None
     ms_step = dev_s * 1e3 / args.steps
-    value = n * world / (dev_s / args.steps)
+    value = n_total / (dev_s / args.steps)
 
     # ---- untimed self-check of the timed step (N = 1): the same CalcDensity through the INDEPENDENT fp64-heap kernel ------
     checked = None
@@ -349,26 +364,47 @@ def main():
                                       "algorithmic_bytes_per_particle": ALG_BYTES["build"], "achieved": n * ALG_BYTES["build"] / (build_ms * 1e-3) / 1e9,
                                       "peak": peak, "unit": "GB/s", "frac": n * ALG_BYTES["build"] / (build_ms * 1e-3) / 1e9 / peak, "traffic": None}}
     if world > 1:
-        extra["sharded_rank0"] = dict(tree.stats)
-    if world > 1 and os.environ.get("BENCH_SHARDED_FOF"):
-        # BASELINE config 5: 3D FOF of the whole slab-sharded periodic box (halo exchange, local union-find, cross-slab merge).
-        # Off by default: a rank-local failure between two collectives would hang the other ranks.
+        # BASELINE configs 4 / 5 on the slab-sharded box: 3D FOF and 6D FOF (in-tree criterion), K steps each; a step is the
+        # whole call on a resident slab tree (local union-find over owned + ghosts, cross-slab merge, global numbering)
+        def timed(fn, reps):
+            ts = []
+            for it in range(1 + reps):
+                barrier(); t1 = time.perf_counter()
+                out = fn()
+                barrier()
+                tt = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                if it > 0:
+                    ts.append(float(tt.item()))
+            return float(np.mean(ts)), out
+
+        tree.close_density()
+        torch.cuda.empty_cache()
         try:
-            tree.close_density()
-            progress("sharded FOF starts")
-            barrier(); t1 = time.perf_counter()
-            gfof, ngl = tree.FOF(0.2 / ng, 20, 1)
-            barrier()
-            tf = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            extra["fof3d_particles_per_s"] = n * world / float(tf.item())
-            extra["fof3d_ms"] = float(tf.item()) * 1e3
-            extra["fof3d_groups"] = int(ngl)
-            extra["fof3d_note"] = "ShardedTree.FOF: halo exchange + local tree build + union-find + cross-slab merge, all inside the timed region"
-            del gfof
-            progress("sharded FOF done")
-        except Exception as ex:  # the headline line must survive a failure of this extra
-            extra["fof3d_error"] = repr(ex)[:300]
+            sums = torch.cat([vel.double().sum(0), (vel.double() ** 2).sum(0)])
+            dist.all_reduce(sums)
+            mean = sums[:3] / n_total
+            sv2 = float(((sums[3:] / n_total) - mean ** 2).sum().item() / 3.0)
+            params = np.zeros(10)
+            params[1] = params[6] = (0.2 / ng) ** 2
+            params[2] = params[7] = (1.25 ** 2) * sv2
+            dt, (g3, ng3) = timed(lambda: tree.FOF(0.2 / ng, 20, 1), max(2, args.steps // 2))
+            rows["fof3d"] = {"metric": "fof3d_particles_per_s", "value": n_total / dt, "unit": "particles/s", "ms_per_step": dt * 1e3, "groups": int(ng3),
+                             "call": "ShardedTree.FOF(0.2 mean spacings, minnum 20, order 1), periodic global box: local union-find over owned + ghosts, "
+                                     "all-gathered cross-slab edges, device-side union, global numbering; max over ranks",
+                             "ghosts_rank0": int(tree.stats.get("ghosts_fof", 0)), "link_kernel_ms_rank0": float(tree.info.last_kernel_ms)}
+            del g3
+            dt, (g6, ng6) = timed(lambda: tree.FOFCriterion(2, params, 20, 1), max(2, args.steps // 2))
+            rows["fof6d"] = {"metric": "fof6d_particles_per_s", "value": n_total / dt, "unit": "particles/s", "ms_per_step": dt * 1e3, "groups": int(ng6),
+                             "call": "ShardedTree.FOFCriterion(FOF6d, ll_x = 0.2 spacings, ll_v = 1.25 sigma_v, minnum 20, order 1), periodic global box; "
+                                     "velocities travel with the ghosts; max over ranks",
+                             "ghosts_rank0": int(tree.stats.get("ghosts_fof", 0)), "link_kernel_ms_rank0": float(tree.info.last_kernel_ms)}
+            del g6
+        except Exception as ex:  # the headline line must survive a failure of these rows
+            extra["fof_error"] = repr(ex)[:300]
+        extra["sharded_rank0"] = dict(tree.stats)
+        extra["box"] = list(map(float, box))
+        extra["particles_total"] = n_total
     tree.close()
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------
@@ -382,7 +418,7 @@ def main():
         for it in range(1 + max(1, args.steps // 2)):
             barrier(); t1 = time.perf_counter()
             dp, dm = hp.to("cuda", non_blocking=True), hm.to("cuda", non_blocking=True)
-            st = ShardedTree(dp, None, dm, period=period, rank=rank, world=world)
+            st = ShardedTree(dp, None, dm, period=period, rank=rank, world=world, box=box)
             r = st.CalcDensity(K_NN)
             out.copy_(r)
             barrier()
@@ -392,8 +428,8 @@ def main():
             del st, dp, dm, r
             if it > 0:
                 ts.append(float(tt.item()))
-        e2e = {"value": n * world / float(np.mean(ts)), "unit": "particles/s", "h2d_bytes_per_step": int((hp.numel() * hp.element_size() + hm.numel() * hm.element_size()) * world),
-               "d2h_bytes_per_step": int(out.numel() * 8 * world), "ms_per_step": float(np.mean(ts)) * 1e3,
+        e2e = {"value": n_total / float(np.mean(ts)), "unit": "particles/s", "h2d_bytes_per_step": int(16 * n_total),
+               "d2h_bytes_per_step": int(8 * n_total), "ms_per_step": float(np.mean(ts)) * 1e3,
                "includes": "per rank: H2D of pos/mass (fp32, pinned host arrays), halo exchange, tree builds (owned + halo), CalcDensity(64) with scatter return, D2H of rho (fp64, pinned); max over ranks"}
     if not args.no_e2e and world == 1:
         hp, hv, hm = (x.cpu().pin_memory().numpy() for x in (pos, vel, mass))
@@ -508,8 +544,11 @@ def main():
             "metric": "knn_density_particles_per_s", "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(ng, nh),
-                       "particles_per_gpu": n, "k": K_NN, "storage": "fp32 coordinates (exact), fp64 distance arithmetic",
+            "config": {"workload": workload_name(ng, nh) if world == 1 else
+                       "one clustered periodic box of %d x %d x %d lattice cells (%d particles, ZA + %d Plummer halos) cut into %d slabs along x, one per GPU, "
+                       "KDTree bucket=16, CalcDensity(%d): kNN + SPH density" % (dims[0] * ng, dims[1] * ng, dims[2] * ng, n_total, nh * world, world, K_NN),
+                       "particles_per_gpu": n_total // world, "particles_total": n_total, "k": K_NN,
+                       "storage": "fp32 coordinates (exact), fp32 screening keys with a certified error band, fp64 distances and sums for the results",
                        "l2": "inputs (%.1f GB) exceed L2, no flush needed" % (n * 16 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "knn_ap_kernel<float,false>", "kernel_ms": kms,

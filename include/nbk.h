@@ -251,6 +251,8 @@ int nbk_union_pairs(int device, int64_t nnodes, int64_t npairs, const int32_t* a
  * reference counterpart: the reference's only knobs are constructor arguments.  Names:
  *   "knn_leaf"    particles per scanned tile of the density kernel (0 = the tree level holding 21..40 particles)
  *   "knn_exact"   1: the Calc* family runs on the fp64-heap kernel only
+ *   "knn_transpose" density kernel: tiles needed by at most this many of a warp's 32 queries are screened query-by-query
+ *                 (-1 = default 12, 0 = never)
  *   "fof_screen"  0: the 3D link kernel skips its fp32 screen
  * Unknown names return NBK_ERR_ARG. */
 int nbk_set_option(const char* name, int64_t value);

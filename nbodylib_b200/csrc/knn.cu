@@ -63,6 +63,7 @@ struct KnnParams {
     // smoothed velocity moments (CalcSmoothVel / CalcSmoothVelDisp): densities in, accumulators out, all tree order
     const double* rho_in; const double* smvel_in; double* smvel_out; double* smdisp_out;
     int64_t n_tree;                                   // particles of the main tree (= n unless a halo is attached)
+    int tr_max;                                       // density kernel: transposed screening threshold (lanes needing a tile)
 };
 
 // ================================================================================================ exact
@@ -454,8 +455,15 @@ template <> struct ApTile<float> {
         if ((int)lane < m) { Vec4<float> c = P[first + lane]; mine = make_float4(c.x, c.y, c.z, 0.f); }
         t[lane] = mine;
     }
+    static constexpr bool TRANSPOSABLE = true;
     __device__ __forceinline__ float key(int j) const { const float4 c = t[j]; return ap_key(qx, qy, qz, c.x, c.y, c.z); }
     __device__ __forceinline__ float key_of(const Vec4<float>& c) const { return ap_key(qx, qy, qz, c.x, c.y, c.z); }
+    // key of lane q's query against candidate j of the staged tile (all lanes call it with the same q)
+    __device__ __forceinline__ unsigned key_bits_for(int q, int j) const {
+        const float4 c = t[j];
+        const float x = __shfl_sync(0xffffffffu, qx, q), y = __shfl_sync(0xffffffffu, qy, q), z = __shfl_sync(0xffffffffu, qz, q);
+        return __float_as_uint(ap_key(x, y, z, c.x, c.y, c.z));
+    }
     __device__ __forceinline__ bool coincident(int j) const { const float4 c = t[j]; return qx == c.x && qy == c.y && qz == c.z; }
 };
 template <> struct ApTile<double> {
@@ -469,8 +477,10 @@ template <> struct ApTile<double> {
         if ((int)lane < m) { Vec4<double> c = P[first + lane]; cx = c.x; cy = c.y; cz = c.z; }
         t[lane] = cx; t[32 + lane] = cy; t[64 + lane] = cz;
     }
+    static constexpr bool TRANSPOSABLE = false;
     __device__ __forceinline__ float key(int j) const { return ap_key(qx, qy, qz, t[j], t[32 + j], t[64 + j]); }
     __device__ __forceinline__ float key_of(const Vec4<double>& c) const { return ap_key(qx, qy, qz, c.x, c.y, c.z); }
+    __device__ __forceinline__ unsigned key_bits_for(int, int) const { return 0u; }
     __device__ __forceinline__ bool coincident(int j) const { return qx == t[j] && qy == t[32 + j] && qz == t[64 + j]; }
 };
 
@@ -624,6 +634,7 @@ struct HpVisitor {
     unsigned limu;        // the same limit for the unsigned screen test (bits(a) - bits(AP_TINY) < limu); 0: nothing passes
     unsigned mindrop;     // smallest word rejected or evicted in a round once the heap was full
     int filled, kcap;     // heap slots taken so far (the first k+1 candidates are stored without sifting), k + 1
+    int tr_max;           // tiles needed by at most this many lanes are screened in the transposed form
     bool failed;
     unsigned lane;
     static constexpr unsigned TINY_BITS = 0x0d800000u;      // bits of AP_TINY = 2^-100
@@ -634,7 +645,7 @@ struct HpVisitor {
         set_limit(w < AP_HUGE ? fminf(__fmul_ru(__uint_as_float(__float_as_uint(w) | AP_CIDMASK), AP_WIDEN), AP_HUGE) : AP_HUGE);
     }
     __device__ __forceinline__ void fail() { failed = true; limf = -1.f; limu = 0u; }
-    __device__ __forceinline__ void leaf(int start, int n, int, unsigned) {
+    __device__ __forceinline__ void leaf(int start, int n, int, unsigned nmask) {
         for (int base = 0; base < n; base += 32) {
             const int m = min(32, n - base);
             if (nt >= AP_MAXTILES) { if (limu != 0u) { STAT(6, 1); fail(); } return; }      // tile list full: the whole group goes to the exact kernel
@@ -648,18 +659,33 @@ struct HpVisitor {
             // pass 1: one unsigned comparison per candidate (NaN padding, keys below 2^-100 -- the query itself, coincident
             // particles, underflow -- and keys above the limit all fail it)
             unsigned acc = 0u, tiny = 0u;
-            for (int j0 = 0; j0 < m; j0 += 8) {
-                float a[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) a[jj] = tile.key(j0 + jj);
-                unsigned a8 = 0u;
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) {
-                    const unsigned u = __float_as_uint(a[jj]) - TINY_BITS;
-                    tiny |= u;
-                    if (u < limu) a8 |= 1u << jj;
+            if (ApTile<S>::TRANSPOSABLE && __popc(nmask) <= tr_max) {
+                // few lanes need this tile: lane j takes candidate j and the needing queries are broadcast one at a time, so a
+                // query costs one key per lane instead of 32 (same expression, same bits as the direct form)
+                unsigned rem = nmask;
+                while (rem) {
+                    const int q = __ffs(rem) - 1;
+                    rem &= rem - 1u;
+                    const unsigned u = tile.key_bits_for(q, lane) - TINY_BITS;
+                    const unsigned lq = __shfl_sync(0xffffffffu, limu, q);
+                    const unsigned mk = __ballot_sync(0xffffffffu, u < lq);
+                    const unsigned tn = __ballot_sync(0xffffffffu, (int)u < 0);
+                    if ((int)lane == q) { acc = mk; tiny = tn ? 0x80000000u : 0u; }
                 }
-                acc |= a8 << j0;
+            } else {
+                for (int j0 = 0; j0 < m; j0 += 8) {
+                    float a[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) a[jj] = tile.key(j0 + jj);
+                    unsigned a8 = 0u;
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        const unsigned u = __float_as_uint(a[jj]) - TINY_BITS;
+                        tiny |= u;
+                        if (u < limu) a8 |= 1u << jj;
+                    }
+                    acc |= a8 << j0;
+                }
             }
             if ((int)tiny < 0 && limu != 0u) {
                 // rare: the query itself and coincident particles (never neighbours), or a distance that underflows fp32
@@ -745,7 +771,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm
         v.hp.kb = kb; v.hp.G = G;
         v.tl = tl; v.nt = 0;
         v.mindrop = 0xffffffffu;
-        v.filled = 0; v.kcap = kcap;
+        v.filled = 0; v.kcap = kcap; v.tr_max = prm.tr_max;
         v.failed = false;
         // empty real slots hold +inf, the padding up to 4G+1 nodes holds 0 (never evicted, never accepted against)
         for (int p = 0; p < NN; p++) *v.hp.keyp(p) = p < kcap ? AP_INF : 0.f;
@@ -827,12 +853,23 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm
 }
 
 
+// tuning overrides of the density kernel (nbk_set_option); the defaults are what ships
+static int g_knn_leaf = 0, g_knn_exact = 0, g_knn_transpose = -1;
+bool set_knn_option(const char* name, int64_t value) {
+    const std::string s(name);
+    if (s == "knn_leaf") { g_knn_leaf = (int)value; return true; }
+    if (s == "knn_exact") { g_knn_exact = (int)value; return true; }
+    if (s == "knn_transpose") { g_knn_transpose = (int)value; return true; }
+    return false;
+}
+
 static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.nlo = t.nlo; p.nhi = t.nhi; p.bucket = t.bucket;
     p.nlo2 = t.nlo2; p.nhi2 = t.nhi2; p.bucket2 = t.bucket;
     p.P = t.prim; p.V = t.vel4(); p.mass = t.mass; p.order = t.order;
     p.n = t.n;
     p.n_tree = t.n_main ? t.n_main : t.n;
+    p.tr_max = g_knn_transpose >= 0 ? g_knn_transpose : 12;
     p.q0 = a.q0; p.q1 = a.q1; p.xq = a.xq; p.mode = a.mode;
     p.qlist = a.qlist; p.nq = a.nq;
     p.gather = a.gather ? 1 : 0; p.vq = a.vq;
@@ -860,15 +897,6 @@ static void run_exact(nbk_tree& t, KnnParams& p, int64_t rows) {
     if (t.store_bytes == 4) { if (filter) go(knn_exact_kernel<float, true>); else go(knn_exact_kernel<float, false>); }
     else { if (filter) go(knn_exact_kernel<double, true>); else go(knn_exact_kernel<double, false>); }
     NBK_CHECK(cudaGetLastError());
-}
-
-// tuning overrides of the density kernel (nbk_set_option); the defaults are what ships
-static int g_knn_leaf = 0, g_knn_exact = 0;
-bool set_knn_option(const char* name, int64_t value) {
-    const std::string s(name);
-    if (s == "knn_leaf") { g_knn_leaf = (int)value; return true; }
-    if (s == "knn_exact") { g_knn_exact = (int)value; return true; }
-    return false;
 }
 
 // The fp32 keys of the density kernel must not overflow: squared distances inside the union of the root boxes stay below

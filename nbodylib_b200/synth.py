@@ -35,39 +35,50 @@ def clustered_small(n, seed=1, nhalo=24, frac=0.5):
     return _f32(pos), _f32(vel), _f32(mass)
 
 
-def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_members=64):
-    """cfg 2-5 generator: ng^3 cell-centred lattice in the unit box + Zel'dovich displacement
-    psi (Gaussian field, P_psi(k) ~ k^-2, rms |psi| = 1.5 lattice spacings, v = psi), wrapped periodically;
-    a random `halo_frac` of the particles is relocated into `nhalo` Plummer spheres:
-        centres U[0,1)^3, membership n_h ~ 1/rank (at least `min_members`), scale radius a_h = 0.3 D (n_h/64)^(1/3),
+def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_members=64, dims=None, slab=None):
+    """cfg 2-5 generator: a cell-centred lattice of spacing D = 1/ng + Zel'dovich displacement psi (Gaussian field,
+    P_psi(k) ~ k^-2, rms |psi| = 1.5 lattice spacings, v = psi), wrapped periodically; a random `halo_frac` of the particles
+    is relocated into `nhalo` Plummer spheres:
+        centres uniform in the box, membership n_h ~ 1/rank (at least `min_members`), scale radius a_h = 0.3 D (n_h/64)^(1/3),
         r = a / sqrt(u^(-2/3) - 1) with u in (0, 0.99), isotropic directions,
-        velocities = bulk N(0, (1.5 D)^2 / 3) per component + N(0, sigma_h^2), sigma_h = 0.3 D (n_h/64)^(1/3)
-    (D = 1/ng).  Returns float32 torch tensors (pos[N,3], vel[N,3], mass[N]) on `device`; every value is therefore
-    exactly representable in fp32 and is widened, not rounded, for the fp64 reference."""
+        velocities = bulk N(0, (1.5 D)^2 / 3) per component + N(0, sigma_h^2), sigma_h = 0.3 D (n_h/64)^(1/3).
+    dims = (cx, cy, cz): the lattice has cx*ng x cy*ng x cz*ng cells and the periodic box is (cx, cy, cz) long (default (1, 1, 1):
+    the ng^3 unit cube).  slab = (rank, world): only the particles whose x falls into slab `rank` of `world` equal slabs along x
+    are returned -- every rank of a sharded run generates the SAME global field and keeps its own slab (BASELINE config 5: one
+    1024^3 cube cut into slabs).  Returns float32 torch tensors (pos[N,3], vel[N,3], mass[N]) on `device`; every value is
+    therefore exactly representable in fp32 and is widened, not rounded, for the fp64 reference."""
     import torch
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(int(seed))
-    n = ng ** 3
+    cx, cy, cz = dims if dims is not None else (1, 1, 1)
+    gx, gy, gz = cx * ng, cy * ng, cz * ng
+    box = torch.tensor([float(cx), float(cy), float(cz)], device=dev, dtype=torch.float32)
+    n = gx * gy * gz
     D = 1.0 / ng
-    w = torch.randn((ng, ng, ng), generator=gen, device=dev, dtype=torch.float32)
+    w = torch.randn((gx, gy, gz), generator=gen, device=dev, dtype=torch.float32)
     wk = torch.fft.rfftn(w)
     del w
-    kx = torch.fft.fftfreq(ng, d=1.0 / ng, device=dev)
-    kz = torch.fft.rfftfreq(ng, d=1.0 / ng, device=dev)
-    k2 = kx[:, None, None] ** 2 + kx[None, :, None] ** 2 + kz[None, None, :] ** 2
+    # wave numbers in units of 2 pi / (unit length): n_d / L_d with L_d = c_d
+    kx = torch.fft.fftfreq(gx, d=1.0 / gx, device=dev) / cx
+    ky = torch.fft.fftfreq(gy, d=1.0 / gy, device=dev) / cy
+    kz = torch.fft.rfftfreq(gz, d=1.0 / gz, device=dev) / cz
+    k2 = kx[:, None, None] ** 2 + ky[None, :, None] ** 2 + kz[None, None, :] ** 2
     k2[0, 0, 0] = 1.0
     phik = wk / k2
     phik[0, 0, 0] = 0
     del wk, k2
     psi = torch.empty((n, 3), device=dev, dtype=torch.float32)
-    for j, kk in enumerate((kx[:, None, None], kx[None, :, None], kz[None, None, :])):
-        psi[:, j] = torch.fft.irfftn(1j * kk * phik, s=(ng, ng, ng)).reshape(-1)
+    for j, kk in enumerate((kx[:, None, None], ky[None, :, None], kz[None, None, :])):
+        psi[:, j] = torch.fft.irfftn(1j * kk * phik, s=(gx, gy, gz)).reshape(-1)
     del phik
     rms = torch.sqrt((psi.double() ** 2).sum(1).mean()).item()
     psi *= (1.5 * D / rms)
-    g = (torch.arange(ng, device=dev, dtype=torch.float32) + 0.5) * D
-    pos = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), dim=-1).reshape(-1, 3).clone()
+    ax = [(torch.arange(g, device=dev, dtype=torch.float32) + 0.5) * D for g in (gx, gy, gz)]
+    pos = torch.empty((n, 3), device=dev, dtype=torch.float32)
+    pos[:, 0] = ax[0][:, None, None].expand(gx, gy, gz).reshape(-1)
+    pos[:, 1] = ax[1][None, :, None].expand(gx, gy, gz).reshape(-1)
+    pos[:, 2] = ax[2][None, None, :].expand(gx, gy, gz).reshape(-1)
     pos += psi
     vel = psi
     if nhalo > 0 and halo_frac > 0:
@@ -80,7 +91,7 @@ def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_m
         assert memb[0] > 0, "halo_frac too small for min_members * nhalo"
         hid = torch.repeat_interleave(torch.arange(nhalo, device=dev), memb)
         sel = torch.randperm(n, generator=gen, device=dev)[:nh_tot]
-        centres = torch.rand((nhalo, 3), generator=gen, device=dev, dtype=torch.float32)
+        centres = torch.rand((nhalo, 3), generator=gen, device=dev, dtype=torch.float32) * box
         a = (0.3 * D * (memb.double() / 64.0) ** (1.0 / 3.0)).float()
         sig = (0.3 * D * (memb.double() / 64.0) ** (1.0 / 3.0)).float()
         bulk = torch.randn((nhalo, 3), generator=gen, device=dev, dtype=torch.float32) * (1.5 * D / 3 ** 0.5)
@@ -91,7 +102,15 @@ def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_m
         d /= d.norm(dim=1, keepdim=True)
         pos[sel] = centres[hid] + r[:, None] * d
         vel[sel] = bulk[hid] + sig[hid][:, None] * torch.randn((nh_tot, 3), generator=gen, device=dev, dtype=torch.float32)
-    pos -= torch.floor(pos)
-    pos[pos >= 1.0] = 0.0          # fp32 rounding of values just below 1
-    mass = torch.ones(n, device=dev, dtype=torch.float32)
+        del hid, sel, u, r, d
+    pos -= torch.floor(pos / box) * box
+    for j in range(3):
+        col = pos[:, j]
+        col[col >= float(box[j])] = 0.0          # fp32 rounding of values just below the period
+    if slab is not None:
+        rk, world = slab
+        x0, x1 = cx * rk / world, cx * (rk + 1) / world
+        keep = (pos[:, 0] >= x0) & (pos[:, 0] < x1)
+        pos, vel = pos[keep], vel[keep]
+    mass = torch.ones(pos.shape[0], device=dev, dtype=torch.float32)
     return pos.contiguous(), vel.contiguous(), mass

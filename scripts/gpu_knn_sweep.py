@@ -36,4 +36,4 @@ for st in settings:
     i = t.info
     print("ng %d k %d opts %s: kernel %.1f ms -> %.1f Mpart/s flagged %d sum %.9e" % (ng, k, opts, i.last_kernel_ms, n / i.last_kernel_ms / 1e3, i.last_flagged, rho.sum().item()), flush=True)
     for name in opts:
-        set_option(name, 0)
+        set_option(name, -1 if name == "knn_transpose" else 0)

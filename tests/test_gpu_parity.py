@@ -179,10 +179,10 @@ def test_fp32_key_ties_fall_back_to_exact_heap(nb, port):
         np.testing.assert_allclose(t.CalcVelDensity(7, 18), port.veldensity(pos, vel, 7, 18), rtol=RTOL_RHO)
 
 
-@pytest.mark.parametrize("opt", [{"knn_leaf": 16}, {"knn_leaf": 64}, {"knn_exact": 1}, {}])
+@pytest.mark.parametrize("opt", [{"knn_leaf": 16}, {"knn_leaf": 64}, {"knn_exact": 1}, {}, {"knn_transpose": 0}, {"knn_transpose": 32}])
 def test_density_kernel_variants(nb, port, opt):
     """Every configuration of the density kernel gives the oracle's answer: unmerged 16-particle leaves, two-tile leaves, the
-    exact fp64 heap only, and the defaults.  Both storage widths."""
+    exact fp64 heap only, the defaults, tiles always / never screened in the transposed form.  Both storage widths."""
     from nbodylib_b200.synth import clustered_small
     n, k = 30011, 40
     pos, vel, mass = clustered_small(n, seed=77)
@@ -200,7 +200,7 @@ def test_density_kernel_variants(nb, port, opt):
                 np.testing.assert_allclose(t.CalcVelDensity(k, k), port.veldensity(pos, vel, k, k), rtol=RTOL_RHO)
     finally:
         for name in opt:
-            nb.set_option(name, 0)
+            nb.set_option(name, -1 if name == "knn_transpose" else 0)
     with pytest.raises(nb.NbkError):
         nb.set_option("no_such_option", 1)
 
