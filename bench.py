@@ -77,6 +77,30 @@ class ClockSampler:
         return out
 
 
+def shim_e2e(pos, vel, mass, k, period, reps):
+    """KDTree(Particle*) + CalcDensity + ~KDTree on an array of 88-byte reference-layout particles through the C++ shim
+    (nbodylib_b200/libnbk_shimbench.so, built from examples/shim_bench.cxx); the first repetition is a warm-up."""
+    import ctypes as C
+    so = os.path.join(ROOT, "nbodylib_b200", "libnbk_shimbench.so")
+    if not os.path.exists(so):
+        return None
+    L = C.CDLL(so)
+    n = len(pos)
+    sec = np.zeros((reps + 1, 4))
+    rho_sum = C.c_double(0)
+    err = C.create_string_buffer(512)
+    per = np.ascontiguousarray(period, dtype=np.float64)
+    L.nbk_shim_e2e.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_char_p, C.c_int]
+    rc = L.nbk_shim_e2e(pos.ctypes.data, vel.ctypes.data, mass.ctypes.data, n, k, per.ctypes.data, reps + 1, sec.ctypes.data, C.byref(rho_sum), err, 512)
+    if rc != 0:
+        return {"error": err.value.decode()[:300]}
+    t = sec[1:].mean(0)
+    return {"unit": "particles/s", "ms_per_step": float(t[3]) * 1e3, "constructor_ms": float(t[0]) * 1e3, "calc_density_ms": float(t[1]) * 1e3,
+            "destructor_ms": float(t[2]) * 1e3, "particle_bytes": 88, "host_threads": host_cores(), "rho_sum": rho_sum.value,
+            "includes": "NBody::KDTree(Particle*, N, 16, TPHYS, KEPAN, 1000, 0, 0, 0, period) [SetID, strided H2D of the fp64 fields, build, "
+                        "array permuted into tree order], CalcDensity(%d) [rho into the particles], ~KDTree [order restored]" % k}
+
+
 def workload_name(ng, nh):
     return "clustered periodic box %d^3 per GPU (ZA lattice + %d Plummer halos), KDTree bucket=16, CalcDensity(%d): kNN + SPH density" % (ng, nh, K_NN)
 
@@ -279,6 +303,11 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_s, wall = float(tmax[0].item()), float(tmax[1].item())
     clocks = sampler.stop() if sampler else None
+    if world > 1:
+        # one more (untimed) step with device-synchronised section timers of the sharded driver
+        tree.profile = True
+        step()
+        tree.profile = False
     ms_step = dev_s * 1e3 / args.steps
     value = n_total / (dev_s / args.steps)
 
@@ -409,6 +438,7 @@ def main():
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------
     e2e = None
+    e2e_aos = None
     if not args.no_e2e and world > 1:
         # every rank: pinned host arrays -> its GPU -> slab-sharded tree (halo exchange, local build) -> CalcDensity -> rho on the host
         hp, hm = (x.cpu().pin_memory() for x in (pos, mass))
@@ -475,6 +505,10 @@ def main():
         dt = e2e_loop(e2e_build)
         rows["build"]["e2e"] = {"value": n / dt, "unit": "particles/s", "h2d_bytes_per_step": int(hp.nbytes + hv.nbytes + hm.nbytes), "d2h_bytes_per_step": 0,
                                 "ms_per_step": dt * 1e3, "includes": "H2D of pos/vel/mass (fp32, pinned), tree build (nothing is read back: the tree stays on the device)"}
+        # the drop-in path: 88-byte fp64 Particle[] through the header-only C++ shim (examples/shim_bench.cxx)
+        e2e_aos = shim_e2e(hp, hv, hm, K_NN, period, 2)
+        if e2e_aos is not None:
+            e2e_aos["value"] = n / (e2e_aos["ms_per_step"] * 1e-3)
         del hp, hv, hm, out, outg
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only) -------------------------------------------------
@@ -557,10 +591,11 @@ def main():
                          **ncu_facts},
             "timer": "CUDA events around the K steps (barrier + device synchronize on both sides), max over ranks; wall_ms_per_step = host clock around the same region; library_ms_per_step = the library's own CUDA events around each call on its stream",
             "wall_ms_per_step": wall * 1e3 / args.steps, "library_ms_per_step": float(np.mean(call_ms)),
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checked": checked, "rows": rows, "extra": extra,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_aos": e2e_aos, "gpu_launches": launches, "clocks": clocks, "checked": checked, "rows": rows, "extra": extra,
         }
         for r in rows.values():
-            r["roofline"]["peak_source"] = peak_src
+            if "roofline" in r:
+                r["roofline"]["peak_source"] = peak_src
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

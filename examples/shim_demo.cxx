@@ -4,6 +4,7 @@
 //   g++ -O2 -std=c++17 -Inbodylib_b200/shim examples/shim_demo.cxx -Lnbodylib_b200 -lnbk -Wl,-rpath,$PWD/nbodylib_b200 -o shim_demo
 #include <KDTree.h>
 
+#include <chrono>
 #include <cmath>
 #include <algorithm>
 #include <cstdio>
@@ -165,6 +166,60 @@ int main() {
     }
     // destructor restored the input order
     for (Int_t i = 0; i < N; i++) if (parts[i].GetID() != i || parts[i].GetPID() != i) { bad++; break; }
+    // third tree: built from a System (KDTree.cxx:1322-1338: the period comes from the System, all-zero = open box), the
+    // per-particle ball search loop of reference tests/test_kdtree.cxx:325-341 against the batched C-ABI call, growing one group
+    // from a particle (FOFCriterionParticle), and OverWriteInputOrder (the array stays in tree order with fresh ids)
+    {
+        System S(N, parts.data(), Coordinate(1.0, 1.0, 1.0));
+        KDTree tree(S, 16, KDTree::TPHYS, KDTree::KEPAN, 1000);
+        if (tree.GetPeriod(0) != 1.0 || tree.GetNumLeafNodes() <= 0) bad++;
+        const double r2 = 0.004 * 0.004;
+        std::vector<int> cnt_loop(N);
+        auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(guided)
+        for (Int_t i = 0; i < N; i++) cnt_loop[i] = (int)tree.SearchBallPosTagged(i, r2).size();
+        const double t_loop = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::vector<int32_t> q(N), idx;
+        std::vector<int64_t> off((size_t)N + 1);
+        for (Int_t i = 0; i < N; i++) q[i] = i;
+        int64_t tot = 0;
+        t0 = std::chrono::steady_clock::now();
+        nbk_ball_particles(tree.GetHandle(), r2, N, q.data(), off.data(), NULL, NULL, 0, &tot, 0);
+        idx.resize((size_t)std::max<int64_t>(tot, 1));
+        if (nbk_ball_particles(tree.GetHandle(), r2, N, q.data(), off.data(), idx.data(), NULL, (int64_t)idx.size(), &tot, 0) != NBK_OK) bad++;
+        const double t_batch = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        long diff = 0;
+        for (Int_t i = 0; i < N; i++) diff += cnt_loop[i] != (int)(off[(size_t)i + 1] - off[i]);
+        printf("SearchBallPosTagged(i) loop over %d particles: %.3f s; batched nbk_ball_particles: %.3f s (ratio %.2f); %ld rows differ\n", N, t_loop, t_batch,
+               t_loop / t_batch, diff);
+        if (diff) bad++;
+        // grow group 7 from one particle with FOF3d: the same set as the FOF group of that particle
+        const double ll = 0.2 / std::cbrt((double)N);
+        Int_t ng = 0;
+        Int_t* pfof = tree.FOF(ll, ng, 2, 0);
+        Int_t seed = -1;
+        for (Int_t i = 0; i < N && seed < 0; i++) if (pfof[parts[i].GetID()] > 0) seed = i;
+        if (seed >= 0) {
+            Double_t params[10] = {0};
+            params[1] = params[6] = ll * ll;
+            std::vector<Int_t> tags(N, 0);
+            std::vector<Int_tree_t> plen(16, 0);
+            Int_t sz = tree.FOFCriterionParticle(FOF3d, tags.data(), seed, 7, params, NULL, NULL, NULL, NULL, NULL, plen.data());
+            const Int_t gseed = pfof[parts[seed].GetID()];
+            long mism = 0, members = 0;
+            for (Int_t i = 0; i < N; i++) { members += pfof[i] == gseed; mism += (pfof[i] == gseed) != (tags[i] == 7); }
+            printf("FOFCriterionParticle: group of %d, FOF group of the seed %ld, %ld mismatches\n", sz, members, mism);
+            if (mism || sz != members || plen[7] != sz) bad++;
+        } else bad++;
+        delete[] pfof;
+        tree.OverWriteInputOrder();
+    }
+    // OverWriteInputOrder: the destructor left the array in tree order and the ids number that order
+    {
+        bool ids = true, moved = false;
+        for (Int_t i = 0; i < N; i++) { ids = ids && parts[i].GetID() == i; moved = moved || parts[i].GetPID() != i; }
+        if (!ids || !moved) bad++;
+    }
     printf(bad ? "FAILED (%d)\n" : "shim demo ok\n", bad);
     return bad ? 1 : 0;
 }

@@ -386,24 +386,25 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
 
 // ========================================================================= density kernel: heap of packed words
 // The density family needs (a) the exact set of the k nearest, (b) the exact k-th distance and (c) a sum over the set.
-// Per lane (= query) the kernel keeps the k+1 smallest candidates seen so far as 32-bit WORDS in a 4-ary max-heap in shared
+// Per lane (= query) the kernel keeps the k+2 smallest candidates seen so far as 32-bit WORDS in a 4-ary max-heap in shared
 // memory:
-//     word = (fp32 key & ~0xfff) | candidate id,      candidate id = (tile sequence number << 5) | slot in the tile
+//     word = (fp32 key & ~0x1fff) | candidate id,     candidate id = (tile sequence number << 6) | slot in the tile
 // (the warp's tile list maps a sequence number back to a tree index; words order like their keys, so the heap needs no
 // separate index array and the kernel no global scratch).  A tile is screened with ONE fp32 distance and one unsigned
 // comparison per candidate into a bit mask; the set bits are inserted in SIMT-serial rounds.  After the traversal the full
-// keys of the k+1 survivors are recomputed from their indices.
+// keys of the k+2 survivors are recomputed from their indices.
 //
 // Exactness.  Full keys are a = fl32(d2) evaluated with 3 subtractions, 1 multiplication, 2 FMAs on exact fp32
 // coordinates: |a - d2| <= 5.01 * 2^-24 * d2 =: eps * d2 (fp64 storage: a = RN_fp32 of the reference's fp64 d2, eps = 2^-24).
-//   * A candidate screened out (a > edge * (1 + 2^-20), edge = upper edge of the root word's 2^-11-wide bin) or lying in a
+//   * A candidate screened out (a > edge * (1 + 2^-20), edge = upper edge of the root word's 2^-10-wide bin) or lying in a
 //     subtree whose box lower bound reaches that limit is farther, in exact arithmetic, than every word the heap holds then
 //     and later (2^-20 > 2 eps).
 //   * A candidate that reaches a round and is rejected, or a root that is evicted, lies in the root's bin or above; the lane
 //     remembers the smallest such word (`mindrop`).
-//   * Among the k+1 survivors let m1 be the largest full key and m2 the second largest.  If m1 > m2 * (1 + 2^-20) -- and, when
-//     some dropped word shares the final root's bin, if that bin's lower edge exceeds m2 * (1 + 2^-20) as well -- every
-//     dropped candidate and the (k+1)-th itself are farther in exact arithmetic than each of the k kept ones: the k smallest
+//   * Among the k+2 survivors let m1 be the (k+1)-th smallest full key and m2 the k-th.  If m1 > m2 * (1 + 2^-20) -- and, when
+//     some dropped word shares the final root's bin, if that bin's lower edge exceeds m2 * (1 + 2^-20) as well (the root is
+//     the (k+2)-th word, so this fails only when three consecutive keys fall into one 2^-10-wide bin) -- every dropped
+//     candidate and the two extra survivors are farther in exact arithmetic than each of the k kept ones: the k smallest
 //     full keys ARE the k nearest.
 //   * The exact k-th distance is the reference fp64 d2 of the entry with key m2 provided the next smaller key is below
 //     m2 * (1 - 2^-20); the SPH sums use fp64 d2 recomputed from the indices.
@@ -415,8 +416,13 @@ constexpr float AP_TINY = 7.888609052210118e-31f;           // 2^-100: below it 
 constexpr float AP_HUGE = 1.0e37f;                           // launch_knn sends boxes that could exceed it to the exact kernel
 constexpr float AP_WIDEN = 1.00000095367431640625f;          // 1 + 2^-20
 constexpr float AP_NARROW = 0.99999904632568359375f;         // 1 - 2^-20
-constexpr unsigned AP_CIDMASK = 0xfffu;                      // 12 bits: 7 bits tile sequence number, 5 bits slot
-constexpr unsigned AP_KEYMASK = ~AP_CIDMASK;
+// A staged tile is a whole node of the scanned tree level: 32 slots when that level's nodes hold at most 32 particles (always
+// so for 2^m particles), else 40 (the level holds 21..40).  Candidate id: 7 bits tile sequence number + 5 / 6 bits slot.
+template <int TILE> struct ApWord {
+    static constexpr int SLOT_BITS = TILE <= 32 ? 5 : 6;
+    static constexpr unsigned CIDMASK = (1u << (7 + SLOT_BITS)) - 1u;
+    static constexpr unsigned KEYMASK = ~CIDMASK;
+};
 constexpr int AP_MAXTILES = 128;
 constexpr float AP_INF = __builtin_huge_valf();
 
@@ -439,9 +445,9 @@ __device__ __forceinline__ float ap_key(double qx, double qy, double qz, double 
 }
 
 // Leaf tile staged in shared memory.
-template <class S> struct ApTile;
-template <> struct ApTile<float> {
-    static constexpr int TILE_BYTES = 32 * 16;
+template <class S, int AP_TILE> struct ApTile;
+template <int AP_TILE> struct ApTile<float, AP_TILE> {
+    static constexpr int TILE_BYTES = AP_TILE * 16;
     float4* t;
     float qx, qy, qz;
     __device__ __forceinline__ void init(void* mem, double x, double y, double z) {
@@ -451,9 +457,11 @@ template <> struct ApTile<float> {
     __device__ __forceinline__ void load(const Vec4<float>* __restrict__ P, int first, int m, unsigned lane) {
         // slots past the end of the leaf hold NaN: every comparison on them is false, so the scan runs over whole groups of 8
         const float nanf_ = __int_as_float(0x7fc00000);
-        float4 mine = make_float4(nanf_, nanf_, nanf_, 0.f);
+        float4 mine = make_float4(nanf_, nanf_, nanf_, 0.f), more = mine;
         if ((int)lane < m) { Vec4<float> c = P[first + lane]; mine = make_float4(c.x, c.y, c.z, 0.f); }
+        if (AP_TILE > 32 && 32 + (int)lane < m) { Vec4<float> c = P[first + 32 + lane]; more = make_float4(c.x, c.y, c.z, 0.f); }
         t[lane] = mine;
+        if (AP_TILE > 32 && (int)lane < AP_TILE - 32) t[32 + lane] = more;
     }
     static constexpr bool TRANSPOSABLE = true;
     __device__ __forceinline__ float key(int j) const { const float4 c = t[j]; return ap_key(qx, qy, qz, c.x, c.y, c.z); }
@@ -466,8 +474,8 @@ template <> struct ApTile<float> {
     }
     __device__ __forceinline__ bool coincident(int j) const { const float4 c = t[j]; return qx == c.x && qy == c.y && qz == c.z; }
 };
-template <> struct ApTile<double> {
-    static constexpr int TILE_BYTES = 96 * 8;
+template <int AP_TILE> struct ApTile<double, AP_TILE> {
+    static constexpr int TILE_BYTES = 3 * AP_TILE * 8;
     double* t;
     double qx, qy, qz;
     __device__ __forceinline__ void init(void* mem, double x, double y, double z) { t = reinterpret_cast<double*>(mem); qx = x; qy = y; qz = z; }
@@ -475,13 +483,18 @@ template <> struct ApTile<double> {
         const double nan_ = __longlong_as_double(0x7ff8000000000000ll);
         double cx = nan_, cy = nan_, cz = nan_;
         if ((int)lane < m) { Vec4<double> c = P[first + lane]; cx = c.x; cy = c.y; cz = c.z; }
-        t[lane] = cx; t[32 + lane] = cy; t[64 + lane] = cz;
+        t[lane] = cx; t[AP_TILE + lane] = cy; t[2 * AP_TILE + lane] = cz;
+        if (AP_TILE > 32 && (int)lane < AP_TILE - 32) {
+            cx = cy = cz = nan_;
+            if (32 + (int)lane < m) { Vec4<double> c = P[first + 32 + lane]; cx = c.x; cy = c.y; cz = c.z; }
+            t[32 + lane] = cx; t[AP_TILE + 32 + lane] = cy; t[2 * AP_TILE + 32 + lane] = cz;
+        }
     }
     static constexpr bool TRANSPOSABLE = false;
-    __device__ __forceinline__ float key(int j) const { return ap_key(qx, qy, qz, t[j], t[32 + j], t[64 + j]); }
+    __device__ __forceinline__ float key(int j) const { return ap_key(qx, qy, qz, t[j], t[AP_TILE + j], t[2 * AP_TILE + j]); }
     __device__ __forceinline__ float key_of(const Vec4<double>& c) const { return ap_key(qx, qy, qz, c.x, c.y, c.z); }
     __device__ __forceinline__ unsigned key_bits_for(int, int) const { return 0u; }
-    __device__ __forceinline__ bool coincident(int j) const { return qx == t[j] && qy == t[32 + j] && qz == t[64 + j]; }
+    __device__ __forceinline__ bool coincident(int j) const { return qx == t[j] && qy == t[AP_TILE + j] && qz == t[2 * AP_TILE + j]; }
 };
 
 // SPH epilogues over a lane's neighbour list: entry s (0 <= s < cnt) is tree index idx_at(s).  All 32 lanes call it (`on`:
@@ -622,10 +635,11 @@ struct WordHeap4 {
     }
 };
 
-template <class S>
+template <class S, int AP_TILE>
 struct HpVisitor {
+    static constexpr unsigned AP_CIDMASK = ApWord<AP_TILE>::CIDMASK, AP_KEYMASK = ApWord<AP_TILE>::KEYMASK;
     const Vec4<S>* P;
-    ApTile<S> tile;
+    ApTile<S, AP_TILE> tile;
     WordHeap4 hp;
     int* tl;              // shared: the warp's tile list (tile sequence number -> first tree index)
     int nt;               // tiles scanned so far (warp-uniform)
@@ -633,7 +647,7 @@ struct HpVisitor {
     float limf;           // screen / node-test limit: upper edge of the root's bin * (1 + 2^-20); -1: the lane accepts nothing
     unsigned limu;        // the same limit for the unsigned screen test (bits(a) - bits(AP_TINY) < limu); 0: nothing passes
     unsigned mindrop;     // smallest word rejected or evicted in a round once the heap was full
-    int filled, kcap;     // heap slots taken so far (the first k+1 candidates are stored without sifting), k + 1
+    int filled, kcap;     // heap slots taken so far (the first k+2 candidates are stored without sifting), k + 2
     int tr_max;           // tiles needed by at most this many lanes are screened in the transposed form
     bool failed;
     unsigned lane;
@@ -646,31 +660,35 @@ struct HpVisitor {
     }
     __device__ __forceinline__ void fail() { failed = true; limf = -1.f; limu = 0u; }
     __device__ __forceinline__ void leaf(int start, int n, int, unsigned nmask) {
-        for (int base = 0; base < n; base += 32) {
-            const int m = min(32, n - base);
+        for (int base = 0; base < n; base += AP_TILE) {
+            const int m = min(AP_TILE, n - base);
             if (nt >= AP_MAXTILES) { if (limu != 0u) { STAT(6, 1); fail(); } return; }      // tile list full: the whole group goes to the exact kernel
             __syncwarp();
             tile.load(P, start + base, m, lane);
             if (lane == 0) tl[nt] = start + base;
             __syncwarp();
-            const unsigned cid0 = (unsigned)nt << 5;
+            const unsigned cid0 = (unsigned)nt << ApWord<AP_TILE>::SLOT_BITS;
             nt++;
             STAT(0, 1);
             // pass 1: one unsigned comparison per candidate (NaN padding, keys below 2^-100 -- the query itself, coincident
-            // particles, underflow -- and keys above the limit all fail it)
-            unsigned acc = 0u, tiny = 0u;
-            if (ApTile<S>::TRANSPOSABLE && __popc(nmask) <= tr_max) {
-                // few lanes need this tile: lane j takes candidate j and the needing queries are broadcast one at a time, so a
-                // query costs one key per lane instead of 32 (same expression, same bits as the direct form)
+            // particles, underflow -- and keys above the limit all fail it).  acc: slots 0..31, acch: slots 32..39
+            unsigned acc = 0u, acch = 0u, tiny = 0u;
+            if (ApTile<S, AP_TILE>::TRANSPOSABLE && __popc(nmask) <= tr_max) {
+                // few lanes need this tile: lane j takes candidate j (and 32 + j) and the needing queries are broadcast one at a
+                // time, so a query costs one key per lane instead of 32 (same expression, same bits as the direct form)
                 unsigned rem = nmask;
                 while (rem) {
                     const int q = __ffs(rem) - 1;
                     rem &= rem - 1u;
-                    const unsigned u = tile.key_bits_for(q, lane) - TINY_BITS;
                     const unsigned lq = __shfl_sync(0xffffffffu, limu, q);
-                    const unsigned mk = __ballot_sync(0xffffffffu, u < lq);
-                    const unsigned tn = __ballot_sync(0xffffffffu, (int)u < 0);
-                    if ((int)lane == q) { acc = mk; tiny = tn ? 0x80000000u : 0u; }
+                    const unsigned u = tile.key_bits_for(q, lane) - TINY_BITS;
+                    unsigned mk = __ballot_sync(0xffffffffu, u < lq), tn = __ballot_sync(0xffffffffu, (int)u < 0), mkh = 0u;
+                    if (AP_TILE > 32 && m > 32) {
+                        const unsigned u2 = tile.key_bits_for(q, 32 + (lane & 7)) - TINY_BITS;
+                        mkh = __ballot_sync(0xffffffffu, (int)lane < AP_TILE - 32 && u2 < lq);
+                        tn |= __ballot_sync(0xffffffffu, (int)lane < AP_TILE - 32 && (int)u2 < 0);
+                    }
+                    if ((int)lane == q) { acc = mk; acch = mkh; tiny = tn ? 0x80000000u : 0u; }
                 }
             } else {
                 for (int j0 = 0; j0 < m; j0 += 8) {
@@ -684,7 +702,7 @@ struct HpVisitor {
                         tiny |= u;
                         if (u < limu) a8 |= 1u << jj;
                     }
-                    acc |= a8 << j0;
+                    if (j0 < 32) acc |= a8 << j0; else acch = a8;
                 }
             }
             if ((int)tiny < 0 && limu != 0u) {
@@ -694,16 +712,17 @@ struct HpVisitor {
                     const float a = tile.key(j);
                     if (a < AP_TINY && !tile.coincident(j)) fail();
                 }
-                if (failed) acc = 0u;
+                if (failed) { acc = 0u; acch = 0u; }
             }
-            STAT_LANE(3, __popc(acc));
+            STAT_LANE(3, __popc(acc) + __popc(acch));
             // pass 2: SIMT-serial insertion rounds over the set bits.  The first k+1 candidates of a lane fill the heap's slots
             // directly (the bound is still infinite) and are heapified together when the last slot is taken.
-            while (__any_sync(0xffffffffu, acc != 0u)) {
+            while (__any_sync(0xffffffffu, (acc | acch) != 0u)) {
                 STAT(2, 1);
-                if (acc) {
-                    const int j = __ffs(acc) - 1;
-                    acc &= acc - 1u;
+                if (acc | acch) {
+                    int j;
+                    if (acc) { j = __ffs(acc) - 1; acc &= acc - 1u; }
+                    else { j = 31 + __ffs(acch); acch &= acch - 1u; }
                     const unsigned wb = (__float_as_uint(tile.key(j)) & AP_KEYMASK) | (cid0 + (unsigned)j);
                     const float w = __uint_as_float(wb);
                     if (filled < kcap) {
@@ -725,26 +744,28 @@ struct HpVisitor {
     }
 };
 
-static inline int hp_groups(int k) { return (k + 3) / 4; }            // internal nodes of the heap of k+1 words
+static inline int hp_groups(int k) { return (k + 4) / 4; }            // internal nodes of the heap of k+2 words
 static inline size_t hp_warp_bytes(int k, bool want_doubles, int tile_bytes) {
     size_t region = (size_t)(hp_groups(k) + 1) * 512;
     if (want_doubles) region += (size_t)k * 32 * 8;
     return region + tile_bytes + TRAV_STACK * 4 + AP_MAXTILES * 4;
 }
 
-template <class S, bool HALO>
+template <class S, bool HALO, int AP_TILE>
 __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm, int want_doubles, int* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    const int k = prm.k, kcap = k + 1;
+    // the heap keeps k + 2 words: the k nearest, the (k+1)-th that certifies them, and one more so that a candidate dropped
+    // from the root's bin almost never sits next to the k-th (see the certificate below)
+    const int k = prm.k, kcap = k + 2;
     const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
     const size_t heap_bytes = (size_t)(G + 1) * 512;
     const size_t region = heap_bytes + (want_doubles ? (size_t)k * 32 * 8 : 0);
-    const size_t warp_bytes = region + ApTile<S>::TILE_BYTES + TRAV_STACK * 4 + AP_MAXTILES * 4;
+    const size_t warp_bytes = region + ApTile<S, AP_TILE>::TILE_BYTES + TRAV_STACK * 4 + AP_MAXTILES * 4;
     unsigned char* base = smem_raw + w * warp_bytes;
     void* tile_mem = base + region;
-    int* stack = reinterpret_cast<int*>(base + region + ApTile<S>::TILE_BYTES);
+    int* stack = reinterpret_cast<int*>(base + region + ApTile<S, AP_TILE>::TILE_BYTES);
     int* tl = stack + TRAV_STACK;
     unsigned char* kb = base + lane * 16;
 
@@ -765,7 +786,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm
         const QueryBox qb = make_qbox(x0, y0, z0);
 
         // ------------------------------------------------------------------------------------------ select
-        HpVisitor<S> v;
+        constexpr unsigned AP_KEYMASK = ApWord<AP_TILE>::KEYMASK;
+        HpVisitor<S, AP_TILE> v;
         v.P = P; v.lane = lane;
         v.tile.init(tile_mem, x0, y0, z0);
         v.hp.kb = kb; v.hp.G = G;
@@ -793,11 +815,11 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm
         }
         auto idx_at = [kb, tl](int s) -> int {
             const unsigned wd = *reinterpret_cast<const unsigned*>(kb + ((s + 3) >> 2) * 512 + ((s + 3) & 3) * 4);
-            return tl[(wd >> 5) & (AP_MAXTILES - 1)] + (int)(wd & 31u);
+            return tl[(wd >> ApWord<AP_TILE>::SLOT_BITS) & (AP_MAXTILES - 1)] + (int)(wd & ((1u << ApWord<AP_TILE>::SLOT_BITS) - 1u));
         };
-        // full keys of the survivors: the three largest f0 >= f1 >= f2 and the slots of the first two
-        float f0 = -1.f, f1 = -1.f, f2 = -1.f;
-        int t0 = -1, t1 = -1;
+        // full keys of the survivors: the four largest f0 >= f1 >= f2 >= f3 and the slots of the first three
+        float f0 = -1.f, f1 = -1.f, f2 = -1.f, f3 = -1.f;
+        int t0 = -1, t1 = -1, t2 = -1;
         {
             const int nmax = __reduce_max_sync(full, cnt);
             for (int s0 = 0; s0 < nmax; s0 += 4) {
@@ -809,8 +831,9 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm
                     if (s0 + u < cnt) {
                         const float a = v.tile.key_of(c[u]);
                         const int s = s0 + u;
-                        const bool g0_ = a > f0, g1_ = a > f1, g2_ = a > f2;
-                        f2 = g1_ ? f1 : (g2_ ? a : f2);
+                        const bool g0_ = a > f0, g1_ = a > f1, g2_ = a > f2, g3_ = a > f3;
+                        f3 = g2_ ? f2 : (g3_ ? a : f3);
+                        f2 = g1_ ? f1 : (g2_ ? a : f2);  t2 = g1_ ? t1 : (g2_ ? s : t2);
                         f1 = g0_ ? f0 : (g1_ ? a : f1);  t1 = g0_ ? t0 : (g1_ ? s : t1);
                         f0 = g0_ ? a : f0;               t0 = g0_ ? s : t0;
                     }
@@ -818,22 +841,33 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm
             }
         }
         bool flagged = v.failed;
-        const int drop = cnt > k ? 1 : 0;                   // k+1 survivors: the largest is the (k+1)-th neighbour
-        float kth = f0, below = f1;
+        const int drop = cnt > k ? cnt - k : 0;             // survivors beyond the k nearest: 2 when the heap is full
+        float kth = f0, above = AP_INF, below = f1;
         int skth = t0;
-        if (drop) { kth = f1; below = f2; skth = t1; }
+        if (drop == 1) { above = f0; kth = f1; below = f2; skth = t1; }
+        if (drop == 2) { above = f1; kth = f2; below = f3; skth = t2; }
         const int nk = cnt - drop;
         const bool short_of_k = nk < k;                     // fewer than k candidates exist: the reference's heap keeps sentinels
         if (valid && !flagged) {
             const float kth_band = __fmul_ru(kth, AP_WIDEN);
-            if (drop && !(f0 > kth_band)) flagged = true;
-            // a candidate dropped in a round may lie anywhere in the root's bin: the k-th has to stay below that bin
-            if (drop && (v.mindrop & AP_KEYMASK) <= (rootw & AP_KEYMASK) && !(__uint_as_float(rootw & AP_KEYMASK) > kth_band)) flagged = true;
+            // the (k+1)-th full key certifies the set if it lies above the k-th by more than the error band ...
+            if (drop >= 1 && !(above > kth_band)) flagged = true;
+            // ... and so must every dropped candidate: those dropped in a round lie in the root's bin or above, and if one shares
+            // the final root's bin it may lie anywhere in it, so the k-th has to stay below that bin's lower edge
+            if (drop == 2 && (v.mindrop & AP_KEYMASK) <= (rootw & AP_KEYMASK) && !(__uint_as_float(rootw & AP_KEYMASK) > kth_band)) flagged = true;
             if (!short_of_k && nk >= 2 && !(below < __fmul_rd(kth, AP_NARROW))) flagged = true;
         }
-        if (valid && !flagged && drop) {
-            const int last = cnt - 1;
-            if (t0 != last) { *word_at(t0) = *word_at(last); if (skth == last) skth = t0; }
+        if (valid && !flagged && drop >= 1) {
+            // close the slots of the dropped survivors with the last entries
+            int last = cnt - 1;
+            int da = t0, db = drop == 2 ? t1 : -1;           // slots to drop
+            if (db > da) { const int t = da; da = db; db = t; }      // larger slot first
+            if (da != last) { *word_at(da) = *word_at(last); if (skth == last) skth = da; }
+            last--;
+            if (db >= 0) {
+                if (db != last) { *word_at(db) = *word_at(last); if (skth == last) skth = db; }
+                last--;
+            }
         }
         if (valid && flagged) {
             STAT_LANE(4, 1);
@@ -962,7 +996,8 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             }
         }
         const int want_doubles = (a.veldens_k > 0 && a.veldens_k < a.k) ? 1 : 0;
-        const int tile_bytes = t.store_bytes == 4 ? 32 * 16 : 96 * 8;
+        const int tile_slots = (p.bucket <= 32 && (!t.nlo2 || p.bucket2 <= 32)) ? 32 : 40;
+        const int tile_bytes = t.store_bytes == 4 ? tile_slots * 16 : 3 * tile_slots * 8;
         const size_t smem = hp_warp_bytes(a.k, want_doubles, tile_bytes) * KNN_WARPS;
         NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");
         int nsm = 0, per_sm = 0;
@@ -980,8 +1015,13 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
             if (blocks > (ngroups + KNN_WARPS - 1) / KNN_WARPS) blocks = (ngroups + KNN_WARPS - 1) / KNN_WARPS;
             kern<<<(int)blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles, counters.p + 1);
         };
-        if (t.store_bytes == 4) { if (t.nlo2) go(knn_hp_kernel<float, true>); else go(knn_hp_kernel<float, false>); }
-        else { if (t.nlo2) go(knn_hp_kernel<double, true>); else go(knn_hp_kernel<double, false>); }
+        if (tile_slots == 32) {
+            if (t.store_bytes == 4) { if (t.nlo2) go(knn_hp_kernel<float, true, 32>); else go(knn_hp_kernel<float, false, 32>); }
+            else { if (t.nlo2) go(knn_hp_kernel<double, true, 32>); else go(knn_hp_kernel<double, false, 32>); }
+        } else {
+            if (t.store_bytes == 4) { if (t.nlo2) go(knn_hp_kernel<float, true, 40>); else go(knn_hp_kernel<float, false, 40>); }
+            else { if (t.nlo2) go(knn_hp_kernel<double, true, 40>); else go(knn_hp_kernel<double, false, 40>); }
+        }
         NBK_CHECK(cudaGetLastError());
 #ifdef NBK_STATS
         {

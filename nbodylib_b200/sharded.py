@@ -107,6 +107,7 @@ class ShardedTree:
         self._fof = None        # cached local tree over owned + ghosts for the FOF passes
         self.last_info = None
         self.stats = {}
+        self.profile = False    # True: device-synchronised timing of the driver's sections into stats (ms_*)
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def _group_max(self, v):
@@ -198,29 +199,44 @@ class ShardedTree:
         self.stats["h_knn"] = float(self.h_knn)
         self.stats["density_setups"] = self.stats.get("density_setups", 0) + 1
 
+    def _mark(self, key, t0):
+        """profile=True: device-synchronised timing of the driver's own sections (stats[key], ms)"""
+        import time
+        if self.profile:
+            if self.dev.type == "cuda":
+                torch.cuda.synchronize(self.dev)
+            t1 = time.perf_counter()
+            self.stats[key] = self.stats.get(key, 0.0) + (t1 - t0) * 1e3
+            return t1
+        return t0
+
     def CalcDensity(self, Nsmooth=64, out=None, max_widen=6):
         """Global KDTree::CalcDensity(Nsmooth) for this rank's owned particles (indexed like the rank's input)."""
+        import time
+        t = time.perf_counter()
         for attempt in range(max_widen + 1):
             if self._dens is None:
                 self._density_setup(Nsmooth)
+                t = self._mark("ms_setup", t)
             d = self._dens
             self.last_info = self.engine.density(d["tree"], Nsmooth, d["rho"], d["hsm"])
+            t = self._mark("ms_engine", t)
             n = self.n_owned
             if self.world == 1:
                 break
             # does every owned k-ball stay inside owned + halo ?  (h is the same on every rank, so what this rank received
-            # from a neighbour is everything within h of the shared face)
-            x = self.pos[:, 0].to(torch.float64)
-            rk = 2.0 * d["hsm"][:n]
+            # from a neighbour is everything within h of the shared face).  Only particles within 2 h_sm of a face can fail.
             h = d["halo"]["h"]
-            bad = torch.zeros(n, dtype=torch.bool, device=self.dev)
+            x = self.pos[:, 0]
+            rk = 2.0 * d["hsm"][:n]
+            bad = torch.zeros((), dtype=torch.int64, device=self.dev)
             if self.rank > 0:
-                bad |= rk > (x - self.x0) + h
+                bad = bad + (rk > (x - self.x0) + h).sum()
             if self.rank < self.world - 1:
-                bad |= rk > (self.x1 - x) + h
-            nbad = bad.sum().to(torch.int64)
-            dist.all_reduce(nbad, group=self.group)
-            if int(nbad.item()) == 0:
+                bad = bad + (rk > (self.x1 - x) + h).sum()
+            dist.all_reduce(bad, group=self.group)
+            t = self._mark("ms_check", t)
+            if int(bad.item()) == 0:
                 break
             if attempt == max_widen:
                 raise RuntimeError("ShardedTree.CalcDensity: halo still too narrow after %d widenings" % max_widen)
@@ -230,6 +246,7 @@ class ShardedTree:
         nl = d["halo"]["from_l"].shape[0]
         gr = d["rho"][n:]
         back_l, back_r = self._return_to_owners(gr[:nl, None], gr[nl:, None])
+        t = self._mark("ms_return", t)
         rho = d["rho"][:n].clone() if out is None else out
         if out is not None:
             out.copy_(d["rho"][:n])
@@ -237,6 +254,7 @@ class ShardedTree:
             rho.index_add_(0, d["halo"]["send_l"], back_l[:, 0])
         if back_r.numel():
             rho.index_add_(0, d["halo"]["send_r"], back_r[:, 0])
+        t = self._mark("ms_add", t)
         return rho
 
     def close_density(self):

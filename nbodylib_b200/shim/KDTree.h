@@ -11,7 +11,7 @@
  *    CalcDensity, CalcVelDensity, CalcSmoothingScale (new: north star), CalcDensityParticle, CalcVelDensityParticle,
  *    CalcDensityPosition, CalcVelDensityPosition, CalcSmoothLocalValue, CalcSmoothVel, CalcSmoothVelDisp
  *    FindNearestCheck, FindNearestCriterion (Int_t tt | Particle | Coordinate)
- *    FOF, FOFCriterion, FOFCriterionSetBasisForLinks (FOF3d / FOF6d), GetRoot / FindLeafNode (host mirror of the node arrays)
+ *    FOF, FOFCriterion, FOFCriterionSetBasisForLinks, FOFCriterionParticle (FOF3d / FOF6d), GetRoot / FindLeafNode (host mirror of the node arrays)
  *    OverWriteInputOrder, SetResetOrder, ~KDTree (restores the caller's particle order)
  *
  *  Semantics kept from the reference: the caller's Particle array is permuted IN PLACE into tree order and
@@ -26,12 +26,30 @@
 #ifndef NBK_SHIM_KDTREE_H
 #define NBK_SHIM_KDTREE_H
 
-#ifndef NBK_USE_REFERENCE_PARTICLE
-#include "Particle.h"
+#ifdef NBK_USE_REFERENCE_PARTICLE
+// the consumer has the NBodylib headers (src/NBody, src/Math and src/KDTree on the include path AFTER this directory):
+// Particle / System / Coordinate / Matrix, the priority queue and the FOF criteria are the reference's own
+#include <NBody.h>
+#include <NBodyMath.h>
+#include <PriorityQueue.h>
+#include <FOFFunc.h>
+namespace NBody {
+// the reference defines these next to its node classes (KDNode.h:29-35), which this header replaces
+#ifdef LARGETREE
+typedef long int Int_tree_t;
+typedef unsigned long int UInt_tree_t;
+#else
+typedef int Int_tree_t;
+typedef unsigned int UInt_tree_t;
+#endif
+}
+#else
+#include "nbk_standalone_types.h"
 #endif
 #include <algorithm>
 #include <cmath>
 #include <memory>
+#include <new>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -39,6 +57,13 @@
 #include <vector>
 
 #include "../../include/nbk.h"
+
+// the marshalling loops over the caller's particle array run on all host threads when the consumer is built with OpenMP
+#if defined(_OPENMP)
+#define NBK_SHIM_PARALLEL_FOR _Pragma("omp parallel for schedule(static)")
+#else
+#define NBK_SHIM_PARALLEL_FOR
+#endif
 
 namespace NBody {
 
@@ -173,9 +198,9 @@ public:
         (void)Aniso; (void)metric; (void)iBuildInParallel; (void)min_bucket_size;
         if (ScaleSpace) throw std::runtime_error("nbk shim: ScaleSpace has no device implementation");
         if (iKeepInputOrder || Rdistadapt > 0 || AdaptiveMedianFac > 0) throw std::runtime_error("nbk shim: adaptive / keep-order builds have no device implementation");
-        for (Int_t i = 0; i < numparts; i++) bucket[i].SetID(i);                    // KDTree.cxx:1291
         std::vector<Double_t> mass(numparts);
-        for (Int_t i = 0; i < numparts; i++) mass[i] = bucket[i].GetMass();
+        NBK_SHIM_PARALLEL_FOR
+        for (Int_t i = 0; i < numparts; i++) { bucket[i].SetID(i); mass[i] = bucket[i].GetMass(); }      // KDTree.cxx:1291
         nbk_particles np;
         np.pos = bucket[0].GetPosition(); np.pos_stride = (int64_t)sizeof(Particle);
         np.vel = bucket[0].GetVelocity(); np.vel_stride = (int64_t)sizeof(Particle);
@@ -190,8 +215,7 @@ public:
         // bring the caller's array into tree order (the reference does this with in-place quickselect swaps)
         std::vector<int32_t> order(numparts);
         check(nbk_get_order(h, order.data(), 0));
-        std::vector<Particle> tmp(bucket, bucket + numparts);
-        for (Int_t i = 0; i < numparts; i++) bucket[i] = tmp[order[i]];
+        permute([&](Int_t i) { return (Int_t)order[i]; });
     }
     KDTree(System& s, Int_t bucket_size = 16, int TreeType = TPHYS, int KernType = KEPAN, int KernRes = 1000, int SplittingCriterion = 0,
            int Aniso = 0, int ScaleSpace = 0)
@@ -205,8 +229,10 @@ public:
         if (period) delete[] period;
         if (iresetorder && bucket) {
             // reference: std::sort(bucket, bucket+numparts, IDCompareVec); ids are a permutation of 0..N-1 -> O(N) placement
-            std::vector<Particle> tmp(bucket, bucket + numparts);
-            for (Int_t i = 0; i < numparts; i++) bucket[tmp[i].GetID()] = tmp[i];
+            std::vector<Int_t> src(numparts);
+            NBK_SHIM_PARALLEL_FOR
+            for (Int_t i = 0; i < numparts; i++) src[bucket[i].GetID()] = i;
+            permute([&](Int_t i) { return src[i]; });
         }
     }
 
@@ -226,7 +252,10 @@ public:
         std::vector<double> d2(Nsearch);
         std::vector<int32_t> n32(Nsearch);
         double xx[3] = {(double)x[0], (double)x[1], (double)x[2]};
-        check(nbk_knn_points(h, (int)Nsearch, 1, xx, n32.data(), d2.data(), 0));
+        {
+            std::lock_guard<std::mutex> g(dev_mutex);
+            check(nbk_knn_points(h, (int)Nsearch, 1, xx, n32.data(), d2.data(), 0));
+        }
         for (Int_t j = 0; j < Nsearch; j++) { nn[j] = n32[j]; dist2[j] = d2[j]; }
     }
     void FindNearest(Double_t* x, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { FindNearestPos(x, nn, dist2, Nsearch); }
@@ -267,13 +296,7 @@ public:
         return (Int_t)v.size();
     }
     Int_t SearchBallPosTagged(Coordinate x, Double_t fdist2, Int_t* tagged) { return SearchBallPosTagged(x.GetCoord(), fdist2, tagged); }
-    std::vector<Int_t> SearchBallPosTagged(Int_t tt, Double_t fdist2) {
-        int32_t q = (int32_t)tt;
-        std::vector<int32_t> idx;
-        csr_row([&](int64_t* off, int32_t* ix, double* d2, int64_t cap, int64_t* tot, int fl) {
-            return nbk_ball_particles(h, (double)fdist2, 1, &q, off, ix, d2, cap, tot, fl); }, 0, idx, NULL);
-        return std::vector<Int_t>(idx.begin(), idx.end());
-    }
+    std::vector<Int_t> SearchBallPosTagged(Int_t tt, Double_t fdist2) { return ball_cached(tt, (double)fdist2, -1, NULL); }
     std::vector<Int_t> SearchBallPosTagged(Double_t* x, Double_t fdist2) {
         double xx[3] = {(double)x[0], (double)x[1], (double)x[2]};
         std::vector<int32_t> idx;
@@ -308,13 +331,7 @@ public:
 
     // ---- criterion search (KDFindNearest.cxx:590-603, 660-706; FOF3d / FOF6d) ----------------------------------
     std::vector<Int_t> SearchCriterionTagged(Int_t tt, FOFcompfunc cmp, Double_t* params) {
-        const int crit = crit_code(cmp, "SearchCriterionTagged");
-        double pr[16]; for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
-        int32_t q = (int32_t)tt;
-        std::vector<int32_t> idx;
-        csr_row([&](int64_t* off, int32_t* ix, double* d2, int64_t cap, int64_t* tot, int fl) {
-            return nbk_search_criterion_particles(h, crit, pr, 1, &q, off, ix, d2, cap, tot, fl); }, 0, idx, NULL);
-        return std::vector<Int_t>(idx.begin(), idx.end());
+        return ball_cached(tt, 0.0, crit_code(cmp, "SearchCriterionTagged"), params);
     }
     std::vector<Int_t> SearchCriterionTagged(Particle& p, FOFcompfunc cmp, Double_t* params) {
         const int crit = crit_code(cmp, "SearchCriterionTagged");
@@ -367,11 +384,13 @@ public:
     void CalcDensity(Int_t Nsmooth = 64) {
         std::vector<double> rho(numparts);
         check(nbk_calc_density(h, (int)Nsmooth, rho.data(), NULL, NBK_TREE_ORDER));
+        NBK_SHIM_PARALLEL_FOR
         for (Int_t i = 0; i < numparts; i++) bucket[i].SetDensity(rho[i]);
     }
     void CalcVelDensity(Int_t Nsmooth = 64, Int_t Nsearch = 64) {
         std::vector<double> rho(numparts);
         check(nbk_calc_veldensity(h, (int)Nsmooth, (int)Nsearch, rho.data(), NBK_TREE_ORDER));
+        NBK_SHIM_PARALLEL_FOR
         for (Int_t i = 0; i < numparts; i++) bucket[i].SetDensity(rho[i]);
     }
     /// hi = 0.5*sqrt(d2 of the Nsmooth-th neighbour) for every particle, indexed by ID (new[]: caller delete[]s)
@@ -500,6 +519,48 @@ public:
         });
     }
 
+    /// KDFOF.cxx:686-734 FOFCriterionParticle: grows group iGroup from particle `target` (a tree index).  pfof is the caller's
+    /// group array indexed by ID; every particle reachable from the target through chains of cmp-linked particles whose pfof is
+    /// >= 0 and != iGroup joins the group (members of other groups are taken over, KDLeafNode.cxx:603-616; particles with a
+    /// negative tag and the group's existing members are not walked through).  Returns pLen[iGroup] = the group's size.  The
+    /// scratch arrays of the reference's breadth-first search (pGroupHead, Fifo) are not needed; pHead / pNext / pTail (tree
+    /// index space, optional) are rebuilt for the group: the target first, then its members in ascending tree index.
+    /// Device work: one component search over the whole tree (nbk_fof_roots) per call.
+    Int_t FOFCriterionParticle(FOFcompfunc cmp, Int_t* pfof, Int_t target, Int_t iGroup, Double_t* params, Int_tree_t* pGroupHead = NULL,
+                               Int_tree_t* Fifo = NULL, Int_tree_t* pHead = NULL, Int_tree_t* pTail = NULL, Int_tree_t* pNext = NULL, Int_tree_t* pLen = NULL) {
+        (void)Fifo;
+        const int crit = crit_code(cmp, "FOFCriterionParticle");
+        if (target < 0 || target >= numparts) throw std::runtime_error("nbk shim: particle index out of range");
+        double pr[16]; for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        const Int_t tid = bucket[target].GetID();
+        std::vector<int32_t> excl((size_t)numparts), root((size_t)numparts);
+        NBK_SHIM_PARALLEL_FOR
+        for (Int_t i = 0; i < numparts; i++) excl[(size_t)i] = (pfof[i] < 0 || (pfof[i] == iGroup && i != tid)) ? 1 : 0;      // by ID
+        {
+            std::lock_guard<std::mutex> g(dev_mutex);
+            check(nbk_fof_roots(h, crit, 0.0, pr, excl.data(), root.data(), 0));
+        }
+        const int32_t rt = root[(size_t)tid];
+        Int_t len = 0;
+        for (Int_t i = 0; i < numparts; i++) { if (root[(size_t)i] == rt && rt >= 0) pfof[i] = iGroup; if (pfof[i] == iGroup) len++; }
+        if (pGroupHead) pGroupHead[iGroup] = target;
+        if (pLen) pLen[iGroup] = len;
+        if (pHead || pNext || pTail) {
+            Int_t prev = target, tail = target;
+            for (Int_t i = 0; i < numparts; i++) if (i != target && pfof[bucket[i].GetID()] == iGroup) tail = i;
+            for (Int_t i = 0; i < numparts; i++) {
+                const bool in = pfof[bucket[i].GetID()] == iGroup;
+                if (pHead) pHead[i] = in ? target : i;
+                if (pTail) pTail[i] = in ? tail : i;
+                if (pNext) pNext[i] = -1;
+            }
+            if (pNext) for (Int_t i = 0; i < numparts; i++) if (i != target && pfof[bucket[i].GetID()] == iGroup) { pNext[prev] = i; prev = i; }
+        }
+        return len;
+    }
+    /// forget the cached FOFcheckfunc values (call after changing the particle fields the function reads)
+    void InvalidateCheckCache() { std::lock_guard<std::mutex> g(chk_mutex); chk_vals.clear(); chk_fn = nullptr; }
+
     // ---- ordering (KDTree.cxx:1358-1362) -----------------------------------------------------------------------
     void OverWriteInputOrder() {
         iresetorder = false;
@@ -508,6 +569,19 @@ public:
     void SetResetOrder(bool a) { iresetorder = a; }
 
 private:
+    /// bucket[i] <- bucket[src(i)] for a permutation src, moving every particle twice (into a scratch array and back); both
+    /// passes are parallel and the scratch array is raw storage: no element is default-constructed or copied
+    /// (KDTree.cxx:328-370 does it with in-place quickselect swaps; ~KDTree with std::sort, :1347)
+    template <class F>
+    void permute(F src) {
+        if (numparts <= 0) return;
+        Particle* tmp = static_cast<Particle*>(::operator new(sizeof(Particle) * (size_t)numparts));
+        NBK_SHIM_PARALLEL_FOR
+        for (Int_t i = 0; i < numparts; i++) new (tmp + i) Particle(std::move(bucket[src(i)]));
+        NBK_SHIM_PARALLEL_FOR
+        for (Int_t i = 0; i < numparts; i++) { bucket[i] = std::move(tmp[i]); tmp[i].~Particle(); }
+        ::operator delete(tmp);
+    }
     void require_pos_tree(const char* who) {
         if (info.treetype != TPHYS && info.treetype != TPHS) throw std::runtime_error(std::string("nbk shim: ") + who + " has a device implementation on position trees only");
     }
@@ -520,24 +594,94 @@ private:
         if (i < size - 1) return K[i] + (K[i + 1] - K[i]) * (r - delta * i) / delta;
         return K[i];
     }
-    /// two-pass CSR protocol for a single query row: count, allocate, fill
+    /// CSR protocol for a single query row in ONE device round trip: the call is made with the capacity the thread's last
+    /// row needed (at least 256 entries); only when the row is larger does NBK_ERR_CAPACITY report the size for a second call
     template <class F>
     void csr_row(F call, int flags, std::vector<int32_t>& idx, std::vector<double>* d2) {
+        static thread_local size_t hint = 256;
         int64_t off[2], tot = 0;
         std::lock_guard<std::mutex> g(dev_mutex);
-        check(call(off, (int32_t*)NULL, (double*)NULL, (int64_t)0, &tot, flags));
-        idx.resize((size_t)std::max<int64_t>(tot, 1));
-        if (d2) d2->resize(idx.size());
-        check(call(off, idx.data(), d2 ? d2->data() : (double*)NULL, (int64_t)idx.size(), &tot, flags));
+        idx.resize(hint);
+        if (d2) d2->resize(hint);
+        int rc = call(off, idx.data(), d2 ? d2->data() : (double*)NULL, (int64_t)idx.size(), &tot, flags);
+        if (rc == NBK_ERR_CAPACITY) {
+            hint = (size_t)tot + (size_t)tot / 4 + 16;
+            idx.resize(hint);
+            if (d2) d2->resize(hint);
+            rc = call(off, idx.data(), d2 ? d2->data() : (double*)NULL, (int64_t)idx.size(), &tot, flags);
+        }
+        check(rc);
         idx.resize((size_t)tot);
         if (d2) d2->resize((size_t)tot);
+    }
+    /// Per-thread block cache behind SearchBallPosTagged(Int_t tt) / SearchCriterionTagged(Int_t tt): like knn_cached, the
+    /// first call of a thread answers the whole block of consecutive tree indices around tt with one batched device query
+    /// (CSR), the following calls are copies from host memory (reference callers loop over every particle:
+    /// tests/test_kdtree.cxx:325-341).  crit < 0: ball of radius^2 r2; otherwise NBK_FOF3D / NBK_FOF6D with params.
+    struct BallBlock {
+        unsigned long long serial = 0; Int_t b0 = 0, b1 = 0; int crit = -2; double r2 = -1, params[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        std::vector<int64_t> off; std::vector<int32_t> idx;
+    };
+    static BallBlock& tls_ball() { static thread_local BallBlock b; return b; }
+    std::vector<Int_t> ball_cached(Int_t tt, double r2, int crit, const Double_t* params) {
+        if (tt < 0 || tt >= numparts) throw std::runtime_error("nbk shim: particle index out of range");
+        BallBlock& c = tls_ball();
+        double pr[16] = {0};
+        if (crit >= 0 && params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        bool same = c.serial == serial && c.crit == crit && c.r2 == r2 && tt >= c.b0 && tt < c.b1;
+        for (int j = 0; same && j < 8; j++) same = c.params[j] == pr[j];
+        if (!same) {
+            const Int_t B = 4096;
+            const Int_t b0 = (tt / B) * B, b1 = std::min(numparts, b0 + B);
+            const int64_t m = b1 - b0;
+            std::vector<int32_t> q((size_t)m);
+            for (int64_t i = 0; i < m; i++) q[(size_t)i] = (int32_t)(b0 + i);
+            c.off.resize((size_t)m + 1);
+            if (c.idx.size() < (size_t)64 * (size_t)m) c.idx.resize((size_t)64 * (size_t)m);
+            int64_t tot = 0;
+            std::lock_guard<std::mutex> g(dev_mutex);
+            auto call = [&]() {
+                return crit < 0 ? nbk_ball_particles(h, r2, m, q.data(), c.off.data(), c.idx.data(), NULL, (int64_t)c.idx.size(), &tot, 0)
+                                : nbk_search_criterion_particles(h, crit, pr, m, q.data(), c.off.data(), c.idx.data(), NULL, (int64_t)c.idx.size(), &tot, 0);
+            };
+            int rc = call();
+            if (rc == NBK_ERR_CAPACITY) { c.idx.resize((size_t)tot + (size_t)tot / 4 + 16); rc = call(); }
+            c.serial = 0;                       // the block is invalid until the call has succeeded
+            check(rc);
+            c.serial = serial; c.b0 = b0; c.b1 = b1; c.crit = crit; c.r2 = r2;
+            for (int j = 0; j < 8; j++) c.params[j] = pr[j];
+        }
+        const int64_t r0 = c.off[(size_t)(tt - c.b0)], r1 = c.off[(size_t)(tt - c.b0) + 1];
+        return std::vector<Int_t>(c.idx.begin() + r0, c.idx.begin() + r1);
+    }
+    /// FOFcheckfunc values of every particle in tree order, computed once per (function, params) and kept: the caller's
+    /// function runs on the host, the device receives the values.  InvalidateCheckCache() after changing the particle fields
+    /// the function reads.
+    std::mutex chk_mutex;
+    std::vector<int32_t> chk_vals;
+    FOFcheckfunc chk_fn = nullptr;
+    double chk_params[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int32_t* check_values(FOFcheckfunc fn, Double_t* params) {
+        double pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        std::lock_guard<std::mutex> g(chk_mutex);
+        bool same = chk_fn == fn && !chk_vals.empty();
+        for (int j = 0; same && j < 8; j++) same = chk_params[j] == pr[j];
+        if (!same) {
+            chk_vals.resize((size_t)numparts);
+            NBK_SHIM_PARALLEL_FOR
+            for (Int_t i = 0; i < numparts; i++) chk_vals[(size_t)i] = fn(bucket[i], params);
+            chk_fn = fn;
+            for (int j = 0; j < 8; j++) chk_params[j] = pr[j];
+        }
+        return chk_vals.data();
     }
     /// crit == -2: plain search; otherwise filtered (crit -1: check function only, >= 0: NBK_FOF3D / NBK_FOF6D)
     void knn_cached(Int_t tt, Int_t* nn, Double_t* dist2, Int_t k, int flags, int crit = -2, FOFcheckfunc checkfn = nullptr, Double_t* params = NULL) {
         if (tt < 0 || tt >= numparts) throw std::runtime_error("nbk shim: particle index out of range");
         KnnBlock& c = tls_block();
         double pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (crit >= 0 && params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
+        if (crit != -2 && params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];      // criterion AND check forms: compared by value
         bool same = c.serial == serial && c.k == k && c.flags == flags && c.crit == crit && c.checkfn == checkfn && tt >= c.b0 && tt < c.b1;
         for (int j = 0; same && j < 8; j++) same = c.params[j] == pr[j];
         if (!same) {
@@ -549,10 +693,9 @@ private:
                 std::lock_guard<std::mutex> g(dev_mutex);
                 check(nbk_knn_particles(h, (int)k, b0, b1, c.nn.data(), c.d2.data(), flags));
             } else {
-                std::vector<int32_t> chk;
-                if (checkfn) { chk.resize(numparts); for (Int_t i = 0; i < numparts; i++) chk[i] = checkfn(bucket[i], params); }   // tree order
+                const int32_t* chk = checkfn ? check_values(checkfn, params) : NULL;                     // tree order, once per (function, params)
                 std::lock_guard<std::mutex> g(dev_mutex);
-                check(nbk_knn_filtered_particles(h, (int)k, b0, b1, crit, pr, checkfn ? chk.data() : NULL, c.nn.data(), c.d2.data(), flags | NBK_TREE_ORDER));
+                check(nbk_knn_filtered_particles(h, (int)k, b0, b1, crit, pr, chk, c.nn.data(), c.d2.data(), flags | NBK_TREE_ORDER));
             }
             c.serial = serial; c.b0 = b0; c.b1 = b1; c.k = k; c.flags = flags; c.crit = crit; c.checkfn = checkfn;
             for (int j = 0; j < 8; j++) c.params[j] = pr[j];
@@ -564,12 +707,12 @@ private:
         double xx[3] = {(double)x[0], (double)x[1], (double)x[2]}, vv[3] = {0, 0, 0}, pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (v) for (int j = 0; j < 3; j++) vv[j] = (double)v[j];
         if (crit >= 0 && params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];
-        std::vector<int32_t> chk, n32(k);
+        std::vector<int32_t> n32(k);
         std::vector<double> d2(k);
-        if (checkfn) { chk.resize(numparts); for (Int_t i = 0; i < numparts; i++) chk[i] = checkfn(bucket[i], params); }
+        const int32_t* chk = checkfn ? check_values(checkfn, params) : NULL;
         {
             std::lock_guard<std::mutex> g(dev_mutex);
-            check(nbk_knn_filtered_points(h, (int)k, 1, xx, v ? vv : NULL, crit, pr, checkfn ? chk.data() : NULL, n32.data(), d2.data(),
+            check(nbk_knn_filtered_points(h, (int)k, 1, xx, v ? vv : NULL, crit, pr, chk, n32.data(), d2.data(),
                                           NBK_TREE_ORDER | (period ? NBK_KNN_TREE_FORM : 0)));
         }
         for (Int_t j = 0; j < k; j++) { nn[j] = n32[j]; dist2[j] = d2[j]; }
@@ -577,7 +720,10 @@ private:
     void knn_range(Int_t q0, Int_t q1, Int_t* nn, Double_t* dist2, Int_t k, int flags) {
         std::vector<int32_t> n32((size_t)(q1 - q0) * k);
         std::vector<double> d2((size_t)(q1 - q0) * k);
-        check(nbk_knn_particles(h, (int)k, q0, q1, n32.data(), d2.data(), flags));
+        {
+            std::lock_guard<std::mutex> g(dev_mutex);
+            check(nbk_knn_particles(h, (int)k, q0, q1, n32.data(), d2.data(), flags));
+        }
         for (size_t j = 0; j < n32.size(); j++) { nn[j] = n32[j]; dist2[j] = d2[j]; }
     }
     void knn_all(Int_t** nn, Double_t** dist2, Int_t k, int flags) {
@@ -586,7 +732,10 @@ private:
         std::vector<double> d2(n32.size());
         for (Int_t q0 = 0; q0 < numparts; q0 += chunk) {
             Int_t q1 = std::min(numparts, q0 + chunk);
-            check(nbk_knn_particles(h, (int)k, q0, q1, n32.data(), d2.data(), flags));
+            {
+                std::lock_guard<std::mutex> g(dev_mutex);
+                check(nbk_knn_particles(h, (int)k, q0, q1, n32.data(), d2.data(), flags));
+            }
             for (Int_t i = q0; i < q1; i++)
                 for (Int_t j = 0; j < k; j++) { nn[i][j] = n32[(size_t)(i - q0) * k + j]; dist2[i][j] = d2[(size_t)(i - q0) * k + j]; }
         }

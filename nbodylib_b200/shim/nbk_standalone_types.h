@@ -1,9 +1,11 @@
-/*! \file Particle.h (nbodylib_b200 shim)
+/*! \file nbk_standalone_types.h (nbodylib_b200 shim)
  *  Minimal stand-in for the reference's NBody::Particle / NBody::Coordinate / NBody::System (reference
  *  src/NBody/Particle.h:264-354, accessors :452-532; src/Math/Coordinate.h:44-70; src/NBody/System.h:59-81) for
  *  programs that do not have the NBodylib headers.  Same default-build field layout (sizeof == 88: mass@0,
  *  position@8, velocity@32, pid@56, id@60, type@64, rho@72, phi@80) and the accessors the tree uses.
- *  A consumer that has the real headers defines NBK_USE_REFERENCE_PARTICLE and includes them first.
+ *  A consumer that has the real headers defines NBK_USE_REFERENCE_PARTICLE: shim/KDTree.h then includes the reference's
+ *  <NBody.h>, <NBodyMath.h>, <PriorityQueue.h> and <FOFFunc.h> instead of this file.  (The file is deliberately NOT called
+ *  Particle.h: with the shim directory first on the include path it must never shadow the reference's <Particle.h>.)
  */
 #ifndef NBK_SHIM_PARTICLE_H
 #define NBK_SHIM_PARTICLE_H

@@ -58,6 +58,21 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+HARNESS = os.path.join(HERE, "_ref", "test_kdtree_shim")
+
+
+def build_harness(reference="/root/reference"):
+    """The reference's own test program (src/tests/test_kdtree.cxx, unchanged) compiled against nbodylib_b200/shim/KDTree.h with
+    the reference's NBody / Math headers and linked with libnbk.so (oracle/Makefile target `harness`).  No-op without the
+    reference sources; returns the binary's path or None."""
+    if os.path.isdir(os.path.join(reference, "src", "tests")):
+        deps = [os.path.join(HERE, "harness_main.cxx"), os.path.join(HERE, "..", "nbodylib_b200", "shim", "KDTree.h"),
+                os.path.join(HERE, "..", "nbodylib_b200", "libnbk.so")]
+        if not os.path.exists(HARNESS) or any(os.path.getmtime(HARNESS) < os.path.getmtime(d) for d in deps if os.path.exists(d)):
+            subprocess.check_call(["make", "-B", "-C", HERE, "harness", "REF=" + reference], stdout=subprocess.DEVNULL)
+    return HARNESS if os.path.exists(HARNESS) else None
+
+
 class Port:
     """Brute-force restatement; all indices are particle IDs (input order)."""
 

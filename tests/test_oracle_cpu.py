@@ -126,6 +126,18 @@ def test_full_host_density_loop_equals_library_calcdensity():
     R.close()
 
 
+def test_reference_harness_compiles_unchanged_against_the_shim(built):
+    """Where the reference sources are present: src/tests/test_kdtree.cxx compiles unchanged with the reference's NBody / Math
+    headers and the shim's KDTree.h first on the include path (NBK_USE_REFERENCE_PARTICLE), and links against libnbk.so.
+    (It needs a GPU to run: tests/test_gpu_parity.py::test_reference_harness_runs_unchanged_on_the_shim.)"""
+    import os
+    from oracle import pyoracle
+    if not os.path.isdir("/root/reference/src/tests"):
+        pytest.skip("reference sources not present")
+    exe = pyoracle.build_harness()
+    assert exe is not None and os.access(exe, os.X_OK)
+
+
 def test_reference_tree_shape_known_answer():
     """N=1e6, b=16 -> 131071 nodes / 65536 leaves: the closed-form shape used by the device build."""
     def shape(n, b):
