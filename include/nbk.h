@@ -138,7 +138,8 @@ int nbk_knn_filtered_points(nbk_tree* t, int k, int64_t m, const double* x, cons
  * for a batch: CSR rows; offsets[m+1]; idx capacity cap; *total = entries required.
  * Rows hold every particle with d2 < fdist2 (strict; minimum image over the reference's reflections
  * when periodic).  Particle form (qidx = tree indices): the query itself is excluded when non periodic,
- * included when periodic (quirk Q5).  Rows are sorted ascending.
+ * included when periodic (quirk Q5).  Rows are sorted ascending (periodic trees: ascending within each of the up to 8 image
+ * passes, which are concatenated).  A batch whose rows hold 2^32 entries or more in all is refused (NBK_ERR_ARG): split it.
  * d2 (optional, cap entries, same layout as idx): squared position distance of every entry -- what the dense forms
  * KDTree::SearchBallPos(tt / x, fdist2, imark, nn, dist2) (KDFindNearest.cxx:567-587) write into dist2[ID]; the shim
  * builds the dense nn[] / dist2[] arrays from a row.  idx == NULL (or cap == 0): count pass only. */

@@ -36,6 +36,13 @@ struct DeviceGuard {
     ~DeviceGuard() { cur_stream() = prev_stream; if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// device + stream of a tree for the duration of an entry point, and the tree's lock (see nbk_tree::mtx)
+struct TreeGuard {
+    std::unique_lock<std::mutex> lock;
+    DeviceGuard dev;
+    explicit TreeGuard(const nbk_tree* t) : lock(t->mtx), dev(t->device, t->stream) {}
+};
+
 // ---- staging kernels -----------------------------------------------------------------------------
 // raw strided reals (device visible) -> packed doubles [n][3]
 template <class R>
@@ -188,7 +195,7 @@ void build_kernel_table(nbk_tree& t) {
     t.h_kernel.resize(t.kernres);
     double delta = 2.0 / (double)(t.kernres - 1);
     for (int i = 0; i < t.kernres; i++) t.h_kernel[i] = kn * kern_w(type, i * delta, 1.0);
-    NBK_CHECK(cudaMallocAsync((void**)&t.d_kernel, sizeof(double) * t.kernres, t.stream));
+    NBK_CHECK(nbk_malloc_async((void**)&t.d_kernel, sizeof(double) * t.kernres, t.stream));
     NBK_CHECK(cudaStreamSynchronize(t.stream));
     NBK_CHECK(cudaMemcpy(t.d_kernel, t.h_kernel.data(), sizeof(double) * t.kernres, cudaMemcpyHostToDevice));
 }
@@ -257,12 +264,6 @@ int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int 
     if (period) for (int d = 0; d < 3; d++) t->period[d] = period[d];
     NBK_CHECK(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
     cur_stream() = t->stream;
-    {
-        cudaMemPool_t pool;
-        NBK_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t thr = UINT64_MAX;
-        NBK_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    }
     NBK_CHECK(cudaEventCreate(&t->ev0)); NBK_CHECK(cudaEventCreate(&t->ev1));
     NBK_CHECK(cudaEventCreate(&t->ev2)); NBK_CHECK(cudaEventCreate(&t->ev3));
     cudaStream_t st = t->stream;
@@ -362,15 +363,8 @@ int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int 
 int nbk_destroy(nbk_tree* t) {
     NBK_API_BEGIN
     if (!t) return NBK_OK;
-    DeviceGuard guard(t->device, t->stream);
-    cudaStreamSynchronize(t->stream);
-    void* bufs[] = {t->prim, t->sec, t->mass, t->order, t->nlo, t->nhi, t->cutdim, t->d_kernel, t->nlo2, t->nhi2};
-    for (void* b : bufs) if (b) cudaFreeAsync(b, t->stream);
-    cudaStreamSynchronize(t->stream);
-
-    cudaEventDestroy(t->ev0); cudaEventDestroy(t->ev1); cudaEventDestroy(t->ev2); cudaEventDestroy(t->ev3);
-    cudaStreamDestroy(t->stream);
-    delete t;
+    { std::lock_guard<std::mutex> wait_for_running_calls(t->mtx); }
+    delete t;                                  // ~nbk_tree frees the buffers, events and the stream
     NBK_API_END
 }
 
@@ -393,7 +387,7 @@ int nbk_attach_halo(nbk_tree* t, nbk_tree* halo) {
                     t->bucket == halo->bucket && (t->sec == nullptr) == (halo->sec == nullptr),
                 NBK_ERR_ARG, "nbk_attach_halo: the two trees must be TPHYS trees on one device with the same storage width, bucket size and columns");
     NBK_REQUIRE(t->n + halo->n < ((int64_t)1 << 31) - 64, NBK_ERR_ARG, "nbk_attach_halo: too many particles");
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     cudaStream_t st = t->stream;
     NBK_CHECK(cudaStreamSynchronize(halo->stream));
     const int64_t n1 = t->n, n2 = halo->n, n = n1 + n2;
@@ -423,8 +417,9 @@ int nbk_attach_halo(nbk_tree* t, nbk_tree* halo) {
     t->knn_fp32_ok = -1;
     t->n_main = n1; t->n = n;
     t->device_bytes += halo->device_bytes;
-    cudaEventDestroy(halo->ev0); cudaEventDestroy(halo->ev1); cudaEventDestroy(halo->ev2); cudaEventDestroy(halo->ev3);
-    cudaStreamDestroy(halo->stream);
+    // the halo handle is consumed: its particle arrays are freed above, its node arrays now belong to t
+    halo->prim = halo->sec = nullptr; halo->mass = nullptr; halo->order = nullptr; halo->cutdim = nullptr; halo->d_kernel = nullptr;
+    halo->nlo = nullptr; halo->nhi = nullptr;
     delete halo;
     NBK_API_END
 }
@@ -447,7 +442,7 @@ int nbk_get_info(const nbk_tree* t, nbk_info* info) {
 int nbk_get_order(const nbk_tree* t, int32_t* ids, int flags) {
     NBK_API_BEGIN
     NBK_REQUIRE(t && ids, NBK_ERR_ARG, "nbk_get_order: null argument");
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     NBK_CHECK(cudaMemcpyAsync(ids, t->order, sizeof(int32_t) * t->n, (flags & NBK_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
     NBK_CHECK(cudaStreamSynchronize(t->stream));
     NBK_API_END
@@ -465,7 +460,7 @@ int nbk_get_nodes(const nbk_tree* t, int64_t* num_slots, int32_t* start, int32_t
     NBK_REQUIRE(t && num_slots, NBK_ERR_ARG, "nbk_get_nodes: null argument");
     *num_slots = t->nslots;
     if (!start && !end && !cutdim && !bounds) return NBK_OK;
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     std::vector<NodeLo> lo(t->nslots);
     std::vector<NodeHi> hi(t->nslots);
     std::vector<int8_t> cd(t->nslots);
@@ -500,7 +495,7 @@ int nbk_knn_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, d
     require_no_halo(t, "nbk_knn_particles");
     NBK_REQUIRE(q0 >= 0 && q1 <= t->n && q0 <= q1, NBK_ERR_ARG, "nbk_knn_particles: bad query range");
     NBK_REQUIRE(k >= 1, NBK_ERR_ARG, "nbk_knn_particles: k must be >= 1");
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const int64_t rows = q1 - q0;
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<int32_t> dnn;
@@ -533,7 +528,7 @@ int nbk_knn_points(nbk_tree* t, int k, int64_t m, const double* x, int32_t* nn, 
     require_no_halo(t, "nbk_knn_points");
     NBK_REQUIRE(k >= 1 && m >= 0, NBK_ERR_ARG, "nbk_knn_points: bad k or m");
     if (m == 0) return NBK_OK;
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<double> dx, dd2;
     DevBuf<int32_t> dnn;
@@ -569,7 +564,7 @@ static void knn_filtered_call(nbk_tree* t, int k, int64_t q0, int64_t q1, int64_
     NBK_REQUIRE(t->treetype == NBK_TPHYS, NBK_ERR_UNSUPPORTED, "FindNearestCheck / FindNearestCriterion need a physical tree");
     NBK_REQUIRE(k >= 1, NBK_ERR_ARG, "filtered kNN: k must be >= 1");
     NBK_REQUIRE(criterion >= 0 || check, NBK_ERR_ARG, "filtered kNN: neither a criterion nor check values given");
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const bool dev = flags & NBK_DEVICE_PTRS;
     const int64_t n = t->n;
     KnnArgs a;
@@ -686,7 +681,7 @@ static void smooth_call(nbk_tree* t, int k, int veldens_k, double* rho, double* 
     require_knn_tree(t);
     NBK_REQUIRE(t->treetype == NBK_TPHYS || veldens_k == 0, NBK_ERR_UNSUPPORTED, "CalcVelDensity needs a physical tree");
     NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const int64_t n = t->n;
     DevBuf<double> drho(rho ? n : 0), dh(hsm ? n : 0);
     KnnArgs a;
@@ -757,7 +752,7 @@ static void smooth_moments_call(nbk_tree* t, int k, const double* rho, const dou
     NBK_REQUIRE(t->sec != nullptr, NBK_ERR_ARG, "CalcSmoothVel* need velocities");
     NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
     NBK_REQUIRE(out && (width == 3 || smvel), NBK_ERR_ARG, "CalcSmoothVel*: null argument");
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const int64_t n = t->n;
     const bool dev = flags & NBK_DEVICE_PTRS, tree_order = flags & NBK_TREE_ORDER;
     const int tb = 256;
@@ -828,7 +823,7 @@ static void fof_call(nbk_tree* t, FofArgs& a, const int32_t* precheck, int32_t* 
     NBK_REQUIRE(group && ngroups, NBK_ERR_ARG, "FOF: null output");
     require_no_halo(t, "FOF");
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "FOF needs a TPHYS or TPHS tree");
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const int64_t n = t->n;
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<int32_t> dpre, dpre_tree, dgroup(n), dlen, dhead, dnext, dtail;
@@ -945,7 +940,7 @@ int nbk_fof_roots(nbk_tree* t, int criterion, double fdist, const double* params
         a.mode = c.mode; a.p0 = c.p0; a.p1 = c.p1; a.prune_x2 = c.prune_x2;
     }
     a.minnum = 1; a.order = 0;
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const int64_t n = t->n;
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<int32_t> dpre, dpre_tree, droot(n), dout;
@@ -984,7 +979,7 @@ static void ball_call(nbk_tree* t, double fdist2, const CritSpec* crit, int64_t 
     NBK_REQUIRE(m >= 0 && cap >= 0, NBK_ERR_ARG, "ball search: negative count");
     require_no_halo(t, "ball search");
     NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "SearchBallPos needs positions as tree coordinates");
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const bool dev = flags & NBK_DEVICE_PTRS;
     if (m == 0) {                               // no queries: one row offset (0), nothing else
         *total = 0;
@@ -1070,7 +1065,7 @@ static void smooth_gather_call(nbk_tree* t, int k, int veldens_k, int64_t m, con
     NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
     NBK_REQUIRE(m >= 0 && out, NBK_ERR_ARG, "Calc*Particle / Calc*Position: bad count or null output");
     if (m == 0) return;
-    DeviceGuard guard(t->device, t->stream);
+    TreeGuard guard(t);
     const bool dev = flags & NBK_DEVICE_PTRS;
     DevBuf<int32_t> dq;
     DevBuf<double> dx, dv, dout;
@@ -1150,10 +1145,10 @@ int nbk_set_option(const char* name, int64_t value) {
 int nbk_release_cached_memory(int device) {
     NBK_API_BEGIN
     if (device < 0) NBK_CHECK(cudaGetDevice(&device));
-    cudaMemPool_t pool;
-    NBK_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    DeviceGuard guard(device);
     NBK_CHECK(cudaDeviceSynchronize());
-    NBK_CHECK(cudaMemPoolTrimTo(pool, 0));
+    cudaMemPool_t pool = nbk_pool(device);
+    if (pool) NBK_CHECK(cudaMemPoolTrimTo(pool, 0));
     NBK_API_END
 }
 

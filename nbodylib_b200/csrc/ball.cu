@@ -118,6 +118,13 @@ __global__ void __launch_bounds__(BALL_WARPS * 32) ball_kernel(BallParams prm) {
     if (!FILL && valid) prm.counts[qi] = v.count;
 }
 
+// 64-bit total of the per-query counts: the offsets are scanned in 32 bits, so a batch whose total does not fit is refused
+__global__ void ball_total_kernel(int64_t m, const uint32_t* __restrict__ counts, unsigned long long* total) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = i < m ? counts[i] : 0ull;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
 __global__ void ball_offsets_kernel(int64_t m, const uint32_t* scan, int64_t* offsets) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= m) offsets[i] = (int64_t)scan[i];
@@ -146,6 +153,15 @@ void launch_ball(nbk_tree& t, BallArgs& a) {
     if (t.store_bytes == 4) ball_kernel<float, false><<<blocks, BALL_WARPS * 32, 0, st>>>(p);
     else ball_kernel<double, false><<<blocks, BALL_WARPS * 32, 0, st>>>(p);
     NBK_CHECK(cudaEventRecord(t.ev3, st));
+    {
+        DevBuf<unsigned long long> tot64(1);
+        NBK_CHECK(cudaMemsetAsync(tot64.p, 0, sizeof(unsigned long long), st));
+        ball_total_kernel<<<div_up(m, 256), 256, 0, st>>>(m, counts.p, tot64.p);
+        unsigned long long h64 = 0;
+        NBK_CHECK(cudaMemcpyAsync(&h64, tot64.p, sizeof(h64), cudaMemcpyDeviceToHost, st));
+        NBK_CHECK(cudaStreamSynchronize(st));
+        NBK_REQUIRE(h64 < 0xffffffffull, NBK_ERR_ARG, "ball / criterion search: the batch returns 2^32 or more entries in all; split the query batch");
+    }
     exclusive_scan_u32(counts.p, counts.p, m + 1, scratch.p, st, &launches);
     ball_offsets_kernel<<<div_up(m + 1, 256), 256, 0, st>>>(m, counts.p, a.offsets);
     uint32_t tot = 0;

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <time.h>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -33,10 +34,38 @@ struct Error : public std::runtime_error {
         if (!(cond)) throw ::nbk::Error((code), std::string(msg));    \
     } while (0)
 
-// Stream the calling API entry point works on: DevBuf allocations are stream-ordered (cudaMallocAsync from the
-// device's default pool, whose release threshold nbk_create raises so that temporaries are recycled, not
-// returned to the driver: cudaMalloc/cudaFree of multi-GB scratch costs more than the kernels using it).
+// Stream the calling API entry point works on: DevBuf allocations are stream-ordered, from the library's OWN memory pool
+// (one per device, created on first use, release threshold unlimited: temporaries are recycled, not returned to the driver --
+// cudaMalloc/cudaFree of multi-GB scratch costs more than the kernels using it).  The device's default pool, and with it
+// every other user of cudaMallocAsync in the process, is left alone; nbk_release_cached_memory trims the private pool.
 inline cudaStream_t& cur_stream() { static thread_local cudaStream_t s = nullptr; return s; }
+inline cudaMemPool_t nbk_pool(int device = -1) {
+    static cudaMemPool_t pools[64] = {nullptr};
+    if (device < 0) cudaGetDevice(&device);
+    if (device < 0 || device >= 64) return nullptr;
+    if (!pools[device]) {
+        static std::mutex m;
+        std::lock_guard<std::mutex> g(m);
+        if (!pools[device]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            cudaMemPool_t pool = nullptr;
+            if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            pools[device] = pool;
+        }
+    }
+    return pools[device];
+}
+// stream-ordered allocation from the library's pool (falls back to the default pool if a private one cannot be created)
+inline cudaError_t nbk_malloc_async(void** ptr, size_t bytes, cudaStream_t st) {
+    cudaMemPool_t pool = nbk_pool();
+    return pool ? cudaMallocFromPoolAsync(ptr, bytes, pool, st) : cudaMallocAsync(ptr, bytes, st);
+}
 
 // RAII device buffer
 template <class T>
@@ -57,7 +86,7 @@ struct DevBuf {
         release();
         n = count;
         if (count) {
-            cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), cur_stream());
+            cudaError_t e = nbk_malloc_async((void**)&p, count * sizeof(T), cur_stream());
             if (e != cudaSuccess) {
                 p = nullptr; n = 0;
                 cudaGetLastError();

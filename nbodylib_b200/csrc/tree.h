@@ -1,10 +1,14 @@
 // tree.h -- the device-resident tree object behind nbk_tree, and the launch entry points each .cu exports.
 #pragma once
 #include <functional>
+#include <mutex>
 
 #include "common.cuh"
 
 struct nbk_tree {
+    // entry points that work on a tree hold this lock: the tree's stream, events and last_* fields are per tree, so two host
+    // threads calling into ONE tree are serialised here (different trees run concurrently)
+    mutable std::mutex mtx;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -53,6 +57,27 @@ struct nbk_tree {
     // nbk_create: called by the build right before the particle gather; joins the side thread that stages the secondary
     // phase-space half and the masses (their host->device copies overlap the sorts and the level loop)
     std::function<void()> before_gather;
+
+    nbk_tree() {}
+    nbk_tree(const nbk_tree&) = delete;
+    nbk_tree& operator=(const nbk_tree&) = delete;
+    // frees everything the tree owns (also on the error paths of nbk_create, where the tree is held by a unique_ptr)
+    ~nbk_tree() {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        if (prev != device) cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        void* bufs[] = {prim, sec, mass, order, nlo, nhi, cutdim, d_kernel, nlo2, nhi2};
+        for (void* b : bufs) if (b) cudaFreeAsync(b, stream);
+        if (stream) cudaStreamSynchronize(stream);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (ev2) cudaEventDestroy(ev2);
+        if (ev3) cudaEventDestroy(ev3);
+        if (stream) cudaStreamDestroy(stream);
+        cudaGetLastError();
+        if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    }
 
     const void* pos4() const { return treetype == NBK_TVEL ? sec : prim; }
     const void* vel4() const { return treetype == NBK_TVEL ? prim : sec; }

@@ -138,6 +138,54 @@ def test_reference_harness_compiles_unchanged_against_the_shim(built):
     assert exe is not None and os.access(exe, os.X_OK)
 
 
+def test_fofvel_in_the_reference_is_not_a_pair_relation():
+    """Why FOFVel (FOFFunc.h:39-46) has no device implementation.  The criterion constrains velocities only,
+    while the reference's walk prunes in position space (params[1]) and applies the criterion to EVERY particle of every leaf it
+    opens (KDSplitNode.cxx:991-1028, KDLeafNode.cxx:591-619).  On the live reference: (a) most of the particles
+    SearchCriterionTagged(FOFVel) returns lie beyond the position radius -- which ones depends on the leaf boxes, not on the
+    pair; (b) the returned relation is not symmetric (j is linked from i but i not from j), so the groups FOFCriterion builds
+    from it depend on the order in which its breadth-first search discovers particles; (c) the partition it returns is
+    neither the components of the symmetric pair relation (velocity criterion AND position radius) nor those of the
+    symmetrised walk relation.  There is no order-independent definition to be bit-exact against."""
+    from oracle.pyoracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    from nbodylib_b200.synth import clustered_small
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    n = 4000
+    pos, vel, mass = clustered_small(n, seed=31)
+    R = Ref(pos, vel, mass, period=None)
+    ll = 0.4 / n ** (1 / 3)
+    sv2 = ((vel - vel.mean(0)) ** 2).sum(1).mean() / 3
+    params = np.zeros(10)
+    params[1] = ll * ll
+    params[2] = params[6] = params[7] = 0.05 * sv2
+    off, ids = R.search_criterion_particles(np.arange(n, dtype=np.int32), 1, params)
+    src = np.repeat(np.arange(n), np.diff(off))
+    walk = np.zeros((n, n), dtype=bool)
+    walk[src, ids] = True
+    np.fill_diagonal(walk, False)
+    dx2 = ((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1)
+    dv2 = ((vel[:, None, :] - vel[None, :, :]) ** 2).sum(-1)
+    pair = (dv2 / params[6] < 1) & (dx2 < params[1])
+    np.fill_diagonal(pair, False)
+    assert (walk & ~(dx2 < params[1])).sum() > 1000                 # (a) links beyond the position radius
+    assert (walk & pair).sum() == pair.sum()                          #     (every true pair is found as well)
+    assert (walk & ~walk.T).sum() > 100                               # (b) asymmetric links
+    g, ng = R.fof_criterion(1, params, 2, 0)
+
+    def components(adj):
+        i, j = np.nonzero(adj)
+        _, comp = connected_components(coo_matrix((np.ones(len(i), dtype=np.int8), (i, j)), shape=(n, n)), directed=False)
+        sizes = np.bincount(comp)
+        lab = np.where(sizes[comp] >= 2, comp + 1, 0)
+        return lab
+    assert not np.array_equal(canon(g), canon(components(pair)))      # (c)
+    assert not np.array_equal(canon(g), canon(components(walk | walk.T)))
+    R.close()
+
+
 def test_reference_tree_shape_known_answer():
     """N=1e6, b=16 -> 131071 nodes / 65536 leaves: the closed-form shape used by the device build."""
     def shape(n, b):
