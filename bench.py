@@ -199,7 +199,18 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -212,6 +223,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: native libraries that print there (NCCL's version banner, for one) are
+    # sent to stderr by pointing file descriptor 1 at it; the line itself goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     # fail fast instead of hanging the caller: a healthy run ends within ~2 minutes at any N
     import signal
     signal.alarm(int(os.environ.get("BENCH_WATCHDOG_S", "900")))
@@ -264,7 +281,10 @@ def main():
             print("[bench rank %d %.1fs] %s" % (rank, time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
 
     if world > 1:
-        from nbodylib_b200.sharded import ShardedTree
+        # the slab-sharded tree: through the C ABI (include/nbk_sharded.h: exchange + merge in C++ over the library's own NCCL
+        # communicator) unless NBK_SHARDED_DRIVER=torch selects the torch.distributed driver of the same algorithm
+        from nbodylib_b200 import sharded as _sh
+        ShardedTree = _sh.ShardedTree if os.environ.get("NBK_SHARDED_DRIVER", "native") == "torch" else _sh.NativeShardedTree
         tree = ShardedTree(pos, vel, mass, period=period, rank=rank, world=world, box=box)
     else:
         tree = KDTree(pos, vel, mass, Period=period, device=local)
@@ -432,6 +452,7 @@ def main():
         except Exception as ex:  # the headline line must survive a failure of these rows
             extra["fof_error"] = repr(ex)[:300]
         extra["sharded_rank0"] = dict(tree.stats)
+        extra["sharded_driver"] = "C ABI (libnbk_sharded.so, NCCL from C++)" if ShardedTree is _sh.NativeShardedTree else "torch.distributed driver (nbodylib_b200/sharded.py)"
         extra["box"] = list(map(float, box))
         extra["particles_total"] = n_total
     tree.close()
@@ -447,8 +468,12 @@ def main():
         ts = []
         for it in range(1 + max(1, args.steps // 2)):
             barrier(); t1 = time.perf_counter()
-            dp, dm = hp.to("cuda", non_blocking=True), hm.to("cuda", non_blocking=True)
-            st = ShardedTree(dp, None, dm, period=period, rank=rank, world=world, box=box)
+            if ShardedTree is _sh.NativeShardedTree:            # host pointers straight into the C ABI
+                dp = dm = None
+                st = ShardedTree(hp, None, hm, period=period, rank=rank, world=world, box=box, device=local)
+            else:
+                dp, dm = hp.to("cuda", non_blocking=True), hm.to("cuda", non_blocking=True)
+                st = ShardedTree(dp, None, dm, period=period, rank=rank, world=world, box=box)
             r = st.CalcDensity(K_NN)
             out.copy_(r)
             barrier()
@@ -596,8 +621,9 @@ def main():
         for r in rows.values():
             if "roofline" in r:
                 r["roofline"]["peak_source"] = peak_src
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
+        _sh.NativeShardedTree.shutdown()
         dist.destroy_process_group()
 
 

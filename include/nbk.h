@@ -54,7 +54,17 @@ enum {
                                    (KDFindNearest.cxx:247-334, quirk Q3)                                        */
     NBK_STORE_F64 = 1 << 4,     /* nbk_create: keep coordinates as fp64 in HBM even if fp32 would be exact      */
     NBK_STORE_F32 = 1 << 5,     /* nbk_create: force fp32 storage (coordinates rounded if not representable)    */
-    NBK_OUT_IDS = 1 << 6        /* neighbour / ball outputs hold particle IDs instead of tree indices           */
+    NBK_OUT_IDS = 1 << 6,       /* neighbour / ball outputs hold particle IDs instead of tree indices           */
+    NBK_WARP_ALIGNED = 1 << 7   /* nbk_create: warp-aligned tree shape.  Nodes above 32 particles split at a multiple of
+                                   32 (the balanced split of their 32-particle units) instead of at ceil(size/2)
+                                   (KDTree.cxx:1012), so every 32 consecutive tree positions are one node and the
+                                   kernels' query groups coincide with nodes for ANY particle count (with the reference
+                                   rule only for powers of two; elsewhere CalcDensity is ~20 % slower).  Still a median
+                                   split in the dimension of largest spread; depth, node count of the upper levels and
+                                   all search / density / FOF RESULTS are unchanged -- what changes is the tree order
+                                   (nbk_get_order) and the node arrays (nbk_get_nodes), which then no longer equal the
+                                   reference's.  Meant for trees whose shape the caller never inspects (the slab trees
+                                   of nbk_sharded.h use it).                                                          */
 };
 
 /* Strided, layout-agnostic description of the caller's particles (reference Particle.h:264-354; in the
@@ -84,6 +94,8 @@ typedef struct {
     int64_t last_launches;                   /* kernels launched by the last call                                   */
     int64_t device_bytes;                    /* HBM held by the tree                                                */
     int64_t last_flagged;                    /* density calls: queries re-run by the exact-heap kernel (fp32 key ties) */
+    int32_t warp_aligned;                    /* 1: built with NBK_WARP_ALIGNED                                     */
+    int32_t reserved;
 } nbk_info;
 
 const char* nbk_last_error(void);

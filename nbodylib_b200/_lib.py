@@ -25,7 +25,8 @@ class NbkInfo(C.Structure):
                 ("inexact_coords", C.c_int64),
                 ("kernnorm", C.c_double), ("period", C.c_double * 3),
                 ("build_ms", C.c_double), ("h2d_ms", C.c_double), ("last_kernel_ms", C.c_double), ("last_call_ms", C.c_double),
-                ("last_launches", C.c_int64), ("device_bytes", C.c_int64), ("last_flagged", C.c_int64)]
+                ("last_launches", C.c_int64), ("device_bytes", C.c_int64), ("last_flagged", C.c_int64),
+                ("warp_aligned", C.c_int32), ("reserved", C.c_int32)]
 
 
 class NbkFofLists(C.Structure):
@@ -33,7 +34,7 @@ class NbkFofLists(C.Structure):
 
 
 # flags (include/nbk.h)
-DEVICE_PTRS, TREE_ORDER, STRICT_PERIODIC, KNN_TREE_FORM, STORE_F64, STORE_F32, OUT_IDS = (1 << i for i in range(7))
+DEVICE_PTRS, TREE_ORDER, STRICT_PERIODIC, KNN_TREE_FORM, STORE_F64, STORE_F32, OUT_IDS, WARP_ALIGNED = (1 << i for i in range(8))
 
 EXPORTS = [
     "nbk_last_error", "nbk_device_count", "nbk_create", "nbk_destroy", "nbk_get_info", "nbk_get_order",
@@ -46,7 +47,47 @@ EXPORTS = [
     "nbk_set_option", "nbk_fof_roots", "nbk_union_pairs",
 ]
 
+SHARDED_PATH = os.path.join(HERE, "libnbk_sharded.so")
+SHARDED_EXPORTS = ["nbk_comm_unique_id", "nbk_comm_init_rank", "nbk_comm_destroy", "nbk_sharded_create", "nbk_sharded_destroy",
+                   "nbk_sharded_calc_density", "nbk_sharded_fof", "nbk_sharded_get_info", "nbk_sharded_release"]
+
+
+class NbkShardedInfo(C.Structure):
+    _fields_ = [("n_local", C.c_int64), ("n_global", C.c_int64), ("first_global_id", C.c_int64),
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("h_knn", C.c_double),
+                ("ghosts_knn", C.c_int64), ("ghosts_fof", C.c_int64), ("density_setups", C.c_int64), ("fof_setups", C.c_int64),
+                ("last_kernel_ms", C.c_double), ("last_call_ms", C.c_double), ("last_launches", C.c_int64), ("last_flagged", C.c_int64)]
+
+
 _lib = None
+_sharded = None
+
+
+def load_sharded():
+    """libnbk_sharded.so (include/nbk_sharded.h).  torch is imported first so that the process holds ONE NCCL (the loader
+    resolves the library's libnccl.so.2 to the copy torch already mapped)."""
+    global _sharded
+    if _sharded is not None:
+        return _sharded
+    load()
+    if not os.path.exists(SHARDED_PATH):
+        raise RuntimeError("nbodylib_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`" % SHARDED_PATH)
+    import torch  # noqa: F401
+    S = C.CDLL(SHARDED_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    S.nbk_comm_unique_id.argtypes = [vp]
+    S.nbk_comm_init_rank.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
+    S.nbk_comm_destroy.argtypes = [vp]
+    S.nbk_sharded_create.argtypes = [vp, C.POINTER(NbkParticles), i64, vp, i32, i32, dbl, C.POINTER(vp)]
+    S.nbk_sharded_destroy.argtypes = [vp]
+    S.nbk_sharded_calc_density.argtypes = [vp, i32, vp, i32]
+    S.nbk_sharded_fof.argtypes = [vp, i32, dbl, vp, i32, i32, vp, C.POINTER(i64), i32]
+    S.nbk_sharded_get_info.argtypes = [vp, C.POINTER(NbkShardedInfo)]
+    S.nbk_sharded_release.argtypes = [vp]
+    for name in SHARDED_EXPORTS:
+        getattr(S, name).restype = i32
+    _sharded = S
+    return S
 
 
 def load():

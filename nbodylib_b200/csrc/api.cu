@@ -13,6 +13,7 @@
 using namespace nbk;
 
 static thread_local std::string g_err;
+namespace nbk { void set_last_error(const char* msg) { g_err = msg ? msg : ""; } }
 
 #define NBK_API_BEGIN try {
 #define NBK_API_END                                                          \
@@ -257,6 +258,7 @@ int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int 
     std::unique_ptr<nbk_tree> t(new nbk_tree);
     t->device = device;
     t->n = n; t->bucket = bucket; t->treetype = treetype; t->kerntype = kerntype;
+    t->aligned = (flags & NBK_WARP_ALIGNED) ? 1 : 0;
     if (kernres < 100) kernres = 100;      // KDTree.cxx:1145-1148
     t->kernres = kernres;
     t->nd = (treetype == NBK_TPHS) ? 6 : 3;
@@ -414,6 +416,7 @@ int nbk_attach_halo(nbk_tree* t, nbk_tree* halo) {
     t->mass = mass.p; mass.p = nullptr;
     t->order = order.p; order.p = nullptr;
     t->nlo2 = halo->nlo; t->nhi2 = halo->nhi;
+    t->aligned2 = halo->aligned;
     t->knn_fp32_ok = -1;
     t->n_main = n1; t->n = n;
     t->device_bytes += halo->device_bytes;
@@ -436,6 +439,7 @@ int nbk_get_info(const nbk_tree* t, nbk_info* info) {
     for (int d = 0; d < 3; d++) info->period[d] = t->period[d];
     info->build_ms = t->build_ms; info->h2d_ms = t->h2d_ms; info->last_kernel_ms = t->last_kernel_ms;
     info->last_call_ms = t->last_call_ms; info->last_launches = t->last_launches; info->device_bytes = t->device_bytes; info->last_flagged = t->last_flagged;
+    info->warp_aligned = t->aligned;
     NBK_API_END
 }
 

@@ -90,7 +90,7 @@ __global__ void v2_rank_gather_kernel(int64_t n, const uint32_t* __restrict__ od
 
 // one thread per node of a GLOBAL level (every node of such a level is split)
 template <class K>
-__global__ void v2_level_nodes_kernel(int level, int64_t n, Cols cur, const K* __restrict__ sk0, const K* __restrict__ sk1, const K* __restrict__ sk2,
+__global__ void v2_level_nodes_kernel(int level, int64_t n, int al, Cols cur, const K* __restrict__ sk0, const K* __restrict__ sk1, const K* __restrict__ sk2,
                                       NodeLo* __restrict__ nlo, NodeHi* __restrict__ nhi, int8_t* __restrict__ cutdim, int32_t* __restrict__ lv_cd,
                                       uint32_t* __restrict__ lv_mr, uint32_t* __restrict__ rcount) {
     typedef typename KeyCoord<K>::type S;
@@ -103,7 +103,7 @@ __global__ void v2_level_nodes_kernel(int level, int64_t n, Cols cur, const K* _
     else {
         int64_t p = (idx - 1) >> 1;
         int ps = nlo[p].start, pe = nhi[p].end;
-        int pm = ps + (pe - ps - 1) / 2;
+        int pm = ps + (int)split_left(pe - ps, al) - 1;
         if (idx & 1) { s = ps; e = pm + 1; } else { s = pm + 1; e = pe; }
     }
     S lo0 = KeyCoord<K>::get(sk0[cur.c[0][0][s]]), hi0 = KeyCoord<K>::get(sk0[cur.c[0][0][e - 1]]);
@@ -117,7 +117,7 @@ __global__ void v2_level_nodes_kernel(int level, int64_t n, Cols cur, const K* _
     NodeHi b; b.x = round_up(hi0); b.y = round_up(hi1); b.z = round_up(hi2); b.end = e;
     nlo[idx] = a; nhi[idx] = b;
     cutdim[idx] = (int8_t)cd;
-    const int m = s + (e - s - 1) / 2;
+    const int m = s + (int)split_left(e - s, al) - 1;
     lv_cd[j] = cd;
     lv_mr[j] = cur.c[cd][cd][m];
     rcount[j] = (uint32_t)(e - (m + 1));
@@ -126,14 +126,14 @@ __global__ void v2_level_nodes_kernel(int level, int64_t n, Cols cur, const K* _
 // the (at most two) nodes a tile of a global level overlaps.  The node holding position `base` is found by walking the
 // split rule from the root (pure arithmetic: the tree shape depends only on n), no search through memory.
 struct TileNodes { int jA, sB, mA, mB, cdA, cdB; uint32_t mrA, mrB; };
-__device__ __forceinline__ TileNodes v2_tile_nodes(int64_t base, int level, int64_t n, const int32_t* __restrict__ lv_cd, const uint32_t* __restrict__ lv_mr) {
+__device__ __forceinline__ TileNodes v2_tile_nodes(int64_t base, int level, int64_t n, int al, const int32_t* __restrict__ lv_cd, const uint32_t* __restrict__ lv_mr) {
     int s = 0, e = (int)n, j = 0;
     for (int l = 0; l < level; l++) {
-        const int m = s + (e - s - 1) / 2;
+        const int m = s + (int)split_left(e - s, al) - 1;
         if (base > m) { s = m + 1; j = 2 * j + 1; } else { e = m + 1; j = 2 * j; }
     }
     TileNodes t;
-    t.jA = j; t.mA = s + (e - s - 1) / 2;
+    t.jA = j; t.mA = s + (int)split_left(e - s, al) - 1;
     const int C = 1 << level;
     const bool hasB = j + 1 < C;
     t.cdA = lv_cd[j]; t.mrA = lv_mr[j];
@@ -144,21 +144,21 @@ __device__ __forceinline__ TileNodes v2_tile_nodes(int64_t base, int level, int6
         // then keep left; equivalently walk the split rule for position e (the first position after node A)
         int s2 = 0, e2 = (int)n;
         for (int l = 0; l < level; l++) {
-            const int m2 = s2 + (e2 - s2 - 1) / 2;
+            const int m2 = s2 + (int)split_left(e2 - s2, al) - 1;
             if (e > m2) s2 = m2 + 1; else e2 = m2 + 1;
         }
-        t.sB = s2; t.mB = s2 + (e2 - s2 - 1) / 2;
+        t.sB = s2; t.mB = s2 + (int)split_left(e2 - s2, al) - 1;
     }
     return t;
 }
 
-__global__ void __launch_bounds__(PRIM_THREADS) v2_count_kernel(int level, int64_t n, Cols cur, const int32_t* __restrict__ lv_cd,
+__global__ void __launch_bounds__(PRIM_THREADS) v2_count_kernel(int level, int64_t n, int al, Cols cur, const int32_t* __restrict__ lv_cd,
                                                                 const uint32_t* __restrict__ lv_mr, uint32_t* __restrict__ tsum, int ntiles) {
     __shared__ uint32_t swarp[8];
     __shared__ TileNodes tn_s;
     const int d = blockIdx.y;
     const int64_t base = (int64_t)blockIdx.x * PRIM_TILE;
-    if (threadIdx.x == 0) tn_s = v2_tile_nodes(base, level, n, lv_cd, lv_mr);
+    if (threadIdx.x == 0) tn_s = v2_tile_nodes(base, level, n, al, lv_cd, lv_mr);
     __syncthreads();
     const TileNodes tn = tn_s;
     uint32_t cnt = 0;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(PRIM_THREADS) v2_count_kernel(int level, int64
     if (threadIdx.x == 0) tsum[(size_t)d * ntiles + blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(PRIM_THREADS, 3) v2_scatter_kernel(int level, int64_t n, Cols cur, Cols nxt, const int32_t* __restrict__ lv_cd,
+__global__ void __launch_bounds__(PRIM_THREADS, 3) v2_scatter_kernel(int level, int64_t n, int al, Cols cur, Cols nxt, const int32_t* __restrict__ lv_cd,
                                                                      const uint32_t* __restrict__ lv_mr, const uint32_t* __restrict__ tscan, int ntiles,
                                                                      const uint32_t* __restrict__ Rb) {
     __shared__ uint32_t cnt[PRIM_ITEMS * 8];
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(PRIM_THREADS, 3) v2_scatter_kernel(int level, 
     const int d = blockIdx.y;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5, lt = lanemask_lt();
     const int64_t base = (int64_t)blockIdx.x * PRIM_TILE;
-    if (threadIdx.x == 0) tn_s = v2_tile_nodes(base, level, n, lv_cd, lv_mr);
+    if (threadIdx.x == 0) tn_s = v2_tile_nodes(base, level, n, al, lv_cd, lv_mr);
     __syncthreads();
     const TileNodes tn = tn_s;
     const uint32_t RbA = Rb[tn.jA], RbB = (tn.sB != 0x7fffffff) ? Rb[tn.jA + 1] : 0u;
@@ -262,7 +262,7 @@ static inline size_t v2_small_smem(int coord_bytes, int ntab) {
 //            thread t owns positions 8t..8t+7 of every order, the three flag counts are scanned together (packed in 64 bits),
 //            prefix values at node starts go through a per-node table.
 template <class S>
-__global__ void __launch_bounds__(V2_T) v2_small_kernel(int L, int nsub, int64_t n, int bucket, Cols cur, const Vec4<S>* __restrict__ P_in,
+__global__ void __launch_bounds__(V2_T) v2_small_kernel(int L, int nsub, int64_t n, int bucket, int al, Cols cur, const Vec4<S>* __restrict__ P_in,
                                                         const uint32_t* __restrict__ ordx, NodeLo* __restrict__ nlo, NodeHi* __restrict__ nhi,
                                                         int8_t* __restrict__ cutdim, uint32_t* __restrict__ tree_ord, int ntab) {
     extern __shared__ __align__(16) unsigned char sm[];
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(V2_T) v2_small_kernel(int L, int nsub, int64_t
         else {
             int64_t p = (idx - 1) >> 1;
             int ps = nlo[p].start, pe = nhi[p].end;
-            int pm = ps + (pe - ps - 1) / 2;
+            int pm = ps + (int)split_left(pe - ps, al) - 1;
             if (idx & 1) { s = ps; e = pm + 1; } else { s = pm + 1; e = pe; }
         }
         se_s[0] = s; se_s[1] = e;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(V2_T) v2_small_kernel(int L, int nsub, int64_t
                 nlo[hidx] = a; nhi[hidx] = b;
                 cutdim[hidx] = split ? (int8_t)cd : (int8_t)-1;
                 if (split) {
-                    const int m1 = s1 + (e1 - s1 - 1) / 2;
+                    const int m1 = s1 + (int)split_left(e1 - s1, al) - 1;
                     const int em = cd == 0 ? ord0[m1] : (cd == 1 ? ord1[m1] : ord2[m1]);       // the median element
                     n_m[k] = (uint16_t)m1; n_cd[k] = (int8_t)cd;
                     n_mr[k] = (uint16_t)(cd == 0 ? em : (cd == 1 ? (int)rk1[em] : (int)rk2[em]));
@@ -449,34 +449,36 @@ template <class S> struct KeyOf;
 template <> struct KeyOf<float> { typedef uint32_t type; };
 template <> struct KeyOf<double> { typedef uint64_t type; };
 
-// Tree shape: depends only on n and bucket (left = ceil(size/2), leaf iff size <= bucket; KDTree.cxx:994,1012)
+// Tree shape: depends only on n, bucket and the split rule (split_left; reference: left = ceil(size/2), leaf iff size <= bucket,
+// KDTree.cxx:994,1012)
 static void tree_shape(nbk_tree& t) {
     const int64_t n = t.n;
-    const int bucket = t.bucket;
+    const int bucket = t.bucket, al = t.aligned;
     int depth = 0;
     {
-        int64_t smax = n;
-        while (smax > bucket) { smax = (smax + 1) / 2; depth++; }
+        int64_t smax = n;                       // the left child is never the smaller one
+        while (smax > bucket) { smax = split_left(smax, al); depth++; }
     }
     NBK_REQUIRE(depth <= 30, NBK_ERR_ARG, "tree too deep for 32-bit node indices");
     t.depth = depth;
     t.nslots = ((int64_t)1 << (depth + 1)) - 1;
-    int64_t sz[2] = {n, -1}, ct[2] = {1, 0};
+    // node sizes of a level with their multiplicities (two sizes for the reference rule, a few more with a ragged last unit)
+    std::vector<std::pair<int64_t, int64_t>> lv(1, std::make_pair(n, (int64_t)1)), nx;
     int64_t nodes = 0, leaves = 0;
-    for (int l = 0; l <= depth; l++) {
-        int64_t nsz[2] = {-1, -1}, nct[2] = {0, 0};
-        for (int q = 0; q < 2; q++) {
-            if (ct[q] == 0) continue;
-            nodes += ct[q];
-            if (sz[q] <= bucket) { leaves += ct[q]; continue; }
-            int64_t ch[2] = {(sz[q] + 1) / 2, sz[q] / 2};
-            for (int c = 0; c < 2; c++) {
-                int slot = (nsz[0] == ch[c] || nsz[0] < 0) ? 0 : 1;
-                if (nsz[slot] >= 0 && nsz[slot] != ch[c]) throw Error(NBK_ERR_ARG, "internal: >2 node sizes on a level");
-                nsz[slot] = ch[c]; nct[slot] += ct[q];
+    for (int l = 0; l <= depth && !lv.empty(); l++) {
+        nx.clear();
+        for (const auto& sc : lv) {
+            nodes += sc.second;
+            if (sc.first <= bucket) { leaves += sc.second; continue; }
+            const int64_t left = split_left(sc.first, al);
+            for (int64_t ch : {left, sc.first - left}) {
+                bool found = false;
+                for (auto& e : nx) if (e.first == ch) { e.second += sc.second; found = true; break; }
+                if (!found) nx.push_back(std::make_pair(ch, sc.second));
             }
         }
-        sz[0] = nsz[0]; sz[1] = nsz[1]; ct[0] = nct[0]; ct[1] = nct[1];
+        NBK_REQUIRE(nx.size() <= 64, NBK_ERR_ARG, "internal: too many node sizes on a level");
+        lv.swap(nx);
     }
     t.num_nodes = nodes; t.num_leaves = leaves;
 }
@@ -492,8 +494,9 @@ static void build_tree_v2(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* se
     tree_shape(t);
     const int depth = t.depth;
     // global levels: all levels whose nodes are larger than V2_CAP (every node of such a level is split: V2_CAP >= bucket)
+    const int al = t.aligned;
     int L = 0;
-    while ((((n - 1) >> L) + 1) > V2_CAP) L++;          // ceil(n / 2^L) > V2_CAP
+    for (int64_t smax = n; smax > V2_CAP; smax = split_left(smax, al)) L++;      // largest node of level L <= V2_CAP
     NBK_REQUIRE(L <= depth, NBK_ERR_ARG, "internal: bucket larger than the shared-memory node capacity");
     const int nsub = depth - L;
     const int ntab = 1 << nsub;
@@ -556,12 +559,12 @@ static void build_tree_v2(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* se
         DevBuf<uint32_t> scratch(sc > sc2 ? sc : sc2);
         for (int l = 0; l < L; l++) {
             const int64_t C = (int64_t)1 << l;
-            v2_level_nodes_kernel<K><<<div_up(C, 128), 128, 0, st>>>(l, n, cols[cur], skeys[0].p, skeys[1].p, skeys[2].p, nlo.p, nhi.p, cutdim.p,
+            v2_level_nodes_kernel<K><<<div_up(C, 128), 128, 0, st>>>(l, n, al, cols[cur], skeys[0].p, skeys[1].p, skeys[2].p, nlo.p, nhi.p, cutdim.p,
                                                                      lv_cd.p, lv_mr.p, rcount.p);
             exclusive_scan_u32(rcount.p, rcount.p, C, scratch.p, st, &launches);
-            v2_count_kernel<<<dim3(ntiles, 3), PRIM_THREADS, 0, st>>>(l, n, cols[cur], lv_cd.p, lv_mr.p, tsum.p, ntiles);
+            v2_count_kernel<<<dim3(ntiles, 3), PRIM_THREADS, 0, st>>>(l, n, al, cols[cur], lv_cd.p, lv_mr.p, tsum.p, ntiles);
             exclusive_scan_u32(tsum.p, tsum.p, (int64_t)3 * ntiles, scratch.p, st, &launches);
-            v2_scatter_kernel<<<dim3(ntiles, 3), PRIM_THREADS, 0, st>>>(l, n, cols[cur], cols[cur ^ 1], lv_cd.p, lv_mr.p, tsum.p, ntiles, rcount.p);
+            v2_scatter_kernel<<<dim3(ntiles, 3), PRIM_THREADS, 0, st>>>(l, n, al, cols[cur], cols[cur ^ 1], lv_cd.p, lv_mr.p, tsum.p, ntiles, rcount.p);
             launches += 3;
             cur ^= 1;
             if (tr.on) { char lb[64]; snprintf(lb, sizeof(lb), "build: level %d", l); tr.point(lb); }
@@ -573,7 +576,7 @@ static void build_tree_v2(nbk_tree& t, const Vec4<S>* prim_in, const Vec4<S>* se
         const size_t smem = v2_small_smem((int)sizeof(S), ntab);
         NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "internal: small-node kernel does not fit shared memory");
         NBK_CHECK(cudaFuncSetAttribute(v2_small_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        v2_small_kernel<S><<<(unsigned)((int64_t)1 << L), V2_T, smem, st>>>(L, nsub, n, bucket, cols[cur], prim_in, ordx.p, nlo.p, nhi.p, cutdim.p,
+        v2_small_kernel<S><<<(unsigned)((int64_t)1 << L), V2_T, smem, st>>>(L, nsub, n, bucket, al, cols[cur], prim_in, ordx.p, nlo.p, nhi.p, cutdim.p,
                                                                            tree_ord.p, ntab);
         NBK_CHECK(cudaGetLastError());
         tr.point("build: small nodes");

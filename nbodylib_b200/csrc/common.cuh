@@ -118,6 +118,17 @@ struct Tracer {
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Size of the LEFT child of a node of `size` particles (the right child takes the rest).
+//   reference shape (aligned = 0): ceil(size / 2)  (KDTree.cxx:1012: split index = start + (size - 1) / 2);
+//   warp-aligned shape (NBK_WARP_ALIGNED trees): a node above 32 particles splits at a multiple of 32 -- the balanced split of its
+//   32-particle units -- so that every run of 32 consecutive tree positions [32 g, 32 g + 32) is exactly one node: the warp's
+//   query group of the density / FOF kernels coincides with a node for ANY particle count, not only for powers of two.
+//   Still a median split (the cut plane moves by less than 32 particles' worth); left >= right, depth unchanged.
+__host__ __device__ __forceinline__ int64_t split_left(int64_t size, int aligned) {
+    if (aligned && size > 32) { const int64_t u = (size + 31) >> 5; return ((u + 1) >> 1) << 5; }
+    return (size + 1) >> 1;
+}
+
 // 4-wide coordinate records: storage type S is float (16 B) or double (32 B)
 template <class S> struct Vec4;
 template <> struct __align__(16) Vec4<float> { float x, y, z, w; };

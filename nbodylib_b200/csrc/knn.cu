@@ -63,6 +63,7 @@ struct KnnParams {
     // smoothed velocity moments (CalcSmoothVel / CalcSmoothVelDisp): densities in, accumulators out, all tree order
     const double* rho_in; const double* smvel_in; double* smvel_out; double* smdisp_out;
     int64_t n_tree;                                   // particles of the main tree (= n unless a halo is attached)
+    int aligned;                                      // the main tree's split rule (split_left)
     int tr_max;                                       // density kernel: transposed screening threshold (lanes needing a tile)
 };
 
@@ -799,7 +800,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm
         for (int p = 0; p < NN; p++) *v.hp.keyp(p) = p < kcap ? AP_INF : 0.f;
         v.topw = AP_INF;
         if (valid) v.set_limit(AP_HUGE); else { v.limf = -1.f; v.limu = 0u; }
-        traverse_bottom_up(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid, prm.n_tree, g0, g1);
+        traverse_bottom_up(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid, prm.n_tree, prm.aligned, g0, g1);
         if (HALO) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);
 
         // ------------------------------------------------------------------------ the k nearest and the k-th
@@ -903,6 +904,7 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.P = t.prim; p.V = t.vel4(); p.mass = t.mass; p.order = t.order;
     p.n = t.n;
     p.n_tree = t.n_main ? t.n_main : t.n;
+    p.aligned = t.aligned;
     p.tr_max = g_knn_transpose >= 0 ? g_knn_transpose : 12;
     p.q0 = a.q0; p.q1 = a.q1; p.xq = a.xq; p.mode = a.mode;
     p.qlist = a.qlist; p.nq = a.nq;
@@ -985,12 +987,12 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
         // two would be scanned as half-empty 16/17-particle tiles.
         {
             int64_t sz = t.n_main ? t.n_main : t.n;
-            while (sz > 40) sz = (sz + 1) / 2;
+            while (sz > 40) sz = split_left(sz, t.aligned);
             int leaf = g_knn_leaf > 0 ? g_knn_leaf : (int)sz;
             if (leaf > p.bucket) p.bucket = leaf;
             if (t.nlo2) {
                 sz = t.n - t.n_main;
-                while (sz > 40) sz = (sz + 1) / 2;
+                while (sz > 40) sz = split_left(sz, t.aligned2);
                 leaf = g_knn_leaf > 0 ? g_knn_leaf : (int)sz;
                 if (leaf > p.bucket2) p.bucket2 = leaf;
             }

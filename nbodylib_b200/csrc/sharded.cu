@@ -21,8 +21,10 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <memory>
 #include <numeric>
 
+#include "../../include/nbk_sharded.h"
 #include "sort_scan.cuh"
 #include "tree.h"
 
@@ -230,7 +232,8 @@ struct nbk_sharded {
     DevBuf<int64_t> fof_gid;
     // statistics of the last calls
     int64_t ghosts_knn = 0, ghosts_fof = 0, density_setups = 0, fof_setups = 0;
-    double last_kernel_ms = 0;
+    double last_kernel_ms = 0, last_call_ms = 0;
+    int64_t last_launches = 0, last_flagged = 0;
 };
 
 namespace {
@@ -253,15 +256,6 @@ double group_max(nbk_comm* c, double v) {
     NBK_CHECK(cudaMemcpyAsync(d.p, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     NBK_NCCL(ncclAllReduce(d.p, d.p, 1, ncclDouble, ncclMax, c->nccl, c->stream));
     NBK_CHECK(cudaMemcpyAsync(&v, d.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    NBK_CHECK(cudaStreamSynchronize(c->stream));
-    return v;
-}
-int64_t group_sum(nbk_comm* c, int64_t v) {
-    if (c->nranks == 1) return v;
-    DevBuf<int64_t> d(1);
-    NBK_CHECK(cudaMemcpyAsync(d.p, &v, sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    NBK_NCCL(ncclAllReduce(d.p, d.p, 1, ncclInt64, ncclSum, c->nccl, c->stream));
-    NBK_CHECK(cudaMemcpyAsync(&v, d.p, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     NBK_CHECK(cudaStreamSynchronize(c->stream));
     return v;
 }
@@ -363,7 +357,7 @@ void check_halo(nbk_sharded* s, double h, const char* what) {
     }
 }
 
-nbk_tree* make_tree(nbk_sharded* s, const void* pos, const void* vel, const void* mass, int64_t n, int real_bytes, const double* period) {
+nbk_tree* make_tree(nbk_sharded* s, const void* pos, const void* vel, const void* mass, int64_t n, int real_bytes, const double* period, int flags = 0) {
     nbk_particles np;
     memset(&np, 0, sizeof(np));
     np.pos = pos; np.pos_stride = 3 * real_bytes;
@@ -372,7 +366,8 @@ nbk_tree* make_tree(nbk_sharded* s, const void* pos, const void* vel, const void
     np.real_bytes = real_bytes; np.on_device = 1;
     nbk_tree* t = nullptr;
     NBK_CHECK(cudaStreamSynchronize(s->comm->stream));       // the library builds on the tree's own stream
-    const int rc = nbk_create(&np, n, 16, NBK_TPHYS, NBK_KEPAN, 1000, 0, period, 0, s->comm->device, &t);
+    // warp-aligned shape: a slab's particle count is arbitrary, and nobody inspects the shape of these trees
+    const int rc = nbk_create(&np, n, 16, NBK_TPHYS, NBK_KEPAN, 1000, 0, period, flags | NBK_WARP_ALIGNED, s->comm->device, &t);
     if (rc != NBK_OK) throw Error(rc, nbk_last_error());
     return t;
 }
@@ -388,7 +383,10 @@ void density_setup(nbk_sharded* s) {
     Halo H;
     halo_exchange<R>(s, s->h_knn, false, false, true, false, H);
     const int64_t g = H.nl + H.nr;
-    nbk_tree* tree = make_tree(s, s->pos, nullptr, s->mass, s->n, s->real_bytes, nullptr);
+    // fp32 input is stored as it is; fp64 input is stored as fp32 when every coordinate is representable -- a property the
+    // owned particles and the ghosts must share for the two trees to be attached
+    const int store = s->real_bytes == 4 ? NBK_STORE_F32 : 0;
+    nbk_tree* tree = make_tree(s, s->pos, nullptr, s->mass, s->n, s->real_bytes, nullptr, store);
     if (g > 0) {
         DevBuf<double> gpos((size_t)(3 * g)), gmass((size_t)g);
         if (H.nl) {
@@ -400,8 +398,15 @@ void density_setup(nbk_sharded* s) {
             sh_col_kernel<<<div_up(H.nr, 256), 256, 0, st>>>(H.nr, (const double*)H.rows_r.p, H.cols, 3, 1, gmass.p + H.nl);
         }
         nbk_tree* halo = nullptr;
-        try { halo = make_tree(s, gpos.p, nullptr, gmass.p, g, 8, nullptr); }
-        catch (...) { nbk_destroy(tree); throw; }
+        try {
+            halo = make_tree(s, gpos.p, nullptr, gmass.p, g, 8, nullptr, store);
+            nbk_info a, b;
+            nbk_get_info(tree, &a); nbk_get_info(halo, &b);
+            if (a.store_bytes != b.store_bytes) {                 // one side needs fp64: both get it
+                if (a.store_bytes == 4) { nbk_destroy(tree); tree = nullptr; tree = make_tree(s, s->pos, nullptr, s->mass, s->n, s->real_bytes, nullptr, NBK_STORE_F64); }
+                else { nbk_destroy(halo); halo = nullptr; halo = make_tree(s, gpos.p, nullptr, gmass.p, g, 8, nullptr, NBK_STORE_F64); }
+            }
+        } catch (...) { if (tree) nbk_destroy(tree); if (halo) nbk_destroy(halo); throw; }
         const int rc = nbk_attach_halo(tree, halo);
         if (rc != NBK_OK) { nbk_destroy(tree); nbk_destroy(halo); throw Error(rc, nbk_last_error()); }
     }
@@ -427,7 +432,7 @@ void calc_density(nbk_sharded* s, int k, double* rho_out, int flags) {
         if (rc != NBK_OK) throw Error(rc, nbk_last_error());
         nbk_info info;
         nbk_get_info(s->dens_tree, &info);
-        s->last_kernel_ms = info.last_kernel_ms;
+        s->last_kernel_ms = info.last_kernel_ms; s->last_call_ms = info.last_call_ms; s->last_launches = info.last_launches; s->last_flagged = info.last_flagged;
         if (W == 1) break;
         DevBuf<unsigned long long> bad(1);
         NBK_CHECK(cudaMemsetAsync(bad.p, 0, sizeof(unsigned long long), st));
@@ -505,7 +510,7 @@ void run_fof(nbk_sharded* s, int criterion, double fdist, const double* params, 
         if (rc != NBK_OK) throw Error(rc, nbk_last_error());
         nbk_info info;
         nbk_get_info(s->fof_tree, &info);
-        s->last_kernel_ms = info.last_kernel_ms;
+        s->last_kernel_ms = info.last_kernel_ms; s->last_call_ms = info.last_call_ms; s->last_launches = info.last_launches; s->last_flagged = 0;
     }
     DevBuf<int32_t> cnt((size_t)n_all);
     NBK_CHECK(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
@@ -562,10 +567,12 @@ void run_fof(nbk_sharded* s, int criterion, double fdist, const double* params, 
         // node names (column 0 of the node table) and both columns of the edge table
         NBK_CHECK(cudaMemcpy2DAsync(ka.p, 8, all_nodes.p, 16, 8, (size_t)nn_all, cudaMemcpyDeviceToDevice, st));
         if (ne_all) NBK_CHECK(cudaMemcpyAsync(ka.p + nn_all, all_edges.p, sizeof(int64_t) * 2 * ne_all, cudaMemcpyDeviceToDevice, st));
+        int key_bits = 8;
+        while (key_bits < 64 && (s->n_global >> key_bits)) key_bits += 8;             // names are global particle ids
         RadixSortPlan<uint64_t> plan(nkeys);
         DevBuf<uint32_t> temp(plan.temp_u32());
         uint64_t* rk; uint32_t* rv;
-        radix_sort_pairs<uint64_t>(ka.p, va.p, kb.p, vb.p, nkeys, 64, true, temp.p, st, &rk, &rv);
+        radix_sort_pairs<uint64_t>(ka.p, va.p, kb.p, vb.p, nkeys, key_bits, true, temp.p, st, &rk, &rv);
         DevBuf<uint32_t> uf((size_t)nkeys + 1), us((size_t)nkeys + 1), scratch(scan_scratch_elems(nkeys + 1));
         sh_unique_flag_kernel<<<div_up(nkeys, 256), 256, 0, st>>>(nkeys, rk, uf.p);
         NBK_CHECK(cudaMemsetAsync(uf.p + nkeys, 0, sizeof(uint32_t), st));
@@ -677,16 +684,14 @@ void stage_local(nbk_sharded* s, const nbk_particles* p) {
     NBK_CHECK(cudaStreamSynchronize(st));
 }
 
-thread_local std::string g_sh_err;
-
 }  // namespace
 
 #define NBK_SH_BEGIN try {
 #define NBK_SH_END                                                                        \
     }                                                                                     \
-    catch (const nbk::Error& e) { nbk_set_last_error(e.what()); return e.code; }          \
-    catch (const std::bad_alloc&) { nbk_set_last_error("host allocation failed"); return NBK_ERR_NOMEM; } \
-    catch (const std::exception& e) { nbk_set_last_error(e.what()); return NBK_ERR_ARG; } \
+    catch (const nbk::Error& e) { nbk::set_last_error(e.what()); return e.code; }          \
+    catch (const std::bad_alloc&) { nbk::set_last_error("host allocation failed"); return NBK_ERR_NOMEM; } \
+    catch (const std::exception& e) { nbk::set_last_error(e.what()); return NBK_ERR_ARG; } \
     return NBK_OK;
 
 extern "C" {
@@ -801,6 +806,16 @@ int nbk_sharded_get_info(const nbk_sharded* s, nbk_sharded_info* info) {
     info->rank = s->comm->rank; info->nranks = s->comm->nranks;
     info->h_knn = s->h_knn; info->ghosts_knn = s->ghosts_knn; info->ghosts_fof = s->ghosts_fof;
     info->density_setups = s->density_setups; info->fof_setups = s->fof_setups; info->last_kernel_ms = s->last_kernel_ms;
+    info->last_call_ms = s->last_call_ms; info->last_launches = s->last_launches; info->last_flagged = s->last_flagged;
+    NBK_SH_END
+}
+
+int nbk_sharded_release(nbk_sharded* s) {
+    NBK_SH_BEGIN
+    NBK_REQUIRE(s != nullptr, NBK_ERR_ARG, "nbk_sharded_release: null argument");
+    CommGuard guard(s->comm);
+    close_density(s);
+    close_fof(s);
     NBK_SH_END
 }
 

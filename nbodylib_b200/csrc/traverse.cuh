@@ -160,18 +160,18 @@ __device__ __forceinline__ void traverse(const NodeLo* __restrict__ nlo, const N
 
 // Bottom-up walk for queries that are particles of the tree: `first` .. `last` (tree positions, inclusive range end
 // exclusive) all lie in one node A0, the deepest node that holds the whole group (found by arithmetic: the tree's shape is a
-// function of (n, bucket) only, left = ceil(size / 2)).  A0's subtree is walked first, then the sibling subtree of A0 and of
+// function of (n, bucket) and the split rule only, split_left).  A0's subtree is walked first, then the sibling subtree of A0 and of
 // every ancestor up to the root: the near field comes first whatever the lanes' bounds are (they may still be infinite), and
 // the upper levels cost one independent box test each instead of a chain of dependent node loads from the root.  The next
 // sibling's record is loaded before the current subtree is walked.
 template <class V>
 __device__ __forceinline__ void traverse_bottom_up(const NodeLo* __restrict__ nlo, const NodeHi* __restrict__ nhi, int bucket, int* stack, V& v,
-                                                   const QueryBox& q, bool on, int64_t ntree, int64_t first, int64_t last) {
+                                                   const QueryBox& q, bool on, int64_t ntree, int aligned, int64_t first, int64_t last) {
     int node = 0;
     {
         int64_t s = 0, e = ntree;
         while (e - s > bucket) {
-            const int64_t mid = s + ((e - s + 1) >> 1);
+            const int64_t mid = s + split_left(e - s, aligned);
             if (last <= mid) { node = 2 * node + 1; e = mid; }
             else if (first >= mid) { node = 2 * node + 2; s = mid; }
             else break;

@@ -34,6 +34,8 @@ struct nbk_tree {
     int8_t* cutdim = nullptr;
     int64_t nslots = 0;
     int depth = 0;                  // deepest level holding nodes
+    int aligned2 = 0;               // split rule of the attached halo tree
+    int aligned = 0;                // 1: warp-aligned shape (NBK_WARP_ALIGNED, split_left in common.cuh), 0: the reference's
     int64_t num_nodes = 0, num_leaves = 0;
 
     // optional second tree over "halo" particles (nbk_attach_halo): its particles are appended to the arrays above at
@@ -158,5 +160,8 @@ struct BallArgs {
     const double* vq = nullptr;     // device, point form with velocities (SearchCriterionTagged(Particle&))
 };
 void launch_ball(nbk_tree& t, BallArgs& a);
+
+// api.cu: what nbk_last_error() reports for the calling thread (libnbk_sharded.so reports through the same call)
+void set_last_error(const char* msg);
 
 }  // namespace nbk

@@ -41,15 +41,17 @@ class CudaEngine:
 
     def build(self, pos, vel, mass, period):
         from .kdtree import KDTree
-        return KDTree(pos, vel, mass, Period=period, device=self.device)
+        from ._lib import WARP_ALIGNED
+        return KDTree(pos, vel, mass, Period=period, device=self.device, flags=WARP_ALIGNED)
 
     def build_with_halo(self, pos, mass, gpos, gmass):
         """owned particles in the main tree, ghosts in an attached second tree (nbk_attach_halo): the main tree's shape
         does not depend on the halo, and a halo that has to be widened does not rebuild it"""
         from .kdtree import KDTree
-        tree = KDTree(pos, None, mass, Period=None, device=self.device)
+        from ._lib import WARP_ALIGNED            # a slab's particle count is arbitrary; nobody inspects these trees' shape
+        tree = KDTree(pos, None, mass, Period=None, device=self.device, flags=WARP_ALIGNED)
         if gpos.shape[0] > 0:
-            halo = KDTree(gpos, None, gmass, Period=None, device=self.device)
+            halo = KDTree(gpos, None, gmass, Period=None, device=self.device, flags=WARP_ALIGNED)
             tree.attach_halo(halo)
         return tree
 
@@ -401,3 +403,124 @@ class ShardedTree:
     def close(self):
         self.close_density()
         self.close_fof()
+
+
+class NativeShardedTree:
+    """The same slab-sharded tree through the C ABI (include/nbk_sharded.h, libnbk_sharded.so): halo exchange, completeness
+    check, return of the scatter terms and the FOF merge all run in C++ over the library's own NCCL communicator.  This class
+    only does the rendezvous (rank 0's 128-byte id is broadcast over the torch.distributed group the process already has, the way
+    an MPI code would MPI_Bcast it) and passes device pointers.  Same call surface as ShardedTree."""
+
+    def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=(1.0, 1.0, 1.0), halo=None, knn_k=64, group=None, device=None):
+        """pos / vel / mass: this rank's particles, CUDA tensors or host tensors (copied to `device`, default the current CUDA
+        device, by the library: pinned host memory makes that copy asynchronous)."""
+        import ctypes as C
+        from . import _lib as L
+        self.L, self.S = L, L.load_sharded()
+        on_device = pos.device.type == "cuda"
+        self.dev = pos.device if on_device else torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.rank = dist.get_rank(group) if rank is None else int(rank)
+        self.world = dist.get_world_size(group) if world is None else int(world)
+        self.comm = self._communicator(group)
+        self.n_owned = int(pos.shape[0])
+        f = pos.dtype
+        if f not in (torch.float32, torch.float64):
+            raise ValueError("positions must be float32 or float64")
+        pos = pos.contiguous()
+        vel = None if vel is None else vel.to(f).contiguous()
+        mass = None if mass is None else mass.to(f).contiguous()
+        es = pos.element_size()
+        p = L.NbkParticles(pos.data_ptr(), 3 * es, 0 if vel is None else vel.data_ptr(), 3 * es, 0 if mass is None else mass.data_ptr(), es, es, 1 if on_device else 0)
+        self.periodic = period is not None
+        b = (C.c_double * 3)(*[float(x) for x in (box if box is not None else (1.0, 1.0, 1.0))])
+        h = C.c_void_p()
+        torch.cuda.synchronize(self.dev)
+        L.check(self.S.nbk_sharded_create(self.comm, C.byref(p), self.n_owned, C.addressof(b), int(self.periodic), int(knn_k), float(halo or 0.0), C.byref(h)))
+        self.h = h
+        self.profile = False
+
+    _comms = {}      # (process group, device) -> nbk_comm*: creating an NCCL communicator costs about a second, trees come and go
+
+    def _communicator(self, group):
+        import ctypes as C
+        L, S = self.L, self.S
+        key = (id(group) if group is not None else None, self.world, self.rank, int(self.dev.index or 0))
+        if key in NativeShardedTree._comms:
+            return NativeShardedTree._comms[key]
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.world > 1:
+            if self.rank == 0:
+                buf = (C.c_ubyte * 128)()
+                L.check(S.nbk_comm_unique_id(C.addressof(buf)))
+                ident = torch.tensor(list(buf), dtype=torch.uint8)
+            ident = ident.to(self.dev) if dist.get_backend(group) == "nccl" else ident
+            dist.broadcast(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ident = ident.cpu()
+        buf = (C.c_ubyte * 128)(*ident.tolist())
+        torch.cuda.synchronize(self.dev)
+        comm = C.c_void_p()
+        L.check(S.nbk_comm_init_rank(self.world, self.rank, C.addressof(buf), int(self.dev.index or 0), C.byref(comm)))
+        NativeShardedTree._comms[key] = comm
+        return comm
+
+    @classmethod
+    def shutdown(cls):
+        """destroy the cached communicators (collective in the NCCL sense: every rank calls it, before the process group goes)"""
+        from . import _lib as L
+        for comm in cls._comms.values():
+            L.load_sharded().nbk_comm_destroy(comm)
+        cls._comms.clear()
+
+    @property
+    def stats(self):
+        i = self.L.NbkShardedInfo()
+        self.L.check(self.S.nbk_sharded_get_info(self.h, i))
+        return {k: getattr(i, k) for k, _ in i._fields_}
+
+    @property
+    def h_knn(self):
+        return self.stats["h_knn"]
+
+    @property
+    def info(self):
+        i = self.L.NbkShardedInfo()
+        self.L.check(self.S.nbk_sharded_get_info(self.h, i))
+        return i
+
+    def close_density(self):
+        self.L.check(self.S.nbk_sharded_release(self.h))
+
+    close_fof = close_density
+
+    def CalcDensity(self, Nsmooth=64, out=None):
+        rho = torch.empty(self.n_owned, dtype=torch.float64, device=self.dev) if out is None else out
+        torch.cuda.current_stream(self.dev).synchronize()
+        self.L.check(self.S.nbk_sharded_calc_density(self.h, int(Nsmooth), rho.data_ptr(), self.L.DEVICE_PTRS))
+        return rho
+
+    def _fof(self, criterion, fdist, params, minnum, order):
+        import ctypes as C
+        g = torch.empty(self.n_owned, dtype=torch.int32, device=self.dev)
+        ng = C.c_int64()
+        prm = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        torch.cuda.current_stream(self.dev).synchronize()
+        self.L.check(self.S.nbk_sharded_fof(self.h, int(criterion), float(fdist), None if prm is None else prm.ctypes.data, int(minnum), int(order),
+                                            g.data_ptr(), C.byref(ng), self.L.DEVICE_PTRS))
+        return g, int(ng.value)
+
+    def FOF(self, fdist, minnum=8, order=0):
+        return self._fof(-1, fdist, None, minnum, order)
+
+    def FOFCriterion(self, cmp, params, minnum=8, order=0):
+        return self._fof(cmp, 0.0, params, minnum, order)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.S.nbk_sharded_destroy(self.h)
+            self.h = None                       # the communicator is cached for the process (destroyed at exit)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

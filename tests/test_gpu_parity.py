@@ -460,7 +460,10 @@ def test_fof_linked_lists(nb):
 
 
 @pytest.mark.parametrize("n,bucket,flags", [(1, 16, 0), (15, 16, 0), (4096, 16, 0), (4097, 16, 0), (8193, 1, 0), (50021, 16, 0), (50021, 3, 1 << 4),
-                                            (300007, 16, 0), (300007, 100, 1 << 4), (131072, 1024, 0)])
+                                            (300007, 16, 0), (300007, 100, 1 << 4), (131072, 1024, 0),
+                                            # warp-aligned shape (NBK_WARP_ALIGNED = 1 << 7): same build rule, split at a multiple of 32
+                                            (33, 16, 1 << 7), (4097, 16, 1 << 7), (4129, 16, 1 << 7), (50021, 16, 1 << 7), (50021, 3, (1 << 7) | (1 << 4)),
+                                            (300007, 40, 1 << 7), (1048576 + 7, 16, 1 << 7), (131072, 16, 1 << 7)])
 def test_build_structure(nb, n, bucket, flags):
     """The rank-space build (global levels + one shared-memory kernel for nodes <= 4096 particles) obeys the reference's
     build rule node by node (KDTree.cxx:459-504, 994, 1012): ranges from left = ceil(size / 2), leaf iff size <= bucket, cut
@@ -491,10 +494,57 @@ def test_build_structure(nb, n, bucket, flags):
         cd = int(np.argmax(ext))                                # first maximum = lowest dimension on ties
         assert c[node] == cd
         mid = lo + (hi - lo + 1) // 2
+        if (flags & (1 << 7)) and hi - lo > 32:                 # include/nbk.h NBK_WARP_ALIGNED: balanced split of the node's 32-particle units
+            assert lo % 32 == 0
+            mid = lo + 32 * (((hi - lo + 31) // 32 + 1) // 2)
         assert P[lo:mid, cd].max() <= P[mid:hi, cd].min()
         stack.append((2 * node + 1, lo, mid))
         stack.append((2 * node + 2, mid, hi))
     assert (seen, leaves) == (nn, nl)
+
+
+@pytest.mark.parametrize("n", [1000, 33333, 200003, (1 << 20) + 77])
+def test_warp_aligned_tree_gives_the_same_results(nb, n):
+    """NBK_WARP_ALIGNED changes the tree's shape (and with it the tree order), never a result: kNN distances and neighbour ids,
+    densities, velocity densities, FOF / FOF6d partitions and ball rows equal those of the reference-shaped tree."""
+    from nbodylib_b200 import _lib as L
+    from nbodylib_b200.synth import clustered_small
+    pos, vel, mass = clustered_small(n, seed=n % 97)
+    ll = 0.25 / n ** (1 / 3)
+    sv2 = ((vel - vel.mean(0)) ** 2).sum(1).mean() / 3.0
+    params = np.zeros(10)
+    params[1] = params[6] = ll * ll
+    params[2] = params[7] = sv2
+    res = []
+    for flags in (0, L.WARP_ALIGNED):
+        for period in (None, np.ones(3)):
+            with nb.KDTree(pos, vel, mass, Period=period, flags=flags) as t:
+                assert t.info.warp_aligned == (1 if flags else 0)
+                order = t.order()
+                inv = np.empty(n, dtype=np.int64)
+                inv[order] = np.arange(n)
+                nn, d2 = t.FindNearestPos(20, ids=True)
+                rho, h = t.CalcDensity(48, want_h=True)
+                vd = t.CalcVelDensity(32, 48)
+                g, ng = t.FOF(ll, 5, 1)
+                g6, ng6 = t.FOFCriterion(nb.FOF6D, params, 5, 1)
+                off, idx = t.SearchBallPosTagged(np.arange(min(n, 4000), dtype=np.int32), (1.5 * ll) ** 2, ids=True)[:2]
+                rows = [np.sort(idx[off[i]:off[i + 1]]) for i in range(len(off) - 1)]
+                # per-particle results are by ID; neighbour lists and ball rows are per tree position: bring them to ID order
+                res.append(dict(nn=nn[inv], d2=d2[inv], rho=rho, h=h, vd=vd, g=g, ng=ng, g6=g6, ng6=ng6, rows={int(order[i]): r for i, r in enumerate(rows)}))
+    for a, b in ((res[0], res[2]), (res[1], res[3])):
+        assert np.array_equal(a["d2"], b["d2"]) and np.array_equal(a["h"], b["h"])
+        same = (a["nn"] == b["nn"]).all(1)
+        for i in np.nonzero(~same)[0]:                      # ties in d2 may be listed in a different order
+            assert np.array_equal(np.sort(a["nn"][i]), np.sort(b["nn"][i])) or len(np.unique(a["d2"][i])) < 20
+        np.testing.assert_allclose(a["rho"], b["rho"], rtol=1e-12)
+        np.testing.assert_allclose(a["vd"], b["vd"], rtol=1e-10)
+        assert a["ng"] == b["ng"] and np.array_equal(canon(a["g"]), canon(b["g"]))
+        assert a["ng6"] == b["ng6"] and np.array_equal(canon(a["g6"]), canon(b["g6"]))
+        common = set(a["rows"]) & set(b["rows"])
+        assert len(common) > 0 or n > 4000
+        for i in common:
+            assert np.array_equal(a["rows"][i], b["rows"][i])
 
 
 @pytest.mark.parametrize("periodic", [False, True])

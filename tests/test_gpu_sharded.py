@@ -24,13 +24,15 @@ def _params6d(pos, vel, n):
     return params
 
 
-def _worker(rank, world, port, tmp, n):
+def _worker(rank, world, port, tmp, n, native):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from nbodylib_b200.sharded import ShardedTree
+        from nbodylib_b200.sharded import NativeShardedTree, ShardedTree
+        if native:                  # the C ABI (include/nbk_sharded.h): exchange and merge in C++ over the library's own NCCL communicator
+            ShardedTree = NativeShardedTree
         from nbodylib_b200.synth import clustered_small
         pos, vel, mass = clustered_small(n, seed=5)
         slab = np.minimum((pos[:, 0] * world).astype(int), world - 1)
@@ -50,8 +52,9 @@ def _worker(rank, world, port, tmp, n):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("native", [False, True], ids=["torch-driver", "c-abi"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_matches_single_gpu(built, world):
+def test_sharded_matches_single_gpu(built, world, native):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import nbodylib_b200 as nb
@@ -59,7 +62,7 @@ def test_sharded_matches_single_gpu(built, world):
     n = 200000
     pos, vel, mass = clustered_small(n, seed=5)
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(_worker, args=(world, 29500 + np.random.randint(0, 2000), tmp, n), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, 29500 + np.random.randint(0, 2000), tmp, n, native), nprocs=world, join=True)
         res = [np.load(os.path.join(tmp, "r%d.npz" % r)) for r in range(world)]
     rho = np.zeros(n)
     g, g6 = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
@@ -100,6 +103,17 @@ def test_world1_driver_and_building_blocks(built):
         roots = t.FOFRoots(ll)
     assert ng == ng1 and np.array_equal(canon(g.cpu().numpy()), canon(g1)) and np.array_equal(np.bincount(g.cpu().numpy())[1:], np.bincount(g1)[1:])
     assert ng6 == nh1 and np.array_equal(canon(g6.cpu().numpy()), canon(h1))
+    # the C ABI with a single rank (no NCCL communicator is created)
+    from nbodylib_b200.sharded import NativeShardedTree
+    nt = NativeShardedTree(torch.from_numpy(pos).to(dev, torch.float32), torch.from_numpy(vel).to(dev, torch.float32), torch.from_numpy(mass).to(dev, torch.float32),
+                           period=np.ones(3), rank=0, world=1, box=(1.0, 1.0, 1.0), knn_k=24)
+    np.testing.assert_allclose(nt.CalcDensity(24).cpu().numpy(), rho, rtol=1e-12)
+    gn, ngn = nt.FOF(ll, 6, 1)
+    g6n, ng6n = nt.FOFCriterion(2, _params6d(pos, vel, n), 6, 0)
+    assert nt.stats["fof_setups"] == 2 and nt.stats["n_global"] == n
+    nt.close()
+    assert ngn == ng1 and np.array_equal(canon(gn.cpu().numpy()), canon(g1)) and np.array_equal(np.bincount(gn.cpu().numpy())[1:], np.bincount(g1)[1:])
+    assert ng6n == nh1 and np.array_equal(canon(g6n.cpu().numpy()), canon(h1))
     # roots: every member of a group shares one representative, which is a member itself
     assert np.array_equal(roots[roots], roots)
     sel = g1 > 0

@@ -216,6 +216,19 @@ def test_cabi_exports_every_declared_symbol(built):
         assert hasattr(lib, name), "libnbk.so does not export %s" % name
     from nbodylib_b200 import _lib
     assert sorted(_lib.EXPORTS) == declared
+    # the sharded layer's own library (include/nbk_sharded.h): loads without a GPU, exports every declared entry point, and a
+    # call without a device fails with a status code instead of computing anything on the host
+    hdr = open(os.path.join(ROOT, "include", "nbk_sharded.h")).read()
+    declared = sorted(set(re.findall(r"\b(nbk_(?:comm|sharded)_[a-z0-9_]+)\s*\(", hdr)))
+    S = _lib.load_sharded()
+    for name in declared:
+        assert hasattr(S, name), "libnbk_sharded.so does not export %s" % name
+    assert sorted(_lib.SHARDED_EXPORTS) == declared
+    import torch
+    if not torch.cuda.is_available():
+        comm = ctypes.c_void_p()
+        assert S.nbk_comm_init_rank(1, 0, ctypes.addressof((ctypes.c_ubyte * 128)()), 0, ctypes.byref(comm)) == -2
+        assert not comm.value and b"cuda" in _lib.load().nbk_last_error().lower()
 
 
 def test_no_cpu_fallback_without_device(built):
