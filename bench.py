@@ -618,9 +618,15 @@ def main():
             "wall_ms_per_step": wall * 1e3 / args.steps, "library_ms_per_step": float(np.mean(call_ms)),
             "cpu_baseline": cpu, "e2e": e2e, "e2e_aos": e2e_aos, "gpu_launches": launches, "clocks": clocks, "checked": checked, "rows": rows, "extra": extra,
         }
-        for r in rows.values():
+        rt = os.path.join(ROOT, "profiles", "row_traffic.json")
+        row_facts = json.load(open(rt)) if os.path.exists(rt) else {}
+        for name, r in rows.items():
             if "roofline" in r:
                 r["roofline"]["peak_source"] = peak_src
+                f = row_facts.get(name)
+                if f:       # measured DRAM bytes per particle of the row's kernel(s) (ncu, 256^3 capture) scaled to this run's particle count
+                    r["roofline"]["traffic"] = f["dram_bytes_per_particle"] * n
+                    r["roofline"]["ncu"] = f
         emit(line)
     if world > 1:
         _sh.NativeShardedTree.shutdown()
