@@ -101,8 +101,13 @@ def shim_e2e(pos, vel, mass, k, period, reps):
                         "array permuted into tree order], CalcDensity(%d) [rho into the particles], ~KDTree [order restored]" % k}
 
 
-def workload_name(ng, nh):
-    return "clustered periodic box %d^3 per GPU (ZA lattice + %d Plummer halos), KDTree bucket=16, CalcDensity(%d): kNN + SPH density" % (ng, nh, K_NN)
+def workload_name(ng, nh, world=1):
+    """config.workload of both arms (the reference arm times a bounded sample of the same box on the host cores)"""
+    if world == 1:
+        return "clustered periodic box %d^3 per GPU (ZA lattice + %d Plummer halos), KDTree bucket=16, CalcDensity(%d): kNN + SPH density" % (ng, nh, K_NN)
+    dims = SHARD_DIMS[world]
+    return ("one clustered periodic box of %d x %d x %d lattice cells (%d particles, ZA + %d Plummer halos) cut into %d slabs along x, one per GPU, "
+            "KDTree bucket=16, CalcDensity(%d): kNN + SPH density" % (dims[0] * ng, dims[1] * ng, dims[2] * ng, world * ng ** 3, nh * world, world, K_NN))
 
 
 def host_cores():
@@ -193,7 +198,7 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "knn_density_particles_per_s", "value": val, "unit": "particles/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "timed_passes": len(leg["seconds"]), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(ng, max(8, min(8192, ng ** 3 // 16384))), "particles_per_gpu": ng ** 3, "k": K_NN},
+        "config": {"workload": workload_name(ng, max(8, min(8192, ng ** 3 // 16384)), world), "particles_per_gpu": ng ** 3, "particles_total": world * ng ** 3, "k": K_NN},
         "cpu_baseline": {"value": val, "unit": "particles/s", "cores": leg["cores"], "kind": leg["kind"], "sample": sample,
                          "build_seconds_sample": leg["build_seconds"]},
         "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -258,7 +263,10 @@ def main():
     dims = SHARD_DIMS[world]
     box = np.array(dims, dtype=np.float64)
     if world > 1:
-        pos, vel, mass = clustered_box(ng, seed=2025, nhalo=nh * world, device="cuda", dims=dims, slab=(rank, world))
+        # slab faces at the x quantiles (equal particle counts, the load-balanced decomposition a production code uses); NBK_SLABS=width
+        # cuts equal-width slabs instead (then the slab holding the largest halo has ~20 % more particles at 8 ranks)
+        slabs = "equal_width" if os.environ.get("NBK_SLABS", "count") == "width" else "equal_count"
+        pos, vel, mass, edges = clustered_box(ng, seed=2025, nhalo=nh * world, device="cuda", dims=dims, slab=(rank, world, slabs), return_edges=True)
         torch.cuda.empty_cache()
     else:
         pos, vel, mass = clustered_box(ng, seed=2025, nhalo=nh, device="cuda")
@@ -285,7 +293,7 @@ def main():
         # communicator) unless NBK_SHARDED_DRIVER=torch selects the torch.distributed driver of the same algorithm
         from nbodylib_b200 import sharded as _sh
         ShardedTree = _sh.ShardedTree if os.environ.get("NBK_SHARDED_DRIVER", "native") == "torch" else _sh.NativeShardedTree
-        tree = ShardedTree(pos, vel, mass, period=period, rank=rank, world=world, box=box)
+        tree = ShardedTree(pos, vel, mass, period=period, rank=rank, world=world, box=box, edges=edges)
     else:
         tree = KDTree(pos, vel, mass, Period=period, device=local)
     info = tree.info
@@ -453,7 +461,12 @@ def main():
             extra["fof_error"] = repr(ex)[:300]
         extra["sharded_rank0"] = dict(tree.stats)
         extra["sharded_driver"] = "C ABI (libnbk_sharded.so, NCCL from C++)" if ShardedTree is _sh.NativeShardedTree else "torch.distributed driver (nbodylib_b200/sharded.py)"
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"particles": int(tree.n_owned), "library_ms_per_step": float(np.mean(call_ms))})
+        extra["per_rank"] = per_rank
         extra["box"] = list(map(float, box))
+        extra["slab_faces_x"] = [float(e) for e in edges]
+        extra["decomposition"] = "%d x-slabs, faces at the x quantiles (equal particle counts)" % world if slabs == "equal_count" else "%d x-slabs of equal width" % world
         extra["particles_total"] = n_total
     tree.close()
 
@@ -470,10 +483,10 @@ def main():
             barrier(); t1 = time.perf_counter()
             if ShardedTree is _sh.NativeShardedTree:            # host pointers straight into the C ABI
                 dp = dm = None
-                st = ShardedTree(hp, None, hm, period=period, rank=rank, world=world, box=box, device=local)
+                st = ShardedTree(hp, None, hm, period=period, rank=rank, world=world, box=box, device=local, edges=edges)
             else:
                 dp, dm = hp.to("cuda", non_blocking=True), hm.to("cuda", non_blocking=True)
-                st = ShardedTree(dp, None, dm, period=period, rank=rank, world=world, box=box)
+                st = ShardedTree(dp, None, dm, period=period, rank=rank, world=world, box=box, edges=edges)
             r = st.CalcDensity(K_NN)
             out.copy_(r)
             barrier()
@@ -603,9 +616,7 @@ def main():
             "metric": "knn_density_particles_per_s", "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(ng, nh) if world == 1 else
-                       "one clustered periodic box of %d x %d x %d lattice cells (%d particles, ZA + %d Plummer halos) cut into %d slabs along x, one per GPU, "
-                       "KDTree bucket=16, CalcDensity(%d): kNN + SPH density" % (dims[0] * ng, dims[1] * ng, dims[2] * ng, n_total, nh * world, world, K_NN),
+            "config": {"workload": workload_name(ng, nh, world),
                        "particles_per_gpu": n_total // world, "particles_total": n_total, "k": K_NN,
                        "storage": "fp32 coordinates (exact), fp32 screening keys with a certified error band, fp64 distances and sums for the results",
                        "l2": "inputs (%.1f GB) exceed L2, no flush needed" % (n * 16 / 1e9)},

@@ -150,6 +150,18 @@ int main() {
             }
             printf("smoothed velocity dispersion: mean trace %.4g\n", tr / ((N + 996) / 997));
             if (!(tr > 0)) bad++;
+            // higher moments: finite, and the reference's kurtosis form carries -3 per contribution (about 2 x 32 of them)
+            Coordinate* sk = tree.CalcSmoothVelSkew(sv, sd, 32);
+            Coordinate* ku = tree.CalcSmoothVelKurtosis(sv, sd, 32);
+            double kmean = 0;
+            for (Int_t i = 0; i < N; i += 997) {
+                for (int j = 0; j < 3; j++) if (!std::isfinite(sk[i][j]) || !std::isfinite(ku[i][j])) bad++;
+                kmean += ku[i][0];
+            }
+            kmean /= ((N + 996) / 997);
+            printf("smoothed velocity kurtosis (reference form): mean %.4g\n", kmean);
+            if (!(kmean < -100.0 && kmean > -300.0)) bad++;
+            delete[] sk; delete[] ku;
             delete[] sv; delete[] sd;
         }
         printf("single-target density vs CalcSmoothLocalValue: worst relative difference %.3g\n", worst);

@@ -205,6 +205,13 @@ int nbk_calc_veldensity_points(nbk_tree* t, int nsmooth, int nsearch, int64_t m,
  * reference's densityset != 1).  smvel: the result of nbk_calc_smooth_vel.  All arrays by ID (tree order with NBK_TREE_ORDER). */
 int nbk_calc_smooth_vel(nbk_tree* t, int nsmooth, const double* rho, double* smvel, int flags);
 int nbk_calc_smooth_veldisp(nbk_tree* t, int nsmooth, const double* rho, const double* smvel, double* smveldisp, int flags);
+/* Replace KDTree::CalcSmoothVelSkew(smvel, smveldisp, Nsmooth, ...) and KDTree::CalcSmoothVelKurtosis(...)
+ * (KDCalcSmoothQuantities.cxx:617-765): per velocity component k, the kernel-smoothed third / fourth power of (v_k - smoothed mean
+ * of the receiving particle) in units of the receiver's dispersion, sigma_kk^1.5 / sigma_kk^2 (n x 3); same symmetric gather +
+ * scatter and weights as CalcSmoothVelDisp.  The reference subtracts 3 from EVERY kurtosis contribution (2 Nsmooth per particle
+ * on average) rather than once; that is reproduced.  smvel / smveldisp: results of the two calls above. */
+int nbk_calc_smooth_velskew(nbk_tree* t, int nsmooth, const double* rho, const double* smvel, const double* smveldisp, double* smvelskew, int flags);
+int nbk_calc_smooth_velkurtosis(nbk_tree* t, int nsmooth, const double* rho, const double* smvel, const double* smveldisp, double* smvelkurt, int flags);
 
 /* Optional FOF by-products in tree-index space (reference KDFOF.cxx:52-55: pHead,pNext,pTail,pLen).
  * Any pointer may be NULL.  head/next/tail have n entries: the members of a group are chained in ascending tree

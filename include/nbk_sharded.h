@@ -10,9 +10,11 @@
  * Results are those of ONE tree over all ranks' particles: densities to rounding (the order of the fp64 sums differs), FOF
  * partitions identical, group ids one numbering for the whole job.
  *
- * Decomposition: the global box [0,box[0]) x [0,box[1]) x [0,box[2]) is cut into `nranks` slabs of equal width along x; rank
- * r passes the particles with x in [r, r+1) * box[0] / nranks, in GLOBAL coordinates.  Global particle id = position in
- * the concatenation of the ranks' arrays in rank order.
+ * Decomposition: the global box [0,box[0]) x [0,box[1]) x [0,box[2]) is cut into `nranks` slabs along x with faces at
+ * slab_edges[0] = 0 < slab_edges[1] < ... < slab_edges[nranks] = box[0] (NULL: equal widths); rank r passes the particles with
+ * slab_edges[r] <= x < slab_edges[r+1], in GLOBAL coordinates.  The caller owns the decomposition, like VELOCIraptor owns its MPI
+ * domains: equal widths, or faces at the x quantiles for equal particle counts.  Global particle id = position in the
+ * concatenation of the ranks' arrays in rank order.
  *
  * Every call is COLLECTIVE: all ranks of the communicator make it, with the same arguments apart from the particle data.
  * Errors: nbk_status codes of nbk.h, text from nbk_last_error().  A rank that fails leaves its peers waiting in NCCL, like
@@ -41,10 +43,11 @@ int nbk_comm_destroy(nbk_comm* c);
 /* This rank's slab.  p: its particles (host or device, any stride; copied -- the caller's arrays are not kept), n_local >= 1.
  * periodic != 0: FOF wraps with the periods box[] (CalcDensity never does: the reference's Calc* family ignores the period,
  * SURVEY.md quirk Q2).  knn_k: the Nsmooth the density halo is sized for (<= 0: 64); halo > 0 overrides the initial halo
- * width (it is widened automatically until every owned k-ball is complete).  Mirrors NBody::KDTree's constructor for
+ * width (it is widened automatically until every owned k-ball is complete).  With three or more ranks a halo must stay below the
+ * narrowest slab's width (particles two slabs away would be missing): such calls fail with NBK_ERR_ARG on every rank.  Mirrors NBody::KDTree's constructor for
  * TPHYS / KEPAN / bucket 16, the configuration of the headline workload. */
-int nbk_sharded_create(nbk_comm* c, const nbk_particles* p, int64_t n_local, const double box[3], int periodic, int knn_k,
-                       double halo, nbk_sharded** out);
+int nbk_sharded_create(nbk_comm* c, const nbk_particles* p, int64_t n_local, const double box[3], const double* slab_edges,
+                       int periodic, int knn_k, double halo, nbk_sharded** out);
 int nbk_sharded_destroy(nbk_sharded* s);
 
 /* KDTree::CalcDensity(nsmooth) over the global particle set; rho[n_local] for this rank's particles in input order

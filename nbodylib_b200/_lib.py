@@ -44,7 +44,7 @@ EXPORTS = [
     "nbk_search_criterion_particles", "nbk_search_criterion_points", "nbk_calc_density_particles",
     "nbk_calc_veldensity_particles", "nbk_calc_density_points", "nbk_calc_veldensity_points",
     "nbk_knn_filtered_particles", "nbk_knn_filtered_points", "nbk_calc_smooth_vel", "nbk_calc_smooth_veldisp",
-    "nbk_set_option", "nbk_fof_roots", "nbk_union_pairs",
+    "nbk_set_option", "nbk_fof_roots", "nbk_union_pairs", "nbk_calc_smooth_velskew", "nbk_calc_smooth_velkurtosis",
 ]
 
 SHARDED_PATH = os.path.join(HERE, "libnbk_sharded.so")
@@ -78,7 +78,7 @@ def load_sharded():
     S.nbk_comm_unique_id.argtypes = [vp]
     S.nbk_comm_init_rank.argtypes = [i32, i32, vp, i32, C.POINTER(vp)]
     S.nbk_comm_destroy.argtypes = [vp]
-    S.nbk_sharded_create.argtypes = [vp, C.POINTER(NbkParticles), i64, vp, i32, i32, dbl, C.POINTER(vp)]
+    S.nbk_sharded_create.argtypes = [vp, C.POINTER(NbkParticles), i64, vp, vp, i32, i32, dbl, C.POINTER(vp)]
     S.nbk_sharded_destroy.argtypes = [vp]
     S.nbk_sharded_calc_density.argtypes = [vp, i32, vp, i32]
     S.nbk_sharded_fof.argtypes = [vp, i32, dbl, vp, i32, i32, vp, C.POINTER(i64), i32]
@@ -114,6 +114,8 @@ def load():
     L.nbk_knn_filtered_points.argtypes = [vp, i32, i64, vp, vp, i32, vp, vp, vp, vp, i32]
     L.nbk_calc_smooth_vel.argtypes = [vp, i32, vp, vp, i32]
     L.nbk_calc_smooth_veldisp.argtypes = [vp, i32, vp, vp, vp, i32]
+    L.nbk_calc_smooth_velskew.argtypes = [vp, i32, vp, vp, vp, vp, i32]
+    L.nbk_calc_smooth_velkurtosis.argtypes = [vp, i32, vp, vp, vp, vp, i32]
     L.nbk_ball_particles.argtypes = [vp, dbl, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]
     L.nbk_ball_points.argtypes = [vp, dbl, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]
     L.nbk_search_criterion_particles.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, i64, C.POINTER(i64), i32]

@@ -749,13 +749,15 @@ int nbk_smoothing_scale(nbk_tree* t, int nsmooth, double* hsm, int flags) {
 }
 
 // CalcSmoothVel / CalcSmoothVelDisp: rows of `width` doubles per particle (3: mean velocity, 9: dispersion tensor)
-static void smooth_moments_call(nbk_tree* t, int k, const double* rho, const double* smvel, double* out, int width, int flags) {
+// width 3: mean velocity (moment 1) or skewness / kurtosis (moment 3 / 4, which also read the dispersions); width 9: dispersion
+static void smooth_moments_call(nbk_tree* t, int k, const double* rho, const double* smvel, double* out, int width, int flags, int moment = 1,
+                                const double* smdisp = nullptr) {
     require_knn_tree(t);
     require_no_halo(t, "CalcSmoothVel*");
     NBK_REQUIRE(t->treetype == NBK_TPHYS, NBK_ERR_UNSUPPORTED, "CalcSmoothVel* need a physical tree");      // KDCalcSmoothQuantities.cxx:488-491
     NBK_REQUIRE(t->sec != nullptr, NBK_ERR_ARG, "CalcSmoothVel* need velocities");
     NBK_REQUIRE(k >= 1 && k < t->n, NBK_ERR_ARG, "smoothing needs 1 <= Nsmooth < numparts");
-    NBK_REQUIRE(out && (width == 3 || smvel), NBK_ERR_ARG, "CalcSmoothVel*: null argument");
+    NBK_REQUIRE(out && (width == 3 || smvel) && (moment == 1 || (smvel && smdisp)), NBK_ERR_ARG, "CalcSmoothVel*: null argument");
     TreeGuard guard(t);
     const int64_t n = t->n;
     const bool dev = flags & NBK_DEVICE_PTRS, tree_order = flags & NBK_TREE_ORDER;
@@ -773,7 +775,7 @@ static void smooth_moments_call(nbk_tree* t, int k, const double* rho, const dou
         gather_rows_f64_kernel<<<div_up(n * w, tb), tb, 0, t->stream>>>(n, w, t->order, d, tree.p);
         return tree.p;
     };
-    DevBuf<double> rho_h, rho_t, sv_h, sv_t, acc((size_t)n * width), out_id;
+    DevBuf<double> rho_h, rho_t, sv_h, sv_t, sd_h, sd_t, acc((size_t)n * width), out_id;
     KnnArgs a;
     a.k = k; a.mode = 0; a.q0 = 0; a.q1 = n; a.periodic = false;      // quirk Q2
     CallTimer tm(*t);
@@ -788,9 +790,12 @@ static void smooth_moments_call(nbk_tree* t, int k, const double* rho, const dou
         launch_knn(*t, d);
         a.rho_in = rho_t.p;
     }
-    if (width == 9) a.smvel_in = stage_rows(smvel, 3, sv_h, sv_t);
+    if (width == 9 || moment > 1) a.smvel_in = stage_rows(smvel, 3, sv_h, sv_t);
+    if (moment > 1) { a.smdisp_in = stage_rows(smdisp, 9, sd_h, sd_t); a.moment = moment; }
     NBK_CHECK(cudaMemsetAsync(acc.p, 0, acc.bytes(), t->stream));
-    if (width == 3) a.smvel_out = acc.p; else a.smdisp_out = acc.p;
+    if (moment > 1) a.smhigh_out = acc.p;
+    else if (width == 3) a.smvel_out = acc.p;
+    else a.smdisp_out = acc.p;
     const int64_t before = t->last_launches;
     launch_knn(*t, a);
     t->last_launches += before;
@@ -820,6 +825,19 @@ int nbk_calc_smooth_veldisp(nbk_tree* t, int nsmooth, const double* rho, const d
     NBK_API_BEGIN
     NBK_REQUIRE(t && smvel && smveldisp, NBK_ERR_ARG, "nbk_calc_smooth_veldisp: null argument");
     smooth_moments_call(t, nsmooth, rho, smvel, smveldisp, 9, flags);
+    NBK_API_END
+}
+
+int nbk_calc_smooth_velskew(nbk_tree* t, int nsmooth, const double* rho, const double* smvel, const double* smveldisp, double* smvelskew, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && smvel && smveldisp && smvelskew, NBK_ERR_ARG, "nbk_calc_smooth_velskew: null argument");
+    smooth_moments_call(t, nsmooth, rho, smvel, smvelskew, 3, flags, 3, smveldisp);
+    NBK_API_END
+}
+int nbk_calc_smooth_velkurtosis(nbk_tree* t, int nsmooth, const double* rho, const double* smvel, const double* smveldisp, double* smvelkurt, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && smvel && smveldisp && smvelkurt, NBK_ERR_ARG, "nbk_calc_smooth_velkurtosis: null argument");
+    smooth_moments_call(t, nsmooth, rho, smvel, smvelkurt, 3, flags, 4, smveldisp);
     NBK_API_END
 }
 

@@ -62,6 +62,7 @@ struct KnnParams {
     const int32_t* cand_excl; int crit_mode; double cp0, cp1;
     // smoothed velocity moments (CalcSmoothVel / CalcSmoothVelDisp): densities in, accumulators out, all tree order
     const double* rho_in; const double* smvel_in; double* smvel_out; double* smdisp_out;
+    const double* smdisp_in; double* smhigh_out; int moment;      // skewness (3) / kurtosis (4) about the receiver's mean, in units of its dispersion
     int64_t n_tree;                                   // particles of the main tree (= n unless a halo is attached)
     int aligned;                                      // the main tree's split rule (split_left)
     int tr_max;                                       // density kernel: transposed screening threshold (lanes needing a tile)
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
         }
         atomicAdd(&prm.rho[qi], acc);
     }
-    if (prm.smvel_out || prm.smdisp_out) {
+    if (prm.smvel_out || prm.smdisp_out || prm.smhigh_out) {
         // CalcSmoothVel / CalcSmoothVelDisp (KDCalcSmoothQuantities.cxx:480-614): symmetric gather + scatter with weights
         // 0.5 * W(r_ij, h_i) * m / rho of the CONTRIBUTING particle; the dispersion is taken about the smoothed mean velocity
         // of the RECEIVING particle (:594-611)
@@ -309,7 +310,14 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
         const double vi[3] = {(double)vq4.x, (double)vq4.y, (double)vq4.z};
         const double wi = prm.mass[qi] / prm.rho_in[qi];        // temp = Wij / rho * m, evaluated as Wij * (m / rho): one extra rounding
         double mi[3] = {0, 0, 0};
-        if (prm.smdisp_out) { mi[0] = prm.smvel_in[3 * qi]; mi[1] = prm.smvel_in[3 * qi + 1]; mi[2] = prm.smvel_in[3 * qi + 2]; }
+        if (prm.smdisp_out || prm.smhigh_out) { mi[0] = prm.smvel_in[3 * qi]; mi[1] = prm.smvel_in[3 * qi + 1]; mi[2] = prm.smvel_in[3 * qi + 2]; }
+        // CalcSmoothVelSkew / CalcSmoothVelKurtosis (KDCalcSmoothQuantities.cxx:617-765): per component k the third / fourth power of
+        // (v - smoothed mean of the RECEIVER) over the receiver's dispersion sigma_kk^1.5 / sigma_kk^2; the kurtosis form subtracts 3
+        // from EVERY contribution (:745,751), which is reproduced
+        double si[3] = {1, 1, 1};
+        if (prm.smhigh_out) {
+            for (int a = 0; a < 3; a++) { const double d = prm.smdisp_in[9 * qi + 4 * a]; si[a] = prm.moment == 3 ? pow(d, 1.5) : d * d; }
+        }
         double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int s = 0; s < kc; s++) {
             int id = v.hp.i(s);
@@ -323,6 +331,18 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
             const double ti = Wij * wi;
             if (prm.smvel_out) {
                 for (int a = 0; a < 3; a++) { acc[a] += tj * vj[a]; atomicAdd(&prm.smvel_out[3 * (int64_t)id + a], ti * vi[a]); }
+            } else if (prm.smhigh_out) {
+                for (int a = 0; a < 3; a++) {
+                    const double dj = vj[a] - mi[a], di = vi[a] - prm.smvel_in[3 * (int64_t)id + a];
+                    const double dd = prm.smdisp_in[9 * (int64_t)id + 4 * a];
+                    if (prm.moment == 3) {
+                        acc[a] += tj * dj * dj * dj / si[a];
+                        atomicAdd(&prm.smhigh_out[3 * (int64_t)id + a], ti * di * di * di / pow(dd, 1.5));
+                    } else {
+                        acc[a] += tj * dj * dj * dj * dj / si[a] - 3.;
+                        atomicAdd(&prm.smhigh_out[3 * (int64_t)id + a], ti * di * di * di * di / (dd * dd) - 3.);
+                    }
+                }
             } else {
                 const double mj[3] = {prm.smvel_in[3 * (int64_t)id], prm.smvel_in[3 * (int64_t)id + 1], prm.smvel_in[3 * (int64_t)id + 2]};
                 for (int a = 0; a < 3; a++)
@@ -333,6 +353,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
             }
         }
         if (prm.smvel_out) { for (int a = 0; a < 3; a++) atomicAdd(&prm.smvel_out[3 * qi + a], acc[a]); }
+        else if (prm.smhigh_out) { for (int a = 0; a < 3; a++) atomicAdd(&prm.smhigh_out[3 * qi + a], acc[a]); }
         else { for (int a = 0; a < 9; a++) atomicAdd(&prm.smdisp_out[9 * qi + a], acc[a]); }
     }
     if (prm.rho && prm.veldens_k > 0) {
@@ -911,6 +932,7 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.gather = a.gather ? 1 : 0; p.vq = a.vq;
     p.cand_excl = a.cand_excl; p.crit_mode = a.crit_mode; p.cp0 = a.cp0; p.cp1 = a.cp1;
     p.rho_in = a.rho_in; p.smvel_in = a.smvel_in; p.smvel_out = a.smvel_out; p.smdisp_out = a.smdisp_out;
+    p.smdisp_in = a.smdisp_in; p.smhigh_out = a.smhigh_out; p.moment = a.moment;
     p.k = a.k;
     p.periodic = a.periodic; p.strict = a.strict; p.tree_form = a.tree_form;
     for (int d = 0; d < 3; d++) p.period[d] = t.period[d];
@@ -973,12 +995,13 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     t.last_launches = 0;
     t.last_flagged = 0;
     if (a.crit_mode == 4) NBK_REQUIRE(p.V != nullptr && (a.mode == 0 || a.vq != nullptr), NBK_ERR_ARG, "FOF6d-filtered search needs velocities");
-    if (a.smvel_out || a.smdisp_out) {
+    if (a.smvel_out || a.smdisp_out || a.smhigh_out) {
         NBK_REQUIRE(a.mode == 0 && !a.qlist && a.rho_in && p.V, NBK_ERR_ARG, "smoothed velocity moments need particle queries, densities and velocities");
         NBK_REQUIRE(!a.smdisp_out || a.smvel_in, NBK_ERR_ARG, "CalcSmoothVelDisp needs the smoothed mean velocities");
+        NBK_REQUIRE(!a.smhigh_out || (a.smvel_in && a.smdisp_in && (a.moment == 3 || a.moment == 4)), NBK_ERR_ARG, "CalcSmoothVelSkew / Kurtosis need the smoothed mean velocities and dispersions");
     }
     const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm) && !a.gather && !a.qlist && !a.cand_excl && !a.crit_mode &&
-                             !a.smvel_out && !a.smdisp_out;
+                             !a.smvel_out && !a.smdisp_out && !a.smhigh_out;
     if (smooth_only && !g_knn_exact && ap_range_ok(t)) {
         // ---- append + prune kernel, exact kernel for the flagged queries -----------------------------------------
         p.kcap = a.k;

@@ -742,7 +742,8 @@ int nbk_comm_destroy(nbk_comm* c) {
     NBK_SH_END
 }
 
-int nbk_sharded_create(nbk_comm* c, const nbk_particles* p, int64_t n_local, const double box[3], int periodic, int knn_k, double halo, nbk_sharded** out) {
+int nbk_sharded_create(nbk_comm* c, const nbk_particles* p, int64_t n_local, const double box[3], const double* slab_edges, int periodic, int knn_k, double halo,
+                       nbk_sharded** out) {
     NBK_SH_BEGIN
     NBK_REQUIRE(c && p && p->pos && box && out && n_local >= 1, NBK_ERR_ARG, "nbk_sharded_create: bad argument");
     NBK_REQUIRE(p->real_bytes == 4 || p->real_bytes == 8, NBK_ERR_ARG, "nbk_sharded_create: real_bytes must be 4 or 8");
@@ -751,9 +752,19 @@ int nbk_sharded_create(nbk_comm* c, const nbk_particles* p, int64_t n_local, con
     std::unique_ptr<nbk_sharded> s(new nbk_sharded);
     s->comm = c; s->n = n_local; s->real_bytes = p->real_bytes; s->periodic = periodic != 0;
     for (int d = 0; d < 3; d++) s->box[d] = box[d];
-    s->slab_width = box[0] / c->nranks;
-    s->x0 = box[0] * c->rank / c->nranks;
-    s->x1 = box[0] * (c->rank + 1) / c->nranks;
+    if (slab_edges) {
+        s->slab_width = box[0];
+        for (int r = 0; r < c->nranks; r++) {
+            NBK_REQUIRE(slab_edges[r + 1] > slab_edges[r], NBK_ERR_ARG, "nbk_sharded_create: slab_edges must ascend strictly");
+            s->slab_width = std::min(s->slab_width, slab_edges[r + 1] - slab_edges[r]);      // the narrowest slab bounds the halo
+        }
+        NBK_REQUIRE(slab_edges[0] == 0.0 && slab_edges[c->nranks] == box[0], NBK_ERR_ARG, "nbk_sharded_create: slab_edges must run from 0 to box[0]");
+        s->x0 = slab_edges[c->rank]; s->x1 = slab_edges[c->rank + 1];
+    } else {
+        s->slab_width = box[0] / c->nranks;
+        s->x0 = box[0] * c->rank / c->nranks;
+        s->x1 = box[0] * (c->rank + 1) / c->nranks;
+    }
     if (p->real_bytes == 4) stage_local<float>(s.get(), p); else stage_local<double>(s.get(), p);
     std::vector<int64_t> counts = gather_pairs(c, n_local, 0);
     for (int r = 0; r < c->nranks; r++) { if (r < c->rank) s->gid0 += counts[2 * (size_t)r]; s->n_global += counts[2 * (size_t)r]; }

@@ -122,6 +122,9 @@ struct KnnArgs {
     const double* smvel_in = nullptr;    // smoothed mean velocities (n x 3), input of the dispersion
     double* smvel_out = nullptr;         // n x 3
     double* smdisp_out = nullptr;        // n x 9 (row-major 3x3)
+    const double* smdisp_in = nullptr;   // dispersions (n x 9), input of the skewness / kurtosis
+    double* smhigh_out = nullptr;        // n x 3: skewness (moment 3) or kurtosis (moment 4)
+    int moment = 0;
 };
 void launch_knn(nbk_tree& t, const KnnArgs& a);
 bool set_knn_option(const char* name, int64_t value);   // nbk_set_option names starting with "knn_"

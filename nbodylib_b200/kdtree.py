@@ -411,6 +411,24 @@ class KDTree:
         L.check(self._lib.nbk_calc_smooth_veldisp(self._h, int(Nsmooth), _ptr(r), _ptr(sv), _ptr(out), 0))
         return out
 
+    def _higher(self, call, smvel, smveldisp, Nsmooth, rho):
+        r = None if rho is None else np.ascontiguousarray(rho, dtype=np.float64)
+        sv = np.ascontiguousarray(smvel, dtype=np.float64)
+        sd = np.ascontiguousarray(smveldisp, dtype=np.float64)
+        assert sv.shape == (self.n, 3) and sd.shape == (self.n, 3, 3)
+        out = np.empty((self.n, 3))
+        L.check(call(self._h, int(Nsmooth), _ptr(r), _ptr(sv), _ptr(sd), _ptr(out), 0))
+        return out
+
+    def CalcSmoothVelSkew(self, smvel, smveldisp, Nsmooth=64, rho=None):
+        """KDTree::CalcSmoothVelSkew(smvel, smveldisp, Nsmooth, ...) (KDCalcSmoothQuantities.cxx:617-689): (n, 3) by ID."""
+        return self._higher(self._lib.nbk_calc_smooth_velskew, smvel, smveldisp, Nsmooth, rho)
+
+    def CalcSmoothVelKurtosis(self, smvel, smveldisp, Nsmooth=64, rho=None):
+        """KDTree::CalcSmoothVelKurtosis(smvel, smveldisp, Nsmooth, ...) (KDCalcSmoothQuantities.cxx:692-765): (n, 3) by ID; like the
+        reference, 3 is subtracted from every neighbour contribution."""
+        return self._higher(self._lib.nbk_calc_smooth_velkurtosis, smvel, smveldisp, Nsmooth, rho)
+
     def CalcSmoothingScale(self, Nsmooth=64):
         """hi = 0.5*sqrt(d2 of the Nsmooth-th neighbour) (KDCalcSmoothQuantities.cxx:260)."""
         h = np.empty(self.n)

@@ -5,7 +5,7 @@ The reference has no distributed code: VELOCIraptor does its own 
 builds one local `KDTree` per rank.  This module is the B200 replacement for that outer layer on one node:
 
 * **Decomposition.**  The global box (Lx, Ly, Lz) is cut into `world` slabs along x; rank r owns the particles with
-  x in [r, r+1) * Lx / world, given in GLOBAL coordinates.  Nothing is ever gathered on one rank, coordinates are never
+  x in [r, r+1) * Lx / world (or between the caller's slab faces `edges`, e.g. the x quantiles for equal counts), given in GLOBAL coordinates.  Nothing is ever gathered on one rank, coordinates are never
   shifted (ghosts keep their owners' exact values, so fp32-exact inputs stay fp32-exact and the local trees keep the
   fp32 storage and the screened kernels).
 * **Halo exchange** (the only data-path communication): each rank sends the particles within `h` of a slab face to the
@@ -73,7 +73,7 @@ class CudaEngine:
 
 
 class ShardedTree:
-    def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=None, halo=None, knn_k=64, engine=None, group=None):
+    def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=None, halo=None, knn_k=64, engine=None, group=None, edges=None):
         """pos/vel/mass: this rank's particles (torch tensors on the rank's device, fp32 or fp64), GLOBAL coordinates inside
         this rank's slab of `box` = (Lx, Ly, Lz).  period: None -> open box; anything else -> the global box is periodic with
         periods `box` (FOF only; Calc* never wrap)."""
@@ -85,9 +85,12 @@ class ShardedTree:
         self.periodic = period is not None
         W = self.world
         self.box = np.asarray(box if box is not None else (1.0, 1.0, 1.0), dtype=np.float64)
-        self.x0 = self.box[0] * self.rank / W
-        self.x1 = self.box[0] * (self.rank + 1) / W
-        self.slab_width = float(self.box[0] / W)
+        # slab faces: equal widths unless the caller passes the world + 1 face positions (e.g. the x quantiles: equal counts)
+        self.edges = np.asarray(edges, dtype=np.float64) if edges is not None else self.box[0] * np.arange(W + 1) / W
+        if len(self.edges) != W + 1 or np.any(np.diff(self.edges) <= 0) or self.edges[0] != 0.0 or self.edges[-1] != self.box[0]:
+            raise ValueError("edges must ascend strictly from 0 to box[0] (world + 1 values)")
+        self.x0, self.x1 = float(self.edges[self.rank]), float(self.edges[self.rank + 1])
+        self.slab_width = float(np.diff(self.edges).min())        # the narrowest slab bounds the halo
         self.pos = pos.contiguous()
         self.f = self.pos.dtype
         self.vel = None if vel is None else vel.to(self.f).contiguous()
@@ -411,7 +414,7 @@ class NativeShardedTree:
     only does the rendezvous (rank 0's 128-byte id is broadcast over the torch.distributed group the process already has, the way
     an MPI code would MPI_Bcast it) and passes device pointers.  Same call surface as ShardedTree."""
 
-    def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=(1.0, 1.0, 1.0), halo=None, knn_k=64, group=None, device=None):
+    def __init__(self, pos, vel, mass, period=None, rank=None, world=None, box=(1.0, 1.0, 1.0), halo=None, knn_k=64, group=None, device=None, edges=None):
         """pos / vel / mass: this rank's particles, CUDA tensors or host tensors (copied to `device`, default the current CUDA
         device, by the library: pinned host memory makes that copy asynchronous)."""
         import ctypes as C
@@ -435,7 +438,9 @@ class NativeShardedTree:
         b = (C.c_double * 3)(*[float(x) for x in (box if box is not None else (1.0, 1.0, 1.0))])
         h = C.c_void_p()
         torch.cuda.synchronize(self.dev)
-        L.check(self.S.nbk_sharded_create(self.comm, C.byref(p), self.n_owned, C.addressof(b), int(self.periodic), int(knn_k), float(halo or 0.0), C.byref(h)))
+        e = None if edges is None else (C.c_double * (self.world + 1))(*[float(x) for x in edges])
+        L.check(self.S.nbk_sharded_create(self.comm, C.byref(p), self.n_owned, C.addressof(b), None if e is None else C.addressof(e), int(self.periodic), int(knn_k),
+                                          float(halo or 0.0), C.byref(h)))
         self.h = h
         self.profile = False
 

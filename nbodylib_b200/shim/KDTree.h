@@ -9,7 +9,8 @@
  *    SearchBallPosTagged (Int_t tt | Double_t* x | Coordinate; array and vector forms), dense SearchBall / SearchBallPos
  *    SearchCriterionTagged (Int_t tt | Particle&; array and vector forms), dense SearchCriterion (FOF3d / FOF6d)
  *    CalcDensity, CalcVelDensity, CalcSmoothingScale (new: north star), CalcDensityParticle, CalcVelDensityParticle,
- *    CalcDensityPosition, CalcVelDensityPosition, CalcSmoothLocalValue, CalcSmoothVel, CalcSmoothVelDisp
+ *    CalcDensityPosition, CalcVelDensityPosition, CalcSmoothLocalValue, CalcSmoothVel, CalcSmoothVelDisp, CalcSmoothVelSkew,
+ *    CalcSmoothVelKurtosis
  *    FindNearestCheck, FindNearestCriterion (Int_t tt | Particle | Coordinate)
  *    FOF, FOFCriterion, FOFCriterionSetBasisForLinks, FOFCriterionParticle (FOF3d / FOF6d), GetRoot / FindLeafNode (host mirror of the node arrays)
  *    OverWriteInputOrder, SetResetOrder, ~KDTree (restores the caller's particle order)
@@ -429,6 +430,36 @@ public:
         Matrix* out = new Matrix[numparts];
         for (Int_t i = 0; i < numparts; i++) { Matrix& mm = out[bucket[i].GetID()]; for (int j = 0; j < 3; j++) for (int l = 0; l < 3; l++) mm(j, l) = sd[(size_t)9 * i + 3 * j + l]; }
         return out;
+    }
+
+    Coordinate* higher_moment(int moment, Coordinate* smvel, Matrix* smveldisp, Int_t Nsmooth, int densityset, int meanvelset, int veldispset) {
+        if (densityset != 1) CalcDensity(Nsmooth);
+        Coordinate* own_v = NULL;
+        Matrix* own_d = NULL;
+        if (meanvelset != 1 || smvel == NULL) smvel = own_v = CalcSmoothVel(Nsmooth);
+        if (veldispset != 1 || smveldisp == NULL) smveldisp = own_d = CalcSmoothVelDisp(smvel, Nsmooth);
+        std::vector<double> rho(numparts), sv((size_t)3 * numparts), sd((size_t)9 * numparts), hm((size_t)3 * numparts);
+        for (Int_t i = 0; i < numparts; i++) {
+            rho[i] = bucket[i].GetDensity();
+            const Coordinate& c = smvel[bucket[i].GetID()];
+            const Matrix& mm = smveldisp[bucket[i].GetID()];
+            for (int j = 0; j < 3; j++) { sv[(size_t)3 * i + j] = c[j]; for (int l = 0; l < 3; l++) sd[(size_t)9 * i + 3 * j + l] = mm(j, l); }
+        }
+        if (own_v) delete[] own_v;
+        if (own_d) delete[] own_d;
+        check(moment == 3 ? nbk_calc_smooth_velskew(h, (int)Nsmooth, rho.data(), sv.data(), sd.data(), hm.data(), NBK_TREE_ORDER)
+                          : nbk_calc_smooth_velkurtosis(h, (int)Nsmooth, rho.data(), sv.data(), sd.data(), hm.data(), NBK_TREE_ORDER));
+        Coordinate* out = new Coordinate[numparts];
+        for (Int_t i = 0; i < numparts; i++) { Coordinate& c = out[bucket[i].GetID()]; for (int j = 0; j < 3; j++) c[j] = hm[(size_t)3 * i + j]; }
+        return out;
+    }
+    /// KDCalcSmoothQuantities.cxx:617-765: smoothed velocity skewness / kurtosis per component, new[] arrays indexed by particle ID.
+    /// *set != 1 recomputes the corresponding input like the reference does (the passed array is then ignored, not deleted).
+    Coordinate* CalcSmoothVelSkew(Coordinate* smvel, Matrix* smveldisp, Int_t Nsmooth = 64, int densityset = 1, int meanvelset = 1, int veldispset = 1) {
+        return higher_moment(3, smvel, smveldisp, Nsmooth, densityset, meanvelset, veldispset);
+    }
+    Coordinate* CalcSmoothVelKurtosis(Coordinate* smvel, Matrix* smveldisp, Int_t Nsmooth = 64, int densityset = 1, int meanvelset = 1, int veldispset = 1) {
+        return higher_moment(4, smvel, smveldisp, Nsmooth, densityset, meanvelset, veldispset);
     }
 
     /// single-target forms (KDCalcSmoothQuantities.cxx:768-921, 1092-1207): gather-only, value returned.  One small device

@@ -35,7 +35,7 @@ def clustered_small(n, seed=1, nhalo=24, frac=0.5):
     return _f32(pos), _f32(vel), _f32(mass)
 
 
-def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_members=64, dims=None, slab=None):
+def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_members=64, dims=None, slab=None, return_edges=False):
     """cfg 2-5 generator: a cell-centred lattice of spacing D = 1/ng + Zel'dovich displacement psi (Gaussian field,
     P_psi(k) ~ k^-2, rms |psi| = 1.5 lattice spacings, v = psi), wrapped periodically; a random `halo_frac` of the particles
     is relocated into `nhalo` Plummer spheres:
@@ -45,7 +45,8 @@ def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_m
     dims = (cx, cy, cz): the lattice has cx*ng x cy*ng x cz*ng cells and the periodic box is (cx, cy, cz) long (default (1, 1, 1):
     the ng^3 unit cube).  slab = (rank, world): only the particles whose x falls into slab `rank` of `world` equal slabs along x
     are returned -- every rank of a sharded run generates the SAME global field and keeps its own slab (BASELINE config 5: one
-    1024^3 cube cut into slabs).  Returns float32 torch tensors (pos[N,3], vel[N,3], mass[N]) on `device`; every value is
+    1024^3 cube cut into slabs); slab = (rank, world, "equal_count") puts the slab faces at the x quantiles instead (equal particle
+    counts, the usual load-balanced decomposition); return_edges adds the world + 1 face positions to the result.  Returns float32 torch tensors (pos[N,3], vel[N,3], mass[N]) on `device`; every value is
     therefore exactly representable in fp32 and is widened, not rounded, for the fp64 reference."""
     import torch
     dev = torch.device(device)
@@ -107,10 +108,20 @@ def clustered_box(ng, seed=2025, nhalo=8192, halo_frac=0.25, device="cpu", min_m
     for j in range(3):
         col = pos[:, j]
         col[col >= float(box[j])] = 0.0          # fp32 rounding of values just below the period
+    edges = None
     if slab is not None:
-        rk, world = slab
-        x0, x1 = cx * rk / world, cx * (rk + 1) / world
-        keep = (pos[:, 0] >= x0) & (pos[:, 0] < x1)
+        rk, world = slab[0], slab[1]
+        if len(slab) > 2 and slab[2] == "equal_count":
+            # slab faces at the x quantiles: every slab holds n / world particles (up to ties at a face)
+            xs = torch.sort(pos[:, 0]).values
+            cut = [float(xs[(n * r) // world].item()) for r in range(1, world)]
+            del xs
+            edges = [0.0] + cut + [float(cx)]
+        else:
+            edges = [cx * r / world for r in range(world + 1)]
+        keep = (pos[:, 0] >= edges[rk]) & (pos[:, 0] < edges[rk + 1])
         pos, vel = pos[keep], vel[keep]
     mass = torch.ones(pos.shape[0], device=dev, dtype=torch.float32)
+    if return_edges:
+        return pos.contiguous(), vel.contiguous(), mass, edges
     return pos.contiguous(), vel.contiguous(), mass

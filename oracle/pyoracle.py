@@ -208,6 +208,7 @@ class Ref:
             L.ref_dump_cuts.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, C.c_long]
             L.ref_knn_filtered.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_long, C.c_long, C.c_long, _dp, _dp, _ip, _dp]
             L.ref_calc_smooth_vel.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+            L.ref_calc_smooth_higher.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
             L.ref_max_threads.restype = C.c_int
             L.ref_sizeof_particle.restype = C.c_int
             cls._lib = L
@@ -416,6 +417,12 @@ class Ref:
         rho, sv, sd = np.zeros(self.n), np.zeros((self.n, 3)), np.zeros((self.n, 3, 3))
         self.lib().ref_calc_smooth_vel(self.h, k, _d(rho), _d(sv), _d(sd))
         return rho, sv, sd
+
+    def calc_smooth_higher(self, k):
+        """CalcSmoothVelSkew / CalcSmoothVelKurtosis after density, mean velocity and dispersion: (skew (n,3), kurtosis (n,3)) by ID"""
+        sk, ku = np.zeros((self.n, 3)), np.zeros((self.n, 3))
+        self.lib().ref_calc_smooth_higher(self.h, k, _d(sk), _d(ku))
+        return sk, ku
 
     def dump_cuts(self):
         cap = self.n + 64

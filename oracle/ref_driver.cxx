@@ -554,4 +554,17 @@ void ref_calc_smooth_vel(void* hv, int k, double* rho_by_id, double* smvel_by_id
     delete[] sv;
 }
 
+/* CalcSmoothVelSkew / CalcSmoothVelKurtosis (KDCalcSmoothQuantities.cxx:617-765) after CalcDensity, CalcSmoothVel, CalcSmoothVelDisp;
+ * outputs by ID, [n][3] each */
+void ref_calc_smooth_higher(void* hv, int k, double* skew_by_id, double* kurt_by_id) {
+    RefTree* h = (RefTree*)hv;
+    h->tree->CalcDensity(k);
+    Coordinate* sv = h->tree->CalcSmoothVel(k, 1);
+    Matrix* sd = h->tree->CalcSmoothVelDisp(sv, k, 1, 1);
+    Coordinate* sk = h->tree->CalcSmoothVelSkew(sv, sd, k, 1, 1, 1);
+    Coordinate* ku = h->tree->CalcSmoothVelKurtosis(sv, sd, k, 1, 1, 1);
+    for (Int_t i = 0; i < h->n; i++) for (int j = 0; j < 3; j++) { skew_by_id[3 * i + j] = sk[i][j]; kurt_by_id[3 * i + j] = ku[i][j]; }
+    delete[] sv; delete[] sd; delete[] sk; delete[] ku;
+}
+
 }  // extern "C"

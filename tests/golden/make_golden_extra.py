@@ -74,6 +74,7 @@ for tag, period in (("np", None), ("p", np.ones(3))):
     out["dense_c6_nn_" + tag], out["dense_c6_d2_" + tag] = nn.copy(), d2.copy()
     if tag == "np":
         out["sm_rho"], out["sm_vel"], out["sm_disp"] = R.calc_smooth_vel(k)
+        out["sm_skew"], out["sm_kurt"] = R.calc_smooth_higher(k)
         ids, d2k = R.knn_particles(k)
         dist = np.sqrt(d2k[7][::-1]).copy()
         w = mass2[ids[7][::-1]].copy()

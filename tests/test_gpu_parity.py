@@ -803,6 +803,10 @@ def test_golden_smoothed_velocity_moments(nb, G, X):
         sd = t.CalcSmoothVelDisp(X["sm_vel"], k, rho=X["sm_rho"])
         np.testing.assert_allclose(sd, X["sm_disp"], rtol=0, atol=1e-11 * np.abs(X["sm_disp"]).max())
         np.testing.assert_allclose(sd, np.transpose(sd, (0, 2, 1)), rtol=0, atol=1e-12 * np.abs(sd).max())
+        sk = t.CalcSmoothVelSkew(X["sm_vel"], X["sm_disp"], k, rho=X["sm_rho"])
+        np.testing.assert_allclose(sk, X["sm_skew"], rtol=0, atol=1e-10 * np.abs(X["sm_skew"]).max())
+        ku = t.CalcSmoothVelKurtosis(X["sm_vel"], X["sm_disp"], k, rho=X["sm_rho"])
+        np.testing.assert_allclose(ku, X["sm_kurt"], rtol=0, atol=1e-10 * np.abs(X["sm_kurt"]).max())
         # densityset != 1: the density is computed first
         sv2 = t.CalcSmoothVel(k)
         np.testing.assert_allclose(sv2, X["sm_vel"], rtol=0, atol=1e-9 * np.abs(X["sm_vel"]).max())

@@ -35,12 +35,18 @@ def _worker(rank, world, port, tmp, n, native):
             ShardedTree = NativeShardedTree
         from nbodylib_b200.synth import clustered_small
         pos, vel, mass = clustered_small(n, seed=5)
-        slab = np.minimum((pos[:, 0] * world).astype(int), world - 1)
+        edges = None
+        if world == 4:                          # slab faces at the x quantiles (equal counts, unequal widths); equal widths at world 2
+            xs = np.sort(pos[:, 0])
+            edges = np.array([0.0] + [xs[(n * r) // world] for r in range(1, world)] + [1.0])
+            slab = np.searchsorted(edges, pos[:, 0], side="right") - 1
+        else:
+            slab = np.minimum((pos[:, 0] * world).astype(int), world - 1)
         mine = np.nonzero(slab == rank)[0]
         dev = torch.device("cuda", rank)
         f = torch.float32                       # clustered_small is fp32-representable: the slab trees keep fp32 storage
         st = ShardedTree(torch.from_numpy(pos[mine]).to(dev, f), torch.from_numpy(vel[mine]).to(dev, f), torch.from_numpy(mass[mine]).to(dev, f),
-                         period=np.ones(3), rank=rank, world=world, box=(1.0, 1.0, 1.0), knn_k=32)
+                         period=np.ones(3), rank=rank, world=world, box=(1.0, 1.0, 1.0), knn_k=32, edges=edges)
         rho = st.CalcDensity(32)
         ll = 0.25 / n ** (1 / 3)
         g, ng = st.FOF(ll, 8, 1)

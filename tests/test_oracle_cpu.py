@@ -463,6 +463,16 @@ def test_smoothed_velocity_moments_restatement(port, G, X):
     np.add.at(sd, ii, (w / rho[jj] * m[jj])[:, None, None] * a[:, :, None] * a[:, None, :])
     np.add.at(sd, jj, (w / rho[ii] * m[ii])[:, None, None] * b[:, :, None] * b[:, None, :])
     np.testing.assert_allclose(sd, X["sm_disp"], rtol=0, atol=1e-12 * np.abs(X["sm_disp"]).max())
+    # CalcSmoothVelSkew / CalcSmoothVelKurtosis (:617-765): third / fourth power over the RECEIVER's dispersion; the kurtosis
+    # form subtracts 3 from every contribution
+    dg = np.stack([X["sm_disp"][:, c, c] for c in range(3)], axis=1)
+    sk, ku = np.zeros((n, 3)), np.zeros((n, 3))
+    np.add.at(sk, ii, (w / rho[jj] * m[jj])[:, None] * a ** 3 / dg[ii] ** 1.5)
+    np.add.at(sk, jj, (w / rho[ii] * m[ii])[:, None] * b ** 3 / dg[jj] ** 1.5)
+    np.add.at(ku, ii, (w / rho[jj] * m[jj])[:, None] * a ** 4 / dg[ii] ** 2 - 3.0)
+    np.add.at(ku, jj, (w / rho[ii] * m[ii])[:, None] * b ** 4 / dg[jj] ** 2 - 3.0)
+    np.testing.assert_allclose(sk, X["sm_skew"], rtol=0, atol=1e-11 * np.abs(X["sm_skew"]).max())
+    np.testing.assert_allclose(ku, X["sm_kurt"], rtol=0, atol=1e-11 * np.abs(X["sm_kurt"]).max())
 
 
 def test_header_is_plain_c_and_shim_links(built, tmp_path):

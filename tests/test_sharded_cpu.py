@@ -88,11 +88,17 @@ def _worker(rank, world, port, tmp, halo, case):
         from nbodylib_b200.sharded import ShardedTree
         pos, vel, mass = _case(case)
         n = len(pos)
-        slab = np.minimum((pos[:, 0] * world).astype(int), world - 1)
+        edges = None
+        if case == "quantile":                 # slab faces at the x quantiles: equal particle counts, unequal widths
+            xs = np.sort(pos[:, 0])
+            edges = np.array([0.0] + [xs[(n * r) // world] for r in range(1, world)] + [1.0])
+            slab = np.searchsorted(edges, pos[:, 0], side="right") - 1
+        else:
+            slab = np.minimum((pos[:, 0] * world).astype(int), world - 1)
         mine = np.nonzero(slab == rank)[0]
         dt = torch.float32 if case == "fp32" else torch.float64
         st = ShardedTree(torch.from_numpy(pos[mine]).to(dt), torch.from_numpy(vel[mine]).to(dt), torch.from_numpy(mass[mine]).to(dt), period=np.ones(3),
-                         rank=rank, world=world, box=(1.0, 1.0, 1.0), halo=halo, knn_k=16, engine=PortEngine())
+                         rank=rank, world=world, box=(1.0, 1.0, 1.0), halo=halo, knn_k=16, engine=PortEngine(), edges=edges)
         rho = st.CalcDensity(16)
         ll = 0.3 / n ** (1 / 3)
         g0, ng0 = st.FOF(ll, 5, 0)
@@ -122,7 +128,8 @@ def _case(case):
     return clustered_small(5000, seed=77)
 
 
-@pytest.mark.parametrize("world,halo,case", [(2, None, "clustered"), (2, 0.01, "clustered"), (3, None, "clustered"), (4, None, "fp32"), (2, None, "uneven")])
+@pytest.mark.parametrize("world,halo,case", [(2, None, "clustered"), (2, 0.01, "clustered"), (3, None, "clustered"), (4, None, "fp32"), (2, None, "uneven"),
+                                             (3, None, "quantile")])
 def test_sharded_host_logic_matches_single_domain(port, world, halo, case):
     pos, vel, mass = _case(case)
     n = len(pos)
