@@ -621,7 +621,7 @@ def main():
                        "storage": "fp32 coordinates (exact), fp32 screening keys with a certified error band, fp64 distances and sums for the results",
                        "l2": "inputs (%.1f GB) exceed L2, no flush needed" % (n * 16 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "knn_ap_kernel<float,false>", "kernel_ms": kms,
+                         "peak_source": peak_src, "kernel": "knn_hp_kernel<float,false,32>", "kernel_ms": kms,
                          "algorithmic_bytes_per_particle": ALG_BYTES["knn_density"],
                          "note": "issue-slot bound tree traversal + selection, not HBM bound: see DESIGN.md section 4; traffic = measured DRAM bytes of one launch (ncu)",
                          **ncu_facts},

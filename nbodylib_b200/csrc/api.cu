@@ -283,7 +283,7 @@ int nbk_create(const nbk_particles* p, int64_t n, int bucket, int treetype, int 
     const int64_t sec_stride = tvel ? p->pos_stride : p->vel_stride;
     const bool host_in = p->on_device == 0;
     const bool width_known = p->real_bytes == 4 || (flags & (NBK_STORE_F64 | NBK_STORE_F32));
-    const bool overlap = host_in && width_known && (sec_src || p->mass) && getenv("NBK_NO_OVERLAP") == nullptr;
+    const bool overlap = host_in && width_known && (sec_src || p->mass);
     DevBuf<double> rprim((size_t)3 * n), rsec, rmass;
     stage3(prim_src, prim_stride, p->real_bytes, !host_in, n, 3, rprim.p, st);
     if (!overlap) {

@@ -1003,7 +1003,7 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm) && !a.gather && !a.qlist && !a.cand_excl && !a.crit_mode &&
                              !a.smvel_out && !a.smdisp_out && !a.smhigh_out;
     if (smooth_only && !g_knn_exact && ap_range_ok(t)) {
-        // ---- append + prune kernel, exact kernel for the flagged queries -----------------------------------------
+        // ---- packed-word heap kernel (knn_hp_kernel), exact kernel for the flagged queries --------------------------
         p.kcap = a.k;
         // Nodes of up to `leaf` particles are scanned as one tile: the level whose nodes hold 21..40 particles (exactly one
         // level does: sizes halve) -- a tile and a bit; with a fixed threshold of 32 a particle count just above a power of

@@ -86,6 +86,102 @@ def test_sharded_matches_single_gpu(built, world, native):
     assert int(res[0]["ng"][1]) == nh1 and np.array_equal(canon(g6), canon(h1))
 
 
+def _variant_worker(rank, world, port, tmp, case):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from nbodylib_b200.sharded import NativeShardedTree
+        pos, vel, mass, box, periodic, k, ll, minnum, order = _variant(case)
+        n = len(pos)
+        slab = np.minimum((pos[:, 0] / box[0] * world).astype(int), world - 1)
+        mine = np.nonzero(slab == rank)[0]
+        # host arrays straight into the C ABI (on_device = 0), fp64
+        st = NativeShardedTree(torch.from_numpy(pos[mine]), torch.from_numpy(vel[mine]), None if mass is None else torch.from_numpy(mass[mine]),
+                               period=box if periodic else None, rank=rank, world=world, box=box, knn_k=k, device=rank)
+        rho = st.CalcDensity(k)
+        rho2 = st.CalcDensity(k)                               # second call on the resident trees
+        g, ng = st.FOF(ll, minnum, order)
+        g6, ng6 = st.FOFCriterion(2, _params6d(pos, vel, n), minnum, order)
+        info = st.stats
+        assert info["density_setups"] >= 1 and info["n_global"] == n and info["nranks"] == world
+        assert torch.equal(rho, rho2) or torch.allclose(rho, rho2, rtol=1e-12, atol=0)
+        np.savez(os.path.join(tmp, "r%d.npz" % rank), idx=mine, rho=rho.cpu().numpy(), g=g.cpu().numpy(), g6=g6.cpu().numpy(), ng=np.array([ng, ng6]))
+        st.close()
+        NativeShardedTree.shutdown()
+    finally:
+        dist.destroy_process_group()
+
+
+def _variant(case):
+    """(pos, vel, mass, box, periodic, k, ll, minnum, order) of the extra C-ABI cases"""
+    from nbodylib_b200.synth import clustered_small
+    if case == "fp64-open":
+        # coordinates that fp32 cannot hold (the slab trees must keep fp64 storage), open box, unordered ids, singletons kept out
+        rng = np.random.default_rng(11)
+        pos, vel, mass = clustered_small(60000, seed=3)
+        pos = np.clip(pos + 1e-9 * rng.standard_normal(pos.shape), 1e-12, 1 - 1e-12)
+        return pos, vel, mass, np.ones(3), False, 20, 0.3 / 60000 ** (1 / 3), 2, 0
+    if case == "box-2x1x1":
+        # a non-cubic periodic box, unit masses (mass = NULL), large groups only
+        rng = np.random.default_rng(12)
+        a, va, _ = clustered_small(50000, seed=4)
+        b, vb, _ = clustered_small(50000, seed=5)
+        pos = np.concatenate([a, b + np.array([1.0, 0, 0])])
+        vel = np.concatenate([va, vb])
+        return pos, vel, None, np.array([2.0, 1.0, 1.0]), True, 48, 0.25 / 50000 ** (1 / 3), 30, 1
+    raise KeyError(case)
+
+
+@pytest.mark.parametrize("world,case", [(3, "fp64-open"), (2, "box-2x1x1"), (4, "box-2x1x1")])
+def test_sharded_c_abi_variants(built, world, case):
+    """The C ABI on inputs the headline case does not touch: fp64 coordinates that are not fp32-representable, host pointers, an
+    open box, a non-cubic periodic box, unit masses, an odd number of ranks, both id orders."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import nbodylib_b200 as nb
+    pos, vel, mass, box, periodic, k, ll, minnum, order = _variant(case)
+    n = len(pos)
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_variant_worker, args=(world, 29500 + np.random.randint(0, 2000), tmp, case), nprocs=world, join=True)
+        res = [np.load(os.path.join(tmp, "r%d.npz" % r)) for r in range(world)]
+    rho = np.zeros(n)
+    g, g6 = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+    for r in res:
+        rho[r["idx"]] = r["rho"]
+        g[r["idx"]] = r["g"]
+        g6[r["idx"]] = r["g6"]
+    with nb.KDTree(pos, vel, mass, Period=box if periodic else None) as t:
+        np.testing.assert_allclose(rho, t.CalcDensity(k), rtol=1e-10)
+        g1, ng1 = t.FOF(ll, minnum, order)
+        h1, nh1 = t.FOFCriterion(nb.FOF6D, _params6d(pos, vel, n), minnum, order)
+    assert int(res[0]["ng"][0]) == ng1 and np.array_equal(canon(g), canon(g1)) and g.max() == ng1
+    assert int(res[0]["ng"][1]) == nh1 and np.array_equal(canon(g6), canon(h1))
+    if order:
+        sizes = np.bincount(g)[1:]
+        assert np.all(np.diff(sizes) <= 0) and np.array_equal(sizes, np.bincount(g1)[1:])
+
+
+def test_sharded_demo_from_plain_cxx(built, tmp_path):
+    """examples/sharded_demo.cxx: the C ABI from a C++ program without Python in the ranks -- one forked process per GPU, the
+    communicator id through a file, system NCCL -- against a single tree in the same program.  One GPU: a single rank."""
+    import shutil
+    import subprocess
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "nbodylib_b200")
+    exe = str(tmp_path / "sharded_demo")
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "sharded_demo.cxx"),
+                           "-L" + lib, "-lnbk_sharded", "-lnbk", "-Wl,-rpath," + lib, "-o", exe])
+    nranks = min(4, torch.cuda.device_count())
+    out = subprocess.run([exe, str(nranks), "400000"], capture_output=True, text=True, timeout=600)
+    print(out.stdout[-1500:], out.stderr[-1500:])
+    assert out.returncode == 0 and "SHARDED DEMO OK" in out.stdout
+
+
 def test_world1_driver_and_building_blocks(built):
     """One GPU: the sharded driver with a single rank (no process group needed) equals the plain tree, which exercises
     nbk_fof_roots; nbk_union_pairs is checked on a random edge list against SciPy."""

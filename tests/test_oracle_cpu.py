@@ -491,6 +491,13 @@ def test_header_is_plain_c_and_shim_links(built, tmp_path):
                            "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", str(tmp_path / "use_nbk")])
     subprocess.check_call([gxx, "-O1", "-std=c++17", "-fopenmp", "-Wall", "-I" + os.path.join(lib, "shim"), os.path.join(ROOT, "examples", "shim_demo.cxx"),
                            "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", str(tmp_path / "shim_demo")])
+    # the sharded C ABI from plain C++ (examples/sharded_demo.cxx); without a GPU its ranks fail with a status code, not a crash
+    subprocess.check_call([gxx, "-O1", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "sharded_demo.cxx"),
+                           "-L" + lib, "-lnbk_sharded", "-lnbk", "-Wl,-rpath," + lib, "-o", str(tmp_path / "sharded_demo")])
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(tmp_path / "sharded_demo"), "1", "1000"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1 and "nbk_comm_init_rank" in r.stderr
 
 
 def test_restatements_vs_live_reference(port):
