@@ -143,6 +143,7 @@ __device__ __forceinline__ void traverse_from(const NodeLo* __restrict__ nlo, co
         bool found = false;
         while (sp > 0) {
             node = stack[--sp];
+            __syncwarp();                      // every lane has read the entry before lane 0 may overwrite the slot with a later push
             lo = nlo[node]; hi = nhi[node];
             float lb = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, lo, hi);
             nmask = __ballot_sync(0xffffffffu, on && v.need(lb));

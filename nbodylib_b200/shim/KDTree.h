@@ -68,6 +68,19 @@ typedef unsigned int UInt_tree_t;
 
 namespace NBody {
 
+/// uninitialised per-particle scratch of the shim (a std::vector would zero a GB-sized array on one thread before the parallel
+/// loop that fills it touches it)
+template <class T>
+struct NbkRawBuf {
+    T* p;
+    explicit NbkRawBuf(size_t n) : p(static_cast<T*>(::operator new(sizeof(T) * (n ? n : 1)))) {}
+    ~NbkRawBuf() { ::operator delete(p); }
+    NbkRawBuf(const NbkRawBuf&) = delete;
+    NbkRawBuf& operator=(const NbkRawBuf&) = delete;
+    T* data() { return p; }
+    T& operator[](size_t i) { return p[i]; }
+};
+
 /// Host mirror of one tree node (reference KDNode.h:45-334 Node, :343-484 SplitNode, :492-610 LeafNode): what callers of
 /// KDTree::GetRoot() / FindLeafNode() read.  IDs number the nodes depth first, left before right, like the reference's
 /// BuildNodes.  Boundaries are the node's particle bounding box (fp32, rounded outward when the tree stores fp64
@@ -199,7 +212,7 @@ public:
         (void)Aniso; (void)metric; (void)iBuildInParallel; (void)min_bucket_size;
         if (ScaleSpace) throw std::runtime_error("nbk shim: ScaleSpace has no device implementation");
         if (iKeepInputOrder || Rdistadapt > 0 || AdaptiveMedianFac > 0) throw std::runtime_error("nbk shim: adaptive / keep-order builds have no device implementation");
-        std::vector<Double_t> mass(numparts);
+        NbkRawBuf<Double_t> mass((size_t)numparts);
         NBK_SHIM_PARALLEL_FOR
         for (Int_t i = 0; i < numparts; i++) { bucket[i].SetID(i); mass[i] = bucket[i].GetMass(); }      // KDTree.cxx:1291
         nbk_particles np;
@@ -214,7 +227,7 @@ public:
         serial = next_serial();
         refresh();
         // bring the caller's array into tree order (the reference does this with in-place quickselect swaps)
-        std::vector<int32_t> order(numparts);
+        NbkRawBuf<int32_t> order((size_t)numparts);
         check(nbk_get_order(h, order.data(), 0));
         permute([&](Int_t i) { return (Int_t)order[i]; });
     }
@@ -230,7 +243,7 @@ public:
         if (period) delete[] period;
         if (iresetorder && bucket) {
             // reference: std::sort(bucket, bucket+numparts, IDCompareVec); ids are a permutation of 0..N-1 -> O(N) placement
-            std::vector<Int_t> src(numparts);
+            NbkRawBuf<Int_t> src((size_t)numparts);
             NBK_SHIM_PARALLEL_FOR
             for (Int_t i = 0; i < numparts; i++) src[bucket[i].GetID()] = i;
             permute([&](Int_t i) { return src[i]; });
@@ -383,13 +396,13 @@ public:
 
     // ---- smoothed estimators (KDCalcSmoothQuantities.cxx:203-389) ----------------------------------------------
     void CalcDensity(Int_t Nsmooth = 64) {
-        std::vector<double> rho(numparts);
+        NbkRawBuf<double> rho((size_t)numparts);
         check(nbk_calc_density(h, (int)Nsmooth, rho.data(), NULL, NBK_TREE_ORDER));
         NBK_SHIM_PARALLEL_FOR
         for (Int_t i = 0; i < numparts; i++) bucket[i].SetDensity(rho[i]);
     }
     void CalcVelDensity(Int_t Nsmooth = 64, Int_t Nsearch = 64) {
-        std::vector<double> rho(numparts);
+        NbkRawBuf<double> rho((size_t)numparts);
         check(nbk_calc_veldensity(h, (int)Nsmooth, (int)Nsearch, rho.data(), NBK_TREE_ORDER));
         NBK_SHIM_PARALLEL_FOR
         for (Int_t i = 0; i < numparts; i++) bucket[i].SetDensity(rho[i]);
