@@ -766,6 +766,10 @@ struct HpVisitor {
     }
 };
 
+// One CTA per SM with as many warps as registers (96 per thread: 21 warps) and shared memory (the per-warp heaps) allow: the
+// warps never synchronise with each other, so the CTA size is free, and one large CTA wastes no per-CTA reserved shared memory
+// (5 CTAs x 4 warps left 13 KB per SM unused -- one warp's worth).
+constexpr int HP_MAX_WARPS = 22;
 static inline int hp_groups(int k) { return (k + 4) / 4; }            // internal nodes of the heap of k+2 words
 static inline size_t hp_warp_bytes(int k, bool want_doubles, int tile_bytes) {
     size_t region = (size_t)(hp_groups(k) + 1) * 512;
@@ -774,7 +778,7 @@ static inline size_t hp_warp_bytes(int k, bool want_doubles, int tile_bytes) {
 }
 
 template <class S, bool HALO, int AP_TILE>
-__global__ void __launch_bounds__(KNN_WARPS * 32, 5) knn_hp_kernel(KnnParams prm, int want_doubles, int* __restrict__ work_counter) {
+__global__ void __launch_bounds__(HP_MAX_WARPS * 32, 1) knn_hp_kernel(KnnParams prm, int want_doubles, int* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
@@ -1023,22 +1027,23 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
         const int want_doubles = (a.veldens_k > 0 && a.veldens_k < a.k) ? 1 : 0;
         const int tile_slots = (p.bucket <= 32 && (!t.nlo2 || p.bucket2 <= 32)) ? 32 : 40;
         const int tile_bytes = t.store_bytes == 4 ? tile_slots * 16 : 3 * tile_slots * 8;
-        const size_t smem = hp_warp_bytes(a.k, want_doubles, tile_bytes) * KNN_WARPS;
-        NBK_REQUIRE(smem <= 227 * 1024, NBK_ERR_ARG, "k too large for the shared-memory heaps");
-        int nsm = 0, per_sm = 0;
+        const size_t warp_bytes = hp_warp_bytes(a.k, want_doubles, tile_bytes);
+        int nsm = 0, smem_max = 0;
         NBK_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, t.device));
+        NBK_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, t.device));
         const int64_t ngroups = (rows + 31) / 32;
+        int warps = (int)std::min<int64_t>(HP_MAX_WARPS, (int64_t)smem_max / (int64_t)warp_bytes);
+        NBK_REQUIRE(warps >= 1, NBK_ERR_ARG, "k too large for the shared-memory heaps");
+        if (ngroups < (int64_t)nsm * warps) warps = (int)std::max<int64_t>(1, (ngroups + nsm - 1) / nsm);      // small inputs: spread over the SMs
+        const size_t smem = warp_bytes * warps;
         DevBuf<int> counters(2);
         DevBuf<int32_t> flist(rows);
         NBK_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), t.stream));
         p.flag_count = counters.p; p.flag_list = flist.p;
         auto go = [&](auto kern) {
             NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            NBK_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KNN_WARPS * 32, smem));
-            NBK_REQUIRE(per_sm >= 1, NBK_ERR_ARG, "k too large for the shared-memory heaps");
-            int64_t blocks = (int64_t)nsm * per_sm;
-            if (blocks > (ngroups + KNN_WARPS - 1) / KNN_WARPS) blocks = (ngroups + KNN_WARPS - 1) / KNN_WARPS;
-            kern<<<(int)blocks, KNN_WARPS * 32, smem, t.stream>>>(p, want_doubles, counters.p + 1);
+            const int64_t blocks = std::min<int64_t>(nsm, (ngroups + warps - 1) / warps);
+            kern<<<(int)blocks, warps * 32, smem, t.stream>>>(p, want_doubles, counters.p + 1);
         };
         if (tile_slots == 32) {
             if (t.store_bytes == 4) { if (t.nlo2) go(knn_hp_kernel<float, true, 32>); else go(knn_hp_kernel<float, false, 32>); }
