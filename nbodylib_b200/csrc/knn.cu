@@ -442,10 +442,10 @@ constexpr float AP_NARROW = 0.99999904632568359375f;         // 1 - 2^-20
 // so for 2^m particles), else 40 (the level holds 21..40).  Candidate id: 7 bits tile sequence number + 5 / 6 bits slot.
 template <int TILE> struct ApWord {
     static constexpr int SLOT_BITS = TILE <= 32 ? 5 : 6;
-    static constexpr unsigned CIDMASK = (1u << (7 + SLOT_BITS)) - 1u;
+    static constexpr unsigned CIDMASK = (1u << (6 + SLOT_BITS)) - 1u;      // candidate id = (tile sequence number, 6 bits: AP_MAXTILES) , slot
     static constexpr unsigned KEYMASK = ~CIDMASK;
 };
-constexpr int AP_MAXTILES = 128;
+constexpr int AP_MAXTILES = 64;
 constexpr float AP_INF = __builtin_huge_valf();
 
 #ifdef NBK_STATS
@@ -624,21 +624,18 @@ __device__ __forceinline__ void sc_epilogue(const KnnParams& prm, const Vec4<S>*
     }
 }
 
-// Per-lane 4-ary max-heap of words in shared memory: node p's four children are the components of ONE 16-byte group (one
-// LDS.128 per level, 3 levels for 65 entries); (G+1)*512 bytes per warp.
+// Per-lane 4-ary max-heap of words.  The ROOT lives in a register (it is the lane's bound anyway); nodes 1 .. 4G live in shared
+// memory: the four children of node p are the components of ONE 16-byte group at kb + p*512 (one LDS.128 per level, 3 levels for
+// 66 entries), node p >= 1 at kb + ((p-1)>>2)*512 + ((p-1)&3)*4.  Gs*512 bytes per warp, Gs = ceil((k+2)/4).
 struct WordHeap4 {
-    unsigned char* kb;   // this lane's byte base inside the [G+1][32] float4 groups (group g of the lane at kb + g*512)
-    int G;
-    // key of node p: group (p+3)>>2, component (p+3)&3 ; children of p = the four components of group p+1
-    __device__ __forceinline__ float* keyp(int p) const { return reinterpret_cast<float*>(kb + ((p + 3) >> 2) * 512 + ((p + 3) & 3) * 4); }
-    __device__ __forceinline__ float rootkey() const { return *reinterpret_cast<const float*>(kb + 12); }
-    // place xk at node p and sift it down; returns the key that ends up at node p
-    __device__ __forceinline__ float sift(int p, float xk) {
-        unsigned char* pa = reinterpret_cast<unsigned char*>(keyp(p));
-        unsigned char* ga = kb + (p + 1) * 512;
-        float at_p = xk;
-        bool moved = false;
+    unsigned char* kb;   // this lane's byte base inside the [Gs][32] float4 groups
+    int G;               // nodes 0 .. G-1 have children
+    __device__ __forceinline__ float* nodep(int p) const { return reinterpret_cast<float*>(kb + ((p - 1) >> 2) * 512 + ((p - 1) & 3) * 4); }
+    // place xk at node p >= 1 (overwriting it) and sift it down
+    __device__ __forceinline__ void sift(int p, float xk) {
+        unsigned char* pa = reinterpret_cast<unsigned char*>(nodep(p));
         while (p < G) {
+            unsigned char* ga = kb + p * 512;
             const float4 ck = *reinterpret_cast<const float4*>(ga);
             const bool a = ck.x >= ck.y, b = ck.z >= ck.w;
             const float m01 = a ? ck.x : ck.y, m23 = b ? ck.z : ck.w;
@@ -647,13 +644,21 @@ struct WordHeap4 {
             if (xk >= m) break;
             const int j = c ? (a ? 0 : 1) : (b ? 2 : 3);
             *reinterpret_cast<float*>(pa) = m;
-            if (!moved) { at_p = m; moved = true; }
             pa = ga + 4 * j;
             p = 4 * p + 1 + j;
-            ga = kb + (p + 1) * 512;
         }
         *reinterpret_cast<float*>(pa) = xk;
-        return at_p;
+    }
+    // xk takes the place of the root (which is dropped); returns the new root
+    __device__ __forceinline__ float replace_root(float xk) {
+        const float4 ck = *reinterpret_cast<const float4*>(kb);
+        const bool a = ck.x >= ck.y, b = ck.z >= ck.w;
+        const float m01 = a ? ck.x : ck.y, m23 = b ? ck.z : ck.w;
+        const bool c = m01 >= m23;
+        const float m = c ? m01 : m23;
+        if (xk >= m) return xk;
+        sift(1 + (c ? (a ? 0 : 1) : (b ? 2 : 3)), xk);       // the largest child moves up into the register, xk sinks from its slot
+        return m;
     }
 };
 
@@ -665,7 +670,7 @@ struct HpVisitor {
     WordHeap4 hp;
     int* tl;              // shared: the warp's tile list (tile sequence number -> first tree index)
     int nt;               // tiles scanned so far (warp-uniform)
-    float topw;           // heap root: the lane's (k+1)-th smallest word so far (+inf while it has fewer)
+    float topw;           // heap root (node 0 lives here, not in shared memory): the lane's (k+2)-th smallest word so far (+inf while it has fewer)
     float limf;           // screen / node-test limit: upper edge of the root's bin * (1 + 2^-20); -1: the lane accepts nothing
     unsigned limu;        // the same limit for the unsigned screen test (bits(a) - bits(AP_TINY) < limu); 0: nothing passes
     unsigned mindrop;     // smallest word rejected or evicted in a round once the heap was full
@@ -748,17 +753,19 @@ struct HpVisitor {
                     const unsigned wb = (__float_as_uint(tile.key(j)) & AP_KEYMASK) | (cid0 + (unsigned)j);
                     const float w = __uint_as_float(wb);
                     if (filled < kcap) {
-                        *hp.keyp(filled) = w;
+                        // candidates 1 .. k+1 go to nodes 1 .. k+1 as they come; the (k+2)-th completes the heap: the inner nodes
+                        // are heapified and the newcomer is sifted in from the root
                         filled++;
-                        if (filled == kcap) {
-                            for (int p = hp.G - 1; p >= 0; p--) hp.sift(p, *hp.keyp(p));
-                            settop(hp.rootkey());
+                        if (filled < kcap) *hp.nodep(filled) = w;
+                        else {
+                            for (int p = hp.G - 1; p >= 1; p--) hp.sift(p, *hp.nodep(p));
+                            settop(hp.replace_root(w));
                         }
                     } else {
                         // the word that does not stay in the heap: the candidate itself, or the root it evicts
                         const unsigned out = w < topw ? __float_as_uint(topw) : wb;
                         mindrop = min(mindrop, out);
-                        if (w < topw) settop(hp.sift(0, w));
+                        if (w < topw) settop(hp.replace_root(w));
                     }
                 }
             }
@@ -769,12 +776,13 @@ struct HpVisitor {
 // One CTA per SM with as many warps as registers (96 per thread: 21 warps) and shared memory (the per-warp heaps) allow: the
 // warps never synchronise with each other, so the CTA size is free, and one large CTA wastes no per-CTA reserved shared memory
 // (5 CTAs x 4 warps left 13 KB per SM unused -- one warp's worth).
-constexpr int HP_MAX_WARPS = 22;
-static inline int hp_groups(int k) { return (k + 4) / 4; }            // internal nodes of the heap of k+2 words
+constexpr int HP_MAX_WARPS = 24;
+constexpr int HP_STACK = 32;       // traversal stack entries of this kernel: at most one per tree level (depth <= 30)
+static inline int hp_store_groups(int k) { return (k + 2 + 3) / 4; }   // 16-byte groups per lane: nodes 1 .. k+2 (the last one is the root's slot of the final pass)
 static inline size_t hp_warp_bytes(int k, bool want_doubles, int tile_bytes) {
-    size_t region = (size_t)(hp_groups(k) + 1) * 512;
+    size_t region = (size_t)hp_store_groups(k) * 512;
     if (want_doubles) region += (size_t)k * 32 * 8;
-    return region + tile_bytes + TRAV_STACK * 4 + AP_MAXTILES * 4;
+    return region + tile_bytes + HP_STACK * 4 + AP_MAXTILES * 4;
 }
 
 template <class S, bool HALO, int AP_TILE>
@@ -785,14 +793,15 @@ __global__ void __launch_bounds__(HP_MAX_WARPS * 32, 1) knn_hp_kernel(KnnParams 
     // the heap keeps k + 2 words: the k nearest, the (k+1)-th that certifies them, and one more so that a candidate dropped
     // from the root's bin almost never sits next to the k-th (see the certificate below)
     const int k = prm.k, kcap = k + 2;
-    const int G = (kcap - 1 + 3) / 4, NN = 4 * G + 1;
-    const size_t heap_bytes = (size_t)(G + 1) * 512;
+    const int G = (kcap - 1 + 3) / 4;                      // nodes 0 .. G-1 have children (the last group may be partly padding)
+    const int Gs = (kcap + 3) / 4;                         // stored groups: nodes 1 .. 4 Gs, 4 Gs >= kcap
+    const size_t heap_bytes = (size_t)Gs * 512;
     const size_t region = heap_bytes + (want_doubles ? (size_t)k * 32 * 8 : 0);
-    const size_t warp_bytes = region + ApTile<S, AP_TILE>::TILE_BYTES + TRAV_STACK * 4 + AP_MAXTILES * 4;
+    const size_t warp_bytes = region + ApTile<S, AP_TILE>::TILE_BYTES + HP_STACK * 4 + AP_MAXTILES * 4;
     unsigned char* base = smem_raw + w * warp_bytes;
     void* tile_mem = base + region;
     int* stack = reinterpret_cast<int*>(base + region + ApTile<S, AP_TILE>::TILE_BYTES);
-    int* tl = stack + TRAV_STACK;
+    int* tl = stack + HP_STACK;
     unsigned char* kb = base + lane * 16;
 
     const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
@@ -821,26 +830,25 @@ __global__ void __launch_bounds__(HP_MAX_WARPS * 32, 1) knn_hp_kernel(KnnParams 
         v.mindrop = 0xffffffffu;
         v.filled = 0; v.kcap = kcap; v.tr_max = prm.tr_max;
         v.failed = false;
-        // empty real slots hold +inf, the padding up to 4G+1 nodes holds 0 (never evicted, never accepted against)
-        for (int p = 0; p < NN; p++) *v.hp.keyp(p) = p < kcap ? AP_INF : 0.f;
+        // the padding nodes of the last child group hold 0 (never the largest child); real nodes are written before they are read
+        for (int p = kcap; p <= 4 * Gs; p++) *v.hp.nodep(p) = 0.f;
         v.topw = AP_INF;
         if (valid) v.set_limit(AP_HUGE); else { v.limf = -1.f; v.limu = 0u; }
         traverse_bottom_up(prm.nlo, prm.nhi, prm.bucket, stack, v, qb, valid, prm.n_tree, prm.aligned, g0, g1);
         if (HALO) traverse(prm.nlo2, prm.nhi2, prm.bucket2, stack, v, qb, valid);
 
         // ------------------------------------------------------------------------ the k nearest and the k-th
-        // linearise: the valid words of the heap nodes move to the front (slot s = storage of node s)
-        auto word_at = [kb](int s) -> unsigned* { return reinterpret_cast<unsigned*>(kb + ((s + 3) >> 2) * 512 + ((s + 3) & 3) * 4); };
-        const unsigned rootw = *word_at(0);
+        // the candidates a lane holds: slot s = node s + 1.  Heap complete: nodes 1 .. k+1 and the root, which is written to the
+        // slot behind them; otherwise (fewer than k + 2 candidates exist) nodes 1 .. filled, never heapified
+        auto word_at = [kb](int s) -> unsigned* { return reinterpret_cast<unsigned*>(kb + (s >> 2) * 512 + (s & 3) * 4); };
+        const unsigned rootw = __float_as_uint(v.topw);
         int cnt = 0;
         if (valid && !v.failed) {
-            for (int s = 0; s < NN; s++) {
-                const unsigned wd = *word_at(s);
-                if (wd != 0x7f800000u && wd != 0u) { *word_at(cnt) = wd; cnt++; }
-            }
+            cnt = v.filled;
+            if (cnt == kcap) *word_at(kcap - 1) = rootw;
         }
         auto idx_at = [kb, tl](int s) -> int {
-            const unsigned wd = *reinterpret_cast<const unsigned*>(kb + ((s + 3) >> 2) * 512 + ((s + 3) & 3) * 4);
+            const unsigned wd = *reinterpret_cast<const unsigned*>(kb + (s >> 2) * 512 + (s & 3) * 4);
             return tl[(wd >> ApWord<AP_TILE>::SLOT_BITS) & (AP_MAXTILES - 1)] + (int)(wd & ((1u << ApWord<AP_TILE>::SLOT_BITS) - 1u));
         };
         // full keys of the survivors: the four largest f0 >= f1 >= f2 >= f3 and the slots of the first three
