@@ -126,9 +126,8 @@ __device__ __forceinline__ void traverse_from(const NodeLo* __restrict__ nlo, co
                     first1 = 2 * __popc(p1) >= __popc(m1 | m2);
                 }
                 if (m1 && m2) {
-                    if (lane == 0) stack[sp] = first1 ? c2 : c1;
+                    if (lane == 0) stack[sp] = first1 ? c2 : c1;       // the stack is lane 0's alone (see the pop): no warp-level ordering needed
                     sp++;
-                    __syncwarp();
                 }
                 bool take1 = m1 && (first1 || !m2);
                 node = take1 ? c1 : c2;
@@ -142,8 +141,10 @@ __device__ __forceinline__ void traverse_from(const NodeLo* __restrict__ nlo, co
         // pop until a still-needed node is found
         bool found = false;
         while (sp > 0) {
-            node = stack[--sp];
-            __syncwarp();                      // every lane has read the entry before lane 0 may overwrite the slot with a later push
+            int top = 0;
+            --sp;
+            if (lane == 0) top = stack[sp];
+            node = __shfl_sync(0xffffffffu, top, 0);     // only lane 0 ever touches the stack: no shared-memory hazard between lanes
             lo = nlo[node]; hi = nhi[node];
             float lb = box_lb(q.lx, q.ly, q.lz, q.hx, q.hy, q.hz, lo, hi);
             nmask = __ballot_sync(0xffffffffu, on && v.need(lb));

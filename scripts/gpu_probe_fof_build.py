@@ -4,6 +4,9 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from nbodylib_b200 import _lib
+if os.environ.get("NBK_LIB_FILE"):
+    _lib.LIB_PATH = os.path.join(ROOT, "nbodylib_b200", os.environ["NBK_LIB_FILE"])
 from nbodylib_b200 import KDTree
 from nbodylib_b200.synth import clustered_box
 ng = int(sys.argv[1]) if len(sys.argv) > 1 else 256
