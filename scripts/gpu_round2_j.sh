@@ -1,7 +1,7 @@
 #!/bin/bash
 # 4-GPU call: warp-aligned tree tests, sharded parity (world 2 and 4, torch driver + C ABI), bench at N = 2 and 4
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "warp_aligned or attached_halo" > gpurun_out/j_aligned_tests.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "warp_aligned" > gpurun_out/j_aligned_tests.log 2>&1
 echo "aligned tests exit $?" >> gpurun_out/j_aligned_tests.log; tail -5 gpurun_out/j_aligned_tests.log
 timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q -x > gpurun_out/j_sharded_tests.log 2>&1
 echo "sharded tests exit $?" >> gpurun_out/j_sharded_tests.log; tail -5 gpurun_out/j_sharded_tests.log
