@@ -16,7 +16,7 @@
 
 namespace nbk {
 
-constexpr int BALL_WARPS = 8;
+constexpr int BALL_WARPS = 4;      // small CTAs: a CTA waits for its slowest warp (see fof.cu)
 
 struct BallParams {
     const NodeLo* nlo; const NodeHi* nhi; int bucket;

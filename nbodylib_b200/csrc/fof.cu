@@ -16,7 +16,11 @@
 
 namespace nbk {
 
-constexpr int FOF_WARPS = 8;
+// Warps per CTA.  A CTA stays resident until its slowest warp is done, and the warps' costs differ by orders of magnitude (a group
+// inside a halo core against one in a void): small CTAs hand their slots back sooner.  Measured at 512^3: 3D link 51.1 ms with 8
+// warps, 39.6 ms with 4; 6D link 116.0 / 109.9 / 107.3 ms with 8 / 4 / 2.
+constexpr int FOF_WARPS = 4;
+constexpr int FOF6_WARPS = 2;      // the general (6D / fp64) link kernel
 
 __device__ __forceinline__ int uf_load(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
@@ -95,11 +99,11 @@ struct FofVisitor {
 };
 
 template <class S>
-__global__ void __launch_bounds__(FOF_WARPS * 32) fof_link_kernel(FofParams prm) {
-    __shared__ double s_tile[FOF_WARPS][192];
-    __shared__ int s_stack[FOF_WARPS][TRAV_STACK];
+__global__ void __launch_bounds__(FOF6_WARPS * 32) fof_link_kernel(FofParams prm) {
+    __shared__ double s_tile[FOF6_WARPS][192];
+    __shared__ int s_stack[FOF6_WARPS][TRAV_STACK];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    int64_t group = (int64_t)blockIdx.x * FOF_WARPS + w;
+    int64_t group = (int64_t)blockIdx.x * FOF6_WARPS + w;
     int64_t qi = group * 32 + lane;
     if (group * 32 >= prm.n) return;
     const Vec4<S>* P = reinterpret_cast<const Vec4<S>*>(prm.P);
@@ -439,8 +443,8 @@ void launch_fof(nbk_tree& t, FofArgs& a) {
     int64_t groups = (n + 31) / 32;
     NBK_CHECK(cudaEventRecord(t.ev2, st));
     if (t.store_bytes == 4 && a.mode == 0 && g_fof_screen) fof_link3f_kernel<<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
-    else if (t.store_bytes == 4) fof_link_kernel<float><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
-    else fof_link_kernel<double><<<div_up(groups, FOF_WARPS), FOF_WARPS * 32, 0, st>>>(p);
+    else if (t.store_bytes == 4) fof_link_kernel<float><<<div_up(groups, FOF6_WARPS), FOF6_WARPS * 32, 0, st>>>(p);
+    else fof_link_kernel<double><<<div_up(groups, FOF6_WARPS), FOF6_WARPS * 32, 0, st>>>(p);
     DevBuf<int32_t> excl2;
     const int32_t* excl_final = a.precheck_tree;
     if (a.attach) {
