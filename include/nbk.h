@@ -130,6 +130,17 @@ int nbk_knn_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, d
  * for m query points x[m][3]. */
 int nbk_knn_points(nbk_tree* t, int k, int64_t m, const double* x, int32_t* nn, double* d2, int flags);
 
+/* Replace KDTree::FindNearestPhase(Int_t tt, nn, dist2, Nsearch) and FindNearestPhase(Double_t* x, Double_t* v, ...) /
+ * (Coordinate x, Coordinate v, ...) (KDFindNearest.cxx:347-361,543-555; leaf code KDLeafNode.cxx:43-57,143-154) and with
+ * them KDTree::FindNearest(tt | x, ...) on a TPHS tree built with Aniso = -1 (KDFindNearest.cxx:260-262,300-301: the same
+ * search): the k nearest in the plain 6D phase-space distance PhaseDistSqd (DistFunc.h:41-49), positions and velocities in
+ * the caller's units.  Tree indices [q0,q1) / m points x[m][3], v[m][3]; outputs like nbk_knn_particles.  TPHYS or TPHS
+ * tree with velocities.  Non periodic particle form: the particle itself and 6D-coincident particles are not neighbours.
+ * Periodic tree: the position is searched in all 8 images (KDSplitNode.cxx:1153-1187; velocities are never reflected); the
+ * particle form returns the k nearest after the query itself.  The metric forms (Aniso >= 0, quirk Q4) are not built. */
+int nbk_knn_phase_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, double* d2, int flags);
+int nbk_knn_phase_points(nbk_tree* t, int k, int64_t m, const double* x, const double* v, int32_t* nn, double* d2, int flags);
+
 /* Replaces KDTree::FindNearestCheck(Int_t tt | Particle p | Coordinate x, check, params, nn, dist2, Nsearch) and
  * KDTree::FindNearestCriterion(Int_t tt | Particle p, cmp, params, nn, dist2, Nsearch) (KDFindNearest.cxx:363-441; leaf code
  * KDLeafNode.cxx:88-118,202-246): the k nearest among the particles i != target with 0 < d2 that pass the filters --

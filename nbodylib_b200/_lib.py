@@ -45,6 +45,7 @@ EXPORTS = [
     "nbk_calc_veldensity_particles", "nbk_calc_density_points", "nbk_calc_veldensity_points",
     "nbk_knn_filtered_particles", "nbk_knn_filtered_points", "nbk_calc_smooth_vel", "nbk_calc_smooth_veldisp",
     "nbk_set_option", "nbk_fof_roots", "nbk_union_pairs", "nbk_calc_smooth_velskew", "nbk_calc_smooth_velkurtosis",
+    "nbk_knn_phase_particles", "nbk_knn_phase_points",
 ]
 
 SHARDED_PATH = os.path.join(HERE, "libnbk_sharded.so")
@@ -110,6 +111,8 @@ def load():
     L.nbk_get_nodes.argtypes = [vp, C.POINTER(i64), vp, vp, vp, vp]
     L.nbk_knn_particles.argtypes = [vp, i32, i64, i64, vp, vp, i32]
     L.nbk_knn_points.argtypes = [vp, i32, i64, vp, vp, vp, i32]
+    L.nbk_knn_phase_particles.argtypes = [vp, i32, i64, i64, vp, vp, i32]
+    L.nbk_knn_phase_points.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32]
     L.nbk_knn_filtered_particles.argtypes = [vp, i32, i64, i64, i32, vp, vp, vp, vp, i32]
     L.nbk_knn_filtered_points.argtypes = [vp, i32, i64, vp, vp, i32, vp, vp, vp, vp, i32]
     L.nbk_calc_smooth_vel.argtypes = [vp, i32, vp, vp, i32]

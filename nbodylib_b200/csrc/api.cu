@@ -649,6 +649,72 @@ int nbk_knn_filtered_points(nbk_tree* t, int k, int64_t m, const double* x, cons
     NBK_API_END
 }
 
+// FindNearestPhase: the exact kernel with 6D keys (knn.cu, PHASE instantiation)
+static void knn_phase_call(nbk_tree* t, int k, int64_t q0, int64_t q1, int64_t m, const double* x, const double* v,
+                           int32_t* nn, double* d2, int flags) {
+    require_no_halo(t, "phase-space kNN");
+    // the walk prunes on the position half of the distance: positions must be the tree coordinates (the reference's
+    // FindNearestPhase walks whatever tree it is called on with GetPhase(cut_dim), KDSplitNode.cxx:69-95)
+    NBK_REQUIRE(t->treetype == NBK_TPHYS || t->treetype == NBK_TPHS, NBK_ERR_UNSUPPORTED, "FindNearestPhase needs a TPHYS or TPHS tree");
+    NBK_REQUIRE(t->vel4() != nullptr, NBK_ERR_ARG, "FindNearestPhase: the tree was built without velocities");
+    NBK_REQUIRE(k >= 1, NBK_ERR_ARG, "phase-space kNN: k must be >= 1");
+    TreeGuard guard(t);
+    const bool dev = flags & NBK_DEVICE_PTRS;
+    KnnArgs a;
+    a.k = k; a.phase = true;
+    a.periodic = t->periodic;
+    a.strict = true;          // the reference walks all 8 position images unconditionally (KDSplitNode.cxx:1153-1187): any exact schedule agrees
+    a.tree_form = true;       // periodic particle form: k + 1 slots, LoadNN(k) keeps the k farthest, i.e. drops the query itself (KDFindNearest.cxx:349,358-359)
+    a.out_ids = flags & NBK_OUT_IDS;
+    DevBuf<int32_t> dnn;
+    DevBuf<double> dx, dv, dd2;
+    int64_t rows;
+    if (x) {
+        NBK_REQUIRE(v, NBK_ERR_ARG, "FindNearestPhase at a point needs the query velocity");
+        a.mode = 1; a.q0 = 0; a.q1 = m; rows = m;
+        if (dev) { a.xq = x; a.vq = v; }
+        else {
+            dx.alloc((size_t)3 * m); dv.alloc((size_t)3 * m);
+            NBK_CHECK(cudaMemcpyAsync(dx.p, x, dx.bytes(), cudaMemcpyHostToDevice, t->stream));
+            NBK_CHECK(cudaMemcpyAsync(dv.p, v, dv.bytes(), cudaMemcpyHostToDevice, t->stream));
+            a.xq = dx.p; a.vq = dv.p;
+        }
+    } else {
+        NBK_REQUIRE(q0 >= 0 && q1 <= t->n && q0 <= q1, NBK_ERR_ARG, "phase-space kNN: bad query range");
+        a.mode = 0; a.q0 = q0; a.q1 = q1; rows = q1 - q0;
+    }
+    if (rows == 0) return;
+    if (dev) { a.nn = nn; a.d2 = d2; }
+    else {
+        if (nn) { dnn.alloc((size_t)rows * k); a.nn = dnn.p; }
+        if (d2) { dd2.alloc((size_t)rows * k); a.d2 = dd2.p; }
+    }
+    NBK_REQUIRE(a.nn || a.d2, NBK_ERR_ARG, "phase-space kNN: no output requested");
+    CallTimer tm(*t);
+    launch_knn(*t, a);
+    tm.stop();
+    t->last_kernel_ms = t->last_call_ms; t->last_launches = 1;
+    if (!dev) {
+        if (nn) NBK_CHECK(cudaMemcpyAsync(nn, dnn.p, dnn.bytes(), cudaMemcpyDeviceToHost, t->stream));
+        if (d2) NBK_CHECK(cudaMemcpyAsync(d2, dd2.p, dd2.bytes(), cudaMemcpyDeviceToHost, t->stream));
+    }
+    NBK_CHECK(cudaStreamSynchronize(t->stream));
+}
+
+int nbk_knn_phase_particles(nbk_tree* t, int k, int64_t q0, int64_t q1, int32_t* nn, double* d2, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t, NBK_ERR_ARG, "nbk_knn_phase_particles: null tree");
+    knn_phase_call(t, k, q0, q1, 0, nullptr, nullptr, nn, d2, flags);
+    NBK_API_END
+}
+int nbk_knn_phase_points(nbk_tree* t, int k, int64_t m, const double* x, const double* v, int32_t* nn, double* d2, int flags) {
+    NBK_API_BEGIN
+    NBK_REQUIRE(t && ((x && v) || m == 0) && m >= 0, NBK_ERR_ARG, "nbk_knn_phase_points: null argument");
+    if (m == 0) return NBK_OK;
+    knn_phase_call(t, k, 0, 0, m, x, v, nn, d2, flags);
+    NBK_API_END
+}
+
 // per-particle double output: tree-order device buffer -> caller (ID order unless NBK_TREE_ORDER)
 static void deliver_f64(nbk_tree* t, const double* src_tree, double* dst, int flags) {
     const int64_t n = t->n;

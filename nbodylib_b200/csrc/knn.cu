@@ -3,7 +3,9 @@
 //
 // Replaces (reference): LeafNode::FindNearestPos KDLeafNode.cxx:15-28,119-130; SplitNode::FindNearestPos
 // KDSplitNode.cxx:15-41; FindNearestPosPeriodic :1119-1148; PriorityQueue.h:14-85; drivers
-// KDFindNearest.cxx:247-334,462-554; KDTree::CalcDensity / CalcVelDensity KDCalcSmoothQuantities.cxx:203-389.
+// KDFindNearest.cxx:247-334,462-554; KDTree::CalcDensity / CalcVelDensity KDCalcSmoothQuantities.cxx:203-389;
+// the phase-space forms LeafNode::FindNearestPhase KDLeafNode.cxx:43-57,143-154, SplitNode::FindNearestPhase(Periodic)
+// KDSplitNode.cxx:69-95,260-289,1153-1187 and their drivers KDFindNearest.cxx:347-361,543-555 (PHASE instantiation).
 //
 // Layout: one warp = 32 queries adjacent in tree order; lane l owns query l and a bounded max-heap in shared
 // memory, slot-major / lane-minor ([slot][32]) so that lanes touching different slots never bank-conflict.
@@ -66,6 +68,7 @@ struct KnnParams {
     int64_t n_tree;                                   // particles of the main tree (= n unless a halo is attached)
     int aligned;                                      // the main tree's split rule (split_left)
     int tr_max;                                       // density kernel: transposed screening threshold (lanes needing a tile)
+    int phase;                                        // FindNearestPhase: the key is the 6D distance (exact kernel, PHASE instantiation)
 };
 
 // ================================================================================================ exact
@@ -109,14 +112,26 @@ struct WarpHeap {
     }
 };
 
-template <class S, bool FILTER = false>
+// PHASE: the heap key is the reference's 6D PhaseDistSqd (DistFunc.h:41-49: one left-to-right sum of the six squares,
+// positions first).  The tree stays the position tree: the position part of the distance is a lower bound of the 6D
+// distance, so the box test prunes conservatively and the k-nearest set is the one any exact search finds.
+__device__ __forceinline__ double phase_dist2_ref(double qx, double qy, double qz, double vx, double vy, double vz,
+                                                  const double* __restrict__ tile, int j) {
+    double d = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+    const double wx = __dsub_rn(vx, tile[96 + j]), wy = __dsub_rn(vy, tile[128 + j]), wz = __dsub_rn(vz, tile[160 + j]);
+    d = __dadd_rn(d, __dmul_rn(wx, wx));
+    d = __dadd_rn(d, __dmul_rn(wy, wy));
+    return __dadd_rn(d, __dmul_rn(wz, wz));
+}
+
+template <class S, bool FILTER = false, bool PHASE = false>
 struct KnnVisitor {
     const Vec4<S>* P;
-    const Vec4<S>* V;   // FILTER with a 6D criterion only
+    const Vec4<S>* V;   // FILTER with a 6D criterion, PHASE
     double* tile;       // [6][32]
     WarpHeap hp;
     double qx, qy, qz;
-    double vx, vy, vz;  // query velocity (FILTER, FOF6d)
+    double vx, vy, vz;  // query velocity (FILTER with FOF6d, PHASE)
     const int32_t* excl; int crit_mode; double cp0, cp1;
     double top;         // heap top (current k-th distance^2)
     float topf;         // top rounded up
@@ -127,6 +142,10 @@ struct KnnVisitor {
 
     __device__ __forceinline__ bool need(float lb) const { return lb < topf; }
     __device__ __forceinline__ void settop() { top = hp.h(0); topf = __double2float_ru(top); }
+    __device__ __forceinline__ double dist(int j) const {
+        if (PHASE) return phase_dist2_ref(qx, qy, qz, vx, vy, vz, tile, j);
+        return dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+    }
 
     __device__ __forceinline__ void leaf(int start, int cnt, int = 0, unsigned = 0) {
         for (int base = 0; base < cnt; base += 32) {
@@ -135,7 +154,7 @@ struct KnnVisitor {
             if ((int)lane < m) {
                 Vec4<S> c = P[start + base + lane];
                 tile[lane] = (double)c.x; tile[32 + lane] = (double)c.y; tile[64 + lane] = (double)c.z;
-                if (FILTER && crit_mode == 4) {
+                if (PHASE || (FILTER && crit_mode == 4)) {
                     Vec4<S> u = V[start + base + lane];
                     tile[96 + lane] = (double)u.x; tile[128 + lane] = (double)u.y; tile[160 + lane] = (double)u.z;
                 }
@@ -144,7 +163,7 @@ struct KnnVisitor {
             unsigned acc = 0;
 #pragma unroll 4
             for (int j = 0; j < m; j++) {
-                double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+                double d2 = dist(j);
                 bool ok = on && d2 < top;
                 if (target_form) ok = ok && (start + base + j != self) && d2 > 0.0;
                 if (FILTER) {
@@ -159,7 +178,7 @@ struct KnnVisitor {
                 if (acc) {
                     int j = __ffs(acc) - 1;
                     acc &= acc - 1;
-                    double d2 = dist2_ref(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j]);
+                    double d2 = dist(j);
                     if (d2 < top) { hp.replace_top(d2, start + base + j); settop(); }
                 }
             }
@@ -170,7 +189,7 @@ struct KnnVisitor {
 constexpr int EXACT_TILE_DOUBLES = 192;   // [6][32]: positions, and velocities for the FOF6d-filtered search
 static __host__ __device__ inline size_t exact_warp_bytes(int kcap) { return (size_t)kcap * 32 * 12 + EXACT_TILE_DOUBLES * 8 + TRAV_STACK * 4; }
 
-template <class S, bool FILTER>
+template <class S, bool FILTER, bool PHASE = false>
 __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
@@ -194,7 +213,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
     const int64_t qi = valid ? (prm.qlist ? (int64_t)prm.qlist[row] : prm.q0 + row) : 0;
     if (valid && prm.active && prm.mode == 0 && !prm.qlist && !prm.active[qi]) valid = false;
 
-    KnnVisitor<S, FILTER> v;
+    KnnVisitor<S, FILTER, PHASE> v;
     v.P = P; v.V = reinterpret_cast<const Vec4<S>*>(prm.V); v.tile = tile; v.hp = hp; v.lane = lane;
     v.excl = prm.cand_excl; v.crit_mode = prm.crit_mode; v.cp0 = prm.cp0; v.cp1 = prm.cp1;
     v.vx = v.vy = v.vz = 0;
@@ -207,10 +226,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_exact_kernel(KnnParams prm
             x0 = (double)c.x; y0 = (double)c.y; z0 = (double)c.z;
             v.self = (int)qi;
             v.target_form = !prm.periodic;      // periodic particle searches use the coordinate form (KDSplitNode.cxx:1075-1080)
-            if (FILTER && prm.crit_mode == 4) { Vec4<S> u = v.V[qi]; v.vx = (double)u.x; v.vy = (double)u.y; v.vz = (double)u.z; }
+            if (PHASE || (FILTER && prm.crit_mode == 4)) { Vec4<S> u = v.V[qi]; v.vx = (double)u.x; v.vy = (double)u.y; v.vz = (double)u.z; }
         } else {
             x0 = prm.xq[3 * qi]; y0 = prm.xq[3 * qi + 1]; z0 = prm.xq[3 * qi + 2];
-            if (FILTER && prm.crit_mode == 4) { v.vx = prm.vq[3 * qi]; v.vy = prm.vq[3 * qi + 1]; v.vz = prm.vq[3 * qi + 2]; }
+            if (PHASE || (FILTER && prm.crit_mode == 4)) { v.vx = prm.vq[3 * qi]; v.vy = prm.vq[3 * qi + 1]; v.vz = prm.vq[3 * qi + 2]; }
         }
     }
     v.qx = x0; v.qy = y0; v.qz = z0;
@@ -953,6 +972,7 @@ static void fill_common(KnnParams& p, nbk_tree& t, const KnnArgs& a) {
     p.kern = t.d_kernel; p.kernres = t.kernres;
     p.flag_count = nullptr; p.flag_list = nullptr;
     p.active = a.active;
+    p.phase = a.phase ? 1 : 0;
 }
 
 static void run_exact(nbk_tree& t, KnnParams& p, int64_t rows) {
@@ -964,7 +984,11 @@ static void run_exact(nbk_tree& t, KnnParams& p, int64_t rows) {
         NBK_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, KNN_WARPS * 32, smem, t.stream>>>(p);
     };
-    if (t.store_bytes == 4) { if (filter) go(knn_exact_kernel<float, true>); else go(knn_exact_kernel<float, false>); }
+    if (p.phase) {
+        NBK_REQUIRE(!filter, NBK_ERR_UNSUPPORTED, "phase-space kNN takes no candidate filters");
+        if (t.store_bytes == 4) go(knn_exact_kernel<float, false, true>); else go(knn_exact_kernel<double, false, true>);
+    }
+    else if (t.store_bytes == 4) { if (filter) go(knn_exact_kernel<float, true>); else go(knn_exact_kernel<float, false>); }
     else { if (filter) go(knn_exact_kernel<double, true>); else go(knn_exact_kernel<double, false>); }
     NBK_CHECK(cudaGetLastError());
 }
@@ -1007,13 +1031,18 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     t.last_launches = 0;
     t.last_flagged = 0;
     if (a.crit_mode == 4) NBK_REQUIRE(p.V != nullptr && (a.mode == 0 || a.vq != nullptr), NBK_ERR_ARG, "FOF6d-filtered search needs velocities");
+    if (a.phase) {
+        NBK_REQUIRE(p.V != nullptr && (a.mode == 0 || a.vq != nullptr), NBK_ERR_ARG, "phase-space search needs velocities");
+        NBK_REQUIRE(!a.rho && !a.hsm && !a.qlist && !a.smvel_out && !a.smdisp_out && !a.smhigh_out, NBK_ERR_UNSUPPORTED,
+                    "phase-space search returns neighbour lists only");
+    }
     if (a.smvel_out || a.smdisp_out || a.smhigh_out) {
         NBK_REQUIRE(a.mode == 0 && !a.qlist && a.rho_in && p.V, NBK_ERR_ARG, "smoothed velocity moments need particle queries, densities and velocities");
         NBK_REQUIRE(!a.smdisp_out || a.smvel_in, NBK_ERR_ARG, "CalcSmoothVelDisp needs the smoothed mean velocities");
         NBK_REQUIRE(!a.smhigh_out || (a.smvel_in && a.smdisp_in && (a.moment == 3 || a.moment == 4)), NBK_ERR_ARG, "CalcSmoothVelSkew / Kurtosis need the smoothed mean velocities and dispersions");
     }
     const bool smooth_only = a.mode == 0 && !a.periodic && !a.nn && !a.d2 && (a.rho || a.hsm) && !a.gather && !a.qlist && !a.cand_excl && !a.crit_mode &&
-                             !a.smvel_out && !a.smdisp_out && !a.smhigh_out;
+                             !a.smvel_out && !a.smdisp_out && !a.smhigh_out && !a.phase;
     if (smooth_only && !g_knn_exact && ap_range_ok(t)) {
         // ---- packed-word heap kernel (knn_hp_kernel), exact kernel for the flagged queries --------------------------
         p.kcap = a.k;
@@ -1092,6 +1121,7 @@ void launch_knn(nbk_tree& t, const KnnArgs& a) {
     p.kcap = a.k + ((a.periodic && a.mode == 0) ? 1 : 0);
     // the reference's periodic FindNearestCheck / FindNearestCriterion search k+1 and drop the nearest in every form
     if ((a.cand_excl || a.crit_mode) && a.periodic && a.tree_form) p.kcap = a.k + 1;
+    // FindNearestPhase(x, v) holds k slots; the particle form k + 1 with the nearest dropped (tree_form set by the caller)
     run_exact(t, p, rows);
     t.last_launches += 1;
 }

@@ -125,6 +125,7 @@ struct KnnArgs {
     const double* smdisp_in = nullptr;   // dispersions (n x 9), input of the skewness / kurtosis
     double* smhigh_out = nullptr;        // n x 3: skewness (moment 3) or kurtosis (moment 4)
     int moment = 0;
+    bool phase = false;                  // FindNearestPhase: 6D distance keys (needs velocities; mode 1: vq)
 };
 void launch_knn(nbk_tree& t, const KnnArgs& a);
 bool set_knn_option(const char* name, int64_t value);   // nbk_set_option names starting with "knn_"

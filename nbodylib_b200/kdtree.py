@@ -44,11 +44,12 @@ class KDTree:
     KSPH, KGAUSS, KEPAN, KTH = 0, 1, 2, 3
 
     def __init__(self, pos, vel=None, mass=None, bucket_size=16, TreeType=TPHYS, KernType=KEPAN, KernRes=1000,
-                 SplittingCriterion=0, Period=None, device=-1, flags=0):
+                 SplittingCriterion=0, Period=None, device=-1, flags=0, Aniso=0):
         """Mirror of KDTree(Particle*, numparts, bucket_size, TreeType, KernType, KernRes, SplittingCriterion,
         Aniso, ScaleSpace, Period) (KDTree.h:229-245) with the particle array given as pos/vel/mass columns."""
         self._lib = L.load()
         self._h = C.c_void_p()
+        self.anisotropic = int(Aniso)     # -1: FindNearest on a TPHS tree is the plain 6D search (KDTree.h:157-158)
         dev_in = _is_torch(pos)
         keep = []
 
@@ -191,6 +192,12 @@ class KDTree:
 
     def FindNearest(self, Nsearch=64, **kw):
         """FindNearest(Int_t tt, ...) (KDFindNearest.cxx:247-318): on a periodic tree the target itself is dropped."""
+        if self.info.treetype == TPHS:
+            # KDFindNearest.cxx:260-262,300-301: phase-space search when the tree was built with Aniso = -1; the metric
+            # searches of Aniso >= 0 (quirk Q4) are not built
+            if self.anisotropic != -1:
+                raise L.NbkError(-3, "FindNearest on a TPHS tree with Aniso >= 0 is the reference's metric search (no device implementation)")
+            return self.FindNearestPhase(Nsearch, **kw)
         kw.setdefault("tree_form", True)
         return self.FindNearestPos(Nsearch, **kw)
 
@@ -202,6 +209,28 @@ class KDTree:
         d2 = np.empty((m, Nsearch), dtype=np.float64)
         flags = (L.OUT_IDS if ids else 0) | (L.STRICT_PERIODIC if strict else 0)
         L.check(self._lib.nbk_knn_points(self._h, int(Nsearch), m, _ptr(x), _ptr(nn), _ptr(d2), flags))
+        return nn, d2
+
+    def FindNearestPhase(self, Nsearch=64, q0=0, q1=None, x=None, v=None, ids=False):
+        """Range / batched form of KDTree::FindNearestPhase(Int_t tt, ...) and FindNearestPhase(Double_t *x, Double_t *v, ...)
+        (KDFindNearest.cxx:347-361,543-555): the Nsearch nearest in the plain 6D distance PhaseDistSqd (DistFunc.h:41-49).  Also
+        what FindNearest does on a TPHS tree built with Aniso = -1 (KDFindNearest.cxx:260-262).  Rows = tree indices q0..q1,
+        or the points (x, v)."""
+        flags = L.OUT_IDS if ids else 0
+        if x is not None:
+            x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+            v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
+            assert x.shape == v.shape
+            rows = len(x)
+        else:
+            q1 = self.n if q1 is None else q1
+            rows = q1 - q0
+        nn = np.empty((rows, Nsearch), dtype=np.int32)
+        d2 = np.empty((rows, Nsearch), dtype=np.float64)
+        if x is not None:
+            L.check(self._lib.nbk_knn_phase_points(self._h, int(Nsearch), rows, _ptr(x), _ptr(v), _ptr(nn), _ptr(d2), flags))
+        else:
+            L.check(self._lib.nbk_knn_phase_particles(self._h, int(Nsearch), int(q0), int(q1), _ptr(nn), _ptr(d2), flags))
         return nn, d2
 
     def _knn_filtered(self, Nsearch, cmp, params, check, q0, q1, x, v, ids, tree_form):

@@ -6,6 +6,7 @@
  *    ctor (Particle*, numparts, bucket_size, TreeType, KernType, KernRes, SplittingCriterion, Aniso, ScaleSpace, Period)
  *    GetNumNodes / GetNumLeafNodes / GetBucketSize / GetTreeType / GetKernType / GetKernNorm / GetPeriod
  *    FindNearest / FindNearestPos (Int_t tt | Double_t* x | Coordinate | whole system)
+ *    FindNearestPhase (Int_t tt | Double_t* x, v | Coordinate x, v | whole system); FindNearest on a TPHS tree with Aniso = -1
  *    SearchBallPosTagged (Int_t tt | Double_t* x | Coordinate; array and vector forms), dense SearchBall / SearchBallPos
  *    SearchCriterionTagged (Int_t tt | Particle&; array and vector forms), dense SearchCriterion (FOF3d / FOF6d)
  *    CalcDensity, CalcVelDensity, CalcSmoothingScale (new: north star), CalcDensityParticle, CalcVelDensityParticle,
@@ -20,7 +21,7 @@
  *  FOF results are new[]-allocated arrays indexed by ID that the caller delete[]s; the destructor sorts the array
  *  back by ID unless OverWriteInputOrder() was called (KDTree.cxx:1340-1362).
  *  Differences: errors throw std::runtime_error instead of printf+exit; calls without a device implementation
- *  (TPROJ/TMETRIC trees, host FOFcompfunc callbacks other than FOF3d/FOF6d, CalcSmoothVelSkew/Kurtosis, FOFNN*) are absent or throw -- there is
+ *  (TPROJ/TMETRIC trees, host FOFcompfunc callbacks other than FOF3d/FOF6d, the metric searches of TPHS trees with Aniso >= 0, FOFNN*) are absent or throw -- there is
  *  no CPU fallback.  Per-particle calls launch one small kernel each; loops over all particles should use the
  *  whole-system forms.
  */
@@ -122,6 +123,7 @@ private:
     nbk_tree* h = nullptr;
     Particle* bucket = nullptr;
     Int_t numparts = 0;
+    int anisotropic = 0;      // the constructor's Aniso: -1 = plain phase-space search on a TPHS tree (KDTree.h:157-158)
     bool iresetorder = true;
     nbk_info info{};
     Double_t* period = nullptr;
@@ -208,8 +210,8 @@ public:
            int SplittingCriterion = KDTREE_SPLIT_SPREAD, int Aniso = 0, int ScaleSpace = 0, Double_t* Period = NULL,
            Double_t** metric = NULL, bool iBuildInParallel = true, bool iKeepInputOrder = false, Double_t Rdistadapt = -1,
            Double_t AdaptiveMedianFac = 0.0, Int_t min_bucket_size = 16)
-        : bucket(p), numparts(nparts) {
-        (void)Aniso; (void)metric; (void)iBuildInParallel; (void)min_bucket_size;
+        : bucket(p), numparts(nparts), anisotropic(Aniso) {
+        (void)metric; (void)iBuildInParallel; (void)min_bucket_size;
         if (ScaleSpace) throw std::runtime_error("nbk shim: ScaleSpace has no device implementation");
         if (iKeepInputOrder || Rdistadapt > 0 || AdaptiveMedianFac > 0) throw std::runtime_error("nbk shim: adaptive / keep-order builds have no device implementation");
         NbkRawBuf<Double_t> mass((size_t)numparts);
@@ -261,7 +263,28 @@ public:
 
     // ---- nearest neighbours (KDFindNearest.cxx:247-334, 444-554) ----------------------------------------------
     void FindNearestPos(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { knn_cached(tt, nn, dist2, Nsearch, 0); }
-    void FindNearest(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { knn_cached(tt, nn, dist2, Nsearch, NBK_KNN_TREE_FORM); }
+    /// On a TPHS tree FindNearest is the phase-space search when the tree was built with Aniso = -1 (KDFindNearest.cxx:260-262,
+    /// 300-301); with the constructor default Aniso = 0 the reference takes its metric path (quirk Q4), which is not built.
+    void FindNearest(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        if (phase_tree("FindNearest")) knn_cached(tt, nn, dist2, Nsearch, 0, -3);
+        else knn_cached(tt, nn, dist2, Nsearch, NBK_KNN_TREE_FORM);
+    }
+    // ---- phase-space nearest neighbours (KDFindNearest.cxx:347-361, 543-555; PhaseDistSqd, DistFunc.h:41-49) ------
+    void FindNearestPhase(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { knn_cached(tt, nn, dist2, Nsearch, 0, -3); }
+    void FindNearestPhase(Double_t* x, Double_t* v, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        std::vector<double> d2(Nsearch);
+        std::vector<int32_t> n32(Nsearch);
+        double xx[3] = {(double)x[0], (double)x[1], (double)x[2]}, vv[3] = {(double)v[0], (double)v[1], (double)v[2]};
+        {
+            std::lock_guard<std::mutex> g(dev_mutex);
+            check(nbk_knn_phase_points(h, (int)Nsearch, 1, xx, vv, n32.data(), d2.data(), 0));
+        }
+        for (Int_t j = 0; j < Nsearch; j++) { nn[j] = n32[j]; dist2[j] = d2[j]; }
+    }
+    void FindNearestPhase(Coordinate x, Coordinate v, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        FindNearestPhase(x.GetCoord(), v.GetCoord(), nn, dist2, Nsearch);
+    }
+    void FindNearestPhase(Int_t** nn, Double_t** dist2, Int_t Nsearch = 64) { knn_all(nn, dist2, Nsearch, 0, true); }
     void FindNearestPos(Double_t* x, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
         std::vector<double> d2(Nsearch);
         std::vector<int32_t> n32(Nsearch);
@@ -272,11 +295,18 @@ public:
         }
         for (Int_t j = 0; j < Nsearch; j++) { nn[j] = n32[j]; dist2[j] = d2[j]; }
     }
-    void FindNearest(Double_t* x, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { FindNearestPos(x, nn, dist2, Nsearch); }
+    /// on a TPHS tree x holds six numbers, position then velocity (KDFindNearest.cxx:474-477)
+    void FindNearest(Double_t* x, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
+        if (phase_tree("FindNearest")) FindNearestPhase(x, x + 3, nn, dist2, Nsearch);
+        else FindNearestPos(x, nn, dist2, Nsearch);
+    }
     void FindNearestPos(Coordinate x, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { FindNearestPos(x.GetCoord(), nn, dist2, Nsearch); }
     /// whole-system forms: nn[i][j], dist2[i][j] for every tree index i
     void FindNearestPos(Int_t** nn, Double_t** dist2, Int_t Nsearch = 64) { knn_all(nn, dist2, Nsearch, 0); }
-    void FindNearest(Int_t** nn, Double_t** dist2, Int_t Nsearch = 64) { knn_all(nn, dist2, Nsearch, NBK_KNN_TREE_FORM); }
+    void FindNearest(Int_t** nn, Double_t** dist2, Int_t Nsearch = 64) {
+        if (phase_tree("FindNearest")) knn_all(nn, dist2, Nsearch, 0, true);
+        else knn_all(nn, dist2, Nsearch, NBK_KNN_TREE_FORM);
+    }
 
     // ---- filtered nearest neighbours (KDFindNearest.cxx:363-441) ------------------------------------------------
     /// Per-particle forms are served from the per-thread block cache like FindNearest(tt).  The caller's FOFcheckfunc runs on
@@ -720,12 +750,18 @@ private:
         }
         return chk_vals.data();
     }
-    /// crit == -2: plain search; otherwise filtered (crit -1: check function only, >= 0: NBK_FOF3D / NBK_FOF6D)
+    /// true on a TPHS tree built with Aniso = -1; throws on a TPHS tree with a metric (Aniso >= 0)
+    bool phase_tree(const char* who) const {
+        if (info.treetype != TPHS) return false;
+        if (anisotropic != -1) throw std::runtime_error(std::string("nbk shim: ") + who + " on a TPHS tree with Aniso >= 0 is the reference's metric search, which has no device implementation (build the tree with Aniso = -1 for the plain 6D search)");
+        return true;
+    }
+    /// crit == -2: plain search; -3: phase-space search; otherwise filtered (crit -1: check function only, >= 0: NBK_FOF3D / NBK_FOF6D)
     void knn_cached(Int_t tt, Int_t* nn, Double_t* dist2, Int_t k, int flags, int crit = -2, FOFcheckfunc checkfn = nullptr, Double_t* params = NULL) {
         if (tt < 0 || tt >= numparts) throw std::runtime_error("nbk shim: particle index out of range");
         KnnBlock& c = tls_block();
         double pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (crit != -2 && params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];      // criterion AND check forms: compared by value
+        if (crit > -2 && params) for (int j = 0; j < 8; j++) pr[j] = (double)params[j];       // criterion AND check forms: compared by value
         bool same = c.serial == serial && c.k == k && c.flags == flags && c.crit == crit && c.checkfn == checkfn && tt >= c.b0 && tt < c.b1;
         for (int j = 0; same && j < 8; j++) same = c.params[j] == pr[j];
         if (!same) {
@@ -736,6 +772,9 @@ private:
             if (crit == -2) {
                 std::lock_guard<std::mutex> g(dev_mutex);
                 check(nbk_knn_particles(h, (int)k, b0, b1, c.nn.data(), c.d2.data(), flags));
+            } else if (crit == -3) {
+                std::lock_guard<std::mutex> g(dev_mutex);
+                check(nbk_knn_phase_particles(h, (int)k, b0, b1, c.nn.data(), c.d2.data(), flags));
             } else {
                 const int32_t* chk = checkfn ? check_values(checkfn, params) : NULL;                     // tree order, once per (function, params)
                 std::lock_guard<std::mutex> g(dev_mutex);
@@ -770,7 +809,7 @@ private:
         }
         for (size_t j = 0; j < n32.size(); j++) { nn[j] = n32[j]; dist2[j] = d2[j]; }
     }
-    void knn_all(Int_t** nn, Double_t** dist2, Int_t k, int flags) {
+    void knn_all(Int_t** nn, Double_t** dist2, Int_t k, int flags, bool phase = false) {
         const Int_t chunk = 1 << 20;
         std::vector<int32_t> n32((size_t)std::min(chunk, numparts) * k);
         std::vector<double> d2(n32.size());
@@ -778,7 +817,8 @@ private:
             Int_t q1 = std::min(numparts, q0 + chunk);
             {
                 std::lock_guard<std::mutex> g(dev_mutex);
-                check(nbk_knn_particles(h, (int)k, q0, q1, n32.data(), d2.data(), flags));
+                check(phase ? nbk_knn_phase_particles(h, (int)k, q0, q1, n32.data(), d2.data(), flags)
+                            : nbk_knn_particles(h, (int)k, q0, q1, n32.data(), d2.data(), flags));
             }
             for (Int_t i = q0; i < q1; i++)
                 for (Int_t j = 0; j < k; j++) { nn[i][j] = n32[(size_t)(i - q0) * k + j]; dist2[i][j] = d2[(size_t)(i - q0) * k + j]; }

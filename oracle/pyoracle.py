@@ -89,6 +89,8 @@ class Port:
         L.orc_fof.argtypes = [C.c_long, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_int, _ip]
         L.orc_ball_points.restype = C.c_long
         L.orc_ball_points.argtypes = [C.c_long, _dp, _dp, C.c_double, C.c_long, _dp, _lp, _ip, C.c_long]
+        L.orc_knn_phase_particles.argtypes = [C.c_long, _dp, _dp, C.c_int, _dp, C.c_long, _ip, _ip, _dp]
+        L.orc_knn_phase_points.argtypes = [C.c_long, _dp, _dp, C.c_int, _dp, C.c_long, _dp, _dp, _ip, _dp]
 
     def kernel_table(self, nd, kerntype, kernres):
         t = np.zeros(kernres)
@@ -109,6 +111,23 @@ class Port:
         ids = np.zeros((len(x), k), dtype=np.int32)
         d2 = np.zeros((len(x), k))
         self.lib.orc_knn_points(len(pos), _d(pos), k, _d(_f64(period)), strict, len(x), _d(x), _i(ids), _d(d2))
+        return ids, d2
+
+    def knn_phase_particles(self, pos, vel, qids, k, period=None):
+        """FindNearestPhase(tt): 6D neighbours of the particles `qids` (IDs)"""
+        pos, vel = _f64(pos), _f64(vel)
+        q = np.ascontiguousarray(qids, dtype=np.int32)
+        ids = np.zeros((len(q), k), dtype=np.int32)
+        d2 = np.zeros((len(q), k))
+        self.lib.orc_knn_phase_particles(len(pos), _d(pos), _d(vel), k, _d(_f64(period)), len(q), _i(q), _i(ids), _d(d2))
+        return ids, d2
+
+    def knn_phase_points(self, pos, vel, x, v, k, period=None):
+        """FindNearestPhase(x, v): 6D neighbours of arbitrary phase-space points"""
+        pos, vel, x, v = _f64(pos), _f64(vel), _f64(x), _f64(v)
+        ids = np.zeros((len(x), k), dtype=np.int32)
+        d2 = np.zeros((len(x), k))
+        self.lib.orc_knn_phase_points(len(pos), _d(pos), _d(vel), k, _d(_f64(period)), len(x), _d(x), _d(v), _i(ids), _d(d2))
         return ids, d2
 
     def density(self, pos, mass, k, kerntype=2, kernres=1000):
@@ -209,6 +228,8 @@ class Ref:
             L.ref_knn_filtered.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_long, C.c_long, C.c_long, _dp, _dp, _ip, _dp]
             L.ref_calc_smooth_vel.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
             L.ref_calc_smooth_higher.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+            L.ref_knn_phase_particles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, _ip, _ip, _dp]
+            L.ref_knn_phase_points.argtypes = [C.c_void_p, C.c_int, C.c_long, _dp, _dp, _ip, _dp]
             L.ref_max_threads.restype = C.c_int
             L.ref_sizeof_particle.restype = C.c_int
             cls._lib = L
@@ -288,6 +309,21 @@ class Ref:
         ids = np.zeros((len(x), k), dtype=np.int32)
         d2 = np.zeros((len(x), k))
         self.last_seconds = self.lib().ref_knn_points(self.h, k, len(x), _d(x), _i(ids), _d(d2))
+        return ids, d2
+
+    def knn_phase_particles(self, qids, k, which=0):
+        """FindNearestPhase(tt) (which = 0) or FindNearest(tt) (which = 1) for a list of particle IDs"""
+        q = np.ascontiguousarray(qids, dtype=np.int32)
+        ids = np.zeros((len(q), k), dtype=np.int32)
+        d2 = np.zeros((len(q), k))
+        self.lib().ref_knn_phase_particles(self.h, which, k, len(q), _i(q), _i(ids), _d(d2))
+        return ids, d2
+
+    def knn_phase_points(self, x, v, k):
+        x, v = _f64(x), _f64(v)
+        ids = np.zeros((len(x), k), dtype=np.int32)
+        d2 = np.zeros((len(x), k))
+        self.lib().ref_knn_phase_points(self.h, k, len(x), _d(x), _d(v), _i(ids), _d(d2))
         return ids, d2
 
     def ball_particles(self, qids, r2):

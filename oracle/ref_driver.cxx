@@ -567,4 +567,45 @@ void ref_calc_smooth_higher(void* hv, int k, double* skew_by_id, double* kurt_by
     delete[] sv; delete[] sd; delete[] sk; delete[] ku;
 }
 
+/* FindNearestPhase(tt) for the given particle IDs (which = 0) or FindNearest(tt) (which = 1: on a TPHS tree built with
+ * anisotropic = -1 the same 6D search, KDFindNearest.cxx:260-262,300-301).  Neighbour particle IDs, rows ascending. */
+void ref_knn_phase_particles(void* hv, int which, int k, long m, const int* qids, int* out_ids, double* out_d2) {
+    RefTree* h = (RefTree*)hv;
+    vector<Int_t> where(h->n);
+    for (Int_t i = 0; i < h->n; i++) where[h->parts[i].GetID()] = i;
+#pragma omp parallel
+    {
+        vector<Int_t> nn(k);
+        vector<Double_t> d2(k);
+#pragma omp for schedule(guided)
+        for (long q = 0; q < m; q++) {
+            Int_t tt = where[qids[q]];
+            if (which == 0) h->tree->FindNearestPhase(tt, nn.data(), d2.data(), k);
+            else h->tree->FindNearest(tt, nn.data(), d2.data(), k);
+            for (int j = 0; j < k; j++) {
+                out_ids[q * k + j] = nn[j] >= 0 ? (int)h->parts[nn[j]].GetID() : -1;
+                out_d2[q * k + j] = d2[j];
+            }
+        }
+    }
+}
+/* FindNearestPhase(Double_t* x, Double_t* v, ...) about arbitrary phase-space points */
+void ref_knn_phase_points(void* hv, int k, long m, const double* x, const double* v, int* out_ids, double* out_d2) {
+    RefTree* h = (RefTree*)hv;
+#pragma omp parallel
+    {
+        vector<Int_t> nn(k);
+        vector<Double_t> d2(k);
+#pragma omp for schedule(guided)
+        for (long q = 0; q < m; q++) {
+            Double_t xx[3] = {x[3 * q], x[3 * q + 1], x[3 * q + 2]}, vv[3] = {v[3 * q], v[3 * q + 1], v[3 * q + 2]};
+            h->tree->FindNearestPhase(xx, vv, nn.data(), d2.data(), k);
+            for (int j = 0; j < k; j++) {
+                out_ids[q * k + j] = nn[j] >= 0 ? (int)h->parts[nn[j]].GetID() : -1;
+                out_d2[q * k + j] = d2[j];
+            }
+        }
+    }
+}
+
 }  // extern "C"

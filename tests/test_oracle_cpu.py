@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from tests.util import ROOT, canon, csr_rows_sorted, load_golden, rows_equal_as_sets
+from tests.util import ROOT, canon, csr_rows_sorted, load_golden, load_golden_phase, rows_equal_as_sets
 
 
 @pytest.fixture(scope="module")
@@ -82,6 +82,51 @@ def test_port_ball_matches_reference_golden(port, G, tag):
     off, idx = port.ball_points(G["pos"], G["xq"], (3 * float(G["ll"])) ** 2, period)
     assert np.array_equal(off, G["ball_off_" + tag])
     assert np.array_equal(np.concatenate(csr_rows_sorted(off, idx)), G["ball_idx_" + tag])
+
+
+@pytest.mark.parametrize("tag", ["np", "p"])
+def test_port_phase_knn_matches_reference_golden(port, G, tag):
+    """FindNearestPhase(tt) / FindNearestPhase(x, v) (KDFindNearest.cxx:347-361,543-555): tests/golden/ref_phase.npz holds the
+    reference's rows on a TPHS tree built with Aniso = -1"""
+    H = load_golden_phase()
+    period = None if tag == "np" else np.ones(3)
+    k = int(H["k"])
+    ids, d2 = port.knn_phase_particles(G["pos"], H["vel"], H["qsel"], k, period=period)
+    assert np.array_equal(d2, H["phase_d2_" + tag]) and rows_equal_as_sets(ids, H["phase_ids_" + tag])
+    assert not np.any(ids == H["qsel"][:, None])                     # the particle itself is never returned, periodic or not
+    ids, d2 = port.knn_phase_points(G["pos"], H["vel"], G["xq"], H["vq"], k, period=period)
+    assert np.array_equal(d2, H["phasex_d2_" + tag]) and rows_equal_as_sets(ids, H["phasex_ids_" + tag])
+    # the 6D key is the position part plus the velocity part: never below the position distance to the same particle
+    dx = G["pos"][ids] - G["xq"][:, None, :]
+    if period is not None:
+        dx -= np.round(dx)
+    assert np.all(d2 >= (dx ** 2).sum(-1) * (1 - 1e-12))
+
+
+def test_phase_port_vs_live_reference(port):
+    """the phase-space port against the reference itself on a fresh seed: TPHS tree (Aniso = -1, both FindNearestPhase(tt) and
+    FindNearest(tt)) and TPHYS tree (FindNearestPhase walks whatever tree it is called on), periodic and not"""
+    from oracle.pyoracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    from nbodylib_b200.synth import clustered_small
+    pos, vel, mass = clustered_small(5000, seed=7)
+    vel = (vel * (0.1 / vel.std())).astype(np.float32).astype(np.float64)
+    rng = np.random.default_rng(3)
+    qs = rng.permutation(5000)[:1500].astype(np.int32)
+    xq = rng.random((200, 3))
+    vq = rng.normal(size=(200, 3)) * 0.1
+    for period in (None, np.ones(3)):
+        pi, pd = port.knn_phase_particles(pos, vel, qs, 20, period=period)
+        px, pxd = port.knn_phase_points(pos, vel, xq, vq, 20, period=period)
+        for tt in (Ref.TPHS, Ref.TPHYS):
+            R = Ref(pos, vel, mass, treetype=tt, period=period, aniso=-1)
+            for which in ((0, 1) if tt == Ref.TPHS else (0,)):
+                ids, d2 = R.knn_phase_particles(qs, 20, which=which)
+                assert np.array_equal(d2, pd) and rows_equal_as_sets(ids, pi)
+            ids, d2 = R.knn_phase_points(xq, vq, 20)
+            assert np.array_equal(d2, pxd) and rows_equal_as_sets(ids, px)
+            R.close()
 
 
 def test_port_vs_live_reference(port):

@@ -32,5 +32,13 @@ def load_golden_extra():
     return {k: g[k] for k in g.files}
 
 
+GOLDEN_PHASE = os.path.join(ROOT, "tests", "golden", "ref_phase.npz")
+
+
+def load_golden_phase():
+    g = np.load(GOLDEN_PHASE)
+    return {k: g[k] for k in g.files}
+
+
 # numpy restatements of the reference algorithms live with the oracle (oracle/restate_np.py); re-exported for the tests
 from oracle.restate_np import ball_min_d2, crit_rows, gather_density, gather_veldensity, reflect_images, wsm_table  # noqa: E402,F401
