@@ -124,6 +124,7 @@ private:
     Particle* bucket = nullptr;
     Int_t numparts = 0;
     int anisotropic = 0;      // the constructor's Aniso: -1 = plain phase-space search on a TPHS tree (KDTree.h:157-158)
+    Int_t bucket_size_caller = 16;
     bool iresetorder = true;
     nbk_info info{};
     Double_t* period = nullptr;
@@ -210,10 +211,21 @@ public:
            int SplittingCriterion = KDTREE_SPLIT_SPREAD, int Aniso = 0, int ScaleSpace = 0, Double_t* Period = NULL,
            Double_t** metric = NULL, bool iBuildInParallel = true, bool iKeepInputOrder = false, Double_t Rdistadapt = -1,
            Double_t AdaptiveMedianFac = 0.0, Int_t min_bucket_size = 16)
-        : bucket(p), numparts(nparts), anisotropic(Aniso) {
-        (void)metric; (void)iBuildInParallel; (void)min_bucket_size;
+        : bucket(p), numparts(nparts), anisotropic(Aniso), bucket_size_caller(bucket_size) {
+        (void)metric; (void)iBuildInParallel;
+        // ScaleSpace: the reference accumulates into xmean[] without ever initialising it and starts the variance sums from 1.0
+        // (KDTree.h:140, KDTree.cxx:1063-1083,1293): its result is not defined, so there is nothing to be faithful to
         if (ScaleSpace) throw std::runtime_error("nbk shim: ScaleSpace has no device implementation");
-        if (iKeepInputOrder || Rdistadapt > 0 || AdaptiveMedianFac > 0) throw std::runtime_error("nbk shim: adaptive / keep-order builds have no device implementation");
+        if (iKeepInputOrder) throw std::runtime_error("nbk shim: keep-order builds have no device implementation");
+        // Rdistadapt / AdaptiveMedianFac / SplittingCriterion shape the REFERENCE's tree (where leaves stop: size <= b and radius <
+        // Rdistadapt, or size <= min_bucket_size, KDTree.cxx:988-991; where the cut goes, :785-960; which dimension is cut,
+        // :459-504).  Every search, density and FOF result is a function of the particle set alone, so they are served from the
+        // device tree, whose shape follows the median / largest-spread rule with leaves of up to min_bucket_size particles in the
+        // adaptive case; GetNumNodes / GetNumLeafNodes / GetRoot describe the device tree.
+        if (Rdistadapt > 0) bucket_size = std::max<Int_t>(1, std::min(bucket_size, min_bucket_size));
+        (void)AdaptiveMedianFac;
+        if (SplittingCriterion < KDTREE_SPLIT_SPREAD || SplittingCriterion > KDTREE_SPLIT_MAXINTERPARTICLESPACING) throw std::runtime_error("nbk shim: unknown splitting criterion");
+        SplittingCriterion = KDTREE_SPLIT_SPREAD;
         NbkRawBuf<Double_t> mass((size_t)numparts);
         NBK_SHIM_PARALLEL_FOR
         for (Int_t i = 0; i < numparts; i++) { bucket[i].SetID(i); mass[i] = bucket[i].GetMass(); }      // KDTree.cxx:1291
@@ -254,7 +266,7 @@ public:
 
     Int_t GetNumNodes() { return info.num_nodes; }
     Int_t GetNumLeafNodes() { return info.num_leaves; }
-    Int_t GetBucketSize() { return info.bucket; }
+    Int_t GetBucketSize() { return bucket_size_caller; }
     Int_t GetTreeType() { return info.treetype; }
     Int_t GetKernType() { return info.kerntype; }
     Double_t GetKernNorm() { return info.kernnorm; }

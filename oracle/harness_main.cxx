@@ -6,11 +6,14 @@
  * its include path and link line.  oracle/Makefile target `harness` -> oracle/_ref/test_kdtree_shim
  * (built where /root/reference exists; the binary travels to the GPU box).
  *
- * The harness functions are called for the tree types whose calls have device implementations:
- *   Physical (TPHYS, b = 16): kdtree_test_NN, kdtree_test_ballsearch, kdtree_test_FOF
- *   Velocity (TVEL,  b = 16): kdtree_test_NN
- *   Phase    (TPHS,  b = 16): kdtree_test_ballsearch, kdtree_test_FOF        (its FindNearest takes the reference's metric path)
- * (the adaptive-radius "Rdist" builds have none), followed by brute-force checks of what the harness only prints.
+ * The harness functions are called for its five tree types (test_kdtree.cxx:48-58) where the calls have device implementations:
+ *   Physical                (TPHYS, b = 16): kdtree_test_NN, kdtree_test_ballsearch, kdtree_test_FOF
+ *   Physical Rdist          (TPHYS, b = 0.01 N, Rdistadapt = 0.01): the same three
+ *   Physical Rdist Adaptfac (TPHYS, b = 0.01 N, Rdistadapt = 0.01, AdaptiveMedianFac = 0.1): the same three
+ *   Velocity                (TVEL,  b = 16): kdtree_test_NN
+ *   Phase                   (TPHS,  b = 16): kdtree_test_ballsearch, kdtree_test_FOF   (its FindNearest takes the reference's metric path: Aniso = 0)
+ * followed by brute-force checks of what the harness only prints.  The Rdist options shape the reference's tree only; the
+ * shim serves the same results from the device tree (shim/KDTree.h constructor).
  */
 #include <cmath>
 #include <cstdio>
@@ -42,10 +45,14 @@ int main(int argc, char** argv) {
     std::vector<NBody::Particle> parts = generate_vector(N, 0.1, 100);
     std::vector<NBody::Particle> input(parts);
     const int k = 16;
-    for (int which = 0; which < 3; which++) {
+    const char* names[5] = {"Physical", "Velocity", "Phase", "Physical Rdist", "Physical Rdist Adaptfac"};
+    for (int cfg = 0; cfg < 5; cfg++) {
+        const int which = cfg < 3 ? cfg : 0;             // 0: position tree, 1: velocity tree, 2: phase-space tree
         const int tt = which == 0 ? NBody::KDTree::TPHYS : (which == 1 ? NBody::KDTree::TVEL : NBody::KDTree::TPHS);
-        std::printf("==== %s tree\n", which == 0 ? "Physical" : (which == 1 ? "Velocity" : "Phase"));
-        NBody::KDTree* tree = build_kdtree(parts, 16, tt, -1, 0.0, 0.0);
+        std::printf("==== %s tree\n", names[cfg]);
+        // arguments of the reference's TreeTypes() table (test_kdtree.cxx:48-58)
+        NBody::KDTree* tree = cfg < 3 ? build_kdtree(parts, 16, tt, -1, 0.0, 0.0) : build_kdtree(parts, 0, tt, 0.01, cfg == 4 ? 0.1 : 0.0, 0.01);
+        if (cfg >= 3) EXPECT(tree->GetBucketSize() == (Int_t)(0.01 * N), "GetBucketSize() returns the caller's leaf size");
         EXPECT(tree->GetNumLeafNodes() > 0 && tree->GetNumNodes() == 2 * tree->GetNumLeafNodes() - 1, "node counts of a binary tree");
         if (which != 2) {
             kdtree_test_NN(tree, parts, k);

@@ -13,10 +13,17 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
-def nb(built):
+def nb():
+    # the prebuilt in-tree library, loaded as a consumer would (numpy + ctypes only); a missing libnbk.so raises here
     import nbodylib_b200
     assert nbodylib_b200._lib.load().nbk_device_count() > 0, "GPU tests need a CUDA device"
     return nbodylib_b200
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle.pyoracle import Port
+    return Port()
 
 
 def by_id(order, rows):
@@ -109,7 +116,7 @@ def test_phase_knn_refusals(nb):
         assert e.value.code == -1
 
 
-def test_cxx_shim_phase_program(built, tmp_path):
+def test_cxx_shim_phase_program(nb, tmp_path):
     """examples/shim_phase_demo.cxx: FindNearest / FindNearestPhase on TPHS trees through the C++ shim against a host scan"""
     import os
     import shutil
