@@ -337,9 +337,9 @@ def test_cxx_shim_program(built, tmp_path):
 def test_reference_harness_runs_unchanged_on_the_shim(built):
     """The reference's own test program, src/tests/test_kdtree.cxx, compiled UNCHANGED with the reference's src/NBody and
     src/Math headers against nbodylib_b200/shim/KDTree.h (oracle/Makefile `harness`, built where /root/reference exists; the
-    binary travels): its Physical, Velocity and Phase trees run on the device through oracle/harness_main.cxx, which also
-    checks what the harness only prints (neighbours and ball counts against brute force, one box-sized FOF group, order
-    restored by the destructor)."""
+    binary travels): all five tree types of its TreeTypes() table (Physical, Physical Rdist, Physical Rdist Adaptfac, Velocity,
+    Phase) run on the device through oracle/harness_main.cxx, which also checks what the harness only prints (neighbours and
+    ball counts against brute force, one box-sized FOF group, order restored by the destructor)."""
     import os
     import subprocess
     from oracle.pyoracle import HARNESS
@@ -347,8 +347,8 @@ def test_reference_harness_runs_unchanged_on_the_shim(built):
         pytest.skip("oracle/_ref/test_kdtree_shim did not travel with this checkout")
     out = subprocess.run([HARNESS, "20000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "HARNESS OK" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
-    for name in ("Physical", "Velocity", "Phase"):
-        assert "==== %s tree" % name in out.stdout
+    for name in ("Physical", "Velocity", "Phase", "Physical Rdist", "Physical Rdist Adaptfac"):
+        assert "==== %s tree\n" % name in out.stdout
 
 
 @pytest.mark.parametrize("bucket,k", [(1, 3), (4, 9), (8, 33), (32, 16), (64, 40), (100, 7)])
