@@ -50,6 +50,7 @@ typedef unsigned int UInt_tree_t;
 #endif
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <memory>
 #include <new>
 #include <mutex>
@@ -59,6 +60,10 @@ typedef unsigned int UInt_tree_t;
 #include <vector>
 
 #include "../../include/nbk.h"
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+#include <type_traits>
 
 // the marshalling loops over the caller's particle array run on all host threads when the consumer is built with OpenMP
 #if defined(_OPENMP)
@@ -81,6 +86,83 @@ struct NbkRawBuf {
     T* data() { return p; }
     T& operator[](size_t i) { return p[i]; }
 };
+
+/// Page-aligned scratch for the permutation of the caller's particle array, with transparent huge pages requested where the
+/// platform has them: at 512^3 the scratch is 11.8 GB, i.e. 2.9 M first-touch faults with 4 KiB pages.
+struct NbkPermScratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool mapped = false;
+    explicit NbkPermScratch(size_t n) {
+#if defined(__linux__)
+        const size_t huge = (size_t)2 << 20;
+        bytes = (n + huge - 1) / huge * huge;
+        void* m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m != MAP_FAILED) {
+#ifdef MADV_HUGEPAGE
+            (void)madvise(m, bytes, MADV_HUGEPAGE);
+#endif
+            p = m; mapped = true;
+            return;
+        }
+#endif
+        p = ::operator new(n ? n : 1);
+    }
+    ~NbkPermScratch() {
+#if defined(__linux__)
+        if (mapped) { munmap(p, bytes); return; }
+#endif
+        ::operator delete(p);
+    }
+    NbkPermScratch(const NbkPermScratch&) = delete;
+    NbkPermScratch& operator=(const NbkPermScratch&) = delete;
+};
+
+/// a[i] <- a[src(i)] for a permutation src of 0..n-1, on all host threads (what the reference does with in-place quickselect
+/// swaps while it builds, KDTree.cxx:328-370, and with std::sort by ID in its destructor, :1347).  Two streaming passes
+/// through a scratch copy: a gather (random reads of whole records, software prefetched) and a block copy back.  Trivially
+/// copyable records move as bytes; any other Particle type goes through its move operations.  The reference's own Particle
+/// has a user-written copy constructor, so the compiler cannot call it trivially copyable even in the default build, where
+/// every member is a scalar: a consumer who knows its Particle build can be relocated byte-wise (no member pointing into the
+/// object itself: true for every NBodylib configuration, whose optional members are unique_ptrs) defines
+/// NBK_SHIM_RELOCATE_BYTES to take the byte path -- each record is moved exactly twice and never copied or destroyed.
+template <class P, class F>
+inline void nbk_permute_impl(P* a, int64_t n, F src, void* scratch, std::true_type /* trivially copyable */) {
+    unsigned char* tmp = static_cast<unsigned char*>(scratch);
+    const int64_t ahead = 16;
+    NBK_SHIM_PARALLEL_FOR
+    for (int64_t i = 0; i < n; i++) {
+        if (i + ahead < n) {
+            const char* nx = reinterpret_cast<const char*>(a + src(i + ahead));
+            __builtin_prefetch(nx); __builtin_prefetch(nx + 64);
+        }
+        std::memcpy(tmp + sizeof(P) * (size_t)i, static_cast<const void*>(a + src(i)), sizeof(P));
+    }
+    const int64_t blk = 1 << 16;          // records per block of the copy back
+    NBK_SHIM_PARALLEL_FOR
+    for (int64_t b = 0; b < (n + blk - 1) / blk; b++) {
+        const int64_t i0 = b * blk, i1 = std::min(n, i0 + blk);
+        std::memcpy(static_cast<void*>(a + i0), tmp + sizeof(P) * (size_t)i0, sizeof(P) * (size_t)(i1 - i0));
+    }
+}
+template <class P, class F>
+inline void nbk_permute_impl(P* a, int64_t n, F src, void* scratch, std::false_type) {
+    P* tmp = static_cast<P*>(scratch);
+    NBK_SHIM_PARALLEL_FOR
+    for (int64_t i = 0; i < n; i++) new (tmp + i) P(std::move(a[src(i)]));
+    NBK_SHIM_PARALLEL_FOR
+    for (int64_t i = 0; i < n; i++) { a[i] = std::move(tmp[i]); tmp[i].~P(); }
+}
+template <class P, class F>
+inline void nbk_permute_records(P* a, int64_t n, F src) {
+    if (n <= 0) return;
+    NbkPermScratch scratch(sizeof(P) * (size_t)n);
+#ifdef NBK_SHIM_RELOCATE_BYTES
+    nbk_permute_impl(a, n, src, scratch.p, std::true_type());
+#else
+    nbk_permute_impl(a, n, src, scratch.p, typename std::is_trivially_copyable<P>::type());
+#endif
+}
 
 /// Host mirror of one tree node (reference KDNode.h:45-334 Node, :343-484 SplitNode, :492-610 LeafNode): what callers of
 /// KDTree::GetRoot() / FindLeafNode() read.  IDs number the nodes depth first, left before right, like the reference's
@@ -659,15 +741,7 @@ private:
     /// passes are parallel and the scratch array is raw storage: no element is default-constructed or copied
     /// (KDTree.cxx:328-370 does it with in-place quickselect swaps; ~KDTree with std::sort, :1347)
     template <class F>
-    void permute(F src) {
-        if (numparts <= 0) return;
-        Particle* tmp = static_cast<Particle*>(::operator new(sizeof(Particle) * (size_t)numparts));
-        NBK_SHIM_PARALLEL_FOR
-        for (Int_t i = 0; i < numparts; i++) new (tmp + i) Particle(std::move(bucket[src(i)]));
-        NBK_SHIM_PARALLEL_FOR
-        for (Int_t i = 0; i < numparts; i++) { bucket[i] = std::move(tmp[i]); tmp[i].~Particle(); }
-        ::operator delete(tmp);
-    }
+    void permute(F src) { nbk_permute_records(bucket, (int64_t)numparts, [&](int64_t i) { return (int64_t)src((Int_t)i); }); }
     void require_pos_tree(const char* who) {
         if (info.treetype != TPHYS && info.treetype != TPHS) throw std::runtime_error(std::string("nbk shim: ") + who + " has a device implementation on position trees only");
     }

@@ -545,6 +545,23 @@ def test_header_is_plain_c_and_shim_links(built, tmp_path):
         assert r.returncode == 1 and "nbk_comm_init_rank" in r.stderr
 
 
+def test_shim_permutation_on_cpu(built, tmp_path):
+    """the shim permutes the caller's 88-byte particles into tree order and back on the host (the reference does it with in-place
+    swaps, KDTree.cxx:328-370,1347): byte path and move path of nbk_permute_records, ragged sizes"""
+    import shutil
+    import subprocess
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    lib = os.path.join(ROOT, "nbodylib_b200")
+    exe = str(tmp_path / "permute_check")
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-fopenmp", "-Wall", "-Werror", "-I" + os.path.join(lib, "shim"),
+                           os.path.join(ROOT, "tests", "cxx", "permute_check.cxx"), "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", exe])
+    for n in ("1", "7", "65537", "1000003"):
+        out = subprocess.run([exe, n], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and " 0 errors" in out.stdout, out.stdout + out.stderr
+
+
 def test_restatements_vs_live_reference(port):
     """The numpy restatements (oracle/restate_np.py) against the reference itself on a second, seeded input (not the golden
     one): single-target estimators, criterion search, filtered kNN.  Skipped where oracle/_ref did not travel."""
