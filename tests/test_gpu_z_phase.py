@@ -74,6 +74,34 @@ def test_phase_port_parity_seeded(nb, port, n, period, k, flags):
         assert np.array_equal(dx, od) and rows_equal_as_sets(nx, oi)
 
 
+def test_phase_knn_config1_scale_against_reference_library(nb):
+    """BASELINE config 1's geometry (10^6 uniform-random particles, periodic unit box, bucket 16, k = 32) for the phase-space search,
+    against the reference LIBRARY itself (oracle/_ref, a TPHS tree built with Aniso = -1): a 20 000-particle sample of
+    FindNearestPhase(tt) and 2 000 phase-space points, bit-exact"""
+    from oracle.pyoracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref did not travel with this checkout")
+    n, k = 1000000, 32
+    rng = np.random.default_rng(2024)
+    pos = rng.random((n, 3)).astype(np.float32).astype(np.float64)
+    vel = (rng.normal(size=(n, 3)) * 0.02).astype(np.float32).astype(np.float64)
+    qs = np.sort(rng.choice(n, 20000, replace=False)).astype(np.int32)
+    xq = rng.random((2000, 3))
+    vq = rng.normal(size=(2000, 3)) * 0.02
+    period = np.ones(3)
+    R = Ref(pos, vel, None, treetype=Ref.TPHS, period=period, aniso=-1)
+    ri, rd = R.knn_phase_particles(qs, k, which=0)
+    rx, rxd = R.knn_phase_points(xq, vq, k)
+    R.close()
+    with nb.KDTree(pos, vel, None, TreeType=nb.TPHS, Period=period, Aniso=-1) as t:
+        assert t.info.store_bytes == 4
+        order = t.order()
+        nn, d2 = t.FindNearestPhase(k, ids=True)
+        assert np.array_equal(by_id(order, d2)[qs], rd) and rows_equal_as_sets(by_id(order, nn)[qs], ri)
+        nx, dx = t.FindNearestPhase(k, x=xq, v=vq, ids=True)
+        assert np.array_equal(dx, rxd) and rows_equal_as_sets(nx, rx)
+
+
 def test_phase_knn_degenerate_inputs(nb, port):
     """coincident phase-space points are never neighbours of one another in the particle form (KDLeafNode.cxx:43-57: dist2 > 0)
     but are found by the coordinate form; fewer candidates than k pads with (-1, 1e32) like every search (KDFindNearest.cxx:16-19)"""
