@@ -72,6 +72,38 @@ int main() {
         if (!threw) bad++;
         tree.FindNearestPhase(0, nn, d2, K);                        // FindNearestPhase itself never looks at Aniso (KDFindNearest.cxx:347-361)
     }
+    // velocity-space neighbours on a TVEL tree: FindNearestVel(tt) = FindNearest(tt) = a brute-force scan of the velocities
+    {
+        KDTree tree(ph.data(), M, 16, KDTree::TVEL);
+        long wrong = 0;
+        for (Int_t tt = 5; tt < M; tt += M / 9) {
+            Int_t nn[K], nn2[K], nnv[K];
+            Double_t d2[K], d22[K], d2v[K];
+            tree.FindNearestVel(tt, nn, d2, K);
+            tree.FindNearest(tt, nn2, d22, K);
+            std::vector<std::pair<double, Int_t>> all;
+            for (Int_t i = 0; i < M; i++) {
+                double sum = 0;
+                for (int k = 3; k < 6; k++) { const double d = ph[tt].GetPhase(k) - ph[i].GetPhase(k); sum += d * d; }
+                if (i != tt && sum > 0) all.push_back(std::make_pair(sum, i));
+            }
+            std::partial_sort(all.begin(), all.begin() + K, all.end());
+            for (int j = 0; j < K; j++) wrong += nn[j] != all[j].second || d2[j] != all[j].first || nn2[j] != nn[j] || d22[j] != d2[j];
+            Double_t v[3] = {ph[tt].GetVelocity(0), ph[tt].GetVelocity(1), ph[tt].GetVelocity(2)};
+            tree.FindNearestVel(v, nnv, d2v, K);                     // coordinate form: the particle itself first
+            wrong += nnv[0] != tt || d2v[0] != 0 || nnv[1] != nn[0];
+        }
+        printf("velocity-space FindNearestVel on a TVEL tree: %ld mismatches against brute force\n", wrong);
+        if (wrong) bad++;
+    }
+    {
+        // on a position tree the reference would prune velocity queries with position cut planes: refused
+        bool threw = false;
+        KDTree ptree(ph.data(), M, 16, KDTree::TPHYS);
+        Int_t nn[K]; Double_t d2[K];
+        try { ptree.FindNearestVel(0, nn, d2, K); } catch (const std::runtime_error&) { threw = true; }
+        if (!threw) bad++;
+    }
     printf(bad ? "FAILED (%d)\n" : "shim phase demo ok\n", bad);
     return bad ? 1 : 0;
 }

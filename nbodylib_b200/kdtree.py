@@ -211,6 +211,15 @@ class KDTree:
         L.check(self._lib.nbk_knn_points(self._h, int(Nsearch), m, _ptr(x), _ptr(nn), _ptr(d2), flags))
         return nn, d2
 
+    def FindNearestVel(self, Nsearch=64, q0=0, q1=None, v=None, ids=False):
+        """Range / batched form of KDTree::FindNearestVel(Int_t tt | Double_t *v, ...) (KDFindNearest.cxx:335-346,530-540): the
+        Nsearch nearest in velocity space on a TVEL tree (never reflected: KDSplitNode.cxx:1082-1085)."""
+        if self.info.treetype != TVEL:
+            raise L.NbkError(-3, "FindNearestVel needs a TVEL tree (the reference prunes with the tree's own cut planes)")
+        if v is not None:
+            return self.FindNearestPosPoints(v, Nsearch, ids=ids)
+        return self.FindNearestPos(Nsearch, q0=q0, q1=q1, ids=ids)
+
     def FindNearestPhase(self, Nsearch=64, q0=0, q1=None, x=None, v=None, ids=False):
         """Range / batched form of KDTree::FindNearestPhase(Int_t tt, ...) and FindNearestPhase(Double_t *x, Double_t *v, ...)
         (KDFindNearest.cxx:347-361,543-555): the Nsearch nearest in the plain 6D distance PhaseDistSqd (DistFunc.h:41-49).  Also

@@ -7,6 +7,7 @@
  *    GetNumNodes / GetNumLeafNodes / GetBucketSize / GetTreeType / GetKernType / GetKernNorm / GetPeriod
  *    FindNearest / FindNearestPos (Int_t tt | Double_t* x | Coordinate | whole system)
  *    FindNearestPhase (Int_t tt | Double_t* x, v | Coordinate x, v | whole system); FindNearest on a TPHS tree with Aniso = -1
+ *    FindNearestVel (Int_t tt | Double_t* v | Coordinate v | whole system) on TVEL trees
  *    SearchBallPosTagged (Int_t tt | Double_t* x | Coordinate; array and vector forms), dense SearchBall / SearchBallPos
  *    SearchCriterionTagged (Int_t tt | Particle&; array and vector forms), dense SearchCriterion (FOF3d / FOF6d)
  *    CalcDensity, CalcVelDensity, CalcSmoothingScale (new: north star), CalcDensityParticle, CalcVelDensityParticle,
@@ -363,6 +364,13 @@ public:
         if (phase_tree("FindNearest")) knn_cached(tt, nn, dist2, Nsearch, 0, -3);
         else knn_cached(tt, nn, dist2, Nsearch, NBK_KNN_TREE_FORM);
     }
+    // ---- velocity-space nearest neighbours (KDFindNearest.cxx:335-346, 451-452, 530-540, 559-561) ---------------
+    /// The reference's FindNearestVel walks whatever tree it is called on with velocity coordinates against the tree's cut
+    /// planes, so it is only meaningful on a TVEL tree: k slots, target form, never reflected -- what nbk_knn_* do on TVEL trees.
+    void FindNearestVel(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { require_vel_tree("FindNearestVel"); knn_cached(tt, nn, dist2, Nsearch, 0); }
+    void FindNearestVel(Double_t* v, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { require_vel_tree("FindNearestVel"); FindNearestPos(v, nn, dist2, Nsearch); }
+    void FindNearestVel(Coordinate v, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { FindNearestVel(v.GetCoord(), nn, dist2, Nsearch); }
+    void FindNearestVel(Int_t** nn, Double_t** dist2, Int_t Nsearch = 64) { require_vel_tree("FindNearestVel"); knn_all(nn, dist2, Nsearch, 0); }
     // ---- phase-space nearest neighbours (KDFindNearest.cxx:347-361, 543-555; PhaseDistSqd, DistFunc.h:41-49) ------
     void FindNearestPhase(Int_t tt, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) { knn_cached(tt, nn, dist2, Nsearch, 0, -3); }
     void FindNearestPhase(Double_t* x, Double_t* v, Int_t* nn, Double_t* dist2, Int_t Nsearch = 64) {
@@ -742,6 +750,9 @@ private:
     /// (KDTree.cxx:328-370 does it with in-place quickselect swaps; ~KDTree with std::sort, :1347)
     template <class F>
     void permute(F src) { nbk_permute_records(bucket, (int64_t)numparts, [&](int64_t i) { return (int64_t)src((Int_t)i); }); }
+    void require_vel_tree(const char* who) {
+        if (info.treetype != TVEL) throw std::runtime_error(std::string("nbk shim: ") + who + " needs a TVEL tree (on any other tree the reference prunes velocity queries with position cut planes)");
+    }
     void require_pos_tree(const char* who) {
         if (info.treetype != TPHYS && info.treetype != TPHS) throw std::runtime_error(std::string("nbk shim: ") + who + " has a device implementation on position trees only");
     }

@@ -230,6 +230,7 @@ class Ref:
             L.ref_calc_smooth_higher.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
             L.ref_knn_phase_particles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, _ip, _ip, _dp]
             L.ref_knn_phase_points.argtypes = [C.c_void_p, C.c_int, C.c_long, _dp, _dp, _ip, _dp]
+            L.ref_knn_vel_points.argtypes = [C.c_void_p, C.c_int, C.c_long, _dp, _ip, _dp]
             L.ref_max_threads.restype = C.c_int
             L.ref_sizeof_particle.restype = C.c_int
             cls._lib = L
@@ -292,7 +293,7 @@ class Ref:
         return ids, d2
 
     def knn_particle_list(self, qids, k, which=0):
-        """FindNearestPos(tt) / FindNearest(tt) for an explicit list of particle IDs"""
+        """FindNearestPos(tt) (which 0) / FindNearest(tt) (1) / FindNearestVel(tt) (2) for an explicit list of particle IDs"""
         q = np.ascontiguousarray(qids, dtype=np.int32)
         ids = np.zeros((len(q), k), dtype=np.int32)
         d2 = np.zeros((len(q), k))
@@ -317,6 +318,14 @@ class Ref:
         ids = np.zeros((len(q), k), dtype=np.int32)
         d2 = np.zeros((len(q), k))
         self.lib().ref_knn_phase_particles(self.h, which, k, len(q), _i(q), _i(ids), _d(d2))
+        return ids, d2
+
+    def knn_vel_points(self, v, k):
+        """FindNearestVel(Double_t *v, ...)"""
+        v = _f64(v)
+        ids = np.zeros((len(v), k), dtype=np.int32)
+        d2 = np.zeros((len(v), k))
+        self.lib().ref_knn_vel_points(self.h, k, len(v), _d(v), _i(ids), _d(d2))
         return ids, d2
 
     def knn_phase_points(self, x, v, k):

@@ -90,7 +90,7 @@ void ref_order(void* hv, int* ids) {
     for (Int_t i = 0; i < h->n; i++) ids[i] = (int)h->parts[i].GetID();
 }
 
-/* kNN for queries q0..q1 (particle IDs, input order).  which: 0 = FindNearestPos(tt), 1 = FindNearest(tt).
+/* kNN for queries q0..q1 (particle IDs, input order).  which: 0 = FindNearestPos(tt), 1 = FindNearest(tt), 2 = FindNearestVel(tt).
  * out_ids / out_d2 : (q1-q0) x k, neighbour particle IDs.  Returns wall seconds of the query loop. */
 double ref_knn_particles(void* hv, int which, int k, long q0, long q1, int* out_ids, double* out_d2) {
     RefTree* h = (RefTree*)hv;
@@ -105,6 +105,7 @@ double ref_knn_particles(void* hv, int which, int k, long q0, long q1, int* out_
         for (long q = q0; q < q1; q++) {
             Int_t tt = where[q];
             if (which == 0) h->tree->FindNearestPos(tt, nn.data(), d2.data(), k);
+            else if (which == 2) h->tree->FindNearestVel(tt, nn.data(), d2.data(), k);
             else h->tree->FindNearest(tt, nn.data(), d2.data(), k);
             if (out_ids) {
                 for (int j = 0; j < k; j++) {
@@ -131,6 +132,7 @@ double ref_knn_particle_list(void* hv, int which, int k, long m, const int* qids
         for (long q = 0; q < m; q++) {
             Int_t tt = where[qids[q]];
             if (which == 0) h->tree->FindNearestPos(tt, nn.data(), d2.data(), k);
+            else if (which == 2) h->tree->FindNearestVel(tt, nn.data(), d2.data(), k);
             else h->tree->FindNearest(tt, nn.data(), d2.data(), k);
             for (int j = 0; j < k; j++) {
                 out_ids[q * k + j] = nn[j] >= 0 ? (int)h->parts[nn[j]].GetID() : -1;
@@ -600,6 +602,25 @@ void ref_knn_phase_points(void* hv, int k, long m, const double* x, const double
         for (long q = 0; q < m; q++) {
             Double_t xx[3] = {x[3 * q], x[3 * q + 1], x[3 * q + 2]}, vv[3] = {v[3 * q], v[3 * q + 1], v[3 * q + 2]};
             h->tree->FindNearestPhase(xx, vv, nn.data(), d2.data(), k);
+            for (int j = 0; j < k; j++) {
+                out_ids[q * k + j] = nn[j] >= 0 ? (int)h->parts[nn[j]].GetID() : -1;
+                out_d2[q * k + j] = d2[j];
+            }
+        }
+    }
+}
+
+/* FindNearestVel(Double_t* v, ...) about arbitrary velocities */
+void ref_knn_vel_points(void* hv, int k, long m, const double* v, int* out_ids, double* out_d2) {
+    RefTree* h = (RefTree*)hv;
+#pragma omp parallel
+    {
+        vector<Int_t> nn(k);
+        vector<Double_t> d2(k);
+#pragma omp for schedule(guided)
+        for (long q = 0; q < m; q++) {
+            Double_t vv[3] = {v[3 * q], v[3 * q + 1], v[3 * q + 2]};
+            h->tree->FindNearestVel(vv, nn.data(), d2.data(), k);
             for (int j = 0; j < k; j++) {
                 out_ids[q * k + j] = nn[j] >= 0 ? (int)h->parts[nn[j]].GetID() : -1;
                 out_d2[q * k + j] = d2[j];

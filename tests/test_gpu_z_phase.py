@@ -122,6 +122,27 @@ def test_phase_knn_degenerate_inputs(nb, port):
         assert np.all(nn[:, 4:] == -1) and np.all(d2[:, 4:] == 1e32) and np.all(nn[:, :4] >= 0)
 
 
+def test_findnearestvel_on_velocity_trees(nb, port):
+    """KDTree::FindNearestVel(tt | v) (KDFindNearest.cxx:335-346,530-540): velocity-space neighbours on a TVEL tree, periodic or
+    not (velocity searches are never reflected, KDSplitNode.cxx:1082-1085); refused on trees whose cut planes are positions"""
+    from nbodylib_b200.synth import clustered_small
+    pos, vel, mass = clustered_small(6007, seed=31)
+    vq = np.random.default_rng(9).normal(size=(129, 3)) * vel.std()
+    for period in (None, np.ones(3)):
+        with nb.KDTree(pos, vel, mass, TreeType=nb.TVEL, Period=period) as t:
+            order = t.order()
+            nn, d2 = t.FindNearestVel(10, ids=True)
+            oi, od = port.knn_particles(vel, 10)
+            assert np.array_equal(by_id(order, d2), od) and rows_equal_as_sets(by_id(order, nn), oi)
+            nx, dx = t.FindNearestVel(10, v=vq, ids=True)
+            oi, od = port.knn_points(vel, vq, 10)
+            assert np.array_equal(dx, od) and rows_equal_as_sets(nx, oi)
+    with nb.KDTree(pos, vel, mass) as t:
+        with pytest.raises(nb.NbkError) as e:
+            t.FindNearestVel(10)
+        assert e.value.code == -3
+
+
 def test_phase_knn_refusals(nb):
     """no silent approximations: metric searches (Aniso >= 0, quirk Q4), velocity trees and trees without velocities are refused"""
     rng = np.random.default_rng(1)
@@ -159,4 +180,4 @@ def test_cxx_shim_phase_program(nb, tmp_path):
                            "-L" + lib, "-lnbk", "-Wl,-rpath," + lib, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "shim phase demo ok" in out.stdout, out.stdout + out.stderr
-    assert out.stdout.count(": 0 mismatches against brute force") == 2
+    assert out.stdout.count(": 0 mismatches against brute force") == 3          # two TPHS trees, one TVEL tree

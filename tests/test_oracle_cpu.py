@@ -129,6 +129,33 @@ def test_phase_port_vs_live_reference(port):
             R.close()
 
 
+def test_velocity_tree_searches_of_the_live_reference(port):
+    """what the device path mirrors on TVEL trees: FindNearestVel(tt | v) returns the k nearest in velocity space, never reflected,
+    whether or not the tree has a period; FindNearest(tt) equals it on a non-periodic tree and, on a PERIODIC velocity tree, drops
+    the nearest neighbour (a latent bug that is documented, not reproduced)"""
+    from oracle.pyoracle import Ref, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    from nbodylib_b200.synth import clustered_small
+    pos, vel, mass = clustered_small(6007, seed=31)
+    vq = np.random.default_rng(9).normal(size=(129, 3)) * vel.std()
+    qs = np.arange(0, 6007, 3, dtype=np.int32)
+    oi, od = port.knn_particles(vel, 11)
+    ox, oxd = port.knn_points(vel, vq, 10)
+    for period in (None, np.ones(3)):
+        R = Ref(pos, vel, mass, treetype=Ref.TVEL, period=period)
+        ids, d2 = R.knn_particle_list(qs, 10, which=2)
+        assert np.array_equal(d2, od[qs, :10]) and rows_equal_as_sets(ids, oi[qs, :10])
+        ids, d2 = R.knn_vel_points(vq, 10)
+        assert np.array_equal(d2, oxd) and rows_equal_as_sets(ids, ox)
+        ids, d2 = R.knn_particle_list(qs, 10, which=1)
+        if period is None:
+            assert np.array_equal(d2, od[qs, :10])
+        else:
+            assert np.array_equal(d2, od[qs, 1:11])              # neighbours 2 .. k+1
+        R.close()
+
+
 def test_port_vs_live_reference(port):
     """Where the reference compiles (oracle/_ref), re-check the port on a fresh seed incl. tree shape facts."""
     from oracle.pyoracle import Ref, have_ref
